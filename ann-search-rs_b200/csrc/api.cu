@@ -1,0 +1,800 @@
+// api.cu -- the C ABI (include/annb200.h) and the host-side orchestration of the kernels.
+#include <algorithm>
+#include <cctype>
+#include <cmath>
+#include <cstring>
+
+#include "index.hpp"
+#include "prep_kernels.cuh"
+#include "simt_kernels.cuh"
+#include "flat_tc.hpp"
+
+namespace annb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+static int fail(int code, const std::string& msg) {
+    set_last_error(msg);
+    return code;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); return; }
+        ok = (cudaSetDevice(dev) == cudaSuccess);
+        if (!ok) (void)cudaGetLastError();
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+#define ANNB_DEVICE(dev)                                                                        \
+    ::annb::DeviceGuard _guard(dev);                                                            \
+    if (!_guard.ok) return ::annb::fail(ANNB_ERR_CUDA, "no usable CUDA device " + std::to_string(dev) + \
+                                        " (libannb200 has no CPU fallback)")
+
+// Dominant-kernel timing: bracket a launch with events on its own stream (option "time_kernels").
+struct KernelTimer {
+    annb_index* ix;
+    cudaStream_t s;
+    cudaEvent_t a = nullptr, b = nullptr;
+    KernelTimer(annb_index* ix_, cudaStream_t s_) : ix(ix_), s(s_) {
+        if (!ix->opt_time_kernels) return;
+        if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; (void)cudaGetLastError(); return; }
+        cudaEventRecord(a, s);
+    }
+    ~KernelTimer() {
+        if (!a) return;
+        cudaEventRecord(b, s);
+        ix->timed.emplace_back(a, b);
+    }
+};
+static void collect_timers(const annb_index* ix) {
+    for (auto& pr : ix->timed) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            ix->timed_ms_total += ms;
+            ix->timed_launches++;
+        }
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    (void)cudaGetLastError();
+    ix->timed.clear();
+}
+
+static inline uint32_t grid_for(uint64_t work, uint32_t block, uint32_t cap = 148 * 32) {
+    uint64_t g = (work + block - 1) / block;
+    return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(g, cap)));
+}
+
+template <typename T>
+static int dmalloc(T** p, size_t count, annb_index* ix) {
+    size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? ANNB_ERR_OUT_OF_MEMORY : ANNB_ERR_CUDA,
+                    std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+    }
+    if (ix) ix->device_bytes += bytes;
+    return ANNB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// kernel dispatch
+// ---------------------------------------------------------------------------
+template <int RT, int QT, int MET, int EPI>
+static int launch_tile(const TileParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+    auto kern = tile_kernel<RT, QT, MET, EPI>;
+    if (smem > 227 * 1024) return fail(ANNB_ERR_UNSUPPORTED, "tile_kernel: dim/k too large for shared memory (DimTooHighForSharedMemory)");
+    ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, TILE_THREADS, smem, s>>>(p);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    return ANNB_OK;
+}
+
+// rt: index dtype; qt: query element type
+static int launch_select_tile(int rt, int qt, int metric, const TileParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+    const bool cos = metric == ANNB_COSINE;
+    if (rt == ANNB_F32 && qt == QT_F32) return cos ? launch_tile<0, QT_F32, MET_COS, EPI_SELECT>(p, grid, smem, s) : launch_tile<0, QT_F32, MET_L2, EPI_SELECT>(p, grid, smem, s);
+    if (rt == ANNB_BF16 && qt == QT_F32) return cos ? launch_tile<1, QT_F32, MET_COS, EPI_SELECT>(p, grid, smem, s) : launch_tile<1, QT_F32, MET_L2, EPI_SELECT>(p, grid, smem, s);
+    if (rt == ANNB_BF16 && qt == QT_BF16) return cos ? launch_tile<1, QT_BF16, MET_COS, EPI_SELECT>(p, grid, smem, s) : launch_tile<1, QT_BF16, MET_L2, EPI_SELECT>(p, grid, smem, s);
+    if (rt == ANNB_SQ8 && qt == QT_I8) return cos ? launch_tile<2, QT_I8, MET_COS, EPI_SELECT>(p, grid, smem, s) : launch_tile<2, QT_I8, MET_L2, EPI_SELECT>(p, grid, smem, s);
+    return fail(ANNB_ERR_INVALID_ARGUMENT, "unsupported (row, query) type pair");
+}
+
+template <int RT, int QT, int MET>
+static int launch_scan_t(const ScanParams& p, uint32_t grid, size_t smem, cudaStream_t s) {
+    auto kern = ivf_scan_kernel<RT, QT, MET>;
+    if (smem > 227 * 1024) return fail(ANNB_ERR_UNSUPPORTED, "ivf_scan_kernel: dim/k too large for shared memory (DimTooHighForSharedMemory)");
+    ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, SCAN_WARPS * 32, smem, s>>>(p);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    return ANNB_OK;
+}
+static int launch_scan(int rt, int qt, int metric, const ScanParams& p, uint32_t grid, size_t smem, cudaStream_t s) {
+    const bool cos = metric == ANNB_COSINE;
+    if (rt == ANNB_F32 && qt == QT_F32) return cos ? launch_scan_t<0, QT_F32, MET_COS>(p, grid, smem, s) : launch_scan_t<0, QT_F32, MET_L2>(p, grid, smem, s);
+    if (rt == ANNB_BF16 && qt == QT_F32) return cos ? launch_scan_t<1, QT_F32, MET_COS>(p, grid, smem, s) : launch_scan_t<1, QT_F32, MET_L2>(p, grid, smem, s);
+    if (rt == ANNB_BF16 && qt == QT_BF16) return cos ? launch_scan_t<1, QT_BF16, MET_COS>(p, grid, smem, s) : launch_scan_t<1, QT_BF16, MET_L2>(p, grid, smem, s);
+    if (rt == ANNB_SQ8 && qt == QT_I8) return cos ? launch_scan_t<2, QT_I8, MET_COS>(p, grid, smem, s) : launch_scan_t<2, QT_I8, MET_L2>(p, grid, smem, s);
+    return fail(ANNB_ERR_INVALID_ARGUMENT, "unsupported (row, query) type pair");
+}
+
+static int run_finalize(annb_index* ix, const uint64_t* keys, uint32_t parts, uint32_t kc, uint32_t k_out, uint64_t nq,
+                        const uint64_t* id_map, uint64_t id_base, const uint64_t* row_map, uint64_t* d_ids, float* d_dist,
+                        uint32_t* d_cnt, cudaStream_t s) {
+    FinalizeParams f{};
+    f.part_keys = keys; f.parts = parts; f.kc = kc; f.k = k_out;
+    f.nsort = next_pow2(std::max(parts * kc, k_out));
+    f.nq = nq; f.id_map = id_map; f.id_base = id_base; f.row_map = row_map;
+    f.out_ids = d_ids; f.out_dist = d_dist; f.out_counts = d_cnt;
+    size_t smem = static_cast<size_t>(f.nsort) * 8;
+    if (smem > 200 * 1024) return fail(ANNB_ERR_UNSUPPORTED, "finalize: parts * k too large");
+    ANNB_CUDA_CHECK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    finalize_kernel<<<static_cast<uint32_t>(nq), 128, smem, s>>>(f);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    ix->stat_launches++;
+    return ANNB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// query preparation
+// ---------------------------------------------------------------------------
+struct PreparedQueries {
+    const uint8_t* scan = nullptr;  // rows the distance kernels consume
+    uint32_t scan_bytes = 0;
+    int qt = QT_F32;
+    int bf16_self = 0;
+    const float* route = nullptr;  // f32 rows used for centroid ranking (IVF)
+    uint32_t route_ld = 0;         // floats
+};
+
+// External f32 queries [nq][dim] (device) -> padded / encoded forms.
+static int prepare_external(annb_index* ix, const float* d_q, uint64_t nq, PreparedQueries* out, cudaStream_t s) {
+    const uint32_t dim = ix->dim;
+    const uint32_t ld = round_up(dim * 4u, 16u) / 4u;
+    const float* f32q = d_q;
+    if (ld != dim || ix->dtype == ANNB_SQ8) {  // SQ8 may normalise in place -> always work on a copy
+        ANNB_TRY(ix->s_qpad.ensure(nq * ld * 4ull));
+        pad_rows_kernel<<<grid_for(nq * ld * 4ull, 256), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(d_q), dim * 4, ix->s_qpad.as<uint8_t>(), ld * 4, nq);
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        ix->stat_launches++;
+        f32q = ix->s_qpad.as<float>();
+    }
+    out->route = f32q;
+    out->route_ld = ld;
+    out->bf16_self = 0;
+    if (ix->dtype == ANNB_SQ8) {
+        // ExhaustiveSq8Index::query (exhaustive_sq8.rs:181-192): normalise (cosine), encode with the codebook
+        float* w = ix->s_qpad.as<float>();
+        if (ix->metric == ANNB_COSINE) {
+            normalise_rows_f32_kernel<<<grid_for(nq, 128, 1u << 30), 128, 0, s>>>(w, ld, dim, nq);
+            ANNB_CUDA_CHECK(cudaGetLastError());
+            ix->stat_launches++;
+        }
+        const uint32_t cb = round_up(dim, 16u);
+        ANNB_TRY(ix->s_qcodes.ensure(nq * static_cast<uint64_t>(cb)));
+        sq8_encode_kernel<<<grid_for(nq * cb, 256), 256, 0, s>>>(w, ld, dim, ix->d_scales, ix->s_qcodes.as<int8_t>(), cb, nq);
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        ix->stat_launches++;
+        out->scan = ix->s_qcodes.as<uint8_t>();
+        out->scan_bytes = cb;
+        out->qt = QT_I8;
+    } else {
+        out->scan = reinterpret_cast<const uint8_t*>(f32q);
+        out->scan_bytes = ld * 4;
+        out->qt = QT_F32;
+    }
+    return ANNB_OK;
+}
+
+// Self queries: stored rows [pos_begin, pos_end) act as queries in their own dtype.
+static int prepare_self(annb_index* ix, uint64_t pos_begin, uint64_t nq, bool need_route, PreparedQueries* out, cudaStream_t s) {
+    out->scan = ix->d_rows + pos_begin * ix->row_bytes;
+    out->scan_bytes = ix->row_bytes;
+    out->qt = ix->dtype == ANNB_F32 ? QT_F32 : (ix->dtype == ANNB_BF16 ? QT_BF16 : QT_I8);
+    out->bf16_self = ix->dtype == ANNB_BF16;
+    out->route = nullptr;
+    if (!need_route) return ANNB_OK;
+    const uint32_t ld = round_up(ix->dim * 4u, 16u) / 4u;
+    out->route_ld = ld;
+    if (ix->dtype == ANNB_F32) {
+        out->route = reinterpret_cast<const float*>(out->scan);
+        out->route_ld = ix->row_bytes / 4;
+        return ANNB_OK;
+    }
+    ANNB_TRY(ix->s_route.ensure(nq * ld * 4ull));
+    float* w = ix->s_route.as<float>();
+    if (ix->dtype == ANNB_BF16)  // query_bf16: decode for routing (ivf_bf16.rs:456)
+        decode_bf16_kernel<<<grid_for(nq * ld, 256), 256, 0, s>>>(reinterpret_cast<const uint16_t*>(out->scan), ix->row_bytes / 2, w, ld, ix->dim, nq);
+    else  // query_quantised: decode codes for routing (ivf_sq8.rs:409)
+        sq8_decode_kernel<<<grid_for(nq * ld, 256), 256, 0, s>>>(reinterpret_cast<const int8_t*>(out->scan), ix->row_bytes, ix->d_scales, w, ld, ix->dim, nq);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    ix->stat_launches++;
+    out->route = w;
+    return ANNB_OK;
+}
+
+// ---------------------------------------------------------------------------
+// flat search core (device pointers, asynchronous on s)
+// ---------------------------------------------------------------------------
+static int flat_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint64_t* d_ids, float* d_dist,
+                     uint32_t* d_cnt, cudaStream_t s) {
+    const uint32_t kk = static_cast<uint32_t>(std::min<uint64_t>(k, ix->n));
+    if (kk == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "k must be >= 1");
+    bool use_tc = false;
+    if (ix->opt_path != ANNB_PATH_SIMT) {
+        use_tc = tc_flat_supported(ix, pq.qt, kk);
+        if (!use_tc && ix->opt_path == ANNB_PATH_TENSOR)
+            return fail(ANNB_ERR_UNSUPPORTED, "tensor path requested but this (dtype, dim, k) is not covered by it yet");
+    }
+    if (use_tc) {
+        ix->stat_last_path = ANNB_PATH_TENSOR;
+        return tc_flat_search(ix, pq.scan, pq.scan_bytes, pq.qt, pq.bf16_self, nq, kk, k, d_ids, d_dist, d_cnt, s);
+    }
+    ix->stat_last_path = ANNB_PATH_SIMT;
+    if (kk > 1024) return fail(ANNB_ERR_UNSUPPORTED, "k > 1024 is not supported");
+    const uint32_t nsort = WarpSelect::sort_size(kk);
+    const uint64_t q_tiles = ceil_div<uint64_t>(nq, CTA_QUERIES);
+    uint32_t splits = ix->opt_db_splits > 0 ? static_cast<uint32_t>(ix->opt_db_splits)
+                                            : static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(64, ceil_div<uint64_t>(2 * 148, q_tiles))));
+    splits = static_cast<uint32_t>(std::min<uint64_t>(splits, std::max<uint64_t>(1, ix->n / 256)));
+    uint64_t rps = round_up<uint64_t>(ceil_div<uint64_t>(ix->n, splits), TILE_ROWS);
+    splits = static_cast<uint32_t>(ceil_div<uint64_t>(ix->n, rps));
+    ANNB_TRY(ix->s_keys.ensure(nq * splits * static_cast<uint64_t>(kk) * 8));
+    TileParams p{};
+    p.rows = ix->d_rows; p.n_rows = ix->n; p.row_bytes = ix->row_bytes;
+    p.row_norms = ix->d_norms; p.row_norms_i = ix->d_norms_i;
+    p.queries = pq.scan; p.q_bytes = pq.scan_bytes; p.nq = nq; p.dim = ix->dim; p.bf16_self = pq.bf16_self;
+    p.k = kk; p.nsort = nsort; p.n_splits = splits; p.rows_per_split = rps; p.part_keys = ix->s_keys.as<uint64_t>();
+    size_t smem = tile_kernel_smem(ix->row_bytes, pq.scan_bytes, nsort, true);
+    {
+        KernelTimer kt(ix, s);
+        ANNB_TRY(launch_select_tile(ix->dtype, pq.qt, ix->metric, p, dim3(static_cast<uint32_t>(q_tiles), splits), smem, s));
+    }
+    ix->stat_launches++;
+    return run_finalize(ix, ix->s_keys.as<uint64_t>(), splits, kk, k, nq, nullptr, ix->id_base, nullptr, d_ids, d_dist, d_cnt, s);
+}
+
+// ---------------------------------------------------------------------------
+// IVF search core
+// ---------------------------------------------------------------------------
+static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint32_t nprobe, const uint64_t* row_map,
+                    uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s) {
+    const uint32_t kk = static_cast<uint32_t>(std::min<uint64_t>(k, ix->n_total));
+    if (kk == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "k must be >= 1");
+    if (kk > 1024) return fail(ANNB_ERR_UNSUPPORTED, "k > 1024 is not supported");
+    // nprobe default and clamp: src/cpu/ivf.rs:345-347
+    uint32_t np = nprobe ? nprobe : std::max<uint32_t>(1, static_cast<uint32_t>(std::sqrt(static_cast<double>(ix->nlist))));
+    np = std::min(np, ix->nlist);
+    const uint32_t nl2 = next_pow2(ix->nlist);
+    if (static_cast<size_t>(nl2) * 8 > 200 * 1024) return fail(ANNB_ERR_UNSUPPORTED, "nlist > 16384 is not supported yet");
+
+    // 1. query -> all centroids (dense), reference arithmetic of get_centroids_dist / _prenorm
+    ANNB_TRY(ix->s_cdist.ensure(nq * static_cast<uint64_t>(ix->nlist) * 4));
+    {
+        TileParams p{};
+        p.rows = reinterpret_cast<const uint8_t*>(ix->d_centroids); p.n_rows = ix->nlist; p.row_bytes = ix->cent_ld * 4;
+        p.row_norms = ix->d_centroid_norms;
+        p.queries = reinterpret_cast<const uint8_t*>(pq.route); p.q_bytes = pq.route_ld * 4; p.nq = nq; p.dim = ix->dim;
+        p.dense_out = ix->s_cdist.as<float>();
+        size_t smem = tile_kernel_smem(p.row_bytes, p.q_bytes, 0, false);
+        dim3 grid(static_cast<uint32_t>(ceil_div<uint64_t>(nq, CTA_QUERIES)), 1);
+        if (ix->metric == ANNB_L2) ANNB_TRY((launch_tile<0, QT_F32, MET_L2, EPI_DENSE>(p, grid, smem, s)));
+        else if (ix->dtype == ANNB_SQ8) ANNB_TRY((launch_tile<0, QT_F32, MET_COS_PRENORM, EPI_DENSE>(p, grid, smem, s)));
+        else ANNB_TRY((launch_tile<0, QT_F32, MET_COS, EPI_DENSE>(p, grid, smem, s)));
+        ix->stat_launches++;
+    }
+    // 2. rank + probe expansion
+    ANNB_TRY(ix->s_flags.ensure(64));
+    ANNB_TRY(ix->s_nprobes.ensure(nq * 4));
+    uint32_t pitch = ix->nlist <= 1024 ? ix->nlist : std::min(ix->nlist, np + 64);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        ANNB_TRY(ix->s_probes.ensure(nq * static_cast<uint64_t>(pitch) * 4));
+        ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 64, s));
+        ProbeParams pp{};
+        pp.cdist = ix->s_cdist.as<float>(); pp.nlist = ix->nlist; pp.nlist_pow2 = nl2; pp.offsets = ix->d_offsets;
+        pp.nprobe = np; pp.k = kk; pp.probes = ix->s_probes.as<uint32_t>(); pp.probe_pitch = pitch;
+        pp.n_probes = ix->s_nprobes.as<uint32_t>();
+        pp.overflow = ix->s_flags.as<uint32_t>();
+        pp.stat_scanned = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 8);
+        pp.stat_probed = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 16);
+        size_t smem = static_cast<size_t>(nl2) * 8;
+        ANNB_CUDA_CHECK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        probe_kernel<<<static_cast<uint32_t>(nq), 256, smem, s>>>(pp);
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        ix->stat_launches++;
+        if (pitch == ix->nlist) break;
+        // rare: a query needed more than nprobe + 64 cells to reach k vectors -> redo with the full pitch
+        uint32_t h_flag[6];
+        ANNB_CUDA_CHECK(cudaMemcpyAsync(h_flag, ix->s_flags.p, sizeof(h_flag), cudaMemcpyDeviceToHost, s));
+        ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (!h_flag[0]) break;
+        pitch = ix->nlist;
+    }
+    // 3. list scan
+    uint32_t parts = ix->opt_scan_parts > 0 ? static_cast<uint32_t>(ix->opt_scan_parts)
+                                            : static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(16, ceil_div<uint64_t>(148ull * 32, std::max<uint64_t>(nq, 1)))));
+    parts = std::max(1u, std::min(parts, np));
+    const uint32_t nsort = WarpSelect::sort_size(kk);
+    ANNB_TRY(ix->s_keys.ensure(nq * parts * static_cast<uint64_t>(kk) * 8));
+    {
+        ScanParams sp{};
+        sp.rows = ix->d_rows; sp.row_bytes = ix->row_bytes; sp.row_norms = ix->d_norms; sp.row_norms_i = ix->d_norms_i;
+        sp.queries = pq.scan; sp.q_bytes = pq.scan_bytes; sp.nq = nq; sp.dim = ix->dim; sp.bf16_self = pq.bf16_self;
+        sp.probes = ix->s_probes.as<uint32_t>(); sp.probe_pitch = pitch; sp.n_probes = ix->s_nprobes.as<uint32_t>();
+        sp.offsets = ix->d_offsets; sp.list_begin = ix->list_begin; sp.list_end = ix->list_end; sp.shard_row0 = ix->shard_row0;
+        sp.parts = parts; sp.k = kk; sp.nsort = nsort; sp.part_keys = ix->s_keys.as<uint64_t>();
+        size_t smem = scan_kernel_smem(ix->row_bytes, pq.scan_bytes, nsort);
+        uint32_t grid = static_cast<uint32_t>(ceil_div<uint64_t>(nq * parts, SCAN_WARPS));
+        {
+            KernelTimer kt(ix, s);
+            ANNB_TRY(launch_scan(ix->dtype, pq.qt, ix->metric, sp, grid, smem, s));
+        }
+        ix->stat_launches++;
+    }
+    // 4. merge parts, map list-order positions to original ids (src/cpu/ivf.rs:383-389)
+    return run_finalize(ix, ix->s_keys.as<uint64_t>(), parts, kk, k, nq, ix->d_original_ids, 0, row_map, d_ids, d_dist, d_cnt, s);
+}
+
+static int read_ivf_stats(annb_index* ix, cudaStream_t s) {
+    unsigned long long h[3] = {0, 0, 0};
+    ANNB_CUDA_CHECK(cudaMemcpyAsync(h, ix->s_flags.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+    ix->stat_scanned += static_cast<int64_t>(h[1]);
+    ix->stat_probed += static_cast<int64_t>(h[2]);
+    return ANNB_OK;
+}
+
+constexpr uint64_t QUERY_BATCH = 16384;
+
+// Host-buffer driver shared by the four host entry points.
+//   mode 0: external queries (host or device f32 [nq][dim]);  mode 1: self queries [pos_begin, pos_begin + nq)
+static int search_host(annb_index* ix, bool ivf, int mode, const float* queries, uint64_t pos_begin, uint64_t nq, uint32_t k,
+                       uint32_t nprobe, int scatter, uint64_t* out_ids, float* out_dist, uint32_t* out_counts) {
+    if (!ix) return fail(ANNB_ERR_INVALID_ARGUMENT, "null index");
+    if (ivf != ix->is_ivf) return fail(ANNB_ERR_INVALID_ARGUMENT, ivf ? "not an IVF index" : "not a flat index");
+    if (!out_ids || (mode == 0 && !queries && nq)) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer");
+    if (k == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "k must be >= 1");
+    ANNB_DEVICE(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t s = ix->stream;
+    ix->stat_scanned = 0;
+    ix->stat_probed = 0;
+    for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
+        const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
+        PreparedQueries pq;
+        if (mode == 0) {
+            ANNB_TRY(ix->s_tmp.ensure(nb * ix->dim * 4ull));
+            ANNB_CUDA_CHECK(cudaMemcpyAsync(ix->s_tmp.p, queries + b0 * ix->dim, nb * ix->dim * 4ull, cudaMemcpyDefault, s));
+            ANNB_TRY(prepare_external(ix, ix->s_tmp.as<float>(), nb, &pq, s));
+        } else {
+            ANNB_TRY(prepare_self(ix, pos_begin + b0, nb, ivf, &pq, s));
+        }
+        ANNB_TRY(ix->s_ids.ensure(nb * k * 8ull));
+        ANNB_TRY(ix->s_dist.ensure(nb * k * 4ull));
+        ANNB_TRY(ix->s_cnt.ensure(nb * 4ull));
+        const uint64_t* row_map = nullptr;
+        if (ivf) {
+            ANNB_TRY(ivf_core(ix, pq, nb, k, nprobe, nullptr, ix->s_ids.as<uint64_t>(), ix->s_dist.as<float>(), ix->s_cnt.as<uint32_t>(), s));
+            (void)row_map;
+        } else {
+            ANNB_TRY(flat_core(ix, pq, nb, k, ix->s_ids.as<uint64_t>(), ix->s_dist.as<float>(), ix->s_cnt.as<uint32_t>(), s));
+        }
+        if (ivf && mode == 1 && scatter) {
+            // generate_knn: row of internal position p belongs to original id original_ids[p] (ivf.rs:476-486)
+            std::vector<uint64_t> oid(nb);
+            std::vector<uint64_t> ids(nb * k);
+            std::vector<float> dist(out_dist ? nb * k : 0);
+            std::vector<uint32_t> cnt(out_counts ? nb : 0);
+            ANNB_CUDA_CHECK(cudaMemcpyAsync(oid.data(), ix->d_original_ids + pos_begin + b0, nb * 8, cudaMemcpyDeviceToHost, s));
+            ANNB_CUDA_CHECK(cudaMemcpyAsync(ids.data(), ix->s_ids.p, nb * k * 8ull, cudaMemcpyDeviceToHost, s));
+            if (out_dist) ANNB_CUDA_CHECK(cudaMemcpyAsync(dist.data(), ix->s_dist.p, nb * k * 4ull, cudaMemcpyDeviceToHost, s));
+            if (out_counts) ANNB_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), ix->s_cnt.p, nb * 4ull, cudaMemcpyDeviceToHost, s));
+            ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+            for (uint64_t i = 0; i < nb; i++) {
+                std::memcpy(out_ids + oid[i] * k, ids.data() + i * k, k * 8ull);
+                if (out_dist) std::memcpy(out_dist + oid[i] * k, dist.data() + i * k, k * 4ull);
+                if (out_counts) out_counts[oid[i]] = cnt[i];
+            }
+        } else {
+            ANNB_CUDA_CHECK(cudaMemcpyAsync(out_ids + b0 * k, ix->s_ids.p, nb * k * 8ull, cudaMemcpyDefault, s));
+            if (out_dist) ANNB_CUDA_CHECK(cudaMemcpyAsync(out_dist + b0 * k, ix->s_dist.p, nb * k * 4ull, cudaMemcpyDefault, s));
+            if (out_counts) ANNB_CUDA_CHECK(cudaMemcpyAsync(out_counts + b0, ix->s_cnt.p, nb * 4ull, cudaMemcpyDefault, s));
+            ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+        }
+        if (ivf) ANNB_TRY(read_ivf_stats(ix, s));
+    }
+    return ANNB_OK;
+}
+
+static int common_create(annb_index* ix, int device) {
+    ix->device = device;
+    ANNB_CUDA_CHECK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    return ANNB_OK;
+}
+
+}  // namespace annb
+
+using namespace annb;
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+const char* annb_last_error(void) { return g_last_error.c_str(); }
+int annb_version(void) { return ANNB_VERSION_MAJOR * 1000 + ANNB_VERSION_MINOR; }
+
+int annb_device_count(int* out) {
+    if (!out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null out");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        *out = 0;
+        return fail(ANNB_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *out = c;
+    return ANNB_OK;
+}
+
+int annb_parse_metric(const char* str) {
+    if (!str) return -1;
+    std::string s(str);
+    for (auto& c : s) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
+    if (s == "euclidean" || s == "l2") return ANNB_L2;
+    if (s == "cosine") return ANNB_COSINE;
+    if (s == "manhattan" || s == "l1") return ANNB_MANHATTAN;
+    return -1;
+}
+
+void annb_destroy(annb_index* ix) {
+    if (!ix) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    collect_timers(ix);
+    tc_destroy(ix);
+    cudaFree(ix->d_rows); cudaFree(ix->d_norms); cudaFree(ix->d_norms_i); cudaFree(ix->d_scales);
+    cudaFree(ix->d_centroids); cudaFree(ix->d_centroid_norms); cudaFree(ix->d_offsets); cudaFree(ix->d_original_ids);
+    for (DevBuf* b : {&ix->s_qpad, &ix->s_qcodes, &ix->s_route, &ix->s_cdist, &ix->s_probes, &ix->s_nprobes, &ix->s_keys, &ix->s_flags,
+                      &ix->s_ids, &ix->s_dist, &ix->s_cnt, &ix->s_tmp})
+        b->release();
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    (void)cudaGetLastError();
+    if (prev >= 0) cudaSetDevice(prev);
+    delete ix;
+}
+
+int annb_flat_create(annb_index** out, const float* data, uint64_t n, uint32_t dim, int dtype, int metric,
+                     const float* sq8_scales, uint64_t id_base, int device) {
+    if (!out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null out");
+    *out = nullptr;
+    if (metric == ANNB_MANHATTAN) return fail(ANNB_ERR_DISTANCE_NOT_SUPPORTED, "Manhattan distance is not supported by the GPU / quantised indices");
+    if (metric != ANNB_L2 && metric != ANNB_COSINE) return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown metric");
+    if (dtype < ANNB_F32 || dtype > ANNB_SQ8) return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown dtype");
+    if (!data || n == 0 || dim == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "empty data");
+    if (n >= 0xFFFFFFFFull) return fail(ANNB_ERR_UNSUPPORTED, "n must be < 2^32 - 1 per handle (shard larger indices)");
+    ANNB_DEVICE(device);
+    annb_index* ix = new annb_index();
+    struct Cleanup { annb_index*& p; bool armed = true; ~Cleanup() { if (armed) annb_destroy(p); } } cleanup{ix};
+    ANNB_TRY(common_create(ix, device));
+    ix->dtype = dtype; ix->metric = metric; ix->n = n; ix->n_total = n; ix->dim = dim; ix->id_base = id_base;
+    ix->row_bytes = padded_row_bytes(dim, dtype);
+    cudaStream_t s = ix->stream;
+
+    // stage the f32 matrix, padded to 16-byte rows
+    const uint32_t ld = round_up(dim * 4u, 16u) / 4u;
+    float* d_f32 = nullptr;
+    DevBuf raw;
+    ANNB_TRY(dmalloc(&d_f32, n * ld, dtype == ANNB_F32 ? ix : nullptr));
+    struct FreeTmp { float*& p; bool keep; ~FreeTmp() { if (!keep && p) cudaFree(p); } } free_tmp{d_f32, dtype == ANNB_F32};
+    if (ld == dim) {
+        ANNB_CUDA_CHECK(cudaMemcpyAsync(d_f32, data, n * dim * 4ull, cudaMemcpyDefault, s));
+    } else {
+        ANNB_CUDA_CHECK(cudaMemsetAsync(d_f32, 0, n * ld * 4ull, s));
+        ANNB_CUDA_CHECK(cudaMemcpy2DAsync(d_f32, ld * 4ull, data, dim * 4ull, dim * 4ull, n, cudaMemcpyDefault, s));
+    }
+    if (dtype == ANNB_F32 || dtype == ANNB_BF16) {
+        if (metric == ANNB_COSINE) {  // norms of the un-rounded rows (exhaustive.rs:86-96, exhaustive_bf16.rs:101-111)
+            ANNB_TRY(dmalloc(&ix->d_norms, n, ix));
+            row_norms_f32_kernel<<<grid_for(n, 128, 1u << 30), 128, 0, s>>>(d_f32, ld, dim, n, ix->d_norms, 0);
+            ANNB_CUDA_CHECK(cudaGetLastError());
+        }
+        if (dtype == ANNB_F32) {
+            ix->d_rows = reinterpret_cast<uint8_t*>(d_f32);
+        } else {
+            uint16_t* d_b = nullptr;
+            ANNB_TRY(dmalloc(&d_b, n * (ix->row_bytes / 2), ix));
+            ix->d_rows = reinterpret_cast<uint8_t*>(d_b);
+            encode_bf16_kernel<<<grid_for(n * (ix->row_bytes / 2), 256), 256, 0, s>>>(d_f32, ld, dim, d_b, ix->row_bytes / 2, n);
+            ANNB_CUDA_CHECK(cudaGetLastError());
+        }
+    } else {
+        // ExhaustiveSq8Index::new (exhaustive_sq8.rs:104-151)
+        if (metric == ANNB_COSINE) {
+            normalise_rows_f32_kernel<<<grid_for(n, 128, 1u << 30), 128, 0, s>>>(d_f32, ld, dim, n);
+            ANNB_CUDA_CHECK(cudaGetLastError());
+        }
+        ANNB_TRY(dmalloc(&ix->d_scales, dim, ix));
+        if (sq8_scales) {
+            ANNB_CUDA_CHECK(cudaMemcpyAsync(ix->d_scales, sq8_scales, dim * 4ull, cudaMemcpyDefault, s));
+        } else {
+            uint32_t* d_max = nullptr;
+            ANNB_TRY(dmalloc(&d_max, dim, nullptr));
+            ANNB_CUDA_CHECK(cudaMemsetAsync(d_max, 0, dim * 4ull, s));
+            dim3 g(static_cast<uint32_t>(std::min<uint64_t>(n, 2048)), ceil_div(dim, 128u));
+            sq8_absmax_kernel<<<g, 128, 0, s>>>(d_f32, ld, dim, n, d_max);
+            sq8_scales_kernel<<<ceil_div(dim, 128u), 128, 0, s>>>(d_max, dim, ix->d_scales);
+            cudaError_t e = cudaGetLastError();
+            cudaStreamSynchronize(s);
+            cudaFree(d_max);
+            ANNB_CUDA_CHECK(e);
+        }
+        int8_t* d_c = nullptr;
+        ANNB_TRY(dmalloc(&d_c, n * ix->row_bytes, ix));
+        ix->d_rows = reinterpret_cast<uint8_t*>(d_c);
+        sq8_encode_kernel<<<grid_for(n * ix->row_bytes, 256), 256, 0, s>>>(d_f32, ld, dim, ix->d_scales, d_c, ix->row_bytes, n);
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        if (metric == ANNB_COSINE) {
+            ANNB_TRY(dmalloc(&ix->d_norms_i, n, ix));
+            sq8_row_norms_kernel<<<grid_for(n, 128, 1u << 30), 128, 0, s>>>(d_c, ix->row_bytes, dim, n, ix->d_norms_i);
+            ANNB_CUDA_CHECK(cudaGetLastError());
+        }
+    }
+    ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+    ANNB_TRY(tc_flat_prepare(ix));
+    ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+    cleanup.armed = false;
+    *out = ix;
+    return ANNB_OK;
+}
+
+int annb_flat_search(const annb_index* index, const float* queries, uint64_t nq, uint32_t dim, uint32_t k,
+                     uint64_t* out_ids, float* out_dist, uint32_t* out_counts) {
+    if (index && dim != index->dim)
+        return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(index->dim));
+    return search_host(const_cast<annb_index*>(index), false, 0, queries, 0, nq, k, 0, 0, out_ids, out_dist, out_counts);
+}
+
+int annb_flat_search_self(const annb_index* index, uint64_t row_begin, uint64_t row_end, uint32_t k,
+                          uint64_t* out_ids, float* out_dist, uint32_t* out_counts) {
+    if (!index) return fail(ANNB_ERR_INVALID_ARGUMENT, "null index");
+    if (row_begin > row_end || row_end > index->n) return fail(ANNB_ERR_INVALID_ARGUMENT, "row range outside the index");
+    return search_host(const_cast<annb_index*>(index), false, 1, nullptr, row_begin, row_end - row_begin, k, 0, 0, out_ids, out_dist, out_counts);
+}
+
+int annb_flat_search_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k,
+                         uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, void* stream) {
+    annb_index* ix = const_cast<annb_index*>(index);
+    if (!ix || ix->is_ivf) return fail(ANNB_ERR_INVALID_ARGUMENT, "not a flat index");
+    if (dim != ix->dim) return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(ix->dim));
+    if (!d_queries || !d_out_ids || k == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / k == 0");
+    ANNB_DEVICE(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
+        const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
+        PreparedQueries pq;
+        ANNB_TRY(prepare_external(ix, d_queries + b0 * dim, nb, &pq, s));
+        ANNB_TRY(flat_core(ix, pq, nb, k, d_out_ids + b0 * k, d_out_dist ? d_out_dist + b0 * k : nullptr,
+                           d_out_counts ? d_out_counts + b0 : nullptr, s));
+    }
+    return ANNB_OK;
+}
+
+int annb_ivf_assign(const float* data, uint64_t n, uint32_t dim, const float* centroids, const float* centroid_norms,
+                    uint32_t nlist, int metric, uint32_t* out_assign, int device) {
+    if (metric == ANNB_MANHATTAN) return fail(ANNB_ERR_DISTANCE_NOT_SUPPORTED, "Manhattan distance is not supported");
+    if (!data || !centroids || !out_assign || n == 0 || dim == 0 || nlist == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "empty input");
+    ANNB_DEVICE(device);
+    const uint32_t ld = round_up(dim * 4u, 16u) / 4u;
+    float *d_c = nullptr, *d_aux = nullptr, *d_x = nullptr, *d_cn = nullptr;
+    uint32_t* d_a = nullptr;
+    const uint64_t chunk = std::min<uint64_t>(n, 1ull << 20);
+    struct Free { float*& a; float*& b; float*& c; float*& e; uint32_t*& d; ~Free() { cudaFree(a); cudaFree(b); cudaFree(c); cudaFree(e); cudaFree(d); } } fr{d_c, d_aux, d_x, d_cn, d_a};
+    ANNB_TRY(dmalloc(&d_c, static_cast<size_t>(nlist) * ld, nullptr));
+    ANNB_TRY(dmalloc(&d_aux, nlist, nullptr));
+    ANNB_TRY(dmalloc(&d_x, chunk * ld, nullptr));
+    ANNB_TRY(dmalloc(&d_a, chunk, nullptr));
+    ANNB_CUDA_CHECK(cudaMemset(d_c, 0, static_cast<size_t>(nlist) * ld * 4));
+    ANNB_CUDA_CHECK(cudaMemcpy2D(d_c, ld * 4ull, centroids, dim * 4ull, dim * 4ull, nlist, cudaMemcpyDefault));
+    if (centroid_norms && metric == ANNB_COSINE) {
+        ANNB_TRY(dmalloc(&d_cn, nlist, nullptr));
+        ANNB_CUDA_CHECK(cudaMemcpy(d_cn, centroid_norms, nlist * 4ull, cudaMemcpyDefault));
+    }
+    assign_aux_kernel<<<ceil_div(nlist, 128u), 128>>>(d_c, ld, dim, nlist, metric == ANNB_COSINE, d_cn, d_aux);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
+        const uint64_t nr = std::min<uint64_t>(chunk, n - r0);
+        if (ld != dim) ANNB_CUDA_CHECK(cudaMemset(d_x, 0, nr * ld * 4ull));
+        ANNB_CUDA_CHECK(cudaMemcpy2D(d_x, ld * 4ull, data + r0 * dim, dim * 4ull, dim * 4ull, nr, cudaMemcpyDefault));
+        TileParams p{};
+        p.rows = reinterpret_cast<const uint8_t*>(d_c); p.n_rows = nlist; p.row_bytes = ld * 4; p.row_aux = d_aux;
+        p.queries = reinterpret_cast<const uint8_t*>(d_x); p.q_bytes = ld * 4; p.nq = nr; p.dim = dim;
+        p.assign_out = d_a; p.assign_cosine = metric == ANNB_COSINE;
+        size_t smem = tile_kernel_smem(p.row_bytes, p.q_bytes, 0, false);
+        ANNB_TRY((launch_tile<0, QT_F32, MET_DOT, EPI_ARGMAX>(p, dim3(static_cast<uint32_t>(ceil_div<uint64_t>(nr, CTA_QUERIES)), 1), smem, 0)));
+        ANNB_CUDA_CHECK(cudaMemcpy(out_assign + r0, d_a, nr * 4ull, cudaMemcpyDefault));
+    }
+    return ANNB_OK;
+}
+
+int annb_ivf_create(annb_index** out, const void* vectors, const void* norms, const float* centroids,
+                    const float* centroid_norms, const uint64_t* offsets, const uint64_t* original_ids,
+                    uint64_t n, uint32_t dim, uint32_t nlist, int dtype, int metric, const float* sq8_scales,
+                    uint32_t list_begin, uint32_t list_end, int device) {
+    if (!out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null out");
+    *out = nullptr;
+    if (metric == ANNB_MANHATTAN) return fail(ANNB_ERR_DISTANCE_NOT_SUPPORTED, "Manhattan distance is not supported by the IVF indices");
+    if (metric != ANNB_L2 && metric != ANNB_COSINE) return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown metric");
+    if (dtype < ANNB_F32 || dtype > ANNB_SQ8) return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown dtype");
+    if (!vectors || !centroids || !offsets || !original_ids || n == 0 || dim == 0 || nlist == 0)
+        return fail(ANNB_ERR_INVALID_ARGUMENT, "empty index contents");
+    if (list_begin > list_end || list_end > nlist) return fail(ANNB_ERR_INVALID_ARGUMENT, "bad list range");
+    if (dtype == ANNB_SQ8 && !sq8_scales) return fail(ANNB_ERR_INVALID_ARGUMENT, "SQ8 index needs its codebook scales");
+    if (metric == ANNB_COSINE && !norms) return fail(ANNB_ERR_INVALID_ARGUMENT, "cosine index needs per-vector norms");
+    if (metric == ANNB_COSINE && dtype != ANNB_SQ8 && !centroid_norms) return fail(ANNB_ERR_INVALID_ARGUMENT, "cosine index needs centroid norms");
+    std::vector<uint64_t> h_off(nlist + 1);
+    {
+        cudaError_t e = cudaMemcpy(h_off.data(), offsets, (nlist + 1) * 8ull, cudaMemcpyDefault);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(ANNB_ERR_CUDA, std::string("offsets copy: ") + cudaGetErrorString(e) + " (libannb200 has no CPU fallback)"); }
+    }
+    for (uint32_t c = 0; c < nlist; c++)
+        if (h_off[c] > h_off[c + 1]) return fail(ANNB_ERR_INVALID_ARGUMENT, "offsets must be non-decreasing");
+    if (h_off[nlist] != n) return fail(ANNB_ERR_INVALID_ARGUMENT, "offsets[nlist] must equal n");
+    const uint64_t n_local = h_off[list_end] - h_off[list_begin];
+    if (n >= 0xFFFFFFFFull) return fail(ANNB_ERR_UNSUPPORTED, "n must be < 2^32 - 1");
+    ANNB_DEVICE(device);
+    annb_index* ix = new annb_index();
+    struct Cleanup { annb_index*& p; bool armed = true; ~Cleanup() { if (armed) annb_destroy(p); } } cleanup{ix};
+    ANNB_TRY(common_create(ix, device));
+    ix->is_ivf = true; ix->dtype = dtype; ix->metric = metric; ix->n = n_local; ix->n_total = n; ix->dim = dim;
+    ix->nlist = nlist; ix->list_begin = list_begin; ix->list_end = list_end; ix->shard_row0 = h_off[list_begin];
+    ix->h_offsets = h_off;
+    ix->row_bytes = padded_row_bytes(dim, dtype);
+    cudaStream_t s = ix->stream;
+    const uint32_t src_row = dim * elem_bytes(dtype);
+    ANNB_TRY(dmalloc(&ix->d_rows, std::max<uint64_t>(n_local, 1) * ix->row_bytes, ix));
+    if (n_local) {
+        if (src_row == ix->row_bytes) {
+            ANNB_CUDA_CHECK(cudaMemcpyAsync(ix->d_rows, vectors, n_local * src_row, cudaMemcpyDefault, s));
+        } else {
+            ANNB_CUDA_CHECK(cudaMemsetAsync(ix->d_rows, 0, n_local * ix->row_bytes, s));
+            ANNB_CUDA_CHECK(cudaMemcpy2DAsync(ix->d_rows, ix->row_bytes, vectors, src_row, src_row, n_local, cudaMemcpyDefault, s));
+        }
+    }
+    if (metric == ANNB_COSINE && n_local) {
+        if (dtype == ANNB_SQ8) {
+            ANNB_TRY(dmalloc(&ix->d_norms_i, n_local, ix));
+            ANNB_CUDA_CHECK(cudaMemcpyAsync(ix->d_norms_i, norms, n_local * 4ull, cudaMemcpyDefault, s));
+        } else {
+            ANNB_TRY(dmalloc(&ix->d_norms, n_local, ix));
+            ANNB_CUDA_CHECK(cudaMemcpyAsync(ix->d_norms, norms, n_local * 4ull, cudaMemcpyDefault, s));
+        }
+    }
+    ix->cent_ld = round_up(dim * 4u, 16u) / 4u;
+    ANNB_TRY(dmalloc(&ix->d_centroids, static_cast<size_t>(nlist) * ix->cent_ld, ix));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(ix->d_centroids, 0, static_cast<size_t>(nlist) * ix->cent_ld * 4, s));
+    ANNB_CUDA_CHECK(cudaMemcpy2DAsync(ix->d_centroids, ix->cent_ld * 4ull, centroids, dim * 4ull, dim * 4ull, nlist, cudaMemcpyDefault, s));
+    if (metric == ANNB_COSINE && dtype != ANNB_SQ8) {
+        ANNB_TRY(dmalloc(&ix->d_centroid_norms, nlist, ix));
+        ANNB_CUDA_CHECK(cudaMemcpyAsync(ix->d_centroid_norms, centroid_norms, nlist * 4ull, cudaMemcpyDefault, s));
+    }
+    ANNB_TRY(dmalloc(&ix->d_offsets, nlist + 1, ix));
+    ANNB_CUDA_CHECK(cudaMemcpyAsync(ix->d_offsets, h_off.data(), (nlist + 1) * 8ull, cudaMemcpyHostToDevice, s));
+    ANNB_TRY(dmalloc(&ix->d_original_ids, std::max<uint64_t>(n_local, 1), ix));
+    if (n_local) ANNB_CUDA_CHECK(cudaMemcpyAsync(ix->d_original_ids, original_ids, n_local * 8ull, cudaMemcpyDefault, s));
+    if (dtype == ANNB_SQ8) {
+        ANNB_TRY(dmalloc(&ix->d_scales, dim, ix));
+        ANNB_CUDA_CHECK(cudaMemcpyAsync(ix->d_scales, sq8_scales, dim * 4ull, cudaMemcpyDefault, s));
+    }
+    ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+    cleanup.armed = false;
+    *out = ix;
+    return ANNB_OK;
+}
+
+int annb_ivf_search(const annb_index* index, const float* queries, uint64_t nq, uint32_t dim, uint32_t k,
+                    uint32_t nprobe, uint64_t* out_ids, float* out_dist, uint32_t* out_counts) {
+    if (index && dim != index->dim)
+        return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(index->dim));
+    return search_host(const_cast<annb_index*>(index), true, 0, queries, 0, nq, k, nprobe, 0, out_ids, out_dist, out_counts);
+}
+
+int annb_ivf_search_self(const annb_index* index, uint64_t pos_begin, uint64_t pos_end, uint32_t k, uint32_t nprobe,
+                         int scatter_to_original, uint64_t* out_ids, float* out_dist, uint32_t* out_counts) {
+    if (!index) return fail(ANNB_ERR_INVALID_ARGUMENT, "null index");
+    if (index->list_begin != 0 || index->list_end != index->nlist) return fail(ANNB_ERR_UNSUPPORTED, "self search needs an unsharded IVF index");
+    if (pos_begin > pos_end || pos_end > index->n) return fail(ANNB_ERR_INVALID_ARGUMENT, "position range outside the index");
+    return search_host(const_cast<annb_index*>(index), true, 1, nullptr, pos_begin, pos_end - pos_begin, k, nprobe, scatter_to_original,
+                       out_ids, out_dist, out_counts);
+}
+
+int annb_ivf_search_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,
+                        uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, void* stream) {
+    annb_index* ix = const_cast<annb_index*>(index);
+    if (!ix || !ix->is_ivf) return fail(ANNB_ERR_INVALID_ARGUMENT, "not an IVF index");
+    if (dim != ix->dim) return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(ix->dim));
+    if (!d_queries || !d_out_ids || k == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / k == 0");
+    ANNB_DEVICE(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ix->stat_scanned = 0;
+    ix->stat_probed = 0;
+    for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
+        const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
+        PreparedQueries pq;
+        ANNB_TRY(prepare_external(ix, d_queries + b0 * dim, nb, &pq, s));
+        ANNB_TRY(ivf_core(ix, pq, nb, k, nprobe, nullptr, d_out_ids + b0 * k, d_out_dist ? d_out_dist + b0 * k : nullptr,
+                          d_out_counts ? d_out_counts + b0 : nullptr, s));
+    }
+    return ANNB_OK;
+}
+
+int annb_merge_topk_dev(const uint64_t* d_part_ids, const float* d_part_dist, uint32_t parts, uint64_t nq, uint32_t k,
+                        uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, void* stream) {
+    if (!d_part_ids || !d_part_dist || !d_out_ids || parts == 0 || k == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / empty shape");
+    if (nq == 0) return ANNB_OK;
+    MergeParams m{};
+    m.part_ids = d_part_ids; m.part_dist = d_part_dist; m.parts = parts; m.k = k; m.nq = nq;
+    m.nsort = next_pow2(std::max(parts * k, 2u));
+    m.out_ids = d_out_ids; m.out_dist = d_out_dist; m.out_counts = d_out_counts;
+    size_t smem = static_cast<size_t>(m.nsort) * 8;
+    if (smem > 200 * 1024) return fail(ANNB_ERR_UNSUPPORTED, "merge: parts * k too large");
+    ANNB_CUDA_CHECK(cudaFuncSetAttribute(merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    merge_kernel<<<static_cast<uint32_t>(nq), 128, smem, static_cast<cudaStream_t>(stream)>>>(m);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    return ANNB_OK;
+}
+
+int annb_index_get_info(const annb_index* ix, annb_index_info* out) {
+    if (!ix || !out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
+    out->n = ix->n; out->n_total = ix->n_total; out->dim = ix->dim; out->nlist = ix->nlist;
+    out->dtype = ix->dtype; out->metric = ix->metric; out->device = ix->device; out->is_ivf = ix->is_ivf;
+    out->device_bytes = ix->device_bytes;
+    out->host_bytes = sizeof(annb_index) + ix->h_offsets.capacity() * 8;
+    return ANNB_OK;
+}
+
+int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
+    if (!ix || !key) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
+    std::lock_guard<std::mutex> lock(ix->mu);
+    std::string k(key);
+    if (k == "path") { if (value < 0 || value > 2) return fail(ANNB_ERR_INVALID_ARGUMENT, "path must be 0..2"); ix->opt_path = static_cast<int>(value); }
+    else if (k == "tc_candidates") ix->opt_tc_candidates = static_cast<int>(value);
+    else if (k == "db_splits") ix->opt_db_splits = static_cast<int>(value);
+    else if (k == "scan_parts") ix->opt_scan_parts = static_cast<int>(value);
+    else if (k == "time_kernels") { ix->opt_time_kernels = static_cast<int>(value); ix->timed_ms_total = 0.0; ix->timed_launches = 0; }
+    else return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown option " + k);
+    return ANNB_OK;
+}
+
+int annb_index_get_stat(const annb_index* ix, const char* key, int64_t* out) {
+    if (!ix || !key || !out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
+    std::string k(key);
+    if (k == "kernel_launches") *out = ix->stat_launches;
+    else if (k == "scanned_vectors") *out = ix->stat_scanned;
+    else if (k == "probed_lists") *out = ix->stat_probed;
+    else if (k == "last_path") *out = ix->stat_last_path;
+    else if (k == "uncertified") *out = ix->stat_uncertified;
+    else if (k == "dominant_kernel_ns" || k == "dominant_kernel_launches") {
+        // synchronises on the recorded events; total device time of the dominant kernel since time_kernels was set
+        DeviceGuard g(ix->device);
+        std::lock_guard<std::mutex> lock(ix->mu);
+        collect_timers(ix);
+        *out = (k == "dominant_kernel_ns") ? static_cast<int64_t>(ix->timed_ms_total * 1e6) : ix->timed_launches;
+    }
+    else return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown stat " + k);
+    return ANNB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,20 @@
+// flat_tc.hpp -- host interface of the tensor-core (tcgen05 / TMEM / TMA) flat search path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct annb_index;
+
+namespace annb {
+
+// Builds the tensor-core operand copies (tf32 hi/lo split, norms) and TMA descriptors of a flat index.
+int tc_flat_prepare(annb_index* ix);
+// True if (dtype, dim, k, query type) is covered by the tensor path.
+bool tc_flat_supported(const annb_index* ix, int qt, uint32_t k_eff);
+// Flat search on the tensor path: approximate pre-selection of k' candidates per (query, split) on the
+// tensor cores, then exact re-rank in the reference's arithmetic and merge.
+int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt, int bf16_self, uint64_t nq, uint32_t k_eff,
+                   uint32_t k_out, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s);
+void tc_destroy(annb_index* ix);
+
+}  // namespace annb

@@ -1,0 +1,95 @@
+// index.hpp -- host-side state behind the opaque annb_index handle.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace annb {
+
+// Grow-only device scratch buffer.
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return ANNB_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 3) + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            set_last_error(std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e));
+            (void)cudaGetLastError();
+            return e == cudaErrorMemoryAllocation ? ANNB_ERR_OUT_OF_MEMORY : ANNB_ERR_CUDA;
+        }
+        cap = want;
+        return ANNB_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct TcState;  // tensor-core operand copies + tensor maps (flat_tc.cu)
+
+}  // namespace annb
+
+struct annb_index {
+    int device = 0;
+    int dtype = ANNB_F32;
+    int metric = ANNB_L2;
+    bool is_ivf = false;
+    uint64_t n = 0;        // rows stored by this handle
+    uint64_t n_total = 0;  // rows of the whole index
+    uint32_t dim = 0;
+    uint32_t row_bytes = 0;  // padded row pitch of d_rows
+    uint64_t id_base = 0;
+
+    uint8_t* d_rows = nullptr;     // [n][row_bytes] in the index dtype
+    float* d_norms = nullptr;      // [n] cosine (f32 / bf16)
+    int32_t* d_norms_i = nullptr;  // [n] cosine (sq8)
+    float* d_scales = nullptr;     // [dim] sq8
+
+    // IVF
+    uint32_t nlist = 0, list_begin = 0, list_end = 0;
+    uint32_t cent_ld = 0;             // centroid pitch in floats
+    float* d_centroids = nullptr;     // [nlist][cent_ld]
+    float* d_centroid_norms = nullptr;
+    uint64_t* d_offsets = nullptr;       // [nlist+1] global
+    uint64_t* d_original_ids = nullptr;  // [n]
+    uint64_t shard_row0 = 0;
+    std::vector<uint64_t> h_offsets;
+
+    // options
+    int opt_path = ANNB_PATH_AUTO;
+    int opt_tc_candidates = 0;
+    int opt_db_splits = 0;
+    int opt_scan_parts = 0;
+    int opt_time_kernels = 0;  // record CUDA events around the dominant kernel of every search
+
+    // stats
+    mutable int64_t stat_launches = 0;
+    mutable int64_t stat_scanned = 0, stat_probed = 0, stat_last_path = 0, stat_uncertified = 0;
+
+    uint64_t device_bytes = 0;
+
+    // dominant-kernel timing (option "time_kernels"): event pairs recorded on the launching stream
+    mutable std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timed;
+    mutable double timed_ms_total = 0.0;
+    mutable int64_t timed_launches = 0;
+
+    // scratch (guarded by mu)
+    mutable std::mutex mu;
+    cudaStream_t stream = nullptr;
+    annb::DevBuf s_qpad, s_qcodes, s_route, s_cdist, s_probes, s_nprobes, s_keys, s_flags, s_ids, s_dist, s_cnt, s_tmp;
+    annb::TcState* tc = nullptr;
+};

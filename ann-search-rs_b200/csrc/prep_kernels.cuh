@@ -1,0 +1,155 @@
+// prep_kernels.cuh -- index-construction and query-preparation kernels.
+// Each mirrors one step of the reference constructors with the same arithmetic, so the
+// device-built index holds exactly the bytes the CPU index would hold.
+#pragma once
+#include "common.cuh"
+#include "refdist.cuh"
+
+namespace annb {
+
+// [n][src_row_bytes] -> [n][dst_row_bytes], zero padded (dst_row_bytes % 16 == 0).
+__global__ void pad_rows_kernel(const uint8_t* __restrict__ src, uint32_t src_row_bytes, uint8_t* __restrict__ dst,
+                                uint32_t dst_row_bytes, uint64_t n) {
+    const uint64_t total = n * dst_row_bytes;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        uint64_t r = i / dst_row_bytes;
+        uint32_t c = static_cast<uint32_t>(i - r * dst_row_bytes);
+        dst[i] = (c < src_row_bytes) ? src[r * src_row_bytes + c] : 0;
+    }
+}
+
+// calculate_l2_norm per row (src/utils/dist.rs:2339-2360), rows padded f32 with pitch ld floats.
+__global__ void row_norms_f32_kernel(const float* __restrict__ rows, uint32_t ld, uint32_t dim, uint64_t n, float* __restrict__ out,
+                                     int squared) {
+    uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    float s = ref_dot_self_f32(rows + i * ld, dim);
+    out[i] = squared ? s : __fsqrt_rn(s);
+}
+
+// normalise_vector per row (src/utils/dist.rs:5336-5344).
+__global__ void normalise_rows_f32_kernel(float* __restrict__ rows, uint32_t ld, uint32_t dim, uint64_t n) {
+    uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    float* v = rows + i * ld;
+    float nrm = __fsqrt_rn(ref_dot_self_f32(v, dim));
+    if (nrm > 0.0f)
+        for (uint32_t e = 0; e < dim; e++) v[e] = __fdiv_rn(v[e], nrm);
+}
+
+// encode_bf16_quantisation (src/quantised/quantisers.rs:31-38): RNE.  f32 pitch ld_src floats ->
+// bf16 pitch ld_dst elements, zero padded.
+__global__ void encode_bf16_kernel(const float* __restrict__ src, uint32_t ld_src, uint32_t dim, uint16_t* __restrict__ dst,
+                                   uint32_t ld_dst, uint64_t n) {
+    const uint64_t total = n * ld_dst;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        uint64_t r = i / ld_dst;
+        uint32_t c = static_cast<uint32_t>(i - r * ld_dst);
+        uint16_t v = 0;
+        if (c < dim) {
+            uint32_t x = __float_as_uint(src[r * ld_src + c]);
+            if ((x & 0x7FFFFFFFu) > 0x7F800000u) v = static_cast<uint16_t>((x >> 16) | 0x0040u);
+            else if ((x & 0x8000u) != 0 && (x & 0x17FFFu) != 0) v = static_cast<uint16_t>((x >> 16) + 1);
+            else v = static_cast<uint16_t>(x >> 16);
+        }
+        dst[i] = v;
+    }
+}
+
+// bf16 -> f32 widening (decode_bf16_quantisation, quantisers.rs:50-62); same pitch in elements.
+__global__ void decode_bf16_kernel(const uint16_t* __restrict__ src, uint32_t ld_src, float* __restrict__ dst, uint32_t ld_dst,
+                                   uint32_t dim, uint64_t n) {
+    const uint64_t total = n * ld_dst;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        uint64_t r = i / ld_dst;
+        uint32_t c = static_cast<uint32_t>(i - r * ld_dst);
+        dst[i] = (c < dim) ? bf16_bits_to_f32(src[r * ld_src + c]) : 0.0f;
+    }
+}
+
+// ScalarQuantiser::train (src/quantised/quantisers.rs:123-146): per-dimension max |x|, then /128.
+__global__ void sq8_absmax_kernel(const float* __restrict__ rows, uint32_t ld, uint32_t dim, uint64_t n, uint32_t* __restrict__ maxbits) {
+    // one thread column per dimension inside a block row-stripe; non-negative floats order like their bits
+    const uint32_t d = blockIdx.y * blockDim.x + threadIdx.x;
+    if (d >= dim) return;
+    uint32_t m = 0;
+    for (uint64_t r = blockIdx.x; r < n; r += gridDim.x) {
+        float a = fabsf(rows[r * ld + d]);
+        if (!(a != a)) m = max(m, __float_as_uint(a));  // Float::max ignores NaN
+    }
+    atomicMax(maxbits + d, m);
+}
+__global__ void sq8_scales_kernel(const uint32_t* __restrict__ maxbits, uint32_t dim, float* __restrict__ scales) {
+    uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= dim) return;
+    float mx = __uint_as_float(maxbits[d]);
+    scales[d] = (mx <= 0.0f) ? 1.0f : __fdiv_rn(mx, 128.0f);
+}
+
+__device__ __forceinline__ int8_t sq8_encode_one(float val, float scale) {
+    // ScalarQuantiser::encode (src/quantised/quantisers.rs:148-165)
+    float scaled = __fdiv_rn(val, scale);
+    if (scaled != scaled) return 0;  // to_i8() of NaN -> None -> 0
+    float sg = (__float_as_uint(scaled) >> 31) ? -1.0f : 1.0f;  // f32::signum (+0 -> 1, -0 -> -1)
+    float rounded = __fadd_rn(scaled, __fmul_rn(0.5f, sg));
+    float clamped = fmaxf(fminf(rounded, 127.0f), -128.0f);
+    return static_cast<int8_t>(static_cast<int>(clamped));  // truncation toward zero
+}
+__global__ void sq8_encode_kernel(const float* __restrict__ src, uint32_t ld_src, uint32_t dim, const float* __restrict__ scales,
+                                  int8_t* __restrict__ dst, uint32_t ld_dst, uint64_t n) {
+    const uint64_t total = n * ld_dst;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        uint64_t r = i / ld_dst;
+        uint32_t c = static_cast<uint32_t>(i - r * ld_dst);
+        dst[i] = (c < dim) ? sq8_encode_one(src[r * ld_src + c], scales[c]) : 0;
+    }
+}
+// ScalarQuantiser::decode (quantisers.rs:167-175): code * scale.
+__global__ void sq8_decode_kernel(const int8_t* __restrict__ src, uint32_t ld_src, const float* __restrict__ scales,
+                                  float* __restrict__ dst, uint32_t ld_dst, uint32_t dim, uint64_t n) {
+    const uint64_t total = n * ld_dst;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        uint64_t r = i / ld_dst;
+        uint32_t c = static_cast<uint32_t>(i - r * ld_dst);
+        dst[i] = (c < dim) ? __fmul_rn(__int2float_rn(src[r * ld_src + c]), scales[c]) : 0.0f;
+    }
+}
+// sum of squared codes per row (exhaustive_sq8.rs:132-141).
+__global__ void sq8_row_norms_kernel(const int8_t* __restrict__ rows, uint32_t ld, uint32_t dim, uint64_t n, int32_t* __restrict__ out) {
+    uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    int32_t s = 0;
+    for (uint32_t e = 0; e < dim; e++) {
+        int32_t v = rows[i * ld + e];
+        s += v * v;
+    }
+    out[i] = s;
+}
+
+// direct_assign shortcut norms (src/utils/k_means_utils.rs:2134-2156): |c|^2 via dot_simd (L2) or
+// 1/norm (cosine; 0 when the norm is 0) where norm is the caller-supplied centroid norm, or when none
+// is supplied the sequential-fold norm IvfIndex::build computes (src/cpu/ivf.rs:193-206).
+__global__ void assign_aux_kernel(const float* __restrict__ cent, uint32_t ld, uint32_t dim, uint32_t nlist, int cosine,
+                                  const float* __restrict__ cnorms, float* __restrict__ aux) {
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nlist) return;
+    const float* v = cent + static_cast<uint64_t>(c) * ld;
+    if (!cosine) aux[c] = ref_dot_self_f32(v, dim);
+    else {
+        float nrm = cnorms ? cnorms[c] : seq_norm<4>(reinterpret_cast<const uint8_t*>(v), dim);
+        aux[c] = (nrm > 0.0f) ? __fdiv_rn(1.0f, nrm) : 0.0f;
+    }
+}
+// Sequential-fold norms of f32 rows (centroid norms, src/cpu/ivf.rs:193-206).
+__global__ void seq_norms_kernel(const float* __restrict__ rows, uint32_t ld, uint32_t dim, uint64_t n, float* __restrict__ out) {
+    uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n) return;
+    out[i] = seq_norm<4>(reinterpret_cast<const uint8_t*>(rows + i * ld), dim);
+}
+
+}  // namespace annb

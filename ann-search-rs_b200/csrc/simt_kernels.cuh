@@ -1,0 +1,538 @@
+// simt_kernels.cuh -- exact (reference-order) CUDA-core kernels.
+//
+//   tile_kernel     : a CTA holds 32 queries and streams 32-row tiles of a row store
+//                     through shared memory (cp.async double buffer); every lane owns one
+//                     row of the tile and computes its distance to 4 queries of its warp.
+//                     Epilogues: top-k select (flat search), dense matrix (IVF centroid
+//                     ranking), argmax (IVF coarse assignment at build time).
+//   ivf_scan_kernel : one warp per (query, part) walks that query's probed inverted lists
+//                     -- contiguous slabs in list order -- with 128-bit cp.async loads
+//                     staged through shared memory, dequantisation fused into the distance.
+//   probe_kernel    : per query, full (distance, cell) sort of the centroid ranking and the
+//                     probe-expansion walk of select_probed_clusters.
+//   finalize_kernel : merges per-split / per-part partial results into the final rows.
+//
+// All arithmetic goes through refdist.cuh, so results are bit-identical to the CPU
+// reference's AVX2 path (see oracle/oracle.c).
+#pragma once
+#include "common.cuh"
+#include "refdist.cuh"
+#include "select.cuh"
+
+namespace annb {
+
+constexpr int TILE_ROWS = 32;      // rows per staged tile = one row per lane
+constexpr int CTA_QUERIES = 32;    // queries per CTA in tile_kernel
+constexpr int WARP_QUERIES = 4;    // queries per warp in tile_kernel
+constexpr int TILE_THREADS = 256;
+
+enum { EPI_SELECT = 0, EPI_DENSE = 1, EPI_ARGMAX = 2 };
+
+// Shared-memory row pitch: an odd number of 16-byte chunks, so that the 8 lanes of a
+// quarter warp reading the same chunk of 8 consecutive rows hit 8 distinct bank groups.
+__host__ __device__ __forceinline__ uint32_t smem_row_pitch(uint32_t row_bytes) { return ((row_bytes >> 4) | 1u) << 4; }
+
+struct TileParams {
+    const uint8_t* rows;        // [n_rows][row_bytes]
+    uint64_t n_rows;
+    uint32_t row_bytes;
+    const float* row_norms;     // cosine (f32 / bf16 rows)
+    const int32_t* row_norms_i; // cosine (sq8 rows)
+    const float* row_aux;       // EPI_ARGMAX: |c|^2 (L2) or 1/|c| (cosine) per centroid
+    const uint8_t* queries;     // [nq][q_bytes]
+    uint32_t q_bytes;
+    uint64_t nq;
+    uint32_t dim;
+    int bf16_self;              // bf16 x bf16: query norm is rounded to bf16 (exhaustive_bf16.rs:259-270)
+    // EPI_SELECT
+    uint32_t k, nsort, n_splits;
+    uint64_t rows_per_split;
+    uint64_t* part_keys;        // [nq][n_splits][k]
+    // EPI_DENSE
+    float* dense_out;           // [nq][n_rows]
+    // EPI_ARGMAX
+    uint32_t* assign_out;       // [nq]
+    int assign_cosine;
+};
+
+// Cooperative copy of `nrows` consecutive rows into a staged tile.
+__device__ __forceinline__ void stage_rows(uint8_t* smem_tile, uint32_t pitch, const uint8_t* gsrc, uint32_t row_bytes,
+                                           uint32_t nrows, uint32_t tid, uint32_t nthreads) {
+    const uint32_t cpr = row_bytes >> 4;
+    const uint32_t total = nrows * cpr;
+    for (uint32_t g = tid; g < total; g += nthreads) {
+        uint32_t r = g / cpr, c = g - r * cpr;
+        cp_async16(smem_tile + r * pitch + (c << 4), gsrc + (static_cast<uint64_t>(g) << 4));
+    }
+}
+
+// RT: 0 = f32 rows, 1 = bf16 rows, 2 = int8 rows.  QT: query element type (QT_*).
+template <int RT, int QT, int MET, int EPI>
+__global__ void __launch_bounds__(TILE_THREADS) tile_kernel(TileParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t xpitch = smem_row_pitch(p.row_bytes);
+    uint8_t* s_q = smem;                                              // [32][q_bytes]
+    float* s_qnorm = reinterpret_cast<float*>(s_q + CTA_QUERIES * p.q_bytes);  // [32]
+    int32_t* s_qnsq = reinterpret_cast<int32_t*>(s_qnorm + CTA_QUERIES);       // [32]
+    uint8_t* s_x = reinterpret_cast<uint8_t*>(s_qnsq + CTA_QUERIES);           // [2][32][xpitch]
+    uint64_t* s_sel = reinterpret_cast<uint64_t*>(s_x + 2 * TILE_ROWS * xpitch);  // [32][nsort]
+
+    const uint64_t q0 = static_cast<uint64_t>(blockIdx.x) * CTA_QUERIES;
+    uint64_t r_begin = 0, r_end = p.n_rows;
+    if (EPI == EPI_SELECT) {
+        r_begin = static_cast<uint64_t>(blockIdx.y) * p.rows_per_split;
+        r_end = min(p.n_rows, r_begin + p.rows_per_split);
+        if (r_begin > r_end) r_begin = r_end;
+    }
+    // ---- queries -> shared (zero rows for q >= nq) ----
+    {
+        const uint32_t cpr = p.q_bytes >> 4;
+        for (uint32_t g = tid; g < CTA_QUERIES * cpr; g += TILE_THREADS) {
+            uint32_t r = g / cpr, c = g - r * cpr;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (q0 + r < p.nq) v = *reinterpret_cast<const uint4*>(p.queries + (q0 + r) * p.q_bytes + (c << 4));
+            *reinterpret_cast<uint4*>(s_q + r * p.q_bytes + (c << 4)) = v;
+        }
+    }
+    __syncthreads();
+    if (tid < CTA_QUERIES) {
+        const uint8_t* q = s_q + tid * p.q_bytes;
+        float qn = 1.0f;
+        int32_t qs = 0;
+        if (QT == QT_I8) {
+            for (uint32_t e = 0; e < p.dim; e++) {
+                int32_t v = reinterpret_cast<const int8_t*>(q)[e];
+                qs += v * v;
+            }
+        } else if (MET == MET_COS) {
+            qn = seq_norm<(QT == QT_F32) ? 4 : 2>(q, p.dim);
+            if (p.bf16_self) qn = round_to_bf16(qn);
+        }
+        s_qnorm[tid] = qn;
+        s_qnsq[tid] = qs;
+    }
+    WarpSelect sel[WARP_QUERIES];
+    if (EPI == EPI_SELECT) {
+#pragma unroll
+        for (int i = 0; i < WARP_QUERIES; i++)
+            sel[i].init(s_sel + static_cast<size_t>(warp * WARP_QUERIES + i) * p.nsort, p.nsort, p.k);
+    }
+    float best_s[WARP_QUERIES];
+    uint32_t best_c[WARP_QUERIES];
+#pragma unroll
+    for (int i = 0; i < WARP_QUERIES; i++) { best_s[i] = -INFINITY; best_c[i] = 0; }
+    __syncthreads();
+
+    const uint8_t* qw = s_q + warp * WARP_QUERIES * p.q_bytes;
+    const uint64_t n_tiles = (r_end - r_begin + TILE_ROWS - 1) / TILE_ROWS;
+    if (n_tiles > 0) {
+        uint32_t nr = static_cast<uint32_t>(min(static_cast<uint64_t>(TILE_ROWS), r_end - r_begin));
+        stage_rows(s_x, xpitch, p.rows + r_begin * p.row_bytes, p.row_bytes, nr, tid, TILE_THREADS);
+    }
+    cp_async_commit();
+    for (uint64_t t = 0; t < n_tiles; t++) {
+        const uint64_t row0 = r_begin + t * TILE_ROWS;
+        if (t + 1 < n_tiles) {
+            const uint64_t nrow0 = row0 + TILE_ROWS;
+            uint32_t nr = static_cast<uint32_t>(min(static_cast<uint64_t>(TILE_ROWS), r_end - nrow0));
+            stage_rows(s_x + ((t + 1) & 1) * TILE_ROWS * xpitch, xpitch, p.rows + nrow0 * p.row_bytes, p.row_bytes, nr, tid,
+                       TILE_THREADS);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        const uint64_t row = row0 + lane;
+        const bool valid = row < r_end;
+        const uint8_t* xr = s_x + (t & 1) * TILE_ROWS * xpitch + lane * xpitch;
+        float dist[WARP_QUERIES];
+#pragma unroll
+        for (int i = 0; i < WARP_QUERIES; i++) dist[i] = 0.0f;
+        if (valid) {
+            if (RT == 2) {
+                int32_t dot[WARP_QUERIES], xx;
+                accumulate_i8<WARP_QUERIES>(xr, qw, p.q_bytes, p.dim, dot, xx);
+                int32_t xn = (MET == MET_COS) ? p.row_norms_i[row] : 0;
+#pragma unroll
+                for (int i = 0; i < WARP_QUERIES; i++)
+                    dist[i] = finish_i8<MET>(dot[i], xx, s_qnsq[warp * WARP_QUERIES + i], xn);
+            } else {
+                float raw[WARP_QUERIES];
+                accumulate_fp<(RT == 0) ? 4 : 2, (QT == QT_F32) ? 4 : 2, MET == MET_L2, WARP_QUERIES>(xr, qw, p.q_bytes, p.dim,
+                                                                                                     raw);
+                float xn = (MET == MET_COS) ? p.row_norms[row] : 1.0f;
+#pragma unroll
+                for (int i = 0; i < WARP_QUERIES; i++) dist[i] = finish_fp<MET>(raw[i], s_qnorm[warp * WARP_QUERIES + i], xn);
+            }
+        }
+        if (EPI == EPI_SELECT) {
+#pragma unroll
+            for (int i = 0; i < WARP_QUERIES; i++) sel[i].offer(make_key(dist[i], static_cast<uint32_t>(row)), valid);
+        } else if (EPI == EPI_DENSE) {
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < WARP_QUERIES; i++) {
+                    uint64_t q = q0 + warp * WARP_QUERIES + i;
+                    if (q < p.nq) p.dense_out[q * p.n_rows + row] = dist[i];
+                }
+            }
+        } else {  // EPI_ARGMAX: direct_assign, src/utils/k_means_utils.rs:2119-2195
+            if (valid) {
+                float aux = p.row_aux[row];
+#pragma unroll
+                for (int i = 0; i < WARP_QUERIES; i++) {
+                    float score = p.assign_cosine ? __fmul_rn(dist[i], aux) : __fsub_rn(__fmul_rn(2.0f, dist[i]), aux);
+                    if (score > best_s[i]) { best_s[i] = score; best_c[i] = static_cast<uint32_t>(row); }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    if (EPI == EPI_SELECT) {
+#pragma unroll
+        for (int i = 0; i < WARP_QUERIES; i++) {
+            sel[i].flush();
+            uint64_t q = q0 + warp * WARP_QUERIES + i;
+            if (q < p.nq) {
+                uint64_t* out = p.part_keys + (q * p.n_splits + blockIdx.y) * p.k;
+                for (uint32_t j = lane; j < p.k; j += 32) out[j] = sel[i].buf[j];
+            }
+        }
+    } else if (EPI == EPI_ARGMAX) {
+#pragma unroll
+        for (int i = 0; i < WARP_QUERIES; i++) {
+            float s = best_s[i];
+            uint32_t c = best_c[i];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                float os = __shfl_xor_sync(0xFFFFFFFFu, s, off);
+                uint32_t oc = __shfl_xor_sync(0xFFFFFFFFu, c, off);
+                if (os > s || (os == s && oc < c)) { s = os; c = oc; }
+            }
+            uint64_t q = q0 + warp * WARP_QUERIES + i;
+            if (lane == 0 && q < p.nq) p.assign_out[q] = c;
+        }
+    }
+}
+
+static inline size_t tile_kernel_smem(uint32_t row_bytes, uint32_t q_bytes, uint32_t nsort, bool select) {
+    size_t s = static_cast<size_t>(CTA_QUERIES) * q_bytes + CTA_QUERIES * 8 + 2ull * TILE_ROWS * smem_row_pitch(row_bytes);
+    if (select) s += static_cast<size_t>(CTA_QUERIES) * nsort * 8;
+    return s;
+}
+
+// ---------------------------------------------------------------------------
+// IVF list scan (src/cpu/ivf.rs:367-381).
+// ---------------------------------------------------------------------------
+constexpr int SCAN_WARPS = 4;
+
+struct ScanParams {
+    const uint8_t* rows;         // this shard's vectors, list order
+    uint32_t row_bytes;
+    const float* row_norms;
+    const int32_t* row_norms_i;
+    const uint8_t* queries;      // scan-side queries [nq][q_bytes]
+    uint32_t q_bytes;
+    uint64_t nq;
+    uint32_t dim;
+    int bf16_self;
+    const uint32_t* probes;      // [nq][probe_pitch] cell ids in rank order
+    uint32_t probe_pitch;
+    const uint32_t* n_probes;    // [nq]
+    const uint64_t* offsets;     // [nlist+1] global CSR offsets
+    uint32_t list_begin, list_end;
+    uint64_t shard_row0;         // offsets[list_begin]
+    uint32_t parts, k, nsort;
+    uint64_t* part_keys;         // [nq][parts][k]; key index = row position inside the shard
+};
+
+template <int RT, int QT, int MET>
+__global__ void __launch_bounds__(SCAN_WARPS * 32) ivf_scan_kernel(ScanParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t xpitch = smem_row_pitch(p.row_bytes);
+    const size_t per_warp = static_cast<size_t>(p.q_bytes) + 2ull * TILE_ROWS * xpitch + static_cast<size_t>(p.nsort) * 8;
+    uint8_t* base = smem + warp * per_warp;
+    uint64_t* s_sel = reinterpret_cast<uint64_t*>(base);                 // [nsort]   (8-byte aligned first)
+    uint8_t* s_q = base + static_cast<size_t>(p.nsort) * 8;              // [q_bytes]
+    uint8_t* s_x = s_q + p.q_bytes;                                       // [2][32][xpitch]
+
+    const uint64_t task = static_cast<uint64_t>(blockIdx.x) * SCAN_WARPS + warp;
+    const uint64_t q = task / p.parts;
+    const uint32_t part = static_cast<uint32_t>(task % p.parts);
+    if (q >= p.nq) return;  // whole warp exits together (task is warp-uniform)
+
+    for (uint32_t c = lane; c < (p.q_bytes >> 4); c += 32)
+        *reinterpret_cast<uint4*>(s_q + (c << 4)) = *reinterpret_cast<const uint4*>(p.queries + q * p.q_bytes + (c << 4));
+    __syncwarp();
+    float qnorm = 1.0f;
+    int32_t qnsq = 0;
+    if (QT == QT_I8) {
+        for (uint32_t e = lane; e < p.dim; e += 32) {
+            int32_t v = reinterpret_cast<const int8_t*>(s_q)[e];
+            qnsq += v * v;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) qnsq += __shfl_xor_sync(0xFFFFFFFFu, qnsq, off);
+    } else if (MET == MET_COS) {
+        if (lane == 0) {
+            qnorm = seq_norm<(QT == QT_F32) ? 4 : 2>(s_q, p.dim);
+            if (p.bf16_self) qnorm = round_to_bf16(qnorm);
+        }
+        qnorm = __shfl_sync(0xFFFFFFFFu, qnorm, 0);
+    }
+    WarpSelect sel;
+    sel.init(s_sel, p.nsort, p.k);
+
+    const uint32_t np = p.n_probes[q];
+    const uint32_t* probes = p.probes + q * p.probe_pitch;
+
+    // tile generator over this part's probe ranks (part, part + parts, ...)
+    uint32_t rank = part;
+    uint64_t pos = 0, end = 0;  // current list: shard-local row range [pos, end)
+    auto next_tile = [&](uint64_t& t_row, uint32_t& t_n) -> bool {
+        while (pos >= end) {
+            if (rank >= np) return false;
+            uint32_t c = probes[rank];
+            rank += p.parts;
+            if (c < p.list_begin || c >= p.list_end) continue;  // list lives on another shard
+            pos = p.offsets[c] - p.shard_row0;
+            end = p.offsets[c + 1] - p.shard_row0;
+        }
+        t_row = pos;
+        t_n = static_cast<uint32_t>(min(static_cast<uint64_t>(TILE_ROWS), end - pos));
+        pos += t_n;
+        return true;
+    };
+
+    uint64_t cur_row = 0, nxt_row = 0;
+    uint32_t cur_n = 0, nxt_n = 0;
+    bool have = next_tile(cur_row, cur_n);
+    uint32_t b = 0;
+    if (have) stage_rows(s_x, xpitch, p.rows + cur_row * p.row_bytes, p.row_bytes, cur_n, lane, 32);
+    cp_async_commit();
+    while (have) {
+        bool have_next = next_tile(nxt_row, nxt_n);
+        if (have_next)
+            stage_rows(s_x + (b ^ 1u) * TILE_ROWS * xpitch, xpitch, p.rows + nxt_row * p.row_bytes, p.row_bytes, nxt_n, lane, 32);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const bool valid = lane < cur_n;
+        const uint64_t row = cur_row + lane;
+        const uint8_t* xr = s_x + b * TILE_ROWS * xpitch + lane * xpitch;
+        float dist = 0.0f;
+        if (valid) {
+            if (RT == 2) {
+                int32_t dot[1], xx;
+                accumulate_i8<1>(xr, s_q, p.q_bytes, p.dim, dot, xx);
+                int32_t xn = (MET == MET_COS) ? p.row_norms_i[row] : 0;
+                dist = finish_i8<MET>(dot[0], xx, qnsq, xn);
+            } else {
+                float raw[1];
+                accumulate_fp<(RT == 0) ? 4 : 2, (QT == QT_F32) ? 4 : 2, MET == MET_L2, 1>(xr, s_q, p.q_bytes, p.dim, raw);
+                float xn = (MET == MET_COS) ? p.row_norms[row] : 1.0f;
+                dist = finish_fp<MET>(raw[0], qnorm, xn);
+            }
+        }
+        sel.offer(make_key(dist, static_cast<uint32_t>(row)), valid);
+        __syncwarp();
+        have = have_next;
+        cur_row = nxt_row;
+        cur_n = nxt_n;
+        b ^= 1u;
+    }
+    cp_async_wait<0>();
+    sel.flush();
+    uint64_t* out = p.part_keys + (q * p.parts + part) * p.k;
+    for (uint32_t j = lane; j < p.k; j += 32) out[j] = sel.buf[j];
+}
+
+static inline size_t scan_kernel_smem(uint32_t row_bytes, uint32_t q_bytes, uint32_t nsort) {
+    return SCAN_WARPS * (static_cast<size_t>(q_bytes) + 2ull * TILE_ROWS * smem_row_pitch(row_bytes) + static_cast<size_t>(nsort) * 8);
+}
+
+// ---------------------------------------------------------------------------
+// Probe selection: get_centroids_dist + select_probed_clusters
+// (src/utils/k_means_utils.rs:76-99, 3007-3029).  One CTA per query sorts all
+// (distance, cell) pairs -- equal distances in ascending cell id -- and walks the
+// ranking until `nprobe` cells are chosen AND at least k vectors are reachable
+// (empty cells count toward nprobe only).  List sizes are global, so every shard
+// of a sharded index derives the same probe list.
+// ---------------------------------------------------------------------------
+struct ProbeParams {
+    const float* cdist;      // [nq][nlist]
+    uint32_t nlist, nlist_pow2;
+    const uint64_t* offsets; // [nlist+1]
+    uint32_t nprobe;
+    uint64_t k;
+    uint32_t* probes;        // [nq][probe_pitch]
+    uint32_t probe_pitch;
+    uint32_t* n_probes;      // [nq]
+    uint32_t* overflow;      // set to 1 if some query needs more than probe_pitch cells
+    unsigned long long* stat_scanned;  // sum over queries of reachable vectors
+    unsigned long long* stat_probed;   // sum over queries of probed cells
+};
+
+__global__ void __launch_bounds__(256) probe_kernel(ProbeParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
+    __shared__ uint32_t s_np;
+    const uint64_t q = blockIdx.x;
+    const float* row = p.cdist + q * p.nlist;
+    for (uint32_t i = threadIdx.x; i < p.nlist_pow2; i += blockDim.x) keys[i] = (i < p.nlist) ? make_key(row[i], i) : KEY_SENTINEL;
+    __syncthreads();
+    bitonic_sort_keys<true>(keys, p.nlist_pow2, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0) {
+        uint32_t chosen = 0;
+        uint64_t reach = 0;
+        for (uint32_t i = 0; i < p.nlist; i++) {
+            uint32_t c = key_idx(keys[i]);
+            chosen++;
+            reach += p.offsets[c + 1] - p.offsets[c];
+            if (chosen >= p.nprobe && reach >= p.k) break;
+        }
+        s_np = chosen;
+        if (chosen > p.probe_pitch) atomicExch(p.overflow, 1u);
+        p.n_probes[q] = min(chosen, p.probe_pitch);
+        atomicAdd(p.stat_scanned, static_cast<unsigned long long>(reach));
+        atomicAdd(p.stat_probed, static_cast<unsigned long long>(chosen));
+    }
+    __syncthreads();
+    const uint32_t np = min(s_np, p.probe_pitch);
+    for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) p.probes[q * p.probe_pitch + i] = key_idx(keys[i]);
+}
+
+// ---------------------------------------------------------------------------
+// Finalize: merge `parts` partial key lists per query, emit the k best.
+//   id = id_map ? id_map[idx] : idx + id_base ; output row = row_map ? row_map[q] : q
+// ---------------------------------------------------------------------------
+struct FinalizeParams {
+    const uint64_t* part_keys;  // [nq][parts][kc]
+    uint32_t parts, kc, k, nsort;
+    uint64_t nq;
+    const uint64_t* id_map;
+    uint64_t id_base;
+    const uint64_t* row_map;
+    uint64_t* out_ids;
+    float* out_dist;
+    uint32_t* out_counts;
+};
+
+__global__ void __launch_bounds__(128) finalize_kernel(FinalizeParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
+    const uint64_t q = blockIdx.x;
+    const uint32_t total = p.parts * p.kc;
+    const uint64_t* src = p.part_keys + q * total;
+    for (uint32_t i = threadIdx.x; i < p.nsort; i += blockDim.x) keys[i] = (i < total) ? src[i] : KEY_SENTINEL;
+    __syncthreads();
+    bitonic_sort_keys<true>(keys, p.nsort, threadIdx.x, blockDim.x);
+    const uint64_t orow = p.row_map ? p.row_map[q] : q;
+    uint32_t my_valid = 0;
+    for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) {
+        uint64_t key = keys[j];
+        bool ok = key_idx(key) != IDX_INVALID;
+        uint64_t id = 0xFFFFFFFFFFFFFFFFull;
+        float d = INFINITY;
+        if (ok) {
+            uint32_t idx = key_idx(key);
+            id = p.id_map ? p.id_map[idx] : (static_cast<uint64_t>(idx) + p.id_base);
+            d = key_dist(key);
+            my_valid++;
+        }
+        p.out_ids[orow * p.k + j] = id;
+        if (p.out_dist) p.out_dist[orow * p.k + j] = d;
+    }
+    if (p.out_counts) {
+        __shared__ uint32_t s_cnt;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        if (my_valid) atomicAdd(&s_cnt, my_valid);
+        __syncthreads();
+        if (threadIdx.x == 0) p.out_counts[orow] = s_cnt;
+    }
+}
+
+// Cross-shard merge (annb_merge_topk_dev): inputs are final (id, dist) rows, [part][nq][k].
+// Order: (distance, id).
+struct MergeParams {
+    const uint64_t* part_ids;
+    const float* part_dist;
+    uint32_t parts, k, nsort;
+    uint64_t nq;
+    uint64_t* out_ids;
+    float* out_dist;
+    uint32_t* out_counts;
+};
+
+__global__ void __launch_bounds__(128) merge_kernel(MergeParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    // sort (ordered dist, slot) keys, then look ids up by slot: ids are 64-bit and do not fit the key
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
+    const uint64_t q = blockIdx.x;
+    const uint32_t total = p.parts * p.k;
+    // Ties on distance must break on id, not slot: use a two-pass approach -- sort by (dist, id_lo32)
+    // when ids fit 32 bits is not general, so keys carry the slot and ties are fixed up below.
+    for (uint32_t i = threadIdx.x; i < p.nsort; i += blockDim.x) {
+        uint64_t key = KEY_SENTINEL;
+        if (i < total) {
+            uint32_t part = i / p.k, j = i - part * p.k;
+            uint64_t src = (static_cast<uint64_t>(part) * p.nq + q) * p.k + j;
+            if (p.part_ids[src] != 0xFFFFFFFFFFFFFFFFull) key = make_key(p.part_dist[src], i);
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    bitonic_sort_keys<true>(keys, p.nsort, threadIdx.x, blockDim.x);
+    // equal-distance runs: order by id (serial insertion sort inside each run; runs are short)
+    if (threadIdx.x == 0) {
+        uint32_t i = 0;
+        while (i < total && key_idx(keys[i]) != IDX_INVALID) {
+            uint32_t j = i + 1;
+            while (j < total && key_idx(keys[j]) != IDX_INVALID && (keys[j] >> 32) == (keys[i] >> 32)) j++;
+            for (uint32_t a = i + 1; a < j; a++) {
+                uint64_t ka = keys[a];
+                uint32_t sa = key_idx(ka);
+                uint64_t ida = p.part_ids[(static_cast<uint64_t>(sa / p.k) * p.nq + q) * p.k + (sa % p.k)];
+                uint32_t b = a;
+                while (b > i) {
+                    uint32_t sb = key_idx(keys[b - 1]);
+                    uint64_t idb = p.part_ids[(static_cast<uint64_t>(sb / p.k) * p.nq + q) * p.k + (sb % p.k)];
+                    if (idb <= ida) break;
+                    keys[b] = keys[b - 1];
+                    b--;
+                }
+                keys[b] = ka;
+            }
+            i = j;
+        }
+    }
+    __syncthreads();
+    uint32_t my_valid = 0;
+    for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) {
+        uint64_t key = keys[j];
+        uint64_t id = 0xFFFFFFFFFFFFFFFFull;
+        float d = INFINITY;
+        if (key_idx(key) != IDX_INVALID) {
+            uint32_t s = key_idx(key);
+            uint64_t src = (static_cast<uint64_t>(s / p.k) * p.nq + q) * p.k + (s % p.k);
+            id = p.part_ids[src];
+            d = p.part_dist[src];
+            my_valid++;
+        }
+        p.out_ids[q * p.k + j] = id;
+        if (p.out_dist) p.out_dist[q * p.k + j] = d;
+    }
+    if (p.out_counts) {
+        __shared__ uint32_t s_cnt;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        if (my_valid) atomicAdd(&s_cnt, my_valid);
+        __syncthreads();
+        if (threadIdx.x == 0) p.out_counts[q] = s_cnt;
+    }
+}
+
+}  // namespace annb

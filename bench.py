@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the flat / IVF kNN hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload flat|ivf] ...
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one query batch.  Default workload (N = 1) is BASELINE.json
+configs[1]: exhaustive flat f32 cosine, 1M x 128 Correlated synthetic, 10k-query batch, k = 10.
+With N > 1 the database rows are sharded over the ranks (strong scaling: the database is fixed), every rank
+searches its shard for the whole batch, per-shard top-k are all-gathered over NCCL and merged on the device.
+
+Prints ONE JSON line (rank 0).  `value` = whole-job QPS with inputs resident in HBM; `e2e` = the same metric
+through the host-buffer C-ABI call (pinned host queries in, host results out, copies inside the timed region).
+`--impl reference` times the CPU restatement of the reference (oracle/, the one place besides cpu_baseline where
+bench.py executes it) with all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "ann-search-rs_b200", "python")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="flat", choices=["flat", "ivf"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "sq8"])
+    ap.add_argument("--metric", default=None, choices=[None, "cosine", "euclidean"])
+    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--nq", type=int, default=10_000)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--nlist", type=int, default=4096)
+    ap.add_argument("--nprobe", type=int, default=32)
+    ap.add_argument("--path", default="auto", choices=["auto", "simt", "tensor"])
+    ap.add_argument("--cpu-sample", type=int, default=None, help="queries in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--recall", action="store_true", help="also report recall@k vs exact f32 ground truth on a query sample")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- helpers
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def make_data(args):
+    from oracle import datagen
+    kind = "correlated"
+    n = args.n
+    data = datagen.make(kind, n, args.dim, seed=42)
+    queries = datagen.subsample_with_noise(data, args.nq, seed=42)
+    return data, queries, kind
+
+
+def metric_name(args):
+    if args.workload == "flat":
+        return f"QPS flat {args.dtype} {args.metric} k={args.k}"
+    return f"QPS ivf {args.dtype} {args.metric} nlist={args.nlist} nprobe={args.nprobe} k={args.k}"
+
+
+def workload_desc(args, kind, n_gpus):
+    if args.workload == "flat":
+        w = f"exhaustive flat {args.dtype} {args.metric}, {args.n}x{args.dim} {kind} synthetic, {args.nq}-query batch, k={args.k}"
+    else:
+        w = (f"IVF {args.dtype} {args.metric}, {args.n}x{args.dim} {kind} synthetic, nlist={args.nlist}, nprobe={args.nprobe}, "
+             f"{args.nq}-query batch, k={args.k}")
+    return {"workload": w, "n": args.n, "dim": args.dim, "nq": args.nq, "k": args.k,
+            "sharding": ("database rows" if args.workload == "flat" else "inverted lists") + f" over {n_gpus} GPU(s)" if n_gpus > 1 else "none",
+            "l2_policy": "inputs larger than L2 (database streamed every step)"}
+
+
+# ----------------------------------------------------------------------------- oracle-side (CPU) runs
+def oracle_index(args, data):
+    from oracle import oracle as o
+    met = o.COSINE if args.metric == "cosine" else o.L2
+    dt = {"f32": o.F32, "bf16": o.BF16, "sq8": o.SQ8}[args.dtype]
+    if args.workload == "flat":
+        return o.build_flat(data, met, dt)
+    return o.build_ivf(data, met, nlist=args.nlist, dtype=dt, kmeans_iters=4)
+
+
+def oracle_search(args, ix, q):
+    from oracle import oracle as o
+    if args.workload == "flat":
+        return o.flat_search(ix, q, args.k)
+    return o.ivf_search(ix, q, args.k, nprobe=args.nprobe)
+
+
+def cpu_sample_size(args):
+    if args.cpu_sample:
+        return min(args.cpu_sample, args.nq)
+    from oracle import oracle as o
+    cores = o.max_threads()
+    if args.workload == "flat":
+        per_query_s = args.n * args.dim / 3.0e9            # ~3 G element-pairs / s / core (AVX2, memory bound)
+    else:
+        per_query_s = (args.nprobe * args.n / args.nlist + args.nlist) * args.dim / 3.0e9
+    want_core_seconds = 16.0
+    return int(max(cores, min(args.nq, want_core_seconds / max(per_query_s, 1e-9))))
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port: no Rust toolchain exists) on host cores."""
+    from oracle import oracle as o
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    data, queries, kind = make_data(args)
+    ix = oracle_index(args, data)
+    ns = cpu_sample_size(args)
+    q = queries[:ns]
+    cores = o.max_threads()
+    for _ in range(max(1, min(args.warmup, 1))):
+        oracle_search(args, ix, q[:max(cores, 8)])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle_search(args, ix, q)
+    dt = (time.perf_counter() - t0) / args.steps
+    qps = ns / dt
+    line = {"impl": "reference", "metric": metric_name(args), "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_desc(args, kind, args.gpus),
+            "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port",
+                             "sample": f"{ns} of {args.nq} queries per step against the full database (linear in queries)"},
+            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import annb200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    lib = annb200.lib()
+    met = annb200.COSINE if args.metric == "cosine" else annb200.L2
+    dt = {"f32": annb200.F32, "bf16": annb200.BF16, "sq8": annb200.SQ8}[args.dtype]
+    path = {"auto": annb200.PATH_AUTO, "simt": annb200.PATH_SIMT, "tensor": annb200.PATH_TENSOR}[args.path]
+
+    data, queries, kind = make_data(args)
+    n, dim, nq, k = args.n, args.dim, args.nq, args.k
+    algo_bytes_per_query = None
+    if args.workload == "flat":
+        lo, hi = (rank * n) // world, ((rank + 1) * n) // world
+        sq8_scales = annb200.sq8_train(annb200.normalise_rows(data) if met == annb200.COSINE else data) if dt == annb200.SQ8 and world > 1 else None
+        index = annb200.ExhaustiveIndexB200.new(data[lo:hi], met, dt, device=local_rank, id_base=lo, sq8_scales=sq8_scales)
+    else:
+        from oracle import oracle as o   # index *construction* for the bench uses the shared oracle build (setup, not timed)
+        oi = oracle_index(args, data)
+        nl = args.nlist
+        sizes = np.diff(oi.offsets)
+        bounds = [0]
+        target = oi.n / world
+        for r in range(1, world):
+            bounds.append(int(np.searchsorted(oi.offsets, target * r)))
+        bounds.append(nl)
+        lb, le = bounds[rank], bounds[rank + 1]
+        r0, r1 = int(oi.offsets[lb]), int(oi.offsets[le])
+        norms = oi.norms_i if oi.dtype == o.SQ8 else oi.norms
+        index = annb200.IvfIndexB200.from_parts(oi.vectors[r0:r1], oi.centroids, oi.offsets, oi.original_ids[r0:r1], oi.dtype, oi.metric,
+                                                norms=None if norms is None else norms[r0:r1], centroid_norms=oi.centroid_norms,
+                                                sq8_scales=oi.scales, list_begin=lb, list_end=le, device=local_rank, n_total=oi.n)
+        del sizes
+    index.set_option("path", path)
+    index.set_option("time_kernels", 1)
+
+    dq = torch.from_numpy(queries).to(dev)
+    out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    out_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    out_cnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+    if world > 1:
+        g_ids = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+        g_dist = torch.empty((world, nq, k), dtype=torch.float32, device=dev)
+        m_ids = torch.empty_like(out_ids)
+        m_dist = torch.empty_like(out_dist)
+    stream = torch.cuda.current_stream()
+    merge_launches = 0
+
+    def step_device():
+        nonlocal merge_launches
+        sp = stream.cuda_stream
+        if args.workload == "flat":
+            annb200._check(lib.annb_flat_search_dev(index.handle, dq.data_ptr(), nq, dim, k, out_ids.data_ptr(), out_dist.data_ptr(),
+                                                    out_cnt.data_ptr(), sp))
+        else:
+            annb200._check(lib.annb_ivf_search_dev(index.handle, dq.data_ptr(), nq, dim, k, args.nprobe, out_ids.data_ptr(),
+                                                   out_dist.data_ptr(), out_cnt.data_ptr(), sp))
+        if world > 1:
+            dist.all_gather_into_tensor(g_ids.view(-1), out_ids.view(-1))
+            dist.all_gather_into_tensor(g_dist.view(-1), out_dist.view(-1))
+            annb200._check(lib.annb_merge_topk_dev(g_ids.data_ptr(), g_dist.data_ptr(), world, nq, k, m_ids.data_ptr(), m_dist.data_ptr(),
+                                                   None, sp))
+            merge_launches += 1
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+    index.set_option("time_kernels", 1)          # reset the dominant-kernel accumulator after warm-up
+    launches0 = index.get_stat("kernel_launches")
+    merge_launches = 0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    dom_ns = index.get_stat("dominant_kernel_ns")
+    dom_launches = max(1, index.get_stat("dominant_kernel_launches"))
+    launches = index.get_stat("kernel_launches") - launches0 + merge_launches
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    qps = nq / (ms_per_step * 1e-3)
+    last_path = index.get_stat("last_path")
+    scanned = index.get_stat("scanned_vectors") if args.workload == "ivf" else 0
+
+    # ---- end to end through the host-buffer C ABI (pinned host queries, host outputs) ----
+    hq = torch.from_numpy(queries).pin_memory()
+    h_ids = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+    h_dist = torch.empty((nq, k), dtype=torch.float32).pin_memory()
+    h_cnt = torch.empty((nq,), dtype=torch.int32).pin_memory()
+
+    def step_host():
+        if args.workload == "flat":
+            annb200._check(lib.annb_flat_search(index.handle, hq.data_ptr(), nq, dim, k, h_ids.data_ptr(), h_dist.data_ptr(), h_cnt.data_ptr()))
+        else:
+            annb200._check(lib.annb_ivf_search(index.handle, hq.data_ptr(), nq, dim, k, args.nprobe, h_ids.data_ptr(), h_dist.data_ptr(),
+                                               h_cnt.data_ptr()))
+        if world > 1:   # shard results -> device -> all-gather -> merge -> host
+            out_ids.copy_(h_ids, non_blocking=True)
+            out_dist.copy_(h_dist, non_blocking=True)
+            dist.all_gather_into_tensor(g_ids.view(-1), out_ids.view(-1))
+            dist.all_gather_into_tensor(g_dist.view(-1), out_dist.view(-1))
+            annb200._check(lib.annb_merge_topk_dev(g_ids.data_ptr(), g_dist.data_ptr(), world, nq, k, m_ids.data_ptr(), m_dist.data_ptr(),
+                                                   None, stream.cuda_stream))
+            h_ids.copy_(m_ids, non_blocking=True)
+            h_dist.copy_(m_dist, non_blocking=True)
+            torch.cuda.synchronize()
+
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    sync_all()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_qps = nq / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peaks, peak_src = measured_peaks()
+    dom_s = dom_ns * 1e-9 / dom_launches
+    if args.workload == "flat":
+        rows_local = (n + world - 1) // world
+        flops = 2.0 * nq * rows_local * dim                      # algorithmic flops per launch: 2 * nq * n * d
+        if args.dtype == "f32":
+            peak = peaks["bf16_tflops"] / 2.0                    # 3xTF32 runs on the TF32 pipe: measured bf16 / 2
+            peak_note = f"{peak_src} bf16 burst peak / 2 (TF32 pipe)"
+        else:
+            peak = peaks["bf16_tflops"]
+            peak_note = f"{peak_src} bf16 burst peak"
+        achieved = flops / dom_s / 1e12
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "kernel": "flat distance + top-k select", "kernel_ms": dom_s * 1e3, "peak_source": peak_note,
+                    "path": {0: "auto", 1: "simt (CUDA cores)", 2: "tensor (tcgen05)"}.get(last_path, str(last_path))}
+    else:
+        esz = {"f32": 4, "bf16": 2, "sq8": 1}[args.dtype]
+        per_vec = dim * esz + (4 if args.metric == "cosine" else 0)
+        algo_bytes = scanned * per_vec / max(1, 1)               # sum over queries of probed list bytes, last step
+        achieved = algo_bytes / dom_s / 1e9
+        peak = peaks["hbm_gbs"]
+        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "kernel": "ivf list scan", "kernel_ms": dom_s * 1e3, "peak_source": f"{peak_src} copy bandwidth",
+                    "algorithmic_bytes_per_launch": algo_bytes}
+        algo_bytes_per_query = algo_bytes / nq
+
+    line = {"metric": metric_name(args), "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": {"f32": "f32 (3xTF32 select + f32 exact re-rank)" if last_path == 2 else "f32", "bf16": "bf16 (f32 accumulate)",
+                      "sq8": "int8 (i32 accumulate)"}[args.dtype],
+            "data": "synthetic", "config": workload_desc(args, kind, world), "clocks": clocks,
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * dim * 4),
+                    "d2h_bytes_per_step": int(nq * k * 12 + nq * 4), "ms_per_step": e2e_s * 1e3},
+            "gpu_launches": int(launches), "roofline": roofline}
+    if algo_bytes_per_query is not None:
+        line["config"]["algorithmic_bytes_per_query"] = algo_bytes_per_query
+
+    # ---- parity spot check + recall on a query sample (outside the timed region) ----
+    if args.recall or True:
+        from oracle import oracle as o
+        ns = min(64, nq)
+        if world == 1:
+            oi2 = oracle_index(args, data) if args.workload == "flat" else oi
+            ref = oracle_search(args, oi2, queries[:ns])
+            got_ids = h_ids[:ns].numpy()
+            got_d = h_dist[:ns].numpy()
+            line["parity_sample"] = {"queries": ns, "ids_equal": bool(np.array_equal(got_ids, ref[0])),
+                                     "dist_bits_equal": bool(np.array_equal(got_d.view(np.uint32), ref[1].view(np.uint32)))}
+            if args.workload == "ivf" or args.dtype != "f32":
+                exact = o.flat_search(o.build_flat(data, o.COSINE if args.metric == "cosine" else o.L2), queries[:ns], k)
+                line["recall_at_k_vs_exact_f32"] = o.recall_at_k(exact[0], got_ids, k)
+
+    # ---- CPU baseline on this host's cores (bounded sample) ----
+    if not args.no_cpu_baseline:
+        from oracle import oracle as o
+        oi3 = oracle_index(args, data) if args.workload == "flat" else oi
+        ns = cpu_sample_size(args)
+        cores = o.max_threads()
+        oracle_search(args, oi3, queries[:max(8, min(ns, cores))])
+        t0 = time.perf_counter()
+        oracle_search(args, oi3, queries[:ns])
+        dtc = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": ns / dtc, "unit": "queries/s", "cores": cores, "kind": "port",
+                                "sample": f"{ns} of {nq} queries against the full database, {dtc:.2f} s wall (QPS is linear in queries)"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.metric is None:
+        args.metric = "cosine" if args.workload == "flat" else "euclidean"
+    if args.n is None:
+        args.n = 1_000_000 if args.workload == "flat" else 10_000_000
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

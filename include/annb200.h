@@ -1,0 +1,206 @@
+/*
+ * annb200.h -- C ABI of libannb200: B200 (sm_100a) flat and IVF kNN search.
+ *
+ * This is the drop-in boundary for the data-parallel search hot path of
+ * GregorLueg/ann-search-rs.  The reference has no FFI of its own: the seam is
+ * the `*_gpu` family of free functions in src/lib.rs:2813-3002 whose device is a
+ * CubeCL `R::Device` type parameter, plus the BF16 / SQ8 twins in
+ * src/lib.rs:1702-1871 and 2100-2290.  Each entry point below names the
+ * reference item it replaces (paths relative to the reference crate root).
+ * INTEGRATION.md shows the Rust `extern "C"` block and the safe wrappers that
+ * keep the crate's build_and query_ signatures on top of these symbols.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross the boundary;
+ *   - every function returns an annb_status (0 = OK, negative = error class that
+ *     maps 1:1 onto a variant of AnnSearchErrors, src/errors.rs); the message of
+ *     the last failure on the calling thread is available via annb_last_error();
+ *   - host-buffer entry points (`annb_*_search`) accept pageable or pinned host
+ *     memory, or device memory (resolved through UVA);
+ *   - `_dev` entry points take device pointers and a cudaStream_t (as void*)
+ *     and are asynchronous with respect to the host;
+ *   - results: `out_ids` is [nq * k] uint64, `out_dist` is [nq * k] float
+ *     (may be NULL = return_dist false), `out_counts` [nq] uint32 (may be NULL).
+ *     Row i holds counts[i] = min(k, reachable) valid entries in ascending
+ *     (distance, id-within-index) order; the tail is padded with
+ *     id = UINT64_MAX, dist = +inf.  Distances are squared Euclidean, or
+ *     1 - cos; SQ8 distances are in code space (src/utils/dist.rs:5015-5077);
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point
+ *     returns ANNB_ERR_CUDA.
+ */
+#ifndef ANNB200_H
+#define ANNB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ANNB_VERSION_MAJOR 0
+#define ANNB_VERSION_MINOR 1
+
+typedef struct annb_index annb_index; /* opaque; device memory is owned by the library */
+
+/* Storage type of the database vectors (queries are always f32 at the ABI). */
+enum annb_dtype {
+    ANNB_F32 = 0,  /* ExhaustiveIndex / IvfIndex              (src/cpu/exhaustive.rs, src/cpu/ivf.rs)        */
+    ANNB_BF16 = 1, /* ExhaustiveIndexBf16 / IvfIndexBf16      (src/quantised/{exhaustive,ivf}_bf16.rs)       */
+    ANNB_SQ8 = 2   /* ExhaustiveSq8Index / IvfSq8Index        (src/quantised/{exhaustive,ivf}_sq8.rs)        */
+};
+
+/* Dist::{SquaredEuclidean, Cosine} (src/utils/dist.rs:29-37).  Manhattan is rejected
+ * by every GPU / quantised / IVF constructor of the reference
+ * (src/gpu/exhaustive_gpu.rs:73-75, src/cpu/ivf.rs:153-155) and here. */
+enum annb_metric { ANNB_L2 = 0, ANNB_COSINE = 1, ANNB_MANHATTAN = 2 };
+
+enum annb_status {
+    ANNB_OK = 0,
+    ANNB_ERR_DIMENSION_MISMATCH = -1,     /* AnnSearchErrors::DimensionMismatch         src/errors.rs:23  */
+    ANNB_ERR_DISTANCE_NOT_SUPPORTED = -2, /* AnnSearchErrors::DistanceNotSupported      src/errors.rs:32  */
+    ANNB_ERR_TOO_FEW_SAMPLES = -3,        /* AnnSearchErrors::TooFewSamplesForCentroids src/errors.rs:90  */
+    ANNB_ERR_INVALID_ARGUMENT = -4,       /* null pointer, n == 0, unsupported k / nlist                 */
+    ANNB_ERR_CUDA = -5,                   /* replaces CubeClServerError / CubeclUtils   src/errors.rs:212-223 */
+    ANNB_ERR_NCCL = -6,
+    ANNB_ERR_OUT_OF_MEMORY = -7,
+    ANNB_ERR_UNSUPPORTED = -8             /* e.g. DimTooHighForSharedMemory             src/errors.rs:231 */
+};
+
+/* Search-path selector (annb_index_set_option "path"). */
+enum annb_path { ANNB_PATH_AUTO = 0, ANNB_PATH_SIMT = 1, ANNB_PATH_TENSOR = 2 };
+
+const char* annb_last_error(void);
+int annb_version(void); /* major * 1000 + minor */
+int annb_device_count(int* out);
+
+/* parse_ann_dist (src/utils/dist.rs:63-70): "euclidean"|"l2", "cosine", "manhattan"|"l1",
+ * case-insensitive.  Returns the annb_metric, or -1 for an unknown string (the reference's
+ * free functions then warn and fall back to L2, src/lib.rs:274-277 -- that policy stays on
+ * the caller's side). */
+int annb_parse_metric(const char* s);
+
+/* ------------------------------------------------------------------ flat -- */
+
+/* Replaces ExhaustiveIndexGpu::new (src/gpu/exhaustive_gpu.rs:72-110), and for dtype BF16 / SQ8
+ * ExhaustiveIndexBf16::new (src/quantised/exhaustive_bf16.rs:94-121) and ExhaustiveSq8Index::new
+ * (src/quantised/exhaustive_sq8.rs:104-151).  `data` is the row-major f32 matrix that
+ * matrix_to_flat (src/utils/mod.rs:44-68) produces; norms, BF16 rounding and SQ8
+ * normalise/train/encode run on the device with the reference's arithmetic.
+ * `sq8_scales` (dim floats) may be given to reuse a codebook (shards of one index); NULL trains
+ * on `data`.  `id_base` is added to every returned id (row-range shards).  The database stays
+ * resident on `device` for the life of the handle (the reference re-uploads it per call,
+ * src/gpu/dist_gpu.rs:662). */
+int annb_flat_create(annb_index** out, const float* data, uint64_t n, uint32_t dim, int dtype, int metric,
+                     const float* sq8_scales, uint64_t id_base, int device);
+
+/* Replaces ExhaustiveIndexGpu::query_batch (src/gpu/exhaustive_gpu.rs:124-162) /
+ * query_exhaustive_index_gpu (src/lib.rs:2842) and the BF16 / SQ8 query paths
+ * (src/lib.rs:1733, 1818).  queries: [nq * dim] f32 row-major. */
+int annb_flat_search(const annb_index* index, const float* queries, uint64_t nq, uint32_t dim, uint32_t k,
+                     uint64_t* out_ids, float* out_dist, uint32_t* out_counts);
+
+/* Replaces ExhaustiveIndexGpu::generate_knn (src/gpu/exhaustive_gpu.rs:179-198) and the
+ * generate_knn of the CPU / BF16 / SQ8 flat indices: every stored row queries the index
+ * (self included at rank 0).  Outputs are [n * k].  With row_begin/row_end a sub-range of rows
+ * acts as the query set (outputs [(row_end-row_begin) * k]); pass 0, n for the whole index. */
+int annb_flat_search_self(const annb_index* index, uint64_t row_begin, uint64_t row_end, uint32_t k,
+                          uint64_t* out_ids, float* out_dist, uint32_t* out_counts);
+
+/* Device-pointer variants (inputs already resident in HBM; asynchronous on `stream`). */
+int annb_flat_search_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k,
+                         uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, void* stream);
+
+/* ------------------------------------------------------------------- IVF -- */
+
+/* Coarse assignment used by the IVF constructors: replaces assign_all_gpu
+ * (src/gpu/k_means_gpu.rs:2658-2726) / assign_all_parallel (src/utils/k_means_utils.rs:2214-2241):
+ * argmax_c 2 x.c - |c|^2 (L2) or x.c / |c| (cosine), lowest centroid id on ties.
+ * data [n*dim], centroids [nlist*dim] (host or device), out_assign [n] uint32 (host).
+ * centroid_norms [nlist] is what the caller of direct_assign passes (cosine only): the
+ * sequential-fold norms of IvfIndex::build (src/cpu/ivf.rs:193-206) or all ones for the SQ8
+ * index (src/quantised/ivf_sq8.rs:214-215); NULL computes the former on the device. */
+int annb_ivf_assign(const float* data, uint64_t n, uint32_t dim, const float* centroids,
+                    const float* centroid_norms, uint32_t nlist, int metric, uint32_t* out_assign, int device);
+
+/* Builds a resident IVF index from the contents of the reference's index struct after
+ * optimise_memory_layout (src/cpu/ivf.rs:25-48, 257-294; src/quantised/ivf_bf16.rs,
+ * src/quantised/ivf_sq8.rs): vectors in list order in the index dtype (f32 / bf16 bit patterns /
+ * int8 codes), per-vector norms (f32 for F32+BF16 cosine, int32 sum-of-squares for SQ8 cosine;
+ * NULL for L2), f32 centroids (+ norms for cosine F32/BF16; NULL otherwise), CSR offsets
+ * [nlist+1], original_ids [n] (list order -> original row), SQ8 scales [dim].
+ * Sharding: `list_begin..list_end` is the range of lists whose vectors this handle stores
+ * (`vectors`, `norms`, `original_ids` then hold only rows offsets[list_begin]..offsets[list_end]);
+ * offsets always describe the whole index so probe expansion sees global list sizes.
+ * Pass 0, nlist for an unsharded index. */
+int annb_ivf_create(annb_index** out, const void* vectors, const void* norms, const float* centroids,
+                    const float* centroid_norms, const uint64_t* offsets, const uint64_t* original_ids,
+                    uint64_t n, uint32_t dim, uint32_t nlist, int dtype, int metric, const float* sq8_scales,
+                    uint32_t list_begin, uint32_t list_end, int device);
+
+/* Replaces IvfIndexGpu::query_batch (src/gpu/ivf_gpu.rs:466-503) / query_ivf_index_gpu
+ * (src/lib.rs:2949) and IvfIndex / IvfIndexBf16 / IvfSq8Index::query
+ * (src/cpu/ivf.rs:337-390, src/quantised/ivf_bf16.rs:277-332, src/quantised/ivf_sq8.rs:303-359).
+ * nprobe == 0 means None -> max(1, floor(sqrt(nlist))); nprobe is a floor: probing expands in
+ * centroid-rank order until k vectors are reachable (src/utils/k_means_utils.rs:3007-3029). */
+int annb_ivf_search(const annb_index* index, const float* queries, uint64_t nq, uint32_t dim, uint32_t k,
+                    uint32_t nprobe, uint64_t* out_ids, float* out_dist, uint32_t* out_counts);
+
+/* Replaces IvfIndexGpu::generate_knn (src/gpu/ivf_gpu.rs:520-583) and the generate_knn of the
+ * CPU / BF16 / SQ8 IVF indices.  Query set = stored rows in list order positions
+ * [pos_begin, pos_end); output row j belongs to internal position pos_begin + j, unless
+ * `scatter_to_original` is non-zero, in which case outputs are [n * k] and row r belongs to
+ * original id r (src/cpu/ivf.rs:476-486).  Unsharded indices only. */
+int annb_ivf_search_self(const annb_index* index, uint64_t pos_begin, uint64_t pos_end, uint32_t k,
+                         uint32_t nprobe, int scatter_to_original, uint64_t* out_ids, float* out_dist,
+                         uint32_t* out_counts);
+
+int annb_ivf_search_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k,
+                        uint32_t nprobe, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
+                        void* stream);
+
+/* ---------------------------------------------------------------- shared -- */
+
+/* Multi-GPU exchange step: merges `parts` per-shard results (each [nq * k], laid out
+ * [part][query][k], padded as described above) into one [nq * k] result under the
+ * (distance, id) order.  Device pointers; runs on `stream`.  The all-gather that fills
+ * d_part_* is NCCL's (torch.distributed / ncclAllGather) -- see DESIGN.md. */
+int annb_merge_topk_dev(const uint64_t* d_part_ids, const float* d_part_dist, uint32_t parts, uint64_t nq,
+                        uint32_t k, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
+                        void* stream);
+
+/* Index facts: ExhaustiveIndexGpu::memory_usage_bytes (src/gpu/exhaustive_gpu.rs:205-209),
+ * IvfIndexGpu::memory_usage_bytes (src/gpu/ivf_gpu.rs:590-604). */
+typedef struct annb_index_info {
+    uint64_t n;          /* vectors stored by this handle            */
+    uint64_t n_total;    /* vectors of the whole (unsharded) index   */
+    uint32_t dim;
+    uint32_t nlist;      /* 0 for a flat index                       */
+    int32_t dtype;
+    int32_t metric;
+    int32_t device;
+    int32_t is_ivf;
+    uint64_t device_bytes; /* HBM held by the handle                 */
+    uint64_t host_bytes;
+} annb_index_info;
+int annb_index_get_info(const annb_index* index, annb_index_info* out);
+
+/* Tunables / instrumentation.
+ *   set_option: "path" (annb_path), "tc_candidates" (k' of the tensor-core pre-selection),
+ *               "db_splits" (flat: database splits per query tile, 0 = auto),
+ *               "scan_parts" (IVF: partial scans per query, 0 = auto),
+ *               "time_kernels" (1 = bracket the dominant kernel of every search with CUDA events on its stream)
+ *   get_stat  : "kernel_launches" (cumulative), "scanned_vectors" (IVF, last call: sum of probed
+ *               list lengths), "probed_lists" (last call), "last_path" (annb_path actually used),
+ *               "uncertified" (tensor path, last call: queries that took the exact fallback),
+ *               "dominant_kernel_ns" / "dominant_kernel_launches" (with "time_kernels": summed device time and count
+ *               of the dominant kernel -- flat distance+select kernel or IVF list-scan kernel -- since the option was set) */
+int annb_index_set_option(annb_index* index, const char* key, int64_t value);
+int annb_index_get_stat(const annb_index* index, const char* key, int64_t* out);
+
+void annb_destroy(annb_index* index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANNB200_H */

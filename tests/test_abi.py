@@ -1,0 +1,93 @@
+"""The C-ABI library loads, exports every symbol include/annb200.h declares, and refuses to
+compute without a GPU (no CPU fallback).  CPU only -- no compute calls."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "annb200.h")
+
+
+def _declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(annb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = _declared_symbols()
+    for s in ["annb_flat_create", "annb_flat_search", "annb_flat_search_self", "annb_flat_search_dev", "annb_ivf_assign",
+              "annb_ivf_create", "annb_ivf_search", "annb_ivf_search_self", "annb_ivf_search_dev", "annb_merge_topk_dev",
+              "annb_destroy", "annb_last_error", "annb_index_get_info", "annb_index_set_option", "annb_index_get_stat"]:
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol():
+    import annb200
+    lib = annb200.lib()
+    for s in _declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/annb200.h but not exported"
+
+
+def test_header_compiles_as_c_and_cpp():
+    for comp, lang in (("gcc", "c"), ("g++", "c++")):
+        r = subprocess.run([f"/usr/bin/{comp}", "-x", lang, "-fsyntax-only", "-Wall", "-Werror", HEADER], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_parse_metric_matches_parse_ann_dist():
+    import annb200
+    # src/utils/dist.rs:63-70
+    assert annb200.parse_ann_dist("euclidean") == annb200.L2 and annb200.parse_ann_dist("L2") == annb200.L2
+    assert annb200.parse_ann_dist("Cosine") == annb200.COSINE
+    assert annb200.parse_ann_dist("manhattan") == annb200.MANHATTAN and annb200.parse_ann_dist("l1") == annb200.MANHATTAN
+    assert annb200.parse_ann_dist("chebyshev") is None
+
+
+def test_argument_errors_do_not_need_a_device():
+    import annb200
+    x = np.zeros((4, 3), np.float32)
+    with pytest.raises(annb200.AnnSearchError) as e:
+        annb200.ExhaustiveIndexB200.new(x, annb200.MANHATTAN)
+    assert e.value.variant == "DistanceNotSupported"          # src/gpu/exhaustive_gpu.rs:73-75
+    with pytest.raises(annb200.AnnSearchError) as e:
+        annb200.ExhaustiveIndexB200.new(np.zeros((0, 3), np.float32), annb200.L2)
+    assert e.value.variant == "InvalidArgument"
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must fail loudly, never compute on the host."""
+    import annb200
+    try:
+        n = annb200.device_count()
+    except annb200.AnnSearchError:
+        n = 0
+    if n > 0:
+        pytest.skip("a GPU is present; the no-device behaviour is exercised on the CPU box")
+    with pytest.raises(annb200.AnnSearchError) as e:
+        annb200.build_exhaustive_index_gpu(np.zeros((4, 3), np.float32))
+    assert e.value.variant == "Cuda"
+    with pytest.raises(annb200.AnnSearchError) as e:
+        annb200.ivf_assign(np.zeros((4, 3), np.float32), np.zeros((2, 3), np.float32), annb200.L2)
+    assert e.value.variant == "Cuda"
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under the product tree may reference it."""
+    prod = os.path.join(ROOT, "ann-search-rs_b200")
+    hits = []
+    for dp, _, fs in os.walk(prod):
+        if os.sep + "build" in dp or os.sep + "lib" in dp:
+            continue
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp", ".rs")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                if re.search(r"\boracle\b", txt) and "oracle/oracle.c)" not in txt:
+                    for line in txt.splitlines():
+                        if re.search(r"\b(import|include|from)\b.*\boracle\b", line):
+                            hits.append((f, line.strip()))
+    assert not hits, hits

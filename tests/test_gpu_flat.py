@@ -1,0 +1,135 @@
+"""GPU parity: flat (exhaustive) search through the C ABI against the CPU oracle.
+Exact path (PATH_SIMT): bit-identical distances and identical ids for f32 / BF16 / SQ8, L2 / cosine,
+external and self queries, ragged sizes, k > n, the reference's own fixtures."""
+import numpy as np
+import pytest
+
+import annb200
+from oracle import datagen, oracle as o
+from util import assert_exact, assert_tolerance
+
+pytestmark = pytest.mark.gpu
+
+SIMPLE = np.array([[1, 0, 0], [0, 1, 0], [0, 0, 1], [1, 1, 0], [1, 0, 1]], dtype=np.float32)
+DT = {"f32": (annb200.F32, o.F32), "bf16": (annb200.BF16, o.BF16), "sq8": (annb200.SQ8, o.SQ8)}
+MET = {"l2": (annb200.L2, o.L2), "cosine": (annb200.COSINE, o.COSINE)}
+
+
+def _pair(data, dtype, metric, path=annb200.PATH_SIMT):
+    g = annb200.ExhaustiveIndexB200.new(data, MET[metric][0], DT[dtype][0])
+    g.set_option("path", path)
+    return g, o.build_flat(data, MET[metric][1], DT[dtype][1])
+
+
+def test_simple_matrix_known_answers(gpu):
+    # src/cpu/exhaustive.rs:319-533
+    g, _ = _pair(SIMPLE, "f32", "cosine")
+    ids, d, cnt = g.query_batch(np.array([[1, 0, 0]], np.float32), 5)
+    assert ids[0, 0] == 0
+    np.testing.assert_allclose(d[0], [0, 1 - 2 ** -0.5, 1 - 2 ** -0.5, 1, 1], atol=1e-5)
+    g, _ = _pair(SIMPLE, "f32", "l2")
+    ids, d, cnt = g.query_batch(np.array([[1, 0, 0]], np.float32), 10)   # k > n
+    assert cnt[0] == 5 and (ids[0, 5:] == -1).all() and np.isinf(d[0, 5:]).all()
+    np.testing.assert_allclose(d[0, :5], [0, 1, 1, 2, 2], atol=1e-6)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "sq8"])
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("n,dim,nq,k", [(5000, 32, 257, 15), (1237, 50, 33, 10), (3000, 128, 64, 10), (700, 7, 5, 31), (40, 3, 3, 64)])
+def test_exact_parity_external_queries(gpu, dtype, metric, n, dim, nq, k):
+    data = datagen.gaussian_noise(n, dim, seed=7)
+    q = datagen.subsample_with_noise(data, nq, seed=7)
+    g, c = _pair(data, dtype, metric)
+    ids, d, cnt = g.query_batch(q, k)
+    rids, rd, rcnt = o.flat_search(c, q, k)
+    assert np.array_equal(cnt, rcnt)
+    assert_exact(ids, d, rids, rd, f"flat {dtype} {metric} n={n} dim={dim}")
+    assert g.get_stat("last_path") == annb200.PATH_SIMT
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "sq8"])
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_exact_parity_self_queries(gpu, dtype, metric):
+    data = datagen.correlated(2000, 50, seed=3)
+    g, c = _pair(data, dtype, metric)
+    ids, d, cnt = g.generate_knn(15)
+    rids, rd, rcnt = o.flat_search(c, None, 15, self_mode=True)
+    assert_exact(ids, d, rids, rd, f"flat self {dtype} {metric}")
+    # sub-range of rows as the query set
+    ids, d, cnt = g.generate_knn(5, row_begin=100, row_end=164)
+    rids, rd, _ = o.flat_search(c, None, 5, self_rows=np.arange(100, 164), self_mode=True)
+    assert_exact(ids, d, rids, rd, f"flat self sub-range {dtype} {metric}")
+
+
+def test_config1_full_size_matches_oracle(gpu):
+    """BASELINE config 1: flat f32 L2, 50k x 32 GaussianNoise, 1k queries, k = 15."""
+    data = datagen.gaussian_noise(50_000, 32)
+    q = datagen.subsample_with_noise(data, 1000)
+    g, c = _pair(data, "f32", "l2")
+    ids, d, _ = g.query_batch(q, 15)
+    rids, rd, _ = o.flat_search(c, q, 15)
+    assert_exact(ids, d, rids, rd, "config 1")
+    assert_tolerance(ids, d, rids, rd, what="config 1 (tolerance form)")
+
+
+def test_formula_fixture_and_ties(gpu):
+    # src/gpu/dist_gpu.rs:1443-1583 data; src/gpu/topk_gpu.rs heavy-ties / all-duplicates order
+    nq, ndb, dim, k = 10, 50, 8, 5
+    q = np.array([((i * 13 + 7) % 29) * 0.1 for i in range(nq * dim)], np.float32).reshape(nq, dim)
+    db = np.array([((i * 17 + 3) % 31) * 0.1 for i in range(ndb * dim)], np.float32).reshape(ndb, dim)
+    for metric in ("l2", "cosine"):
+        g, c = _pair(db, "f32", metric)
+        assert_exact(*g.query_batch(q, k)[:2], *o.flat_search(c, q, k)[:2], f"formula {metric}")
+    vals = np.array([(i % 8) * 0.5 for i in range(512)], np.float32)[:, None]      # heavy ties
+    g, c = _pair(vals, "f32", "l2")
+    assert_exact(*g.query_batch(np.zeros((1, 1), np.float32), 40)[:2], *o.flat_search(c, np.zeros((1, 1), np.float32), 40)[:2], "ties")
+    same = np.full((256, 4), 0.5, np.float32)                                      # all duplicates: ids 0..k-1
+    g, _ = _pair(same, "f32", "l2")
+    ids, d, _ = g.query_batch(np.zeros((2, 4), np.float32), 30)
+    assert (ids == np.arange(30)[None, :]).all()
+
+
+def test_large_k_and_id_base(gpu):
+    data = datagen.gaussian_noise(3000, 16, seed=11)
+    q = datagen.subsample_with_noise(data, 9, seed=11)
+    g = annb200.ExhaustiveIndexB200.new(data, annb200.L2, annb200.F32, id_base=1000)
+    g.set_option("path", annb200.PATH_SIMT)
+    c = o.build_flat(data, o.L2)
+    for k in (1, 100, 250):
+        ids, d, _ = g.query_batch(q, k)
+        rids, rd, _ = o.flat_search(c, q, k)
+        assert_exact(ids - 1000, d, rids, rd, f"k={k}")
+
+
+def test_errors(gpu):
+    g, _ = _pair(SIMPLE, "f32", "l2")
+    with pytest.raises(annb200.AnnSearchError) as e:
+        g.query_batch(np.zeros((2, 4), np.float32), 1)
+    assert e.value.variant == "DimensionMismatch"
+    with pytest.raises(annb200.AnnSearchError) as e:
+        annb200.ExhaustiveIndexB200.new(SIMPLE, annb200.MANHATTAN)
+    assert e.value.variant == "DistanceNotSupported"
+    ids, d, cnt = g.query_batch(np.zeros((0, 3), np.float32), 3)     # empty query set
+    assert ids.shape == (0, 3)
+
+
+def test_determinism(gpu):
+    data = datagen.gaussian_noise(4000, 32, seed=5)
+    q = datagen.subsample_with_noise(data, 100, seed=5)
+    g, _ = _pair(data, "sq8", "l2")
+    a = g.query_batch(q, 20)
+    b = g.query_batch(q, 20)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+
+
+def test_mirror_free_functions(gpu):
+    data = datagen.gaussian_noise(1000, 32, seed=9)
+    q = datagen.subsample_with_noise(data, 20, seed=9)
+    ix = annb200.build_exhaustive_index_gpu(data, "euclidean")
+    ids, dist = annb200.query_exhaustive_index_gpu(q, ix, 5, return_dist=True)
+    ids2, none = annb200.query_exhaustive_index_gpu(q, ix, 5, return_dist=False)
+    assert none is None and np.array_equal(ids, ids2)
+    ids, dist = annb200.query_exhaustive_index_gpu_self(ix, 3)
+    assert (ids[:, 0] == np.arange(1000)).all()
+    ram, vram = ix.memory_usage_bytes()
+    assert vram >= 1000 * 32 * 4
