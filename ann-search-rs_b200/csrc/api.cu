@@ -771,11 +771,21 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     std::string k(key);
     if (k == "path") { if (value < 0 || value > 2) return fail(ANNB_ERR_INVALID_ARGUMENT, "path must be 0..2"); ix->opt_path = static_cast<int>(value); }
     else if (k == "tc_candidates") ix->opt_tc_candidates = static_cast<int>(value);
+    else if (k == "tc_debug") { DeviceGuard g(ix->device); return tc_debug_enable(ix, value != 0); }
     else if (k == "db_splits") ix->opt_db_splits = static_cast<int>(value);
     else if (k == "scan_parts") ix->opt_scan_parts = static_cast<int>(value);
     else if (k == "time_kernels") { ix->opt_time_kernels = static_cast<int>(value); ix->timed_ms_total = 0.0; ix->timed_launches = 0; }
     else return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown option " + k);
     return ANNB_OK;
+}
+
+int annb_debug_fetch_tile(annb_index* ix, float* host_out) {
+    if (!ix || !host_out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard g(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    int rc = tc_debug_fetch(ix, host_out);
+    if (rc != ANNB_OK && rc != ANNB_ERR_CUDA) set_last_error("tc_debug is not enabled on this index");
+    return rc;
 }
 
 int annb_index_get_stat(const annb_index* ix, const char* key, int64_t* out) {

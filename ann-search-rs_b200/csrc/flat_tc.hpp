@@ -16,5 +16,8 @@ bool tc_flat_supported(const annb_index* ix, int qt, uint32_t k_eff);
 int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt, int bf16_self, uint64_t nq, uint32_t k_eff,
                    uint32_t k_out, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s);
 void tc_destroy(annb_index* ix);
+// Test hooks: CTA (0,0) of the tensor kernel dumps the 128 x 128 values of its first tile.
+int tc_debug_enable(annb_index* ix, bool on);
+int tc_debug_fetch(annb_index* ix, float* host_out);
 
 }  // namespace annb

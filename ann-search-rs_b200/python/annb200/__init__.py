@@ -87,6 +87,7 @@ def lib():
         _lib.annb_destroy.argtypes = [vp]
         _lib.annb_destroy.restype = None
         _lib.annb_device_count.argtypes = [C.POINTER(C.c_int)]
+        _lib.annb_debug_fetch_tile.argtypes = [vp, vp]
     return _lib
 
 
@@ -164,6 +165,11 @@ class _IndexBase:
         v = C.c_int64(0)
         _check(lib().annb_index_get_stat(self._h, key.encode(), C.byref(v)))
         return int(v.value)
+
+    def debug_fetch_tile(self) -> np.ndarray:
+        out = np.empty((128, 128), dtype=np.float32)
+        _check(lib().annb_debug_fetch_tile(self._h, _ptr(out)))
+        return out
 
     def close(self):
         if self._h is not None:

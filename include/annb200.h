@@ -198,6 +198,10 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
 int annb_index_set_option(annb_index* index, const char* key, int64_t value);
 int annb_index_get_stat(const annb_index* index, const char* key, int64_t* out);
 
+/* Diagnostics (tests only): with option "tc_debug" = 1 the first CTA of the tensor-core flat kernel dumps the
+ * 128 x 128 selection values v = fma(q.x, a, b) of its first tile; this copies them to host_out[128 * 128]. */
+int annb_debug_fetch_tile(annb_index* index, float* host_out);
+
 void annb_destroy(annb_index* index);
 
 #ifdef __cplusplus

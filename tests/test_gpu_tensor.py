@@ -1,0 +1,92 @@
+"""GPU parity of the tensor-core flat path (tcgen05 / TMEM / TMA pre-selection + exact re-rank).
+The re-rank recomputes the k' survivors in the reference's own arithmetic, so results must be
+bit-identical to the oracle whenever the pre-selection covers the true top-k."""
+import numpy as np
+import pytest
+
+import annb200
+from oracle import datagen, oracle as o
+from util import assert_exact, assert_tolerance
+
+pytestmark = pytest.mark.gpu
+
+DT = {"f32": (annb200.F32, o.F32), "bf16": (annb200.BF16, o.BF16)}
+MET = {"l2": (annb200.L2, o.L2), "cosine": (annb200.COSINE, o.COSINE)}
+
+
+def _pair(data, dtype, metric):
+    g = annb200.ExhaustiveIndexB200.new(data, MET[metric][0], DT[dtype][0])
+    g.set_option("path", annb200.PATH_TENSOR)
+    return g, o.build_flat(data, MET[metric][1], DT[dtype][1])
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("dim", [128, 32, 50])
+def test_first_tile_values_match_a_float64_gemm(gpu, dtype, metric, dim):
+    """The selection value of tile (0,0): v = |x|^2 - 2 q.x (L2) or -q.x/|x| (cosine)."""
+    data = datagen.gaussian_noise(8192, dim, seed=3)
+    q = datagen.subsample_with_noise(data, 128, seed=3)
+    g, c = _pair(data, dtype, metric)
+    g.set_option("tc_debug", 1)
+    g.set_option("db_splits", 1)
+    g.query_batch(q, 10)
+    v = g.debug_fetch_tile().astype(np.float64)
+    x = (o.decode_bf16(c.vectors[:128]) if dtype == "bf16" else data[:128]).astype(np.float64)
+    s = q.astype(np.float64) @ x.T
+    if metric == "l2":
+        want = (x * x).sum(1)[None, :] - 2 * s
+    else:
+        want = -s / c.norms[:128].astype(np.float64)[None, :]
+    scale = np.abs(want).max()
+    err = np.abs(v - want).max() / scale
+    assert err < 2e-6, f"tile error {err:.3e} (3xTF32 / bf16x3 should be ~1e-7)"
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("n,dim,nq,k", [(20000, 128, 300, 10), (9000, 32, 129, 15), (5000, 50, 64, 10), (4100, 96, 7, 1)])
+def test_exact_parity_with_oracle(gpu, dtype, metric, n, dim, nq, k):
+    data = datagen.gaussian_noise(n, dim, seed=19)
+    q = datagen.subsample_with_noise(data, nq, seed=19)
+    g, c = _pair(data, dtype, metric)
+    ids, d, cnt = g.query_batch(q, k)
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    rids, rd, rcnt = o.flat_search(c, q, k)
+    assert_exact(ids, d, rids, rd, f"tensor flat {dtype} {metric} n={n} dim={dim} k={k}")
+    for splits in (1, 3):
+        g.set_option("db_splits", splits)
+        ids, d, cnt = g.query_batch(q, k)
+        assert_exact(ids, d, rids, rd, f"tensor flat db_splits={splits}")
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_self_queries(gpu, dtype):
+    data = datagen.correlated(6000, 64, seed=23)
+    g, c = _pair(data, dtype, "cosine")
+    ids, d, _ = g.generate_knn(10, row_begin=0, row_end=1000)
+    rids, rd, _ = o.flat_search(c, None, 10, self_rows=np.arange(1000), self_mode=True)
+    assert_exact(ids, d, rids, rd, f"tensor self {dtype}")
+
+
+def test_correlated_cosine_hard_case(gpu):
+    """BASELINE config 2 at reduced n: Correlated data, cosine -- nearest-neighbour gaps ~1e-6, the case 3xTF32 exists for."""
+    data = datagen.correlated(100_000, 128, seed=42)
+    q = datagen.subsample_with_noise(data, 1000, seed=42)
+    g, c = _pair(data, "f32", "cosine")
+    ids, d, _ = g.query_batch(q, 10)
+    rids, rd, _ = o.flat_search(c, q, 10)
+    assert_tolerance(ids, d, rids, rd, what="correlated cosine (tolerance contract)")
+    assert_exact(ids, d, rids, rd, "correlated cosine")
+
+
+def test_tensor_equals_simt_at_scale(gpu):
+    """Size-independent property at a size the oracle would not finish quickly: both GPU paths agree bit for bit."""
+    data = datagen.gaussian_noise(300_000, 128, seed=8)
+    q = datagen.subsample_with_noise(data, 2000, seed=8)
+    g = annb200.ExhaustiveIndexB200.new(data, annb200.L2, annb200.F32)
+    g.set_option("path", annb200.PATH_TENSOR)
+    a = g.query_batch(q, 10)
+    g.set_option("path", annb200.PATH_SIMT)
+    b = g.query_batch(q, 10)
+    assert_exact(a[0], a[1], b[0], b[1], "tensor vs simt")
