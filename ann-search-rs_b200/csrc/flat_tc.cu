@@ -50,6 +50,7 @@ struct Params {
     uint32_t a_pieces;        // query terms actually present (bf16 self query: 1)
     const float2* aux;        // per database row: v = fma(s, aux.x, aux.y)  (L2: -2, |x|^2; cosine: -1/|x|, 0; pad: 0, +inf)
     uint64_t* part_keys;      // [nq][n_splits][KPRIME] packed (approx value, row)
+    uint32_t* gtau;           // [nq_pad] shared pruning threshold per query (order-preserving image, atomicMin)
     float* dbg;               // optional: CTA (0,0) dumps v of its first tile [BM][BN]
 };
 
@@ -287,46 +288,76 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const uint32_t e = threadIdx.x - 64;                // 0..127, used to stage aux
         TopList<KP> top;
         top.init();
-        float scratch[32];
+        float scratch[64];
+        // Shared threshold: the k'-th best value any CTA of this query has seen so far (monotone, atomicMin on the
+        // order-preserving integer image).  A value that does not beat it cannot be in the merged top-k', whichever
+        // split holds it, so every split prunes with the tightest bound known anywhere.  Stale reads are only looser.
+        uint32_t* gtau_ptr = p.gtau + q0 + row_in_tile;
         float2 aux_next = (n_tiles > 0) ? p.aux[r_begin + e] : make_float2(0.f, INFINITY);
         for (uint32_t t = 0; t < n_tiles; t++) {
             const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
             const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
             s_aux[acc * BN + e] = aux_next;
             if (t + 1 < n_tiles) aux_next = p.aux[static_cast<uint64_t>(row0) + BN + e];
+            const uint32_t g_bits = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
             mbar_wait(bar_tfull + acc, aph);
             tc_fence_after();
+            const float g_tau = ordered_to_f32(g_bits);       // NaN (all-ones init) is ignored by fminf
+            float tau = fminf(top.tau(), g_tau);
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN;
             const float2* ax = s_aux + acc * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c * 32, r);
+            for (int c = 0; c < BN / 64; c++) {
+                uint32_t r[64];
+                tmem_ld32(taddr + c * 64, r);
+                tmem_ld32(taddr + c * 64 + 32, r + 32);
                 tmem_ld_wait();
-                float v[32];
-                float m = INFINITY;
+                float v[64];
+                float gm[8];  // minima of the 8 groups of 8 columns
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const float2 ab = ax[c * 32 + j];
-                    v[j] = fmaf(__uint_as_float(r[j]), ab.x, ab.y);
-                    m = fminf(m, v[j]);
+                for (int g = 0; g < 8; g++) {
+                    float mg = INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float2 ab = ax[c * 64 + g * 8 + j];
+                        v[g * 8 + j] = fmaf(__uint_as_float(r[g * 8 + j]), ab.x, ab.y);
+                        mg = fminf(mg, v[g * 8 + j]);
+                    }
+                    gm[g] = mg;
                 }
+                const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
                 if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) p.dbg[row_in_tile * BN + c * 32 + j] = v[j];
+                    for (int j = 0; j < 64; j++) p.dbg[row_in_tile * BN + c * 64 + j] = v[j];
                 }
-                if (m < top.tau()) {
+                if (m < tau) {
+                    // Rare path, cost proportional to the number of groups that really hold a candidate: stash the
+                    // 64 values once (independent stores), then visit only the groups whose minimum beats tau.
 #pragma unroll
-                    for (int j = 0; j < 32; j++) scratch[j] = v[j];
-                    for (int j = 0; j < 32; j++) {
-                        const float x = scratch[j];
-                        if (x < top.tau()) top.insert(x, row0 + c * 32 + j);
+                    for (int j = 0; j < 64; j++) scratch[j] = v[j];
+                    uint32_t gmask = 0;
+#pragma unroll
+                    for (int g = 0; g < 8; g++) gmask |= (gm[g] < tau) ? (1u << g) : 0u;
+                    while (gmask) {
+                        const int g = __ffs(gmask) - 1;
+                        gmask &= gmask - 1;
+                        float s8[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) s8[j] = scratch[g * 8 + j];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            if (s8[j] < tau) {
+                                top.insert(s8[j], row0 + c * 64 + g * 8 + j);
+                                tau = fminf(tau, top.tau());
+                            }
+                        }
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive(bar_tempty + acc);
+            if (top.tau() < g_tau || (g_tau != g_tau && top.tau() < INFINITY)) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));
         }
         const uint64_t q = static_cast<uint64_t>(q0) + row_in_tile;
         if (q < p.nq) {
@@ -508,7 +539,7 @@ struct TcState {
     void* d_x = nullptr;      // stacked database operand (nullptr: the index rows themselves are used)
     float2* d_aux = nullptr;  // [n_pad + BN]
     CUtensorMap tm_x;
-    DevBuf q_op, part, dbg;
+    DevBuf q_op, part, dbg, gtau;
     uint64_t bytes = 0;
 };
 
@@ -604,6 +635,7 @@ void tc_destroy(annb_index* ix) {
     ix->tc->q_op.release();
     ix->tc->part.release();
     ix->tc->dbg.release();
+    ix->tc->gtau.release();
     delete ix->tc;
     ix->tc = nullptr;
 }
@@ -702,10 +734,12 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     const size_t smem = q_smem + static_cast<size_t>(stages) * nb * tc::SLAB_TILE + fixed;
 
     ANNB_TRY(st->part.ensure(nq * splits * static_cast<uint64_t>(kprime) * 8));
+    ANNB_TRY(st->gtau.ensure(static_cast<uint64_t>(nq_pad) * 4));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(st->gtau.p, 0xFF, static_cast<uint64_t>(nq_pad) * 4, s));
     tc::Params p{};
     p.nq = nq; p.n_rows = ix->n; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
     p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = na; p.aux = st->d_aux;
-    p.part_keys = st->part.as<uint64_t>(); p.dbg = st->dbg.as<float>();
+    p.part_keys = st->part.as<uint64_t>(); p.dbg = st->dbg.as<float>(); p.gtau = st->gtau.as<uint32_t>();
     {
         dim3 grid(static_cast<uint32_t>(q_tiles), splits);
         // timed as the dominant kernel of the flat path
