@@ -788,6 +788,15 @@ int annb_debug_fetch_tile(annb_index* ix, float* host_out) {
     return rc;
 }
 
+int annb_debug_fetch_cycles(annb_index* ix, uint64_t* host_out8) {
+    if (!ix || !host_out8) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
+    DeviceGuard g(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    int rc = tc_debug_cycles(ix, reinterpret_cast<unsigned long long*>(host_out8));
+    if (rc != ANNB_OK && rc != ANNB_ERR_CUDA) set_last_error("tc_debug is not enabled on this index");
+    return rc;
+}
+
 int annb_index_get_stat(const annb_index* ix, const char* key, int64_t* out) {
     if (!ix || !key || !out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
     std::string k(key);

@@ -31,10 +31,11 @@ constexpr int BM = 128;              // queries per CTA (UMMA M, TMEM lanes)
 constexpr int BN = 128;              // database rows per MMA tile (UMMA N, TMEM columns per accumulator)
 constexpr int SLAB_BYTES = 128;      // K extent of one smem slab = one 128-byte swizzle atom
 constexpr int SLAB_TILE = BM * SLAB_BYTES;  // 16 KiB: 128 rows x 128 B
-constexpr int NUM_THREADS = 192;
-constexpr int EPI_THREADS = 128;
-constexpr int ACC_STAGES = 2;
-constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 256
+constexpr int NUM_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_THREADS = 256;        // two warps per TMEM lane quarter, each owning one 64-column half of the tile
+constexpr int ACC_STAGES = 4;          // accumulator ring in TMEM (4 x 128 columns = all 512)
+constexpr int AUX_STAGES = 2;
+constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 512
 
 enum { KIND_TF32X3 = 0, KIND_BF16 = 1 };
 
@@ -48,10 +49,12 @@ struct Params {
     uint32_t n_splits;
     uint64_t rows_per_split;  // multiple of BN
     uint32_t a_pieces;        // query terms actually present (bf16 self query: 1)
-    const float2* aux;        // per database row: v = fma(s, aux.x, aux.y)  (L2: -2, |x|^2; cosine: -1/|x|, 0; pad: 0, +inf)
-    uint64_t* part_keys;      // [nq][n_splits][KPRIME] packed (approx value, row)
+    const float* aux;         // per database row: L2  v = aux - 2 s  (aux = |x|^2, pad rows +inf);
+                              //                   cos v = s * aux    (aux = -1/|x|, pad rows +inf -> 0 * inf = NaN, never selected)
+    uint64_t* part_keys;      // [nq][2 * n_splits][KPRIME] packed (approx value, row); one list per 64-column half
     uint32_t* gtau;           // [nq_pad] shared pruning threshold per query (order-preserving image, atomicMin)
     float* dbg;               // optional: CTA (0,0) dumps v of its first tile [BM][BN]
+    unsigned long long* dbg_cycles;  // optional: CTA (0,0) wait-cycle counters {total, prod_empty, mma_full, mma_tempty, epi_tfull, epi_slow}
 };
 
 // ----------------------------------------------------------------------------------------------- PTX wrappers
@@ -82,6 +85,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
+}
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, long long& acc) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
+// One lane of a converged warp (elect.sync): lets the compiler keep the surrounding values in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -170,7 +184,7 @@ struct TopList {
 };
 
 // ----------------------------------------------------------------------------------------------- the kernel
-template <int KIND, int KP>
+template <int KIND, int KP, int MET>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const Params p) {
     constexpr int NA = (KIND == KIND_TF32X3) ? 2 : 3;  // stacked query pieces
@@ -186,8 +200,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     uint8_t* s_q = smem;                                                         // [NA][nslab] slabs
     uint8_t* s_x = s_q + static_cast<size_t>(NA) * p.nslab * SLAB_TILE;          // [n_stages][NB] slabs
     uint8_t* s_tail = s_x + static_cast<size_t>(p.n_stages) * NB * SLAB_TILE;
-    float2* s_aux = reinterpret_cast<float2*>(s_tail);                           // [ACC_STAGES][BN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail + ACC_STAGES * BN * sizeof(float2));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail);
     uint64_t* bar_full = bars;                         // [n_stages]
     uint64_t* bar_empty = bars + p.n_stages;           // [n_stages]
     uint64_t* bar_q = bars + 2 * p.n_stages;           // [1]
@@ -224,91 +237,114 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     tma_load_2d(smem_u32(s_q + (static_cast<size_t>(a) * p.nslab + s) * SLAB_TILE), &tm_q, bar_q, s * SLAB_ELEMS,
                                 a * p.nq_pad + q0);
             uint32_t it = 0;
+            long long w_prod = 0;
             for (uint32_t t = 0; t < n_tiles; t++) {
                 const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
                 for (uint32_t s = 0; s < p.nslab; s++, it++) {
                     const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
-                    mbar_wait(bar_empty + stage, ph ^ 1u);
+                    mbar_wait_timed(bar_empty + stage, ph ^ 1u, w_prod);
                     mbar_expect_tx(bar_full + stage, NB * SLAB_TILE);
                     for (int b = 0; b < NB; b++)
                         tma_load_2d(smem_u32(s_x + (static_cast<size_t>(stage) * NB + b) * SLAB_TILE), &tm_x, bar_full + stage, s * SLAB_ELEMS,
                                     b * p.n_pad + row0);
                 }
             }
+            if (p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0) p.dbg_cycles[1] = w_prod;
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================================================================== MMA issuer (one thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(KIND);
-            mbar_wait(bar_q, 0);
+        // ===================================================================== MMA issuer
+        // The whole warp walks the pipeline converged (so every address / descriptor is warp-uniform and lives in
+        // uniform registers); only the tcgen05 instructions themselves are issued by one elected lane.
+        constexpr uint32_t idesc = make_idesc(KIND);
+        constexpr uint32_t SLAB_DESC = SLAB_TILE >> 4;    // descriptor start-address units (16 B) per slab
+        mbar_wait(bar_q, 0);
+        tc_fence_after();
+        const uint64_t q_desc0 = make_smem_desc(smem_u32(s_q));
+        const uint64_t x_desc0 = make_smem_desc(smem_u32(s_x));
+        uint32_t it = 0;
+        long long w_full = 0, w_tempty = 0;
+        const long long t_start = clock64();
+        for (uint32_t t = 0; t < n_tiles; t++) {
+            const uint32_t acc = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1u;
+            mbar_wait_timed(bar_tempty + acc, aph ^ 1u, w_tempty);
             tc_fence_after();
-            uint32_t it = 0;
-            for (uint32_t t = 0; t < n_tiles; t++) {
-                const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
-                mbar_wait(bar_tempty + acc, aph ^ 1u);
+            const uint32_t tmem_c = tmem_base + acc * BN;
+            for (uint32_t s = 0; s < p.nslab; s++, it++) {
+                const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
+                mbar_wait_timed(bar_full + stage, ph, w_full);
                 tc_fence_after();
-                const uint32_t tmem_c = tmem_base + acc * BN;
-                uint32_t accumulate = 0;
-                for (uint32_t s = 0; s < p.nslab; s++, it++) {
-                    const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
-                    mbar_wait(bar_full + stage, ph);
-                    tc_fence_after();
-                    const uint32_t xb = smem_u32(s_x + static_cast<size_t>(stage) * NB * SLAB_TILE);
+                const uint64_t xd = x_desc0 + static_cast<uint64_t>(stage * NB) * SLAB_DESC;
+                const uint64_t qd = q_desc0 + static_cast<uint64_t>(s) * SLAB_DESC;
+                const uint64_t q_piece = static_cast<uint64_t>(p.nslab) * SLAB_DESC;
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < KSTEPS; k++) {
+                        const uint32_t first = (s | static_cast<uint32_t>(k)) != 0 ? 1u : 0u;   // 0 only for the tile's first MMA
                         if (KIND == KIND_TF32X3) {
                             // s = Qhi.Xhi + Qlo.Xhi + Qhi.Xlo   (the lo.lo term is below 2^-22 relative)
-                            const uint64_t a_hi = make_smem_desc(smem_u32(s_q + (0 * p.nslab + s) * SLAB_TILE) + k * 32);
-                            const uint64_t a_lo = make_smem_desc(smem_u32(s_q + (1 * p.nslab + s) * SLAB_TILE) + k * 32);
-                            const uint64_t b_hi = make_smem_desc(xb + 0 * SLAB_TILE + k * 32);
-                            const uint64_t b_lo = make_smem_desc(xb + 1 * SLAB_TILE + k * 32);
-                            umma<KIND>(tmem_c, a_hi, b_hi, idesc, accumulate);
-                            umma<KIND>(tmem_c, a_lo, b_hi, idesc, 1);
-                            umma<KIND>(tmem_c, a_hi, b_lo, idesc, 1);
+                            umma<KIND>(tmem_c, qd + 2 * k, xd + 2 * k, idesc, first);
+                            umma<KIND>(tmem_c, qd + q_piece + 2 * k, xd + 2 * k, idesc, 1u);
+                            umma<KIND>(tmem_c, qd + 2 * k, xd + SLAB_DESC + 2 * k, idesc, 1u);
                         } else {
-                            const uint64_t b0 = make_smem_desc(xb + k * 32);
-                            for (uint32_t a = 0; a < p.a_pieces; a++) {
-                                const uint64_t ad = make_smem_desc(smem_u32(s_q + (a * p.nslab + s) * SLAB_TILE) + k * 32);
-                                umma<KIND>(tmem_c, ad, b0, idesc, a == 0 ? accumulate : 1u);
+                            umma<KIND>(tmem_c, qd + 2 * k, xd + 2 * k, idesc, first);
+                            if (p.a_pieces > 1) {
+                                umma<KIND>(tmem_c, qd + q_piece + 2 * k, xd + 2 * k, idesc, 1u);
+                                umma<KIND>(tmem_c, qd + 2 * q_piece + 2 * k, xd + 2 * k, idesc, 1u);
                             }
                         }
-                        accumulate = 1;
                     }
-                    umma_commit(bar_empty + stage);  // slab consumed once the MMAs above retire
+                    umma_commit(bar_empty + stage);                       // slab consumed once the MMAs above retire
+                    if (s + 1 == p.nslab) umma_commit(bar_tfull + acc);   // accumulator ready for the epilogue
                 }
-                umma_commit(bar_tfull + acc);        // accumulator ready for the epilogue
+                __syncwarp();
             }
+        }
+        if (p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+            p.dbg_cycles[0] = clock64() - t_start;
+            p.dbg_cycles[2] = w_full;
+            p.dbg_cycles[3] = w_tempty;
+            p.dbg_cycles[6] = n_tiles;
         }
         __syncwarp();
     } else {
         // ===================================================================== epilogue (4 warps, thread = query row)
         const uint32_t quarter = warp & 3u;                 // TMEM lane quarter this warp may access
         const uint32_t row_in_tile = quarter * 32 + lane;   // query row inside the tile
-        const uint32_t e = threadIdx.x - 64;                // 0..127, used to stage aux
+        const uint32_t half = (warp - 2) >> 2;              // which 64-column half of every tile this warp scans
+        const uint32_t e = threadIdx.x - 64;                // 0..255; the first 128 stage aux
         TopList<KP> top;
         top.init();
         float scratch[64];
+        long long w_tfull = 0, w_slow = 0;
         // Shared threshold: the k'-th best value any CTA of this query has seen so far (monotone, atomicMin on the
         // order-preserving integer image).  A value that does not beat it cannot be in the merged top-k', whichever
         // split holds it, so every split prunes with the tightest bound known anywhere.  Stale reads are only looser.
         uint32_t* gtau_ptr = p.gtau + q0 + row_in_tile;
-        float2 aux_next = (n_tiles > 0) ? p.aux[r_begin + e] : make_float2(0.f, INFINITY);
+        uint32_t g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
+        // Per-column constants of this warp's 64-column half: lane l keeps columns l and l + 32 in registers
+        // (coalesced load, fetched one tile ahead) and the warp broadcasts them with shuffles -- no shared memory,
+        // no barrier between the epilogue warps.
+        const float* aux_half = p.aux + r_begin + half * 64 + lane;
+        float aux_lo_next = 0.f, aux_hi_next = 0.f;
+        if (n_tiles > 0) { aux_lo_next = __ldg(aux_half); aux_hi_next = __ldg(aux_half + 32); }
         for (uint32_t t = 0; t < n_tiles; t++) {
-            const uint32_t acc = t & 1u, aph = (t >> 1) & 1u;
+            const uint32_t acc = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1u;
             const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
-            s_aux[acc * BN + e] = aux_next;
-            if (t + 1 < n_tiles) aux_next = p.aux[static_cast<uint64_t>(row0) + BN + e];
-            const uint32_t g_bits = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
-            mbar_wait(bar_tfull + acc, aph);
+            const uint32_t g_bits = g_next;
+            const float aux_lo = aux_lo_next, aux_hi = aux_hi_next;
+            if (t + 1 < n_tiles) {   // prefetch for the next tile: latency hidden behind this tile's work
+                aux_lo_next = __ldg(aux_half + static_cast<size_t>(t + 1) * BN);
+                aux_hi_next = __ldg(aux_half + static_cast<size_t>(t + 1) * BN + 32);
+                g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
+            }
+            mbar_wait_timed(bar_tfull + acc, aph, w_tfull);
             tc_fence_after();
             const float g_tau = ordered_to_f32(g_bits);       // NaN (all-ones init) is ignored by fminf
             float tau = fminf(top.tau(), g_tau);
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN;
-            const float2* ax = s_aux + acc * BN;
-#pragma unroll 1
-            for (int c = 0; c < BN / 64; c++) {
+            {
+                const int c = static_cast<int>(half);
                 uint32_t r[64];
                 tmem_ld32(taddr + c * 64, r);
                 tmem_ld32(taddr + c * 64 + 32, r + 32);
@@ -320,8 +356,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     float mg = INFINITY;
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        const float2 ab = ax[c * 64 + g * 8 + j];
-                        v[g * 8 + j] = fmaf(__uint_as_float(r[g * 8 + j]), ab.x, ab.y);
+                        const int col = g * 8 + j;   // compile-time after unrolling
+                        const float cst = __shfl_sync(0xFFFFFFFFu, col < 32 ? aux_lo : aux_hi, col & 31);
+                        const float sdot = __uint_as_float(r[col]);
+                        v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
                         mg = fminf(mg, v[g * 8 + j]);
                     }
                     gm[g] = mg;
@@ -332,6 +370,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     for (int j = 0; j < 64; j++) p.dbg[row_in_tile * BN + c * 64 + j] = v[j];
                 }
                 if (m < tau) {
+                    const long long ts0 = clock64();
                     // Rare path, cost proportional to the number of groups that really hold a candidate: stash the
                     // 64 values once (independent stores), then visit only the groups whose minimum beats tau.
 #pragma unroll
@@ -353,15 +392,17 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                             }
                         }
                     }
+                    w_slow += clock64() - ts0;
                 }
             }
             tc_fence_before();
             mbar_arrive(bar_tempty + acc);
             if (top.tau() < g_tau || (g_tau != g_tau && top.tau() < INFINITY)) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));
         }
+        if (p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) { p.dbg_cycles[4] = w_tfull; p.dbg_cycles[5] = w_slow; }
         const uint64_t q = static_cast<uint64_t>(q0) + row_in_tile;
         if (q < p.nq) {
-            uint64_t* out = p.part_keys + (q * p.n_splits + blockIdx.y) * KP;
+            uint64_t* out = p.part_keys + (q * (2 * p.n_splits) + 2 * blockIdx.y + half) * KP;
 #pragma unroll
             for (int j = 0; j < KP; j++) out[j] = (top.i[j] == IDX_INVALID) ? KEY_SENTINEL : make_key(top.v[j], top.i[j]);
         }
@@ -430,13 +471,13 @@ __global__ void pad_bf16_kernel(const uint16_t* __restrict__ src, uint32_t ld_sr
 // Epilogue constants per database row.  L2: (-2, |x|^2) with |x|^2 of the stored (possibly bf16-rounded) row;
 // cosine: (-1/norm, 0) with the index norm (f32 norm of the un-rounded row, as the reference divides by it).
 __global__ void aux_kernel(const uint8_t* __restrict__ rows, uint32_t row_bytes, int is_bf16, uint32_t dim, const float* __restrict__ norms,
-                           uint64_t n, uint64_t n_pad_total, float2* __restrict__ aux) {
+                           uint64_t n, uint64_t n_pad_total, float* __restrict__ aux) {
     const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (i >= n_pad_total) return;
-    float2 o = make_float2(0.f, INFINITY);
+    float o = INFINITY;
     if (i < n) {
         if (norms) {
-            o = make_float2(-1.0f / norms[i], 0.f);
+            o = -1.0f / norms[i];
         } else {
             float s = 0.f;
             const uint8_t* r = rows + i * row_bytes;
@@ -444,7 +485,7 @@ __global__ void aux_kernel(const uint8_t* __restrict__ rows, uint32_t row_bytes,
                 const float x = is_bf16 ? bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(r)[e]) : reinterpret_cast<const float*>(r)[e];
                 s = fmaf(x, x, s);
             }
-            o = make_float2(-2.0f, s);
+            o = s;
         }
     }
     aux[i] = o;
@@ -537,9 +578,9 @@ struct TcState {
     uint32_t nslab = 0;
     uint32_t n_pad = 0;
     void* d_x = nullptr;      // stacked database operand (nullptr: the index rows themselves are used)
-    float2* d_aux = nullptr;  // [n_pad + BN]
+    float* d_aux = nullptr;   // [n_pad + BN]
     CUtensorMap tm_x;
-    DevBuf q_op, part, dbg, gtau;
+    DevBuf q_op, part, dbg, gtau, dbgc;
     uint64_t bytes = 0;
 };
 
@@ -592,9 +633,9 @@ int tc_flat_prepare(annb_index* ix) {
     cudaStream_t s = ix->stream;
     const uint64_t aux_rows = static_cast<uint64_t>(st->n_pad) + tc::BN;
     {
-        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&st->d_aux), aux_rows * sizeof(float2));
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&st->d_aux), aux_rows * sizeof(float));
         if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc tc aux: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
-        st->bytes += aux_rows * sizeof(float2);
+        st->bytes += aux_rows * sizeof(float);
     }
     tc::aux_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(ix->d_rows, ix->row_bytes, kind == tc::KIND_BF16, ix->dim,
                                                                                 ix->metric == ANNB_COSINE ? ix->d_norms : nullptr, ix->n, aux_rows,
@@ -636,6 +677,7 @@ void tc_destroy(annb_index* ix) {
     ix->tc->part.release();
     ix->tc->dbg.release();
     ix->tc->gtau.release();
+    ix->tc->dbgc.release();
     delete ix->tc;
     ix->tc = nullptr;
 }
@@ -672,9 +714,9 @@ static uint32_t pick_splits(uint64_t q_tiles, uint64_t n_tiles_db, int requested
     return best;
 }
 
-template <int KIND, int KP>
+template <int KIND, int KP, int MET>
 static int launch_tc(const CUtensorMap& tmq, const CUtensorMap& tmx, const tc::Params& p, dim3 grid, size_t smem, cudaStream_t s) {
-    auto kern = tc::flat_tc_kernel<KIND, KP>;
+    auto kern = tc::flat_tc_kernel<KIND, KP, MET>;
     ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<grid, tc::NUM_THREADS, smem, s>>>(tmq, tmx, p);
     ANNB_CUDA_CHECK(cudaGetLastError());
@@ -726,36 +768,39 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
     const uint32_t nb = kind == tc::KIND_TF32X3 ? 2 : 1;
     const size_t q_smem = static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * st->nslab * tc::SLAB_TILE;
-    const size_t fixed = tc::ACC_STAGES * tc::BN * sizeof(float2) + 256 /*barriers*/;
+    const size_t fixed = 256 /*barriers*/;
     const size_t budget = 227 * 1024;
     if (q_smem + fixed + nb * tc::SLAB_TILE > budget) { set_last_error("tensor path: query tile too large for shared memory"); return ANNB_ERR_UNSUPPORTED; }
     uint32_t stages = static_cast<uint32_t>((budget - q_smem - fixed) / (nb * tc::SLAB_TILE));
     stages = std::min<uint32_t>(stages, 8);
     const size_t smem = q_smem + static_cast<size_t>(stages) * nb * tc::SLAB_TILE + fixed;
 
-    ANNB_TRY(st->part.ensure(nq * splits * static_cast<uint64_t>(kprime) * 8));
+    ANNB_TRY(st->part.ensure(nq * 2 * splits * static_cast<uint64_t>(kprime) * 8));
     ANNB_TRY(st->gtau.ensure(static_cast<uint64_t>(nq_pad) * 4));
     ANNB_CUDA_CHECK(cudaMemsetAsync(st->gtau.p, 0xFF, static_cast<uint64_t>(nq_pad) * 4, s));
     tc::Params p{};
     p.nq = nq; p.n_rows = ix->n; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
     p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = na; p.aux = st->d_aux;
-    p.part_keys = st->part.as<uint64_t>(); p.dbg = st->dbg.as<float>(); p.gtau = st->gtau.as<uint32_t>();
+    p.part_keys = st->part.as<uint64_t>(); p.dbg = st->dbg.as<float>(); p.gtau = st->gtau.as<uint32_t>(); p.dbg_cycles = st->dbgc.as<unsigned long long>();
     {
         dim3 grid(static_cast<uint32_t>(q_tiles), splits);
         // timed as the dominant kernel of the flat path
         cudaEvent_t ea = nullptr, eb = nullptr;
         if (ix->opt_time_kernels && cudaEventCreate(&ea) == cudaSuccess && cudaEventCreate(&eb) == cudaSuccess) cudaEventRecord(ea, s);
         int rc;
-        if (kind == tc::KIND_TF32X3) rc = kprime == 16 ? launch_tc<tc::KIND_TF32X3, 16>(tmq, st->tm_x, p, grid, smem, s) : launch_tc<tc::KIND_TF32X3, 32>(tmq, st->tm_x, p, grid, smem, s);
-        else rc = kprime == 16 ? launch_tc<tc::KIND_BF16, 16>(tmq, st->tm_x, p, grid, smem, s) : launch_tc<tc::KIND_BF16, 32>(tmq, st->tm_x, p, grid, smem, s);
+        const bool l2 = ix->metric == ANNB_L2;
+#define ANNB_TC_LAUNCH(KIND_, KP_) (l2 ? launch_tc<KIND_, KP_, MET_L2>(tmq, st->tm_x, p, grid, smem, s) : launch_tc<KIND_, KP_, MET_COS>(tmq, st->tm_x, p, grid, smem, s))
+        if (kind == tc::KIND_TF32X3) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32);
+        else rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_BF16, 16) : ANNB_TC_LAUNCH(tc::KIND_BF16, 32);
+#undef ANNB_TC_LAUNCH
         if (ea && eb) { cudaEventRecord(eb, s); ix->timed.emplace_back(ea, eb); }
         ANNB_TRY(rc);
         ix->stat_launches++;
     }
     // ---- exact re-rank + merge ----
     tc::RerankParams r{};
-    r.part_keys = st->part.as<uint64_t>(); r.parts = splits; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out;
-    r.nsort = next_pow2(std::max(splits * kprime, 64u));
+    r.part_keys = st->part.as<uint64_t>(); r.parts = 2 * splits; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out;
+    r.nsort = next_pow2(std::max(2 * splits * kprime, 64u));
     r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
     r.bf16_self = bf16_self; r.id_base = ix->id_base; r.out_ids = d_ids; r.out_dist = d_dist; r.out_counts = d_cnt;
     const bool cos = ix->metric == ANNB_COSINE;
@@ -771,13 +816,20 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
 // Debug hook used by tests: allocate / fetch the 128 x 128 tile dump of CTA (0, 0).
 int tc_debug_enable(annb_index* ix, bool on) {
     if (!ix->tc) return ANNB_ERR_UNSUPPORTED;
-    if (on) return ix->tc->dbg.ensure(tc::BM * tc::BN * sizeof(float));
+    if (on) { ANNB_TRY(ix->tc->dbgc.ensure(64)); cudaMemset(ix->tc->dbgc.p, 0, 64); return ix->tc->dbg.ensure(tc::BM * tc::BN * sizeof(float)); }
     ix->tc->dbg.release();
+    ix->tc->dbgc.release();
     return ANNB_OK;
 }
 int tc_debug_fetch(annb_index* ix, float* host_out) {
     if (!ix->tc || !ix->tc->dbg.p) return ANNB_ERR_UNSUPPORTED;
     ANNB_CUDA_CHECK(cudaMemcpy(host_out, ix->tc->dbg.p, tc::BM * tc::BN * sizeof(float), cudaMemcpyDeviceToHost));
+    // the first 8 floats' worth of the dump are followed out-of-band by the cycle counters (see tc_debug_cycles)
+    return ANNB_OK;
+}
+int tc_debug_cycles(annb_index* ix, unsigned long long* host_out8) {
+    if (!ix->tc || !ix->tc->dbgc.p) return ANNB_ERR_UNSUPPORTED;
+    ANNB_CUDA_CHECK(cudaMemcpy(host_out8, ix->tc->dbgc.p, 64, cudaMemcpyDeviceToHost));
     return ANNB_OK;
 }
 

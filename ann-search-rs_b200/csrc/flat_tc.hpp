@@ -19,5 +19,6 @@ void tc_destroy(annb_index* ix);
 // Test hooks: CTA (0,0) of the tensor kernel dumps the 128 x 128 values of its first tile.
 int tc_debug_enable(annb_index* ix, bool on);
 int tc_debug_fetch(annb_index* ix, float* host_out);
+int tc_debug_cycles(annb_index* ix, unsigned long long* host_out8);
 
 }  // namespace annb

@@ -201,6 +201,9 @@ int annb_index_get_stat(const annb_index* index, const char* key, int64_t* out);
 /* Diagnostics (tests only): with option "tc_debug" = 1 the first CTA of the tensor-core flat kernel dumps the
  * 128 x 128 selection values v = fma(q.x, a, b) of its first tile; this copies them to host_out[128 * 128]. */
 int annb_debug_fetch_tile(annb_index* index, float* host_out);
+/* ... and its role wait-cycle counters {mma_total, producer_wait_empty, mma_wait_full, mma_wait_tmem_empty,
+ * epilogue_wait_tmem_full, epilogue_slow_path, tiles, 0} of the last tensor-path launch. */
+int annb_debug_fetch_cycles(annb_index* index, uint64_t* host_out8);
 
 void annb_destroy(annb_index* index);
 
