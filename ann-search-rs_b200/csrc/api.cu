@@ -771,6 +771,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     std::string k(key);
     if (k == "path") { if (value < 0 || value > 2) return fail(ANNB_ERR_INVALID_ARGUMENT, "path must be 0..2"); ix->opt_path = static_cast<int>(value); }
     else if (k == "tc_candidates") ix->opt_tc_candidates = static_cast<int>(value);
+    else if (k == "tc_ts") ix->opt_tc_ts = static_cast<int>(value);
     else if (k == "tc_debug") { DeviceGuard g(ix->device); return tc_debug_enable(ix, value != 0); }
     else if (k == "db_splits") ix->opt_db_splits = static_cast<int>(value);
     else if (k == "scan_parts") ix->opt_scan_parts = static_cast<int>(value);

@@ -52,6 +52,8 @@ struct Params {
     const float* aux;         // per database row: L2  v = aux - 2 s  (aux = |x|^2, pad rows +inf);
                               //                   cos v = s * aux    (aux = -1/|x|, pad rows +inf -> 0 * inf = NaN, never selected)
     uint64_t* part_keys;      // [nq][2 * n_splits][KPRIME] packed (approx value, row); one list per 64-column half
+    const float* q_op;        // stacked query operand [a_pieces][nq_pad][kp] (TS mode loads it into TMEM)
+    uint32_t kp;              // padded K in elements
     uint32_t* gtau;           // [nq_pad] shared pruning threshold per query (order-preserving image, atomicMin)
     float* dbg;               // optional: CTA (0,0) dumps v of its first tile [BM][BN]
     unsigned long long* dbg_cycles;  // optional: CTA (0,0) wait-cycle counters {total, prod_empty, mma_full, mma_tempty, epi_tfull, epi_slow}
@@ -144,6 +146,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
         : "r"(taddr)
         : "memory");
 }
+// A operand from TMEM (row m of A = TMEM lane m, K along columns), B from shared memory.
+template <int KIND>
+__device__ __forceinline__ void umma_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == KIND_TF32X3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_c),
+                     "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_c),
+                     "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t r[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "
+        "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+        "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor: K-major operand tile, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart.
@@ -184,7 +208,9 @@ struct TopList {
 };
 
 // ----------------------------------------------------------------------------------------------- the kernel
-template <int KIND, int KP, int MET>
+// TS = the query operand lives in TMEM (columns [0, 256): hi then lo) instead of shared memory: the MMAs read only the
+// database slab from shared memory (half the operand bandwidth) and the whole 227 KB becomes database ring.
+template <int KIND, int KP, int MET, bool TS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const Params p) {
     constexpr int NA = (KIND == KIND_TF32X3) ? 2 : 3;  // stacked query pieces
@@ -192,13 +218,16 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     constexpr int ELEM = (KIND == KIND_TF32X3) ? 4 : 2;
     constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;      // 32 tf32 / 64 bf16 per slab row
     constexpr int KSTEPS = 4;                          // 128 B / 32 B per UMMA K step (8 tf32 / 16 bf16)
+    constexpr int NACC = TS ? 2 : ACC_STAGES;          // accumulator stages (TS: 256 of the 512 columns hold the queries)
+    constexpr uint32_t ACC_COL0 = TS ? 256u : 0u;
+    static_assert(!TS || KIND == KIND_TF32X3, "TS mode is implemented for the tf32 kernel");
 
     extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte aligned bases
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     if ((smem_u32(smem) & 1023u) != 0) __trap();
 
     uint8_t* s_q = smem;                                                         // [NA][nslab] slabs
-    uint8_t* s_x = s_q + static_cast<size_t>(NA) * p.nslab * SLAB_TILE;          // [n_stages][NB] slabs
+    uint8_t* s_x = TS ? smem : s_q + static_cast<size_t>(NA) * p.nslab * SLAB_TILE;  // [n_stages][NB] slabs
     uint8_t* s_tail = s_x + static_cast<size_t>(p.n_stages) * NB * SLAB_TILE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail);
     uint64_t* bar_full = bars;                         // [n_stages]
@@ -215,8 +244,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.n_stages; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
-        mbar_init(bar_q, 1);
-        for (int a = 0; a < ACC_STAGES; a++) { mbar_init(bar_tfull + a, 1); mbar_init(bar_tempty + a, EPI_THREADS); }
+        mbar_init(bar_q, TS ? EPI_THREADS : 1);
+        for (int a = 0; a < NACC; a++) { mbar_init(bar_tfull + a, 1); mbar_init(bar_tempty + a, EPI_THREADS); }
         fence_barrier_init();
         fence_proxy_async();
         tma_prefetch_desc(&tm_q);
@@ -231,11 +260,13 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
-            mbar_expect_tx(bar_q, p.a_pieces * p.nslab * SLAB_TILE);
-            for (uint32_t a = 0; a < p.a_pieces; a++)
-                for (uint32_t s = 0; s < p.nslab; s++)
-                    tma_load_2d(smem_u32(s_q + (static_cast<size_t>(a) * p.nslab + s) * SLAB_TILE), &tm_q, bar_q, s * SLAB_ELEMS,
-                                a * p.nq_pad + q0);
+            if (!TS) {
+                mbar_expect_tx(bar_q, p.a_pieces * p.nslab * SLAB_TILE);
+                for (uint32_t a = 0; a < p.a_pieces; a++)
+                    for (uint32_t s = 0; s < p.nslab; s++)
+                        tma_load_2d(smem_u32(s_q + (static_cast<size_t>(a) * p.nslab + s) * SLAB_TILE), &tm_q, bar_q, s * SLAB_ELEMS,
+                                    a * p.nq_pad + q0);
+            }
             uint32_t it = 0;
             long long w_prod = 0;
             for (uint32_t t = 0; t < n_tiles; t++) {
@@ -266,10 +297,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         long long w_full = 0, w_tempty = 0;
         const long long t_start = clock64();
         for (uint32_t t = 0; t < n_tiles; t++) {
-            const uint32_t acc = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1u;
+            const uint32_t acc = t % NACC, aph = (t / NACC) & 1u;
             mbar_wait_timed(bar_tempty + acc, aph ^ 1u, w_tempty);
             tc_fence_after();
-            const uint32_t tmem_c = tmem_base + acc * BN;
+            const uint32_t tmem_c = tmem_base + ACC_COL0 + acc * BN;
             for (uint32_t s = 0; s < p.nslab; s++, it++) {
                 const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
                 mbar_wait_timed(bar_full + stage, ph, w_full);
@@ -281,7 +312,13 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < KSTEPS; k++) {
                         const uint32_t first = (s | static_cast<uint32_t>(k)) != 0 ? 1u : 0u;   // 0 only for the tile's first MMA
-                        if (KIND == KIND_TF32X3) {
+                        if (TS) {
+                            // queries in TMEM: hi at columns [0, 128), lo at [128, 256); 8 columns (tf32) per K step
+                            const uint32_t a_hi = tmem_base + s * 32 + k * 8, a_lo = a_hi + 128;
+                            umma_ts<KIND>(tmem_c, a_hi, xd + 2 * k, idesc, first);
+                            umma_ts<KIND>(tmem_c, a_lo, xd + 2 * k, idesc, 1u);
+                            umma_ts<KIND>(tmem_c, a_hi, xd + SLAB_DESC + 2 * k, idesc, 1u);
+                        } else if (KIND == KIND_TF32X3) {
                             // s = Qhi.Xhi + Qlo.Xhi + Qhi.Xlo   (the lo.lo term is below 2^-22 relative)
                             umma<KIND>(tmem_c, qd + 2 * k, xd + 2 * k, idesc, first);
                             umma<KIND>(tmem_c, qd + q_piece + 2 * k, xd + 2 * k, idesc, 1u);
@@ -320,6 +357,24 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         // Shared threshold: the k'-th best value any CTA of this query has seen so far (monotone, atomicMin on the
         // order-preserving integer image).  A value that does not beat it cannot be in the merged top-k', whichever
         // split holds it, so every split prunes with the tightest bound known anywhere.  Stale reads are only looser.
+        if (TS) {
+            // Stage this CTA's 128 queries into TMEM once: the four warps with half == 0 write the tf32 "hi" terms,
+            // the other four the "lo" terms; thread = query row = TMEM lane, 32 columns per tcgen05.st.
+            const float* src = p.q_op + (static_cast<size_t>(half) * p.nq_pad + q0 + row_in_tile) * p.kp;
+            const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + half * 128;
+            for (uint32_t c = 0; c < p.kp; c += 32) {
+                uint32_t w[32];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(src + c) + j);
+                    w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
+                }
+                tmem_st32(tq + c, w);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_q);
+        }
         uint32_t* gtau_ptr = p.gtau + q0 + row_in_tile;
         uint32_t g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
         // Per-column constants of this warp's 64-column half: lane l keeps columns l and l + 32 in registers
@@ -329,7 +384,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         float aux_lo_next = 0.f, aux_hi_next = 0.f;
         if (n_tiles > 0) { aux_lo_next = __ldg(aux_half); aux_hi_next = __ldg(aux_half + 32); }
         for (uint32_t t = 0; t < n_tiles; t++) {
-            const uint32_t acc = t % ACC_STAGES, aph = (t / ACC_STAGES) & 1u;
+            const uint32_t acc = t % NACC, aph = (t / NACC) & 1u;
             const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
             const uint32_t g_bits = g_next;
             const float aux_lo = aux_lo_next, aux_hi = aux_hi_next;
@@ -342,7 +397,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             tc_fence_after();
             const float g_tau = ordered_to_f32(g_bits);       // NaN (all-ones init) is ignored by fminf
             float tau = fminf(top.tau(), g_tau);
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * BN;
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + ACC_COL0 + acc * BN;
             {
                 const int c = static_cast<int>(half);
                 uint32_t r[64];
@@ -714,9 +769,9 @@ static uint32_t pick_splits(uint64_t q_tiles, uint64_t n_tiles_db, int requested
     return best;
 }
 
-template <int KIND, int KP, int MET>
+template <int KIND, int KP, int MET, bool TS>
 static int launch_tc(const CUtensorMap& tmq, const CUtensorMap& tmx, const tc::Params& p, dim3 grid, size_t smem, cudaStream_t s) {
-    auto kern = tc::flat_tc_kernel<KIND, KP, MET>;
+    auto kern = tc::flat_tc_kernel<KIND, KP, MET, TS>;
     ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<grid, tc::NUM_THREADS, smem, s>>>(tmq, tmx, p);
     ANNB_CUDA_CHECK(cudaGetLastError());
@@ -767,7 +822,8 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;
     const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
     const uint32_t nb = kind == tc::KIND_TF32X3 ? 2 : 1;
-    const size_t q_smem = static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * st->nslab * tc::SLAB_TILE;
+    const bool ts = kind == tc::KIND_TF32X3 && ix->opt_tc_ts != 0;   // queries in TMEM (tf32 path)
+    const size_t q_smem = ts ? 0 : static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * st->nslab * tc::SLAB_TILE;
     const size_t fixed = 256 /*barriers*/;
     const size_t budget = 227 * 1024;
     if (q_smem + fixed + nb * tc::SLAB_TILE > budget) { set_last_error("tensor path: query tile too large for shared memory"); return ANNB_ERR_UNSUPPORTED; }
@@ -781,7 +837,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     tc::Params p{};
     p.nq = nq; p.n_rows = ix->n; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
     p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = na; p.aux = st->d_aux;
-    p.part_keys = st->part.as<uint64_t>(); p.dbg = st->dbg.as<float>(); p.gtau = st->gtau.as<uint32_t>(); p.dbg_cycles = st->dbgc.as<unsigned long long>();
+    p.part_keys = st->part.as<uint64_t>(); p.dbg = st->dbg.as<float>(); p.gtau = st->gtau.as<uint32_t>(); p.q_op = st->q_op.as<float>(); p.kp = kp; p.dbg_cycles = st->dbgc.as<unsigned long long>();
     {
         dim3 grid(static_cast<uint32_t>(q_tiles), splits);
         // timed as the dominant kernel of the flat path
@@ -789,9 +845,10 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
         if (ix->opt_time_kernels && cudaEventCreate(&ea) == cudaSuccess && cudaEventCreate(&eb) == cudaSuccess) cudaEventRecord(ea, s);
         int rc;
         const bool l2 = ix->metric == ANNB_L2;
-#define ANNB_TC_LAUNCH(KIND_, KP_) (l2 ? launch_tc<KIND_, KP_, MET_L2>(tmq, st->tm_x, p, grid, smem, s) : launch_tc<KIND_, KP_, MET_COS>(tmq, st->tm_x, p, grid, smem, s))
-        if (kind == tc::KIND_TF32X3) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32);
-        else rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_BF16, 16) : ANNB_TC_LAUNCH(tc::KIND_BF16, 32);
+#define ANNB_TC_LAUNCH(KIND_, KP_, TS_) (l2 ? launch_tc<KIND_, KP_, MET_L2, TS_>(tmq, st->tm_x, p, grid, smem, s) : launch_tc<KIND_, KP_, MET_COS, TS_>(tmq, st->tm_x, p, grid, smem, s))
+        if (kind == tc::KIND_TF32X3 && ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, true) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, true);
+        else if (kind == tc::KIND_TF32X3) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, false) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, false);
+        else rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_BF16, 16, false) : ANNB_TC_LAUNCH(tc::KIND_BF16, 32, false);
 #undef ANNB_TC_LAUNCH
         if (ea && eb) { cudaEventRecord(eb, s); ix->timed.emplace_back(ea, eb); }
         ANNB_TRY(rc);

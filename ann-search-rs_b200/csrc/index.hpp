@@ -72,6 +72,7 @@ struct annb_index {
     // options
     int opt_path = ANNB_PATH_AUTO;
     int opt_tc_candidates = 0;
+    int opt_tc_ts = 1;         // tensor path, f32: keep the query operand in TMEM (TS-mode MMA)
     int opt_db_splits = 0;
     int opt_scan_parts = 0;
     int opt_time_kernels = 0;  // record CUDA events around the dominant kernel of every search
