@@ -52,7 +52,7 @@ struct Params {
     const float* aux;         // per database row: L2  v = aux - 2 s  (aux = |x|^2, pad rows +inf);
                               //                   cos v = s * aux    (aux = -1/|x|, pad rows +inf -> 0 * inf = NaN, never selected)
     uint64_t* part_keys;      // [nq][2 * n_splits][KPRIME] packed (approx value, row); one list per 64-column half
-    const float* q_op;        // stacked query operand [a_pieces][nq_pad][kp] (TS mode loads it into TMEM)
+    const void* q_op;         // stacked query operand [a_pieces][nq_pad][kp] (TS mode loads it into TMEM)
     uint32_t kp;              // padded K in elements
     uint32_t* gtau;           // [nq_pad] shared pruning threshold per query (order-preserving image, atomicMin)
     float* dbg;               // optional: CTA (0,0) dumps v of its first tile [BM][BN]
@@ -220,7 +220,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     constexpr int KSTEPS = 4;                          // 128 B / 32 B per UMMA K step (8 tf32 / 16 bf16)
     constexpr int NACC = TS ? 2 : ACC_STAGES;          // accumulator stages (TS: 256 of the 512 columns hold the queries)
     constexpr uint32_t ACC_COL0 = TS ? 256u : 0u;
-    static_assert(!TS || KIND == KIND_TF32X3, "TS mode is implemented for the tf32 kernel");
+    constexpr uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : 64u;   // TMEM columns per query piece (32-bit words per row)
 
     extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte aligned bases
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -312,12 +312,20 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < KSTEPS; k++) {
                         const uint32_t first = (s | static_cast<uint32_t>(k)) != 0 ? 1u : 0u;   // 0 only for the tile's first MMA
-                        if (TS) {
-                            // queries in TMEM: hi at columns [0, 128), lo at [128, 256); 8 columns (tf32) per K step
-                            const uint32_t a_hi = tmem_base + s * 32 + k * 8, a_lo = a_hi + 128;
+                        if (TS && KIND == KIND_TF32X3) {
+                            // queries in TMEM: hi at columns [0, 128), lo at [128, 256); 8 columns (8 tf32) per K step
+                            const uint32_t a_hi = tmem_base + s * 32 + k * 8, a_lo = a_hi + PIECE_COLS;
                             umma_ts<KIND>(tmem_c, a_hi, xd + 2 * k, idesc, first);
                             umma_ts<KIND>(tmem_c, a_lo, xd + 2 * k, idesc, 1u);
                             umma_ts<KIND>(tmem_c, a_hi, xd + SLAB_DESC + 2 * k, idesc, 1u);
+                        } else if (TS) {
+                            // bf16 query terms q0, q1, q2 in TMEM at columns [0,64), [64,128), [128,192); 8 columns (16 bf16) per K step
+                            const uint32_t a0 = tmem_base + s * 32 + k * 8;
+                            umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
+                            if (p.a_pieces > 1) {
+                                umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
+                                umma_ts<KIND>(tmem_c, a0 + 2 * PIECE_COLS, xd + 2 * k, idesc, 1u);
+                            }
                         } else if (KIND == KIND_TF32X3) {
                             // s = Qhi.Xhi + Qlo.Xhi + Qhi.Xlo   (the lo.lo term is below 2^-22 relative)
                             umma<KIND>(tmem_c, qd + 2 * k, xd + 2 * k, idesc, first);
@@ -358,18 +366,22 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         // order-preserving integer image).  A value that does not beat it cannot be in the merged top-k', whichever
         // split holds it, so every split prunes with the tightest bound known anywhere.  Stale reads are only looser.
         if (TS) {
-            // Stage this CTA's 128 queries into TMEM once: the four warps with half == 0 write the tf32 "hi" terms,
-            // the other four the "lo" terms; thread = query row = TMEM lane, 32 columns per tcgen05.st.
-            const float* src = p.q_op + (static_cast<size_t>(half) * p.nq_pad + q0 + row_in_tile) * p.kp;
-            const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + half * 128;
-            for (uint32_t c = 0; c < p.kp; c += 32) {
-                uint32_t w[32];
+            // Stage this CTA's 128 queries into TMEM once: query pieces are dealt to the two warps of each lane quarter
+            // (even pieces to half 0, odd to half 1); thread = query row = TMEM lane, 32 columns (128 B of the row) per
+            // tcgen05.st.  16-bit operands sit two per column, low half = even k, exactly as in memory.
+            const uint32_t row_words = p.kp * ELEM / 4;
+            for (uint32_t pc = half; pc < p.a_pieces; pc += 2) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(p.q_op) + (static_cast<size_t>(pc) * p.nq_pad + q0 + row_in_tile) * row_words;
+                const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + pc * PIECE_COLS;
+                for (uint32_t c = 0; c < row_words; c += 32) {
+                    uint32_t w[32];
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(src + c) + j);
-                    w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
+                    for (int j = 0; j < 8; j++) {
+                        const uint4 x = __ldg(reinterpret_cast<const uint4*>(src + c) + j);
+                        w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
+                    }
+                    tmem_st32(tq + c, w);
                 }
-                tmem_st32(tq + c, w);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -822,7 +834,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;
     const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
     const uint32_t nb = kind == tc::KIND_TF32X3 ? 2 : 1;
-    const bool ts = kind == tc::KIND_TF32X3 && ix->opt_tc_ts != 0;   // queries in TMEM (tf32 path)
+    const bool ts = ix->opt_tc_ts != 0;   // query operand resident in TMEM (TS-mode MMA)
     const size_t q_smem = ts ? 0 : static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * st->nslab * tc::SLAB_TILE;
     const size_t fixed = 256 /*barriers*/;
     const size_t budget = 227 * 1024;
@@ -837,7 +849,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     tc::Params p{};
     p.nq = nq; p.n_rows = ix->n; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
     p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = na; p.aux = st->d_aux;
-    p.part_keys = st->part.as<uint64_t>(); p.dbg = st->dbg.as<float>(); p.gtau = st->gtau.as<uint32_t>(); p.q_op = st->q_op.as<float>(); p.kp = kp; p.dbg_cycles = st->dbgc.as<unsigned long long>();
+    p.part_keys = st->part.as<uint64_t>(); p.dbg = st->dbg.as<float>(); p.gtau = st->gtau.as<uint32_t>(); p.q_op = st->q_op.as<void>(); p.kp = kp; p.dbg_cycles = st->dbgc.as<unsigned long long>();
     {
         dim3 grid(static_cast<uint32_t>(q_tiles), splits);
         // timed as the dominant kernel of the flat path
@@ -848,6 +860,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
 #define ANNB_TC_LAUNCH(KIND_, KP_, TS_) (l2 ? launch_tc<KIND_, KP_, MET_L2, TS_>(tmq, st->tm_x, p, grid, smem, s) : launch_tc<KIND_, KP_, MET_COS, TS_>(tmq, st->tm_x, p, grid, smem, s))
         if (kind == tc::KIND_TF32X3 && ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, true) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, true);
         else if (kind == tc::KIND_TF32X3) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, false) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, false);
+        else if (ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_BF16, 16, true) : ANNB_TC_LAUNCH(tc::KIND_BF16, 32, true);
         else rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_BF16, 16, false) : ANNB_TC_LAUNCH(tc::KIND_BF16, 32, false);
 #undef ANNB_TC_LAUNCH
         if (ea && eb) { cudaEventRecord(eb, s); ix->timed.emplace_back(ea, eb); }
