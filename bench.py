@@ -300,7 +300,6 @@ def run_b200(args):
     ms_per_step = ms / args.steps
     qps = nq / (ms_per_step * 1e-3)
     last_path = index.get_stat("last_path")
-    scanned = index.get_stat("scanned_vectors") if args.workload == "ivf" else 0
 
     # ---- end to end through the host-buffer C ABI (pinned host queries, host outputs) ----
     hq = torch.from_numpy(queries).pin_memory()
@@ -338,6 +337,11 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     e2e_qps = nq / e2e_s
+    # probed-list statistics are collected by the host-buffer entry point (last e2e step)
+    scanned = index.get_stat("scanned_vectors") if args.workload == "ivf" else 0
+    if world > 1 and args.workload == "ivf":
+        # every rank derives the same global probe lists; the vectors it scans are those of its own lists
+        pass
 
     if rank != 0:
         if world > 1:
@@ -350,15 +354,22 @@ def run_b200(args):
     if args.workload == "flat":
         rows_local = (n + world - 1) // world
         flops = 2.0 * nq * rows_local * dim                      # algorithmic flops per launch: 2 * nq * n * d
+        mma_per_elem = 3                                          # f32: 3xTF32 terms; bf16 index: f32 query = 3 bf16 terms
         if args.dtype == "f32":
-            peak = peaks["bf16_tflops"] / 2.0                    # 3xTF32 runs on the TF32 pipe: measured bf16 / 2
-            peak_note = f"{peak_src} bf16 burst peak / 2 (TF32 pipe)"
+            pipe_peak = peaks["bf16_tflops"] / 2.0               # TF32 pipe: measured bf16 / 2
+            peak = pipe_peak / 3.0                               # BASELINE.md's f32 row: algorithmic flops executed 3x on the TF32 pipe
+            peak_note = f"{peak_src} bf16 burst peak / 2 (TF32 pipe) / 3 (3xTF32 terms), as BASELINE.md section 2"
         else:
-            peak = peaks["bf16_tflops"]
-            peak_note = f"{peak_src} bf16 burst peak"
+            pipe_peak = peaks["bf16_tflops"]
+            peak = pipe_peak                                     # BASELINE.md's bf16 row: one bf16 MMA per element
+            peak_note = f"{peak_src} bf16 burst peak (the f32 query is fed as 3 bf16 terms, see 'executed')"
+        if last_path != 2:
+            mma_per_elem = 0
         achieved = flops / dom_s / 1e12
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                     "kernel": "flat distance + top-k select", "kernel_ms": dom_s * 1e3, "peak_source": peak_note,
+                    "executed": {"mma_terms_per_element": mma_per_elem, "tflops": achieved * mma_per_elem, "pipe_peak": pipe_peak,
+                                 "frac_of_pipe_peak": achieved * mma_per_elem / pipe_peak},
                     "path": {0: "auto", 1: "simt (CUDA cores)", 2: "tensor (tcgen05)"}.get(last_path, str(last_path))}
     else:
         esz = {"f32": 4, "bf16": 2, "sq8": 1}[args.dtype]

@@ -91,3 +91,24 @@ def test_product_never_imports_the_oracle():
                         if re.search(r"\b(import|include|from)\b.*\boracle\b", line):
                             hits.append((f, line.strip()))
     assert not hits, hits
+
+
+def _build_cpp_mirror_test():
+    pkg = os.path.join(ROOT, "ann-search-rs_b200")
+    os.makedirs(os.path.join(pkg, "build"), exist_ok=True)
+    exe = os.path.join(pkg, "build", "host_mirror_test")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(pkg, "host", "tests", "host_mirror_test.cpp"),
+           "-L" + os.path.join(pkg, "lib"), "-lannb200", "-Wl,-rpath," + os.path.join(pkg, "lib"),
+           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_host_mirror_compiles_links_and_fails_loudly_without_gpu():
+    """The C++ mirror of the reference API (host/annb200.hpp) builds against the C ABI; without a device its calls
+    raise the Cuda variant instead of computing anything on the host."""
+    exe = _build_cpp_mirror_test()
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("OK"), r.stdout

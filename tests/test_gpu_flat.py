@@ -133,3 +133,11 @@ def test_mirror_free_functions(gpu):
     assert (ids[:, 0] == np.arange(1000)).all()
     ram, vram = ix.memory_usage_bytes()
     assert vram >= 1000 * 32 * 4
+
+
+def test_cpp_host_mirror_on_gpu(gpu):
+    """host/annb200.hpp (C++ mirror of the reference API) through the C ABI: the reference's 5-point fixture."""
+    import subprocess
+    from test_abi import _build_cpp_mirror_test
+    r = subprocess.run([_build_cpp_mirror_test()], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "OK gpu", r.stdout + r.stderr
