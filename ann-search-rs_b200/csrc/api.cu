@@ -126,10 +126,29 @@ static int launch_scan(int rt, int qt, int metric, const ScanParams& p, uint32_t
     return fail(ANNB_ERR_INVALID_ARGUMENT, "unsupported (row, query) type pair");
 }
 
+template <int RT, int QT, int MET>
+static int launch_list_scan_t(const ListScanParams& p, uint32_t grid, size_t smem, cudaStream_t s) {
+    auto kern = ivf_list_kernel<RT, QT, MET>;
+    if (smem > 227 * 1024) return fail(ANNB_ERR_UNSUPPORTED, "ivf_list_kernel: dim/k too large for shared memory (DimTooHighForSharedMemory)");
+    ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, TILE_THREADS, smem, s>>>(p);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    return ANNB_OK;
+}
+static int launch_list_scan(int rt, int qt, int metric, const ListScanParams& p, uint32_t grid, size_t smem, cudaStream_t s) {
+    const bool cos = metric == ANNB_COSINE;
+    if (rt == ANNB_F32 && qt == QT_F32) return cos ? launch_list_scan_t<0, QT_F32, MET_COS>(p, grid, smem, s) : launch_list_scan_t<0, QT_F32, MET_L2>(p, grid, smem, s);
+    if (rt == ANNB_BF16 && qt == QT_F32) return cos ? launch_list_scan_t<1, QT_F32, MET_COS>(p, grid, smem, s) : launch_list_scan_t<1, QT_F32, MET_L2>(p, grid, smem, s);
+    if (rt == ANNB_BF16 && qt == QT_BF16) return cos ? launch_list_scan_t<1, QT_BF16, MET_COS>(p, grid, smem, s) : launch_list_scan_t<1, QT_BF16, MET_L2>(p, grid, smem, s);
+    if (rt == ANNB_SQ8 && qt == QT_I8) return cos ? launch_list_scan_t<2, QT_I8, MET_COS>(p, grid, smem, s) : launch_list_scan_t<2, QT_I8, MET_L2>(p, grid, smem, s);
+    return fail(ANNB_ERR_INVALID_ARGUMENT, "unsupported (row, query) type pair");
+}
+
 static int run_finalize(annb_index* ix, const uint64_t* keys, uint32_t parts, uint32_t kc, uint32_t k_out, uint64_t nq,
                         const uint64_t* id_map, uint64_t id_base, const uint64_t* row_map, uint64_t* d_ids, float* d_dist,
-                        uint32_t* d_cnt, cudaStream_t s) {
+                        uint32_t* d_cnt, cudaStream_t s, const uint32_t* parts_used = nullptr) {
     FinalizeParams f{};
+    f.parts_used = parts_used;
     f.part_keys = keys; f.parts = parts; f.kc = kc; f.k = k_out;
     f.nsort = next_pow2(std::max(parts * kc, k_out));
     f.nq = nq; f.id_map = id_map; f.id_base = id_base; f.row_map = row_map;
@@ -318,7 +337,50 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         if (!h_flag[0]) break;
         pitch = ix->nlist;
     }
-    // 3. list scan
+    // 3. list scan.  A batch that probes every list many times goes list-major (one staged list tile serves up to 32
+    //    queries); small batches keep the query-major streaming kernel (one warp per query part).
+    const uint64_t n_local_lists = std::max<uint32_t>(1, ix->list_end - ix->list_begin);
+    const bool list_major = ix->opt_ivf_list_major == 1 || (ix->opt_ivf_list_major < 0 && nq * static_cast<uint64_t>(np) >= 8 * n_local_lists);
+    if (list_major) {
+        const uint32_t nsort = WarpSelect::sort_size(kk);
+        const uint64_t slots = nq * static_cast<uint64_t>(pitch);
+        ANNB_TRY(ix->s_keys.ensure(slots * kk * 8));
+        ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_keys.p, 0xFF, slots * kk * 8, s));       // unvisited (query, rank) slots stay sentinels
+        // scratch: cnt | cursor | pair_off | task_off | task_counter | pairs
+        const size_t nl = ix->nlist;
+        const size_t hdr = (4 * (nl + 1) + 4) * sizeof(uint32_t);
+        ANNB_TRY(ix->s_pairs.ensure(hdr + slots * sizeof(uint2)));
+        uint32_t* w = ix->s_pairs.as<uint32_t>();
+        ANNB_CUDA_CHECK(cudaMemsetAsync(w, 0, hdr, s));
+        PairParams pp{};
+        pp.probes = ix->s_probes.as<uint32_t>(); pp.probe_pitch = pitch; pp.n_probes = ix->s_nprobes.as<uint32_t>(); pp.nq = nq;
+        pp.nlist = ix->nlist; pp.list_begin = ix->list_begin; pp.list_end = ix->list_end;
+        pp.cnt = w; pp.cursor = w + (nl + 1); pp.pair_off = w + 2 * (nl + 1); pp.task_off = w + 3 * (nl + 1); pp.task_counter = w + 4 * (nl + 1);
+        pp.pairs = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(w) + hdr);
+        const uint32_t g = static_cast<uint32_t>(ceil_div<uint64_t>(slots, 256));
+        ivf_count_pairs_kernel<<<g, 256, 0, s>>>(pp);
+        ivf_pair_offsets_kernel<<<1, 1024, 0, s>>>(pp);
+        ivf_fill_pairs_kernel<<<g, 256, 0, s>>>(pp);
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        ix->stat_launches += 3;
+        ListScanParams lp{};
+        lp.rows = ix->d_rows; lp.row_bytes = ix->row_bytes; lp.row_norms = ix->d_norms; lp.row_norms_i = ix->d_norms_i;
+        lp.queries = pq.scan; lp.q_bytes = pq.scan_bytes; lp.dim = ix->dim; lp.bf16_self = pq.bf16_self;
+        lp.offsets = ix->d_offsets; lp.shard_row0 = ix->shard_row0; lp.nlist = ix->nlist;
+        lp.pair_off = pp.pair_off; lp.task_off = pp.task_off; lp.pairs = pp.pairs; lp.task_counter = pp.task_counter;
+        lp.probe_pitch = pitch; lp.k = kk; lp.nsort = nsort; lp.part_keys = ix->s_keys.as<uint64_t>();
+        const size_t smem = list_kernel_smem(ix->row_bytes, pq.scan_bytes, nsort);
+        const uint64_t max_tasks = ceil_div<uint64_t>(slots, CTA_QUERIES) + n_local_lists;
+        const uint32_t ctas_per_sm = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / std::max<size_t>(smem, 1))));
+        const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>(max_tasks, 148ull * ctas_per_sm));
+        {
+            KernelTimer kt(ix, s);
+            ANNB_TRY(launch_list_scan(ix->dtype, pq.qt, ix->metric, lp, grid, smem, s));
+        }
+        ix->stat_launches++;
+        return run_finalize(ix, ix->s_keys.as<uint64_t>(), pitch, kk, k, nq, ix->d_original_ids, 0, row_map, d_ids, d_dist, d_cnt, s,
+                            ix->s_nprobes.as<uint32_t>());
+    }
     uint32_t parts = ix->opt_scan_parts > 0 ? static_cast<uint32_t>(ix->opt_scan_parts)
                                             : static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(16, ceil_div<uint64_t>(148ull * 32, std::max<uint64_t>(nq, 1)))));
     parts = std::max(1u, std::min(parts, np));
@@ -466,7 +528,7 @@ void annb_destroy(annb_index* ix) {
     cudaFree(ix->d_rows); cudaFree(ix->d_norms); cudaFree(ix->d_norms_i); cudaFree(ix->d_scales);
     cudaFree(ix->d_centroids); cudaFree(ix->d_centroid_norms); cudaFree(ix->d_offsets); cudaFree(ix->d_original_ids);
     for (DevBuf* b : {&ix->s_qpad, &ix->s_qcodes, &ix->s_route, &ix->s_cdist, &ix->s_probes, &ix->s_nprobes, &ix->s_keys, &ix->s_flags,
-                      &ix->s_ids, &ix->s_dist, &ix->s_cnt, &ix->s_tmp})
+                      &ix->s_ids, &ix->s_dist, &ix->s_cnt, &ix->s_tmp, &ix->s_pairs})
         b->release();
     if (ix->stream) cudaStreamDestroy(ix->stream);
     (void)cudaGetLastError();
@@ -775,6 +837,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "tc_debug") { DeviceGuard g(ix->device); return tc_debug_enable(ix, value != 0); }
     else if (k == "db_splits") ix->opt_db_splits = static_cast<int>(value);
     else if (k == "scan_parts") ix->opt_scan_parts = static_cast<int>(value);
+    else if (k == "ivf_list_major") ix->opt_ivf_list_major = static_cast<int>(value);
     else if (k == "time_kernels") { ix->opt_time_kernels = static_cast<int>(value); ix->timed_ms_total = 0.0; ix->timed_launches = 0; }
     else return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown option " + k);
     return ANNB_OK;

@@ -75,6 +75,7 @@ struct annb_index {
     int opt_tc_ts = 1;         // tensor path, f32: keep the query operand in TMEM (TS-mode MMA)
     int opt_db_splits = 0;
     int opt_scan_parts = 0;
+    int opt_ivf_list_major = -1;  // -1 auto, 0 query-major scan, 1 list-major scan
     int opt_time_kernels = 0;  // record CUDA events around the dominant kernel of every search
 
     // stats
@@ -91,6 +92,6 @@ struct annb_index {
     // scratch (guarded by mu)
     mutable std::mutex mu;
     cudaStream_t stream = nullptr;
-    annb::DevBuf s_qpad, s_qcodes, s_route, s_cdist, s_probes, s_nprobes, s_keys, s_flags, s_ids, s_dist, s_cnt, s_tmp;
+    annb::DevBuf s_qpad, s_qcodes, s_route, s_cdist, s_probes, s_nprobes, s_keys, s_flags, s_ids, s_dist, s_cnt, s_tmp, s_pairs;
     annb::TcState* tc = nullptr;
 };

@@ -354,6 +354,225 @@ static inline size_t scan_kernel_smem(uint32_t row_bytes, uint32_t q_bytes, uint
 }
 
 // ---------------------------------------------------------------------------
+// IVF list scan, list-major ("batched") variant.
+//
+// With a query batch every inverted list is probed by many queries (10k queries x 32 probes over 4096 lists: ~78
+// queries per list).  The (query, probe-rank) pairs are bucketed by list on the device; one task = one list x a group
+// of up to 32 of the queries that probe it.  A CTA stages the list's 32-row tiles once (cp.async double buffer) and
+// every warp scores its 4 queries of the group against the staged rows -- the same inner loop as tile_kernel, same
+// reference-order arithmetic -- so each byte fetched from HBM / L2 is used by up to 32 queries instead of one.
+// Persistent CTAs pull tasks from an atomic counter (lists differ a lot in length).
+// Output: one k-list per (query, probe rank), merged by finalize_kernel.
+// ---------------------------------------------------------------------------
+struct PairParams {
+    const uint32_t* probes;    // [nq][probe_pitch]
+    uint32_t probe_pitch;
+    const uint32_t* n_probes;  // [nq]
+    uint64_t nq;
+    uint32_t nlist, list_begin, list_end;
+    uint32_t* cnt;             // [nlist]   pairs per list (zeroed by the caller)
+    uint32_t* cursor;          // [nlist]
+    uint32_t* pair_off;        // [nlist+1]
+    uint32_t* task_off;        // [nlist+1] prefix sum of ceil(cnt / CTA_QUERIES)
+    uint2* pairs;              // [sum cnt] (query, rank) grouped by list
+    uint32_t* task_counter;    // persistent-CTA work counter (zeroed by the caller)
+};
+
+__global__ void ivf_count_pairs_kernel(PairParams p) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= p.nq * p.probe_pitch) return;
+    const uint64_t q = i / p.probe_pitch;
+    const uint32_t r = static_cast<uint32_t>(i - q * p.probe_pitch);
+    if (r >= p.n_probes[q]) return;
+    const uint32_t c = p.probes[i];
+    if (c >= p.list_begin && c < p.list_end) atomicAdd(p.cnt + c, 1u);
+}
+// Single block: exclusive scans of the per-list pair counts and task counts (nlist <= 16384).
+__global__ void __launch_bounds__(1024) ivf_pair_offsets_kernel(PairParams p) {
+    __shared__ uint32_t s_pairs[1024], s_tasks[1024];
+    const uint32_t per = (p.nlist + 1023) / 1024;
+    const uint32_t lo = min(p.nlist, threadIdx.x * per), hi = min(p.nlist, lo + per);
+    uint32_t a = 0, b = 0;
+    for (uint32_t c = lo; c < hi; c++) { a += p.cnt[c]; b += (p.cnt[c] + CTA_QUERIES - 1) / CTA_QUERIES; }
+    s_pairs[threadIdx.x] = a;
+    s_tasks[threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t ra = 0, rb = 0;
+        for (int i = 0; i < 1024; i++) { uint32_t ta = s_pairs[i], tb = s_tasks[i]; s_pairs[i] = ra; s_tasks[i] = rb; ra += ta; rb += tb; }
+        p.pair_off[p.nlist] = ra;
+        p.task_off[p.nlist] = rb;
+    }
+    __syncthreads();
+    a = s_pairs[threadIdx.x];
+    b = s_tasks[threadIdx.x];
+    for (uint32_t c = lo; c < hi; c++) {
+        p.pair_off[c] = a; p.cursor[c] = a; p.task_off[c] = b;
+        a += p.cnt[c]; b += (p.cnt[c] + CTA_QUERIES - 1) / CTA_QUERIES;
+    }
+}
+__global__ void ivf_fill_pairs_kernel(PairParams p) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= p.nq * p.probe_pitch) return;
+    const uint64_t q = i / p.probe_pitch;
+    const uint32_t r = static_cast<uint32_t>(i - q * p.probe_pitch);
+    if (r >= p.n_probes[q]) return;
+    const uint32_t c = p.probes[i];
+    if (c >= p.list_begin && c < p.list_end) p.pairs[atomicAdd(p.cursor + c, 1u)] = make_uint2(static_cast<uint32_t>(q), r);
+}
+
+struct ListScanParams {
+    const uint8_t* rows;
+    uint32_t row_bytes;
+    const float* row_norms;
+    const int32_t* row_norms_i;
+    const uint8_t* queries;
+    uint32_t q_bytes;
+    uint32_t dim;
+    int bf16_self;
+    const uint64_t* offsets;   // global CSR offsets
+    uint64_t shard_row0;
+    uint32_t nlist;
+    const uint32_t* pair_off;
+    const uint32_t* task_off;
+    const uint2* pairs;
+    uint32_t* task_counter;
+    uint32_t probe_pitch, k, nsort;
+    uint64_t* part_keys;       // [nq][probe_pitch][k]
+};
+
+template <int RT, int QT, int MET>
+__global__ void __launch_bounds__(TILE_THREADS) ivf_list_kernel(ListScanParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t xpitch = smem_row_pitch(p.row_bytes);
+    uint8_t* s_q = smem;
+    float* s_qnorm = reinterpret_cast<float*>(s_q + CTA_QUERIES * p.q_bytes);
+    int32_t* s_qnsq = reinterpret_cast<int32_t*>(s_qnorm + CTA_QUERIES);
+    uint2* s_pair = reinterpret_cast<uint2*>(s_qnsq + CTA_QUERIES);             // [32] (query, rank) of the group
+    uint8_t* s_x = reinterpret_cast<uint8_t*>(s_pair + CTA_QUERIES);
+    uint64_t* s_sel = reinterpret_cast<uint64_t*>(s_x + 2 * TILE_ROWS * xpitch);
+    __shared__ uint32_t s_task;
+    const uint32_t total_tasks = p.task_off[p.nlist];
+
+    for (;;) {
+        __syncthreads();  // previous task fully retired (shared buffers reusable)
+        if (tid == 0) s_task = atomicAdd(p.task_counter, 1u);
+        __syncthreads();
+        const uint32_t task = s_task;
+        if (task >= total_tasks) break;
+        // list of this task: largest c with task_off[c] <= task
+        uint32_t lo = 0, hi = p.nlist;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (p.task_off[mid] <= task) lo = mid; else hi = mid;
+        }
+        const uint32_t c = lo;
+        const uint32_t g = task - p.task_off[c];
+        const uint32_t pair0 = p.pair_off[c] + g * CTA_QUERIES;
+        const uint32_t n_in_group = min(static_cast<uint32_t>(CTA_QUERIES), p.pair_off[c + 1] - pair0);
+        const uint64_t r_begin = p.offsets[c] - p.shard_row0, r_end = p.offsets[c + 1] - p.shard_row0;
+
+        if (tid < CTA_QUERIES) s_pair[tid] = (tid < n_in_group) ? p.pairs[pair0 + tid] : make_uint2(0xFFFFFFFFu, 0u);
+        __syncthreads();
+        {
+            const uint32_t cpr = p.q_bytes >> 4;
+            for (uint32_t i = tid; i < CTA_QUERIES * cpr; i += TILE_THREADS) {
+                const uint32_t r = i / cpr, ch = i - r * cpr;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                const uint32_t q = s_pair[r].x;
+                if (q != 0xFFFFFFFFu) v = *reinterpret_cast<const uint4*>(p.queries + static_cast<uint64_t>(q) * p.q_bytes + (ch << 4));
+                *reinterpret_cast<uint4*>(s_q + r * p.q_bytes + (ch << 4)) = v;
+            }
+        }
+        __syncthreads();
+        if (tid < CTA_QUERIES) {
+            const uint8_t* q = s_q + tid * p.q_bytes;
+            float qn = 1.0f;
+            int32_t qs = 0;
+            if (QT == QT_I8) {
+                for (uint32_t e = 0; e < p.dim; e++) {
+                    const int32_t v = reinterpret_cast<const int8_t*>(q)[e];
+                    qs += v * v;
+                }
+            } else if (MET == MET_COS) {
+                qn = seq_norm<(QT == QT_F32) ? 4 : 2>(q, p.dim);
+                if (p.bf16_self) qn = round_to_bf16(qn);
+            }
+            s_qnorm[tid] = qn;
+            s_qnsq[tid] = qs;
+        }
+        const bool warp_active = warp * WARP_QUERIES < n_in_group;
+        WarpSelect sel[WARP_QUERIES];
+#pragma unroll
+        for (int i = 0; i < WARP_QUERIES; i++) sel[i].init(s_sel + static_cast<size_t>(warp * WARP_QUERIES + i) * p.nsort, p.nsort, p.k);
+        __syncthreads();
+
+        const uint8_t* qw = s_q + warp * WARP_QUERIES * p.q_bytes;
+        const uint64_t n_tiles = (r_end - r_begin + TILE_ROWS - 1) / TILE_ROWS;
+        if (n_tiles > 0) {
+            const uint32_t nr = static_cast<uint32_t>(min(static_cast<uint64_t>(TILE_ROWS), r_end - r_begin));
+            stage_rows(s_x, xpitch, p.rows + r_begin * p.row_bytes, p.row_bytes, nr, tid, TILE_THREADS);
+        }
+        cp_async_commit();
+        for (uint64_t t = 0; t < n_tiles; t++) {
+            const uint64_t row0 = r_begin + t * TILE_ROWS;
+            if (t + 1 < n_tiles) {
+                const uint64_t nrow0 = row0 + TILE_ROWS;
+                const uint32_t nr = static_cast<uint32_t>(min(static_cast<uint64_t>(TILE_ROWS), r_end - nrow0));
+                stage_rows(s_x + ((t + 1) & 1) * TILE_ROWS * xpitch, xpitch, p.rows + nrow0 * p.row_bytes, p.row_bytes, nr, tid, TILE_THREADS);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();
+            __syncthreads();
+            if (warp_active) {
+                const uint64_t row = row0 + lane;
+                const bool valid = row < r_end;
+                const uint8_t* xr = s_x + (t & 1) * TILE_ROWS * xpitch + lane * xpitch;
+                float dist[WARP_QUERIES];
+#pragma unroll
+                for (int i = 0; i < WARP_QUERIES; i++) dist[i] = 0.0f;
+                if (valid) {
+                    if (RT == 2) {
+                        int32_t dot[WARP_QUERIES], xx;
+                        accumulate_i8<WARP_QUERIES>(xr, qw, p.q_bytes, p.dim, dot, xx);
+                        const int32_t xn = (MET == MET_COS) ? p.row_norms_i[row] : 0;
+#pragma unroll
+                        for (int i = 0; i < WARP_QUERIES; i++) dist[i] = finish_i8<MET>(dot[i], xx, s_qnsq[warp * WARP_QUERIES + i], xn);
+                    } else {
+                        float raw[WARP_QUERIES];
+                        accumulate_fp<(RT == 0) ? 4 : 2, (QT == QT_F32) ? 4 : 2, MET == MET_L2, WARP_QUERIES>(xr, qw, p.q_bytes, p.dim, raw);
+                        const float xn = (MET == MET_COS) ? p.row_norms[row] : 1.0f;
+#pragma unroll
+                        for (int i = 0; i < WARP_QUERIES; i++) dist[i] = finish_fp<MET>(raw[i], s_qnorm[warp * WARP_QUERIES + i], xn);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < WARP_QUERIES; i++) sel[i].offer(make_key(dist[i], static_cast<uint32_t>(row)), valid);
+            }
+            __syncthreads();
+        }
+        cp_async_wait<0>();
+        if (warp_active) {
+#pragma unroll
+            for (int i = 0; i < WARP_QUERIES; i++) {
+                sel[i].flush();
+                const uint2 pr = s_pair[warp * WARP_QUERIES + i];
+                if (pr.x != 0xFFFFFFFFu) {
+                    uint64_t* out = p.part_keys + (static_cast<uint64_t>(pr.x) * p.probe_pitch + pr.y) * p.k;
+                    for (uint32_t j = lane; j < p.k; j += 32) out[j] = sel[i].buf[j];
+                }
+            }
+        }
+    }
+}
+
+static inline size_t list_kernel_smem(uint32_t row_bytes, uint32_t q_bytes, uint32_t nsort) {
+    return static_cast<size_t>(CTA_QUERIES) * q_bytes + CTA_QUERIES * 8 + CTA_QUERIES * 8 + 2ull * TILE_ROWS * smem_row_pitch(row_bytes) +
+           static_cast<size_t>(CTA_QUERIES) * nsort * 8;
+}
+
+// ---------------------------------------------------------------------------
 // Probe selection: get_centroids_dist + select_probed_clusters
 // (src/utils/k_means_utils.rs:76-99, 3007-3029).  One CTA per query sorts all
 // (distance, cell) pairs -- equal distances in ascending cell id -- and walks the
@@ -415,6 +634,7 @@ struct FinalizeParams {
     const uint64_t* id_map;
     uint64_t id_base;
     const uint64_t* row_map;
+    const uint32_t* parts_used;  // optional [nq]: only the first parts_used[q] lists of a query hold data
     uint64_t* out_ids;
     float* out_dist;
     uint32_t* out_counts;
@@ -424,11 +644,13 @@ __global__ void __launch_bounds__(128) finalize_kernel(FinalizeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
     const uint64_t q = blockIdx.x;
-    const uint32_t total = p.parts * p.kc;
-    const uint64_t* src = p.part_keys + q * total;
-    for (uint32_t i = threadIdx.x; i < p.nsort; i += blockDim.x) keys[i] = (i < total) ? src[i] : KEY_SENTINEL;
+    const uint32_t parts_q = p.parts_used ? min(p.parts, p.parts_used[q]) : p.parts;
+    const uint32_t total = parts_q * p.kc;
+    const uint32_t nsort = min(p.nsort, next_pow2(max(max(total, p.k), 2u)));   // sort only what this query filled
+    const uint64_t* src = p.part_keys + q * (static_cast<uint64_t>(p.parts) * p.kc);
+    for (uint32_t i = threadIdx.x; i < nsort; i += blockDim.x) keys[i] = (i < total) ? src[i] : KEY_SENTINEL;
     __syncthreads();
-    bitonic_sort_keys<true>(keys, p.nsort, threadIdx.x, blockDim.x);
+    bitonic_sort_keys<true>(keys, nsort, threadIdx.x, blockDim.x);
     const uint64_t orow = p.row_map ? p.row_map[q] : q;
     uint32_t my_valid = 0;
     for (uint32_t j = threadIdx.x; j < p.k; j += blockDim.x) {

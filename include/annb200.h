@@ -189,6 +189,7 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
  *   set_option: "path" (annb_path), "tc_candidates" (k' of the tensor-core pre-selection),
  *               "db_splits" (flat: database splits per query tile, 0 = auto),
  *               "scan_parts" (IVF: partial scans per query, 0 = auto),
+ *               "ivf_list_major" (IVF list scan: -1 auto, 0 query-major streaming kernel, 1 list-major batched kernel),
  *               "time_kernels" (1 = bracket the dominant kernel of every search with CUDA events on its stream)
  *   get_stat  : "kernel_launches" (cumulative), "scanned_vectors" (IVF, last call: sum of probed
  *               list lengths), "probed_lists" (last call), "last_path" (annb_path actually used),
