@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=None, help="queries in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--recall", action="store_true", help="also report recall@k vs exact f32 ground truth on a query sample")
+    ap.add_argument("--gpu-setup", default="auto", choices=["auto", "on", "off"],
+                    help="IVF workload: generate data and build the index on the GPU (auto: when n > 2M)")
+    ap.add_argument("--kmeans-iters", type=int, default=8)
     return ap.parse_args()
 
 
@@ -211,30 +214,56 @@ def run_b200(args):
     dt = {"f32": annb200.F32, "bf16": annb200.BF16, "sq8": annb200.SQ8}[args.dtype]
     path = {"auto": annb200.PATH_AUTO, "simt": annb200.PATH_SIMT, "tensor": annb200.PATH_TENSOR}[args.path]
 
-    data, queries, kind = make_data(args)
     n, dim, nq, k = args.n, args.dim, args.nq, args.k
     algo_bytes_per_query = None
-    if args.workload == "flat":
+    gpu_setup = args.workload == "ivf" and (args.gpu_setup == "on" or (args.gpu_setup == "auto" and n > 2_000_000))
+    truth_ids = None
+    oi = None
+    data = None
+    if gpu_setup:
+        # data + index built on the device with the library's own kernels (tools/gpu_setup.py); setup is not timed
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import gpu_setup as gs
+        from annb200 import distributed as D
+        kind = "correlated"
+        t_setup = time.perf_counter()
+        data_t = gs.correlated_gpu(n, dim, dev, seed=42)
+        q_t = gs.subsample_with_noise_gpu(data_t, nq, seed=42)
+        parts = gs.build_ivf_parts_gpu(data_t, args.nlist, dt, local_rank, seed=42, kmeans_iters=args.kmeans_iters)
+        lb, le = D.list_ranges(parts["offsets"], world)[rank]
+        index = gs.ivf_handle_from_parts(parts, n, dim, dt, met, local_rank, lb, le)
+        queries = q_t.cpu().numpy()
+        if rank == 0:
+            truth_ids = gs.exact_ground_truth(data_t, q_t[:min(1000, nq)].contiguous(), k, met, local_rank)
+            if not args.no_cpu_baseline:
+                from oracle import oracle as o
+                oi = o.IvfIndex({"f32": o.F32, "bf16": o.BF16, "sq8": o.SQ8}[args.dtype], o.L2 if met == annb200.L2 else o.COSINE, n, dim, args.nlist,
+                                (parts["vectors"].view(torch.int16) if dt == annb200.BF16 else parts["vectors"]).cpu().numpy().view(
+                                    {"f32": np.float32, "bf16": np.uint16, "sq8": np.int8}[args.dtype]),
+                                parts["centroids"].cpu().numpy(), parts["offsets"].astype(np.int64), parts["original_ids"].cpu().numpy(),
+                                scales=None if parts["scales"] is None else parts["scales"].cpu().numpy())
+        del data_t, q_t, parts
+        torch.cuda.empty_cache()
+        if rank == 0:
+            print(f"[setup] data + IVF index on GPU in {time.perf_counter() - t_setup:.1f} s", file=sys.stderr)
+    else:
+        data, queries, kind = make_data(args)
+    if gpu_setup:
+        pass
+    elif args.workload == "flat":
         lo, hi = (rank * n) // world, ((rank + 1) * n) // world
         sq8_scales = annb200.sq8_train(annb200.normalise_rows(data) if met == annb200.COSINE else data) if dt == annb200.SQ8 and world > 1 else None
         index = annb200.ExhaustiveIndexB200.new(data[lo:hi], met, dt, device=local_rank, id_base=lo, sq8_scales=sq8_scales)
     else:
-        from oracle import oracle as o   # index *construction* for the bench uses the shared oracle build (setup, not timed)
+        from annb200 import distributed as D
+        from oracle import oracle as o   # index *construction* for the small IVF bench uses the shared oracle build (setup, not timed)
         oi = oracle_index(args, data)
-        nl = args.nlist
-        sizes = np.diff(oi.offsets)
-        bounds = [0]
-        target = oi.n / world
-        for r in range(1, world):
-            bounds.append(int(np.searchsorted(oi.offsets, target * r)))
-        bounds.append(nl)
-        lb, le = bounds[rank], bounds[rank + 1]
+        lb, le = D.list_ranges(oi.offsets, world)[rank]
         r0, r1 = int(oi.offsets[lb]), int(oi.offsets[le])
         norms = oi.norms_i if oi.dtype == o.SQ8 else oi.norms
         index = annb200.IvfIndexB200.from_parts(oi.vectors[r0:r1], oi.centroids, oi.offsets, oi.original_ids[r0:r1], oi.dtype, oi.metric,
                                                 norms=None if norms is None else norms[r0:r1], centroid_norms=oi.centroid_norms,
                                                 sq8_scales=oi.scales, list_begin=lb, list_end=le, device=local_rank, n_total=oi.n)
-        del sizes
     index.set_option("path", path)
     index.set_option("time_kernels", 1)
 
@@ -394,23 +423,24 @@ def run_b200(args):
         line["config"]["algorithmic_bytes_per_query"] = algo_bytes_per_query
 
     # ---- parity spot check + recall on a query sample (outside the timed region) ----
-    if args.recall or True:
-        from oracle import oracle as o
+    from oracle import oracle as o
+    got_ids_all = h_ids.numpy()
+    got_d_all = h_dist.numpy()
+    if world == 1 and (args.workload == "flat" or oi is not None):
         ns = min(64, nq)
-        if world == 1:
-            oi2 = oracle_index(args, data) if args.workload == "flat" else oi
-            ref = oracle_search(args, oi2, queries[:ns])
-            got_ids = h_ids[:ns].numpy()
-            got_d = h_dist[:ns].numpy()
-            line["parity_sample"] = {"queries": ns, "ids_equal": bool(np.array_equal(got_ids, ref[0])),
-                                     "dist_bits_equal": bool(np.array_equal(got_d.view(np.uint32), ref[1].view(np.uint32)))}
-            if args.workload == "ivf" or args.dtype != "f32":
-                exact = o.flat_search(o.build_flat(data, o.COSINE if args.metric == "cosine" else o.L2), queries[:ns], k)
-                line["recall_at_k_vs_exact_f32"] = o.recall_at_k(exact[0], got_ids, k)
+        oi2 = oracle_index(args, data) if args.workload == "flat" else oi
+        ref = oracle_search(args, oi2, queries[:ns])
+        line["parity_sample"] = {"queries": ns, "ids_equal": bool(np.array_equal(got_ids_all[:ns], ref[0])),
+                                 "dist_bits_equal": bool(np.array_equal(got_d_all[:ns].view(np.uint32), ref[1].view(np.uint32)))}
+    if truth_ids is not None:
+        line["recall_at_k_vs_exact_f32"] = {"value": o.recall_at_k(truth_ids, got_ids_all[:truth_ids.shape[0]], k), "queries": int(truth_ids.shape[0])}
+    elif data is not None and (args.workload == "ivf" or args.dtype != "f32"):
+        ns = min(64, nq)
+        exact = o.flat_search(o.build_flat(data, o.COSINE if args.metric == "cosine" else o.L2), queries[:ns], k)
+        line["recall_at_k_vs_exact_f32"] = {"value": o.recall_at_k(exact[0], got_ids_all[:ns], k), "queries": ns}
 
     # ---- CPU baseline on this host's cores (bounded sample) ----
-    if not args.no_cpu_baseline:
-        from oracle import oracle as o
+    if not args.no_cpu_baseline and (args.workload == "flat" or oi is not None):
         oi3 = oracle_index(args, data) if args.workload == "flat" else oi
         ns = cpu_sample_size(args)
         cores = o.max_threads()
