@@ -411,6 +411,16 @@ def run_b200(args):
                     "algorithmic_bytes_per_launch": algo_bytes}
         algo_bytes_per_query = algo_bytes / nq
 
+    # DRAM traffic of the dominant kernel: from the committed ncu capture of this exact workload, if there is one
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        key = (f"flat {args.dtype} n={n} dim={dim} nq={nq}" if args.workload == "flat"
+               else f"ivf {args.dtype} n={n} dim={dim} nq={nq} nlist={args.nlist} nprobe={args.nprobe}")
+        if key in tr and world == 1:
+            roofline["traffic"] = tr[key]["dram_bytes"]
+            roofline["traffic_source"] = tr[key]["source"]
+    except Exception:
+        pass
     line = {"metric": metric_name(args), "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": {"f32": "f32 (3xTF32 select + f32 exact re-rank)" if last_path == 2 else "f32", "bf16": "bf16 (f32 accumulate)",
