@@ -1,0 +1,97 @@
+"""Full-size, size-independent properties (BASELINE.json configs 2, 3 and 5) on data generated on the device:
+the oracle cannot finish these sizes in seconds, so the checks are (i) the two independent GPU paths agree bit for
+bit, (ii) sortedness / self-at-rank-0 / idempotence, (iii) a small oracle sample."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import annb200
+from oracle import oracle as o
+from util import assert_exact
+
+pytestmark = pytest.mark.gpu
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+
+
+def _search_dev(ix, q_t, k, ivf_nprobe=None):
+    import torch
+    lib = annb200.lib()
+    nq, dim = q_t.shape
+    ids = torch.empty((nq, k), dtype=torch.int64, device=q_t.device)
+    d = torch.empty((nq, k), dtype=torch.float32, device=q_t.device)
+    st = torch.cuda.current_stream().cuda_stream
+    if ivf_nprobe is None:
+        annb200._check(lib.annb_flat_search_dev(ix.handle, q_t.data_ptr(), nq, dim, k, ids.data_ptr(), d.data_ptr(), None, st))
+    else:
+        annb200._check(lib.annb_ivf_search_dev(ix.handle, q_t.data_ptr(), nq, dim, k, ivf_nprobe, ids.data_ptr(), d.data_ptr(), None, st))
+    torch.cuda.synchronize()
+    return ids.cpu().numpy(), d.cpu().numpy()
+
+
+def test_config2_flat_1m_x_128_cosine_tensor_equals_exact_path(gpu):
+    import torch
+    import gpu_setup as gs
+    dev = torch.device("cuda:0")
+    data = gs.correlated_gpu(1_000_000, 128, dev, seed=42)
+    q = gs.subsample_with_noise_gpu(data, 1024, seed=42)
+    ix = gs._flat_handle_from_device(data, annb200.COSINE, annb200.F32, 0)
+    ix.set_option("path", annb200.PATH_TENSOR)
+    a = _search_dev(ix, q, 10)
+    b = _search_dev(ix, q, 10)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32)), "not idempotent"
+    ix.set_option("path", annb200.PATH_SIMT)
+    c = _search_dev(ix, q, 10)
+    assert_exact(a[0], a[1], c[0], c[1], "1M x 128 cosine: tensor path vs exact CUDA-core path")
+    assert (np.diff(a[1], axis=1) >= 0).all()
+    # oracle on a few queries (host copy of the data)
+    host = data.cpu().numpy()
+    ref = o.flat_search(o.build_flat(host, o.COSINE), q[:16].cpu().numpy(), 10)
+    assert_exact(a[0][:16], a[1][:16], ref[0], ref[1], "1M x 128 cosine vs oracle sample")
+
+
+def test_config5_self_knn_dim50_k15(gpu):
+    """Self-kNN at d = 50 (padded to 64 on the tensor path), k = 15 -> k' = 32; a 200k slice of config 5."""
+    import torch
+    import gpu_setup as gs
+    dev = torch.device("cuda:0")
+    data = gs.correlated_gpu(200_000, 50, dev, seed=7)
+    ix = gs._flat_handle_from_device(data, annb200.L2, annb200.F32, 0)
+    n, k = 4096, 15
+    ids = np.empty((n, k), np.uint64); d = np.empty((n, k), np.float32); cnt = np.empty(n, np.uint32)
+    lib = annb200.lib()
+    ix.set_option("path", annb200.PATH_TENSOR)
+    annb200._check(lib.annb_flat_search_self(ix.handle, 1000, 1000 + n, k, C.c_void_p(ids.ctypes.data), C.c_void_p(d.ctypes.data), C.c_void_p(cnt.ctypes.data)))
+    assert ix.get_stat("last_path") == annb200.PATH_TENSOR
+    assert (ids[:, 0] == np.arange(1000, 1000 + n)).all() and (d[:, 0] == 0).all(), "self must be at rank 0 with distance 0"
+    ids2 = np.empty_like(ids); d2 = np.empty_like(d)
+    ix.set_option("path", annb200.PATH_SIMT)
+    annb200._check(lib.annb_flat_search_self(ix.handle, 1000, 1000 + n, k, C.c_void_p(ids2.ctypes.data), C.c_void_p(d2.ctypes.data), C.c_void_p(cnt.ctypes.data)))
+    assert_exact(ids.view(np.int64), d, ids2.view(np.int64), d2, "self-kNN d=50: tensor vs exact path")
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "sq8"])
+def test_config3_4_ivf_2m_x_128_scan_variants_agree(gpu, dtype):
+    """IVF at 2M x 128, nlist 1024: the list-major and the query-major scan kernels are independent implementations
+    of the same (distance, position) selection -- their outputs must be identical; recall against the exact flat
+    search must be in the expected range."""
+    import torch
+    import gpu_setup as gs
+    dev = torch.device("cuda:0")
+    dt = {"f32": annb200.F32, "bf16": annb200.BF16, "sq8": annb200.SQ8}[dtype]
+    data = gs.correlated_gpu(2_000_000, 128, dev, seed=11)
+    q = gs.subsample_with_noise_gpu(data, 512, seed=11)
+    parts = gs.build_ivf_parts_gpu(data, 1024, dt, 0, seed=11, kmeans_iters=4)
+    ix = gs.ivf_handle_from_parts(parts, data.shape[0], 128, dt, annb200.L2, 0)
+    ix.set_option("ivf_list_major", 1)
+    a = _search_dev(ix, q, 10, ivf_nprobe=16)
+    ix.set_option("ivf_list_major", 0)
+    b = _search_dev(ix, q, 10, ivf_nprobe=16)
+    assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
+    assert np.array_equal(a[0], b[0])
+    assert (np.diff(a[1], axis=1) >= 0).all() and (a[0] >= 0).all()
+    truth = gs.exact_ground_truth(data, q, 10, annb200.L2, 0)
+    rec = o.recall_at_k(truth, a[0], 10)
+    assert rec > {"f32": 0.9, "bf16": 0.85, "sq8": 0.5}[dtype], rec
