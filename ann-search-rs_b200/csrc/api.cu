@@ -342,10 +342,16 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
     const uint64_t n_local_lists = std::max<uint32_t>(1, ix->list_end - ix->list_begin);
     const bool list_major = ix->opt_ivf_list_major == 1 || (ix->opt_ivf_list_major < 0 && nq * static_cast<uint64_t>(np) >= 8 * n_local_lists);
     if (list_major) {
+        const bool use_tc = ix->opt_path != ANNB_PATH_SIMT && tc_ivf_supported(ix, pq.qt, kk);
+        if (!use_tc && ix->opt_path == ANNB_PATH_TENSOR)
+            return fail(ANNB_ERR_UNSUPPORTED, "tensor path requested but this IVF (dtype, dim, k, query type) is not covered by it yet");
+        ix->stat_last_path = use_tc ? ANNB_PATH_TENSOR : ANNB_PATH_SIMT;
         const uint32_t nsort = WarpSelect::sort_size(kk);
         const uint64_t slots = nq * static_cast<uint64_t>(pitch);
-        ANNB_TRY(ix->s_keys.ensure(slots * kk * 8));
-        ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_keys.p, 0xFF, slots * kk * 8, s));       // unvisited (query, rank) slots stay sentinels
+        if (!use_tc) {
+            ANNB_TRY(ix->s_keys.ensure(slots * kk * 8));
+            ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_keys.p, 0xFF, slots * kk * 8, s));   // unvisited (query, rank) slots stay sentinels
+        }
         // scratch: cnt | cursor | pair_off | task_off | task_counter | pairs
         const size_t nl = ix->nlist;
         const size_t hdr = (4 * (nl + 1) + 4) * sizeof(uint32_t);
@@ -357,12 +363,18 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         pp.nlist = ix->nlist; pp.list_begin = ix->list_begin; pp.list_end = ix->list_end;
         pp.cnt = w; pp.cursor = w + (nl + 1); pp.pair_off = w + 2 * (nl + 1); pp.task_off = w + 3 * (nl + 1); pp.task_counter = w + 4 * (nl + 1);
         pp.pairs = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(w) + hdr);
+        pp.group = use_tc ? 128u : static_cast<uint32_t>(CTA_QUERIES);
         const uint32_t g = static_cast<uint32_t>(ceil_div<uint64_t>(slots, 256));
         ivf_count_pairs_kernel<<<g, 256, 0, s>>>(pp);
         ivf_pair_offsets_kernel<<<1, 1024, 0, s>>>(pp);
         ivf_fill_pairs_kernel<<<g, 256, 0, s>>>(pp);
         ANNB_CUDA_CHECK(cudaGetLastError());
         ix->stat_launches += 3;
+        if (use_tc) {
+            const uint64_t max_tasks_tc = ceil_div<uint64_t>(slots, 128) + n_local_lists;
+            return tc_ivf_scan(ix, pq.scan, pq.scan_bytes, nq, kk, k, pitch, pp.pair_off, pp.task_off, pp.pairs, pp.task_counter, max_tasks_tc,
+                               ix->s_nprobes.as<uint32_t>(), row_map, d_ids, d_dist, d_cnt, s);
+        }
         ListScanParams lp{};
         lp.rows = ix->d_rows; lp.row_bytes = ix->row_bytes; lp.row_norms = ix->d_norms; lp.row_norms_i = ix->d_norms_i;
         lp.queries = pq.scan; lp.q_bytes = pq.scan_bytes; lp.dim = ix->dim; lp.bf16_self = pq.bf16_self;
@@ -525,6 +537,7 @@ void annb_destroy(annb_index* ix) {
     if (ix->stream) cudaStreamSynchronize(ix->stream);
     collect_timers(ix);
     tc_destroy(ix);
+    tc_ivf_destroy(ix);
     cudaFree(ix->d_rows); cudaFree(ix->d_norms); cudaFree(ix->d_norms_i); cudaFree(ix->d_scales);
     cudaFree(ix->d_centroids); cudaFree(ix->d_centroid_norms); cudaFree(ix->d_offsets); cudaFree(ix->d_original_ids);
     for (DevBuf* b : {&ix->s_qpad, &ix->s_qcodes, &ix->s_route, &ix->s_cdist, &ix->s_probes, &ix->s_nprobes, &ix->s_keys, &ix->s_flags,
@@ -759,6 +772,8 @@ int annb_ivf_create(annb_index** out, const void* vectors, const void* norms, co
         ANNB_TRY(dmalloc(&ix->d_scales, dim, ix));
         ANNB_CUDA_CHECK(cudaMemcpyAsync(ix->d_scales, sq8_scales, dim * 4ull, cudaMemcpyDefault, s));
     }
+    ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+    ANNB_TRY(tc_ivf_prepare(ix));
     ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
     cleanup.armed = false;
     *out = ix;

@@ -16,6 +16,14 @@ bool tc_flat_supported(const annb_index* ix, int qt, uint32_t k_eff);
 int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt, int bf16_self, uint64_t nq, uint32_t k_eff,
                    uint32_t k_out, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s);
 void tc_destroy(annb_index* ix);
+
+// Tensor-core IVF list scan (ivf_tc.cu): operand copies in list order, grouped (list x 128 queries) tasks, exact re-rank.
+int tc_ivf_prepare(annb_index* ix);
+void tc_ivf_destroy(annb_index* ix);
+bool tc_ivf_supported(const annb_index* ix, int qt, uint32_t k_eff);
+int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t nq, uint32_t k_eff, uint32_t k_out, uint32_t probe_pitch,
+                const uint32_t* d_pair_off, const uint32_t* d_task_off, const void* d_pairs, uint32_t* d_task_counter, uint64_t max_tasks,
+                const uint32_t* d_n_probes, const uint64_t* row_map, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s);
 // Test hooks: CTA (0,0) of the tensor kernel dumps the 128 x 128 values of its first tile.
 int tc_debug_enable(annb_index* ix, bool on);
 int tc_debug_fetch(annb_index* ix, float* host_out);

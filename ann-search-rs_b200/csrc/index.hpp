@@ -39,7 +39,8 @@ struct DevBuf {
     T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct TcState;  // tensor-core operand copies + tensor maps (flat_tc.cu)
+struct TcState;     // tensor-core operand copies + tensor maps (flat_tc.cu)
+struct IvfTcState;  // same for the IVF list scan (ivf_tc.cu)
 
 }  // namespace annb
 
@@ -94,4 +95,5 @@ struct annb_index {
     cudaStream_t stream = nullptr;
     annb::DevBuf s_qpad, s_qcodes, s_route, s_cdist, s_probes, s_nprobes, s_keys, s_flags, s_ids, s_dist, s_cnt, s_tmp, s_pairs;
     annb::TcState* tc = nullptr;
+    annb::IvfTcState* tc_ivf = nullptr;
 };

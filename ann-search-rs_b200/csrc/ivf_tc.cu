@@ -1,0 +1,479 @@
+// ivf_tc.cu -- IVF list scan on the tensor cores ("grouped" distance tiles).
+//
+// The (query, probe-rank) pairs of a batch are bucketed by inverted list on the device (api.cu).  One task = one list x a
+// group of up to 128 of the queries that probe it.  Persistent CTAs pull tasks from an atomic counter and run the same
+// warp-specialised pipeline as flat_tc_kernel, with three differences:
+//   * the 128 query rows of a task are *gathered* by the epilogue threads (thread = TMEM lane = one (query, rank) pair),
+//     split into tf32 hi/lo (or three bf16 terms) on the fly and stored into TMEM (TS-mode MMA) -- no query operand array;
+//   * the database operand is the list's own slab [offsets[c], offsets[c+1]) of the list-ordered operand copy, walked
+//     in 128-row tiles by TMA; rows of the last tile that belong to the next list are masked with a NaN row constant;
+//   * each (query, rank) keeps its own k' candidates; ivf rerank recomputes the merged survivors exactly in the reference's
+//     arithmetic and orders them by (distance, list position) like SortedBuffer (src/cpu/ivf.rs:367-381).
+// Replaces compute_ivf_mega_* + radix_select_ivf_topk of the reference (src/gpu/dist_gpu.rs:922-1355, src/gpu/topk_gpu.rs:599-832).
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "flat_tc.hpp"
+#include "index.hpp"
+#include "tc_common.cuh"
+
+namespace annb {
+
+namespace tc {
+
+struct IvfTcParams {
+    const uint8_t* queries;   // prepared scan queries: f32 rows (q_bytes pitch)
+    uint32_t q_bytes;
+    uint32_t dim;
+    uint32_t nslab, n_stages;
+    uint32_t n_pad;           // rows per piece of the stacked database operand
+    const float* aux;         // per stored row (shard-local list order): L2 |x|^2, cosine -1/|x|
+    const uint64_t* offsets;  // global CSR offsets
+    uint64_t shard_row0;
+    uint32_t nlist;
+    const uint32_t* pair_off;
+    const uint32_t* task_off;  // prefix sum of ceil(pairs per list / 128)
+    const uint2* pairs;        // (query, rank) grouped by list
+    uint32_t* task_counter;
+    uint32_t probe_pitch;
+    uint64_t* part_keys;       // [nq][probe_pitch][2][KP]
+    uint32_t* gtau;            // [nq] shared pruning threshold
+};
+
+template <int KIND, int KP, int MET>
+__global__ void __launch_bounds__(NUM_THREADS, 1) ivf_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const IvfTcParams p) {
+    constexpr int NB = (KIND == KIND_TF32X3) ? 2 : 1;
+    constexpr int ELEM = (KIND == KIND_TF32X3) ? 4 : 2;
+    constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;
+    constexpr int KSTEPS = 4;
+    constexpr int NACC = 2;
+    constexpr uint32_t ACC_COL0 = 256u;
+    constexpr uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : 64u;
+    constexpr uint32_t idesc = make_idesc(KIND);
+    constexpr uint32_t SLAB_DESC = SLAB_TILE >> 4;
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint8_t* s_x = smem;                                                    // [n_stages][NB] slabs
+    uint8_t* s_tail = s_x + static_cast<size_t>(p.n_stages) * NB * SLAB_TILE;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail);
+    uint64_t* bar_full = bars;                     // [n_stages]
+    uint64_t* bar_empty = bars + p.n_stages;       // [n_stages]
+    uint64_t* bar_q = bars + 2 * p.n_stages;       // [1]  queries of the current task are in TMEM
+    uint64_t* bar_tfull = bar_q + 1;               // [NACC]
+    uint64_t* bar_tempty = bar_tfull + NACC;       // [NACC]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + NACC);
+    uint32_t* s_task = s_tmem + 1;                 // [4]: list, pair0, n_in_group, valid flag
+    uint64_t* s_rows = reinterpret_cast<uint64_t*>(s_tmem + 6);  // [2]: r_begin, r_end (8-byte aligned: bars + ... even count)
+
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < p.n_stages; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+        mbar_init(bar_q, EPI_THREADS);
+        for (int a = 0; a < NACC; a++) { mbar_init(bar_tfull + a, 1); mbar_init(bar_tempty + a, EPI_THREADS); }
+        fence_barrier_init();
+        fence_proxy_async();
+        tma_prefetch_desc(&tm_x);
+    }
+    if (warp == 1) tmem_alloc(s_tmem, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const uint32_t total_tasks = p.task_off[p.nlist];
+
+    // role-local running counters: the smem ring and the accumulator ring keep rolling across tasks
+    uint32_t it = 0;        // K-slab counter (producer and MMA issuer advance it identically)
+    uint32_t tg = 0;        // tile counter (MMA issuer and epilogue advance it identically)
+    uint32_t task_no = 0;   // tasks done by this CTA (parity of bar_q)
+
+    // epilogue-only state
+    const uint32_t quarter = warp & 3u;
+    const uint32_t row_in_tile = quarter * 32 + lane;
+    const uint32_t half = (warp >= 2) ? ((warp - 2) >> 2) : 0;
+    TopList<KP> top;
+    float scratch[64];
+
+    for (;;) {
+        __syncthreads();   // every role has finished the previous task (TMEM query region and s_task are reusable)
+        if (threadIdx.x == 0) {
+            const uint32_t task = atomicAdd(p.task_counter, 1u);
+            if (task < total_tasks) {
+                uint32_t lo = 0, hi = p.nlist;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (p.task_off[mid] <= task) lo = mid; else hi = mid;
+                }
+                const uint32_t g = task - p.task_off[lo];
+                const uint32_t pair0 = p.pair_off[lo] + g * BM;
+                s_task[0] = lo;
+                s_task[1] = pair0;
+                s_task[2] = min(static_cast<uint32_t>(BM), p.pair_off[lo + 1] - pair0);
+                s_task[3] = 1;
+                s_rows[0] = p.offsets[lo] - p.shard_row0;
+                s_rows[1] = p.offsets[lo + 1] - p.shard_row0;
+            } else {
+                s_task[3] = 0;
+            }
+        }
+        __syncthreads();
+        if (s_task[3] == 0) break;
+        const uint32_t pair0 = s_task[1], n_in_group = s_task[2];
+        const uint64_t r_begin = s_rows[0], r_end = s_rows[1];
+        const uint32_t n_tiles = static_cast<uint32_t>((r_end - r_begin + BN - 1) / BN);
+
+        if (warp == 0) {
+            // ================================================================= TMA producer
+            if (lane == 0) {
+                for (uint32_t t = 0; t < n_tiles; t++) {
+                    const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
+                    for (uint32_t s = 0; s < p.nslab; s++, it++) {
+                        const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
+                        mbar_wait(bar_empty + stage, ph ^ 1u);
+                        mbar_expect_tx(bar_full + stage, NB * SLAB_TILE);
+                        for (int b = 0; b < NB; b++)
+                            tma_load_2d(smem_u32(s_x + (static_cast<size_t>(stage) * NB + b) * SLAB_TILE), &tm_x, bar_full + stage, s * SLAB_ELEMS,
+                                        b * p.n_pad + row0);
+                    }
+                }
+            } else {
+                it += n_tiles * p.nslab;   // keep the other lanes' copy consistent (only lane 0's is used)
+            }
+            __syncwarp();
+        } else if (warp == 1) {
+            // ================================================================= MMA issuer (converged warp, elected issue)
+            mbar_wait(bar_q, task_no & 1u);
+            tc_fence_after();
+            const uint64_t x_desc0 = make_smem_desc(smem_u32(s_x));
+            for (uint32_t t = 0; t < n_tiles; t++, tg++) {
+                const uint32_t acc = tg % NACC, aph = (tg / NACC) & 1u;
+                mbar_wait(bar_tempty + acc, aph ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_c = tmem_base + ACC_COL0 + acc * BN;
+                for (uint32_t s = 0; s < p.nslab; s++, it++) {
+                    const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
+                    mbar_wait(bar_full + stage, ph);
+                    tc_fence_after();
+                    const uint64_t xd = x_desc0 + static_cast<uint64_t>(stage * NB) * SLAB_DESC;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < KSTEPS; k++) {
+                            const uint32_t first = (s | static_cast<uint32_t>(k)) != 0 ? 1u : 0u;
+                            const uint32_t a0 = tmem_base + s * 32 + k * 8;
+                            if (KIND == KIND_TF32X3) {
+                                umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
+                                umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
+                                umma_ts<KIND>(tmem_c, a0, xd + SLAB_DESC + 2 * k, idesc, 1u);
+                            } else {
+                                umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
+                                umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
+                                umma_ts<KIND>(tmem_c, a0 + 2 * PIECE_COLS, xd + 2 * k, idesc, 1u);
+                            }
+                        }
+                        umma_commit(bar_empty + stage);
+                        if (s + 1 == p.nslab) umma_commit(bar_tfull + acc);
+                    }
+                    __syncwarp();
+                }
+            }
+        } else {
+            // ================================================================= epilogue (8 warps)
+            const uint2 pr = (row_in_tile < n_in_group) ? p.pairs[pair0 + row_in_tile] : make_uint2(0xFFFFFFFFu, 0u);
+            const bool has_query = pr.x != 0xFFFFFFFFu;
+            // ---- gather this lane's query, split it, store it into TMEM ----
+            {
+                const float* qrow = reinterpret_cast<const float*>(p.queries + static_cast<uint64_t>(has_query ? pr.x : 0) * p.q_bytes);
+                const uint32_t kp = p.nslab * SLAB_ELEMS;
+                if (KIND == KIND_TF32X3) {
+                    // half 0 writes hi = rna_tf32(q) at columns [0,128), half 1 writes lo = rna_tf32(q - hi) at [128,256)
+                    const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + half * PIECE_COLS;
+                    for (uint32_t c = 0; c < kp; c += 32) {
+                        uint32_t w[32];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (has_query && c + 4 * j < p.dim) x = __ldg(reinterpret_cast<const float4*>(qrow + c) + j);   // rows are zero padded to 16 B
+                            float v[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                            for (int e = 0; e < 4; e++) {
+                                const float hi = rna_tf32(v[e]);
+                                w[4 * j + e] = __float_as_uint(half == 0 ? hi : rna_tf32(__fsub_rn(v[e], hi)));
+                            }
+                        }
+                        tmem_st32(tq + c, w);
+                    }
+                } else {
+                    // bf16 terms q0 (half 0), q1 (half 1), q2 (half 0) at columns [0,64), [64,128), [128,192); two elements per column
+                    for (uint32_t pc = half; pc < 3; pc += 2) {
+                        const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + pc * PIECE_COLS;
+                        for (uint32_t c = 0; c < kp / 2; c += 32) {       // c counts 32-bit columns = element pairs
+                            uint32_t w[32];
+#pragma unroll
+                            for (int j = 0; j < 16; j++) {
+                                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (has_query && 2 * c + 4 * j < p.dim) x = __ldg(reinterpret_cast<const float4*>(qrow + 2 * c) + j);
+                                float v[4] = {x.x, x.y, x.z, x.w};
+                                uint32_t b[4];
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    const __nv_bfloat16 b0 = __float2bfloat16_rn(v[e]);
+                                    const float r1 = __fsub_rn(v[e], __bfloat162float(b0));
+                                    const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
+                                    const __nv_bfloat16 b2 = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(b1)));
+                                    const __nv_bfloat16 sel = pc == 0 ? b0 : (pc == 1 ? b1 : b2);
+                                    b[e] = static_cast<uint32_t>(__bfloat16_as_ushort(sel));
+                                }
+                                w[2 * j] = b[0] | (b[1] << 16);
+                                w[2 * j + 1] = b[2] | (b[3] << 16);
+                            }
+                            tmem_st32(tq + c, w);
+                        }
+                    }
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(bar_q);
+            }
+            top.init();
+            uint32_t* gtau_ptr = p.gtau + (has_query ? pr.x : 0);
+            uint32_t g_next = has_query ? *reinterpret_cast<volatile uint32_t*>(gtau_ptr) : 0u;   // 0 = ordered(-NaN): prunes everything
+            const float* aux_half = p.aux + r_begin + half * 64 + lane;
+            auto load_aux = [&](uint32_t t, float& lo_v, float& hi_v) {
+                const uint64_t c0 = r_begin + static_cast<uint64_t>(t) * BN + half * 64 + lane;
+                lo_v = (c0 < r_end) ? __ldg(aux_half + static_cast<size_t>(t) * BN) : __int_as_float(0x7FC00000);        // NaN masks rows of other lists
+                hi_v = (c0 + 32 < r_end) ? __ldg(aux_half + static_cast<size_t>(t) * BN + 32) : __int_as_float(0x7FC00000);
+            };
+            float aux_lo_next = 0.f, aux_hi_next = 0.f;
+            if (n_tiles > 0) load_aux(0, aux_lo_next, aux_hi_next);
+            for (uint32_t t = 0; t < n_tiles; t++, tg++) {
+                const uint32_t acc = tg % NACC, aph = (tg / NACC) & 1u;
+                const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
+                const uint32_t g_bits = g_next;
+                const float aux_lo = aux_lo_next, aux_hi = aux_hi_next;
+                if (t + 1 < n_tiles) {
+                    load_aux(t + 1, aux_lo_next, aux_hi_next);
+                    if (has_query) g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
+                }
+                mbar_wait(bar_tfull + acc, aph);
+                tc_fence_after();
+                const float g_tau = has_query ? ordered_to_f32(g_bits) : -INFINITY;   // lanes without a query never select
+                float tau = fminf(top.tau(), g_tau);
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + ACC_COL0 + acc * BN;
+                {
+                    const int c = static_cast<int>(half);
+                    uint32_t r[64];
+                    tmem_ld32(taddr + c * 64, r);
+                    tmem_ld32(taddr + c * 64 + 32, r + 32);
+                    tmem_ld_wait();
+                    float v[64];
+                    float gm[8];
+#pragma unroll
+                    for (int g = 0; g < 8; g++) {
+                        float mg = INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const int col = g * 8 + j;
+                            const float cst = __shfl_sync(0xFFFFFFFFu, col < 32 ? aux_lo : aux_hi, col & 31);
+                            const float sdot = __uint_as_float(r[col]);
+                            v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
+                            mg = fminf(mg, v[col]);
+                        }
+                        gm[g] = mg;
+                    }
+                    const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
+                    if (m < tau) {
+#pragma unroll
+                        for (int j = 0; j < 64; j++) scratch[j] = v[j];
+                        uint32_t gmask = 0;
+#pragma unroll
+                        for (int g = 0; g < 8; g++) gmask |= (gm[g] < tau) ? (1u << g) : 0u;
+                        while (gmask) {
+                            const int g = __ffs(gmask) - 1;
+                            gmask &= gmask - 1;
+                            float s8[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) s8[j] = scratch[g * 8 + j];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                if (s8[j] < tau) {
+                                    top.insert(s8[j], row0 + c * 64 + g * 8 + j);
+                                    tau = fminf(tau, top.tau());
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar_tempty + acc);
+                if (has_query && (top.tau() < g_tau || (g_tau != g_tau && top.tau() < INFINITY))) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));
+            }
+            if (has_query) {
+                uint64_t* out = p.part_keys + ((static_cast<uint64_t>(pr.x) * p.probe_pitch + pr.y) * 2 + half) * KP;
+#pragma unroll
+                for (int j = 0; j < KP; j++) out[j] = (top.i[j] == IDX_INVALID) ? KEY_SENTINEL : make_key(top.v[j], top.i[j]);
+            }
+        }
+        task_no++;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+}  // namespace tc
+
+// =============================================================================================== host side
+// (EncodeTiled / tensor-map helpers live in flat_tc.cu)
+int tc_make_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint32_t kp_elems, int elem_bytes);
+uint32_t tc_blocks_for(uint64_t work);
+
+struct IvfTcState {
+    int kind = -1;
+    uint32_t kp_elems = 0, nslab = 0, n_pad = 0;
+    void* d_x = nullptr;
+    float* d_aux = nullptr;
+    CUtensorMap tm_x;
+    DevBuf part, gtau;
+    uint64_t bytes = 0;
+};
+
+int tc_ivf_prepare(annb_index* ix) {
+    if (!ix->is_ivf || ix->dtype == ANNB_SQ8 || ix->n == 0) return ANNB_OK;
+    const int kind = ix->dtype == ANNB_F32 ? tc::KIND_TF32X3 : tc::KIND_BF16;
+    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : 2;
+    const uint32_t slab_elems = tc::SLAB_BYTES / elem;
+    const uint32_t kp = round_up(ix->dim, slab_elems);
+    if (kp * elem > 512) return ANNB_OK;     // query piece must fit its TMEM column budget; larger dims stay on the CUDA-core scan
+    IvfTcState* st = new IvfTcState();
+    ix->tc_ivf = st;
+    st->kind = kind;
+    st->kp_elems = kp;
+    st->nslab = kp / slab_elems;
+    st->n_pad = static_cast<uint32_t>(round_up<uint64_t>(ix->n, tc::BN)) + tc::BN;   // tiles may start anywhere: one extra tile of padding
+    cudaStream_t s = ix->stream;
+    const uint64_t aux_rows = static_cast<uint64_t>(st->n_pad) + tc::BN;
+    {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&st->d_aux), aux_rows * sizeof(float));
+        if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc aux: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
+        st->bytes += aux_rows * sizeof(float);
+    }
+    tc::aux_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(ix->d_rows, ix->row_bytes, kind == tc::KIND_BF16, ix->dim,
+                                                                                ix->metric == ANNB_COSINE ? ix->d_norms : nullptr, ix->n, aux_rows, st->d_aux);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    uint64_t xrows = 0;
+    if (kind == tc::KIND_TF32X3) {
+        const uint64_t bytes = 2ull * st->n_pad * kp * 4;
+        cudaError_t e = cudaMalloc(&st->d_x, bytes);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
+        st->bytes += bytes;
+        tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * kp), 256, 0, s>>>(reinterpret_cast<const float*>(ix->d_rows), ix->row_bytes / 4, ix->dim,
+                                                                                                   ix->n, st->n_pad, kp, static_cast<float*>(st->d_x));
+        xrows = 2ull * st->n_pad;
+    } else {
+        const uint64_t bytes = static_cast<uint64_t>(st->n_pad) * kp * 2;
+        cudaError_t e = cudaMalloc(&st->d_x, bytes);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
+        st->bytes += bytes;
+        tc::pad_bf16_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * kp), 256, 0, s>>>(reinterpret_cast<const uint16_t*>(ix->d_rows), ix->row_bytes / 2, ix->dim,
+                                                                                                 ix->n, st->n_pad, kp, static_cast<uint16_t*>(st->d_x));
+        xrows = st->n_pad;
+    }
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    ANNB_TRY(tc_make_tmap(&st->tm_x, st->d_x, xrows, kp, elem));
+    ix->device_bytes += st->bytes;
+    return ANNB_OK;
+}
+
+void tc_ivf_destroy(annb_index* ix) {
+    if (!ix->tc_ivf) return;
+    cudaFree(ix->tc_ivf->d_x);
+    cudaFree(ix->tc_ivf->d_aux);
+    ix->tc_ivf->part.release();
+    ix->tc_ivf->gtau.release();
+    delete ix->tc_ivf;
+    ix->tc_ivf = nullptr;
+}
+
+bool tc_ivf_supported(const annb_index* ix, int qt, uint32_t k_eff) {
+    return ix->tc_ivf != nullptr && qt == QT_F32 && k_eff <= 24;
+}
+
+uint32_t tc_ivf_kprime(const annb_index* ix, uint32_t k_eff) {
+    if (ix->opt_tc_candidates == 32) return 32;
+    return k_eff <= 10 ? 16 : 32;
+}
+
+template <int KIND, int KP, int MET>
+static int launch_ivf_tc(const CUtensorMap& tmx, const tc::IvfTcParams& p, uint32_t grid, size_t smem, cudaStream_t s) {
+    auto kern = tc::ivf_tc_kernel<KIND, KP, MET>;
+    ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, tc::NUM_THREADS, smem, s>>>(tmx, p);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    return ANNB_OK;
+}
+
+template <int RT, int MET>
+static int launch_ivf_rerank(const tc::RerankParams& r, cudaStream_t s) {
+    auto kern = tc::rerank_kernel<RT, QT_F32, MET>;
+    const size_t smem = static_cast<size_t>(r.nsort) * 8;
+    if (smem > 200 * 1024) { set_last_error("ivf rerank: nprobe * k' too large"); return ANNB_ERR_UNSUPPORTED; }
+    ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<static_cast<uint32_t>(r.nq), 128, smem, s>>>(r);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    return ANNB_OK;
+}
+
+// Scan + exact re-rank.  The pair buckets (grouped by list, 128 pairs per task) were built by the caller.
+int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t nq, uint32_t k_eff, uint32_t k_out, uint32_t probe_pitch,
+                const uint32_t* d_pair_off, const uint32_t* d_task_off, const void* d_pairs, uint32_t* d_task_counter, uint64_t max_tasks,
+                const uint32_t* d_n_probes, const uint64_t* row_map, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s) {
+    IvfTcState* st = ix->tc_ivf;
+    const uint32_t kprime = tc_ivf_kprime(ix, k_eff);
+    const uint32_t nb = st->kind == tc::KIND_TF32X3 ? 2 : 1;
+    const size_t fixed = 512;
+    const size_t budget = 227 * 1024;
+    uint32_t stages = static_cast<uint32_t>(std::min<size_t>(8, (budget - fixed) / (nb * tc::SLAB_TILE)));
+    const size_t smem = static_cast<size_t>(stages) * nb * tc::SLAB_TILE + fixed;
+    const uint64_t slots = nq * static_cast<uint64_t>(probe_pitch) * 2;
+    ANNB_TRY(st->part.ensure(slots * kprime * 8));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(st->part.p, 0xFF, slots * kprime * 8, s));
+    ANNB_TRY(st->gtau.ensure(nq * 4 + 16));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(st->gtau.p, 0xFF, nq * 4 + 16, s));
+    tc::IvfTcParams p{};
+    p.queries = d_q; p.q_bytes = q_bytes; p.dim = ix->dim; p.nslab = st->nslab; p.n_stages = stages; p.n_pad = st->n_pad; p.aux = st->d_aux;
+    p.offsets = ix->d_offsets; p.shard_row0 = ix->shard_row0; p.nlist = ix->nlist; p.pair_off = d_pair_off; p.task_off = d_task_off;
+    p.pairs = static_cast<const uint2*>(d_pairs); p.task_counter = d_task_counter; p.probe_pitch = probe_pitch;
+    p.part_keys = st->part.as<uint64_t>(); p.gtau = st->gtau.as<uint32_t>();
+    const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(max_tasks, 1), 148));
+    const bool l2 = ix->metric == ANNB_L2;
+    {
+        cudaEvent_t ea = nullptr, eb = nullptr;
+        if (ix->opt_time_kernels && cudaEventCreate(&ea) == cudaSuccess && cudaEventCreate(&eb) == cudaSuccess) cudaEventRecord(ea, s);
+        int rc;
+#define ANNB_IVF_TC(KIND_, KP_) (l2 ? launch_ivf_tc<KIND_, KP_, MET_L2>(st->tm_x, p, grid, smem, s) : launch_ivf_tc<KIND_, KP_, MET_COS>(st->tm_x, p, grid, smem, s))
+        if (st->kind == tc::KIND_TF32X3) rc = kprime == 16 ? ANNB_IVF_TC(tc::KIND_TF32X3, 16) : ANNB_IVF_TC(tc::KIND_TF32X3, 32);
+        else rc = kprime == 16 ? ANNB_IVF_TC(tc::KIND_BF16, 16) : ANNB_IVF_TC(tc::KIND_BF16, 32);
+#undef ANNB_IVF_TC
+        if (ea && eb) { cudaEventRecord(eb, s); ix->timed.emplace_back(ea, eb); }
+        ANNB_TRY(rc);
+        ix->stat_launches++;
+    }
+    tc::RerankParams r{};
+    r.part_keys = st->part.as<uint64_t>(); r.parts = probe_pitch * 2; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out;
+    r.nsort = next_pow2(std::max(probe_pitch * 2 * kprime, 64u));
+    r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
+    r.bf16_self = 0; r.id_base = 0; r.parts_used = d_n_probes; r.part_mult = 2; r.id_map = ix->d_original_ids; r.row_map = row_map;
+    r.out_ids = d_ids; r.out_dist = d_dist; r.out_counts = d_cnt;
+    int rc;
+    if (ix->dtype == ANNB_F32) rc = l2 ? launch_ivf_rerank<0, MET_L2>(r, s) : launch_ivf_rerank<0, MET_COS>(r, s);
+    else rc = l2 ? launch_ivf_rerank<1, MET_L2>(r, s) : launch_ivf_rerank<1, MET_COS>(r, s);
+    ANNB_TRY(rc);
+    ix->stat_launches++;
+    return ANNB_OK;
+}
+
+}  // namespace annb

@@ -373,7 +373,8 @@ struct PairParams {
     uint32_t* cnt;             // [nlist]   pairs per list (zeroed by the caller)
     uint32_t* cursor;          // [nlist]
     uint32_t* pair_off;        // [nlist+1]
-    uint32_t* task_off;        // [nlist+1] prefix sum of ceil(cnt / CTA_QUERIES)
+    uint32_t* task_off;        // [nlist+1] prefix sum of ceil(cnt / group)
+    uint32_t group;            // queries per task (32 for the CUDA-core kernel, 128 for the tensor-core kernel)
     uint2* pairs;              // [sum cnt] (query, rank) grouped by list
     uint32_t* task_counter;    // persistent-CTA work counter (zeroed by the caller)
 };
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(1024) ivf_pair_offsets_kernel(PairParams p) {
     const uint32_t per = (p.nlist + 1023) / 1024;
     const uint32_t lo = min(p.nlist, threadIdx.x * per), hi = min(p.nlist, lo + per);
     uint32_t a = 0, b = 0;
-    for (uint32_t c = lo; c < hi; c++) { a += p.cnt[c]; b += (p.cnt[c] + CTA_QUERIES - 1) / CTA_QUERIES; }
+    for (uint32_t c = lo; c < hi; c++) { a += p.cnt[c]; b += (p.cnt[c] + p.group - 1) / p.group; }
     s_pairs[threadIdx.x] = a;
     s_tasks[threadIdx.x] = b;
     __syncthreads();
@@ -408,7 +409,7 @@ __global__ void __launch_bounds__(1024) ivf_pair_offsets_kernel(PairParams p) {
     b = s_tasks[threadIdx.x];
     for (uint32_t c = lo; c < hi; c++) {
         p.pair_off[c] = a; p.cursor[c] = a; p.task_off[c] = b;
-        a += p.cnt[c]; b += (p.cnt[c] + CTA_QUERIES - 1) / CTA_QUERIES;
+        a += p.cnt[c]; b += (p.cnt[c] + p.group - 1) / p.group;
     }
 }
 __global__ void ivf_fill_pairs_kernel(PairParams p) {

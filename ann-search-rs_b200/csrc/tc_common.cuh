@@ -1,0 +1,358 @@
+// tc_common.cuh -- shared pieces of the tensor-core (tcgen05 / TMEM / TMA) kernels: PTX wrappers, UMMA descriptors,
+// the per-thread k' list, operand-preparation kernels and the exact re-rank kernel.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+#include "refdist.cuh"
+#include "select.cuh"
+
+namespace annb {
+
+namespace tc {
+
+constexpr int BM = 128;              // queries per CTA (UMMA M, TMEM lanes)
+constexpr int BN = 128;              // database rows per MMA tile (UMMA N, TMEM columns per accumulator)
+constexpr int SLAB_BYTES = 128;      // K extent of one smem slab = one 128-byte swizzle atom
+constexpr int SLAB_TILE = BM * SLAB_BYTES;  // 16 KiB: 128 rows x 128 B
+constexpr int NUM_THREADS = 320;        // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int EPI_THREADS = 256;        // two warps per TMEM lane quarter, each owning one 64-column half of the tile
+constexpr int ACC_STAGES = 4;          // accumulator ring in TMEM (4 x 128 columns = all 512)
+constexpr int AUX_STAGES = 2;
+constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 512
+
+enum { KIND_TF32X3 = 0, KIND_BF16 = 1 };
+
+struct Params {
+    uint64_t nq;
+    uint64_t n_rows;
+    uint32_t nq_pad;          // rows per query piece in the stacked query operand
+    uint32_t n_pad;           // rows per database piece in the stacked database operand
+    uint32_t nslab;           // K slabs (KP * elem / 128)
+    uint32_t n_stages;        // database ring depth
+    uint32_t n_splits;
+    uint64_t rows_per_split;  // multiple of BN
+    uint32_t a_pieces;        // query terms actually present (bf16 self query: 1)
+    const float* aux;         // per database row: L2  v = aux - 2 s  (aux = |x|^2, pad rows +inf);
+                              //                   cos v = s * aux    (aux = -1/|x|, pad rows +inf -> 0 * inf = NaN, never selected)
+    uint64_t* part_keys;      // [nq][2 * n_splits][KPRIME] packed (approx value, row); one list per 64-column half
+    const void* q_op;         // stacked query operand [a_pieces][nq_pad][kp] (TS mode loads it into TMEM)
+    uint32_t kp;              // padded K in elements
+    uint32_t* gtau;           // [nq_pad] shared pruning threshold per query (order-preserving image, atomicMin)
+    float* dbg;               // optional: CTA (0,0) dumps v of its first tile [BM][BN]
+    unsigned long long* dbg_cycles;  // optional: CTA (0,0) wait-cycle counters {total, prod_empty, mma_full, mma_tempty, epi_tfull, epi_slow}
+};
+
+// ----------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, long long& acc) {
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    acc += clock64() - t0;
+}
+// One lane of a converged warp (elect.sync): lets the compiler keep the surrounding values in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* tm, uint64_t* bar, int32_t x, int32_t y) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_dst),
+                 "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int KIND>
+__device__ __forceinline__ void umma(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == KIND_TF32X3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+}
+// 32 lanes x 32 columns of 32-bit accumulators: thread i of the warp receives columns [c, c+32) of TMEM lane base+i.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// A operand from TMEM (row m of A = TMEM lane m, K along columns), B from shared memory.
+template <int KIND>
+__device__ __forceinline__ void umma_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == KIND_TF32X3)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_c),
+                     "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_c),
+                     "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t r[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "
+        "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+        "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
+        "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor: K-major operand tile, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart.
+// (field layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    return static_cast<uint64_t>((saddr >> 4) & 0x3FFFu) | (1ull << 16)  // LBO (unused for swizzled K-major)
+           | (static_cast<uint64_t>(1024 >> 4) << 32)                    // SBO = 1024 B
+           | (1ull << 46)                                                // descriptor version (Blackwell)
+           | (2ull << 61);                                               // SWIZZLE_128B
+}
+// UMMA instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): f32 accumulate, K-major A and B.
+__host__ __device__ constexpr uint32_t make_idesc(int kind) {
+    const uint32_t fmt = (kind == KIND_TF32X3) ? 2u : 1u;  // TF32 = 2, BF16 = 1
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------------------------- per-thread k' list
+template <int KP>
+struct TopList {
+    float v[KP];
+    uint32_t i[KP];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < KP; j++) { v[j] = INFINITY; i[j] = IDX_INVALID; }
+    }
+    __device__ __forceinline__ float tau() const { return v[KP - 1]; }
+    // requires x < tau(); keeps ascending order, earlier entries win ties
+    __device__ __forceinline__ void insert(float x, uint32_t idx) {
+#pragma unroll
+        for (int j = KP - 1; j > 0; j--) {
+            const bool shift = v[j - 1] > x;           // element j-1 moves down to j
+            const bool here = !shift && (v[j] > x);    // x lands at j
+            v[j] = shift ? v[j - 1] : (here ? x : v[j]);
+            i[j] = shift ? i[j - 1] : (here ? idx : i[j]);
+        }
+        if (v[0] > x) { v[0] = x; i[0] = idx; }
+    }
+};
+
+
+// ----------------------------------------------------------------------------------------------- operand preparation
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+// f32 rows (pitch ld_src floats) -> stacked [2][rows_pad][kp] tf32 hi / lo, zero padded.
+static __global__ void split_tf32_kernel(const float* __restrict__ src, uint32_t ld_src, uint32_t dim, uint64_t rows, uint64_t rows_pad, uint32_t kp,
+                                  float* __restrict__ dst) {
+    const uint64_t total = rows_pad * kp;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t r = i / kp;
+        const uint32_t c = static_cast<uint32_t>(i - r * kp);
+        float hi = 0.f, lo = 0.f;
+        if (r < rows && c < dim) {
+            const float x = src[r * ld_src + c];
+            hi = rna_tf32(x);
+            lo = rna_tf32(__fsub_rn(x, hi));
+        }
+        dst[i] = hi;
+        dst[total + i] = lo;
+    }
+}
+// f32 queries -> stacked [3][rows_pad][kp] bf16 terms q0 + q1 + q2 (each RNE), zero padded.
+static __global__ void split_bf16x3_kernel(const float* __restrict__ src, uint32_t ld_src, uint32_t dim, uint64_t rows, uint64_t rows_pad, uint32_t kp,
+                                    __nv_bfloat16* __restrict__ dst) {
+    const uint64_t total = rows_pad * kp;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t r = i / kp;
+        const uint32_t c = static_cast<uint32_t>(i - r * kp);
+        __nv_bfloat16 b0 = __float2bfloat16_rn(0.f), b1 = b0, b2 = b0;
+        if (r < rows && c < dim) {
+            const float x = src[r * ld_src + c];
+            b0 = __float2bfloat16_rn(x);
+            const float r1 = __fsub_rn(x, __bfloat162float(b0));
+            b1 = __float2bfloat16_rn(r1);
+            b2 = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(b1)));
+        }
+        dst[i] = b0;
+        dst[total + i] = b1;
+        dst[2 * total + i] = b2;
+    }
+}
+// bf16 rows (pitch ld_src elements) -> [rows_pad][kp] bf16, zero padded (database operand / bf16 self queries).
+static __global__ void pad_bf16_kernel(const uint16_t* __restrict__ src, uint32_t ld_src, uint32_t dim, uint64_t rows, uint64_t rows_pad, uint32_t kp,
+                                uint16_t* __restrict__ dst) {
+    const uint64_t total = rows_pad * kp;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t r = i / kp;
+        const uint32_t c = static_cast<uint32_t>(i - r * kp);
+        dst[i] = (r < rows && c < dim) ? src[r * ld_src + c] : static_cast<uint16_t>(0);
+    }
+}
+// Epilogue constants per database row.  L2: (-2, |x|^2) with |x|^2 of the stored (possibly bf16-rounded) row;
+// cosine: (-1/norm, 0) with the index norm (f32 norm of the un-rounded row, as the reference divides by it).
+static __global__ void aux_kernel(const uint8_t* __restrict__ rows, uint32_t row_bytes, int is_bf16, uint32_t dim, const float* __restrict__ norms,
+                           uint64_t n, uint64_t n_pad_total, float* __restrict__ aux) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n_pad_total) return;
+    float o = INFINITY;
+    if (i < n) {
+        if (norms) {
+            o = -1.0f / norms[i];
+        } else {
+            float s = 0.f;
+            const uint8_t* r = rows + i * row_bytes;
+            for (uint32_t e = 0; e < dim; e++) {
+                const float x = is_bf16 ? bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(r)[e]) : reinterpret_cast<const float*>(r)[e];
+                s = fmaf(x, x, s);
+            }
+            o = s;
+        }
+    }
+    aux[i] = o;
+}
+
+// ----------------------------------------------------------------------------------------------- exact re-rank + merge
+struct RerankParams {
+    const uint64_t* part_keys;  // [nq][parts][kp] approximate keys
+    uint32_t parts, kp, k_eff, k_out, nsort;
+    uint64_t nq;
+    const uint8_t* rows;  // index rows in the index dtype
+    uint32_t row_bytes;
+    const float* row_norms;
+    const uint8_t* queries;  // prepared queries (f32 padded rows, or bf16 rows for self queries)
+    uint32_t q_bytes;
+    uint32_t dim;
+    int bf16_self;
+    uint64_t id_base;
+    const uint32_t* parts_used;  // optional [nq]: only the first parts_used[q] * part_mult lists of a query hold data (IVF probe ranks)
+    uint32_t part_mult;
+    const uint64_t* id_map;      // optional: id = id_map[row] (IVF original ids) instead of row + id_base
+    const uint64_t* row_map;     // optional: output row of query q
+    uint64_t* out_ids;
+    float* out_dist;
+    uint32_t* out_counts;
+};
+
+// One CTA per query: merge the per-split candidate lists by approximate value, keep the best kp, recompute their
+// distances exactly (reference order, bit-identical to the CPU path), order by (distance, id) and emit k.
+template <int RT, int QT, int MET>
+__global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
+    __shared__ uint64_t exact[64];
+    const uint64_t q = blockIdx.x;
+    const uint32_t parts_q = p.parts_used ? min(p.parts, p.parts_used[q] * p.part_mult) : p.parts;
+    const uint32_t total = parts_q * p.kp;
+    const uint32_t nsort = min(p.nsort, next_pow2(max(total, 64u)));
+    const uint64_t* src = p.part_keys + q * (static_cast<uint64_t>(p.parts) * p.kp);
+    for (uint32_t i = threadIdx.x; i < nsort; i += blockDim.x) keys[i] = (i < total) ? src[i] : KEY_SENTINEL;
+    __syncthreads();
+    bitonic_sort_keys<true>(keys, nsort, threadIdx.x, blockDim.x);
+    const uint64_t orow = p.row_map ? p.row_map[q] : q;
+    if (threadIdx.x < 64) {
+        uint64_t ek = KEY_SENTINEL;
+        if (threadIdx.x < p.kp) {
+            const uint64_t key = keys[threadIdx.x];
+            const uint32_t idx = key_idx(key);
+            if (idx != IDX_INVALID) {
+                const uint8_t* row = p.rows + static_cast<uint64_t>(idx) * p.row_bytes;
+                const uint8_t* qv = p.queries + q * p.q_bytes;
+                float raw[1];
+                accumulate_fp<(RT == 0) ? 4 : 2, (QT == QT_F32) ? 4 : 2, MET == MET_L2, 1>(row, qv, p.q_bytes, p.dim, raw);
+                float qn = 1.0f, xn = 1.0f;
+                if (MET == MET_COS) {
+                    qn = seq_norm<(QT == QT_F32) ? 4 : 2>(qv, p.dim);
+                    if (p.bf16_self) qn = round_to_bf16(qn);
+                    xn = p.row_norms[idx];
+                }
+                ek = make_key(finish_fp<MET>(raw[0], qn, xn), idx);
+            }
+        }
+        exact[threadIdx.x] = ek;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) bitonic_sort_keys<false>(exact, 64, threadIdx.x, 32);
+    __syncthreads();
+    uint32_t valid = 0;
+    for (uint32_t j = threadIdx.x; j < p.k_out; j += blockDim.x) {
+        uint64_t key = (j < p.k_eff && j < 64) ? exact[j] : KEY_SENTINEL;
+        uint64_t id = 0xFFFFFFFFFFFFFFFFull;
+        float d = INFINITY;
+        if (key_idx(key) != IDX_INVALID) {
+            id = p.id_map ? p.id_map[key_idx(key)] : static_cast<uint64_t>(key_idx(key)) + p.id_base;
+            d = key_dist(key);
+            valid++;
+        }
+        p.out_ids[orow * p.k_out + j] = id;
+        if (p.out_dist) p.out_dist[orow * p.k_out + j] = d;
+    }
+    if (p.out_counts) {
+        __shared__ uint32_t s_cnt;
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        if (valid) atomicAdd(&s_cnt, valid);
+        __syncthreads();
+        if (threadIdx.x == 0) p.out_counts[orow] = s_cnt;
+    }
+}
+
+}  // namespace tc
+
+}  // namespace annb

@@ -57,8 +57,14 @@ def test_exact_parity_external_queries(gpu, dtype, metric, n, dim, nlist, nq, k,
     ref = o.ivf_search(c, q, k, nprobe=nprobe)
     _check(dtype, got, ref, f"ivf {dtype} {metric} n={n} dim={dim} nprobe={nprobe}")
     assert g.get_stat("scanned_vectors") == int(ref[4].sum())
-    g.set_option("ivf_list_major", 1)      # list-major batched scan: (list, 32-query group) tasks
-    _check(dtype, g.query_batch(q, k, nprobe=nprobe), ref, "list-major scan")
+    g.set_option("ivf_list_major", 1)      # list-major batched scans: (list, query group) tasks
+    g.set_option("path", annb200.PATH_SIMT)
+    _check(dtype, g.query_batch(q, k, nprobe=nprobe), ref, "list-major CUDA-core scan")
+    if dtype != "sq8" and k <= 24:         # tensor-core grouped scan (tcgen05) + exact re-rank
+        g.set_option("path", annb200.PATH_TENSOR)
+        _check(dtype, g.query_batch(q, k, nprobe=nprobe), ref, "list-major tensor-core scan")
+        assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    g.set_option("path", annb200.PATH_AUTO)
     g.set_option("ivf_list_major", 0)      # query-major streaming scan: one warp per (query, part)
     for parts in (1, 3):       # result must not depend on how probes are split across warps
         g.set_option("scan_parts", parts)
