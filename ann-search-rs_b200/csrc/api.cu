@@ -295,9 +295,50 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
     const uint32_t nl2 = next_pow2(ix->nlist);
     if (static_cast<size_t>(nl2) * 8 > 200 * 1024) return fail(ANNB_ERR_UNSUPPORTED, "nlist > 16384 is not supported yet");
 
+    // 1+2 (fast path). rank only the `pitch` nearest centroids: the tile kernel's fused select replaces the dense
+    //      [nq][nlist] matrix and the full per-query sort; a one-thread-per-query walk applies the probe-expansion rule.
+    ANNB_TRY(ix->s_flags.ensure(64));
+    ANNB_TRY(ix->s_nprobes.ensure(nq * 4));
+    // ranked prefix length: room for probe expansion (>= nprobe + 16 cells) and pitch + 64 a power of two, so the fused
+    // select's sort buffer is exactly full (smaller shared memory -> more resident CTAs)
+    uint32_t pitch = ix->nlist <= 1024 ? ix->nlist : std::min(ix->nlist, next_pow2(np + 16 + 64) - 64);
+    bool probes_ready = false;
+    // (wide prefixes make the fused select's sort buffers large and its pass rate high: above 64 ranks the dense matrix + sort wins)
+    if (pitch < ix->nlist && (ix->opt_ivf_fast_probe == 1 ? pitch <= 64 : ix->opt_ivf_fast_probe != 0)) {
+        const uint32_t nsort = WarpSelect::sort_size(pitch);
+        const uint32_t cb = ix->cent_ld * 4, qb = pq.route_ld * 4;
+        const size_t smem = tile_kernel_smem(cb, qb, nsort, true);
+        if (smem <= 200 * 1024) {
+            ANNB_TRY(ix->s_cdist.ensure(nq * static_cast<uint64_t>(pitch) * 8));
+            ANNB_TRY(ix->s_probes.ensure(nq * static_cast<uint64_t>(pitch) * 4));
+            ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 64, s));
+            TileParams p{};
+            p.rows = reinterpret_cast<const uint8_t*>(ix->d_centroids); p.n_rows = ix->nlist; p.row_bytes = cb; p.row_norms = ix->d_centroid_norms;
+            p.queries = reinterpret_cast<const uint8_t*>(pq.route); p.q_bytes = qb; p.nq = nq; p.dim = ix->dim;
+            p.k = pitch; p.nsort = nsort; p.n_splits = 1; p.rows_per_split = round_up<uint64_t>(ix->nlist, TILE_ROWS); p.part_keys = ix->s_cdist.as<uint64_t>();
+            dim3 grid(static_cast<uint32_t>(ceil_div<uint64_t>(nq, CTA_QUERIES)), 1);
+            if (ix->metric == ANNB_L2) ANNB_TRY((launch_tile<0, QT_F32, MET_L2, EPI_SELECT>(p, grid, smem, s)));
+            else if (ix->dtype == ANNB_SQ8) ANNB_TRY((launch_tile<0, QT_F32, MET_COS_PRENORM, EPI_SELECT>(p, grid, smem, s)));
+            else ANNB_TRY((launch_tile<0, QT_F32, MET_COS, EPI_SELECT>(p, grid, smem, s)));
+            ProbeParams pp{};
+            pp.nq = nq; pp.nlist = ix->nlist; pp.offsets = ix->d_offsets; pp.nprobe = np; pp.k = kk;
+            pp.probes = ix->s_probes.as<uint32_t>(); pp.probe_pitch = pitch; pp.n_probes = ix->s_nprobes.as<uint32_t>();
+            pp.overflow = ix->s_flags.as<uint32_t>();
+            pp.stat_scanned = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 8);
+            pp.stat_probed = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 16);
+            probe_walk_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 128)), 128, 0, s>>>(ix->s_cdist.as<uint64_t>(), pp);
+            ANNB_CUDA_CHECK(cudaGetLastError());
+            ix->stat_launches += 2;
+            uint32_t h_flag[2];
+            ANNB_CUDA_CHECK(cudaMemcpyAsync(h_flag, ix->s_flags.p, sizeof(h_flag), cudaMemcpyDeviceToHost, s));
+            ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+            if (!h_flag[0]) probes_ready = true;
+            else pitch = ix->nlist;      // rare: some query needs more than nprobe + 64 cells -> full ranking below
+        }
+    }
     // 1. query -> all centroids (dense), reference arithmetic of get_centroids_dist / _prenorm
-    ANNB_TRY(ix->s_cdist.ensure(nq * static_cast<uint64_t>(ix->nlist) * 4));
-    {
+    if (!probes_ready) ANNB_TRY(ix->s_cdist.ensure(nq * static_cast<uint64_t>(ix->nlist) * 4));
+    if (!probes_ready) {
         TileParams p{};
         p.rows = reinterpret_cast<const uint8_t*>(ix->d_centroids); p.n_rows = ix->nlist; p.row_bytes = ix->cent_ld * 4;
         p.row_norms = ix->d_centroid_norms;
@@ -310,15 +351,12 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         else ANNB_TRY((launch_tile<0, QT_F32, MET_COS, EPI_DENSE>(p, grid, smem, s)));
         ix->stat_launches++;
     }
-    // 2. rank + probe expansion
-    ANNB_TRY(ix->s_flags.ensure(64));
-    ANNB_TRY(ix->s_nprobes.ensure(nq * 4));
-    uint32_t pitch = ix->nlist <= 1024 ? ix->nlist : std::min(ix->nlist, np + 64);
-    for (int attempt = 0; attempt < 2; attempt++) {
+    // 2. rank + probe expansion (full per-query sort)
+    for (int attempt = 0; attempt < 2 && !probes_ready; attempt++) {
         ANNB_TRY(ix->s_probes.ensure(nq * static_cast<uint64_t>(pitch) * 4));
         ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 64, s));
         ProbeParams pp{};
-        pp.cdist = ix->s_cdist.as<float>(); pp.nlist = ix->nlist; pp.nlist_pow2 = nl2; pp.offsets = ix->d_offsets;
+        pp.cdist = ix->s_cdist.as<float>(); pp.nq = nq; pp.nlist = ix->nlist; pp.nlist_pow2 = nl2; pp.offsets = ix->d_offsets;
         pp.nprobe = np; pp.k = kk; pp.probes = ix->s_probes.as<uint32_t>(); pp.probe_pitch = pitch;
         pp.n_probes = ix->s_nprobes.as<uint32_t>();
         pp.overflow = ix->s_flags.as<uint32_t>();
@@ -340,9 +378,13 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
     // 3. list scan.  A batch that probes every list many times goes list-major (one staged list tile serves up to 32
     //    queries); small batches keep the query-major streaming kernel (one warp per query part).
     const uint64_t n_local_lists = std::max<uint32_t>(1, ix->list_end - ix->list_begin);
-    const bool list_major = ix->opt_ivf_list_major == 1 || (ix->opt_ivf_list_major < 0 && nq * static_cast<uint64_t>(np) >= 8 * n_local_lists);
+    // the merge kernels sort all per-(query, rank) lists of a query in shared memory: very wide probe sets go query-major
+    const bool merge_fits_simt = static_cast<uint64_t>(pitch) * kk * 8 <= 192 * 1024;
+    const bool merge_fits_tc = static_cast<uint64_t>(pitch) * 2 * (kk <= 10 ? 16 : 32) * 8 <= 192 * 1024;
+    const bool list_major = merge_fits_simt &&
+                            (ix->opt_ivf_list_major == 1 || (ix->opt_ivf_list_major < 0 && nq * static_cast<uint64_t>(np) >= 8 * n_local_lists));
     if (list_major) {
-        const bool use_tc = ix->opt_path != ANNB_PATH_SIMT && tc_ivf_supported(ix, pq.qt, kk);
+        const bool use_tc = ix->opt_path != ANNB_PATH_SIMT && merge_fits_tc && tc_ivf_supported(ix, pq.qt, kk);
         if (!use_tc && ix->opt_path == ANNB_PATH_TENSOR)
             return fail(ANNB_ERR_UNSUPPORTED, "tensor path requested but this IVF (dtype, dim, k, query type) is not covered by it yet");
         ix->stat_last_path = use_tc ? ANNB_PATH_TENSOR : ANNB_PATH_SIMT;
@@ -853,6 +895,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "db_splits") ix->opt_db_splits = static_cast<int>(value);
     else if (k == "scan_parts") ix->opt_scan_parts = static_cast<int>(value);
     else if (k == "ivf_list_major") ix->opt_ivf_list_major = static_cast<int>(value);
+    else if (k == "ivf_fast_probe") ix->opt_ivf_fast_probe = static_cast<int>(value);
     else if (k == "time_kernels") { ix->opt_time_kernels = static_cast<int>(value); ix->timed_ms_total = 0.0; ix->timed_launches = 0; }
     else return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown option " + k);
     return ANNB_OK;

@@ -76,6 +76,7 @@ struct annb_index {
     int opt_tc_ts = 1;         // tensor path, f32: keep the query operand in TMEM (TS-mode MMA)
     int opt_db_splits = 0;
     int opt_scan_parts = 0;
+    int opt_ivf_fast_probe = 1;   // rank only nprobe + 64 centroids with the fused select (0: always dense matrix + full sort)
     int opt_ivf_list_major = -1;  // -1 auto, 0 query-major scan, 1 list-major scan
     int opt_time_kernels = 0;  // record CUDA events around the dominant kernel of every search
 

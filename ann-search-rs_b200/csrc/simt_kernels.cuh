@@ -583,6 +583,7 @@ static inline size_t list_kernel_smem(uint32_t row_bytes, uint32_t q_bytes, uint
 // ---------------------------------------------------------------------------
 struct ProbeParams {
     const float* cdist;      // [nq][nlist]
+    uint64_t nq;
     uint32_t nlist, nlist_pow2;
     const uint64_t* offsets; // [nlist+1]
     uint32_t nprobe;
@@ -622,6 +623,31 @@ __global__ void __launch_bounds__(256) probe_kernel(ProbeParams p) {
     __syncthreads();
     const uint32_t np = min(s_np, p.probe_pitch);
     for (uint32_t i = threadIdx.x; i < np; i += blockDim.x) p.probes[q * p.probe_pitch + i] = key_idx(keys[i]);
+}
+
+// Probe-expansion walk over an already ranked prefix: `ranked` holds, per query, the `pitch` nearest (distance, cell)
+// keys in ascending order (tile_kernel<EPI_SELECT> over the centroid table).  One thread per query applies the
+// select_probed_clusters rule; if the prefix is exhausted before the rule is satisfied the query is flagged and the
+// caller repeats the batch with the full ranking (probe_kernel).
+__global__ void probe_walk_kernel(const uint64_t* __restrict__ ranked, ProbeParams p) {
+    const uint64_t q = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (q >= p.nq) return;
+    const uint64_t* keys = ranked + q * p.probe_pitch;
+    uint32_t chosen = 0;
+    uint64_t reach = 0;
+    bool done = false;
+    for (uint32_t i = 0; i < p.probe_pitch; i++) {
+        const uint32_t c = key_idx(keys[i]);
+        if (c == IDX_INVALID) break;
+        p.probes[q * p.probe_pitch + i] = c;
+        chosen++;
+        reach += p.offsets[c + 1] - p.offsets[c];
+        if (chosen >= p.nprobe && reach >= p.k) { done = true; break; }
+    }
+    if (!done && chosen < p.nlist) atomicExch(p.overflow, 1u);
+    p.n_probes[q] = chosen;
+    atomicAdd(p.stat_scanned, static_cast<unsigned long long>(reach));
+    atomicAdd(p.stat_probed, static_cast<unsigned long long>(chosen));
 }
 
 // ---------------------------------------------------------------------------

@@ -312,11 +312,13 @@ def run_b200(args):
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    torch.cuda.profiler.start()     # `ncu --profile-from-start off` then sees exactly the timed region
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
     e1.record(stream)
     sync_all()
+    torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     dom_ns = index.get_stat("dominant_kernel_ns")
     dom_launches = max(1, index.get_stat("dominant_kernel_launches"))

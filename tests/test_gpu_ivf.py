@@ -153,3 +153,22 @@ def test_mirror_build_and_query(gpu):
     with pytest.raises(annb200.AnnSearchError) as e:
         annb200.build_ivf_index_gpu(data, nlist=8, dist_metric="manhattan")
     assert e.value.variant == "DistanceNotSupported"
+
+
+@pytest.mark.parametrize("dtype", ["f32", "sq8"])
+def test_fast_probe_path_and_overflow_fallback(gpu, dtype):
+    """nlist > 1024 ranks only nprobe + 64 centroids with the fused select; a query that needs more cells than that to
+    reach k vectors (tiny lists) must fall back to the full ranking -- both must equal the oracle."""
+    data = datagen.gaussian_noise(6000, 24, seed=41)
+    q = datagen.subsample_with_noise(data, 96, seed=41)
+    c = o.build_ivf(data, o.L2, nlist=1500, dtype=DT[dtype][1], kmeans_iters=2)      # ~4 vectors per list
+    g = _gpu_from_oracle(c)
+    for k, nprobe in ((10, 8), (10, 40), (200, 1), (5, 1499)):     # (200, 1): needs ~50+ cells; may or may not overflow
+        ref = o.ivf_search(c, q, k, nprobe=nprobe)
+        for fast in (2, 0):      # 2 = force the fused select regardless of the prefix length
+            g.set_option("ivf_fast_probe", fast)
+            _check(dtype, g.query_batch(q, k, nprobe=nprobe), ref, f"fast_probe={fast} k={k} nprobe={nprobe}")
+            assert g.get_stat("scanned_vectors") == int(ref[4].sum())
+    ref = o.ivf_search(c, q, 600, nprobe=1)                        # certainly more than nprobe + 64 cells
+    g.set_option("ivf_fast_probe", 2)
+    _check(dtype, g.query_batch(q, 600, nprobe=1), ref, "overflow fallback")
