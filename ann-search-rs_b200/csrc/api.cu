@@ -243,6 +243,18 @@ static int prepare_self(annb_index* ix, uint64_t pos_begin, uint64_t nq, bool ne
 // ---------------------------------------------------------------------------
 // flat search core (device pointers, asynchronous on s)
 // ---------------------------------------------------------------------------
+static int flat_simt(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint32_t kk, uint64_t* d_ids, float* d_dist,
+                     uint32_t* d_cnt, cudaStream_t s);
+static int read_ivf_stats(annb_index* ix, cudaStream_t s);
+
+// Number of queries of the tensor-path call just issued on `s` that failed the coverage certificate (synchronises s).
+static int read_uncertified(annb_index* ix, uint32_t* out, cudaStream_t s) {
+    *out = 0;
+    if (!ix->opt_cert_fallback || ix->opt_cert_eps <= 0.f || !ix->s_uncert.p) return ANNB_OK;
+    ANNB_CUDA_CHECK(cudaMemcpyAsync(out, ix->s_uncert.p, 4, cudaMemcpyDeviceToHost, s));
+    ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+    return ANNB_OK;
+}
 static int flat_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint64_t* d_ids, float* d_dist,
                      uint32_t* d_cnt, cudaStream_t s) {
     const uint32_t kk = static_cast<uint32_t>(std::min<uint64_t>(k, ix->n));
@@ -255,9 +267,35 @@ static int flat_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uin
     }
     if (use_tc) {
         ix->stat_last_path = ANNB_PATH_TENSOR;
-        return tc_flat_search(ix, pq.scan, pq.scan_bytes, pq.qt, pq.bf16_self, nq, kk, k, d_ids, d_dist, d_cnt, s);
+        ANNB_TRY(tc_flat_search(ix, pq.scan, pq.scan_bytes, pq.qt, pq.bf16_self, nq, kk, k, d_ids, d_dist, d_cnt, s));
+        // queries whose pre-selection could not be certified are recomputed on the exact path (rare)
+        uint32_t n_unc = 0;
+        ANNB_TRY(read_uncertified(ix, &n_unc, s));
+        if (n_unc == 0) return ANNB_OK;
+        const uint32_t* list = ix->s_uncert.as<uint32_t>() + 1;
+        PreparedQueries sub = pq;
+        ANNB_TRY(ix->s_fbq.ensure(static_cast<uint64_t>(n_unc) * pq.scan_bytes));
+        gather_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * (pq.scan_bytes >> 4), 256), 256, 0, s>>>(pq.scan, pq.scan_bytes, list, n_unc, ix->s_fbq.as<uint8_t>());
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        sub.scan = ix->s_fbq.as<uint8_t>();
+        ANNB_TRY(ix->s_fbi.ensure(static_cast<uint64_t>(n_unc) * k * 8));
+        ANNB_TRY(ix->s_fbd.ensure(static_cast<uint64_t>(n_unc) * k * 4));
+        ANNB_TRY(ix->s_fbc.ensure(static_cast<uint64_t>(n_unc) * 4));
+        ANNB_TRY(flat_simt(ix, sub, n_unc, k, kk, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(), ix->s_fbc.as<uint32_t>(), s));
+        scatter_results_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * k, 256), 256, 0, s>>>(list, n_unc, k, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(),
+                                                                                             ix->s_fbc.as<uint32_t>(), d_ids, d_dist, d_cnt);
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        ix->stat_launches += 2;
+        ix->stat_fallback_queries += n_unc;
+        return ANNB_OK;
     }
     ix->stat_last_path = ANNB_PATH_SIMT;
+    return flat_simt(ix, pq, nq, k, kk, d_ids, d_dist, d_cnt, s);
+}
+
+// Exact CUDA-core flat search (tile_kernel + finalize).
+static int flat_simt(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint32_t kk, uint64_t* d_ids, float* d_dist,
+                     uint32_t* d_cnt, cudaStream_t s) {
     if (kk > 1024) return fail(ANNB_ERR_UNSUPPORTED, "k > 1024 is not supported");
     const uint32_t nsort = WarpSelect::sort_size(kk);
     const uint64_t q_tiles = ceil_div<uint64_t>(nq, CTA_QUERIES);
@@ -285,7 +323,7 @@ static int flat_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uin
 // IVF search core
 // ---------------------------------------------------------------------------
 static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint32_t nprobe, const uint64_t* row_map,
-                    uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s) {
+                    uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s, bool force_simt = false) {
     const uint32_t kk = static_cast<uint32_t>(std::min<uint64_t>(k, ix->n_total));
     if (kk == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "k must be >= 1");
     if (kk > 1024) return fail(ANNB_ERR_UNSUPPORTED, "k > 1024 is not supported");
@@ -384,8 +422,8 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
     const bool list_major = merge_fits_simt &&
                             (ix->opt_ivf_list_major == 1 || (ix->opt_ivf_list_major < 0 && nq * static_cast<uint64_t>(np) >= 8 * n_local_lists));
     if (list_major) {
-        const bool use_tc = ix->opt_path != ANNB_PATH_SIMT && merge_fits_tc && tc_ivf_supported(ix, pq.qt, kk);
-        if (!use_tc && ix->opt_path == ANNB_PATH_TENSOR)
+        const bool use_tc = !force_simt && ix->opt_path != ANNB_PATH_SIMT && merge_fits_tc && tc_ivf_supported(ix, pq.qt, kk);
+        if (!use_tc && !force_simt && ix->opt_path == ANNB_PATH_TENSOR)
             return fail(ANNB_ERR_UNSUPPORTED, "tensor path requested but this IVF (dtype, dim, k, query type) is not covered by it yet");
         ix->stat_last_path = use_tc ? ANNB_PATH_TENSOR : ANNB_PATH_SIMT;
         const uint32_t nsort = WarpSelect::sort_size(kk);
@@ -414,8 +452,36 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         ix->stat_launches += 3;
         if (use_tc) {
             const uint64_t max_tasks_tc = ceil_div<uint64_t>(slots, 128) + n_local_lists;
-            return tc_ivf_scan(ix, pq.scan, pq.scan_bytes, nq, kk, k, pitch, pp.pair_off, pp.task_off, pp.pairs, pp.task_counter, max_tasks_tc,
-                               ix->s_nprobes.as<uint32_t>(), row_map, d_ids, d_dist, d_cnt, s);
+            ANNB_TRY(tc_ivf_scan(ix, pq.scan, pq.scan_bytes, nq, kk, k, pitch, pp.pair_off, pp.task_off, pp.pairs, pp.task_counter, max_tasks_tc,
+                                 ix->s_nprobes.as<uint32_t>(), row_map, d_ids, d_dist, d_cnt, s));
+            uint32_t n_unc = 0;
+            ANNB_TRY(read_uncertified(ix, &n_unc, s));
+            if (n_unc == 0 || row_map != nullptr) return ANNB_OK;
+            // exact fallback: the uncertified queries go through the CUDA-core pipeline again
+            ANNB_TRY(read_ivf_stats(ix, s));          // keep the whole batch's probe statistics
+            ix->skip_next_ivf_stats = true;
+            const uint32_t* list = ix->s_uncert.as<uint32_t>() + 1;
+            PreparedQueries sub = pq;
+            ANNB_TRY(ix->s_fbq.ensure(static_cast<uint64_t>(n_unc) * pq.scan_bytes));
+            gather_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * (pq.scan_bytes >> 4), 256), 256, 0, s>>>(pq.scan, pq.scan_bytes, list, n_unc, ix->s_fbq.as<uint8_t>());
+            sub.scan = ix->s_fbq.as<uint8_t>();
+            ANNB_TRY(ix->s_fbr.ensure(static_cast<uint64_t>(n_unc) * pq.route_ld * 4));
+            gather_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * (pq.route_ld >> 2), 256), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(pq.route), pq.route_ld * 4, list, n_unc,
+                                                                                                                ix->s_fbr.as<uint8_t>());
+            ANNB_CUDA_CHECK(cudaGetLastError());
+            sub.route = ix->s_fbr.as<float>();
+            ANNB_TRY(ix->s_fbi.ensure(static_cast<uint64_t>(n_unc) * k * 8));
+            ANNB_TRY(ix->s_fbd.ensure(static_cast<uint64_t>(n_unc) * k * 4));
+            ANNB_TRY(ix->s_fbc.ensure(static_cast<uint64_t>(n_unc) * 4));
+            // the list of uncertified queries lives in s_uncert, which the nested call does not touch (it stays on the CUDA-core path)
+            ANNB_TRY(ivf_core(ix, sub, n_unc, k, nprobe, nullptr, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(), ix->s_fbc.as<uint32_t>(), s, true));
+            scatter_results_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * k, 256), 256, 0, s>>>(list, n_unc, k, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(),
+                                                                                                 ix->s_fbc.as<uint32_t>(), d_ids, d_dist, d_cnt);
+            ANNB_CUDA_CHECK(cudaGetLastError());
+            ix->stat_launches += 3;
+            ix->stat_fallback_queries += n_unc;
+            ix->stat_last_path = ANNB_PATH_TENSOR;
+            return ANNB_OK;
         }
         ListScanParams lp{};
         lp.rows = ix->d_rows; lp.row_bytes = ix->row_bytes; lp.row_norms = ix->d_norms; lp.row_norms_i = ix->d_norms_i;
@@ -460,6 +526,7 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
 }
 
 static int read_ivf_stats(annb_index* ix, cudaStream_t s) {
+    if (ix->skip_next_ivf_stats) { ix->skip_next_ivf_stats = false; return ANNB_OK; }
     unsigned long long h[3] = {0, 0, 0};
     ANNB_CUDA_CHECK(cudaMemcpyAsync(h, ix->s_flags.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -583,7 +650,7 @@ void annb_destroy(annb_index* ix) {
     cudaFree(ix->d_rows); cudaFree(ix->d_norms); cudaFree(ix->d_norms_i); cudaFree(ix->d_scales);
     cudaFree(ix->d_centroids); cudaFree(ix->d_centroid_norms); cudaFree(ix->d_offsets); cudaFree(ix->d_original_ids);
     for (DevBuf* b : {&ix->s_qpad, &ix->s_qcodes, &ix->s_route, &ix->s_cdist, &ix->s_probes, &ix->s_nprobes, &ix->s_keys, &ix->s_flags,
-                      &ix->s_ids, &ix->s_dist, &ix->s_cnt, &ix->s_tmp, &ix->s_pairs})
+                      &ix->s_ids, &ix->s_dist, &ix->s_cnt, &ix->s_tmp, &ix->s_pairs, &ix->s_uncert, &ix->s_fbq, &ix->s_fbr, &ix->s_fbi, &ix->s_fbd, &ix->s_fbc})
         b->release();
     if (ix->stream) cudaStreamDestroy(ix->stream);
     (void)cudaGetLastError();
@@ -891,6 +958,8 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     if (k == "path") { if (value < 0 || value > 2) return fail(ANNB_ERR_INVALID_ARGUMENT, "path must be 0..2"); ix->opt_path = static_cast<int>(value); }
     else if (k == "tc_candidates") ix->opt_tc_candidates = static_cast<int>(value);
     else if (k == "tc_ts") ix->opt_tc_ts = static_cast<int>(value);
+    else if (k == "cert_fallback") ix->opt_cert_fallback = static_cast<int>(value);
+    else if (k == "cert_eps_log2") ix->opt_cert_eps = value == 0 ? 0.f : std::ldexp(1.0f, static_cast<int>(value));   // e.g. -18; 0 switches the certificate off
     else if (k == "tc_debug") { DeviceGuard g(ix->device); return tc_debug_enable(ix, value != 0); }
     else if (k == "db_splits") ix->opt_db_splits = static_cast<int>(value);
     else if (k == "scan_parts") ix->opt_scan_parts = static_cast<int>(value);
@@ -926,7 +995,18 @@ int annb_index_get_stat(const annb_index* ix, const char* key, int64_t* out) {
     else if (k == "scanned_vectors") *out = ix->stat_scanned;
     else if (k == "probed_lists") *out = ix->stat_probed;
     else if (k == "last_path") *out = ix->stat_last_path;
-    else if (k == "uncertified") *out = ix->stat_uncertified;
+    else if (k == "fallback_queries") *out = ix->stat_fallback_queries;
+    else if (k == "uncertified") {
+        // queries of the last tensor-path call whose pre-selection margin could not be certified (see rerank_kernel)
+        *out = 0;
+        if (ix->s_uncert.p && ix->stat_last_path == ANNB_PATH_TENSOR) {
+            DeviceGuard g(ix->device);
+            std::lock_guard<std::mutex> lock(ix->mu);
+            uint32_t c = 0;
+            ANNB_CUDA_CHECK(cudaMemcpy(&c, ix->s_uncert.p, 4, cudaMemcpyDeviceToHost));
+            *out = c;
+        }
+    }
     else if (k == "dominant_kernel_ns" || k == "dominant_kernel_launches") {
         // synchronises on the recorded events; total device time of the dominant kernel since time_kernels was set
         DeviceGuard g(ix->device);

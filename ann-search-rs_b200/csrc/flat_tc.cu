@@ -15,6 +15,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -348,6 +349,25 @@ int tc_make_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint32_t kp_elems, 
 
 uint32_t tc_blocks_for(uint64_t work) { return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>((work + 255) / 256, 148 * 16))); }
 
+// Largest stored-row norm from the per-row constants (L2 only; cosine needs no norm bound).
+int tc_compute_xnorm_max(annb_index* ix, const float* d_aux, uint64_t n) {
+    ix->tc_xnorm_max = 0.f;
+    if (ix->metric != ANNB_L2) return ANNB_OK;
+    uint32_t* d_bits = nullptr;
+    ANNB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_bits), 4));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(d_bits, 0, 4, ix->stream));
+    tc::aux_max_kernel<<<148, 256, 0, ix->stream>>>(d_aux, n, d_bits);
+    uint32_t bits = 0;
+    cudaError_t e = cudaMemcpyAsync(&bits, d_bits, 4, cudaMemcpyDeviceToHost, ix->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+    cudaFree(d_bits);
+    ANNB_CUDA_CHECK(e);
+    float sq;
+    std::memcpy(&sq, &bits, 4);
+    ix->tc_xnorm_max = std::sqrt(sq);
+    return ANNB_OK;
+}
+
 int tc_flat_prepare(annb_index* ix) {
     if (ix->is_ivf || ix->dtype == ANNB_SQ8) return ANNB_OK;
     const int kind = ix->dtype == ANNB_F32 ? tc::KIND_TF32X3 : tc::KIND_BF16;
@@ -397,6 +417,7 @@ int tc_flat_prepare(annb_index* ix) {
         xrows = st->n_pad;
     }
     ANNB_TRY(tc_make_tmap(&st->tm_x, xbase, xrows, kp, elem));
+    ANNB_TRY(tc_compute_xnorm_max(ix, st->d_aux, ix->n));
     ix->device_bytes += st->bytes;
     return ANNB_OK;
 }
@@ -538,6 +559,9 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     r.nsort = next_pow2(std::max(2 * splits * kprime, 64u));
     r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
     r.bf16_self = bf16_self; r.id_base = ix->id_base; r.out_ids = d_ids; r.out_dist = d_dist; r.out_counts = d_cnt;
+    ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
+    r.cert_eps = ix->opt_cert_eps; r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
     const bool cos = ix->metric == ANNB_COSINE;
     int rc;
     if (ix->dtype == ANNB_F32) rc = cos ? launch_rerank<0, QT_F32, MET_COS>(r, s) : launch_rerank<0, QT_F32, MET_L2>(r, s);

@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) ivf_tc_kernel(const __grid_con
 // (EncodeTiled / tensor-map helpers live in flat_tc.cu)
 int tc_make_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint32_t kp_elems, int elem_bytes);
 uint32_t tc_blocks_for(uint64_t work);
+int tc_compute_xnorm_max(annb_index* ix, const float* d_aux, uint64_t n);
 
 struct IvfTcState {
     int kind = -1;
@@ -384,6 +385,7 @@ int tc_ivf_prepare(annb_index* ix) {
     }
     ANNB_CUDA_CHECK(cudaGetLastError());
     ANNB_TRY(tc_make_tmap(&st->tm_x, st->d_x, xrows, kp, elem));
+    ANNB_TRY(tc_compute_xnorm_max(ix, st->d_aux, ix->n));
     ix->device_bytes += st->bytes;
     return ANNB_OK;
 }
@@ -468,6 +470,9 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
     r.bf16_self = 0; r.id_base = 0; r.parts_used = d_n_probes; r.part_mult = 2; r.id_map = ix->d_original_ids; r.row_map = row_map;
     r.out_ids = d_ids; r.out_dist = d_dist; r.out_counts = d_cnt;
+    ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
+    r.cert_eps = ix->opt_cert_eps; r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
     int rc;
     if (ix->dtype == ANNB_F32) rc = l2 ? launch_ivf_rerank<0, MET_L2>(r, s) : launch_ivf_rerank<0, MET_COS>(r, s);
     else rc = l2 ? launch_ivf_rerank<1, MET_L2>(r, s) : launch_ivf_rerank<1, MET_COS>(r, s);

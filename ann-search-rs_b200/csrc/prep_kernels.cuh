@@ -131,6 +131,29 @@ __global__ void sq8_row_norms_kernel(const int8_t* __restrict__ rows, uint32_t l
     out[i] = s;
 }
 
+// Row gather / result scatter used by the exact fallback of the tensor paths.
+__global__ void gather_rows_kernel(const uint8_t* __restrict__ src, uint32_t row_bytes, const uint32_t* __restrict__ list, uint32_t count,
+                                   uint8_t* __restrict__ dst) {
+    const uint32_t cpr = row_bytes >> 4;
+    const uint64_t total = static_cast<uint64_t>(count) * cpr;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t r = static_cast<uint32_t>(i / cpr), c = static_cast<uint32_t>(i - static_cast<uint64_t>(r) * cpr);
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src + static_cast<uint64_t>(list[r]) * row_bytes)[c];
+    }
+}
+__global__ void scatter_results_kernel(const uint32_t* __restrict__ list, uint32_t count, uint32_t k, const uint64_t* __restrict__ ids,
+                                       const float* __restrict__ dist, const uint32_t* __restrict__ cnt, uint64_t* __restrict__ out_ids,
+                                       float* __restrict__ out_dist, uint32_t* __restrict__ out_cnt) {
+    const uint64_t total = static_cast<uint64_t>(count) * k;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t r = static_cast<uint32_t>(i / k), j = static_cast<uint32_t>(i - static_cast<uint64_t>(r) * k);
+        const uint64_t o = static_cast<uint64_t>(list[r]) * k + j;
+        out_ids[o] = ids[i];
+        if (out_dist) out_dist[o] = dist[i];
+        if (out_cnt && j == 0) out_cnt[list[r]] = cnt[r];
+    }
+}
+
 // direct_assign shortcut norms (src/utils/k_means_utils.rs:2134-2156): |c|^2 via dot_simd (L2) or
 // 1/norm (cosine; 0 when the norm is 0) where norm is the caller-supplied centroid norm, or when none
 // is supplied the sequential-fold norm IvfIndex::build computes (src/cpu/ivf.rs:193-206).

@@ -247,6 +247,15 @@ static __global__ void pad_bf16_kernel(const uint16_t* __restrict__ src, uint32_
 }
 // Epilogue constants per database row.  L2: (-2, |x|^2) with |x|^2 of the stored (possibly bf16-rounded) row;
 // cosine: (-1/norm, 0) with the index norm (f32 norm of the un-rounded row, as the reference divides by it).
+// max over rows of aux (L2: |x|^2, all >= 0): non-negative floats order like their bit patterns
+static __global__ void aux_max_kernel(const float* __restrict__ aux, uint64_t n, uint32_t* __restrict__ out_bits) {
+    uint32_t m = 0;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const float v = aux[i];
+        if (v == v && v < INFINITY && v > 0.f) m = max(m, __float_as_uint(v));
+    }
+    atomicMax(out_bits, m);
+}
 static __global__ void aux_kernel(const uint8_t* __restrict__ rows, uint32_t row_bytes, int is_bf16, uint32_t dim, const float* __restrict__ norms,
                            uint64_t n, uint64_t n_pad_total, float* __restrict__ aux) {
     const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
@@ -285,6 +294,13 @@ struct RerankParams {
     uint32_t part_mult;
     const uint64_t* id_map;      // optional: id = id_map[row] (IVF original ids) instead of row + id_base
     const uint64_t* row_map;     // optional: output row of query q
+    // Coverage certificate: every row that was NOT re-ranked has an approximate value >= the k'-th merged approximate
+    // value A.  If A (mapped back to distance units) exceeds the k-th exact distance by more than the error bound of the
+    // approximate values, no such row can belong to the exact top-k: the result is provably the reference's.
+    float cert_eps;              // relative error bound of the pre-selection values (0 = certificate off)
+    float xnorm_max;             // L2: largest stored-row norm
+    uint32_t* uncert_count;      // number of queries that could not be certified
+    uint32_t* uncert_list;       // their indices (capacity nq)
     uint64_t* out_ids;
     float* out_dist;
     uint32_t* out_counts;
@@ -330,6 +346,30 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     __syncthreads();
     if (threadIdx.x < 32) bitonic_sort_keys<false>(exact, 64, threadIdx.x, 32);
     __syncthreads();
+    if (threadIdx.x == 0 && p.uncert_count != nullptr && p.cert_eps > 0.f) {
+        const uint64_t a_key = keys[p.kp - 1];                       // k'-th merged approximate key (sentinel: every row was re-ranked)
+        const uint64_t d_key = exact[p.k_eff - 1];                   // k-th exact key (sentinel: fewer than k rows exist)
+        bool certified = true;
+        if (key_idx(a_key) != IDX_INVALID && key_idx(d_key) != IDX_INVALID) {
+            const uint8_t* qv = p.queries + q * p.q_bytes;
+            float qn2 = 0.f;
+            for (uint32_t e = 0; e < p.dim; e++) {
+                const float x = load1<(QT == QT_F32) ? 4 : 2>(qv, e);
+                qn2 = fmaf(x, x, qn2);
+            }
+            const float a_thr = key_dist(a_key), dk = key_dist(d_key);
+            if (MET == MET_L2) {
+                // approx value = |x|^2 - 2 q.x = dist - |q|^2 ; error <= eps * (|q| + |x|max)^2
+                const float s = sqrtf(qn2) + p.xnorm_max;
+                certified = (a_thr + qn2 - p.cert_eps * s * s) > dk;
+            } else {
+                // approx value = -q.x / |x| = (dist - 1) * |q| ; error <= eps * |q|
+                const float qn = sqrtf(qn2);
+                certified = qn > 0.f ? ((a_thr / qn + 1.0f - p.cert_eps) > dk) : true;
+            }
+        }
+        if (!certified) p.uncert_list[atomicAdd(p.uncert_count, 1u)] = static_cast<uint32_t>(q);
+    }
     uint32_t valid = 0;
     for (uint32_t j = threadIdx.x; j < p.k_out; j += blockDim.x) {
         uint64_t key = (j < p.k_eff && j < 64) ? exact[j] : KEY_SENTINEL;

@@ -190,10 +190,14 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
  *               "db_splits" (flat: database splits per query tile, 0 = auto),
  *               "scan_parts" (IVF: partial scans per query, 0 = auto),
  *               "ivf_list_major" (IVF list scan: -1 auto, 0 query-major streaming kernel, 1 list-major batched kernel),
- *               "time_kernels" (1 = bracket the dominant kernel of every search with CUDA events on its stream)
+ *               "time_kernels" (1 = bracket the dominant kernel of every search with CUDA events on its stream),
+ *               "tc_ts" (tensor paths: 1 = query operand resident in TMEM), "ivf_fast_probe" (0/1/2),
+ *               "cert_eps_log2" (error bound assumed by the coverage certificate of the tensor paths, default -20; 0 = off),
+ *               "cert_fallback" (1 = queries that fail the certificate are recomputed on the exact CUDA-core path)
  *   get_stat  : "kernel_launches" (cumulative), "scanned_vectors" (IVF, last call: sum of probed
  *               list lengths), "probed_lists" (last call), "last_path" (annb_path actually used),
- *               "uncertified" (tensor path, last call: queries that took the exact fallback),
+ *               "uncertified" (tensor path, last call: queries that failed the coverage certificate),
+ *               "fallback_queries" (cumulative: queries recomputed on the exact path),
  *               "dominant_kernel_ns" / "dominant_kernel_launches" (with "time_kernels": summed device time and count
  *               of the dominant kernel -- flat distance+select kernel or IVF list-scan kernel -- since the option was set) */
 int annb_index_set_option(annb_index* index, const char* key, int64_t value);

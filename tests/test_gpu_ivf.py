@@ -172,3 +172,20 @@ def test_fast_probe_path_and_overflow_fallback(gpu, dtype):
     ref = o.ivf_search(c, q, 600, nprobe=1)                        # certainly more than nprobe + 64 cells
     g.set_option("ivf_fast_probe", 2)
     _check(dtype, g.query_batch(q, 600, nprobe=1), ref, "overflow fallback")
+
+
+def test_ivf_tensor_certificate_fallback(gpu):
+    data = datagen.gaussian_noise(8000, 32, seed=33)
+    q = datagen.subsample_with_noise(data, 150, seed=33)
+    c = o.build_ivf(data, o.L2, nlist=40, kmeans_iters=4)
+    g = _gpu_from_oracle(c)
+    g.set_option("ivf_list_major", 1)
+    g.set_option("path", annb200.PATH_TENSOR)
+    ref = o.ivf_search(c, q, 10, nprobe=6)
+    g.set_option("cert_eps_log2", -2)          # every query fails the certificate -> exact pipeline for all of them
+    got = g.query_batch(q, 10, nprobe=6)
+    assert g.get_stat("fallback_queries") == 150
+    _check("f32", got, ref, "ivf fallback")
+    assert g.get_stat("scanned_vectors") == int(ref[4].sum())
+    g.set_option("cert_eps_log2", -20)
+    _check("f32", g.query_batch(q, 10, nprobe=6), ref, "ivf default bound")

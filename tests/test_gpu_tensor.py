@@ -90,3 +90,23 @@ def test_tensor_equals_simt_at_scale(gpu):
     g.set_option("path", annb200.PATH_SIMT)
     b = g.query_batch(q, 10)
     assert_exact(a[0], a[1], b[0], b[1], "tensor vs simt")
+
+
+def test_certificate_and_exact_fallback(gpu):
+    """With an absurdly pessimistic error bound every query fails the coverage certificate and is recomputed on the
+    exact CUDA-core path; with the certificate off nothing is; results are identical either way."""
+    data = datagen.gaussian_noise(12000, 64, seed=29)
+    q = datagen.subsample_with_noise(data, 200, seed=29)
+    g, c = _pair(data, "f32", "l2")
+    ref = o.flat_search(c, q, 10)
+    g.set_option("cert_eps_log2", -2)
+    ids, d, _ = g.query_batch(q, 10)
+    assert g.get_stat("uncertified") == 200 and g.get_stat("fallback_queries") == 200
+    assert_exact(ids, d, ref[0], ref[1], "all queries through the fallback")
+    g.set_option("cert_eps_log2", 0)
+    ids, d, _ = g.query_batch(q, 10)
+    assert g.get_stat("uncertified") == 0 and g.get_stat("fallback_queries") == 200
+    assert_exact(ids, d, ref[0], ref[1], "certificate off")
+    g.set_option("cert_eps_log2", -20)
+    ids, d, _ = g.query_batch(q, 10)
+    assert_exact(ids, d, ref[0], ref[1], "default bound")
