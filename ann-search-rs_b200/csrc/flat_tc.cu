@@ -33,14 +33,15 @@ namespace tc {
 template <int KIND, int KP, int MET, bool TS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const Params p) {
-    constexpr int NA = (KIND == KIND_TF32X3) ? 2 : 3;  // stacked query pieces
+    constexpr int NA = (KIND == KIND_TF32X3) ? 2 : (KIND == KIND_I8 ? 1 : 3);  // stacked query pieces
     constexpr int NB = (KIND == KIND_TF32X3) ? 2 : 1;  // stacked database pieces
-    constexpr int ELEM = (KIND == KIND_TF32X3) ? 4 : 2;
+    constexpr int ELEM = (KIND == KIND_TF32X3) ? 4 : (KIND == KIND_I8 ? 1 : 2);
+    static_assert(KIND != KIND_I8 || TS, "the int8 kernel keeps its queries in TMEM");
     constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;      // 32 tf32 / 64 bf16 per slab row
     constexpr int KSTEPS = 4;                          // 128 B / 32 B per UMMA K step (8 tf32 / 16 bf16)
     constexpr int NACC = TS ? 2 : ACC_STAGES;          // accumulator stages (TS: 256 of the 512 columns hold the queries)
     constexpr uint32_t ACC_COL0 = TS ? 256u : 0u;
-    constexpr uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : 64u;   // TMEM columns per query piece (32-bit words per row)
+    constexpr uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : (KIND == KIND_I8 ? 32u : 64u);   // TMEM columns per query piece (32-bit words per row)
 
     extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte aligned bases
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -138,6 +139,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                             umma_ts<KIND>(tmem_c, a_hi, xd + 2 * k, idesc, first);
                             umma_ts<KIND>(tmem_c, a_lo, xd + 2 * k, idesc, 1u);
                             umma_ts<KIND>(tmem_c, a_hi, xd + SLAB_DESC + 2 * k, idesc, 1u);
+                        } else if (TS && KIND == KIND_I8) {
+                            // int8 codes, four per column: 8 columns (32 codes) per K step; one exact s32 term
+                            umma_ts<KIND>(tmem_c, tmem_base + s * 32 + k * 8, xd + 2 * k, idesc, first);
                         } else if (TS) {
                             // bf16 query terms q0, q1, q2 in TMEM at columns [0,64), [64,128), [128,192); 8 columns (16 bf16) per K step
                             const uint32_t a0 = tmem_base + s * 32 + k * 8;
@@ -245,7 +249,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     for (int j = 0; j < 8; j++) {
                         const int col = g * 8 + j;   // compile-time after unrolling
                         const float cst = __shfl_sync(0xFFFFFFFFu, col < 32 ? aux_lo : aux_hi, col & 31);
-                        const float sdot = __uint_as_float(r[col]);
+                        const float sdot = (KIND == KIND_I8) ? __int2float_rn(static_cast<int32_t>(r[col])) : __uint_as_float(r[col]);   // s32 dots are exact in f32 (< 2^24)
                         v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
                         mg = fminf(mg, v[g * 8 + j]);
                     }
@@ -341,7 +345,7 @@ int tc_make_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint32_t kp_elems, 
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(kp_elems) * elem_bytes};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(tc::SLAB_BYTES / elem_bytes), static_cast<cuuint32_t>(tc::BM)};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr,
+    CUresult r = fn(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8), 2, base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r))); return ANNB_ERR_CUDA; }
     return ANNB_OK;
@@ -369,9 +373,9 @@ int tc_compute_xnorm_max(annb_index* ix, const float* d_aux, uint64_t n) {
 }
 
 int tc_flat_prepare(annb_index* ix) {
-    if (ix->is_ivf || ix->dtype == ANNB_SQ8) return ANNB_OK;
-    const int kind = ix->dtype == ANNB_F32 ? tc::KIND_TF32X3 : tc::KIND_BF16;
-    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : 2;
+    if (ix->is_ivf) return ANNB_OK;
+    const int kind = ix->dtype == ANNB_F32 ? tc::KIND_TF32X3 : (ix->dtype == ANNB_BF16 ? tc::KIND_BF16 : tc::KIND_I8);
+    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : (kind == tc::KIND_BF16 ? 2 : 1);
     const uint32_t slab_elems = tc::SLAB_BYTES / elem;
     const uint32_t kp = round_up(ix->dim, slab_elems);
     if (kp * elem > 512) return ANNB_OK;  // query tile would not fit in shared memory: the exact CUDA-core path serves this index
@@ -389,9 +393,8 @@ int tc_flat_prepare(annb_index* ix) {
         if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc tc aux: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
         st->bytes += aux_rows * sizeof(float);
     }
-    tc::aux_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(ix->d_rows, ix->row_bytes, kind == tc::KIND_BF16, ix->dim,
-                                                                                ix->metric == ANNB_COSINE ? ix->d_norms : nullptr, ix->n, aux_rows,
-                                                                                st->d_aux);
+    tc::aux_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(ix->d_rows, ix->row_bytes, kind, ix->dim, ix->d_norms, ix->d_norms_i,
+                                                                                ix->metric == ANNB_COSINE, ix->n, aux_rows, st->d_aux);
     ANNB_CUDA_CHECK(cudaGetLastError());
     void* xbase = nullptr;
     uint64_t xrows = 0;
@@ -405,6 +408,16 @@ int tc_flat_prepare(annb_index* ix) {
         ANNB_CUDA_CHECK(cudaGetLastError());
         xbase = st->d_x;
         xrows = 2ull * st->n_pad;
+    } else if (kind == tc::KIND_I8) {
+        const uint64_t bytes = static_cast<uint64_t>(st->n_pad) * kp;
+        cudaError_t e = cudaMalloc(&st->d_x, bytes);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
+        st->bytes += bytes;
+        tc::pad_i8_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * kp), 256, 0, s>>>(reinterpret_cast<const int8_t*>(ix->d_rows), ix->row_bytes, ix->dim, ix->n,
+                                                                                            st->n_pad, kp, static_cast<int8_t*>(st->d_x));
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        xbase = st->d_x;
+        xrows = st->n_pad;
     } else {
         const uint64_t bytes = static_cast<uint64_t>(st->n_pad) * kp * 2;
         cudaError_t e = cudaMalloc(&st->d_x, bytes);
@@ -445,6 +458,7 @@ bool tc_flat_supported(const annb_index* ix, int qt, uint32_t k_eff) {
     if (k_eff > 24) return false;
     if (ix->dtype == ANNB_F32) return qt == QT_F32;
     if (ix->dtype == ANNB_BF16) return qt == QT_F32 || qt == QT_BF16;
+    if (ix->dtype == ANNB_SQ8) return qt == QT_I8;
     return false;
 }
 
@@ -490,15 +504,18 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
                    uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s) {
     TcState* st = ix->tc;
     const int kind = st->kind;
-    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : 2;
+    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : (kind == tc::KIND_BF16 ? 2 : 1);
     const uint32_t kp = st->kp_elems;
     const uint32_t kprime = pick_kprime(ix, k_eff);
     const uint32_t nq_pad = static_cast<uint32_t>(round_up<uint64_t>(nq, tc::BM));
-    const uint32_t na = kind == tc::KIND_TF32X3 ? 2 : (qt == QT_BF16 ? 1 : 3);
+    const uint32_t na = kind == tc::KIND_TF32X3 ? 2 : ((qt == QT_BF16 || kind == tc::KIND_I8) ? 1 : 3);
 
     // ---- query operand: stacked pieces, zero padded ----
     ANNB_TRY(st->q_op.ensure(static_cast<uint64_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * nq_pad * kp * elem));
-    if (kind == tc::KIND_TF32X3) {
+    if (kind == tc::KIND_I8) {
+        tc::pad_i8_kernel<<<tc_blocks_for(static_cast<uint64_t>(nq_pad) * kp), 256, 0, s>>>(reinterpret_cast<const int8_t*>(d_q), q_bytes, ix->dim, nq, nq_pad, kp,
+                                                                                         st->q_op.as<int8_t>());
+    } else if (kind == tc::KIND_TF32X3) {
         tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(nq_pad) * kp), 256, 0, s>>>(reinterpret_cast<const float*>(d_q), q_bytes / 4, ix->dim, nq, nq_pad, kp,
                                                                                              st->q_op.as<float>());
     } else if (qt == QT_F32) {
@@ -520,7 +537,8 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;
     const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
     const uint32_t nb = kind == tc::KIND_TF32X3 ? 2 : 1;
-    const bool ts = ix->opt_tc_ts != 0;   // query operand resident in TMEM (TS-mode MMA)
+    // query operand resident in TMEM (TS-mode MMA) when its pieces fit their column budget (bf16 terms: 64 columns each)
+    const bool ts = kind == tc::KIND_I8 || (ix->opt_tc_ts != 0 && (kind != tc::KIND_BF16 || kp * elem <= 256));
     const size_t q_smem = ts ? 0 : static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * st->nslab * tc::SLAB_TILE;
     const size_t fixed = 256 /*barriers*/;
     const size_t budget = 227 * 1024;
@@ -544,7 +562,8 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
         int rc;
         const bool l2 = ix->metric == ANNB_L2;
 #define ANNB_TC_LAUNCH(KIND_, KP_, TS_) (l2 ? launch_tc<KIND_, KP_, MET_L2, TS_>(tmq, st->tm_x, p, grid, smem, s) : launch_tc<KIND_, KP_, MET_COS, TS_>(tmq, st->tm_x, p, grid, smem, s))
-        if (kind == tc::KIND_TF32X3 && ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, true) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, true);
+        if (kind == tc::KIND_I8) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_I8, 16, true) : ANNB_TC_LAUNCH(tc::KIND_I8, 32, true);
+        else if (kind == tc::KIND_TF32X3 && ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, true) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, true);
         else if (kind == tc::KIND_TF32X3) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, false) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, false);
         else if (ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_BF16, 16, true) : ANNB_TC_LAUNCH(tc::KIND_BF16, 32, true);
         else rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_BF16, 16, false) : ANNB_TC_LAUNCH(tc::KIND_BF16, 32, false);
@@ -557,14 +576,17 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     tc::RerankParams r{};
     r.part_keys = st->part.as<uint64_t>(); r.parts = 2 * splits; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out;
     r.nsort = next_pow2(std::max(2 * splits * kprime, 64u));
-    r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
+    r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.row_norms_i = ix->d_norms_i; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
     r.bf16_self = bf16_self; r.id_base = ix->id_base; r.out_ids = d_ids; r.out_dist = d_dist; r.out_counts = d_cnt;
     ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));
     ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
-    r.cert_eps = ix->opt_cert_eps; r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
+    // SQ8 L2 (dim <= 256): the pre-selection values are exact integers, so the certificate only has to exclude a tie between
+    // the k-th exact distance and the k'-th pre-selected value (pruning is strict, a tied row of lower id could have been dropped)
+    r.cert_eps = (kind == tc::KIND_I8 && ix->metric != ANNB_COSINE && ix->dim <= 256) ? std::min(ix->opt_cert_eps, 1e-30f) : ix->opt_cert_eps; r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
     const bool cos = ix->metric == ANNB_COSINE;
     int rc;
-    if (ix->dtype == ANNB_F32) rc = cos ? launch_rerank<0, QT_F32, MET_COS>(r, s) : launch_rerank<0, QT_F32, MET_L2>(r, s);
+    if (ix->dtype == ANNB_SQ8) rc = cos ? launch_rerank<2, QT_I8, MET_COS>(r, s) : launch_rerank<2, QT_I8, MET_L2>(r, s);
+    else if (ix->dtype == ANNB_F32) rc = cos ? launch_rerank<0, QT_F32, MET_COS>(r, s) : launch_rerank<0, QT_F32, MET_L2>(r, s);
     else if (qt == QT_F32) rc = cos ? launch_rerank<1, QT_F32, MET_COS>(r, s) : launch_rerank<1, QT_F32, MET_L2>(r, s);
     else rc = cos ? launch_rerank<1, QT_BF16, MET_COS>(r, s) : launch_rerank<1, QT_BF16, MET_L2>(r, s);
     ANNB_TRY(rc);

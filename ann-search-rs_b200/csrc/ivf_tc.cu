@@ -44,12 +44,12 @@ struct IvfTcParams {
 template <int KIND, int KP, int MET>
 __global__ void __launch_bounds__(NUM_THREADS, 1) ivf_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const IvfTcParams p) {
     constexpr int NB = (KIND == KIND_TF32X3) ? 2 : 1;
-    constexpr int ELEM = (KIND == KIND_TF32X3) ? 4 : 2;
+    constexpr int ELEM = (KIND == KIND_TF32X3) ? 4 : (KIND == KIND_I8 ? 1 : 2);
     constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;
     constexpr int KSTEPS = 4;
     constexpr int NACC = 2;
     constexpr uint32_t ACC_COL0 = 256u;
-    constexpr uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : 64u;
+    constexpr uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : (KIND == KIND_I8 ? 32u : 64u);
     constexpr uint32_t idesc = make_idesc(KIND);
     constexpr uint32_t SLAB_DESC = SLAB_TILE >> 4;
 
@@ -165,6 +165,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) ivf_tc_kernel(const __grid_con
                                 umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
                                 umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
                                 umma_ts<KIND>(tmem_c, a0, xd + SLAB_DESC + 2 * k, idesc, 1u);
+                            } else if (KIND == KIND_I8) {
+                                umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
                             } else {
                                 umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
                                 umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
@@ -185,7 +187,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) ivf_tc_kernel(const __grid_con
             {
                 const float* qrow = reinterpret_cast<const float*>(p.queries + static_cast<uint64_t>(has_query ? pr.x : 0) * p.q_bytes);
                 const uint32_t kp = p.nslab * SLAB_ELEMS;
-                if (KIND == KIND_TF32X3) {
+                if (KIND == KIND_I8) {
+                    // the scan queries are already int8 codes (zero padded to 16): four codes per TMEM column, written by half 0
+                    if (half == 0) {
+                        const uint32_t* qw = reinterpret_cast<const uint32_t*>(qrow);
+                        const uint32_t tq = tmem_base + ((quarter * 32u) << 16);
+                        for (uint32_t c = 0; c < kp / 4; c += 32) {
+                            uint32_t w[32];
+#pragma unroll
+                            for (int j = 0; j < 32; j++) w[j] = (has_query && 4 * (c + j) < p.q_bytes) ? __ldg(qw + c + j) : 0u;
+                            tmem_st32(tq + c, w);
+                        }
+                    }
+                } else if (KIND == KIND_TF32X3) {
                     // half 0 writes hi = rna_tf32(q) at columns [0,128), half 1 writes lo = rna_tf32(q - hi) at [128,256)
                     const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + half * PIECE_COLS;
                     for (uint32_t c = 0; c < kp; c += 32) {
@@ -275,7 +289,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) ivf_tc_kernel(const __grid_con
                         for (int j = 0; j < 8; j++) {
                             const int col = g * 8 + j;
                             const float cst = __shfl_sync(0xFFFFFFFFu, col < 32 ? aux_lo : aux_hi, col & 31);
-                            const float sdot = __uint_as_float(r[col]);
+                            const float sdot = (KIND == KIND_I8) ? __int2float_rn(static_cast<int32_t>(r[col])) : __uint_as_float(r[col]);
                             v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
                             mg = fminf(mg, v[col]);
                         }
@@ -343,12 +357,13 @@ struct IvfTcState {
 };
 
 int tc_ivf_prepare(annb_index* ix) {
-    if (!ix->is_ivf || ix->dtype == ANNB_SQ8 || ix->n == 0) return ANNB_OK;
-    const int kind = ix->dtype == ANNB_F32 ? tc::KIND_TF32X3 : tc::KIND_BF16;
-    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : 2;
+    if (!ix->is_ivf || ix->n == 0) return ANNB_OK;
+    const int kind = ix->dtype == ANNB_F32 ? tc::KIND_TF32X3 : (ix->dtype == ANNB_BF16 ? tc::KIND_BF16 : tc::KIND_I8);
+    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : (kind == tc::KIND_BF16 ? 2 : 1);
     const uint32_t slab_elems = tc::SLAB_BYTES / elem;
     const uint32_t kp = round_up(ix->dim, slab_elems);
-    if (kp * elem > 512) return ANNB_OK;     // query piece must fit its TMEM column budget; larger dims stay on the CUDA-core scan
+    // the query pieces live in TMEM (128 columns per f32 / int8 piece, 64 per bf16 term); larger dims stay on the CUDA-core scan
+    if (kp * elem > (kind == tc::KIND_BF16 ? 256u : 512u)) return ANNB_OK;
     IvfTcState* st = new IvfTcState();
     ix->tc_ivf = st;
     st->kind = kind;
@@ -362,8 +377,8 @@ int tc_ivf_prepare(annb_index* ix) {
         if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc aux: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
         st->bytes += aux_rows * sizeof(float);
     }
-    tc::aux_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(ix->d_rows, ix->row_bytes, kind == tc::KIND_BF16, ix->dim,
-                                                                                ix->metric == ANNB_COSINE ? ix->d_norms : nullptr, ix->n, aux_rows, st->d_aux);
+    tc::aux_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(ix->d_rows, ix->row_bytes, kind, ix->dim, ix->d_norms, ix->d_norms_i,
+                                                                                ix->metric == ANNB_COSINE, ix->n, aux_rows, st->d_aux);
     ANNB_CUDA_CHECK(cudaGetLastError());
     uint64_t xrows = 0;
     if (kind == tc::KIND_TF32X3) {
@@ -374,6 +389,14 @@ int tc_ivf_prepare(annb_index* ix) {
         tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * kp), 256, 0, s>>>(reinterpret_cast<const float*>(ix->d_rows), ix->row_bytes / 4, ix->dim,
                                                                                                    ix->n, st->n_pad, kp, static_cast<float*>(st->d_x));
         xrows = 2ull * st->n_pad;
+    } else if (kind == tc::KIND_I8) {
+        const uint64_t bytes = static_cast<uint64_t>(st->n_pad) * kp;
+        cudaError_t e = cudaMalloc(&st->d_x, bytes);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
+        st->bytes += bytes;
+        tc::pad_i8_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * kp), 256, 0, s>>>(reinterpret_cast<const int8_t*>(ix->d_rows), ix->row_bytes, ix->dim, ix->n,
+                                                                                            st->n_pad, kp, static_cast<int8_t*>(st->d_x));
+        xrows = st->n_pad;
     } else {
         const uint64_t bytes = static_cast<uint64_t>(st->n_pad) * kp * 2;
         cudaError_t e = cudaMalloc(&st->d_x, bytes);
@@ -401,7 +424,8 @@ void tc_ivf_destroy(annb_index* ix) {
 }
 
 bool tc_ivf_supported(const annb_index* ix, int qt, uint32_t k_eff) {
-    return ix->tc_ivf != nullptr && qt == QT_F32 && k_eff <= 24;
+    if (ix->tc_ivf == nullptr || k_eff > 24) return false;
+    return ix->dtype == ANNB_SQ8 ? qt == QT_I8 : qt == QT_F32;
 }
 
 uint32_t tc_ivf_kprime(const annb_index* ix, uint32_t k_eff) {
@@ -420,7 +444,7 @@ static int launch_ivf_tc(const CUtensorMap& tmx, const tc::IvfTcParams& p, uint3
 
 template <int RT, int MET>
 static int launch_ivf_rerank(const tc::RerankParams& r, cudaStream_t s) {
-    auto kern = tc::rerank_kernel<RT, QT_F32, MET>;
+    auto kern = tc::rerank_kernel<RT, (RT == 2) ? QT_I8 : QT_F32, MET>;
     const size_t smem = static_cast<size_t>(r.nsort) * 8;
     if (smem > 200 * 1024) { set_last_error("ivf rerank: nprobe * k' too large"); return ANNB_ERR_UNSUPPORTED; }
     ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -457,7 +481,8 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
         if (ix->opt_time_kernels && cudaEventCreate(&ea) == cudaSuccess && cudaEventCreate(&eb) == cudaSuccess) cudaEventRecord(ea, s);
         int rc;
 #define ANNB_IVF_TC(KIND_, KP_) (l2 ? launch_ivf_tc<KIND_, KP_, MET_L2>(st->tm_x, p, grid, smem, s) : launch_ivf_tc<KIND_, KP_, MET_COS>(st->tm_x, p, grid, smem, s))
-        if (st->kind == tc::KIND_TF32X3) rc = kprime == 16 ? ANNB_IVF_TC(tc::KIND_TF32X3, 16) : ANNB_IVF_TC(tc::KIND_TF32X3, 32);
+        if (st->kind == tc::KIND_I8) rc = kprime == 16 ? ANNB_IVF_TC(tc::KIND_I8, 16) : ANNB_IVF_TC(tc::KIND_I8, 32);
+        else if (st->kind == tc::KIND_TF32X3) rc = kprime == 16 ? ANNB_IVF_TC(tc::KIND_TF32X3, 16) : ANNB_IVF_TC(tc::KIND_TF32X3, 32);
         else rc = kprime == 16 ? ANNB_IVF_TC(tc::KIND_BF16, 16) : ANNB_IVF_TC(tc::KIND_BF16, 32);
 #undef ANNB_IVF_TC
         if (ea && eb) { cudaEventRecord(eb, s); ix->timed.emplace_back(ea, eb); }
@@ -467,14 +492,16 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     tc::RerankParams r{};
     r.part_keys = st->part.as<uint64_t>(); r.parts = probe_pitch * 2; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out;
     r.nsort = next_pow2(std::max(probe_pitch * 2 * kprime, 64u));
-    r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
+    r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.row_norms_i = ix->d_norms_i; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
     r.bf16_self = 0; r.id_base = 0; r.parts_used = d_n_probes; r.part_mult = 2; r.id_map = ix->d_original_ids; r.row_map = row_map;
     r.out_ids = d_ids; r.out_dist = d_dist; r.out_counts = d_cnt;
     ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));
     ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
-    r.cert_eps = ix->opt_cert_eps; r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
+    r.cert_eps = (st->kind == tc::KIND_I8 && l2 && ix->dim <= 256) ? std::min(ix->opt_cert_eps, 1e-30f) : ix->opt_cert_eps;   // exact integers: tie check only
+    r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
     int rc;
-    if (ix->dtype == ANNB_F32) rc = l2 ? launch_ivf_rerank<0, MET_L2>(r, s) : launch_ivf_rerank<0, MET_COS>(r, s);
+    if (ix->dtype == ANNB_SQ8) rc = l2 ? launch_ivf_rerank<2, MET_L2>(r, s) : launch_ivf_rerank<2, MET_COS>(r, s);
+    else if (ix->dtype == ANNB_F32) rc = l2 ? launch_ivf_rerank<0, MET_L2>(r, s) : launch_ivf_rerank<0, MET_COS>(r, s);
     else rc = l2 ? launch_ivf_rerank<1, MET_L2>(r, s) : launch_ivf_rerank<1, MET_COS>(r, s);
     ANNB_TRY(rc);
     ix->stat_launches++;

@@ -21,7 +21,7 @@ constexpr int ACC_STAGES = 4;          // accumulator ring in TMEM (4 x 128 colu
 constexpr int AUX_STAGES = 2;
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 512
 
-enum { KIND_TF32X3 = 0, KIND_BF16 = 1 };
+enum { KIND_TF32X3 = 0, KIND_BF16 = 1, KIND_I8 = 2 };   // 3xTF32 (f32 index), bf16 x3 query terms (BF16 index), int8 x int8 -> s32 (SQ8 index)
 
 struct Params {
     uint64_t nq;
@@ -113,6 +113,10 @@ __device__ __forceinline__ void umma(uint32_t tmem_c, uint64_t adesc, uint64_t b
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
                      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
                      : "memory");
+    else if (KIND == KIND_I8)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
     else
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
                      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
@@ -135,6 +139,10 @@ template <int KIND>
 __device__ __forceinline__ void umma_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     if (KIND == KIND_TF32X3)
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_c),
+                     "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    else if (KIND == KIND_I8)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_c),
                      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
                      : "memory");
     else
@@ -164,8 +172,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 }
 // UMMA instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): f32 accumulate, K-major A and B.
 __host__ __device__ constexpr uint32_t make_idesc(int kind) {
-    const uint32_t fmt = (kind == KIND_TF32X3) ? 2u : 1u;  // TF32 = 2, BF16 = 1
-    return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
+    const uint32_t fmt = (kind == KIND_TF32X3) ? 2u : 1u;  // TF32 = 2, BF16 = 1, signed INT8 = 1 (S8Format)
+    const uint32_t cfmt = (kind == KIND_I8) ? 2u : 1u;     // accumulator: F32 = 1, S32 = 2
+    return (cfmt << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
 }
 
 // ----------------------------------------------------------------------------------------------- per-thread k' list
@@ -256,25 +265,51 @@ static __global__ void aux_max_kernel(const float* __restrict__ aux, uint64_t n,
     }
     atomicMax(out_bits, m);
 }
-static __global__ void aux_kernel(const uint8_t* __restrict__ rows, uint32_t row_bytes, int is_bf16, uint32_t dim, const float* __restrict__ norms,
-                           uint64_t n, uint64_t n_pad_total, float* __restrict__ aux) {
+static __global__ void aux_kernel(const uint8_t* __restrict__ rows, uint32_t row_bytes, int rt, uint32_t dim, const float* __restrict__ norms,
+                                  const int32_t* __restrict__ norms_i, int cosine, uint64_t n, uint64_t n_pad_total, float* __restrict__ aux) {
+    // rt: 0 f32 rows, 1 bf16 rows, 2 int8 codes.  L2: aux = |x|^2 (of the stored, possibly rounded / quantised row);
+    // cosine: aux = -1/norm with the index norm (f32 norm of the un-rounded row; sqrt of the code norm for SQ8, 0 if that is 0).
     const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (i >= n_pad_total) return;
     float o = INFINITY;
     if (i < n) {
-        if (norms) {
-            o = -1.0f / norms[i];
-        } else {
-            float s = 0.f;
-            const uint8_t* r = rows + i * row_bytes;
-            for (uint32_t e = 0; e < dim; e++) {
-                const float x = is_bf16 ? bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(r)[e]) : reinterpret_cast<const float*>(r)[e];
-                s = fmaf(x, x, s);
+        if (cosine) {
+            if (rt == 2) {
+                const float nn = sqrtf(static_cast<float>(norms_i[i]));
+                o = nn > 0.f ? -1.0f / nn : 0.f;
+            } else {
+                o = -1.0f / norms[i];
             }
-            o = s;
+        } else {
+            const uint8_t* r = rows + i * row_bytes;
+            if (rt == 2) {
+                int32_t s = 0;
+                for (uint32_t e = 0; e < dim; e++) {
+                    const int32_t x = reinterpret_cast<const int8_t*>(r)[e];
+                    s += x * x;
+                }
+                o = static_cast<float>(s);
+            } else {
+                float s = 0.f;
+                for (uint32_t e = 0; e < dim; e++) {
+                    const float x = rt == 1 ? bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(r)[e]) : reinterpret_cast<const float*>(r)[e];
+                    s = fmaf(x, x, s);
+                }
+                o = s;
+            }
         }
     }
     aux[i] = o;
+}
+// int8 codes (pitch ld_src bytes) -> [rows_pad][kp] zero padded (database operand / encoded queries of the SQ8 index).
+static __global__ void pad_i8_kernel(const int8_t* __restrict__ src, uint32_t ld_src, uint32_t dim, uint64_t rows, uint64_t rows_pad, uint32_t kp,
+                                     int8_t* __restrict__ dst) {
+    const uint64_t total = rows_pad * kp;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t r = i / kp;
+        const uint32_t c = static_cast<uint32_t>(i - r * kp);
+        dst[i] = (r < rows && c < dim) ? src[r * ld_src + c] : static_cast<int8_t>(0);
+    }
 }
 
 // ----------------------------------------------------------------------------------------------- exact re-rank + merge
@@ -285,6 +320,7 @@ struct RerankParams {
     const uint8_t* rows;  // index rows in the index dtype
     uint32_t row_bytes;
     const float* row_norms;
+    const int32_t* row_norms_i;  // SQ8 cosine
     const uint8_t* queries;  // prepared queries (f32 padded rows, or bf16 rows for self queries)
     uint32_t q_bytes;
     uint32_t dim;
@@ -330,15 +366,26 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
             if (idx != IDX_INVALID) {
                 const uint8_t* row = p.rows + static_cast<uint64_t>(idx) * p.row_bytes;
                 const uint8_t* qv = p.queries + q * p.q_bytes;
-                float raw[1];
-                accumulate_fp<(RT == 0) ? 4 : 2, (QT == QT_F32) ? 4 : 2, MET == MET_L2, 1>(row, qv, p.q_bytes, p.dim, raw);
-                float qn = 1.0f, xn = 1.0f;
-                if (MET == MET_COS) {
-                    qn = seq_norm<(QT == QT_F32) ? 4 : 2>(qv, p.dim);
-                    if (p.bf16_self) qn = round_to_bf16(qn);
-                    xn = p.row_norms[idx];
+                if constexpr (RT == 2) {
+                    // SQ8: exact code-space distance (src/utils/dist.rs:5015-5077)
+                    int32_t dot[1], xx, qs = 0;
+                    accumulate_i8<1>(row, qv, p.q_bytes, p.dim, dot, xx);
+                    for (uint32_t e = 0; e < p.dim; e++) {
+                        const int32_t v = reinterpret_cast<const int8_t*>(qv)[e];
+                        qs += v * v;
+                    }
+                    ek = make_key(finish_i8<MET>(dot[0], xx, qs, (MET == MET_COS) ? p.row_norms_i[idx] : 0), idx);
+                } else {
+                    float raw[1];
+                    accumulate_fp<(RT == 0) ? 4 : 2, (QT == QT_F32) ? 4 : 2, MET == MET_L2, 1>(row, qv, p.q_bytes, p.dim, raw);
+                    float qn = 1.0f, xn = 1.0f;
+                    if (MET == MET_COS) {
+                        qn = seq_norm<(QT == QT_F32) ? 4 : 2>(qv, p.dim);
+                        if (p.bf16_self) qn = round_to_bf16(qn);
+                        xn = p.row_norms[idx];
+                    }
+                    ek = make_key(finish_fp<MET>(raw[0], qn, xn), idx);
                 }
-                ek = make_key(finish_fp<MET>(raw[0], qn, xn), idx);
             }
         }
         exact[threadIdx.x] = ek;
@@ -354,7 +401,9 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
             const uint8_t* qv = p.queries + q * p.q_bytes;
             float qn2 = 0.f;
             for (uint32_t e = 0; e < p.dim; e++) {
-                const float x = load1<(QT == QT_F32) ? 4 : 2>(qv, e);
+                float x;
+                if constexpr (QT == QT_I8) x = static_cast<float>(reinterpret_cast<const int8_t*>(qv)[e]);
+                else x = load1<(QT == QT_F32) ? 4 : 2>(qv, e);
                 qn2 = fmaf(x, x, qn2);
             }
             const float a_thr = key_dist(a_key), dk = key_dist(d_key);

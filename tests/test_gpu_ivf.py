@@ -60,7 +60,7 @@ def test_exact_parity_external_queries(gpu, dtype, metric, n, dim, nlist, nq, k,
     g.set_option("ivf_list_major", 1)      # list-major batched scans: (list, query group) tasks
     g.set_option("path", annb200.PATH_SIMT)
     _check(dtype, g.query_batch(q, k, nprobe=nprobe), ref, "list-major CUDA-core scan")
-    if dtype != "sq8" and k <= 24:         # tensor-core grouped scan (tcgen05) + exact re-rank
+    if k <= 24:                            # tensor-core grouped scan (tcgen05) + exact re-rank
         g.set_option("path", annb200.PATH_TENSOR)
         _check(dtype, g.query_batch(q, k, nprobe=nprobe), ref, "list-major tensor-core scan")
         assert g.get_stat("last_path") == annb200.PATH_TENSOR

@@ -10,7 +10,7 @@ from util import assert_exact, assert_tolerance
 
 pytestmark = pytest.mark.gpu
 
-DT = {"f32": (annb200.F32, o.F32), "bf16": (annb200.BF16, o.BF16)}
+DT = {"f32": (annb200.F32, o.F32), "bf16": (annb200.BF16, o.BF16), "sq8": (annb200.SQ8, o.SQ8)}
 MET = {"l2": (annb200.L2, o.L2), "cosine": (annb200.COSINE, o.COSINE)}
 
 
@@ -43,7 +43,7 @@ def test_first_tile_values_match_a_float64_gemm(gpu, dtype, metric, dim):
     assert err < 2e-6, f"tile error {err:.3e} (3xTF32 / bf16x3 should be ~1e-7)"
 
 
-@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "sq8"])
 @pytest.mark.parametrize("metric", ["l2", "cosine"])
 @pytest.mark.parametrize("n,dim,nq,k", [(20000, 128, 300, 10), (9000, 32, 129, 15), (5000, 50, 64, 10), (4100, 96, 7, 1)])
 def test_exact_parity_with_oracle(gpu, dtype, metric, n, dim, nq, k):
@@ -60,7 +60,7 @@ def test_exact_parity_with_oracle(gpu, dtype, metric, n, dim, nq, k):
         assert_exact(ids, d, rids, rd, f"tensor flat db_splits={splits}")
 
 
-@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "sq8"])
 def test_self_queries(gpu, dtype):
     data = datagen.correlated(6000, 64, seed=23)
     g, c = _pair(data, dtype, "cosine")
@@ -110,3 +110,33 @@ def test_certificate_and_exact_fallback(gpu):
     g.set_option("cert_eps_log2", -20)
     ids, d, _ = g.query_batch(q, 10)
     assert_exact(ids, d, ref[0], ref[1], "default bound")
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("dim", [200, 400])
+def test_sq8_int8_mma_wide_rows_and_ties(gpu, metric, dim):
+    """SQ8 on the int8 tensor path (kind::i8, s32 accumulators): dims spanning several 128-code slabs, and coarse data whose
+    integer distances tie heavily -- a tie between the k-th distance and the k'-th pre-selected value must be routed
+    to the exact path, never resolved differently from the reference's (distance, id) order."""
+    rng = np.random.default_rng(dim)
+    data = rng.integers(-3, 4, size=(6000, dim)).astype(np.float32)          # few distinct codes -> many equal distances
+    q = data[rng.choice(6000, 150, replace=False)] + rng.integers(-1, 2, size=(150, dim)).astype(np.float32)
+    g, c = _pair(data, "sq8", metric)
+    ref = o.flat_search(c, q, 10)
+    for splits in (0, 1, 4):
+        g.set_option("db_splits", splits)
+        ids, d, _ = g.query_batch(q, 10)
+        assert g.get_stat("last_path") == annb200.PATH_TENSOR
+        assert_exact(ids, d, ref[0], ref[1], f"sq8 tensor {metric} dim={dim} splits={splits}")
+
+
+def test_bf16_wide_rows_use_the_smem_query_operand(gpu):
+    """bf16 rows wider than 128 do not fit the TMEM query budget (3 terms x 128 columns): the kernel falls back to
+    shared-memory query operands and stays exact."""
+    data = datagen.gaussian_noise(9000, 200, seed=31)
+    q = datagen.subsample_with_noise(data, 140, seed=31)
+    g, c = _pair(data, "bf16", "l2")
+    ids, d, _ = g.query_batch(q, 10)
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    ref = o.flat_search(c, q, 10)
+    assert_exact(ids, d, ref[0], ref[1], "bf16 dim 200")
