@@ -323,7 +323,10 @@ static int flat_simt(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uin
 // IVF search core
 // ---------------------------------------------------------------------------
 static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint32_t nprobe, const uint64_t* row_map,
-                    uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s, bool force_simt = false) {
+                    uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s, bool force_simt = false,
+                    const uint32_t* preset_probes = nullptr, const uint32_t* preset_nprobes = nullptr, uint32_t preset_pitch = 0) {
+    // preset_*: probe lists already computed for these queries (the exact fallback of the tensor path re-uses the
+    // parent call's ranking instead of ranking the centroids again)
     const uint32_t kk = static_cast<uint32_t>(std::min<uint64_t>(k, ix->n_total));
     if (kk == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "k must be >= 1");
     if (kk > 1024) return fail(ANNB_ERR_UNSUPPORTED, "k > 1024 is not supported");
@@ -341,8 +344,34 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
     // select's sort buffer is exactly full (smaller shared memory -> more resident CTAs)
     uint32_t pitch = ix->nlist <= 1024 ? ix->nlist : std::min(ix->nlist, next_pow2(np + 16 + 64) - 64);
     bool probes_ready = false;
+    if (preset_probes) { pitch = preset_pitch; probes_ready = true; }
+    ix->stat_coarse_path = 0;
+    // 1+2 (tensor path). dense approximate values on the tensor cores, then per query: radix select of the nearest
+    //      np + 32 cells, exact distances for those, certified (distance, cell) prefix -> the same probe walk.
+    if (!probes_ready && !force_simt && ix->opt_path != ANNB_PATH_SIMT && ix->opt_ivf_tc_coarse && tc_coarse_supported(ix)) {
+        const uint32_t p_tc = round_up(np + 32u, 32u);
+        if (p_tc < ix->nlist && p_tc <= 480) {
+            ANNB_TRY(ix->s_cdist.ensure(nq * static_cast<uint64_t>(p_tc) * 8));
+            ANNB_TRY(ix->s_probes.ensure(nq * static_cast<uint64_t>(p_tc) * 4));
+            ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 64, s));
+            ANNB_TRY(tc_coarse_rank(ix, pq.route, pq.route_ld, nq, p_tc, ix->s_cdist.as<uint64_t>(), s));
+            ProbeParams pp{};
+            pp.nq = nq; pp.nlist = ix->nlist; pp.offsets = ix->d_offsets; pp.nprobe = np; pp.k = kk;
+            pp.probes = ix->s_probes.as<uint32_t>(); pp.probe_pitch = p_tc; pp.n_probes = ix->s_nprobes.as<uint32_t>();
+            pp.overflow = ix->s_flags.as<uint32_t>();
+            pp.stat_scanned = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 8);
+            pp.stat_probed = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 16);
+            probe_walk_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 128)), 128, 0, s>>>(ix->s_cdist.as<uint64_t>(), pp);
+            ANNB_CUDA_CHECK(cudaGetLastError());
+            ix->stat_launches++;
+            uint32_t h_flag[2];
+            ANNB_CUDA_CHECK(cudaMemcpyAsync(h_flag, ix->s_flags.p, sizeof(h_flag), cudaMemcpyDeviceToHost, s));
+            ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+            if (!h_flag[0]) { probes_ready = true; pitch = p_tc; ix->stat_coarse_path = 2; }   // else: some rank was not certifiable -> exact ranking below
+        }
+    }
     // (wide prefixes make the fused select's sort buffers large and its pass rate high: above 64 ranks the dense matrix + sort wins)
-    if (pitch < ix->nlist && (ix->opt_ivf_fast_probe == 1 ? pitch <= 64 : ix->opt_ivf_fast_probe != 0)) {
+    if (!probes_ready && pitch < ix->nlist && (ix->opt_ivf_fast_probe == 1 ? pitch <= 64 : ix->opt_ivf_fast_probe != 0)) {
         const uint32_t nsort = WarpSelect::sort_size(pitch);
         const uint32_t cb = ix->cent_ld * 4, qb = pq.route_ld * 4;
         const size_t smem = tile_kernel_smem(cb, qb, nsort, true);
@@ -370,7 +399,7 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
             uint32_t h_flag[2];
             ANNB_CUDA_CHECK(cudaMemcpyAsync(h_flag, ix->s_flags.p, sizeof(h_flag), cudaMemcpyDeviceToHost, s));
             ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
-            if (!h_flag[0]) probes_ready = true;
+            if (!h_flag[0]) { probes_ready = true; ix->stat_coarse_path = 1; }
             else pitch = ix->nlist;      // rare: some query needs more than nprobe + 64 cells -> full ranking below
         }
     }
@@ -413,6 +442,8 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         if (!h_flag[0]) break;
         pitch = ix->nlist;
     }
+    const uint32_t* d_probes = preset_probes ? preset_probes : ix->s_probes.as<uint32_t>();
+    const uint32_t* d_nprobes = preset_probes ? preset_nprobes : ix->s_nprobes.as<uint32_t>();
     // 3. list scan.  A batch that probes every list many times goes list-major (one staged list tile serves up to 32
     //    queries); small batches keep the query-major streaming kernel (one warp per query part).
     const uint64_t n_local_lists = std::max<uint32_t>(1, ix->list_end - ix->list_begin);
@@ -439,7 +470,7 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         uint32_t* w = ix->s_pairs.as<uint32_t>();
         ANNB_CUDA_CHECK(cudaMemsetAsync(w, 0, hdr, s));
         PairParams pp{};
-        pp.probes = ix->s_probes.as<uint32_t>(); pp.probe_pitch = pitch; pp.n_probes = ix->s_nprobes.as<uint32_t>(); pp.nq = nq;
+        pp.probes = d_probes; pp.probe_pitch = pitch; pp.n_probes = d_nprobes; pp.nq = nq;
         pp.nlist = ix->nlist; pp.list_begin = ix->list_begin; pp.list_end = ix->list_end;
         pp.cnt = w; pp.cursor = w + (nl + 1); pp.pair_off = w + 2 * (nl + 1); pp.task_off = w + 3 * (nl + 1); pp.task_counter = w + 4 * (nl + 1);
         pp.pairs = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(w) + hdr);
@@ -453,7 +484,7 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         if (use_tc) {
             const uint64_t max_tasks_tc = ceil_div<uint64_t>(slots, 128) + n_local_lists;
             ANNB_TRY(tc_ivf_scan(ix, pq.scan, pq.scan_bytes, nq, kk, k, pitch, pp.pair_off, pp.task_off, pp.pairs, pp.task_counter, max_tasks_tc,
-                                 ix->s_nprobes.as<uint32_t>(), row_map, d_ids, d_dist, d_cnt, s));
+                                 d_nprobes, row_map, d_ids, d_dist, d_cnt, s));
             uint32_t n_unc = 0;
             ANNB_TRY(read_uncertified(ix, &n_unc, s));
             if (n_unc == 0 || row_map != nullptr) return ANNB_OK;
@@ -465,20 +496,24 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
             ANNB_TRY(ix->s_fbq.ensure(static_cast<uint64_t>(n_unc) * pq.scan_bytes));
             gather_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * (pq.scan_bytes >> 4), 256), 256, 0, s>>>(pq.scan, pq.scan_bytes, list, n_unc, ix->s_fbq.as<uint8_t>());
             sub.scan = ix->s_fbq.as<uint8_t>();
-            ANNB_TRY(ix->s_fbr.ensure(static_cast<uint64_t>(n_unc) * pq.route_ld * 4));
-            gather_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * (pq.route_ld >> 2), 256), 256, 0, s>>>(reinterpret_cast<const uint8_t*>(pq.route), pq.route_ld * 4, list, n_unc,
-                                                                                                                ix->s_fbr.as<uint8_t>());
+            // their probe lists are re-used: [n_unc][pitch] cell ids followed by [n_unc] probe counts
+            ANNB_TRY(ix->s_fbr.ensure(static_cast<uint64_t>(n_unc) * (pitch + 1) * 4));
+            uint32_t* fb_probes = ix->s_fbr.as<uint32_t>();
+            uint32_t* fb_nprobes = fb_probes + static_cast<uint64_t>(n_unc) * pitch;
+            gather_u32_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * pitch, 256), 256, 0, s>>>(d_probes, pitch, list, n_unc, fb_probes);
+            gather_u32_rows_kernel<<<grid_for(n_unc, 256), 256, 0, s>>>(d_nprobes, 1, list, n_unc, fb_nprobes);
             ANNB_CUDA_CHECK(cudaGetLastError());
-            sub.route = ix->s_fbr.as<float>();
+            sub.route = nullptr;
             ANNB_TRY(ix->s_fbi.ensure(static_cast<uint64_t>(n_unc) * k * 8));
             ANNB_TRY(ix->s_fbd.ensure(static_cast<uint64_t>(n_unc) * k * 4));
             ANNB_TRY(ix->s_fbc.ensure(static_cast<uint64_t>(n_unc) * 4));
             // the list of uncertified queries lives in s_uncert, which the nested call does not touch (it stays on the CUDA-core path)
-            ANNB_TRY(ivf_core(ix, sub, n_unc, k, nprobe, nullptr, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(), ix->s_fbc.as<uint32_t>(), s, true));
+            ANNB_TRY(ivf_core(ix, sub, n_unc, k, nprobe, nullptr, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(), ix->s_fbc.as<uint32_t>(), s, true,
+                              fb_probes, fb_nprobes, pitch));
             scatter_results_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * k, 256), 256, 0, s>>>(list, n_unc, k, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(),
                                                                                                  ix->s_fbc.as<uint32_t>(), d_ids, d_dist, d_cnt);
             ANNB_CUDA_CHECK(cudaGetLastError());
-            ix->stat_launches += 3;
+            ix->stat_launches += 4;
             ix->stat_fallback_queries += n_unc;
             ix->stat_last_path = ANNB_PATH_TENSOR;
             return ANNB_OK;
@@ -498,23 +533,26 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
             ANNB_TRY(launch_list_scan(ix->dtype, pq.qt, ix->metric, lp, grid, smem, s));
         }
         ix->stat_launches++;
-        return run_finalize(ix, ix->s_keys.as<uint64_t>(), pitch, kk, k, nq, ix->d_original_ids, 0, row_map, d_ids, d_dist, d_cnt, s,
-                            ix->s_nprobes.as<uint32_t>());
+        return run_finalize(ix, ix->s_keys.as<uint64_t>(), pitch, kk, k, nq, ix->d_original_ids, 0, row_map, d_ids, d_dist, d_cnt, s, d_nprobes);
     }
-    uint32_t parts = ix->opt_scan_parts > 0 ? static_cast<uint32_t>(ix->opt_scan_parts)
-                                            : static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(16, ceil_div<uint64_t>(148ull * 32, std::max<uint64_t>(nq, 1)))));
+    // warps wanted per query so that a small batch still fills the machine (148 SMs x 32 warps)
+    const uint64_t want = std::max<uint64_t>(1, std::min<uint64_t>(256, ceil_div<uint64_t>(148ull * 32, std::max<uint64_t>(nq, 1))));
+    uint32_t parts = ix->opt_scan_parts > 0 ? static_cast<uint32_t>(ix->opt_scan_parts) : static_cast<uint32_t>(std::min<uint64_t>(want, 32));
     parts = std::max(1u, std::min(parts, np));
+    // very small batches (the tensor path's exact fallback): also cut every list into row segments
+    uint32_t subs = ix->opt_scan_parts > 0 ? 1u : static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(8, want / parts)));
+    while (subs > 1 && static_cast<uint64_t>(parts) * subs * kk * 8 > 128 * 1024) subs--;
     const uint32_t nsort = WarpSelect::sort_size(kk);
-    ANNB_TRY(ix->s_keys.ensure(nq * parts * static_cast<uint64_t>(kk) * 8));
+    ANNB_TRY(ix->s_keys.ensure(nq * parts * subs * static_cast<uint64_t>(kk) * 8));
     {
         ScanParams sp{};
         sp.rows = ix->d_rows; sp.row_bytes = ix->row_bytes; sp.row_norms = ix->d_norms; sp.row_norms_i = ix->d_norms_i;
         sp.queries = pq.scan; sp.q_bytes = pq.scan_bytes; sp.nq = nq; sp.dim = ix->dim; sp.bf16_self = pq.bf16_self;
-        sp.probes = ix->s_probes.as<uint32_t>(); sp.probe_pitch = pitch; sp.n_probes = ix->s_nprobes.as<uint32_t>();
+        sp.probes = d_probes; sp.probe_pitch = pitch; sp.n_probes = d_nprobes;
         sp.offsets = ix->d_offsets; sp.list_begin = ix->list_begin; sp.list_end = ix->list_end; sp.shard_row0 = ix->shard_row0;
-        sp.parts = parts; sp.k = kk; sp.nsort = nsort; sp.part_keys = ix->s_keys.as<uint64_t>();
+        sp.parts = parts; sp.subs = subs; sp.k = kk; sp.nsort = nsort; sp.part_keys = ix->s_keys.as<uint64_t>();
         size_t smem = scan_kernel_smem(ix->row_bytes, pq.scan_bytes, nsort);
-        uint32_t grid = static_cast<uint32_t>(ceil_div<uint64_t>(nq * parts, SCAN_WARPS));
+        uint32_t grid = static_cast<uint32_t>(ceil_div<uint64_t>(nq * parts * subs, SCAN_WARPS));
         {
             KernelTimer kt(ix, s);
             ANNB_TRY(launch_scan(ix->dtype, pq.qt, ix->metric, sp, grid, smem, s));
@@ -522,7 +560,7 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         ix->stat_launches++;
     }
     // 4. merge parts, map list-order positions to original ids (src/cpu/ivf.rs:383-389)
-    return run_finalize(ix, ix->s_keys.as<uint64_t>(), parts, kk, k, nq, ix->d_original_ids, 0, row_map, d_ids, d_dist, d_cnt, s);
+    return run_finalize(ix, ix->s_keys.as<uint64_t>(), parts * subs, kk, k, nq, ix->d_original_ids, 0, row_map, d_ids, d_dist, d_cnt, s);
 }
 
 static int read_ivf_stats(annb_index* ix, cudaStream_t s) {
@@ -647,6 +685,7 @@ void annb_destroy(annb_index* ix) {
     collect_timers(ix);
     tc_destroy(ix);
     tc_ivf_destroy(ix);
+    tc_coarse_destroy(ix);
     cudaFree(ix->d_rows); cudaFree(ix->d_norms); cudaFree(ix->d_norms_i); cudaFree(ix->d_scales);
     cudaFree(ix->d_centroids); cudaFree(ix->d_centroid_norms); cudaFree(ix->d_offsets); cudaFree(ix->d_original_ids);
     for (DevBuf* b : {&ix->s_qpad, &ix->s_qcodes, &ix->s_route, &ix->s_cdist, &ix->s_probes, &ix->s_nprobes, &ix->s_keys, &ix->s_flags,
@@ -883,6 +922,7 @@ int annb_ivf_create(annb_index** out, const void* vectors, const void* norms, co
     }
     ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
     ANNB_TRY(tc_ivf_prepare(ix));
+    ANNB_TRY(tc_coarse_prepare(ix));
     ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
     cleanup.armed = false;
     *out = ix;
@@ -965,6 +1005,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "scan_parts") ix->opt_scan_parts = static_cast<int>(value);
     else if (k == "ivf_list_major") ix->opt_ivf_list_major = static_cast<int>(value);
     else if (k == "ivf_fast_probe") ix->opt_ivf_fast_probe = static_cast<int>(value);
+    else if (k == "ivf_tc_coarse") ix->opt_ivf_tc_coarse = static_cast<int>(value);
     else if (k == "time_kernels") { ix->opt_time_kernels = static_cast<int>(value); ix->timed_ms_total = 0.0; ix->timed_launches = 0; }
     else return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown option " + k);
     return ANNB_OK;
@@ -995,6 +1036,7 @@ int annb_index_get_stat(const annb_index* ix, const char* key, int64_t* out) {
     else if (k == "scanned_vectors") *out = ix->stat_scanned;
     else if (k == "probed_lists") *out = ix->stat_probed;
     else if (k == "last_path") *out = ix->stat_last_path;
+    else if (k == "coarse_path") *out = ix->stat_coarse_path;
     else if (k == "fallback_queries") *out = ix->stat_fallback_queries;
     else if (k == "uncertified") {
         // queries of the last tensor-path call whose pre-selection margin could not be certified (see rerank_kernel)

@@ -30,7 +30,9 @@ namespace tc {
 // ----------------------------------------------------------------------------------------------- the kernel
 // TS = the query operand lives in TMEM (columns [0, 256): hi then lo) instead of shared memory: the MMAs read only the
 // database slab from shared memory (half the operand bandwidth) and the whole 227 KB becomes database ring.
-template <int KIND, int KP, int MET, bool TS>
+// DENSE = write every selection value to p.dense instead of keeping a top-k' (the IVF centroid ranking consumes the full
+// [nq x nlist] matrix of approximate values; see coarse_select_kernel).
+template <int KIND, int KP, int MET, bool TS, bool DENSE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const Params p) {
     constexpr int NA = (KIND == KIND_TF32X3) ? 2 : (KIND == KIND_I8 ? 1 : 3);  // stacked query pieces
@@ -212,7 +214,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             mbar_arrive(bar_q);
         }
         uint32_t* gtau_ptr = p.gtau + q0 + row_in_tile;
-        uint32_t g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
+        uint32_t g_next = DENSE ? 0xFFFFFFFFu : *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
         // Per-column constants of this warp's 64-column half: lane l keeps columns l and l + 32 in registers
         // (coalesced load, fetched one tile ahead) and the warp broadcasts them with shuffles -- no shared memory,
         // no barrier between the epilogue warps.
@@ -227,7 +229,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             if (t + 1 < n_tiles) {   // prefetch for the next tile: latency hidden behind this tile's work
                 aux_lo_next = __ldg(aux_half + static_cast<size_t>(t + 1) * BN);
                 aux_hi_next = __ldg(aux_half + static_cast<size_t>(t + 1) * BN + 32);
-                g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
+                if (!DENSE) g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
             }
             mbar_wait_timed(bar_tfull + acc, aph, w_tfull);
             tc_fence_after();
@@ -255,7 +257,14 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     }
                     gm[g] = mg;
                 }
-                const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
+                if constexpr (DENSE) {
+                    if (static_cast<uint64_t>(q0) + row_in_tile < p.nq) {
+                        float4* dst = reinterpret_cast<float4*>(p.dense + (static_cast<uint64_t>(q0) + row_in_tile) * p.dense_ld + row0 + c * 64);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                    }
+                }
+                const float m = DENSE ? INFINITY : fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
                 if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t == 0) {
 #pragma unroll
                     for (int j = 0; j < 64; j++) p.dbg[row_in_tile * BN + c * 64 + j] = v[j];
@@ -288,11 +297,11 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             }
             tc_fence_before();
             mbar_arrive(bar_tempty + acc);
-            if (top.tau() < g_tau || (g_tau != g_tau && top.tau() < INFINITY)) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));
+            if (!DENSE && (top.tau() < g_tau || (g_tau != g_tau && top.tau() < INFINITY))) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));
         }
         if (p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) { p.dbg_cycles[4] = w_tfull; p.dbg_cycles[5] = w_slow; }
         const uint64_t q = static_cast<uint64_t>(q0) + row_in_tile;
-        if (q < p.nq) {
+        if (!DENSE && q < p.nq) {
             uint64_t* out = p.part_keys + (q * (2 * p.n_splits) + 2 * blockIdx.y + half) * KP;
 #pragma unroll
             for (int j = 0; j < KP; j++) out[j] = (top.i[j] == IDX_INVALID) ? KEY_SENTINEL : make_key(top.v[j], top.i[j]);
@@ -306,6 +315,163 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     }
 }
 
+// ----------------------------------------------------------------------------------------------- IVF centroid ranking
+// Second stage of the tensor-core centroid ranking (src/cpu/ivf.rs:349-365 get_centroids_dist + select_probed_clusters'
+// sort): one warp per query turns its row of approximate values (DENSE mode of the kernel above) into the `pitch`
+// nearest (distance, cell) keys in ascending order, exact in the reference's arithmetic:
+//   1. radix select (4 passes of 8 bits over the order-preserving integer image) finds the pitch-th smallest value,
+//   2. every cell at or below it becomes a candidate (ties included; more than cmax candidates -> nothing is emitted),
+//   3. the candidates' distances are recomputed with refdist.cuh and sorted by (distance, cell),
+//   4. only ranks that provably precede every non-candidate are emitted: exact distance < threshold - error bound.
+// Ranks that cannot be certified are written as sentinels; probe_walk_kernel flags a query that runs into one and the
+// caller repeats the batch on the exact CUDA-core ranking.
+struct CoarseSelectParams {
+    const float* dense;         // [nq][dense_ld] approximate selection values
+    uint32_t dense_ld;
+    uint64_t nq;
+    uint32_t nlist, pitch, cmax;   // cmax: candidate capacity, a power of two >= pitch
+    const float* queries;       // f32 routing queries [nq][q_ld]
+    uint32_t q_ld;
+    const float* centroids;     // [nlist][c_ld]
+    uint32_t c_ld;
+    const float* centroid_norms;
+    uint32_t dim;
+    float eps, cnorm_max;
+    uint64_t* ranked;           // [nq][pitch]
+};
+
+__host__ __device__ inline size_t coarse_select_warp_bytes(uint32_t nlist, uint32_t cmax) {
+    return static_cast<size_t>(cmax) * 8 + static_cast<size_t>((nlist + 31u) & ~31u) * 4 + 256 * 4 + static_cast<size_t>(cmax) * 4;
+}
+
+template <int MET>
+__global__ void __launch_bounds__(128) coarse_select_kernel(CoarseSelectParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t q = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    if (q >= p.nq) return;   // warps are independent: no block-wide barrier below
+    uint8_t* base = smem + warp * coarse_select_warp_bytes(p.nlist, p.cmax);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(base);                  // [cmax]
+    uint32_t* vals = reinterpret_cast<uint32_t*>(keys + p.cmax);         // [nlist rounded up to 32]
+    uint32_t* hist = vals + ((p.nlist + 31u) & ~31u);                    // [256]
+    uint32_t* cand = hist + 256;                                          // [cmax]
+    const float* src = p.dense + q * p.dense_ld;
+    for (uint32_t i = lane; i < p.nlist; i += 32) vals[i] = f32_to_ordered(src[i]);
+    __syncwarp();
+
+    // 1. pitch-th smallest value
+    uint32_t thr = 0xFFFFFFFFu;
+    const bool partial = p.pitch < p.nlist;
+    if (partial) {
+        uint32_t prefix = 0, mask = 0, need = p.pitch;
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            for (uint32_t b = lane; b < 256; b += 32) hist[b] = 0;
+            __syncwarp();
+            for (uint32_t i = lane; i < p.nlist; i += 32) {
+                const uint32_t u = vals[i];
+                if ((u & mask) == prefix) atomicAdd(hist + ((u >> shift) & 255u), 1u);
+            }
+            __syncwarp();
+            uint32_t h[8], local = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) { h[j] = hist[8 * lane + j]; local += h[j]; }
+            uint32_t incl = local;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                if (lane >= static_cast<uint32_t>(off)) incl += t;
+            }
+            const uint32_t excl = incl - local;
+            const bool mine = excl < need && need <= incl;
+            const int owner = __ffs(__ballot_sync(0xFFFFFFFFu, mine)) - 1;
+            uint32_t bin = 0, before = 0;
+            if (mine) {
+                uint32_t c = excl;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    if (need > c && need <= c + h[j]) { bin = 8 * lane + j; before = c; }
+                    c += h[j];
+                }
+            }
+            bin = __shfl_sync(0xFFFFFFFFu, bin, owner);
+            before = __shfl_sync(0xFFFFFFFFu, before, owner);
+            need -= before;
+            prefix |= bin << shift;
+            mask |= 255u << shift;
+            __syncwarp();
+        }
+        thr = prefix;
+    }
+    // 2. candidates: every cell with value <= thr
+    uint32_t count = 0;
+    for (uint32_t i0 = 0; i0 < p.nlist; i0 += 32) {
+        const uint32_t i = i0 + lane;
+        const bool hit = i < p.nlist && vals[i] <= thr;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+        if (hit) {
+            const uint32_t pos = count + __popc(m & ((1u << lane) - 1u));
+            if (pos < p.cmax) cand[pos] = i;
+        }
+        count += __popc(m);
+    }
+    __syncwarp();
+    uint64_t* out = p.ranked + q * p.pitch;
+    if (count > p.cmax) {   // a huge tie class: leave the query to the exact ranking
+        for (uint32_t j = lane; j < p.pitch; j += 32) out[j] = KEY_SENTINEL;
+        return;
+    }
+    // 3. exact distances of the candidates, reference arithmetic
+    const uint8_t* qrow = reinterpret_cast<const uint8_t*>(p.queries + q * p.q_ld);
+    float qn = 1.0f;
+    if (MET == MET_COS) {
+        if (lane == 0) qn = seq_norm<4>(qrow, p.dim);
+        qn = __shfl_sync(0xFFFFFFFFu, qn, 0);
+    }
+    for (uint32_t j = lane; j < p.cmax; j += 32) {
+        uint64_t key = KEY_SENTINEL;
+        if (j < count) {
+            const uint32_t c = cand[j];
+            float raw[1];
+            accumulate_fp<4, 4, MET == MET_L2, 1>(reinterpret_cast<const uint8_t*>(p.centroids + static_cast<uint64_t>(c) * p.c_ld), qrow, p.q_ld * 4, p.dim, raw);
+            const float cn = (MET == MET_COS) ? p.centroid_norms[c] : 1.0f;
+            key = make_key(finish_fp<MET>(raw[0], qn, cn), c);
+        }
+        keys[j] = key;
+    }
+    __syncwarp();
+    bitonic_sort_keys<false>(keys, p.cmax, lane, 32);
+    // 4. certified prefix
+    float bound = INFINITY;
+    if (partial) {
+        float qn2 = 0.f;
+        for (uint32_t e = lane; e < p.dim; e += 32) {
+            const float x = reinterpret_cast<const float*>(qrow)[e];
+            qn2 = fmaf(x, x, qn2);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) qn2 += __shfl_xor_sync(0xFFFFFFFFu, qn2, off);
+        const float tv = ordered_to_f32(thr);   // every non-candidate's approximate value exceeds this
+        if (MET == MET_L2) {
+            const float s = sqrtf(qn2) + p.cnorm_max;            // value = dist - |q|^2, error <= eps (|q| + |c|max)^2
+            bound = tv + qn2 - p.eps * s * s;
+        } else if (MET == MET_COS) {
+            const float qq = sqrtf(qn2);                          // value = (dist - 1) |q|, error <= eps |q|
+            bound = qq > 0.f ? tv / qq + 1.0f - p.eps : -INFINITY;
+        } else {
+            bound = tv + 1.0f - p.eps * fmaxf(1.0f, sqrtf(qn2) * p.cnorm_max);   // pre-normalised: value = dist - 1
+        }
+    }
+    for (uint32_t j = lane; j < p.pitch; j += 32) {
+        const uint64_t key = keys[j];
+        out[j] = (key_idx(key) != IDX_INVALID && key_dist(key) < bound) ? key : KEY_SENTINEL;
+    }
+}
+
+static __global__ void fill_aux_kernel(float* __restrict__ aux, uint64_t n, uint64_t n_total, float value) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i < n_total) aux[i] = i < n ? value : INFINITY;
+}
+
 }  // namespace tc
 
 // =============================================================================================== host side
@@ -317,7 +483,7 @@ struct TcState {
     void* d_x = nullptr;      // stacked database operand (nullptr: the index rows themselves are used)
     float* d_aux = nullptr;   // [n_pad + BN]
     CUtensorMap tm_x;
-    DevBuf q_op, part, dbg, gtau, dbgc;
+    DevBuf q_op, part, dbg, gtau, dbgc, dense;
     uint64_t bytes = 0;
 };
 
@@ -354,9 +520,14 @@ int tc_make_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint32_t kp_elems, 
 uint32_t tc_blocks_for(uint64_t work) { return static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>((work + 255) / 256, 148 * 16))); }
 
 // Largest stored-row norm from the per-row constants (L2 only; cosine needs no norm bound).
+static int tc_aux_norm_max(annb_index* ix, const float* d_aux, uint64_t n, float* out);
 int tc_compute_xnorm_max(annb_index* ix, const float* d_aux, uint64_t n) {
     ix->tc_xnorm_max = 0.f;
     if (ix->metric != ANNB_L2) return ANNB_OK;
+    return tc_aux_norm_max(ix, d_aux, n, &ix->tc_xnorm_max);
+}
+// sqrt of the largest of n squared norms held in d_aux
+static int tc_aux_norm_max(annb_index* ix, const float* d_aux, uint64_t n, float* out) {
     uint32_t* d_bits = nullptr;
     ANNB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_bits), 4));
     ANNB_CUDA_CHECK(cudaMemsetAsync(d_bits, 0, 4, ix->stream));
@@ -368,7 +539,7 @@ int tc_compute_xnorm_max(annb_index* ix, const float* d_aux, uint64_t n) {
     ANNB_CUDA_CHECK(e);
     float sq;
     std::memcpy(&sq, &bits, 4);
-    ix->tc_xnorm_max = std::sqrt(sq);
+    *out = std::sqrt(sq);
     return ANNB_OK;
 }
 
@@ -591,6 +762,116 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     else rc = cos ? launch_rerank<1, QT_BF16, MET_COS>(r, s) : launch_rerank<1, QT_BF16, MET_L2>(r, s);
     ANNB_TRY(rc);
     ix->stat_launches++;
+    return ANNB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- IVF centroid ranking
+// The centroid table as a tensor-core operand (3xTF32, like a flat f32 index); see coarse_select_kernel.
+int tc_coarse_prepare(annb_index* ix) {
+    if (!ix->is_ivf || ix->nlist < 512) return ANNB_OK;      // small tables: the exact CUDA-core ranking is already cheap
+    const uint32_t slab_elems = tc::SLAB_BYTES / 4;
+    const uint32_t kp = round_up(ix->dim, slab_elems);
+    if (kp * 4 > 512) return ANNB_OK;
+    TcState* st = new TcState();
+    ix->tc_coarse = st;
+    st->kind = tc::KIND_TF32X3;
+    st->kp_elems = kp;
+    st->nslab = kp / slab_elems;
+    st->n_pad = round_up<uint32_t>(ix->nlist, tc::BN);
+    cudaStream_t s = ix->stream;
+    const uint64_t aux_rows = static_cast<uint64_t>(st->n_pad) + tc::BN;
+    ANNB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&st->d_aux), aux_rows * sizeof(float)));
+    const uint32_t ag = static_cast<uint32_t>((aux_rows + 127) / 128);
+    const uint8_t* crow = reinterpret_cast<const uint8_t*>(ix->d_centroids);
+    tc::aux_kernel<<<ag, 128, 0, s>>>(crow, ix->cent_ld * 4, 0, ix->dim, nullptr, nullptr, 0, ix->nlist, aux_rows, st->d_aux);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    ANNB_TRY(tc_aux_norm_max(ix, st->d_aux, ix->nlist, &ix->tc_cnorm_max));
+    if (ix->metric == ANNB_COSINE) {
+        if (ix->dtype == ANNB_SQ8) tc::fill_aux_kernel<<<ag, 128, 0, s>>>(st->d_aux, ix->nlist, aux_rows, -1.0f);   // pre-normalised: value = -q.c
+        else tc::aux_kernel<<<ag, 128, 0, s>>>(crow, ix->cent_ld * 4, 0, ix->dim, ix->d_centroid_norms, nullptr, 1, ix->nlist, aux_rows, st->d_aux);
+        ANNB_CUDA_CHECK(cudaGetLastError());
+    }
+    const uint64_t bytes = 2ull * st->n_pad * kp * 4;
+    ANNB_CUDA_CHECK(cudaMalloc(&st->d_x, bytes));
+    tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * kp), 256, 0, s>>>(ix->d_centroids, ix->cent_ld, ix->dim, ix->nlist, st->n_pad, kp,
+                                                                                            static_cast<float*>(st->d_x));
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    ANNB_TRY(tc_make_tmap(&st->tm_x, st->d_x, 2ull * st->n_pad, kp, 4));
+    st->bytes = bytes + aux_rows * sizeof(float);
+    ix->device_bytes += st->bytes;
+    return ANNB_OK;
+}
+
+void tc_coarse_destroy(annb_index* ix) {
+    if (!ix->tc_coarse) return;
+    cudaFree(ix->tc_coarse->d_x);
+    cudaFree(ix->tc_coarse->d_aux);
+    ix->tc_coarse->q_op.release();
+    ix->tc_coarse->dense.release();
+    delete ix->tc_coarse;
+    ix->tc_coarse = nullptr;
+}
+
+bool tc_coarse_supported(const annb_index* ix) { return ix->tc_coarse != nullptr; }
+
+template <int MET>
+static int launch_coarse_select(const tc::CoarseSelectParams& c, cudaStream_t s) {
+    auto kern = tc::coarse_select_kernel<MET>;
+    const size_t per_warp = tc::coarse_select_warp_bytes(c.nlist, c.cmax);
+    const uint32_t warps = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(4, (100 * 1024) / per_warp)));
+    const size_t smem = per_warp * warps;
+    if (smem > 200 * 1024) { set_last_error("centroid ranking: nlist too large for the tensor-core selection"); return ANNB_ERR_UNSUPPORTED; }
+    ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<static_cast<uint32_t>((c.nq + warps - 1) / warps), warps * 32, smem, s>>>(c);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    return ANNB_OK;
+}
+
+// Ranked prefix of the centroid table for every query: d_ranked[nq][pitch] ascending (distance, cell) keys, sentinels
+// where a rank could not be certified.
+int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint64_t nq, uint32_t pitch, uint64_t* d_ranked, cudaStream_t s) {
+    TcState* st = ix->tc_coarse;
+    const uint32_t kp = st->kp_elems;
+    const uint32_t nq_pad = static_cast<uint32_t>(round_up<uint64_t>(nq, tc::BM));
+    ANNB_TRY(st->q_op.ensure(2ull * nq_pad * kp * 4));
+    tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(nq_pad) * kp), 256, 0, s>>>(d_route, route_ld, ix->dim, nq, nq_pad, kp, st->q_op.as<float>());
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    CUtensorMap tmq;
+    ANNB_TRY(tc_make_tmap(&tmq, st->q_op.p, 2ull * nq_pad, kp, 4));
+    const uint64_t q_tiles = nq_pad / tc::BM, db_tiles = st->n_pad / tc::BN;
+    // about two waves of CTAs: the whole matrix is a few tens of microseconds of tensor work
+    const uint32_t splits_req = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(db_tiles, (2 * 148 + q_tiles - 1) / q_tiles)));
+    const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;
+    const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
+    const size_t fixed = 256, budget = 227 * 1024;
+    const uint32_t stages = static_cast<uint32_t>(std::min<size_t>(8, (budget - fixed) / (2 * tc::SLAB_TILE)));
+    const size_t smem = static_cast<size_t>(stages) * 2 * tc::SLAB_TILE + fixed;
+    ANNB_TRY(st->dense.ensure(nq * static_cast<uint64_t>(st->n_pad) * 4));
+    tc::Params p{};
+    p.nq = nq; p.n_rows = ix->nlist; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
+    p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = 2; p.aux = st->d_aux;
+    p.q_op = st->q_op.as<void>(); p.kp = kp; p.dense = st->dense.as<float>(); p.dense_ld = st->n_pad;
+    {
+        dim3 grid(static_cast<uint32_t>(q_tiles), splits);
+        if (ix->metric == ANNB_L2) {
+            auto kern = tc::flat_tc_kernel<tc::KIND_TF32X3, 16, MET_L2, true, true>;
+            ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kern<<<grid, tc::NUM_THREADS, smem, s>>>(tmq, st->tm_x, p);
+        } else {
+            auto kern = tc::flat_tc_kernel<tc::KIND_TF32X3, 16, MET_COS, true, true>;
+            ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kern<<<grid, tc::NUM_THREADS, smem, s>>>(tmq, st->tm_x, p);
+        }
+        ANNB_CUDA_CHECK(cudaGetLastError());
+    }
+    tc::CoarseSelectParams c{};
+    c.dense = st->dense.as<float>(); c.dense_ld = st->n_pad; c.nq = nq; c.nlist = ix->nlist; c.pitch = pitch; c.cmax = next_pow2(pitch + 1);
+    c.queries = d_route; c.q_ld = route_ld; c.centroids = ix->d_centroids; c.c_ld = ix->cent_ld; c.centroid_norms = ix->d_centroid_norms;
+    c.dim = ix->dim; c.eps = ix->opt_cert_eps; c.cnorm_max = ix->tc_cnorm_max; c.ranked = d_ranked;
+    if (ix->metric == ANNB_L2) ANNB_TRY(launch_coarse_select<MET_L2>(c, s));
+    else if (ix->dtype == ANNB_SQ8) ANNB_TRY(launch_coarse_select<MET_COS_PRENORM>(c, s));
+    else ANNB_TRY(launch_coarse_select<MET_COS>(c, s));
+    ix->stat_launches += 3;
     return ANNB_OK;
 }
 

@@ -104,4 +104,8 @@ struct annb_index {
     annb::DevBuf s_uncert;         // [1 + nq] uncertified-query counter + list of the last tensor-path call
     annb::TcState* tc = nullptr;
     annb::IvfTcState* tc_ivf = nullptr;
+    annb::TcState* tc_coarse = nullptr;   // centroid table as a tensor-core operand (IVF centroid ranking)
+    float tc_cnorm_max = 0.f;             // largest centroid norm
+    int opt_ivf_tc_coarse = 1;            // rank the centroids on the tensor cores (0: CUDA-core ranking only)
+    mutable int64_t stat_coarse_path = 0; // last IVF call: 0 exact dense ranking, 1 fused CUDA-core select, 2 tensor cores
 };

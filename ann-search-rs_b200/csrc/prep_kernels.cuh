@@ -141,6 +141,13 @@ __global__ void gather_rows_kernel(const uint8_t* __restrict__ src, uint32_t row
         reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src + static_cast<uint64_t>(list[r]) * row_bytes)[c];
     }
 }
+// dst[i][:] = src[list[i]][:] for rows of `ld` 32-bit words (probe lists of the queries sent to the exact fallback).
+__global__ void gather_u32_rows_kernel(const uint32_t* __restrict__ src, uint32_t ld, const uint32_t* __restrict__ list, uint32_t n, uint32_t* __restrict__ dst) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= static_cast<uint64_t>(n) * ld) return;
+    const uint64_t r = i / ld;
+    dst[i] = src[static_cast<uint64_t>(list[r]) * ld + (i - r * ld)];
+}
 __global__ void scatter_results_kernel(const uint32_t* __restrict__ list, uint32_t count, uint32_t k, const uint64_t* __restrict__ ids,
                                        const float* __restrict__ dist, const uint32_t* __restrict__ cnt, uint64_t* __restrict__ out_ids,
                                        float* __restrict__ out_dist, uint32_t* __restrict__ out_cnt) {

@@ -244,7 +244,8 @@ struct ScanParams {
     uint32_t list_begin, list_end;
     uint64_t shard_row0;         // offsets[list_begin]
     uint32_t parts, k, nsort;
-    uint64_t* part_keys;         // [nq][parts][k]; key index = row position inside the shard
+    uint32_t subs;               // every probed list is cut into `subs` row segments, one warp each (tiny batches)
+    uint64_t* part_keys;         // [nq][parts * subs][k]; key index = row position inside the shard
 };
 
 template <int RT, int QT, int MET>
@@ -259,8 +260,10 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) ivf_scan_kernel(ScanParams p)
     uint8_t* s_x = s_q + p.q_bytes;                                       // [2][32][xpitch]
 
     const uint64_t task = static_cast<uint64_t>(blockIdx.x) * SCAN_WARPS + warp;
-    const uint64_t q = task / p.parts;
-    const uint32_t part = static_cast<uint32_t>(task % p.parts);
+    const uint32_t slices = p.parts * p.subs;
+    const uint64_t q = task / slices;
+    const uint32_t slice = static_cast<uint32_t>(task % slices);
+    const uint32_t part = slice / p.subs, sub = slice - part * p.subs;
     if (q >= p.nq) return;  // whole warp exits together (task is warp-uniform)
 
     for (uint32_t c = lane; c < (p.q_bytes >> 4); c += 32)
@@ -299,6 +302,11 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) ivf_scan_kernel(ScanParams p)
             if (c < p.list_begin || c >= p.list_end) continue;  // list lives on another shard
             pos = p.offsets[c] - p.shard_row0;
             end = p.offsets[c + 1] - p.shard_row0;
+            if (p.subs > 1) {   // this warp's segment of the list (whole tiles)
+                const uint64_t seg = ((end - pos + p.subs - 1) / p.subs + TILE_ROWS - 1) / TILE_ROWS * TILE_ROWS;
+                pos = min(end, pos + sub * seg);
+                end = min(end, pos + seg);
+            }
         }
         t_row = pos;
         t_n = static_cast<uint32_t>(min(static_cast<uint64_t>(TILE_ROWS), end - pos));
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) ivf_scan_kernel(ScanParams p)
     }
     cp_async_wait<0>();
     sel.flush();
-    uint64_t* out = p.part_keys + (q * p.parts + part) * p.k;
+    uint64_t* out = p.part_keys + (q * slices + slice) * p.k;
     for (uint32_t j = lane; j < p.k; j += 32) out[j] = sel.buf[j];
 }
 

@@ -39,6 +39,8 @@ struct Params {
     const void* q_op;         // stacked query operand [a_pieces][nq_pad][kp] (TS mode loads it into TMEM)
     uint32_t kp;              // padded K in elements
     uint32_t* gtau;           // [nq_pad] shared pruning threshold per query (order-preserving image, atomicMin)
+    float* dense;             // DENSE mode: the selection values themselves, [nq][dense_ld] (IVF centroid ranking)
+    uint32_t dense_ld;
     float* dbg;               // optional: CTA (0,0) dumps v of its first tile [BM][BN]
     unsigned long long* dbg_cycles;  // optional: CTA (0,0) wait-cycle counters {total, prod_empty, mma_full, mma_tempty, epi_tfull, epi_slow}
 };

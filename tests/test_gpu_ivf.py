@@ -165,13 +165,19 @@ def test_fast_probe_path_and_overflow_fallback(gpu, dtype):
     g = _gpu_from_oracle(c)
     for k, nprobe in ((10, 8), (10, 40), (200, 1), (5, 1499)):     # (200, 1): needs ~50+ cells; may or may not overflow
         ref = o.ivf_search(c, q, k, nprobe=nprobe)
-        for fast in (2, 0):      # 2 = force the fused select regardless of the prefix length
+        for tc_coarse, fast in ((0, 2), (0, 0), (1, 1)):      # fast = 2: force the fused select regardless of the prefix length
+            g.set_option("ivf_tc_coarse", tc_coarse)
             g.set_option("ivf_fast_probe", fast)
-            _check(dtype, g.query_batch(q, k, nprobe=nprobe), ref, f"fast_probe={fast} k={k} nprobe={nprobe}")
+            _check(dtype, g.query_batch(q, k, nprobe=nprobe), ref, f"tc_coarse={tc_coarse} fast_probe={fast} k={k} nprobe={nprobe}")
             assert g.get_stat("scanned_vectors") == int(ref[4].sum())
+            if tc_coarse == 0:
+                assert g.get_stat("coarse_path") != 2
     ref = o.ivf_search(c, q, 600, nprobe=1)                        # certainly more than nprobe + 64 cells
-    g.set_option("ivf_fast_probe", 2)
-    _check(dtype, g.query_batch(q, 600, nprobe=1), ref, "overflow fallback")
+    for tc_coarse in (0, 1):
+        g.set_option("ivf_tc_coarse", tc_coarse)
+        g.set_option("ivf_fast_probe", 2)
+        _check(dtype, g.query_batch(q, 600, nprobe=1), ref, "overflow fallback")
+        assert g.get_stat("coarse_path") == 0
 
 
 def test_ivf_tensor_certificate_fallback(gpu):
@@ -189,3 +195,51 @@ def test_ivf_tensor_certificate_fallback(gpu):
     assert g.get_stat("scanned_vectors") == int(ref[4].sum())
     g.set_option("cert_eps_log2", -20)
     _check("f32", g.query_batch(q, 10, nprobe=6), ref, "ivf default bound")
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "sq8"])
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_tensor_core_centroid_ranking(gpu, dtype, metric):
+    """nlist >= 512: the centroid ranking runs on the tensor cores (dense 3xTF32 values -> radix select -> exact distances
+    of the candidates -> certified prefix).  The probe sets, and therefore the results and the scan statistics, must be
+    those of the exact ranking."""
+    data = datagen.gaussian_noise(30000, 32, seed=51)
+    q = datagen.subsample_with_noise(data, 300, seed=51)
+    c = o.build_ivf(data, MET[metric][1], nlist=700, dtype=DT[dtype][1], kmeans_iters=3)
+    g = _gpu_from_oracle(c)
+    for k, nprobe in ((10, 8), (10, 60), (24, 1)):
+        ref = o.ivf_search(c, q, k, nprobe=nprobe)
+        got = g.query_batch(q, k, nprobe=nprobe)
+        assert g.get_stat("coarse_path") == 2
+        _check(dtype, got, ref, f"tc coarse {dtype} {metric} k={k} nprobe={nprobe}")
+        assert g.get_stat("scanned_vectors") == int(ref[4].sum()) and g.get_stat("probed_lists") == int(ref[3].sum())
+    got = g.generate_knn(10, nprobe=12, pos_begin=100, pos_end=700)        # self queries: routing on decoded rows
+    assert g.get_stat("coarse_path") == 2
+    ref = o.ivf_search(c, None, 10, nprobe=12, self_rows=np.arange(100, 700), self_mode=True)
+    _check(dtype, got, ref, f"tc coarse self {dtype} {metric}")
+
+
+def test_tensor_core_centroid_ranking_ties_and_uncertifiable(gpu):
+    """Duplicate centroids tie exactly (broken by cell id, as the exact ranking does); a tie class larger than the
+    candidate capacity, or an error bound that certifies nothing, sends the batch to the exact ranking."""
+    rng = np.random.default_rng(5)
+    data = datagen.gaussian_noise(20000, 16, seed=61)
+    base = data[rng.choice(20000, 200, replace=False)]
+    cent = np.concatenate([base, base, base, base[:40]]).astype(np.float32)       # 640 cells, every centre 3-4 times
+    c = o.build_ivf(data, o.L2, nlist=640, centroids=cent)
+    g = _gpu_from_oracle(c)
+    q = datagen.subsample_with_noise(data, 200, seed=61)
+    ref = o.ivf_search(c, q, 10, nprobe=9)
+    _check("f32", g.query_batch(q, 10, nprobe=9), ref, "duplicate centroids")
+    assert g.get_stat("coarse_path") == 2
+    g.set_option("cert_eps_log2", -2)                 # nothing certifiable -> exact ranking, same answer
+    _check("f32", g.query_batch(q, 10, nprobe=9), ref, "uncertifiable ranking")
+    assert g.get_stat("coarse_path") != 2
+    g.set_option("cert_eps_log2", -20)
+    cent2 = np.concatenate([np.repeat(base[:1], 300, axis=0), base, base[:140]]).astype(np.float32)   # one centre 301 times
+    c2 = o.build_ivf(data, o.L2, nlist=640, centroids=cent2)
+    g2 = _gpu_from_oracle(c2)
+    q2 = (base[:1] + 0.01 * rng.standard_normal((40, 16))).astype(np.float32)
+    ref2 = o.ivf_search(c2, q2, 10, nprobe=9)
+    _check("f32", g2.query_batch(q2, 10, nprobe=9), ref2, "tie class beyond the candidate capacity")
+    assert g2.get_stat("coarse_path") != 2
