@@ -42,8 +42,8 @@ struct KernelTimer {
     annb_index* ix;
     cudaStream_t s;
     cudaEvent_t a = nullptr, b = nullptr;
-    KernelTimer(annb_index* ix_, cudaStream_t s_) : ix(ix_), s(s_) {
-        if (!ix->opt_time_kernels) return;
+    KernelTimer(annb_index* ix_, cudaStream_t s_, bool enable = true) : ix(ix_), s(s_) {
+        if (!ix->opt_time_kernels || !enable) return;
         if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { a = b = nullptr; (void)cudaGetLastError(); return; }
         cudaEventRecord(a, s);
     }
@@ -156,7 +156,7 @@ static int run_finalize(annb_index* ix, const uint64_t* keys, uint32_t parts, ui
     size_t smem = static_cast<size_t>(f.nsort) * 8;
     if (smem > 200 * 1024) return fail(ANNB_ERR_UNSUPPORTED, "finalize: parts * k too large");
     ANNB_CUDA_CHECK(cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    finalize_kernel<<<static_cast<uint32_t>(nq), 128, smem, s>>>(f);
+    finalize_kernel<<<static_cast<uint32_t>(nq), f.nsort >= 2048 ? 512 : 128, smem, s>>>(f);
     ANNB_CUDA_CHECK(cudaGetLastError());
     ix->stat_launches++;
     return ANNB_OK;
@@ -554,7 +554,7 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         size_t smem = scan_kernel_smem(ix->row_bytes, pq.scan_bytes, nsort);
         uint32_t grid = static_cast<uint32_t>(ceil_div<uint64_t>(nq * parts * subs, SCAN_WARPS));
         {
-            KernelTimer kt(ix, s);
+            KernelTimer kt(ix, s, preset_probes == nullptr);   // (the exact fallback of a tensor-path call is not the dominant kernel)
             ANNB_TRY(launch_scan(ix->dtype, pq.qt, ix->metric, sp, grid, smem, s));
         }
         ix->stat_launches++;

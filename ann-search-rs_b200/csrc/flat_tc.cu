@@ -356,20 +356,39 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(CoarseSelectParams p
     uint32_t* hist = vals + ((p.nlist + 31u) & ~31u);                    // [256]
     uint32_t* cand = hist + 256;                                          // [cmax]
     const float* src = p.dense + q * p.dense_ld;
-    for (uint32_t i = lane; i < p.nlist; i += 32) vals[i] = f32_to_ordered(src[i]);
+    uint32_t umin = 0xFFFFFFFFu, umax = 0u;
+    for (uint32_t i = lane; i < p.nlist; i += 32) {
+        const uint32_t u = f32_to_ordered(src[i]);
+        vals[i] = u;
+        umin = min(umin, u);
+        umax = max(umax, u);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        umin = min(umin, __shfl_xor_sync(0xFFFFFFFFu, umin, off));
+        umax = max(umax, __shfl_xor_sync(0xFFFFFFFFu, umax, off));
+    }
     __syncwarp();
 
-    // 1. pitch-th smallest value
+    // 1. threshold: radix select, most significant digit first, starting at the first bit in which the row's values
+    //    differ (the common high bits -- sign, exponent -- would put every value into one histogram bin).  It stops as
+    //    soon as the cells at or below the chosen bin number between pitch and cmax: all of them become candidates and
+    //    the bin's upper edge is the threshold.
     uint32_t thr = 0xFFFFFFFFu;
     const bool partial = p.pitch < p.nlist;
     if (partial) {
-        uint32_t prefix = 0, mask = 0, need = p.pitch;
-        for (int shift = 24; shift >= 0; shift -= 8) {
+        uint32_t rem = 32u - __clz(umin ^ umax);          // unresolved low bits (0: all values equal)
+        uint32_t prefix = rem >= 32u ? 0u : (umin >> rem) << rem;
+        uint32_t need = p.pitch, below = 0;
+        thr = prefix;                                      // rem == 0
+        while (rem > 0) {
+            const uint32_t w = min(8u, rem), sh = rem - w, dmask = (1u << w) - 1u;
+            const uint32_t hmask = rem >= 32u ? 0u : ~0u << rem;
             for (uint32_t b = lane; b < 256; b += 32) hist[b] = 0;
             __syncwarp();
             for (uint32_t i = lane; i < p.nlist; i += 32) {
                 const uint32_t u = vals[i];
-                if ((u & mask) == prefix) atomicAdd(hist + ((u >> shift) & 255u), 1u);
+                if ((u & hmask) == prefix) atomicAdd(hist + ((u >> sh) & dmask), 1u);
             }
             __syncwarp();
             uint32_t h[8], local = 0;
@@ -384,23 +403,28 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(CoarseSelectParams p
             const uint32_t excl = incl - local;
             const bool mine = excl < need && need <= incl;
             const int owner = __ffs(__ballot_sync(0xFFFFFFFFu, mine)) - 1;
-            uint32_t bin = 0, before = 0;
+            uint32_t bin = 0, before = 0, upto = 0;
             if (mine) {
                 uint32_t c = excl;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    if (need > c && need <= c + h[j]) { bin = 8 * lane + j; before = c; }
+                    if (need > c && need <= c + h[j]) { bin = 8 * lane + j; before = c; upto = c + h[j]; }
                     c += h[j];
                 }
             }
             bin = __shfl_sync(0xFFFFFFFFu, bin, owner);
             before = __shfl_sync(0xFFFFFFFFu, before, owner);
-            need -= before;
-            prefix |= bin << shift;
-            mask |= 255u << shift;
+            upto = __shfl_sync(0xFFFFFFFFu, upto, owner);
             __syncwarp();
+            if (below + upto <= p.cmax || sh == 0) {      // few enough cells at or below this bin (or nothing left to refine)
+                thr = prefix | (bin << sh) | ((sh ? (1u << sh) : 1u) - 1u);
+                break;
+            }
+            below += before;
+            need -= before;
+            prefix |= bin << sh;
+            rem = sh;
         }
-        thr = prefix;
     }
     // 2. candidates: every cell with value <= thr
     uint32_t count = 0;
@@ -745,7 +769,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     }
     // ---- exact re-rank + merge ----
     tc::RerankParams r{};
-    r.part_keys = st->part.as<uint64_t>(); r.parts = 2 * splits; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out;
+    r.part_keys = st->part.as<uint64_t>(); r.parts = 2 * splits; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out; r.gtau = st->gtau.as<uint32_t>();
     r.nsort = next_pow2(std::max(2 * splits * kprime, 64u));
     r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.row_norms_i = ix->d_norms_i; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
     r.bf16_self = bf16_self; r.id_base = ix->id_base; r.out_ids = d_ids; r.out_dist = d_dist; r.out_counts = d_cnt;

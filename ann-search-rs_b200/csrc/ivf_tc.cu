@@ -41,8 +41,15 @@ struct IvfTcParams {
     uint32_t* gtau;            // [nq] shared pruning threshold
 };
 
+// f32 lists: the kernel streams the index's own f32 rows (one 128 B K-slab per TMA load) and four extra "transform" warps
+// split every landed slab into tf32 hi (in place) and lo (second slab of the stage) before the MMA reads it -- the list is
+// read from HBM once per task at 4 B per element instead of 8 B from a pre-split copy, and no such copy is stored.
+constexpr int XF_THREADS = 128;
+template <int KIND> constexpr int ivf_tc_threads() { return KIND == KIND_TF32X3 ? NUM_THREADS + XF_THREADS : NUM_THREADS; }
+
 template <int KIND, int KP, int MET>
-__global__ void __launch_bounds__(NUM_THREADS, 1) ivf_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const IvfTcParams p) {
+__global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const IvfTcParams p) {
+    constexpr bool XFORM = (KIND == KIND_TF32X3);
     constexpr int NB = (KIND == KIND_TF32X3) ? 2 : 1;
     constexpr int ELEM = (KIND == KIND_TF32X3) ? 4 : (KIND == KIND_I8 ? 1 : 2);
     constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;
@@ -61,7 +68,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) ivf_tc_kernel(const __grid_con
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail);
     uint64_t* bar_full = bars;                     // [n_stages]
     uint64_t* bar_empty = bars + p.n_stages;       // [n_stages]
-    uint64_t* bar_q = bars + 2 * p.n_stages;       // [1]  queries of the current task are in TMEM
+    uint64_t* bar_xf = bars + 2 * p.n_stages;      // [n_stages] slab split into hi / lo (f32 lists)
+    uint64_t* bar_q = bars + 3 * p.n_stages;       // [1]  queries of the current task are in TMEM
     uint64_t* bar_tfull = bar_q + 1;               // [NACC]
     uint64_t* bar_tempty = bar_tfull + NACC;       // [NACC]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + NACC);
@@ -69,7 +77,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) ivf_tc_kernel(const __grid_con
     uint64_t* s_rows = reinterpret_cast<uint64_t*>(s_tmem + 6);  // [2]: r_begin, r_end (8-byte aligned: bars + ... even count)
 
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < p.n_stages; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+        for (uint32_t s = 0; s < p.n_stages; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); mbar_init(bar_xf + s, XF_THREADS); }
         mbar_init(bar_q, EPI_THREADS);
         for (int a = 0; a < NACC; a++) { mbar_init(bar_tfull + a, 1); mbar_init(bar_tempty + a, EPI_THREADS); }
         fence_barrier_init();
@@ -131,10 +139,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) ivf_tc_kernel(const __grid_con
                     for (uint32_t s = 0; s < p.nslab; s++, it++) {
                         const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
                         mbar_wait(bar_empty + stage, ph ^ 1u);
-                        mbar_expect_tx(bar_full + stage, NB * SLAB_TILE);
-                        for (int b = 0; b < NB; b++)
-                            tma_load_2d(smem_u32(s_x + (static_cast<size_t>(stage) * NB + b) * SLAB_TILE), &tm_x, bar_full + stage, s * SLAB_ELEMS,
-                                        b * p.n_pad + row0);
+                        if (XFORM) {   // raw f32 slab; rows past the shard's end are zero filled by TMA
+                            mbar_expect_tx(bar_full + stage, SLAB_TILE);
+                            tma_load_2d(smem_u32(s_x + static_cast<size_t>(stage) * NB * SLAB_TILE), &tm_x, bar_full + stage, s * SLAB_ELEMS, row0);
+                        } else {
+                            mbar_expect_tx(bar_full + stage, NB * SLAB_TILE);
+                            for (int b = 0; b < NB; b++)
+                                tma_load_2d(smem_u32(s_x + (static_cast<size_t>(stage) * NB + b) * SLAB_TILE), &tm_x, bar_full + stage, s * SLAB_ELEMS,
+                                            b * p.n_pad + row0);
+                        }
                     }
                 }
             } else {
@@ -153,7 +166,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) ivf_tc_kernel(const __grid_con
                 const uint32_t tmem_c = tmem_base + ACC_COL0 + acc * BN;
                 for (uint32_t s = 0; s < p.nslab; s++, it++) {
                     const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
-                    mbar_wait(bar_full + stage, ph);
+                    mbar_wait((XFORM ? bar_xf : bar_full) + stage, ph);
                     tc_fence_after();
                     const uint64_t xd = x_desc0 + static_cast<uint64_t>(stage * NB) * SLAB_DESC;
                     if (elect_one()) {
@@ -177,6 +190,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) ivf_tc_kernel(const __grid_con
                         if (s + 1 == p.nslab) umma_commit(bar_tfull + acc);
                     }
                     __syncwarp();
+                }
+            }
+        } else if (XFORM && warp >= 2 + EPI_THREADS / 32) {
+            // ================================================================= transform (4 warps): slab -> tf32 hi (in place) + lo
+            const uint32_t xt = threadIdx.x - (2 * 32 + EPI_THREADS);
+            for (uint32_t t = 0; t < n_tiles; t++) {
+                for (uint32_t s = 0; s < p.nslab; s++, it++) {
+                    const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
+                    mbar_wait(bar_full + stage, ph);
+                    uint8_t* raw = s_x + static_cast<size_t>(stage) * NB * SLAB_TILE;
+                    // elementwise, so the slab's swizzled layout carries over: thread i owns 16-byte chunks i, i + 128, ...
+#pragma unroll
+                    for (int j = 0; j < SLAB_TILE / 16 / XF_THREADS; j++) {
+                        const uint32_t off = (xt + XF_THREADS * j) * 16;
+                        const float4 x = *reinterpret_cast<const float4*>(raw + off);
+                        float4 h, l;
+                        h.x = rna_tf32(x.x); l.x = rna_tf32(__fsub_rn(x.x, h.x));
+                        h.y = rna_tf32(x.y); l.y = rna_tf32(__fsub_rn(x.y, h.y));
+                        h.z = rna_tf32(x.z); l.z = rna_tf32(__fsub_rn(x.z, h.z));
+                        h.w = rna_tf32(x.w); l.w = rna_tf32(__fsub_rn(x.w, h.w));
+                        *reinterpret_cast<float4*>(raw + off) = h;
+                        *reinterpret_cast<float4*>(raw + SLAB_TILE + off) = l;
+                    }
+                    fence_proxy_async();           // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                    mbar_arrive(bar_xf + stage);
                 }
             }
         } else {
@@ -380,34 +418,20 @@ int tc_ivf_prepare(annb_index* ix) {
     tc::aux_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(ix->d_rows, ix->row_bytes, kind, ix->dim, ix->d_norms, ix->d_norms_i,
                                                                                 ix->metric == ANNB_COSINE, ix->n, aux_rows, st->d_aux);
     ANNB_CUDA_CHECK(cudaGetLastError());
-    uint64_t xrows = 0;
-    if (kind == tc::KIND_TF32X3) {
-        const uint64_t bytes = 2ull * st->n_pad * kp * 4;
+    // Database operand: the index's own rows whenever their pitch is a whole number of 128-byte K slabs (dim % 32 == 0 for
+    // f32, % 64 for bf16, % 128 for SQ8) -- TMA zero-fills the rows past the end; otherwise a zero-padded copy.  f32 rows
+    // are split into tf32 hi / lo inside the kernel.
+    void* xbase = ix->d_rows;
+    if (ix->row_bytes != kp * elem) {
+        const uint64_t bytes = static_cast<uint64_t>(ix->n) * kp * elem;
         cudaError_t e = cudaMalloc(&st->d_x, bytes);
         if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
         st->bytes += bytes;
-        tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * kp), 256, 0, s>>>(reinterpret_cast<const float*>(ix->d_rows), ix->row_bytes / 4, ix->dim,
-                                                                                                   ix->n, st->n_pad, kp, static_cast<float*>(st->d_x));
-        xrows = 2ull * st->n_pad;
-    } else if (kind == tc::KIND_I8) {
-        const uint64_t bytes = static_cast<uint64_t>(st->n_pad) * kp;
-        cudaError_t e = cudaMalloc(&st->d_x, bytes);
-        if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
-        st->bytes += bytes;
-        tc::pad_i8_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * kp), 256, 0, s>>>(reinterpret_cast<const int8_t*>(ix->d_rows), ix->row_bytes, ix->dim, ix->n,
-                                                                                            st->n_pad, kp, static_cast<int8_t*>(st->d_x));
-        xrows = st->n_pad;
-    } else {
-        const uint64_t bytes = static_cast<uint64_t>(st->n_pad) * kp * 2;
-        cudaError_t e = cudaMalloc(&st->d_x, bytes);
-        if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
-        st->bytes += bytes;
-        tc::pad_bf16_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * kp), 256, 0, s>>>(reinterpret_cast<const uint16_t*>(ix->d_rows), ix->row_bytes / 2, ix->dim,
-                                                                                                 ix->n, st->n_pad, kp, static_cast<uint16_t*>(st->d_x));
-        xrows = st->n_pad;
+        pad_rows_kernel<<<tc_blocks_for(bytes), 256, 0, s>>>(ix->d_rows, ix->row_bytes, static_cast<uint8_t*>(st->d_x), kp * elem, ix->n);
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        xbase = st->d_x;
     }
-    ANNB_CUDA_CHECK(cudaGetLastError());
-    ANNB_TRY(tc_make_tmap(&st->tm_x, st->d_x, xrows, kp, elem));
+    ANNB_TRY(tc_make_tmap(&st->tm_x, xbase, ix->n, kp, elem));
     ANNB_TRY(tc_compute_xnorm_max(ix, st->d_aux, ix->n));
     ix->device_bytes += st->bytes;
     return ANNB_OK;
@@ -437,7 +461,7 @@ template <int KIND, int KP, int MET>
 static int launch_ivf_tc(const CUtensorMap& tmx, const tc::IvfTcParams& p, uint32_t grid, size_t smem, cudaStream_t s) {
     auto kern = tc::ivf_tc_kernel<KIND, KP, MET>;
     ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, tc::NUM_THREADS, smem, s>>>(tmx, p);
+    kern<<<grid, tc::ivf_tc_threads<KIND>(), smem, s>>>(tmx, p);
     ANNB_CUDA_CHECK(cudaGetLastError());
     return ANNB_OK;
 }
@@ -490,7 +514,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
         ix->stat_launches++;
     }
     tc::RerankParams r{};
-    r.part_keys = st->part.as<uint64_t>(); r.parts = probe_pitch * 2; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out;
+    r.part_keys = st->part.as<uint64_t>(); r.parts = probe_pitch * 2; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out; r.gtau = st->gtau.as<uint32_t>();
     r.nsort = next_pow2(std::max(probe_pitch * 2 * kprime, 64u));
     r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.row_norms_i = ix->d_norms_i; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
     r.bf16_self = 0; r.id_base = 0; r.parts_used = d_n_probes; r.part_mult = 2; r.id_map = ix->d_original_ids; r.row_map = row_map;

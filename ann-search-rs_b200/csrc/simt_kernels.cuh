@@ -675,7 +675,7 @@ struct FinalizeParams {
     uint32_t* out_counts;
 };
 
-__global__ void __launch_bounds__(128) finalize_kernel(FinalizeParams p) {
+__global__ void __launch_bounds__(512) finalize_kernel(FinalizeParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
     const uint64_t q = blockIdx.x;

@@ -339,6 +339,7 @@ struct RerankParams {
     float xnorm_max;             // L2: largest stored-row norm
     uint32_t* uncert_count;      // number of queries that could not be certified
     uint32_t* uncert_list;       // their indices (capacity nq)
+    const uint32_t* gtau;        // optional [nq]: final shared pruning threshold of the scan (ordered image); bounds the k'-th merged value
     uint64_t* out_ids;
     float* out_dist;
     uint32_t* out_counts;
@@ -356,9 +357,29 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     const uint32_t total = parts_q * p.kp;
     const uint32_t nsort = min(p.nsort, next_pow2(max(total, 64u)));
     const uint64_t* src = p.part_keys + q * (static_cast<uint64_t>(p.parts) * p.kp);
-    for (uint32_t i = threadIdx.x; i < nsort; i += blockDim.x) keys[i] = (i < total) ? src[i] : KEY_SENTINEL;
-    __syncthreads();
-    bitonic_sort_keys<true>(keys, nsort, threadIdx.x, blockDim.x);
+    if (p.gtau != nullptr) {
+        // Only keys at or below the query's shared pruning threshold can be among the k' best of the merged lists (the
+        // threshold is some single list's k'-th value): compact those -- typically a few dozen of the parts * k' slots --
+        // and sort just them.
+        __shared__ uint32_t s_n;
+        const uint32_t thr = p.gtau[q];
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
+            const uint64_t key = src[i];
+            if (key != KEY_SENTINEL && static_cast<uint32_t>(key >> 32) <= thr) keys[atomicAdd(&s_n, 1u)] = key;
+        }
+        __syncthreads();
+        const uint32_t n = s_n;
+        const uint32_t nsort2 = min(nsort, next_pow2(max(n, 64u)));
+        for (uint32_t i = n + threadIdx.x; i < nsort2; i += blockDim.x) keys[i] = KEY_SENTINEL;
+        __syncthreads();
+        bitonic_sort_keys<true>(keys, nsort2, threadIdx.x, blockDim.x);
+    } else {
+        for (uint32_t i = threadIdx.x; i < nsort; i += blockDim.x) keys[i] = (i < total) ? src[i] : KEY_SENTINEL;
+        __syncthreads();
+        bitonic_sort_keys<true>(keys, nsort, threadIdx.x, blockDim.x);
+    }
     const uint64_t orow = p.row_map ? p.row_map[q] : q;
     if (threadIdx.x < 64) {
         uint64_t ek = KEY_SENTINEL;
