@@ -1015,7 +1015,7 @@ int annb_debug_fetch_tile(annb_index* ix, float* host_out) {
     if (!ix || !host_out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
     DeviceGuard g(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
-    int rc = tc_debug_fetch(ix, host_out);
+    int rc = ix->is_ivf ? tc_ivf_debug_fetch(ix, host_out) : tc_debug_fetch(ix, host_out);
     if (rc != ANNB_OK && rc != ANNB_ERR_CUDA) set_last_error("tc_debug is not enabled on this index");
     return rc;
 }

@@ -114,8 +114,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         constexpr uint32_t SLAB_DESC = SLAB_TILE >> 4;    // descriptor start-address units (16 B) per slab
         mbar_wait(bar_q, 0);
         tc_fence_after();
-        const uint64_t q_desc0 = make_smem_desc(smem_u32(s_q));
-        const uint64_t x_desc0 = make_smem_desc(smem_u32(s_x));
+        const uint32_t q_desc0 = make_smem_desc(smem_u32(s_q));   // low descriptor words; the constant high word is added by umma()
+        const uint32_t x_desc0 = make_smem_desc(smem_u32(s_x));
         uint32_t it = 0;
         long long w_full = 0, w_tempty = 0;
         const long long t_start = clock64();
@@ -128,9 +128,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
                 mbar_wait_timed(bar_full + stage, ph, w_full);
                 tc_fence_after();
-                const uint64_t xd = x_desc0 + static_cast<uint64_t>(stage * NB) * SLAB_DESC;
-                const uint64_t qd = q_desc0 + static_cast<uint64_t>(s) * SLAB_DESC;
-                const uint64_t q_piece = static_cast<uint64_t>(p.nslab) * SLAB_DESC;
+                const uint32_t xd = x_desc0 + stage * NB * SLAB_DESC;
+                const uint32_t qd = q_desc0 + s * SLAB_DESC;
+                const uint32_t q_piece = p.nslab * SLAB_DESC;
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < KSTEPS; k++) {
@@ -239,9 +239,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             {
                 const int c = static_cast<int>(half);
                 uint32_t r[64];
-                tmem_ld32(taddr + c * 64, r);
-                tmem_ld32(taddr + c * 64 + 32, r + 32);
-                tmem_ld_wait();
+                tmem_ld64_sync(taddr + c * 64, r);
                 float v[64];
                 float gm[8];  // minima of the 8 groups of 8 columns
 #pragma unroll

@@ -33,6 +33,7 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
 // Test hooks: CTA (0,0) of the tensor kernel dumps the 128 x 128 values of its first tile.
 int tc_debug_enable(annb_index* ix, bool on);
 int tc_debug_fetch(annb_index* ix, float* host_out);
+int tc_ivf_debug_fetch(annb_index* ix, float* host_out);
 int tc_debug_cycles(annb_index* ix, unsigned long long* host_out8);
 
 }  // namespace annb

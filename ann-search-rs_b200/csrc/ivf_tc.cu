@@ -41,10 +41,11 @@ struct IvfTcParams {
     uint32_t* gtau;            // [nq] shared pruning threshold
 };
 
-// f32 lists: the kernel streams the index's own f32 rows (one 128 B K-slab per TMA load) and four extra "transform" warps
+// f32 lists: the kernel streams the index's own f32 rows (one 128 B K-slab per TMA load) and two extra "transform" warps
 // split every landed slab into tf32 hi (in place) and lo (second slab of the stage) before the MMA reads it -- the list is
 // read from HBM once per task at 4 B per element instead of 8 B from a pre-split copy, and no such copy is stored.
-constexpr int XF_THREADS = 128;
+// Warp roles: 0 TMA, 1 MMA, [2, 3 transform,] then the 8 epilogue warps.
+constexpr int XF_THREADS = 64;
 template <int KIND> constexpr int ivf_tc_threads() { return KIND == KIND_TF32X3 ? NUM_THREADS + XF_THREADS : NUM_THREADS; }
 
 template <int KIND, int KP, int MET>
@@ -99,7 +100,12 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     // epilogue-only state
     const uint32_t quarter = warp & 3u;
     const uint32_t row_in_tile = quarter * 32 + lane;
-    const uint32_t half = (warp >= 2) ? ((warp - 2) >> 2) : 0;
+#if defined(ANNB_XF_VARIANT) && ANNB_XF_VARIANT == 3
+    constexpr uint32_t EPI_WARP0 = 2;
+#else
+    constexpr uint32_t EPI_WARP0 = XFORM ? 2 + XF_THREADS / 32 : 2;
+#endif
+    const uint32_t half = (warp >= EPI_WARP0) ? ((warp - EPI_WARP0) >> 2) : 0;
     TopList<KP> top;
     float scratch[64];
 
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
             // ================================================================= MMA issuer (converged warp, elected issue)
             mbar_wait(bar_q, task_no & 1u);
             tc_fence_after();
-            const uint64_t x_desc0 = make_smem_desc(smem_u32(s_x));
+            const uint32_t x_desc0 = make_smem_desc(smem_u32(s_x));   // low descriptor word
             for (uint32_t t = 0; t < n_tiles; t++, tg++) {
                 const uint32_t acc = tg % NACC, aph = (tg / NACC) & 1u;
                 mbar_wait(bar_tempty + acc, aph ^ 1u);
@@ -168,7 +174,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                     const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
                     mbar_wait((XFORM ? bar_xf : bar_full) + stage, ph);
                     tc_fence_after();
-                    const uint64_t xd = x_desc0 + static_cast<uint64_t>(stage * NB) * SLAB_DESC;
+                    const uint32_t xd = x_desc0 + stage * NB * SLAB_DESC;
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < KSTEPS; k++) {
@@ -192,15 +198,20 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                     __syncwarp();
                 }
             }
-        } else if (XFORM && warp >= 2 + EPI_THREADS / 32) {
-            // ================================================================= transform (4 warps): slab -> tf32 hi (in place) + lo
-            const uint32_t xt = threadIdx.x - (2 * 32 + EPI_THREADS);
+#if defined(ANNB_XF_VARIANT) && ANNB_XF_VARIANT == 3
+        } else if (XFORM && warp >= 10) {
+            const uint32_t xt = threadIdx.x - 320;
+#else
+        } else if (XFORM && warp < EPI_WARP0) {
+            // ================================================================= transform (2 warps): slab -> tf32 hi (in place) + lo
+            const uint32_t xt = threadIdx.x - 2 * 32;
+#endif
             for (uint32_t t = 0; t < n_tiles; t++) {
                 for (uint32_t s = 0; s < p.nslab; s++, it++) {
                     const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
                     mbar_wait(bar_full + stage, ph);
                     uint8_t* raw = s_x + static_cast<size_t>(stage) * NB * SLAB_TILE;
-                    // elementwise, so the slab's swizzled layout carries over: thread i owns 16-byte chunks i, i + 128, ...
+                    // elementwise, so the slab's swizzled layout carries over: thread i owns 16-byte chunks i, i + 64, ...
 #pragma unroll
                     for (int j = 0; j < SLAB_TILE / 16 / XF_THREADS; j++) {
                         const uint32_t off = (xt + XF_THREADS * j) * 16;
@@ -210,9 +221,14 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                         h.y = rna_tf32(x.y); l.y = rna_tf32(__fsub_rn(x.y, h.y));
                         h.z = rna_tf32(x.z); l.z = rna_tf32(__fsub_rn(x.z, h.z));
                         h.w = rna_tf32(x.w); l.w = rna_tf32(__fsub_rn(x.w, h.w));
+#if !defined(ANNB_XF_VARIANT) || ANNB_XF_VARIANT != 1
                         *reinterpret_cast<float4*>(raw + off) = h;
+#endif
                         *reinterpret_cast<float4*>(raw + SLAB_TILE + off) = l;
                     }
+#if defined(ANNB_XF_VARIANT) && ANNB_XF_VARIANT == 2
+                    __threadfence_block();
+#endif
                     fence_proxy_async();           // generic-proxy writes -> visible to the tensor core's async-proxy reads
                     mbar_arrive(bar_xf + stage);
                 }
@@ -315,9 +331,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                 {
                     const int c = static_cast<int>(half);
                     uint32_t r[64];
-                    tmem_ld32(taddr + c * 64, r);
-                    tmem_ld32(taddr + c * 64 + 32, r + 32);
-                    tmem_ld_wait();
+                    tmem_ld64_sync(taddr + c * 64, r);
                     float v[64];
                     float gm[8];
 #pragma unroll
@@ -427,7 +441,7 @@ int tc_ivf_prepare(annb_index* ix) {
         cudaError_t e = cudaMalloc(&st->d_x, bytes);
         if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
         st->bytes += bytes;
-        pad_rows_kernel<<<tc_blocks_for(bytes), 256, 0, s>>>(ix->d_rows, ix->row_bytes, static_cast<uint8_t*>(st->d_x), kp * elem, ix->n);
+        tc::repitch_rows_kernel<<<tc_blocks_for(bytes), 256, 0, s>>>(ix->d_rows, ix->row_bytes, static_cast<uint8_t*>(st->d_x), kp * elem, ix->n);
         ANNB_CUDA_CHECK(cudaGetLastError());
         xbase = st->d_x;
     }
@@ -445,6 +459,13 @@ void tc_ivf_destroy(annb_index* ix) {
     ix->tc_ivf->gtau.release();
     delete ix->tc_ivf;
     ix->tc_ivf = nullptr;
+}
+
+// Test hook: the first 64 KiB of the per-(query, rank, half) candidate lists of the last scan (packed keys).
+int tc_ivf_debug_fetch(annb_index* ix, float* host_out) {
+    if (!ix->tc_ivf || !ix->tc_ivf->part.p) return ANNB_ERR_UNSUPPORTED;
+    ANNB_CUDA_CHECK(cudaMemcpy(host_out, ix->tc_ivf->part.p, std::min<size_t>(65536, ix->tc_ivf->part.cap), cudaMemcpyDeviceToHost));
+    return ANNB_OK;
 }
 
 bool tc_ivf_supported(const annb_index* ix, int qt, uint32_t k_eff) {
@@ -515,6 +536,9 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     }
     tc::RerankParams r{};
     r.part_keys = st->part.as<uint64_t>(); r.parts = probe_pitch * 2; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out; r.gtau = st->gtau.as<uint32_t>();
+#if defined(ANNB_XF_VARIANT) && ANNB_XF_VARIANT == 4
+    r.gtau = nullptr;
+#endif
     r.nsort = next_pow2(std::max(probe_pitch * 2 * kprime, 64u));
     r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.row_norms_i = ix->d_norms_i; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
     r.bf16_self = 0; r.id_base = 0; r.parts_used = d_n_probes; r.part_mult = 2; r.id_map = ix->d_original_ids; r.row_map = row_map;

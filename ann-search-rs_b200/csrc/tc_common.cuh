@@ -109,21 +109,23 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+constexpr uint32_t SMEM_DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);   // 0x40004040
+// The 64-bit shared-memory descriptors are handed to the instruction as {low word, high word} pairs assembled inside the
+// asm statement.  Their high word is a compile-time constant (SBO, version, swizzle mode); when it reached ptxas as part
+// of a 64-bit add with a wide immediate, ptxas 12.9 was seen to drop it on the uniform datapath (the descriptor's high
+// word then held an unrelated kernel parameter) -- keeping the halves separate 32-bit values rules that out.
+#define ANNB_UMMA_SS(KINDSTR)                                                                                                          \
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\tsetp.ne.b32 p, %6, 0;\n\t" \
+                 "tcgen05.mma.cta_group::1.kind::" KINDSTR " [%0], da, db, %5, p;\n\t}" ::"r"(tmem_c),                                  \
+                 "r"(adesc), "r"(SMEM_DESC_HI), "r"(bdesc), "r"(SMEM_DESC_HI), "r"(idesc), "r"(accumulate)                                \
+                 : "memory")
 template <int KIND>
-__device__ __forceinline__ void umma(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (KIND == KIND_TF32X3)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
-                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-                     : "memory");
-    else if (KIND == KIND_I8)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
-                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-                     : "memory");
-    else
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
-                     "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-                     : "memory");
+__device__ __forceinline__ void umma(uint32_t tmem_c, uint32_t adesc, uint32_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == KIND_TF32X3) ANNB_UMMA_SS("tf32");
+    else if (KIND == KIND_I8) ANNB_UMMA_SS("i8");
+    else ANNB_UMMA_SS("f16");
 }
+#undef ANNB_UMMA_SS
 // 32 lanes x 32 columns of 32-bit accumulators: thread i of the warp receives columns [c, c+32) of TMEM lane base+i.
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
     asm volatile(
@@ -136,26 +138,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
         : "r"(taddr)
         : "memory");
 }
-// A operand from TMEM (row m of A = TMEM lane m, K along columns), B from shared memory.
-template <int KIND>
-__device__ __forceinline__ void umma_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (KIND == KIND_TF32X3)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_c),
-                     "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-                     : "memory");
-    else if (KIND == KIND_I8)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_c),
-                     "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-                     : "memory");
-    else
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_c),
-                     "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-                     : "memory");
+// 64 consecutive columns of this warp's 32 lanes, *completed*: both loads and the tcgen05.wait::ld sit in one asm statement,
+// so the compiler cannot move, copy or spill the destination registers while the asynchronous loads are still in flight
+// (with separate statements it may, under register pressure, and the late-arriving data then lands in re-used registers).
+__device__ __forceinline__ void tmem_ld64_sync(uint32_t taddr, uint32_t r[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr), "r"(taddr + 32)
+        : "memory");
 }
+// A operand from TMEM (row m of A = TMEM lane m, K along columns), B from shared memory.
+#define ANNB_UMMA_TS(KINDSTR)                                                                                                          \
+    asm volatile("{\n\t.reg .pred p;\n\t.reg .b64 db;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"                           \
+                 "tcgen05.mma.cta_group::1.kind::" KINDSTR " [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_c),                                \
+                 "r"(tmem_a), "r"(bdesc), "r"(SMEM_DESC_HI), "r"(idesc), "r"(accumulate)                                                \
+                 : "memory")
+template <int KIND>
+__device__ __forceinline__ void umma_ts(uint32_t tmem_c, uint32_t tmem_a, uint32_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == KIND_TF32X3) ANNB_UMMA_TS("tf32");
+    else if (KIND == KIND_I8) ANNB_UMMA_TS("i8");
+    else ANNB_UMMA_TS("f16");
+}
+#undef ANNB_UMMA_TS
+// Store + wait in one asm statement: the store is asynchronous, so its source registers must stay untouched until
+// tcgen05.wait::st -- with separate statements the compiler is free to re-use them in between.
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t r[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, "
-        "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "%22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n\t"
+        "tcgen05.wait::st.sync.aligned;" ::"r"(taddr),
         "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
         "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]),
         "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
@@ -165,13 +179,10 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor: K-major operand tile, 128-byte swizzle, rows 128 B apart, 8-row groups 1024 B apart.
-// (field layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    return static_cast<uint64_t>((saddr >> 4) & 0x3FFFu) | (1ull << 16)  // LBO (unused for swizzled K-major)
-           | (static_cast<uint64_t>(1024 >> 4) << 32)                    // SBO = 1024 B
-           | (1ull << 46)                                                // descriptor version (Blackwell)
-           | (2ull << 61);                                               // SWIZZLE_128B
-}
+// (field layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor).  Kept as two 32-bit words: the low word carries the start
+// address (>> 4, 14 bits -- all descriptor arithmetic in the kernels is on this word) and the LBO field, the high word is
+// the constant {SBO = 1024 B, descriptor version 1, SWIZZLE_128B}.
+__device__ __forceinline__ uint32_t make_smem_desc(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 // UMMA instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): f32 accumulate, K-major A and B.
 __host__ __device__ constexpr uint32_t make_idesc(int kind) {
     const uint32_t fmt = (kind == KIND_TF32X3) ? 2u : 1u;  // TF32 = 2, BF16 = 1, signed INT8 = 1 (S8Format)
@@ -302,6 +313,15 @@ static __global__ void aux_kernel(const uint8_t* __restrict__ rows, uint32_t row
         }
     }
     aux[i] = o;
+}
+// rows of src_bytes -> rows of dst_bytes (>= src_bytes), zero padded
+static __global__ void repitch_rows_kernel(const uint8_t* __restrict__ src, uint32_t src_bytes, uint8_t* __restrict__ dst, uint32_t dst_bytes, uint64_t n) {
+    const uint64_t total = n * dst_bytes;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t r = i / dst_bytes;
+        const uint32_t c = static_cast<uint32_t>(i - r * dst_bytes);
+        dst[i] = c < src_bytes ? src[r * src_bytes + c] : 0;
+    }
 }
 // int8 codes (pitch ld_src bytes) -> [rows_pad][kp] zero padded (database operand / encoded queries of the SQ8 index).
 static __global__ void pad_i8_kernel(const int8_t* __restrict__ src, uint32_t ld_src, uint32_t dim, uint64_t rows, uint64_t rows_pad, uint32_t kp,

@@ -25,7 +25,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libannb200.so"))
+LIB_PATH = os.environ.get("ANNB200_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libannb200.so"))   # override: debugging builds
 
 F32, BF16, SQ8 = 0, 1, 2
 L2, COSINE, MANHATTAN = 0, 1, 2
