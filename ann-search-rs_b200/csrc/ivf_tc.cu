@@ -100,11 +100,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     // epilogue-only state
     const uint32_t quarter = warp & 3u;
     const uint32_t row_in_tile = quarter * 32 + lane;
-#if defined(ANNB_XF_VARIANT) && ANNB_XF_VARIANT == 3
-    constexpr uint32_t EPI_WARP0 = 2;
-#else
     constexpr uint32_t EPI_WARP0 = XFORM ? 2 + XF_THREADS / 32 : 2;
-#endif
     const uint32_t half = (warp >= EPI_WARP0) ? ((warp - EPI_WARP0) >> 2) : 0;
     TopList<KP> top;
     float scratch[64];
@@ -198,14 +194,9 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                     __syncwarp();
                 }
             }
-#if defined(ANNB_XF_VARIANT) && ANNB_XF_VARIANT == 3
-        } else if (XFORM && warp >= 10) {
-            const uint32_t xt = threadIdx.x - 320;
-#else
         } else if (XFORM && warp < EPI_WARP0) {
-            // ================================================================= transform (2 warps): slab -> tf32 hi (in place) + lo
+            // ================================================================= transform (2 warps): slab -> tf32 lo tile (hi = the raw slab)
             const uint32_t xt = threadIdx.x - 2 * 32;
-#endif
             for (uint32_t t = 0; t < n_tiles; t++) {
                 for (uint32_t s = 0; s < p.nslab; s++, it++) {
                     const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
@@ -215,20 +206,17 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
 #pragma unroll
                     for (int j = 0; j < SLAB_TILE / 16 / XF_THREADS; j++) {
                         const uint32_t off = (xt + XF_THREADS * j) * 16;
-                        const float4 x = *reinterpret_cast<const float4*>(raw + off);
-                        float4 h, l;
-                        h.x = rna_tf32(x.x); l.x = rna_tf32(__fsub_rn(x.x, h.x));
-                        h.y = rna_tf32(x.y); l.y = rna_tf32(__fsub_rn(x.y, h.y));
-                        h.z = rna_tf32(x.z); l.z = rna_tf32(__fsub_rn(x.z, h.z));
-                        h.w = rna_tf32(x.w); l.w = rna_tf32(__fsub_rn(x.w, h.w));
-#if !defined(ANNB_XF_VARIANT) || ANNB_XF_VARIANT != 1
-                        *reinterpret_cast<float4*>(raw + off) = h;
-#endif
-                        *reinterpret_cast<float4*>(raw + SLAB_TILE + off) = l;
+                        // hi needs no work: the tensor core reads only the upper 19 bits of a tf32 operand, i.e. it truncates x in
+                        // place.  lo = x - trunc(x) is exact in f32 (<= 13 significant bits); adding half a tf32 ulp to its bit
+                        // pattern makes the hardware's truncation round it to nearest.  |lo| < 2^-10 |x|, error <= 2^-21 |x|.
+                        const uint4 x = *reinterpret_cast<const uint4*>(raw + off);
+                        uint4 l;
+                        l.x = __float_as_uint(__fsub_rn(__uint_as_float(x.x), __uint_as_float(x.x & 0xFFFFE000u))) + 0x1000u;
+                        l.y = __float_as_uint(__fsub_rn(__uint_as_float(x.y), __uint_as_float(x.y & 0xFFFFE000u))) + 0x1000u;
+                        l.z = __float_as_uint(__fsub_rn(__uint_as_float(x.z), __uint_as_float(x.z & 0xFFFFE000u))) + 0x1000u;
+                        l.w = __float_as_uint(__fsub_rn(__uint_as_float(x.w), __uint_as_float(x.w & 0xFFFFE000u))) + 0x1000u;
+                        *reinterpret_cast<uint4*>(raw + SLAB_TILE + off) = l;
                     }
-#if defined(ANNB_XF_VARIANT) && ANNB_XF_VARIANT == 2
-                    __threadfence_block();
-#endif
                     fence_proxy_async();           // generic-proxy writes -> visible to the tensor core's async-proxy reads
                     mbar_arrive(bar_xf + stage);
                 }
@@ -237,6 +225,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
             // ================================================================= epilogue (8 warps)
             const uint2 pr = (row_in_tile < n_in_group) ? p.pairs[pair0 + row_in_tile] : make_uint2(0xFFFFFFFFu, 0u);
             const bool has_query = pr.x != 0xFFFFFFFFu;
+            const bool warp_has_query = __any_sync(0xFFFFFFFFu, has_query);   // groups are filled from row 0: whole warps may be idle
             // ---- gather this lane's query, split it, store it into TMEM ----
             {
                 const float* qrow = reinterpret_cast<const float*>(p.queries + static_cast<uint64_t>(has_query ? pr.x : 0) * p.q_bytes);
@@ -328,7 +317,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                 const float g_tau = has_query ? ordered_to_f32(g_bits) : -INFINITY;   // lanes without a query never select
                 float tau = fminf(top.tau(), g_tau);
                 const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + ACC_COL0 + acc * BN;
-                {
+                if (warp_has_query) {
                     const int c = static_cast<int>(half);
                     uint32_t r[64];
                     tmem_ld64_sync(taddr + c * 64, r);
@@ -536,9 +525,6 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     }
     tc::RerankParams r{};
     r.part_keys = st->part.as<uint64_t>(); r.parts = probe_pitch * 2; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out; r.gtau = st->gtau.as<uint32_t>();
-#if defined(ANNB_XF_VARIANT) && ANNB_XF_VARIANT == 4
-    r.gtau = nullptr;
-#endif
     r.nsort = next_pow2(std::max(probe_pitch * 2 * kprime, 64u));
     r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.row_norms_i = ix->d_norms_i; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
     r.bf16_self = 0; r.id_base = 0; r.parts_used = d_n_probes; r.part_mult = 2; r.id_map = ix->d_original_ids; r.row_map = row_map;
