@@ -1000,7 +1000,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "tc_ts") ix->opt_tc_ts = static_cast<int>(value);
     else if (k == "cert_fallback") ix->opt_cert_fallback = static_cast<int>(value);
     else if (k == "cert_eps_log2") ix->opt_cert_eps = value == 0 ? 0.f : std::ldexp(1.0f, static_cast<int>(value));   // e.g. -18; 0 switches the certificate off
-    else if (k == "tc_debug") { DeviceGuard g(ix->device); return tc_debug_enable(ix, value != 0); }
+    else if (k == "tc_debug") { DeviceGuard g(ix->device); return ix->is_ivf ? tc_ivf_debug_enable(ix, value != 0) : tc_debug_enable(ix, value != 0); }
     else if (k == "db_splits") ix->opt_db_splits = static_cast<int>(value);
     else if (k == "scan_parts") ix->opt_scan_parts = static_cast<int>(value);
     else if (k == "ivf_list_major") ix->opt_ivf_list_major = static_cast<int>(value);
@@ -1024,7 +1024,7 @@ int annb_debug_fetch_cycles(annb_index* ix, uint64_t* host_out8) {
     if (!ix || !host_out8) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
     DeviceGuard g(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
-    int rc = tc_debug_cycles(ix, reinterpret_cast<unsigned long long*>(host_out8));
+    int rc = ix->is_ivf ? tc_ivf_debug_cycles(ix, reinterpret_cast<unsigned long long*>(host_out8)) : tc_debug_cycles(ix, reinterpret_cast<unsigned long long*>(host_out8));
     if (rc != ANNB_OK && rc != ANNB_ERR_CUDA) set_last_error("tc_debug is not enabled on this index");
     return rc;
 }

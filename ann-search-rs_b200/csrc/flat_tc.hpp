@@ -34,6 +34,8 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
 int tc_debug_enable(annb_index* ix, bool on);
 int tc_debug_fetch(annb_index* ix, float* host_out);
 int tc_ivf_debug_fetch(annb_index* ix, float* host_out);
+int tc_ivf_debug_enable(annb_index* ix, bool on);
+int tc_ivf_debug_cycles(annb_index* ix, unsigned long long* host_out8);
 int tc_debug_cycles(annb_index* ix, unsigned long long* host_out8);
 
 }  // namespace annb

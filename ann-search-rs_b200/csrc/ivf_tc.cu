@@ -39,6 +39,7 @@ struct IvfTcParams {
     uint32_t probe_pitch;
     uint64_t* part_keys;       // [nq][probe_pitch][2][KP]
     uint32_t* gtau;            // [nq] shared pruning threshold
+    unsigned long long* dbg;   // optional [8]: CTA 0 cycle counters {total, schedule, gather, epi wait-tfull, mma wait-queries, mma wait-data, mma wait-tempty, tasks << 32 | tiles}
 };
 
 // f32 lists: the kernel streams the index's own f32 rows (one 128 B K-slab per TMA load) and two extra "transform" warps
@@ -105,8 +106,12 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     TopList<KP> top;
     float scratch[64];
 
+    const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
+    long long c_sched = 0, c_gather = 0, c_tfull = 0, c_wq = 0, c_wdata = 0, c_wtempty = 0, c_tasks = 0, c_tiles = 0;
+    const long long c_start = clock64();
     for (;;) {
         __syncthreads();   // every role has finished the previous task (TMEM query region and s_task are reusable)
+        const long long c_t0 = clock64();
         if (threadIdx.x == 0) {
             const uint32_t task = atomicAdd(p.task_counter, 1u);
             if (task < total_tasks) {
@@ -129,6 +134,8 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
         }
         __syncthreads();
         if (s_task[3] == 0) break;
+        const long long c_t1 = clock64();
+        c_sched += c_t1 - c_t0;
         const uint32_t pair0 = s_task[1], n_in_group = s_task[2];
         const uint64_t r_begin = s_rows[0], r_end = s_rows[1];
         const uint32_t n_tiles = static_cast<uint32_t>((r_end - r_begin + BN - 1) / BN);
@@ -158,17 +165,17 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
             __syncwarp();
         } else if (warp == 1) {
             // ================================================================= MMA issuer (converged warp, elected issue)
-            mbar_wait(bar_q, task_no & 1u);
+            mbar_wait_timed(bar_q, task_no & 1u, c_wq);
             tc_fence_after();
             const uint32_t x_desc0 = make_smem_desc(smem_u32(s_x));   // low descriptor word
             for (uint32_t t = 0; t < n_tiles; t++, tg++) {
                 const uint32_t acc = tg % NACC, aph = (tg / NACC) & 1u;
-                mbar_wait(bar_tempty + acc, aph ^ 1u);
+                mbar_wait_timed(bar_tempty + acc, aph ^ 1u, c_wtempty);
                 tc_fence_after();
                 const uint32_t tmem_c = tmem_base + ACC_COL0 + acc * BN;
                 for (uint32_t s = 0; s < p.nslab; s++, it++) {
                     const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
-                    mbar_wait((XFORM ? bar_xf : bar_full) + stage, ph);
+                    mbar_wait_timed((XFORM ? bar_xf : bar_full) + stage, ph, c_wdata);
                     tc_fence_after();
                     const uint32_t xd = x_desc0 + stage * NB * SLAB_DESC;
                     if (elect_one()) {
@@ -291,6 +298,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(bar_q);
+                c_gather += clock64() - c_t1;
             }
             top.init();
             uint32_t* gtau_ptr = p.gtau + (has_query ? pr.x : 0);
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                     load_aux(t + 1, aux_lo_next, aux_hi_next);
                     if (has_query) g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
                 }
-                mbar_wait(bar_tfull + acc, aph);
+                mbar_wait_timed(bar_tfull + acc, aph, c_tfull);
                 tc_fence_after();
                 const float g_tau = has_query ? ordered_to_f32(g_bits) : -INFINITY;   // lanes without a query never select
                 float tau = fminf(top.tau(), g_tau);
@@ -370,6 +378,13 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
             }
         }
         task_no++;
+        c_tasks++;
+        c_tiles += n_tiles;
+    }
+    if (dbg_on) {
+        if (threadIdx.x == 0) { p.dbg[0] = clock64() - c_start; p.dbg[1] = c_sched; p.dbg[7] = (static_cast<unsigned long long>(c_tasks) << 32) | static_cast<unsigned long long>(c_tiles); }
+        if (threadIdx.x == 32) { p.dbg[4] = c_wq; p.dbg[5] = c_wdata; p.dbg[6] = c_wtempty; }
+        if (threadIdx.x == EPI_WARP0 * 32) { p.dbg[2] = c_gather; p.dbg[3] = c_tfull; }
     }
     tc_fence_before();
     __syncthreads();
@@ -378,6 +393,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
+
 
 }  // namespace tc
 
@@ -393,7 +409,7 @@ struct IvfTcState {
     void* d_x = nullptr;
     float* d_aux = nullptr;
     CUtensorMap tm_x;
-    DevBuf part, gtau;
+    DevBuf part, gtau, dbgc;
     uint64_t bytes = 0;
 };
 
@@ -446,10 +462,24 @@ void tc_ivf_destroy(annb_index* ix) {
     cudaFree(ix->tc_ivf->d_aux);
     ix->tc_ivf->part.release();
     ix->tc_ivf->gtau.release();
+    ix->tc_ivf->dbgc.release();
     delete ix->tc_ivf;
     ix->tc_ivf = nullptr;
 }
 
+// Test hooks: role wait-cycle counters of CTA 0 of the scan kernel.
+int tc_ivf_debug_enable(annb_index* ix, bool on) {
+    if (!ix->tc_ivf) return ANNB_ERR_UNSUPPORTED;
+    if (!on) { ix->tc_ivf->dbgc.release(); return ANNB_OK; }
+    ANNB_TRY(ix->tc_ivf->dbgc.ensure(64));
+    ANNB_CUDA_CHECK(cudaMemset(ix->tc_ivf->dbgc.p, 0, 64));
+    return ANNB_OK;
+}
+int tc_ivf_debug_cycles(annb_index* ix, unsigned long long* host_out8) {
+    if (!ix->tc_ivf || !ix->tc_ivf->dbgc.p) return ANNB_ERR_UNSUPPORTED;
+    ANNB_CUDA_CHECK(cudaMemcpy(host_out8, ix->tc_ivf->dbgc.p, 64, cudaMemcpyDeviceToHost));
+    return ANNB_OK;
+}
 // Test hook: the first 64 KiB of the per-(query, rank, half) candidate lists of the last scan (packed keys).
 int tc_ivf_debug_fetch(annb_index* ix, float* host_out) {
     if (!ix->tc_ivf || !ix->tc_ivf->part.p) return ANNB_ERR_UNSUPPORTED;
@@ -503,13 +533,13 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     ANNB_CUDA_CHECK(cudaMemsetAsync(st->part.p, 0xFF, slots * kprime * 8, s));
     ANNB_TRY(st->gtau.ensure(nq * 4 + 16));
     ANNB_CUDA_CHECK(cudaMemsetAsync(st->gtau.p, 0xFF, nq * 4 + 16, s));
+    const bool l2 = ix->metric == ANNB_L2;
     tc::IvfTcParams p{};
     p.queries = d_q; p.q_bytes = q_bytes; p.dim = ix->dim; p.nslab = st->nslab; p.n_stages = stages; p.n_pad = st->n_pad; p.aux = st->d_aux;
     p.offsets = ix->d_offsets; p.shard_row0 = ix->shard_row0; p.nlist = ix->nlist; p.pair_off = d_pair_off; p.task_off = d_task_off;
     p.pairs = static_cast<const uint2*>(d_pairs); p.task_counter = d_task_counter; p.probe_pitch = probe_pitch;
-    p.part_keys = st->part.as<uint64_t>(); p.gtau = st->gtau.as<uint32_t>();
+    p.part_keys = st->part.as<uint64_t>(); p.gtau = st->gtau.as<uint32_t>(); p.dbg = st->dbgc.as<unsigned long long>();
     const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(max_tasks, 1), 148));
-    const bool l2 = ix->metric == ANNB_L2;
     {
         cudaEvent_t ea = nullptr, eb = nullptr;
         if (ix->opt_time_kernels && cudaEventCreate(&ea) == cudaSuccess && cudaEventCreate(&eb) == cudaSuccess) cudaEventRecord(ea, s);

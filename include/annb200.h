@@ -19,6 +19,9 @@
  *     memory, or device memory (resolved through UVA);
  *   - `_dev` entry points take device pointers and a cudaStream_t (as void*)
  *     and are asynchronous with respect to the host;
+ *   - the create / host-buffer entry points copy on a private non-blocking
+ *     stream: device buffers passed to them must be complete (no kernel of
+ *     the caller still writing them) when the call is made;
  *   - results: `out_ids` is [nq * k] uint64, `out_dist` is [nq * k] float
  *     (may be NULL = return_dist false), `out_counts` [nq] uint32 (may be NULL).
  *     Row i holds counts[i] = min(k, reachable) valid entries in ascending

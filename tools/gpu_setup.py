@@ -78,6 +78,7 @@ def subsample_with_noise_gpu(data, nq, seed=42):
 
 
 def _flat_handle_from_device(t, metric, dtype, device_index, id_base=0):
+    torch.cuda.synchronize(t.device)      # the library copies on its own stream: the tensor must be complete
     h = C.c_void_p()
     annb200._check(annb200.lib().annb_flat_create(C.byref(h), C.c_void_p(t.data_ptr()), t.shape[0], t.shape[1], dtype, metric, None, id_base, device_index))
     return annb200.ExhaustiveIndexB200(h)
@@ -152,6 +153,7 @@ def ivf_handle_from_parts(parts, n_total, dim, dtype, metric, device_index, list
     oid = parts["original_ids"][r0:r1]
     cent = parts["centroids"].contiguous()
     sc = parts["scales"]
+    torch.cuda.synchronize(vec.device)    # the library copies on its own stream: the tensors must be complete
     h = C.c_void_p()
     annb200._check(lib.annb_ivf_create(C.byref(h), C.c_void_p(vec.data_ptr()), None, C.c_void_p(cent.data_ptr()), None,
                                        C.c_void_p(off.ctypes.data), C.c_void_p(oid.data_ptr()), n_total, dim, nlist, dtype, metric,
