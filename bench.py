@@ -390,10 +390,15 @@ def run_b200(args):
             pipe_peak = peaks["bf16_tflops"] / 2.0               # TF32 pipe: measured bf16 / 2
             peak = pipe_peak / 3.0                               # BASELINE.md's f32 row: algorithmic flops executed 3x on the TF32 pipe
             peak_note = f"{peak_src} bf16 burst peak / 2 (TF32 pipe) / 3 (3xTF32 terms), as BASELINE.md section 2"
-        else:
+        elif args.dtype == "bf16":
             pipe_peak = peaks["bf16_tflops"]
             peak = pipe_peak                                     # BASELINE.md's bf16 row: one bf16 MMA per element
             peak_note = f"{peak_src} bf16 burst peak (the f32 query is fed as 3 bf16 terms, see 'executed')"
+        else:
+            mma_per_elem = 1                                     # int8 codes x int8 codes, s32 accumulate: one exact term
+            pipe_peak = peaks["bf16_tflops"] * 2.0               # no measured int8 peak on this pool: nominal 2x the bf16 rate
+            peak = pipe_peak
+            peak_note = f"2 x {peak_src} bf16 burst peak (nominal int8:bf16 ratio; the int8 pipe is not measured separately)"
         if last_path != 2:
             mma_per_elem = 0
         achieved = flops / dom_s / 1e12
@@ -405,13 +410,34 @@ def run_b200(args):
     else:
         esz = {"f32": 4, "bf16": 2, "sq8": 1}[args.dtype]
         per_vec = dim * esz + (4 if args.metric == "cosine" else 0)
-        algo_bytes = scanned * per_vec / max(1, 1)               # sum over queries of probed list bytes, last step
-        achieved = algo_bytes / dom_s / 1e9
-        peak = peaks["hbm_gbs"]
-        roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "kernel": "ivf list scan", "kernel_ms": dom_s * 1e3, "peak_source": f"{peak_src} copy bandwidth",
-                    "algorithmic_bytes_per_launch": algo_bytes}
+        algo_bytes = scanned * per_vec                           # sum over queries of probed list bytes, last step
         algo_bytes_per_query = algo_bytes / nq
+        hbm = {"algorithmic_bytes_per_launch": algo_bytes, "algorithmic_gbs": algo_bytes / dom_s / 1e9, "peak_gbs": peaks["hbm_gbs"]}
+        if last_path == 2:
+            # tensor-core grouped scan: one list load serves up to 128 queries, so the per-query byte count is not what the
+            # kernel moves (algorithmic GB/s exceeds the HBM peak by design); the kernel is a grouped GEMM and is
+            # bounded by the tensor pipe + its select epilogue.  HBM view: measured dram bytes from the ncu capture, if any.
+            flops = 2.0 * scanned * dim
+            if args.dtype == "f32":
+                pipe_peak, terms = peaks["bf16_tflops"] / 2.0, 3
+            elif args.dtype == "bf16":
+                pipe_peak, terms = peaks["bf16_tflops"], 3
+            else:
+                pipe_peak, terms = peaks["bf16_tflops"] * 2.0, 1
+            peak = pipe_peak / (3.0 if args.dtype == "f32" else 1.0)
+            achieved = flops / dom_s / 1e12
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                        "kernel": "ivf grouped list scan (tcgen05) + top-k' select", "kernel_ms": dom_s * 1e3,
+                        "peak_source": f"{peak_src} bf16 burst peak scaled as for the flat kernel ({args.dtype})",
+                        "algorithmic_flops_per_launch": flops,
+                        "executed": {"mma_terms_per_element": terms, "note": "padded (list x 128-query group) tiles execute more MMA work than the algorithmic count"},
+                        "hbm_view": hbm, "path": "tensor (tcgen05)"}
+        else:
+            achieved = algo_bytes / dom_s / 1e9
+            peak = peaks["hbm_gbs"]
+            roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                        "kernel": "ivf list scan (CUDA cores)", "kernel_ms": dom_s * 1e3, "peak_source": f"{peak_src} copy bandwidth",
+                        "algorithmic_bytes_per_launch": algo_bytes, "path": "simt (CUDA cores)"}
 
     # DRAM traffic of the dominant kernel: from the committed ncu capture of this exact workload, if there is one
     try:
@@ -421,6 +447,9 @@ def run_b200(args):
         if key in tr and world == 1:
             roofline["traffic"] = tr[key]["dram_bytes"]
             roofline["traffic_source"] = tr[key]["source"]
+            if "hbm_view" in roofline:
+                roofline["hbm_view"]["dram_gbs_from_traffic"] = tr[key]["dram_bytes"] / dom_s / 1e9
+                roofline["hbm_view"]["frac_of_hbm_peak"] = tr[key]["dram_bytes"] / dom_s / 1e9 / peaks["hbm_gbs"]
     except Exception:
         pass
     line = {"metric": metric_name(args), "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
