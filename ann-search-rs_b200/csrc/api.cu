@@ -361,6 +361,7 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
             pp.overflow = ix->s_flags.as<uint32_t>();
             pp.stat_scanned = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 8);
             pp.stat_probed = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 16);
+            pp.list_begin = ix->list_begin; pp.list_end = ix->list_end;
             probe_walk_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 128)), 128, 0, s>>>(ix->s_cdist.as<uint64_t>(), pp);
             ANNB_CUDA_CHECK(cudaGetLastError());
             ix->stat_launches++;
@@ -393,6 +394,7 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
             pp.overflow = ix->s_flags.as<uint32_t>();
             pp.stat_scanned = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 8);
             pp.stat_probed = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 16);
+            pp.list_begin = ix->list_begin; pp.list_end = ix->list_end;
             probe_walk_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 128)), 128, 0, s>>>(ix->s_cdist.as<uint64_t>(), pp);
             ANNB_CUDA_CHECK(cudaGetLastError());
             ix->stat_launches += 2;
@@ -429,6 +431,7 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         pp.overflow = ix->s_flags.as<uint32_t>();
         pp.stat_scanned = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 8);
         pp.stat_probed = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 16);
+            pp.list_begin = ix->list_begin; pp.list_end = ix->list_end;
         size_t smem = static_cast<size_t>(nl2) * 8;
         ANNB_CUDA_CHECK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         probe_kernel<<<static_cast<uint32_t>(nq), 256, smem, s>>>(pp);
@@ -565,11 +568,12 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
 
 static int read_ivf_stats(annb_index* ix, cudaStream_t s) {
     if (ix->skip_next_ivf_stats) { ix->skip_next_ivf_stats = false; return ANNB_OK; }
-    unsigned long long h[3] = {0, 0, 0};
+    unsigned long long h[4] = {0, 0, 0, 0};
     ANNB_CUDA_CHECK(cudaMemcpyAsync(h, ix->s_flags.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
     ix->stat_scanned += static_cast<int64_t>(h[1]);
     ix->stat_probed += static_cast<int64_t>(h[2]);
+    ix->stat_scanned_local += static_cast<int64_t>(h[3]);
     return ANNB_OK;
 }
 
@@ -588,6 +592,7 @@ static int search_host(annb_index* ix, bool ivf, int mode, const float* queries,
     cudaStream_t s = ix->stream;
     ix->stat_scanned = 0;
     ix->stat_probed = 0;
+    ix->stat_scanned_local = 0;
     for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
         const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
         PreparedQueries pq;
@@ -956,6 +961,7 @@ int annb_ivf_search_dev(const annb_index* index, const float* d_queries, uint64_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     ix->stat_scanned = 0;
     ix->stat_probed = 0;
+    ix->stat_scanned_local = 0;
     for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
         const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
         PreparedQueries pq;
@@ -1035,6 +1041,7 @@ int annb_index_get_stat(const annb_index* ix, const char* key, int64_t* out) {
     if (k == "kernel_launches") *out = ix->stat_launches;
     else if (k == "scanned_vectors") *out = ix->stat_scanned;
     else if (k == "probed_lists") *out = ix->stat_probed;
+    else if (k == "scanned_vectors_local") *out = ix->stat_scanned_local;
     else if (k == "last_path") *out = ix->stat_last_path;
     else if (k == "coarse_path") *out = ix->stat_coarse_path;
     else if (k == "fallback_queries") *out = ix->stat_fallback_queries;

@@ -83,6 +83,7 @@ struct annb_index {
     // stats
     mutable int64_t stat_launches = 0;
     mutable int64_t stat_scanned = 0, stat_probed = 0, stat_last_path = 0, stat_uncertified = 0;
+    mutable int64_t stat_scanned_local = 0;   // vectors of this shard's own lists among stat_scanned
 
     uint64_t device_bytes = 0;
 

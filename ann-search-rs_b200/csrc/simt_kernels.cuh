@@ -602,6 +602,7 @@ struct ProbeParams {
     uint32_t* overflow;      // set to 1 if some query needs more than probe_pitch cells
     unsigned long long* stat_scanned;  // sum over queries of reachable vectors
     unsigned long long* stat_probed;   // sum over queries of probed cells
+    uint32_t list_begin, list_end;     // this shard's lists: stat_scanned[1] counts only their vectors
 };
 
 __global__ void __launch_bounds__(256) probe_kernel(ProbeParams p) {
@@ -615,11 +616,12 @@ __global__ void __launch_bounds__(256) probe_kernel(ProbeParams p) {
     bitonic_sort_keys<true>(keys, p.nlist_pow2, threadIdx.x, blockDim.x);
     if (threadIdx.x == 0) {
         uint32_t chosen = 0;
-        uint64_t reach = 0;
+        uint64_t reach = 0, local = 0;
         for (uint32_t i = 0; i < p.nlist; i++) {
             uint32_t c = key_idx(keys[i]);
             chosen++;
             reach += p.offsets[c + 1] - p.offsets[c];
+            if (c >= p.list_begin && c < p.list_end) local += p.offsets[c + 1] - p.offsets[c];
             if (chosen >= p.nprobe && reach >= p.k) break;
         }
         s_np = chosen;
@@ -627,6 +629,7 @@ __global__ void __launch_bounds__(256) probe_kernel(ProbeParams p) {
         p.n_probes[q] = min(chosen, p.probe_pitch);
         atomicAdd(p.stat_scanned, static_cast<unsigned long long>(reach));
         atomicAdd(p.stat_probed, static_cast<unsigned long long>(chosen));
+        atomicAdd(p.stat_probed + 1, static_cast<unsigned long long>(local));
     }
     __syncthreads();
     const uint32_t np = min(s_np, p.probe_pitch);
@@ -642,7 +645,7 @@ __global__ void probe_walk_kernel(const uint64_t* __restrict__ ranked, ProbePara
     if (q >= p.nq) return;
     const uint64_t* keys = ranked + q * p.probe_pitch;
     uint32_t chosen = 0;
-    uint64_t reach = 0;
+    uint64_t reach = 0, local = 0;
     bool done = false;
     for (uint32_t i = 0; i < p.probe_pitch; i++) {
         const uint32_t c = key_idx(keys[i]);
@@ -650,12 +653,14 @@ __global__ void probe_walk_kernel(const uint64_t* __restrict__ ranked, ProbePara
         p.probes[q * p.probe_pitch + i] = c;
         chosen++;
         reach += p.offsets[c + 1] - p.offsets[c];
+        if (c >= p.list_begin && c < p.list_end) local += p.offsets[c + 1] - p.offsets[c];
         if (chosen >= p.nprobe && reach >= p.k) { done = true; break; }
     }
     if (!done && chosen < p.nlist) atomicExch(p.overflow, 1u);
     p.n_probes[q] = chosen;
     atomicAdd(p.stat_scanned, static_cast<unsigned long long>(reach));
     atomicAdd(p.stat_probed, static_cast<unsigned long long>(chosen));
+    atomicAdd(p.stat_probed + 1, static_cast<unsigned long long>(local));
 }
 
 // ---------------------------------------------------------------------------

@@ -370,6 +370,7 @@ def run_b200(args):
     e2e_qps = nq / e2e_s
     # probed-list statistics are collected by the host-buffer entry point (last e2e step)
     scanned = index.get_stat("scanned_vectors") if args.workload == "ivf" else 0
+    scanned_local = index.get_stat("scanned_vectors_local") if args.workload == "ivf" else 0   # this rank's own lists
     if world > 1 and args.workload == "ivf":
         # every rank derives the same global probe lists; the vectors it scans are those of its own lists
         pass
@@ -410,14 +411,14 @@ def run_b200(args):
     else:
         esz = {"f32": 4, "bf16": 2, "sq8": 1}[args.dtype]
         per_vec = dim * esz + (4 if args.metric == "cosine" else 0)
-        algo_bytes = scanned * per_vec                           # sum over queries of probed list bytes, last step
-        algo_bytes_per_query = algo_bytes / nq
+        algo_bytes = scanned_local * per_vec                     # sum over queries of probed list bytes on this rank, last step
+        algo_bytes_per_query = scanned * per_vec / nq            # whole index
         hbm = {"algorithmic_bytes_per_launch": algo_bytes, "algorithmic_gbs": algo_bytes / dom_s / 1e9, "peak_gbs": peaks["hbm_gbs"]}
         if last_path == 2:
             # tensor-core grouped scan: one list load serves up to 128 queries, so the per-query byte count is not what the
             # kernel moves (algorithmic GB/s exceeds the HBM peak by design); the kernel is a grouped GEMM and is
             # bounded by the tensor pipe + its select epilogue.  HBM view: measured dram bytes from the ncu capture, if any.
-            flops = 2.0 * scanned * dim
+            flops = 2.0 * scanned_local * dim                        # this rank's kernel scans its own lists only
             if args.dtype == "f32":
                 pipe_peak, terms = peaks["bf16_tflops"] / 2.0, 3
             elif args.dtype == "bf16":

@@ -195,10 +195,13 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
  *               "ivf_list_major" (IVF list scan: -1 auto, 0 query-major streaming kernel, 1 list-major batched kernel),
  *               "time_kernels" (1 = bracket the dominant kernel of every search with CUDA events on its stream),
  *               "tc_ts" (tensor paths: 1 = query operand resident in TMEM), "ivf_fast_probe" (0/1/2),
+ *               "ivf_tc_coarse" (1 = rank the centroids on the tensor cores when nlist >= 512, 0 = CUDA-core ranking only),
  *               "cert_eps_log2" (error bound assumed by the coverage certificate of the tensor paths, default -20; 0 = off),
  *               "cert_fallback" (1 = queries that fail the certificate are recomputed on the exact CUDA-core path)
  *   get_stat  : "kernel_launches" (cumulative), "scanned_vectors" (IVF, last call: sum of probed
- *               list lengths), "probed_lists" (last call), "last_path" (annb_path actually used),
+ *               list lengths), "scanned_vectors_local" (the part of it that lies in this handle's own lists),
+ *               "probed_lists" (last call), "last_path" (annb_path actually used),
+ *               "coarse_path" (IVF, last call: 0 exact dense centroid ranking, 1 fused CUDA-core select, 2 tensor cores),
  *               "uncertified" (tensor path, last call: queries that failed the coverage certificate),
  *               "fallback_queries" (cumulative: queries recomputed on the exact path),
  *               "dominant_kernel_ns" / "dominant_kernel_launches" (with "time_kernels": summed device time and count
@@ -207,10 +210,13 @@ int annb_index_set_option(annb_index* index, const char* key, int64_t value);
 int annb_index_get_stat(const annb_index* index, const char* key, int64_t* out);
 
 /* Diagnostics (tests only): with option "tc_debug" = 1 the first CTA of the tensor-core flat kernel dumps the
- * 128 x 128 selection values v = fma(q.x, a, b) of its first tile; this copies them to host_out[128 * 128]. */
+ * 128 x 128 selection values v = fma(q.x, a, b) of its first tile; this copies them to host_out[128 * 128].
+ * IVF handle: the first 64 KiB of the packed (value, row) candidate lists of the last tensor-core scan. */
 int annb_debug_fetch_tile(annb_index* index, float* host_out);
 /* ... and its role wait-cycle counters {mma_total, producer_wait_empty, mma_wait_full, mma_wait_tmem_empty,
- * epilogue_wait_tmem_full, epilogue_slow_path, tiles, 0} of the last tensor-path launch. */
+ * epilogue_wait_tmem_full, epilogue_slow_path, tiles, 0} of the last tensor-path launch.
+ * IVF handle: {total, schedule, query gather, epilogue wait-tmem-full, mma wait-queries, mma wait-data,
+ * mma wait-tmem-empty, tasks << 32 | tiles} of CTA 0 of the last tensor-core scan. */
 int annb_debug_fetch_cycles(annb_index* index, uint64_t* host_out8);
 
 void annb_destroy(annb_index* index);
