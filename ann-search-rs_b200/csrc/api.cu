@@ -244,7 +244,7 @@ static int prepare_self(annb_index* ix, uint64_t pos_begin, uint64_t nq, bool ne
 // flat search core (device pointers, asynchronous on s)
 // ---------------------------------------------------------------------------
 static int flat_simt(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint32_t kk, uint64_t* d_ids, float* d_dist,
-                     uint32_t* d_cnt, cudaStream_t s);
+                     uint32_t* d_cnt, cudaStream_t s, bool is_fallback = false);
 static int read_ivf_stats(annb_index* ix, cudaStream_t s);
 
 // Number of queries of the tensor-path call just issued on `s` that failed the coverage certificate (synchronises s).
@@ -281,7 +281,7 @@ static int flat_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uin
         ANNB_TRY(ix->s_fbi.ensure(static_cast<uint64_t>(n_unc) * k * 8));
         ANNB_TRY(ix->s_fbd.ensure(static_cast<uint64_t>(n_unc) * k * 4));
         ANNB_TRY(ix->s_fbc.ensure(static_cast<uint64_t>(n_unc) * 4));
-        ANNB_TRY(flat_simt(ix, sub, n_unc, k, kk, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(), ix->s_fbc.as<uint32_t>(), s));
+        ANNB_TRY(flat_simt(ix, sub, n_unc, k, kk, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(), ix->s_fbc.as<uint32_t>(), s, true));
         scatter_results_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * k, 256), 256, 0, s>>>(list, n_unc, k, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(),
                                                                                              ix->s_fbc.as<uint32_t>(), d_ids, d_dist, d_cnt);
         ANNB_CUDA_CHECK(cudaGetLastError());
@@ -295,13 +295,14 @@ static int flat_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uin
 
 // Exact CUDA-core flat search (tile_kernel + finalize).
 static int flat_simt(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint32_t kk, uint64_t* d_ids, float* d_dist,
-                     uint32_t* d_cnt, cudaStream_t s) {
+                     uint32_t* d_cnt, cudaStream_t s, bool is_fallback) {
     if (kk > 1024) return fail(ANNB_ERR_UNSUPPORTED, "k > 1024 is not supported");
     const uint32_t nsort = WarpSelect::sort_size(kk);
     const uint64_t q_tiles = ceil_div<uint64_t>(nq, CTA_QUERIES);
     uint32_t splits = ix->opt_db_splits > 0 ? static_cast<uint32_t>(ix->opt_db_splits)
-                                            : static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(64, ceil_div<uint64_t>(2 * 148, q_tiles))));
+                                            : static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(592, ceil_div<uint64_t>(4 * 148, q_tiles))));   // tiny batches (the tensor path's fallback): up to four waves of splits
     splits = static_cast<uint32_t>(std::min<uint64_t>(splits, std::max<uint64_t>(1, ix->n / 256)));
+    splits = std::min<uint32_t>(splits, std::max<uint32_t>(1, 16384u / kk));   // finalize sorts splits * k keys in shared memory
     uint64_t rps = round_up<uint64_t>(ceil_div<uint64_t>(ix->n, splits), TILE_ROWS);
     splits = static_cast<uint32_t>(ceil_div<uint64_t>(ix->n, rps));
     ANNB_TRY(ix->s_keys.ensure(nq * splits * static_cast<uint64_t>(kk) * 8));
@@ -312,7 +313,7 @@ static int flat_simt(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uin
     p.k = kk; p.nsort = nsort; p.n_splits = splits; p.rows_per_split = rps; p.part_keys = ix->s_keys.as<uint64_t>();
     size_t smem = tile_kernel_smem(ix->row_bytes, pq.scan_bytes, nsort, true);
     {
-        KernelTimer kt(ix, s);
+        KernelTimer kt(ix, s, !is_fallback);
         ANNB_TRY(launch_select_tile(ix->dtype, pq.qt, ix->metric, p, dim3(static_cast<uint32_t>(q_tiles), splits), smem, s));
     }
     ix->stat_launches++;

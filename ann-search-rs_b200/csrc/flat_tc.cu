@@ -59,6 +59,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     uint64_t* bar_tfull = bar_q + 1;                   // [ACC_STAGES]
     uint64_t* bar_tempty = bar_tfull + ACC_STAGES;     // [ACC_STAGES]
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + ACC_STAGES);
+    float* s_aux_all = reinterpret_cast<float*>(s_tail + 256);   // [8 epilogue warps][64]: per-row constants of the warp's current half tile
 
     const uint32_t q0 = blockIdx.x * BM;
     const uint64_t r_begin = static_cast<uint64_t>(blockIdx.y) * p.rows_per_split;
@@ -215,9 +216,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         }
         uint32_t* gtau_ptr = p.gtau + q0 + row_in_tile;
         uint32_t g_next = DENSE ? 0xFFFFFFFFu : *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
-        // Per-column constants of this warp's 64-column half: lane l keeps columns l and l + 32 in registers
-        // (coalesced load, fetched one tile ahead) and the warp broadcasts them with shuffles -- no shared memory,
-        // no barrier between the epilogue warps.
+        // Per-column constants of this warp's 64-column half: lane l fetches columns l and l + 32 (coalesced, one tile
+        // ahead) and parks them in a warp-private shared-memory row; the value loop reads them back as 128-bit broadcast
+        // loads (16 per tile instead of 64 shuffles).  No CTA-wide barrier: only __syncwarp.
+        float* s_aux = s_aux_all + (warp - 2) * 64;
         const float* aux_half = p.aux + r_begin + half * 64 + lane;
         float aux_lo_next = 0.f, aux_hi_next = 0.f;
         if (n_tiles > 0) { aux_lo_next = __ldg(aux_half); aux_hi_next = __ldg(aux_half + 32); }
@@ -231,6 +233,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 aux_hi_next = __ldg(aux_half + static_cast<size_t>(t + 1) * BN + 32);
                 if (!DENSE) g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
             }
+            __syncwarp();                      // every lane is done with the previous tile's constants
+            s_aux[lane] = aux_lo;
+            s_aux[lane + 32] = aux_hi;
+            __syncwarp();
             mbar_wait_timed(bar_tfull + acc, aph, w_tfull);
             tc_fence_after();
             const float g_tau = ordered_to_f32(g_bits);       // NaN (all-ones init) is ignored by fminf
@@ -248,7 +254,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const int col = g * 8 + j;   // compile-time after unrolling
-                        const float cst = __shfl_sync(0xFFFFFFFFu, col < 32 ? aux_lo : aux_hi, col & 31);
+                        const float cst = s_aux[col];
                         const float sdot = (KIND == KIND_I8) ? __int2float_rn(static_cast<int32_t>(r[col])) : __uint_as_float(r[col]);   // s32 dots are exact in f32 (< 2^24)
                         v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
                         mg = fminf(mg, v[g * 8 + j]);
@@ -733,7 +739,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     // query operand resident in TMEM (TS-mode MMA) when its pieces fit their column budget (bf16 terms: 64 columns each)
     const bool ts = kind == tc::KIND_I8 || (ix->opt_tc_ts != 0 && (kind != tc::KIND_BF16 || kp * elem <= 256));
     const size_t q_smem = ts ? 0 : static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * st->nslab * tc::SLAB_TILE;
-    const size_t fixed = 256 /*barriers*/;
+    const size_t fixed = 256 /*barriers*/ + 8 * 64 * 4 /*per-warp row constants*/;
     const size_t budget = 227 * 1024;
     if (q_smem + fixed + nb * tc::SLAB_TILE > budget) { set_last_error("tensor path: query tile too large for shared memory"); return ANNB_ERR_UNSUPPORTED; }
     uint32_t stages = static_cast<uint32_t>((budget - q_smem - fixed) / (nb * tc::SLAB_TILE));
@@ -775,7 +781,9 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
     // SQ8 L2 (dim <= 256): the pre-selection values are exact integers, so the certificate only has to exclude a tie between
     // the k-th exact distance and the k'-th pre-selected value (pruning is strict, a tied row of lower id could have been dropped)
-    r.cert_eps = (kind == tc::KIND_I8 && ix->metric != ANNB_COSINE && ix->dim <= 256) ? std::min(ix->opt_cert_eps, 1e-30f) : ix->opt_cert_eps; r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
+    r.cert_eps = (kind == tc::KIND_I8 && ix->metric != ANNB_COSINE && ix->dim <= 256) ? std::min(ix->opt_cert_eps, 1e-30f) : ix->opt_cert_eps;
+    // SQ8 cosine: the selection value is two float operations on an exact integer dot (a few ulp): 2^-21 bounds it
+    if (kind == tc::KIND_I8 && ix->metric == ANNB_COSINE) r.cert_eps = std::min(r.cert_eps, 4.7683716e-07f); r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
     const bool cos = ix->metric == ANNB_COSINE;
     int rc;
     if (ix->dtype == ANNB_SQ8) rc = cos ? launch_rerank<2, QT_I8, MET_COS>(r, s) : launch_rerank<2, QT_I8, MET_L2>(r, s);
@@ -865,7 +873,7 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     const uint32_t splits_req = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(db_tiles, (2 * 148 + q_tiles - 1) / q_tiles)));
     const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;
     const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
-    const size_t fixed = 256, budget = 227 * 1024;
+    const size_t fixed = 256 + 8 * 64 * 4, budget = 227 * 1024;
     const uint32_t stages = static_cast<uint32_t>(std::min<size_t>(8, (budget - fixed) / (2 * tc::SLAB_TILE)));
     const size_t smem = static_cast<size_t>(stages) * 2 * tc::SLAB_TILE + fixed;
     ANNB_TRY(st->dense.ensure(nq * static_cast<uint64_t>(st->n_pad) * 4));

@@ -562,6 +562,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));
     ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
     r.cert_eps = (st->kind == tc::KIND_I8 && l2 && ix->dim <= 256) ? std::min(ix->opt_cert_eps, 1e-30f) : ix->opt_cert_eps;   // exact integers: tie check only
+    if (st->kind == tc::KIND_I8 && !l2) r.cert_eps = std::min(r.cert_eps, 4.7683716e-07f);   // SQ8 cosine: a few ulp on an exact integer dot
     r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
     int rc;
     if (ix->dtype == ANNB_SQ8) rc = l2 ? launch_ivf_rerank<2, MET_L2>(r, s) : launch_ivf_rerank<2, MET_COS>(r, s);

@@ -331,6 +331,7 @@ def run_b200(args):
     ms_per_step = ms / args.steps
     qps = nq / (ms_per_step * 1e-3)
     last_path = index.get_stat("last_path")
+    uncertified = index.get_stat("uncertified")      # tensor path, last step: queries recomputed on the exact path
 
     # ---- end to end through the host-buffer C ABI (pinned host queries, host outputs) ----
     hq = torch.from_numpy(queries).pin_memory()
@@ -460,7 +461,7 @@ def run_b200(args):
             "data": "synthetic", "config": workload_desc(args, kind, world), "clocks": clocks,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * dim * 4),
                     "d2h_bytes_per_step": int(nq * k * 12 + nq * 4), "ms_per_step": e2e_s * 1e3},
-            "gpu_launches": int(launches), "roofline": roofline}
+            "gpu_launches": int(launches), "roofline": roofline, "uncertified_queries_last_step": int(uncertified)}
     if algo_bytes_per_query is not None:
         line["config"]["algorithmic_bytes_per_query"] = algo_bytes_per_query
 
