@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + NACC);
     uint32_t* s_task = s_tmem + 1;                 // [4]: list, pair0, n_in_group, valid flag
     uint64_t* s_rows = reinterpret_cast<uint64_t*>(s_tmem + 6);  // [2]: r_begin, r_end (8-byte aligned: bars + ... even count)
+    float* s_aux_all = reinterpret_cast<float*>(s_tail + 256);   // [8 epilogue warps][64] row constants of the warp's current half tile
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.n_stages; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); mbar_init(bar_xf + s, XF_THREADS); }
@@ -309,6 +310,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                 lo_v = (c0 < r_end) ? __ldg(aux_half + static_cast<size_t>(t) * BN) : __int_as_float(0x7FC00000);        // NaN masks rows of other lists
                 hi_v = (c0 + 32 < r_end) ? __ldg(aux_half + static_cast<size_t>(t) * BN + 32) : __int_as_float(0x7FC00000);
             };
+            float* s_aux = s_aux_all + (warp - EPI_WARP0) * 64;   // warp-private: read back as broadcast loads by the value loop
             float aux_lo_next = 0.f, aux_hi_next = 0.f;
             if (n_tiles > 0) load_aux(0, aux_lo_next, aux_hi_next);
             for (uint32_t t = 0; t < n_tiles; t++, tg++) {
@@ -319,6 +321,12 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                 if (t + 1 < n_tiles) {
                     load_aux(t + 1, aux_lo_next, aux_hi_next);
                     if (has_query) g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
+                }
+                if (warp_has_query) {
+                    __syncwarp();                  // every lane is done with the previous tile's constants
+                    s_aux[lane] = aux_lo;
+                    s_aux[lane + 32] = aux_hi;
+                    __syncwarp();
                 }
                 mbar_wait_timed(bar_tfull + acc, aph, c_tfull);
                 tc_fence_after();
@@ -337,7 +345,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
                             const int col = g * 8 + j;
-                            const float cst = __shfl_sync(0xFFFFFFFFu, col < 32 ? aux_lo : aux_hi, col & 31);
+                            const float cst = s_aux[col];
                             const float sdot = (KIND == KIND_I8) ? __int2float_rn(static_cast<int32_t>(r[col])) : __uint_as_float(r[col]);
                             v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
                             mg = fminf(mg, v[col]);
@@ -524,7 +532,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     IvfTcState* st = ix->tc_ivf;
     const uint32_t kprime = tc_ivf_kprime(ix, k_eff);
     const uint32_t nb = st->kind == tc::KIND_TF32X3 ? 2 : 1;
-    const size_t fixed = 512;
+    const size_t fixed = 256 /*barriers, task slots*/ + 8 * 64 * 4 /*per-warp row constants*/;
     const size_t budget = 227 * 1024;
     uint32_t stages = static_cast<uint32_t>(std::min<size_t>(8, (budget - fixed) / (nb * tc::SLAB_TILE)));
     const size_t smem = static_cast<size_t>(stages) * nb * tc::SLAB_TILE + fixed;

@@ -53,6 +53,7 @@ def parse_args():
     ap.add_argument("--gpu-setup", default="auto", choices=["auto", "on", "off"],
                     help="IVF workload: generate data and build the index on the GPU (auto: when n > 2M)")
     ap.add_argument("--kmeans-iters", type=int, default=8)
+    ap.add_argument("--tc-candidates", type=int, default=0, choices=[0, 16, 32], help="k' of the tensor-core pre-selection (0 = library default)")
     return ap.parse_args()
 
 
@@ -265,6 +266,8 @@ def run_b200(args):
                                                 norms=None if norms is None else norms[r0:r1], centroid_norms=oi.centroid_norms,
                                                 sq8_scales=oi.scales, list_begin=lb, list_end=le, device=local_rank, n_total=oi.n)
     index.set_option("path", path)
+    if args.tc_candidates:
+        index.set_option("tc_candidates", args.tc_candidates)
     index.set_option("time_kernels", 1)
 
     dq = torch.from_numpy(queries).to(dev)

@@ -23,3 +23,20 @@ for metric, mname in ((annb200.COSINE, "cosine"), (annb200.L2, "l2")):
             torch.cuda.synchronize()
             print(f"flat {dname} {mname}: eps=2^{e}: uncertified {ix.get_stat('uncertified')} / {nq}")
         ix.close()
+
+# IVF list scan (10M x 128 L2 unless CERT_N is set)
+n2 = int(os.environ.get("CERT_N", 10_000_000))
+data = None
+torch.cuda.empty_cache()
+data = gs.correlated_gpu(n2, dim, dev, seed=42)
+q = gs.subsample_with_noise_gpu(data, nq, seed=42)
+for dt, dname in ((annb200.F32, "f32"), (annb200.BF16, "bf16"), (annb200.SQ8, "sq8")):
+    parts = gs.build_ivf_parts_gpu(data, 4096, dt, 0, seed=42, kmeans_iters=8)
+    ix = gs.ivf_handle_from_parts(parts, n2, dim, dt, annb200.L2, 0)
+    ix.set_option("cert_fallback", 0)
+    for e in (-18, -20, -22):
+        ix.set_option("cert_eps_log2", e)
+        annb200._check(lib.annb_ivf_search_dev(ix.handle, q.data_ptr(), nq, dim, 10, 32, ids.data_ptr(), d.data_ptr(), None, st))
+        torch.cuda.synchronize()
+        print(f"ivf {dname} l2 nprobe=32: eps=2^{e}: uncertified {ix.get_stat('uncertified')} / {nq} (coarse path {ix.get_stat('coarse_path')})")
+    ix.close()
