@@ -41,8 +41,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     static_assert(KIND != KIND_I8 || TS, "the int8 kernel keeps its queries in TMEM");
     constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;      // 32 tf32 / 64 bf16 per slab row
     constexpr int KSTEPS = 4;                          // 128 B / 32 B per UMMA K step (8 tf32 / 16 bf16)
-    constexpr int NACC = TS ? 2 : ACC_STAGES;          // accumulator stages (TS: 256 of the 512 columns hold the queries)
-    constexpr uint32_t ACC_COL0 = TS ? 256u : 0u;
+    // accumulator stages behind the TMEM-resident queries (TS): f32 / bf16 pieces take up to 256 columns, int8 codes 128
+    constexpr int NACC = TS ? (KIND == KIND_I8 ? 3 : 2) : ACC_STAGES;
+    constexpr uint32_t ACC_COL0 = TS ? (KIND == KIND_I8 ? 128u : 256u) : 0u;
     constexpr uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : (KIND == KIND_I8 ? 32u : 64u);   // TMEM columns per query piece (32-bit words per row)
 
     extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte aligned bases
@@ -344,35 +345,41 @@ struct CoarseSelectParams {
     uint64_t* ranked;           // [nq][pitch]
 };
 
-__host__ __device__ inline size_t coarse_select_warp_bytes(uint32_t nlist, uint32_t cmax) {
-    return static_cast<size_t>(cmax) * 8 + static_cast<size_t>((nlist + 31u) & ~31u) * 4 + 256 * 4 + static_cast<size_t>(cmax) * 4;
+__host__ __device__ inline size_t coarse_select_warp_bytes(uint32_t cmax) {
+    return static_cast<size_t>(cmax) * 8 + 256 * 4 + static_cast<size_t>(cmax) * 4;   // keys | histogram | candidate cells
 }
 
 template <int MET>
-__global__ void __launch_bounds__(128) coarse_select_kernel(CoarseSelectParams p) {
+__global__ void __launch_bounds__(256) coarse_select_kernel(CoarseSelectParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t q = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
     if (q >= p.nq) return;   // warps are independent: no block-wide barrier below
-    uint8_t* base = smem + warp * coarse_select_warp_bytes(p.nlist, p.cmax);
+    uint8_t* base = smem + warp * coarse_select_warp_bytes(p.cmax);
     uint64_t* keys = reinterpret_cast<uint64_t*>(base);                  // [cmax]
-    uint32_t* vals = reinterpret_cast<uint32_t*>(keys + p.cmax);         // [nlist rounded up to 32]
-    uint32_t* hist = vals + ((p.nlist + 31u) & ~31u);                    // [256]
+    uint32_t* hist = reinterpret_cast<uint32_t*>(keys + p.cmax);         // [256]
     uint32_t* cand = hist + 256;                                          // [cmax]
-    const float* src = p.dense + q * p.dense_ld;
+    // The row of values is not staged: the (few) passes re-read it with coalesced 128-bit loads -- it stays in L1 / L2,
+    // and the small shared-memory footprint keeps many warps resident to hide the latency.  dense_ld is a multiple of 128.
+    const float4* src4 = reinterpret_cast<const float4*>(p.dense + q * p.dense_ld);
+    const uint32_t n4 = (p.nlist + 3) >> 2;
+    auto ord = [&](float4 x, uint32_t i4, uint32_t u[4]) {   // ordered images; columns past nlist never qualify
+        u[0] = f32_to_ordered(x.x); u[1] = f32_to_ordered(x.y); u[2] = f32_to_ordered(x.z); u[3] = f32_to_ordered(x.w);
+#pragma unroll
+        for (int e = 0; e < 4; e++) if (4 * i4 + e >= p.nlist) u[e] = 0xFFFFFFFFu;
+    };
     uint32_t umin = 0xFFFFFFFFu, umax = 0u;
-    for (uint32_t i = lane; i < p.nlist; i += 32) {
-        const uint32_t u = f32_to_ordered(src[i]);
-        vals[i] = u;
-        umin = min(umin, u);
-        umax = max(umax, u);
+    for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
+        uint32_t u[4];
+        ord(__ldg(src4 + i4), i4, u);
+#pragma unroll
+        for (int e = 0; e < 4; e++) if (4 * i4 + e < p.nlist) { umin = min(umin, u[e]); umax = max(umax, u[e]); }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         umin = min(umin, __shfl_xor_sync(0xFFFFFFFFu, umin, off));
         umax = max(umax, __shfl_xor_sync(0xFFFFFFFFu, umax, off));
     }
-    __syncwarp();
 
     // 1. threshold: radix select, most significant digit first, starting at the first bit in which the row's values
     //    differ (the common high bits -- sign, exponent -- would put every value into one histogram bin).  It stops as
@@ -390,9 +397,12 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(CoarseSelectParams p
             const uint32_t hmask = rem >= 32u ? 0u : ~0u << rem;
             for (uint32_t b = lane; b < 256; b += 32) hist[b] = 0;
             __syncwarp();
-            for (uint32_t i = lane; i < p.nlist; i += 32) {
-                const uint32_t u = vals[i];
-                if ((u & hmask) == prefix) atomicAdd(hist + ((u >> sh) & dmask), 1u);
+            for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
+                uint32_t u[4];
+                ord(__ldg(src4 + i4), i4, u);
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    if (4 * i4 + e < p.nlist && (u[e] & hmask) == prefix) atomicAdd(hist + ((u[e] >> sh) & dmask), 1u);
             }
             __syncwarp();
             uint32_t h[8], local = 0;
@@ -432,15 +442,25 @@ __global__ void __launch_bounds__(128) coarse_select_kernel(CoarseSelectParams p
     }
     // 2. candidates: every cell with value <= thr
     uint32_t count = 0;
-    for (uint32_t i0 = 0; i0 < p.nlist; i0 += 32) {
-        const uint32_t i = i0 + lane;
-        const bool hit = i < p.nlist && vals[i] <= thr;
-        const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
-        if (hit) {
-            const uint32_t pos = count + __popc(m & ((1u << lane) - 1u));
-            if (pos < p.cmax) cand[pos] = i;
+    for (uint32_t i0 = 0; i0 < n4; i0 += 32) {
+        const uint32_t i4 = i0 + lane;
+        uint32_t u[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+        if (i4 < n4) ord(__ldg(src4 + i4), i4, u);
+        uint32_t mine = 0;
+#pragma unroll
+        for (int e = 0; e < 4; e++) mine += (4 * i4 + e < p.nlist && u[e] <= thr) ? 1u : 0u;
+        // exclusive prefix of the per-lane hit counts
+        uint32_t incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (lane >= static_cast<uint32_t>(off)) incl += t;
         }
-        count += __popc(m);
+        uint32_t pos = count + incl - mine;
+#pragma unroll
+        for (int e = 0; e < 4; e++)
+            if (4 * i4 + e < p.nlist && u[e] <= thr) { if (pos < p.cmax) cand[pos] = 4 * i4 + e; pos++; }
+        count += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
     __syncwarp();
     uint64_t* out = p.ranked + q * p.pitch;
@@ -847,10 +867,9 @@ bool tc_coarse_supported(const annb_index* ix) { return ix->tc_coarse != nullptr
 template <int MET>
 static int launch_coarse_select(const tc::CoarseSelectParams& c, cudaStream_t s) {
     auto kern = tc::coarse_select_kernel<MET>;
-    const size_t per_warp = tc::coarse_select_warp_bytes(c.nlist, c.cmax);
-    const uint32_t warps = static_cast<uint32_t>(std::max<size_t>(1, std::min<size_t>(4, (100 * 1024) / per_warp)));
+    const size_t per_warp = tc::coarse_select_warp_bytes(c.cmax);
+    const uint32_t warps = 8;
     const size_t smem = per_warp * warps;
-    if (smem > 200 * 1024) { set_last_error("centroid ranking: nlist too large for the tensor-core selection"); return ANNB_ERR_UNSUPPORTED; }
     ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<static_cast<uint32_t>((c.nq + warps - 1) / warps), warps * 32, smem, s>>>(c);
     ANNB_CUDA_CHECK(cudaGetLastError());

@@ -56,8 +56,9 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     constexpr int ELEM = (KIND == KIND_TF32X3) ? 4 : (KIND == KIND_I8 ? 1 : 2);
     constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;
     constexpr int KSTEPS = 4;
-    constexpr int NACC = 2;
-    constexpr uint32_t ACC_COL0 = 256u;
+    // TMEM: query pieces at column 0 (f32 256 columns, bf16 192, int8 32), accumulator ring behind them
+    constexpr int NACC = (KIND == KIND_I8) ? 3 : 2;
+    constexpr uint32_t ACC_COL0 = (KIND == KIND_I8) ? 128u : 256u;
     constexpr uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : (KIND == KIND_I8 ? 32u : 64u);
     constexpr uint32_t idesc = make_idesc(KIND);
     constexpr uint32_t SLAB_DESC = SLAB_TILE >> 4;
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + NACC);
     uint32_t* s_task = s_tmem + 1;                 // [4]: list, pair0, n_in_group, valid flag
     uint64_t* s_rows = reinterpret_cast<uint64_t*>(s_tmem + 6);  // [2]: r_begin, r_end (8-byte aligned: bars + ... even count)
-    float* s_aux_all = reinterpret_cast<float*>(s_tail + 256);   // [8 epilogue warps][64] row constants of the warp's current half tile
+    float* s_aux_all = reinterpret_cast<float*>(s_tail + 512);   // [8 epilogue warps][64] row constants of the warp's current half tile
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.n_stages; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); mbar_init(bar_xf + s, XF_THREADS); }
@@ -532,7 +533,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     IvfTcState* st = ix->tc_ivf;
     const uint32_t kprime = tc_ivf_kprime(ix, k_eff);
     const uint32_t nb = st->kind == tc::KIND_TF32X3 ? 2 : 1;
-    const size_t fixed = 256 /*barriers, task slots*/ + 8 * 64 * 4 /*per-warp row constants*/;
+    const size_t fixed = 512 /*barriers, task slots (<= 296 B)*/ + 8 * 64 * 4 /*per-warp row constants*/;
     const size_t budget = 227 * 1024;
     uint32_t stages = static_cast<uint32_t>(std::min<size_t>(8, (budget - fixed) / (nb * tc::SLAB_TILE)));
     const size_t smem = static_cast<size_t>(stages) * nb * tc::SLAB_TILE + fixed;
