@@ -276,27 +276,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 }
                 if (m < tau) {
                     const long long ts0 = clock64();
-                    // Rare path, cost proportional to the number of groups that really hold a candidate: stash the
-                    // 64 values once (independent stores), then visit only the groups whose minimum beats tau.
-#pragma unroll
-                    for (int j = 0; j < 64; j++) scratch[j] = v[j];
-                    uint32_t gmask = 0;
-#pragma unroll
-                    for (int g = 0; g < 8; g++) gmask |= (gm[g] < tau) ? (1u << g) : 0u;
-                    while (gmask) {
-                        const int g = __ffs(gmask) - 1;
-                        gmask &= gmask - 1;
-                        float s8[8];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) s8[j] = scratch[g * 8 + j];
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            if (s8[j] < tau) {
-                                top.insert(s8[j], row0 + c * 64 + g * 8 + j);
-                                tau = fminf(tau, top.tau());
-                            }
-                        }
-                    }
+                    select_from_tile<KP>(top, tau, v, gm, m, row0 + c * 64, scratch);
                     w_slow += clock64() - ts0;
                 }
             }

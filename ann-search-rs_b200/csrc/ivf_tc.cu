@@ -354,27 +354,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                         gm[g] = mg;
                     }
                     const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
-                    if (m < tau) {
-#pragma unroll
-                        for (int j = 0; j < 64; j++) scratch[j] = v[j];
-                        uint32_t gmask = 0;
-#pragma unroll
-                        for (int g = 0; g < 8; g++) gmask |= (gm[g] < tau) ? (1u << g) : 0u;
-                        while (gmask) {
-                            const int g = __ffs(gmask) - 1;
-                            gmask &= gmask - 1;
-                            float s8[8];
-#pragma unroll
-                            for (int j = 0; j < 8; j++) s8[j] = scratch[g * 8 + j];
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                if (s8[j] < tau) {
-                                    top.insert(s8[j], row0 + c * 64 + g * 8 + j);
-                                    tau = fminf(tau, top.tau());
-                                }
-                            }
-                        }
-                    }
+                    if (m < tau) select_from_tile<KP>(top, tau, v, gm, m, row0 + c * 64, scratch);
                 }
                 tc_fence_before();
                 mbar_arrive(bar_tempty + acc);

@@ -214,6 +214,63 @@ struct TopList {
 };
 
 
+// Candidate handling of one 64-value half tile for a thread whose tile minimum m beats its threshold tau.
+// In the steady state a thread has one such value per tile at most, but several lanes of a warp have one in the same
+// tile; so the common case is straight-line code that every such lane executes together: locate the minimum (group via
+// the group minima, column via selects -- no dynamically indexed registers, no local memory) and insert it.  Only if a
+// second value of the tile also beats the (now tighter) threshold does the thread fall back to the bulk path: stash
+// the 64 values in local memory and walk the groups that hold candidates.
+template <int KP>
+__device__ __forceinline__ void select_from_tile(TopList<KP>& top, float& tau, const float (&v)[64], const float (&gm)[8], float m, uint32_t col0,
+                                                 float (&scratch)[64]) {
+    uint32_t gs = 0;
+#pragma unroll
+    for (int g = 7; g >= 0; g--) gs = (gm[g] == m) ? static_cast<uint32_t>(g) : gs;   // lowest group holding the minimum
+    float s8[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) s8[j] = v[j];
+#pragma unroll
+    for (int g = 1; g < 8; g++) {
+        const bool here = gs == static_cast<uint32_t>(g);
+#pragma unroll
+        for (int j = 0; j < 8; j++) s8[j] = here ? v[g * 8 + j] : s8[j];
+    }
+    uint32_t js = 0;
+#pragma unroll
+    for (int j = 7; j >= 0; j--) js = (s8[j] == m) ? static_cast<uint32_t>(j) : js;   // lowest column of the group holding it
+    top.insert(m, col0 + gs * 8 + js);
+    tau = fminf(tau, top.tau());
+    // second-best value of the tile: other groups' minima, and the minimum's own group without it
+    float m2 = INFINITY;
+#pragma unroll
+    for (int g = 0; g < 8; g++) m2 = fminf(m2, gs == static_cast<uint32_t>(g) ? INFINITY : gm[g]);
+#pragma unroll
+    for (int j = 0; j < 8; j++) m2 = fminf(m2, js == static_cast<uint32_t>(j) ? INFINITY : s8[j]);
+    if (m2 < tau) {
+        const uint32_t done = gs * 8 + js;
+#pragma unroll
+        for (int j = 0; j < 64; j++) scratch[j] = v[j];
+        uint32_t gmask = 0;
+#pragma unroll
+        for (int g = 0; g < 8; g++) gmask |= (gm[g] < tau || gs == static_cast<uint32_t>(g)) ? (1u << g) : 0u;
+        while (gmask) {
+            const int g = __ffs(gmask) - 1;
+            gmask &= gmask - 1;
+            float t8[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) t8[j] = scratch[g * 8 + j];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (t8[j] < tau && static_cast<uint32_t>(g * 8 + j) != done) {
+                    top.insert(t8[j], col0 + g * 8 + j);
+                    tau = fminf(tau, top.tau());
+                }
+            }
+        }
+    }
+}
+
+
 // ----------------------------------------------------------------------------------------------- operand preparation
 __device__ __forceinline__ float rna_tf32(float x) {
     uint32_t r;
