@@ -92,6 +92,15 @@ def test_config3_4_ivf_2m_x_128_scan_variants_agree(gpu, dtype):
     assert np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
     assert np.array_equal(a[0], b[0])
     assert (np.diff(a[1], axis=1) >= 0).all() and (a[0] >= 0).all()
+    assert ix.get_stat("coarse_path") == 2                      # both runs ranked the centroids on the tensor cores
+    # ... and the whole pipeline on the exact CUDA-core kernels (exact centroid ranking, list-major CUDA-core scan)
+    ix.set_option("ivf_tc_coarse", 0)
+    ix.set_option("ivf_list_major", 1)
+    ix.set_option("path", annb200.PATH_SIMT)
+    c = _search_dev(ix, q, 10, ivf_nprobe=16)
+    assert ix.get_stat("coarse_path") != 2 and ix.get_stat("last_path") == annb200.PATH_SIMT
+    assert np.array_equal(a[1].view(np.uint32), c[1].view(np.uint32))
+    assert np.array_equal(a[0], c[0])
     truth = gs.exact_ground_truth(data, q, 10, annb200.L2, 0)
     rec = o.recall_at_k(truth, a[0], 10)
     assert rec > {"f32": 0.9, "bf16": 0.85, "sq8": 0.5}[dtype], rec
