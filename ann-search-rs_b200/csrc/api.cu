@@ -857,6 +857,72 @@ int annb_ivf_assign(const float* data, uint64_t n, uint32_t dim, const float* ce
     return ANNB_OK;
 }
 
+int annb_kmeans_lloyd(const float* data, uint64_t n, uint32_t dim, float* centroids, uint32_t nlist, int metric, uint32_t max_iters,
+                      uint32_t* out_iters, int device) {
+    if (metric == ANNB_MANHATTAN) return fail(ANNB_ERR_DISTANCE_NOT_SUPPORTED, "Manhattan distance is not supported");
+    if (metric != ANNB_L2 && metric != ANNB_COSINE) return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown metric");
+    if (!data || !centroids || n == 0 || dim == 0 || nlist == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "empty input");
+    if (nlist > n) return fail(ANNB_ERR_TOO_FEW_SAMPLES, std::to_string(n) + " training samples for " + std::to_string(nlist) + " centroids");
+    ANNB_DEVICE(device);
+    const uint32_t ld = round_up(dim * 4u, 16u) / 4u;
+    float *d_c = nullptr, *d_aux = nullptr, *d_x = nullptr, *d_cn = nullptr;
+    uint32_t *d_a = nullptr, *d_prev = nullptr, *d_cnt = nullptr;
+    double* d_sums = nullptr;
+    unsigned long long* d_changed = nullptr;
+    struct Free {
+        std::vector<void**> p;
+        ~Free() { for (void** q : p) cudaFree(*q); }
+    } fr{{reinterpret_cast<void**>(&d_c), reinterpret_cast<void**>(&d_aux), reinterpret_cast<void**>(&d_x), reinterpret_cast<void**>(&d_cn),
+          reinterpret_cast<void**>(&d_a), reinterpret_cast<void**>(&d_prev), reinterpret_cast<void**>(&d_cnt), reinterpret_cast<void**>(&d_sums),
+          reinterpret_cast<void**>(&d_changed)}};
+    ANNB_TRY(dmalloc(&d_c, static_cast<size_t>(nlist) * ld, nullptr));
+    ANNB_TRY(dmalloc(&d_aux, nlist, nullptr));
+    ANNB_TRY(dmalloc(&d_cn, nlist, nullptr));
+    ANNB_TRY(dmalloc(&d_x, n * ld, nullptr));
+    ANNB_TRY(dmalloc(&d_a, n, nullptr));
+    ANNB_TRY(dmalloc(&d_prev, n, nullptr));
+    ANNB_TRY(dmalloc(&d_cnt, nlist, nullptr));
+    ANNB_TRY(dmalloc(&d_sums, static_cast<size_t>(nlist) * dim, nullptr));
+    ANNB_TRY(dmalloc(&d_changed, 1, nullptr));
+    ANNB_CUDA_CHECK(cudaMemset(d_c, 0, static_cast<size_t>(nlist) * ld * 4));
+    ANNB_CUDA_CHECK(cudaMemcpy2D(d_c, ld * 4ull, centroids, dim * 4ull, dim * 4ull, nlist, cudaMemcpyDefault));
+    if (ld != dim) ANNB_CUDA_CHECK(cudaMemset(d_x, 0, n * ld * 4ull));
+    ANNB_CUDA_CHECK(cudaMemcpy2D(d_x, ld * 4ull, data, dim * 4ull, dim * 4ull, n, cudaMemcpyDefault));
+    ANNB_CUDA_CHECK(cudaMemset(d_prev, 0xFF, n * 4ull));      // usize::MAX: every point counts as changed in the first iteration
+    const uint64_t change_floor = std::max<uint64_t>(n / 10000, 1);
+    uint32_t it = 0;
+    for (; it < max_iters; it++) {
+        // assignment: direct_assign arithmetic (k_means_utils.rs:2119-2195) on the current centroids
+        if (metric == ANNB_COSINE) row_norms_f32_kernel<<<ceil_div(nlist, 128u), 128>>>(d_c, ld, dim, nlist, d_cn, 0);   // calculate_l2_norm
+        assign_aux_kernel<<<ceil_div(nlist, 128u), 128>>>(d_c, ld, dim, nlist, metric == ANNB_COSINE, d_cn, d_aux);
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        const uint64_t chunk = 1ull << 20;
+        for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
+            const uint64_t nr = std::min<uint64_t>(chunk, n - r0);
+            TileParams p{};
+            p.rows = reinterpret_cast<const uint8_t*>(d_c); p.n_rows = nlist; p.row_bytes = ld * 4; p.row_aux = d_aux;
+            p.queries = reinterpret_cast<const uint8_t*>(d_x + r0 * ld); p.q_bytes = ld * 4; p.nq = nr; p.dim = dim;
+            p.assign_out = d_a + r0; p.assign_cosine = metric == ANNB_COSINE;
+            const size_t smem = tile_kernel_smem(p.row_bytes, p.q_bytes, 0, false);
+            ANNB_TRY((launch_tile<0, QT_F32, MET_DOT, EPI_ARGMAX>(p, dim3(static_cast<uint32_t>(ceil_div<uint64_t>(nr, CTA_QUERIES)), 1), smem, 0)));
+        }
+        // convergence is tested before the update (k_means_utils.rs:1611-1624)
+        ANNB_CUDA_CHECK(cudaMemset(d_changed, 0, 8));
+        kmeans_changed_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(n, 256)), 256>>>(d_a, d_prev, n, d_changed);
+        unsigned long long changed = 0;
+        ANNB_CUDA_CHECK(cudaMemcpy(&changed, d_changed, 8, cudaMemcpyDeviceToHost));
+        if (changed <= change_floor) break;
+        ANNB_CUDA_CHECK(cudaMemset(d_sums, 0, static_cast<size_t>(nlist) * dim * 8));
+        ANNB_CUDA_CHECK(cudaMemset(d_cnt, 0, nlist * 4ull));
+        kmeans_accumulate_kernel<<<grid_for(n * dim, 256, 148u * 32u), 256>>>(d_x, ld, dim, n, d_a, d_sums, d_cnt);
+        kmeans_update_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(static_cast<uint64_t>(nlist) * dim, 256)), 256>>>(d_sums, d_cnt, d_c, ld, dim, nlist);
+        ANNB_CUDA_CHECK(cudaGetLastError());
+    }
+    ANNB_CUDA_CHECK(cudaMemcpy2D(centroids, dim * 4ull, d_c, ld * 4ull, dim * 4ull, nlist, cudaMemcpyDefault));
+    if (out_iters) *out_iters = it;
+    return ANNB_OK;
+}
+
 int annb_ivf_create(annb_index** out, const void* vectors, const void* norms, const float* centroids,
                     const float* centroid_norms, const uint64_t* offsets, const uint64_t* original_ids,
                     uint64_t n, uint32_t dim, uint32_t nlist, int dtype, int metric, const float* sq8_scales,

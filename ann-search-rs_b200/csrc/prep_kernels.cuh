@@ -175,6 +175,37 @@ __global__ void assign_aux_kernel(const float* __restrict__ cent, uint32_t ld, u
         aux[c] = (nrm > 0.0f) ? __fdiv_rn(1.0f, nrm) : 0.0f;
     }
 }
+// ---- Lloyd iteration pieces (parallel_lloyd, src/utils/k_means_utils.rs:1572-1700) ----
+// changed = #{i : assign[i] != prev[i]}; prev <- assign
+__global__ void kmeans_changed_kernel(const uint32_t* __restrict__ assign, uint32_t* __restrict__ prev, uint64_t n, unsigned long long* __restrict__ changed) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    const bool diff = i < n && assign[i] != prev[i];
+    if (i < n) prev[i] = assign[i];
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, diff);
+    if ((threadIdx.x & 31u) == 0 && m) atomicAdd(changed, static_cast<unsigned long long>(__popc(m)));
+}
+// per-cluster sums (f64 accumulators: the order of the reference's per-thread f32 partial sums depends on the rayon
+// pool size and is not reproducible; f64 makes the mean independent of the accumulation order to ~1e-16) and counts
+__global__ void kmeans_accumulate_kernel(const float* __restrict__ x, uint32_t ld, uint32_t dim, uint64_t n, const uint32_t* __restrict__ assign,
+                                         double* __restrict__ sums, uint32_t* __restrict__ counts) {
+    const uint64_t total = n * dim;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t r = i / dim;
+        const uint32_t e = static_cast<uint32_t>(i - r * dim);
+        const uint32_t c = assign[r];
+        atomicAdd(sums + static_cast<uint64_t>(c) * dim + e, static_cast<double>(x[r * ld + e]));
+        if (e == 0) atomicAdd(counts + c, 1u);
+    }
+}
+// centroid <- sum / count for non-empty clusters; empty clusters keep their centroid (k_means_utils.rs:1657-1666)
+__global__ void kmeans_update_kernel(const double* __restrict__ sums, const uint32_t* __restrict__ counts, float* __restrict__ cent, uint32_t ld, uint32_t dim,
+                                     uint32_t k) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= static_cast<uint64_t>(k) * dim) return;
+    const uint32_t c = static_cast<uint32_t>(i / dim), e = static_cast<uint32_t>(i - static_cast<uint64_t>(c) * dim);
+    if (counts[c] > 0) cent[static_cast<uint64_t>(c) * ld + e] = static_cast<float>(sums[i] / static_cast<double>(counts[c]));
+}
+
 // Sequential-fold norms of f32 rows (centroid norms, src/cpu/ivf.rs:193-206).
 __global__ void seq_norms_kernel(const float* __restrict__ rows, uint32_t ld, uint32_t dim, uint64_t n, float* __restrict__ out) {
     uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;

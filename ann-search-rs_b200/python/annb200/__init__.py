@@ -76,6 +76,7 @@ def lib():
         _lib.annb_flat_search_self.argtypes = [vp, u64, u64, u32, vp, vp, vp]
         _lib.annb_flat_search_dev.argtypes = [vp, vp, u64, u32, u32, vp, vp, vp, vp]
         _lib.annb_ivf_assign.argtypes = [vp, u64, u32, vp, vp, u32, i32, vp, i32]
+        _lib.annb_kmeans_lloyd.argtypes = [vp, u64, u32, vp, u32, i32, u32, vp, i32]
         _lib.annb_ivf_create.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, vp, u32, u32, i32]
         _lib.annb_ivf_search.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, vp]
         _lib.annb_ivf_search_self.argtypes = [vp, u64, u64, u32, u32, i32, vp, vp, vp]
@@ -386,29 +387,28 @@ def normalise_rows(x: np.ndarray) -> np.ndarray:
     return np.where((nrm > 0)[:, None], x / safe[:, None], x).astype(np.float32)
 
 
+def kmeans_lloyd(train: np.ndarray, init_centroids: np.ndarray, metric: int, max_iters: int = 30, device: int = 0) -> Tuple[np.ndarray, int]:
+    """Lloyd iterations of train_centroids on the device (annb_kmeans_lloyd): unbalanced parallel_lloyd
+    (src/utils/k_means_utils.rs:1572-1700) from the given initial centroids.  Returns (centroids, updates done)."""
+    train = _as_rowmajor_f32(train)
+    cent = _as_rowmajor_f32(init_centroids).copy()
+    if train.shape[1] != cent.shape[1]:
+        raise AnnSearchError(-1, f"training data has dim {train.shape[1]}, centroids {cent.shape[1]}")
+    it = C.c_uint32(0)
+    _check(lib().annb_kmeans_lloyd(_ptr(train), train.shape[0], train.shape[1], _ptr(cent), cent.shape[0], metric, max_iters, C.byref(it), device))
+    return cent, int(it.value)
+
+
 def train_centroids_lloyd(train: np.ndarray, nlist: int, metric: int, iters: int = 30, device: int = 0) -> np.ndarray:
-    """Interim centroid trainer (plain Lloyd; assignment on the GPU, centroid update on the host).
-    The reference's train_centroids (src/utils/k_means_utils.rs:2771-2938) is a "next" row of the scope
-    table; its StdRng-driven init cannot be reproduced, so the init here is evenly spaced training rows.
-    Empty clusters keep their previous centroid (k_means_utils.rs:1097-1105)."""
+    """Centroid trainer of the build_* mirrors: device Lloyd (annb_kmeans_lloyd) from evenly spaced training rows.
+    The reference's train_centroids (src/utils/k_means_utils.rs:2771-2938) seeds with rand's StdRng
+    (fast_random_init / k-means||), which cannot be reproduced here; the Lloyd loop itself is the restated one."""
     train = _as_rowmajor_f32(train)
     n, dim = train.shape
     if n < nlist:
         raise AnnSearchError(-3, f"{n} training samples for {nlist} centroids")
-    cent = train[(np.arange(nlist, dtype=np.int64) * n) // nlist].copy()
-    prev = None
-    for _ in range(max(1, iters)):
-        a = ivf_assign(train, cent, metric, seq_row_norms(cent) if metric == COSINE else None, device).astype(np.int64)
-        order = np.argsort(a, kind="stable")
-        counts = np.bincount(a, minlength=nlist)
-        starts = np.concatenate([[0], np.cumsum(counts)[:-1]])
-        nz = counts > 0
-        sums = np.add.reduceat(train[order].astype(np.float64), starts[nz], axis=0)
-        cent[nz] = (sums / counts[nz][:, None]).astype(np.float32)
-        if prev is not None and (a != prev).sum() <= max(1, n // 10000):   # k_means_utils.rs:1486-1513 stop rule
-            break
-        prev = a
-    return cent
+    init = train[(np.arange(nlist, dtype=np.int64) * n) // nlist].copy()
+    return kmeans_lloyd(train, init, metric, max(1, iters), device)[0]
 
 
 def build_ivf_host_parts(mat, centroids, metric: int, dtype: int, train_rows=None, device: int = 0) -> dict:

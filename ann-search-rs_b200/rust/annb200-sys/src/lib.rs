@@ -30,6 +30,8 @@ extern "C" {
                                  out_dist: *mut f32, out_counts: *mut u32) -> c_int;
     pub fn annb_ivf_assign(data: *const f32, n: u64, dim: u32, centroids: *const f32, centroid_norms: *const f32, nlist: u32,
                            metric: c_int, out_assign: *mut u32, device: c_int) -> c_int;
+    pub fn annb_kmeans_lloyd(data: *const f32, n: u64, dim: u32, centroids: *mut f32, nlist: u32, metric: c_int, max_iters: u32,
+                             out_iters: *mut u32, device: c_int) -> c_int;
     pub fn annb_ivf_create(out: *mut *mut annb_index, vectors: *const c_void, norms: *const c_void, centroids: *const f32,
                            centroid_norms: *const f32, offsets: *const u64, original_ids: *const u64, n: u64, dim: u32,
                            nlist: u32, dtype: c_int, metric: c_int, sq8_scales: *const f32, list_begin: u32, list_end: u32,

@@ -126,6 +126,17 @@ int annb_flat_search_dev(const annb_index* index, const float* d_queries, uint64
 int annb_ivf_assign(const float* data, uint64_t n, uint32_t dim, const float* centroids,
                     const float* centroid_norms, uint32_t nlist, int metric, uint32_t* out_assign, int device);
 
+/* Lloyd iterations of train_centroids on the device (first step of section 8f: IVF build on the GPU).  Restates the
+ * unbalanced `parallel_lloyd` loop (src/utils/k_means_utils.rs:1572-1700; GPU analogue src/gpu/k_means_gpu.rs:1813-2260):
+ * per iteration  assignment with the direct_assign arithmetic (bit-identical to annb_ivf_assign; cosine uses
+ * calculate_l2_norm of the current centroids)  ->  stop if at most max(1, n / 10000) assignments changed (tested before
+ * the update)  ->  centroid = mean of its members (f64 accumulation; empty clusters keep their centroid).
+ * `centroids` [nlist * dim] (host or device): in = the initial centroids (the reference draws them with rand's StdRng,
+ * fast_random_init / k-means||, which stays on the caller's side), out = the trained centroids.  `out_iters` (may be
+ * NULL): number of centroid updates performed.  data [n * dim] host or device. */
+int annb_kmeans_lloyd(const float* data, uint64_t n, uint32_t dim, float* centroids, uint32_t nlist, int metric,
+                      uint32_t max_iters, uint32_t* out_iters, int device);
+
 /* Builds a resident IVF index from the contents of the reference's index struct after
  * optimise_memory_layout (src/cpu/ivf.rs:25-48, 257-294; src/quantised/ivf_bf16.rs,
  * src/quantised/ivf_sq8.rs): vectors in list order in the index dtype (f32 / bf16 bit patterns /

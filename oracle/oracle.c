@@ -755,6 +755,48 @@ void orc_kmeans_lloyd(const float* train, int64_t n, int dim, int nlist, int met
     free(cnt);
 }
 
+/* parallel_lloyd, unbalanced (src/utils/k_means_utils.rs:1572-1700), from caller-supplied initial centroids:
+ * assign (direct_assign; cosine with calculate_l2_norm of the current centroids) -> stop when at most
+ * max(1, n / 10000) assignments changed, tested BEFORE the update (:1611-1624) -> centroid = sum / count, empty
+ * clusters keep their centroid (:1657-1666).  The reference sums f32 partials per rayon chunk (order depends on the
+ * pool size, not reproducible); this restatement and the device kernel accumulate in f64, the comparison between
+ * them is by tolerance.  Returns the number of centroid updates performed. */
+int orc_parallel_lloyd(const float* data, int64_t n, int dim, int nlist, int metric, int max_iters, float* centroids,
+                       int nthreads) {
+    int64_t* assign = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+    int64_t* prev = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+    float* cn = (float*)malloc(sizeof(float) * (size_t)nlist);
+    double* sums = (double*)malloc(sizeof(double) * (size_t)nlist * dim);
+    int64_t* cnt = (int64_t*)malloc(sizeof(int64_t) * (size_t)nlist);
+    for (int64_t i = 0; i < n; i++) prev[i] = -1;
+    const int64_t change_floor = (n / 10000) > 1 ? (n / 10000) : 1;
+    int it = 0;
+    for (; it < max_iters; it++) {
+        for (int c = 0; c < nlist; c++) cn[c] = orc_l2_norm_f32(centroids + (int64_t)c * dim, dim);
+        orc_assign_all(data, n, dim, centroids, cn, nlist, metric, assign, nthreads);
+        int64_t changed = 0;
+        for (int64_t i = 0; i < n; i++) changed += assign[i] != prev[i];
+        if (changed <= change_floor) break;
+        memset(sums, 0, sizeof(double) * (size_t)nlist * dim);
+        memset(cnt, 0, sizeof(int64_t) * (size_t)nlist);
+        for (int64_t i = 0; i < n; i++) {
+            int64_t c = assign[i];
+            cnt[c]++;
+            for (int d = 0; d < dim; d++) sums[c * dim + d] += data[i * dim + d];
+        }
+        for (int c = 0; c < nlist; c++)
+            if (cnt[c] > 0)
+                for (int d = 0; d < dim; d++) centroids[(int64_t)c * dim + d] = (float)(sums[(int64_t)c * dim + d] / (double)cnt[c]);
+        memcpy(prev, assign, sizeof(int64_t) * (size_t)n);
+    }
+    free(assign);
+    free(prev);
+    free(cn);
+    free(sums);
+    free(cnt);
+    return it;
+}
+
 /* Host-thread count the batch entry points will use. */
 int orc_max_threads(void) {
 #ifdef _OPENMP

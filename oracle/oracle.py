@@ -193,6 +193,18 @@ def kmeans_lloyd(train, nlist, metric, iters=10, nthreads=0):
     return cent
 
 
+def parallel_lloyd(data, init_centroids, metric, max_iters=30, nthreads=0):
+    """Unbalanced parallel_lloyd (src/utils/k_means_utils.rs:1572-1700) from given initial centroids.
+    Returns (centroids, number of updates performed)."""
+    data = _f32(data)
+    cent = _f32(init_centroids).copy()
+    L = lib()
+    L.orc_parallel_lloyd.restype = C.c_int
+    it = L.orc_parallel_lloyd(_p(data), C.c_int64(data.shape[0]), C.c_int(data.shape[1]), C.c_int(cent.shape[0]), C.c_int(metric),
+                              C.c_int(max_iters), _p(cent), C.c_int(nthreads))
+    return cent, int(it)
+
+
 # --------------------------------------------------------------------------
 # index containers (host mirrors of the reference structs)
 # --------------------------------------------------------------------------

@@ -243,3 +243,44 @@ def test_tensor_core_centroid_ranking_ties_and_uncertifiable(gpu):
     ref2 = o.ivf_search(c2, q2, 10, nprobe=9)
     _check("f32", g2.query_batch(q2, 10, nprobe=9), ref2, "tie class beyond the candidate capacity")
     assert g2.get_stat("coarse_path") != 2
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("dim", [16, 50])
+def test_device_lloyd_matches_the_restated_parallel_lloyd(gpu, metric, dim):
+    """annb_kmeans_lloyd vs the oracle's restatement of parallel_lloyd (k_means_utils.rs:1572-1700) from the same
+    initial centroids.  One step: assignments are bit-exact (direct_assign arithmetic), the means agree to f32
+    rounding of an f64 sum; a full run stops after the same number of updates with centroids within 1e-5."""
+    data = datagen.gaussian_noise(6000, dim, seed=71)
+    rng = np.random.default_rng(3)
+    init = data[rng.choice(6000, 48, replace=False)].copy()
+    m_g, m_o = MET[metric]
+    c1, it1 = annb200.kmeans_lloyd(data, init, m_g, max_iters=1)
+    r1, rit1 = o.parallel_lloyd(data, init, m_o, max_iters=1)
+    assert it1 == rit1 == 1
+    np.testing.assert_allclose(c1, r1, rtol=2e-7, atol=1e-7)
+    c, it = annb200.kmeans_lloyd(data, init, m_g, max_iters=30)
+    r, rit = o.parallel_lloyd(data, init, m_o, max_iters=30)
+    assert it == rit and 1 < it <= 30
+    np.testing.assert_allclose(c, r, rtol=1e-5, atol=1e-5)
+    # the trained centroids are a fixed point up to the stop rule: one more assignment changes few points
+    cn = np.array([o.l2_norm_f32(x) for x in c], np.float32)
+    a = annb200.ivf_assign(data, c, m_g, cn if metric == "cosine" else None)
+    assert len(np.unique(a)) > 40
+
+
+def test_device_lloyd_edge_cases(gpu):
+    data = datagen.gaussian_noise(500, 8, seed=5)
+    # an initial centroid far from every point stays where it is (empty clusters keep their centroid)
+    init = np.concatenate([data[:3], np.full((1, 8), 1e3, np.float32)])
+    c, it = annb200.kmeans_lloyd(data, init, annb200.L2, max_iters=5)
+    assert np.array_equal(c[3], init[3]) and it >= 1
+    r, rit = o.parallel_lloyd(data, init, o.L2, max_iters=5)
+    assert it == rit
+    np.testing.assert_allclose(c, r, rtol=1e-5, atol=1e-5)
+    with pytest.raises(annb200.AnnSearchError) as e:          # TooFewSamplesForCentroids (k_means_utils.rs:2788-2793)
+        annb200.kmeans_lloyd(data[:3], data[:4], annb200.L2)
+    assert e.value.variant == "TooFewSamplesForCentroids"
+    with pytest.raises(annb200.AnnSearchError) as e:
+        annb200.kmeans_lloyd(data, data[:4], annb200.MANHATTAN)
+    assert e.value.variant == "DistanceNotSupported"

@@ -325,3 +325,22 @@ def test_mega_kernel_known_answer():
     assert d[0].tolist() == [1.0, 1.0, 3.0, 5.0, 10.0] and ids[0].tolist() == [0, 1, 2, 3, 4]
     ids, d, c, _, _ = o.ivf_search(ix, q[1:], 3, nprobe=1)
     assert c[0] == 3
+
+
+def test_parallel_lloyd_restatement_stop_rule_and_means():
+    """parallel_lloyd (k_means_utils.rs:1572-1700): convergence is tested before the update with a floor of
+    max(1, n / 10000) changed assignments; a non-empty cluster's centroid is the mean of its members; an empty
+    cluster keeps its centroid (:1657-1666)."""
+    rng = np.random.default_rng(0)
+    a = rng.normal(0.0, 0.1, (200, 4)).astype(np.float32)
+    b = rng.normal(5.0, 0.1, (300, 4)).astype(np.float32)
+    data = np.concatenate([a, b])
+    init = np.stack([data[0], data[250], np.full(4, 100.0, np.float32)])
+    cent, iters = o.parallel_lloyd(data, init, o.L2, max_iters=30)
+    # iteration 0 assigns and updates, iteration 1 sees no change and stops before updating: one update
+    assert iters == 1
+    np.testing.assert_allclose(cent[0], a.astype(np.float64).mean(0), rtol=1e-6)
+    np.testing.assert_allclose(cent[1], b.astype(np.float64).mean(0), rtol=1e-6)
+    assert np.array_equal(cent[2], init[2])
+    cent0, it0 = o.parallel_lloyd(data, init, o.L2, max_iters=0)
+    assert it0 == 0 and np.array_equal(cent0, init)
