@@ -204,4 +204,15 @@ inline KnnResult query_ivf_index_gpu_self(const IvfIndexB200& index, size_t k, s
     return index.generate_knn(k, nprobe, return_dist);
 }
 
+// Lloyd loop of train_centroids on the device (src/utils/k_means_utils.rs:1572-1700, unbalanced parallel_lloyd) from the
+// caller's initial centroids [n_centroids * dim]; returns the trained centroids, *iters (optional) = updates performed.
+inline std::vector<float> kmeans_lloyd(const MatRef& train, std::vector<float> centroids, size_t n_centroids, const std::string& dist_metric,
+                                       size_t max_iters = 30, uint32_t* iters = nullptr, int device = 0) {
+    const std::vector<float> flat = matrix_to_flat(train);
+    if (centroids.size() != n_centroids * train.ncols) throw AnnSearchError(ANNB_ERR_DIMENSION_MISMATCH, "centroids must be n_centroids x dim");
+    check(annb_kmeans_lloyd(flat.data(), train.nrows, static_cast<uint32_t>(train.ncols), centroids.data(), static_cast<uint32_t>(n_centroids),
+                            metric_or_default(dist_metric), static_cast<uint32_t>(max_iters), iters, device));
+    return centroids;
+}
+
 }  // namespace annb200
