@@ -470,7 +470,9 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         // scratch: cnt | cursor | pair_off | task_off | task_counter | pairs
         const size_t nl = ix->nlist;
         const size_t hdr = (4 * (nl + 1) + 4) * sizeof(uint32_t);
-        ANNB_TRY(ix->s_pairs.ensure(hdr + slots * sizeof(uint2)));
+        const uint64_t max_tasks_tc = ceil_div<uint64_t>(slots, 128) + n_local_lists;
+        const size_t pairs_bytes = round_up<size_t>(slots * sizeof(uint2), 16);
+        ANNB_TRY(ix->s_pairs.ensure(hdr + pairs_bytes + (use_tc ? max_tasks_tc * 32 : 0)));
         uint32_t* w = ix->s_pairs.as<uint32_t>();
         ANNB_CUDA_CHECK(cudaMemsetAsync(w, 0, hdr, s));
         PairParams pp{};
@@ -479,6 +481,8 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         pp.cnt = w; pp.cursor = w + (nl + 1); pp.pair_off = w + 2 * (nl + 1); pp.task_off = w + 3 * (nl + 1); pp.task_counter = w + 4 * (nl + 1);
         pp.pairs = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(w) + hdr);
         pp.group = use_tc ? 128u : static_cast<uint32_t>(CTA_QUERIES);
+        pp.tasks = use_tc ? reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(w) + hdr + pairs_bytes) : nullptr;
+        pp.offsets = ix->d_offsets; pp.shard_row0 = ix->shard_row0;
         const uint32_t g = static_cast<uint32_t>(ceil_div<uint64_t>(slots, 256));
         ivf_count_pairs_kernel<<<g, 256, 0, s>>>(pp);
         ivf_pair_offsets_kernel<<<1, 1024, 0, s>>>(pp);
@@ -486,9 +490,8 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         ANNB_CUDA_CHECK(cudaGetLastError());
         ix->stat_launches += 3;
         if (use_tc) {
-            const uint64_t max_tasks_tc = ceil_div<uint64_t>(slots, 128) + n_local_lists;
             ANNB_TRY(tc_ivf_scan(ix, pq.scan, pq.scan_bytes, nq, kk, k, pitch, pp.pair_off, pp.task_off, pp.pairs, pp.task_counter, max_tasks_tc,
-                                 d_nprobes, row_map, d_ids, d_dist, d_cnt, s));
+                                 d_nprobes, row_map, d_ids, d_dist, d_cnt, s, pp.tasks));
             uint32_t n_unc = 0;
             ANNB_TRY(read_uncertified(ix, &n_unc, s));
             if (n_unc == 0 || row_map != nullptr) return ANNB_OK;

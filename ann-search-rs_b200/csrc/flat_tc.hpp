@@ -23,7 +23,8 @@ void tc_ivf_destroy(annb_index* ix);
 bool tc_ivf_supported(const annb_index* ix, int qt, uint32_t k_eff);
 int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t nq, uint32_t k_eff, uint32_t k_out, uint32_t probe_pitch,
                 const uint32_t* d_pair_off, const uint32_t* d_task_off, const void* d_pairs, uint32_t* d_task_counter, uint64_t max_tasks,
-                const uint32_t* d_n_probes, const uint64_t* row_map, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s);
+                const uint32_t* d_n_probes, const uint64_t* row_map, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s,
+                const void* d_tasks);
 // Tensor-core centroid ranking of an IVF index: dense approximate values (DENSE mode of the flat kernel) + per-query
 // radix select, exact re-computation and certification of the `pitch` nearest cells.
 int tc_coarse_prepare(annb_index* ix);

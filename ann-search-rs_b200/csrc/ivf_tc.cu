@@ -35,6 +35,7 @@ struct IvfTcParams {
     const uint32_t* pair_off;
     const uint32_t* task_off;  // prefix sum of ceil(pairs per list / 128)
     const uint2* pairs;        // (query, rank) grouped by list
+    const uint4* tasks;        // [2 * n_tasks] task records written by ivf_pair_offsets_kernel
     uint32_t* task_counter;
     uint32_t probe_pitch;
     uint64_t* part_keys;       // [nq][probe_pitch][2][KP]
@@ -117,19 +118,13 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
         if (threadIdx.x == 0) {
             const uint32_t task = atomicAdd(p.task_counter, 1u);
             if (task < total_tasks) {
-                uint32_t lo = 0, hi = p.nlist;
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (p.task_off[mid] <= task) lo = mid; else hi = mid;
-                }
-                const uint32_t g = task - p.task_off[lo];
-                const uint32_t pair0 = p.pair_off[lo] + g * BM;
-                s_task[0] = lo;
-                s_task[1] = pair0;
-                s_task[2] = min(static_cast<uint32_t>(BM), p.pair_off[lo + 1] - pair0);
+                const uint4 a = __ldg(p.tasks + 2 * static_cast<size_t>(task)), b = __ldg(p.tasks + 2 * static_cast<size_t>(task) + 1);
+                s_task[0] = a.x;
+                s_task[1] = a.y;
+                s_task[2] = a.z;
                 s_task[3] = 1;
-                s_rows[0] = p.offsets[lo] - p.shard_row0;
-                s_rows[1] = p.offsets[lo + 1] - p.shard_row0;
+                s_rows[0] = static_cast<uint64_t>(b.x) | (static_cast<uint64_t>(b.y) << 32);
+                s_rows[1] = static_cast<uint64_t>(b.z) | (static_cast<uint64_t>(b.w) << 32);
             } else {
                 s_task[3] = 0;
             }
@@ -509,7 +504,8 @@ static int launch_ivf_rerank(const tc::RerankParams& r, cudaStream_t s) {
 // Scan + exact re-rank.  The pair buckets (grouped by list, 128 pairs per task) were built by the caller.
 int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t nq, uint32_t k_eff, uint32_t k_out, uint32_t probe_pitch,
                 const uint32_t* d_pair_off, const uint32_t* d_task_off, const void* d_pairs, uint32_t* d_task_counter, uint64_t max_tasks,
-                const uint32_t* d_n_probes, const uint64_t* row_map, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s) {
+                const uint32_t* d_n_probes, const uint64_t* row_map, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s,
+                const void* d_tasks) {
     IvfTcState* st = ix->tc_ivf;
     const uint32_t kprime = tc_ivf_kprime(ix, k_eff);
     const uint32_t nb = st->kind == tc::KIND_TF32X3 ? 2 : 1;
@@ -526,7 +522,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     tc::IvfTcParams p{};
     p.queries = d_q; p.q_bytes = q_bytes; p.dim = ix->dim; p.nslab = st->nslab; p.n_stages = stages; p.n_pad = st->n_pad; p.aux = st->d_aux;
     p.offsets = ix->d_offsets; p.shard_row0 = ix->shard_row0; p.nlist = ix->nlist; p.pair_off = d_pair_off; p.task_off = d_task_off;
-    p.pairs = static_cast<const uint2*>(d_pairs); p.task_counter = d_task_counter; p.probe_pitch = probe_pitch;
+    p.pairs = static_cast<const uint2*>(d_pairs); p.tasks = static_cast<const uint4*>(d_tasks); p.task_counter = d_task_counter; p.probe_pitch = probe_pitch;
     p.part_keys = st->part.as<uint64_t>(); p.gtau = st->gtau.as<uint32_t>(); p.dbg = st->dbgc.as<unsigned long long>();
     const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(max_tasks, 1), 148));
     {

@@ -385,6 +385,9 @@ struct PairParams {
     uint32_t group;            // queries per task (32 for the CUDA-core kernel, 128 for the tensor-core kernel)
     uint2* pairs;              // [sum cnt] (query, rank) grouped by list
     uint32_t* task_counter;    // persistent-CTA work counter (zeroed by the caller)
+    uint4* tasks;              // optional [2 * n_tasks]: ready-made task records {list, pair0, pairs in group, 0} {row begin, row end (u64 each)}
+    const uint64_t* offsets;   // global CSR offsets (task records)
+    uint64_t shard_row0;
 };
 
 __global__ void ivf_count_pairs_kernel(PairParams p) {
@@ -417,7 +420,15 @@ __global__ void __launch_bounds__(1024) ivf_pair_offsets_kernel(PairParams p) {
     b = s_tasks[threadIdx.x];
     for (uint32_t c = lo; c < hi; c++) {
         p.pair_off[c] = a; p.cursor[c] = a; p.task_off[c] = b;
-        a += p.cnt[c]; b += (p.cnt[c] + p.group - 1) / p.group;
+        const uint32_t nt = (p.cnt[c] + p.group - 1) / p.group;
+        if (p.tasks != nullptr) {   // one record per task, so the scan kernel fetches a task with a single round trip
+            const uint64_t rb = p.offsets[c] - p.shard_row0, re = p.offsets[c + 1] - p.shard_row0;
+            for (uint32_t g = 0; g < nt; g++) {
+                p.tasks[2 * (b + g)] = make_uint4(c, a + g * p.group, min(p.group, p.cnt[c] - g * p.group), 0u);
+                p.tasks[2 * (b + g) + 1] = make_uint4(static_cast<uint32_t>(rb), static_cast<uint32_t>(rb >> 32), static_cast<uint32_t>(re), static_cast<uint32_t>(re >> 32));
+            }
+        }
+        a += p.cnt[c]; b += nt;
     }
 }
 __global__ void ivf_fill_pairs_kernel(PairParams p) {
