@@ -23,8 +23,10 @@ namespace annb {
 namespace tc {
 
 struct IvfTcParams {
-    const uint8_t* queries;   // prepared scan queries: f32 rows (q_bytes pitch)
+    const uint8_t* queries;   // prepared scan queries: f32 rows / int8 codes (q_bytes pitch)
     uint32_t q_bytes;
+    const void* q_op;         // f32 / bf16 lists: the batch's queries pre-split into operand pieces, [pieces][nq][kp] (tf32 hi, lo / bf16 q0, q1, q2)
+    uint64_t nq;
     uint32_t dim;
     uint32_t nslab, n_stages;
     uint32_t n_pad;           // rows per piece of the stacked database operand
@@ -247,50 +249,37 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                         }
                     }
                 } else if (KIND == KIND_TF32X3) {
-                    // half 0 writes hi = rna_tf32(q) at columns [0,128), half 1 writes lo = rna_tf32(q - hi) at [128,256)
+                    // pieces were split once per batch (split_tf32_kernel): half 0 copies hi to columns [0,128), half 1 lo to [128,256)
+                    const uint4* src = reinterpret_cast<const uint4*>(static_cast<const float*>(p.q_op) + (static_cast<uint64_t>(half) * p.nq + (has_query ? pr.x : 0)) * kp);
                     const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + half * PIECE_COLS;
                     for (uint32_t c = 0; c < kp; c += 32) {
                         uint32_t w[32];
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-                            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (has_query && c + 4 * j < p.dim) x = __ldg(reinterpret_cast<const float4*>(qrow + c) + j);   // rows are zero padded to 16 B
-                            float v[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                            for (int e = 0; e < 4; e++) {
-                                const float hi = rna_tf32(v[e]);
-                                w[4 * j + e] = __float_as_uint(half == 0 ? hi : rna_tf32(__fsub_rn(v[e], hi)));
-                            }
+                            uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                            if (has_query) x = __ldg(src + c / 4 + j);
+                            w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
                         }
                         tmem_st32(tq + c, w);
                     }
                 } else {
-                    // bf16 terms q0 (half 0), q1 (half 1), q2 (half 0) at columns [0,64), [64,128), [128,192); two elements per column
-                    for (uint32_t pc = half; pc < 3; pc += 2) {
-                        const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + pc * PIECE_COLS;
-                        for (uint32_t c = 0; c < kp / 2; c += 32) {       // c counts 32-bit columns = element pairs
-                            uint32_t w[32];
+                    // bf16 terms q0, q1, q2 (split once per batch) at columns [0,64), [64,128), [128,192), two elements per column:
+                    // half 0 copies q0 and the even 32-column chunks of q2, half 1 copies q1 and the odd chunks of q2
+                    const uint32_t row_words = kp / 2;
+                    auto copy_chunk = [&](uint32_t pc, uint32_t c) {
+                        const uint4* src = reinterpret_cast<const uint4*>(static_cast<const uint32_t*>(p.q_op) +
+                                                                          (static_cast<uint64_t>(pc) * p.nq + (has_query ? pr.x : 0)) * row_words + c);
+                        uint32_t w[32];
 #pragma unroll
-                            for (int j = 0; j < 16; j++) {
-                                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                                if (has_query && 2 * c + 4 * j < p.dim) x = __ldg(reinterpret_cast<const float4*>(qrow + 2 * c) + j);
-                                float v[4] = {x.x, x.y, x.z, x.w};
-                                uint32_t b[4];
-#pragma unroll
-                                for (int e = 0; e < 4; e++) {
-                                    const __nv_bfloat16 b0 = __float2bfloat16_rn(v[e]);
-                                    const float r1 = __fsub_rn(v[e], __bfloat162float(b0));
-                                    const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
-                                    const __nv_bfloat16 b2 = __float2bfloat16_rn(__fsub_rn(r1, __bfloat162float(b1)));
-                                    const __nv_bfloat16 sel = pc == 0 ? b0 : (pc == 1 ? b1 : b2);
-                                    b[e] = static_cast<uint32_t>(__bfloat16_as_ushort(sel));
-                                }
-                                w[2 * j] = b[0] | (b[1] << 16);
-                                w[2 * j + 1] = b[2] | (b[3] << 16);
-                            }
-                            tmem_st32(tq + c, w);
+                        for (int j = 0; j < 8; j++) {
+                            uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                            if (has_query) x = __ldg(src + j);
+                            w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
                         }
-                    }
+                        tmem_st32(tmem_base + ((quarter * 32u) << 16) + pc * PIECE_COLS + c, w);
+                    };
+                    for (uint32_t c = 0; c < row_words; c += 32) copy_chunk(half, c);
+                    for (uint32_t c = half * 32; c < row_words; c += 64) copy_chunk(2, c);
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -393,7 +382,7 @@ struct IvfTcState {
     void* d_x = nullptr;
     float* d_aux = nullptr;
     CUtensorMap tm_x;
-    DevBuf part, gtau, dbgc;
+    DevBuf part, gtau, dbgc, q_op;
     uint64_t bytes = 0;
 };
 
@@ -447,6 +436,7 @@ void tc_ivf_destroy(annb_index* ix) {
     ix->tc_ivf->part.release();
     ix->tc_ivf->gtau.release();
     ix->tc_ivf->dbgc.release();
+    ix->tc_ivf->q_op.release();
     delete ix->tc_ivf;
     ix->tc_ivf = nullptr;
 }
@@ -519,7 +509,21 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     ANNB_TRY(st->gtau.ensure(nq * 4 + 16));
     ANNB_CUDA_CHECK(cudaMemsetAsync(st->gtau.p, 0xFF, nq * 4 + 16, s));
     const bool l2 = ix->metric == ANNB_L2;
+    // operand pieces of the batch's queries, split once (every query is gathered once per probed list)
+    const uint32_t kp_q = st->kp_elems;
+    if (st->kind == tc::KIND_TF32X3) {
+        ANNB_TRY(st->q_op.ensure(2ull * nq * kp_q * 4));
+        tc::split_tf32_kernel<<<tc_blocks_for(nq * kp_q), 256, 0, s>>>(reinterpret_cast<const float*>(d_q), q_bytes / 4, ix->dim, nq, nq, kp_q, st->q_op.as<float>());
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        ix->stat_launches++;
+    } else if (st->kind == tc::KIND_BF16) {
+        ANNB_TRY(st->q_op.ensure(3ull * nq * kp_q * 2));
+        tc::split_bf16x3_kernel<<<tc_blocks_for(nq * kp_q), 256, 0, s>>>(reinterpret_cast<const float*>(d_q), q_bytes / 4, ix->dim, nq, nq, kp_q, st->q_op.as<__nv_bfloat16>());
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        ix->stat_launches++;
+    }
     tc::IvfTcParams p{};
+    p.q_op = st->q_op.p; p.nq = nq;
     p.queries = d_q; p.q_bytes = q_bytes; p.dim = ix->dim; p.nslab = st->nslab; p.n_stages = stages; p.n_pad = st->n_pad; p.aux = st->d_aux;
     p.offsets = ix->d_offsets; p.shard_row0 = ix->shard_row0; p.nlist = ix->nlist; p.pair_off = d_pair_off; p.task_off = d_task_off;
     p.pairs = static_cast<const uint2*>(d_pairs); p.tasks = static_cast<const uint4*>(d_tasks); p.task_counter = d_task_counter; p.probe_pitch = probe_pitch;
