@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     const uint32_t total = parts_q * p.kp;
     const uint32_t nsort = min(p.nsort, next_pow2(max(total, 64u)));
     const uint64_t* src = p.part_keys + q * (static_cast<uint64_t>(p.parts) * p.kp);
+    uint32_t n_cand = 0;   // candidates in keys[] after compaction (gtau path)
     if (p.gtau != nullptr) {
         // Only keys at or below the query's shared pruning threshold can be among the k' best of the merged lists (the
         // threshold is some single list's k'-th value): compact those -- typically a few dozen of the parts * k' slots --
@@ -448,6 +449,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         }
         __syncthreads();
         const uint32_t n = s_n;
+        n_cand = n;
         const uint32_t nsort2 = min(nsort, next_pow2(max(n, 64u)));
         for (uint32_t i = n + threadIdx.x; i < nsort2; i += blockDim.x) keys[i] = KEY_SENTINEL;
         __syncthreads();
@@ -458,66 +460,82 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         bitonic_sort_keys<true>(keys, nsort, threadIdx.x, blockDim.x);
     }
     const uint64_t orow = p.row_map ? p.row_map[q] : q;
-    if (threadIdx.x < 64) {
-        uint64_t ek = KEY_SENTINEL;
-        if (threadIdx.x < p.kp) {
-            const uint64_t key = keys[threadIdx.x];
-            const uint32_t idx = key_idx(key);
-            if (idx != IDX_INVALID) {
-                const uint8_t* row = p.rows + static_cast<uint64_t>(idx) * p.row_bytes;
-                const uint8_t* qv = p.queries + q * p.q_bytes;
-                if constexpr (RT == 2) {
-                    // SQ8: exact code-space distance (src/utils/dist.rs:5015-5077)
-                    int32_t dot[1], xx, qs = 0;
-                    accumulate_i8<1>(row, qv, p.q_bytes, p.dim, dot, xx);
-                    for (uint32_t e = 0; e < p.dim; e++) {
-                        const int32_t v = reinterpret_cast<const int8_t*>(qv)[e];
-                        qs += v * v;
-                    }
-                    ek = make_key(finish_i8<MET>(dot[0], xx, qs, (MET == MET_COS) ? p.row_norms_i[idx] : 0), idx);
-                } else {
-                    float raw[1];
-                    accumulate_fp<(RT == 0) ? 4 : 2, (QT == QT_F32) ? 4 : 2, MET == MET_L2, 1>(row, qv, p.q_bytes, p.dim, raw);
-                    float qn = 1.0f, xn = 1.0f;
-                    if (MET == MET_COS) {
-                        qn = seq_norm<(QT == QT_F32) ? 4 : 2>(qv, p.dim);
-                        if (p.bf16_self) qn = round_to_bf16(qn);
-                        xn = p.row_norms[idx];
-                    }
-                    ek = make_key(finish_fp<MET>(raw[0], qn, xn), idx);
-                }
+    const uint8_t* qv = p.queries + q * p.q_bytes;
+    // exact distance of a candidate in the reference's arithmetic
+    auto exact_of = [&](uint64_t key) -> uint64_t {
+        const uint32_t idx = key_idx(key);
+        if (idx == IDX_INVALID) return KEY_SENTINEL;
+        const uint8_t* row = p.rows + static_cast<uint64_t>(idx) * p.row_bytes;
+        if constexpr (RT == 2) {
+            // SQ8: exact code-space distance (src/utils/dist.rs:5015-5077)
+            int32_t dot[1], xx, qs = 0;
+            accumulate_i8<1>(row, qv, p.q_bytes, p.dim, dot, xx);
+            for (uint32_t e = 0; e < p.dim; e++) {
+                const int32_t v = reinterpret_cast<const int8_t*>(qv)[e];
+                qs += v * v;
             }
+            return make_key(finish_i8<MET>(dot[0], xx, qs, (MET == MET_COS) ? p.row_norms_i[idx] : 0), idx);
+        } else {
+            float raw[1];
+            accumulate_fp<(RT == 0) ? 4 : 2, (QT == QT_F32) ? 4 : 2, MET == MET_L2, 1>(row, qv, p.q_bytes, p.dim, raw);
+            float qn = 1.0f, xn = 1.0f;
+            if (MET == MET_COS) {
+                qn = seq_norm<(QT == QT_F32) ? 4 : 2>(qv, p.dim);
+                if (p.bf16_self) qn = round_to_bf16(qn);
+                xn = p.row_norms[idx];
+            }
+            return make_key(finish_fp<MET>(raw[0], qn, xn), idx);
         }
-        exact[threadIdx.x] = ek;
-    }
+    };
+    // coverage test: every row that was not re-ranked has an approximate value >= a_thr; is the k-th exact distance safely below?
+    auto covered = [&](float a_thr, float dk) -> bool {
+        float qn2 = 0.f;
+        for (uint32_t e = 0; e < p.dim; e++) {
+            float x;
+            if constexpr (QT == QT_I8) x = static_cast<float>(reinterpret_cast<const int8_t*>(qv)[e]);
+            else x = load1<(QT == QT_F32) ? 4 : 2>(qv, e);
+            qn2 = fmaf(x, x, qn2);
+        }
+        if (MET == MET_L2) {
+            // approx value = |x|^2 - 2 q.x = dist - |q|^2 ; error <= eps * (|q| + |x|max)^2
+            const float s = sqrtf(qn2) + p.xnorm_max;
+            return (a_thr + qn2 - p.cert_eps * s * s) > dk;
+        }
+        // approx value = -q.x / |x| = (dist - 1) * |q| ; error <= eps * |q|
+        const float qn = sqrtf(qn2);
+        return qn > 0.f ? ((a_thr / qn + 1.0f - p.cert_eps) > dk) : true;
+    };
+    __shared__ int s_extend;
+    if (threadIdx.x < 64) exact[threadIdx.x] = (threadIdx.x < p.kp) ? exact_of(keys[threadIdx.x]) : KEY_SENTINEL;
+    if (threadIdx.x == 0) s_extend = 0;
     __syncthreads();
     if (threadIdx.x < 32) bitonic_sort_keys<false>(exact, 64, threadIdx.x, 32);
     __syncthreads();
-    if (threadIdx.x == 0 && p.uncert_count != nullptr && p.cert_eps > 0.f) {
+    const bool certify = p.uncert_count != nullptr && p.cert_eps > 0.f;
+    if (threadIdx.x == 0 && certify) {
         const uint64_t a_key = keys[p.kp - 1];                       // k'-th merged approximate key (sentinel: every row was re-ranked)
         const uint64_t d_key = exact[p.k_eff - 1];                   // k-th exact key (sentinel: fewer than k rows exist)
-        bool certified = true;
-        if (key_idx(a_key) != IDX_INVALID && key_idx(d_key) != IDX_INVALID) {
-            const uint8_t* qv = p.queries + q * p.q_bytes;
-            float qn2 = 0.f;
-            for (uint32_t e = 0; e < p.dim; e++) {
-                float x;
-                if constexpr (QT == QT_I8) x = static_cast<float>(reinterpret_cast<const int8_t*>(qv)[e]);
-                else x = load1<(QT == QT_F32) ? 4 : 2>(qv, e);
-                qn2 = fmaf(x, x, qn2);
-            }
-            const float a_thr = key_dist(a_key), dk = key_dist(d_key);
-            if (MET == MET_L2) {
-                // approx value = |x|^2 - 2 q.x = dist - |q|^2 ; error <= eps * (|q| + |x|max)^2
-                const float s = sqrtf(qn2) + p.xnorm_max;
-                certified = (a_thr + qn2 - p.cert_eps * s * s) > dk;
-            } else {
-                // approx value = -q.x / |x| = (dist - 1) * |q| ; error <= eps * |q|
-                const float qn = sqrtf(qn2);
-                certified = qn > 0.f ? ((a_thr / qn + 1.0f - p.cert_eps) > dk) : true;
-            }
+        if (key_idx(a_key) != IDX_INVALID && key_idx(d_key) != IDX_INVALID && !covered(key_dist(a_key), key_dist(d_key))) {
+            // Second chance before the exact fallback: the compacted candidate set holds every scanned row whose value is
+            // at or below the query's final pruning threshold G (every rejected row is >= G, which is usually well above
+            // the k'-th merged value).  Re-rank up to 64 of them and test against G (or the 65th value).
+            if (p.gtau != nullptr && n_cand > p.kp) s_extend = 1;
+            else p.uncert_list[atomicAdd(p.uncert_count, 1u)] = static_cast<uint32_t>(q);
         }
-        if (!certified) p.uncert_list[atomicAdd(p.uncert_count, 1u)] = static_cast<uint32_t>(q);
+    }
+    __syncthreads();
+    if (s_extend) {
+        if (threadIdx.x < 64) exact[threadIdx.x] = (threadIdx.x < n_cand) ? exact_of(keys[threadIdx.x]) : KEY_SENTINEL;
+        __syncthreads();
+        if (threadIdx.x < 32) bitonic_sort_keys<false>(exact, 64, threadIdx.x, 32);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint64_t d_key = exact[p.k_eff - 1];
+            bool ok = true;
+            if (n_cand > 64) ok = covered(key_dist(keys[64]), key_dist(d_key));
+            else if (p.gtau[q] != 0xFFFFFFFFu) ok = covered(ordered_to_f32(p.gtau[q]), key_dist(d_key));   // 0xFFFFFFFF: nothing was ever pruned
+            if (!ok) p.uncert_list[atomicAdd(p.uncert_count, 1u)] = static_cast<uint32_t>(q);
+        }
     }
     uint32_t valid = 0;
     for (uint32_t j = threadIdx.x; j < p.k_out; j += blockDim.x) {
