@@ -54,6 +54,7 @@ def parse_args():
                     help="IVF workload: generate data and build the index on the GPU (auto: when n > 2M)")
     ap.add_argument("--kmeans-iters", type=int, default=8)
     ap.add_argument("--tc-candidates", type=int, default=0, choices=[0, 16, 32], help="k' of the tensor-core pre-selection (0 = library default)")
+    ap.add_argument("--cert-eps-log2", type=int, default=0, help="log2 of the certificate's error bound (0 = library default)")
     return ap.parse_args()
 
 
@@ -270,6 +271,8 @@ def run_b200(args):
     index.set_option("path", path)
     if args.tc_candidates:
         index.set_option("tc_candidates", args.tc_candidates)
+    if args.cert_eps_log2:
+        index.set_option("cert_eps_log2", args.cert_eps_log2)
     index.set_option("time_kernels", 1)
 
     dq = torch.from_numpy(queries).to(dev)

@@ -207,7 +207,7 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
  *               "time_kernels" (1 = bracket the dominant kernel of every search with CUDA events on its stream),
  *               "tc_ts" (tensor paths: 1 = query operand resident in TMEM), "ivf_fast_probe" (0/1/2),
  *               "ivf_tc_coarse" (1 = rank the centroids on the tensor cores when nlist >= 512, 0 = CUDA-core ranking only),
- *               "cert_eps_log2" (error bound assumed by the coverage certificate of the tensor paths, default -20; 0 = off),
+ *               "cert_eps_log2" (error bound assumed by the coverage certificate of the tensor paths, default -19; 0 = off),
  *               "cert_fallback" (1 = queries that fail the certificate are recomputed on the exact CUDA-core path)
  *   get_stat  : "kernel_launches" (cumulative), "scanned_vectors" (IVF, last call: sum of probed
  *               list lengths), "scanned_vectors_local" (the part of it that lies in this handle's own lists),

@@ -140,3 +140,19 @@ def test_bf16_wide_rows_use_the_smem_query_operand(gpu):
     assert g.get_stat("last_path") == annb200.PATH_TENSOR
     ref = o.flat_search(c, q, 10)
     assert_exact(ids, d, ref[0], ref[1], "bf16 dim 200")
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_second_chance_certificate(gpu, dtype):
+    """Correlated data, L2: row norms dwarf the neighbour gaps, so with a conservative bound nearly every query fails the
+    first coverage test (k'-th merged value).  The second test -- all candidates below the scan's final pruning
+    threshold re-ranked, bound = that threshold -- must certify (almost) all of them, and results stay exact."""
+    data = datagen.correlated(60_000, 128, seed=37)
+    q = datagen.subsample_with_noise(data, 500, seed=37)
+    g, c = _pair(data, dtype, "l2")
+    ref = o.flat_search(c, q, 10)
+    for e in (-18, -19):
+        g.set_option("cert_eps_log2", e)
+        ids, d, _ = g.query_batch(q, 10)
+        assert g.get_stat("uncertified") <= 5, (e, g.get_stat("uncertified"))
+        assert_exact(ids, d, ref[0], ref[1], f"second chance {dtype} eps=2^{e}")
