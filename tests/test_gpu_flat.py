@@ -141,3 +141,20 @@ def test_cpp_host_mirror_on_gpu(gpu):
     from test_abi import _build_cpp_mirror_test
     r = subprocess.run([_build_cpp_mirror_test()], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.strip() == "OK gpu", r.stdout + r.stderr
+
+
+def test_host_entry_batches_large_query_sets(gpu):
+    """The host-buffer entry points walk the queries in internal batches of 16384: a 20 000-query call must equal the
+    oracle row for row (flat tensor path and IVF list-major path)."""
+    data = datagen.gaussian_noise(5000, 16, seed=91)
+    q = datagen.subsample_with_noise(np.repeat(data, 4, axis=0), 20000, seed=91)
+    g, c = _pair(data, "f32", "l2")
+    ids, d, cnt = g.query_batch(q, 10)
+    rids, rd, rcnt = o.flat_search(c, q, 10)
+    assert_exact(ids, d, rids, rd, "flat, 20000 queries")
+    ci = o.build_ivf(data, o.L2, nlist=64, kmeans_iters=4)
+    gi = annb200.IvfIndexB200.from_parts(ci.vectors, ci.centroids, ci.offsets, ci.original_ids, ci.dtype, ci.metric)
+    got = gi.query_batch(q, 10, nprobe=8)
+    ref = o.ivf_search(ci, q, 10, nprobe=8)
+    assert_exact(got[0], got[1], ref[0], ref[1], "ivf, 20000 queries")
+    assert gi.get_stat("scanned_vectors") == int(ref[4].sum())
