@@ -323,11 +323,14 @@ static int flat_simt(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uin
 // ---------------------------------------------------------------------------
 // IVF search core
 // ---------------------------------------------------------------------------
+struct RouteOut { uint32_t* probes; uint32_t* n_probes; uint32_t pitch; };
 static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint32_t nprobe, const uint64_t* row_map,
                     uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s, bool force_simt = false,
-                    const uint32_t* preset_probes = nullptr, const uint32_t* preset_nprobes = nullptr, uint32_t preset_pitch = 0) {
+                    const uint32_t* preset_probes = nullptr, const uint32_t* preset_nprobes = nullptr, uint32_t preset_pitch = 0,
+                    const RouteOut* route_out = nullptr) {
     // preset_*: probe lists already computed for these queries (the exact fallback of the tensor path re-uses the
-    // parent call's ranking instead of ranking the centroids again)
+    // parent call's ranking instead of ranking the centroids again; sharded searches route a slice of the batch per rank).
+    // route_out: stop after the routing stage and export the probe lists.
     const uint32_t kk = static_cast<uint32_t>(std::min<uint64_t>(k, ix->n_total));
     if (kk == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "k must be >= 1");
     if (kk > 1024) return fail(ANNB_ERR_UNSUPPORTED, "k > 1024 is not supported");
@@ -448,6 +451,18 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
     }
     const uint32_t* d_probes = preset_probes ? preset_probes : ix->s_probes.as<uint32_t>();
     const uint32_t* d_nprobes = preset_probes ? preset_nprobes : ix->s_nprobes.as<uint32_t>();
+    if (route_out != nullptr) {
+        ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 4, s));
+        export_probes_kernel<<<grid_for(nq * route_out->pitch, 256, 1u << 30), 256, 0, s>>>(d_probes, pitch, d_nprobes, nq, route_out->probes, route_out->pitch,
+                                                                                      route_out->n_probes, ix->s_flags.as<uint32_t>());
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        ix->stat_launches++;
+        uint32_t over = 0;
+        ANNB_CUDA_CHECK(cudaMemcpyAsync(&over, ix->s_flags.p, 4, cudaMemcpyDeviceToHost, s));
+        ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (over) return fail(ANNB_ERR_UNSUPPORTED, "a query needs more probed lists than the caller's probe pitch");
+        return ANNB_OK;
+    }
     // 3. list scan.  A batch that probes every list many times goes list-major (one staged list tile serves up to 32
     //    queries); small batches keep the query-major streaming kernel (one warp per query part).
     const uint64_t n_local_lists = std::max<uint32_t>(1, ix->list_end - ix->list_begin);
@@ -1039,6 +1054,47 @@ int annb_ivf_search_dev(const annb_index* index, const float* d_queries, uint64_
         ANNB_TRY(ivf_core(ix, pq, nb, k, nprobe, nullptr, d_out_ids + b0 * k, d_out_dist ? d_out_dist + b0 * k : nullptr,
                           d_out_counts ? d_out_counts + b0 : nullptr, s));
     }
+    return ANNB_OK;
+}
+
+int annb_ivf_route_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,
+                       uint32_t* d_probes, uint32_t* d_n_probes, uint32_t probe_pitch, void* stream) {
+    annb_index* ix = const_cast<annb_index*>(index);
+    if (!ix || !ix->is_ivf) return fail(ANNB_ERR_INVALID_ARGUMENT, "not an IVF index");
+    if (dim != ix->dim) return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(ix->dim));
+    if (!d_queries || !d_probes || !d_n_probes || k == 0 || probe_pitch == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / k == 0 / zero pitch");
+    ANNB_DEVICE(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
+        const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
+        PreparedQueries pq;
+        ANNB_TRY(prepare_external(ix, d_queries + b0 * dim, nb, &pq, s));
+        RouteOut ro{d_probes + b0 * probe_pitch, d_n_probes + b0, probe_pitch};
+        ANNB_TRY(ivf_core(ix, pq, nb, k, nprobe, nullptr, nullptr, nullptr, nullptr, s, false, nullptr, nullptr, 0, &ro));
+    }
+    return ANNB_OK;
+}
+
+int annb_ivf_search_probes_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,
+                               const uint32_t* d_probes, const uint32_t* d_n_probes, uint32_t probe_pitch, uint64_t* d_out_ids, float* d_out_dist,
+                               uint32_t* d_out_counts, void* stream) {
+    annb_index* ix = const_cast<annb_index*>(index);
+    if (!ix || !ix->is_ivf) return fail(ANNB_ERR_INVALID_ARGUMENT, "not an IVF index");
+    if (dim != ix->dim) return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(ix->dim));
+    if (!d_queries || !d_probes || !d_n_probes || !d_out_ids || k == 0 || probe_pitch == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / k == 0 / zero pitch");
+    ANNB_DEVICE(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
+        const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
+        PreparedQueries pq;
+        ANNB_TRY(prepare_external(ix, d_queries + b0 * dim, nb, &pq, s));
+        ix->skip_next_ivf_stats = true;   // no routing ran in this call
+        ANNB_TRY(ivf_core(ix, pq, nb, k, nprobe, nullptr, d_out_ids + b0 * k, d_out_dist ? d_out_dist + b0 * k : nullptr,
+                          d_out_counts ? d_out_counts + b0 : nullptr, s, false, d_probes + b0 * probe_pitch, d_n_probes + b0, probe_pitch));
+    }
+    ix->skip_next_ivf_stats = false;
     return ANNB_OK;
 }
 

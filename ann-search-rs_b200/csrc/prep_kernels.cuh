@@ -148,6 +148,20 @@ __global__ void gather_u32_rows_kernel(const uint32_t* __restrict__ src, uint32_
     const uint64_t r = i / ld;
     dst[i] = src[static_cast<uint64_t>(list[r]) * ld + (i - r * ld)];
 }
+// Probe lists [nq][src_pitch] -> caller layout [nq][dst_pitch]; flags a query whose list does not fit.
+__global__ void export_probes_kernel(const uint32_t* __restrict__ probes, uint32_t src_pitch, const uint32_t* __restrict__ n_probes, uint64_t nq,
+                                     uint32_t* __restrict__ out_probes, uint32_t dst_pitch, uint32_t* __restrict__ out_n, uint32_t* __restrict__ overflow) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= nq * dst_pitch) return;
+    const uint64_t q = i / dst_pitch;
+    const uint32_t r = static_cast<uint32_t>(i - q * dst_pitch);
+    const uint32_t np = n_probes[q];
+    out_probes[i] = (r < np && r < src_pitch) ? probes[q * src_pitch + r] : 0xFFFFFFFFu;
+    if (r == 0) {
+        out_n[q] = min(np, dst_pitch);
+        if (np > dst_pitch) atomicExch(overflow, 1u);
+    }
+}
 __global__ void scatter_results_kernel(const uint32_t* __restrict__ list, uint32_t count, uint32_t k, const uint64_t* __restrict__ ids,
                                        const float* __restrict__ dist, const uint32_t* __restrict__ cnt, uint64_t* __restrict__ out_ids,
                                        float* __restrict__ out_dist, uint32_t* __restrict__ out_cnt) {

@@ -77,6 +77,8 @@ def lib():
         _lib.annb_flat_search_dev.argtypes = [vp, vp, u64, u32, u32, vp, vp, vp, vp]
         _lib.annb_ivf_assign.argtypes = [vp, u64, u32, vp, vp, u32, i32, vp, i32]
         _lib.annb_kmeans_lloyd.argtypes = [vp, u64, u32, vp, u32, i32, u32, vp, i32]
+        _lib.annb_ivf_route_dev.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, u32, vp]
+        _lib.annb_ivf_search_probes_dev.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, u32, vp, vp, vp, vp]
         _lib.annb_ivf_create.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, vp, u32, u32, i32]
         _lib.annb_ivf_search.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, vp]
         _lib.annb_ivf_search_self.argtypes = [vp, u64, u64, u32, u32, i32, vp, vp, vp]

@@ -58,3 +58,53 @@ def merge_topk_device(g_ids, g_dist, out_ids=None, out_dist=None, stream=None):
     st = (stream or torch.cuda.current_stream(g_ids.device)).cuda_stream
     _check(lib().annb_merge_topk_dev(g_ids.data_ptr(), g_dist.data_ptr(), parts, nq, k, out_ids.data_ptr(), out_dist.data_ptr(), None, st))
     return out_ids, out_dist
+
+
+def probe_pitch(nprobe: int) -> int:
+    """Probe-list pitch used for the exchange: room for the probe expansion of select_probed_clusters."""
+    return ((max(1, nprobe) + 32 + 31) // 32) * 32
+
+
+def ivf_search_sharded(index, queries, k: int, nprobe: int, out_ids=None, out_dist=None, group=None, stream=None):
+    """One sharded IVF search step on CUDA tensors (one process per GPU, `index` = this rank's list range):
+      1. every rank ranks the centroids for ITS slice of the query batch (annb_ivf_route_dev),
+      2. the probe lists are all-gathered (4 * nq * pitch bytes),
+      3. every rank scans its own lists for the whole batch (annb_ivf_search_probes_dev),
+      4. the per-shard top-k are all-gathered and merged (annb_merge_topk_dev).
+    Falls back to replicated routing (annb_ivf_search_dev) when a probe set does not fit the pitch.
+    Returns (ids [nq, k] int64, dist [nq, k] float32) on the rank's device."""
+    import torch
+    import torch.distributed as dist_
+
+    from . import AnnSearchError, _check, lib
+    world, rank = dist_.get_world_size(group), dist_.get_rank(group)
+    nq, dim = queries.shape
+    dev = queries.device
+    st = (stream or torch.cuda.current_stream(dev)).cuda_stream
+    L = lib()
+    pitch = probe_pitch(nprobe)
+    per = (nq + world - 1) // world
+    lo, hi = min(nq, rank * per), min(nq, (rank + 1) * per)
+    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    dst = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    my_probes = torch.full((per, pitch), -1, dtype=torch.int32, device=dev)
+    my_n = torch.zeros((per,), dtype=torch.int32, device=dev)
+    ok = torch.ones((1,), dtype=torch.int32, device=dev)
+    if hi > lo:
+        rc = L.annb_ivf_route_dev(index.handle, queries[lo:hi].data_ptr(), hi - lo, dim, k, nprobe, my_probes.data_ptr(), my_n.data_ptr(), pitch, st)
+        if rc == -8:
+            ok.zero_()            # a probe set did not fit: every rank falls back together
+        else:
+            _check(rc)
+    dist_.all_reduce(ok, op=dist_.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 1:
+        g_probes = torch.empty((world * per, pitch), dtype=torch.int32, device=dev)
+        g_n = torch.empty((world * per,), dtype=torch.int32, device=dev)
+        dist_.all_gather_into_tensor(g_probes.view(-1), my_probes.view(-1), group=group)
+        dist_.all_gather_into_tensor(g_n, my_n, group=group)
+        _check(L.annb_ivf_search_probes_dev(index.handle, queries.data_ptr(), nq, dim, k, nprobe, g_probes.data_ptr(), g_n.data_ptr(), pitch,
+                                            ids.data_ptr(), dst.data_ptr(), None, st))
+    else:
+        _check(L.annb_ivf_search_dev(index.handle, queries.data_ptr(), nq, dim, k, nprobe, ids.data_ptr(), dst.data_ptr(), None, st))
+    g_ids, g_dist = allgather_topk(ids, dst, group)
+    return merge_topk_device(g_ids, g_dist, out_ids, out_dist, stream)

@@ -173,6 +173,19 @@ int annb_ivf_search_dev(const annb_index* index, const float* d_queries, uint64_
                         uint32_t nprobe, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
                         void* stream);
 
+/* The two halves of annb_ivf_search_dev, for sharded deployments: every rank holds the replicated centroid
+ * table but only needs to rank the centroids for its slice of the query batch; the probe lists are exchanged
+ * (all-gather of nq * probe_pitch cell ids) and every rank then scans its own lists for the whole batch.
+ *   route : centroid ranking + probe expansion (src/cpu/ivf.rs:349-365) -> d_probes [nq * probe_pitch] (cell ids in
+ *           rank order, UINT32_MAX padding), d_n_probes [nq].  ANNB_ERR_UNSUPPORTED if a query's expanded probe set
+ *           does not fit probe_pitch (the caller then routes with a larger pitch or uses annb_ivf_search_dev).
+ *   search_probes : list scan + top-k for the given probe lists (the same scan kernels as annb_ivf_search_dev). */
+int annb_ivf_route_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,
+                       uint32_t* d_probes, uint32_t* d_n_probes, uint32_t probe_pitch, void* stream);
+int annb_ivf_search_probes_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,
+                               const uint32_t* d_probes, const uint32_t* d_n_probes, uint32_t probe_pitch, uint64_t* d_out_ids,
+                               float* d_out_dist, uint32_t* d_out_counts, void* stream);
+
 /* ---------------------------------------------------------------- shared -- */
 
 /* Multi-GPU exchange step: merges `parts` per-shard results (each [nq * k], laid out

@@ -284,3 +284,56 @@ def test_device_lloyd_edge_cases(gpu):
     with pytest.raises(annb200.AnnSearchError) as e:
         annb200.kmeans_lloyd(data, data[:4], annb200.MANHATTAN)
     assert e.value.variant == "DistanceNotSupported"
+
+
+@pytest.mark.parametrize("dtype", ["f32", "sq8"])
+def test_route_then_search_with_probes_equals_the_one_call_search(gpu, dtype):
+    """annb_ivf_route_dev + annb_ivf_search_probes_dev are the two halves of annb_ivf_search_dev.  Emulates two ranks on
+    one device: each "rank" routes its half of the batch, the probe lists are concatenated, each shard scans its own
+    lists for the whole batch with those lists, and the merged answer equals the unsharded search."""
+    import torch
+    from annb200 import distributed as D
+    data = datagen.gaussian_noise(30000, 32, seed=81)
+    q = datagen.subsample_with_noise(data, 257, seed=81)
+    c = o.build_ivf(data, o.L2, nlist=600, dtype=DT[dtype][1], kmeans_iters=3)
+    k, nprobe = 10, 12
+    ref = o.ivf_search(c, q, k, nprobe=nprobe)
+    full = _gpu_from_oracle(c)
+    lb = D.list_ranges(c.offsets, 2)
+    shards = [_gpu_from_oracle(c, *lb[0]), _gpu_from_oracle(c, *lb[1])]
+    lib = annb200.lib()
+    dq = torch.from_numpy(q).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    pitch = D.probe_pitch(nprobe)
+    nq = q.shape[0]
+    probes = torch.full((nq, pitch), -1, dtype=torch.int32, device="cuda")
+    npb = torch.zeros((nq,), dtype=torch.int32, device="cuda")
+    half = 129
+    for r, (lo, hi) in enumerate(((0, half), (half, nq))):      # rank r routes its slice on its own shard handle
+        annb200._check(lib.annb_ivf_route_dev(shards[r].handle, dq[lo:hi].data_ptr(), hi - lo, 32, k, nprobe, probes[lo:hi].data_ptr(),
+                                              npb[lo:hi].data_ptr(), pitch, st))
+    torch.cuda.synchronize()
+    assert int(npb.sum().item()) == int(ref[3].sum())            # same probe counts as select_probed_clusters
+    # one handle, whole index: halves == one call
+    ids = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    dd = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    cnt = torch.empty((nq,), dtype=torch.int32, device="cuda")
+    annb200._check(lib.annb_ivf_search_probes_dev(full.handle, dq.data_ptr(), nq, 32, k, nprobe, probes.data_ptr(), npb.data_ptr(), pitch,
+                                                  ids.data_ptr(), dd.data_ptr(), cnt.data_ptr(), st))
+    torch.cuda.synchronize()
+    _check(dtype, (ids.cpu().numpy(), dd.cpu().numpy(), cnt.cpu().numpy().astype(ref[2].dtype)), ref, "route + search_probes")
+    # two shards: scan own lists for the whole batch, merge
+    pid = torch.empty((2, nq, k), dtype=torch.int64, device="cuda")
+    pd = torch.empty((2, nq, k), dtype=torch.float32, device="cuda")
+    for r in range(2):
+        annb200._check(lib.annb_ivf_search_probes_dev(shards[r].handle, dq.data_ptr(), nq, 32, k, nprobe, probes.data_ptr(), npb.data_ptr(), pitch,
+                                                      pid[r].data_ptr(), pd[r].data_ptr(), None, st))
+    m_ids, m_d = D.merge_topk_device(pid, pd)
+    torch.cuda.synchronize()
+    assert (m_d.cpu().numpy().view(np.uint32) == ref[1].view(np.uint32)).all()
+    if dtype != "sq8":
+        assert (np.sort(m_ids.cpu().numpy(), axis=1) == np.sort(ref[0], axis=1)).all()
+    # a pitch that cannot hold the expanded probe set is reported, not truncated
+    small = torch.empty((nq, 4), dtype=torch.int32, device="cuda")
+    rc = lib.annb_ivf_route_dev(full.handle, dq.data_ptr(), nq, 32, k, nprobe, small.data_ptr(), npb.data_ptr(), 4, st)
+    assert rc == -8
