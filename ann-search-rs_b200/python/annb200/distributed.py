@@ -71,12 +71,12 @@ def ivf_search_sharded(index, queries, k: int, nprobe: int, out_ids=None, out_di
       2. the probe lists are all-gathered (4 * nq * pitch bytes),
       3. every rank scans its own lists for the whole batch (annb_ivf_search_probes_dev),
       4. the per-shard top-k are all-gathered and merged (annb_merge_topk_dev).
-    Falls back to replicated routing (annb_ivf_search_dev) when a probe set does not fit the pitch.
+    Raises AnnSearchError(Unsupported) when a probe set does not fit the pitch.
     Returns (ids [nq, k] int64, dist [nq, k] float32) on the rank's device."""
     import torch
     import torch.distributed as dist_
 
-    from . import AnnSearchError, _check, lib
+    from . import _check, lib
     world, rank = dist_.get_world_size(group), dist_.get_rank(group)
     nq, dim = queries.shape
     dev = queries.device
@@ -89,22 +89,15 @@ def ivf_search_sharded(index, queries, k: int, nprobe: int, out_ids=None, out_di
     dst = torch.empty((nq, k), dtype=torch.float32, device=dev)
     my_probes = torch.full((per, pitch), -1, dtype=torch.int32, device=dev)
     my_n = torch.zeros((per,), dtype=torch.int32, device=dev)
-    ok = torch.ones((1,), dtype=torch.int32, device=dev)
     if hi > lo:
-        rc = L.annb_ivf_route_dev(index.handle, queries[lo:hi].data_ptr(), hi - lo, dim, k, nprobe, my_probes.data_ptr(), my_n.data_ptr(), pitch, st)
-        if rc == -8:
-            ok.zero_()            # a probe set did not fit: every rank falls back together
-        else:
-            _check(rc)
-    dist_.all_reduce(ok, op=dist_.ReduceOp.MIN, group=group)
-    if int(ok.item()) == 1:
-        g_probes = torch.empty((world * per, pitch), dtype=torch.int32, device=dev)
-        g_n = torch.empty((world * per,), dtype=torch.int32, device=dev)
-        dist_.all_gather_into_tensor(g_probes.view(-1), my_probes.view(-1), group=group)
-        dist_.all_gather_into_tensor(g_n, my_n, group=group)
-        _check(L.annb_ivf_search_probes_dev(index.handle, queries.data_ptr(), nq, dim, k, nprobe, g_probes.data_ptr(), g_n.data_ptr(), pitch,
-                                            ids.data_ptr(), dst.data_ptr(), None, st))
-    else:
-        _check(L.annb_ivf_search_dev(index.handle, queries.data_ptr(), nq, dim, k, nprobe, ids.data_ptr(), dst.data_ptr(), None, st))
+        # ANNB_ERR_UNSUPPORTED here means a probe set did not fit the pitch (tiny lists, huge k): the error is raised on this
+        # rank before any collective of the step, so the job fails loudly instead of hanging; use a larger pitch then
+        _check(L.annb_ivf_route_dev(index.handle, queries[lo:hi].data_ptr(), hi - lo, dim, k, nprobe, my_probes.data_ptr(), my_n.data_ptr(), pitch, st))
+    g_probes = torch.empty((world * per, pitch), dtype=torch.int32, device=dev)
+    g_n = torch.empty((world * per,), dtype=torch.int32, device=dev)
+    dist_.all_gather_into_tensor(g_probes.view(-1), my_probes.view(-1), group=group)
+    dist_.all_gather_into_tensor(g_n, my_n, group=group)
+    _check(L.annb_ivf_search_probes_dev(index.handle, queries.data_ptr(), nq, dim, k, nprobe, g_probes.data_ptr(), g_n.data_ptr(), pitch,
+                                        ids.data_ptr(), dst.data_ptr(), None, st))
     g_ids, g_dist = allgather_topk(ids, dst, group)
     return merge_topk_device(g_ids, g_dist, out_ids, out_dist, stream)

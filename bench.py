@@ -54,6 +54,7 @@ def parse_args():
                     help="IVF workload: generate data and build the index on the GPU (auto: when n > 2M)")
     ap.add_argument("--kmeans-iters", type=int, default=8)
     ap.add_argument("--tc-candidates", type=int, default=0, choices=[0, 16, 32], help="k' of the tensor-core pre-selection (0 = library default)")
+    ap.add_argument("--replicated-routing", action="store_true", help="multi-GPU IVF: every rank ranks the centroids for the whole batch (no probe exchange)")
     ap.add_argument("--cert-eps-log2", type=int, default=0, help="log2 of the certificate's error bound (0 = library default)")
     return ap.parse_args()
 
@@ -202,6 +203,7 @@ def run_b200(args):
     import torch.distributed as dist
 
     import annb200
+    from annb200 import distributed as D
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -293,6 +295,11 @@ def run_b200(args):
         if args.workload == "flat":
             annb200._check(lib.annb_flat_search_dev(index.handle, dq.data_ptr(), nq, dim, k, out_ids.data_ptr(), out_dist.data_ptr(),
                                                     out_cnt.data_ptr(), sp))
+        elif world > 1 and not args.replicated_routing:
+            # every rank ranks the centroids for its slice of the batch only; probe lists are exchanged (annb200.distributed)
+            D.ivf_search_sharded(index, dq, k, args.nprobe, m_ids, m_dist)
+            merge_launches += 1
+            return
         else:
             annb200._check(lib.annb_ivf_search_dev(index.handle, dq.data_ptr(), nq, dim, k, args.nprobe, out_ids.data_ptr(),
                                                    out_dist.data_ptr(), out_cnt.data_ptr(), sp))
@@ -477,6 +484,8 @@ def run_b200(args):
     from oracle import oracle as o
     got_ids_all = h_ids.numpy()
     got_d_all = h_dist.numpy()
+    if world > 1:   # the device-resident leg and the host-buffer leg are different call chains: their merged results must agree
+        line["device_vs_e2e"] = {"dist_bits_equal": bool(np.array_equal(m_dist.cpu().numpy().view(np.uint32), got_d_all.view(np.uint32)))}
     if world == 1 and (args.workload == "flat" or oi is not None):
         ns = min(64, nq)
         oi2 = oracle_index(args, data) if args.workload == "flat" else oi
