@@ -2,16 +2,20 @@
 // into the TMEM epilogue (the [nq x n] distance matrix never exists), then an exact re-rank of the k'
 // survivors in the reference's own floating-point order (refdist.cuh).
 //
-// Replaces, for the flat f32 / bf16 indices, the reference's distance-matrix kernels + separate top-k pass
-// (src/gpu/dist_gpu.rs:79-488 euclidean/cosine_tiled{,_reg}; :553-613 extract_topk; src/gpu/topk_gpu.rs:992-1237).
+// Replaces, for the flat f32 / bf16 / SQ8 indices, the reference's distance-matrix kernels + separate top-k pass
+// (src/gpu/dist_gpu.rs:79-488 euclidean/cosine_tiled{,_reg}; :553-613 extract_topk; src/gpu/topk_gpu.rs:992-1237), and with
+// DENSE + coarse_select_kernel the centroid ranking of the IVF query (src/cpu/ivf.rs:349-365).
 //
-// Kernel shape (one CTA = 128 queries x one database split, 192 threads, 1 CTA / SM):
-//   warp 0      TMA producer: query tile once, then a ring of database K-slabs (128 rows x 128 B, SWIZZLE_128B)
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, accumulators double buffered in TMEM
-//   warps 2..5  epilogue: tcgen05.ld 32 columns at a time, v = fma(s, a[col], b[col]) (norm terms fused),
-//               min-tree + threshold test; rare insert into a register-resident sorted k' list per query
+// Kernel shape (one CTA = 128 queries x one database split, 320 threads, 1 CTA / SM):
+//   warp 0      TMA producer: a ring of database K-slabs (128 rows x 128 B, SWIZZLE_128B)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (converged warp, elect.sync), accumulator ring in TMEM
+//   warps 2..9  epilogue, two per TMEM lane quarter (one 64-column half each): stage the query tile into TMEM once (TS
+//               mode), then per tile tcgen05.ld 64 columns, v = fma(s, -2, |x|^2) or s * (-1/|x|) with the row constants
+//               from a warp-private shared-memory row, min-tree + threshold test; a value that beats the threshold is
+//               inserted into a register-resident sorted k' list (select_from_tile)
 //   f32 index : 3xTF32 split precision  s = Qhi.Xhi + Qlo.Xhi + Qhi.Xlo   (kind::tf32, hi/lo rounded with cvt.rna)
 //   bf16 index: f32 queries split into three bf16 terms, s = (q0 + q1 + q2).X  (kind::f16), X = the stored bf16 rows
+//   SQ8 index : int8 codes x int8 codes, s32 accumulators (kind::i8): exact integer dots, three accumulator stages
 #include <cuda.h>
 
 #include <algorithm>

@@ -3,10 +3,11 @@
 // The (query, probe-rank) pairs of a batch are bucketed by inverted list on the device (api.cu).  One task = one list x a
 // group of up to 128 of the queries that probe it.  Persistent CTAs pull tasks from an atomic counter and run the same
 // warp-specialised pipeline as flat_tc_kernel, with three differences:
-//   * the 128 query rows of a task are *gathered* by the epilogue threads (thread = TMEM lane = one (query, rank) pair),
-//     split into tf32 hi/lo (or three bf16 terms) on the fly and stored into TMEM (TS-mode MMA) -- no query operand array;
-//   * the database operand is the list's own slab [offsets[c], offsets[c+1]) of the list-ordered operand copy, walked
-//     in 128-row tiles by TMA; rows of the last tile that belong to the next list are masked with a NaN row constant;
+//   * the 128 query rows of a task are *gathered* by the epilogue threads (thread = TMEM lane = one (query, rank) pair)
+//     from the batch's pre-split operand pieces (tf32 hi/lo, three bf16 terms, or the int8 codes) into TMEM (TS-mode MMA);
+//   * the database operand is the list's own slab [offsets[c], offsets[c+1]) of the index rows themselves, walked in
+//     128-row tiles by TMA (f32: two transform warps derive the lo operand from every landed slab, the raw slab is hi);
+//     rows of the last tile that belong to the next list are masked with a NaN row constant;
 //   * each (query, rank) keeps its own k' candidates; ivf rerank recomputes the merged survivors exactly in the reference's
 //     arithmetic and orders them by (distance, list position) like SortedBuffer (src/cpu/ivf.rs:367-381).
 // Replaces compute_ivf_mega_* + radix_select_ivf_topk of the reference (src/gpu/dist_gpu.rs:922-1355, src/gpu/topk_gpu.rs:599-832).
