@@ -55,6 +55,7 @@ def parse_args():
     ap.add_argument("--kmeans-iters", type=int, default=8)
     ap.add_argument("--tc-candidates", type=int, default=0, choices=[0, 16, 32], help="k' of the tensor-core pre-selection (0 = library default)")
     ap.add_argument("--replicated-routing", action="store_true", help="multi-GPU IVF: every rank ranks the centroids for the whole batch (no probe exchange)")
+    ap.add_argument("--list-major", type=int, default=-1, choices=[-1, 0, 1], help="IVF scan: -1 auto, 0 query-major streaming kernel, 1 list-major")
     ap.add_argument("--no-cert-fallback", action="store_true", help="diagnostic: do not read back / act on the uncertified count")
     ap.add_argument("--cert-eps-log2", type=int, default=0, help="log2 of the certificate's error bound (0 = library default)")
     return ap.parse_args()
@@ -278,6 +279,8 @@ def run_b200(args):
         index.set_option("cert_eps_log2", args.cert_eps_log2)
     if args.no_cert_fallback:
         index.set_option("cert_fallback", 0)
+    if args.workload == "ivf" and args.list_major >= 0:
+        index.set_option("ivf_list_major", args.list_major)
     index.set_option("time_kernels", 1)
 
     dq = torch.from_numpy(queries).to(dev)
