@@ -467,10 +467,12 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
     //    queries); small batches keep the query-major streaming kernel (one warp per query part).
     const uint64_t n_local_lists = std::max<uint32_t>(1, ix->list_end - ix->list_begin);
     // the merge kernels sort all per-(query, rank) lists of a query in shared memory: very wide probe sets go query-major
-    const bool merge_fits_simt = static_cast<uint64_t>(pitch) * kk * 8 <= 192 * 1024;
-    const bool merge_fits_tc = static_cast<uint64_t>(pitch) * 2 * (kk <= 10 ? 16 : 32) * 8 <= 192 * 1024;
+    // (both kernels sort a power-of-two padded array, so the guard is on the padded size)
+    const auto sort_fits = [](uint64_t entries) { return entries <= (1u << 30) && static_cast<uint64_t>(next_pow2(static_cast<uint32_t>(std::max<uint64_t>(entries, 64)))) * 8 <= 200 * 1024; };
+    const bool merge_fits_simt = sort_fits(static_cast<uint64_t>(pitch) * kk);
+    const bool merge_fits_tc = sort_fits(static_cast<uint64_t>(pitch) * 2 * tc_ivf_kprime(ix, kk));
     const bool list_major = merge_fits_simt &&
-                            (ix->opt_ivf_list_major == 1 || (ix->opt_ivf_list_major < 0 && nq * static_cast<uint64_t>(np) >= 8 * n_local_lists));
+                            (ix->opt_ivf_list_major == 1 || (ix->opt_ivf_list_major < 0 && nq * static_cast<uint64_t>(np) * 8 >= n_local_lists));
     if (list_major) {
         const bool use_tc = !force_simt && ix->opt_path != ANNB_PATH_SIMT && merge_fits_tc && tc_ivf_supported(ix, pq.qt, kk);
         if (!use_tc && !force_simt && ix->opt_path == ANNB_PATH_TENSOR)

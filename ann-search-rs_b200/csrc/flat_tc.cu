@@ -251,6 +251,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 const int c = static_cast<int>(half);
                 uint32_t r[64];
                 tmem_ld64_sync(taddr + c * 64, r);
+                // the tile's values are in registers: hand the accumulator stage back before the select work, so the
+                // issuer never waits on this warp's candidate inserts
+                tc_fence_before();
+                mbar_arrive(bar_tempty + acc);
                 float v[64];
                 float gm[8];  // minima of the 8 groups of 8 columns
 #pragma unroll
@@ -284,8 +288,6 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     w_slow += clock64() - ts0;
                 }
             }
-            tc_fence_before();
-            mbar_arrive(bar_tempty + acc);
             if (!DENSE && (top.tau() < g_tau || (g_tau != g_tau && top.tau() < INFINITY))) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));
         }
         if (p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) { p.dbg_cycles[4] = w_tfull; p.dbg_cycles[5] = w_slow; }

@@ -21,6 +21,7 @@ void tc_destroy(annb_index* ix);
 int tc_ivf_prepare(annb_index* ix);
 void tc_ivf_destroy(annb_index* ix);
 bool tc_ivf_supported(const annb_index* ix, int qt, uint32_t k_eff);
+uint32_t tc_ivf_kprime(const annb_index* ix, uint32_t k_eff);   // candidates kept per (query, rank, half tile)
 int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t nq, uint32_t k_eff, uint32_t k_out, uint32_t probe_pitch,
                 const uint32_t* d_pair_off, const uint32_t* d_task_off, const void* d_pairs, uint32_t* d_task_counter, uint64_t max_tasks,
                 const uint32_t* d_n_probes, const uint64_t* row_map, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s,

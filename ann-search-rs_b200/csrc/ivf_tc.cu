@@ -253,7 +253,18 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                     // pieces were split once per batch (split_tf32_kernel): half 0 copies hi to columns [0,128), half 1 lo to [128,256)
                     const uint4* src = reinterpret_cast<const uint4*>(static_cast<const float*>(p.q_op) + (static_cast<uint64_t>(half) * p.nq + (has_query ? pr.x : 0)) * kp);
                     const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + half * PIECE_COLS;
-                    for (uint32_t c = 0; c < kp; c += 32) {
+                    uint32_t c = 0;
+                    for (; c + 64 <= kp; c += 64) {   // 16 loads in flight per round trip to L2
+                        uint32_t w[64];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                            if (has_query) x = __ldg(src + c / 4 + j);
+                            w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
+                        }
+                        tmem_st64(tq + c, w);
+                    }
+                    if (c < kp) {
                         uint32_t w[32];
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
@@ -323,6 +334,8 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                     const int c = static_cast<int>(half);
                     uint32_t r[64];
                     tmem_ld64_sync(taddr + c * 64, r);
+                    tc_fence_before();             // values are in registers: free the accumulator stage before the select work
+                    mbar_arrive(bar_tempty + acc);
                     float v[64];
                     float gm[8];
 #pragma unroll
@@ -340,9 +353,10 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                     }
                     const float m = fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
                     if (m < tau) select_from_tile<KP>(top, tau, v, gm, m, row0 + c * 64, scratch);
+                } else {
+                    tc_fence_before();
+                    mbar_arrive(bar_tempty + acc);
                 }
-                tc_fence_before();
-                mbar_arrive(bar_tempty + acc);
                 if (has_query && (top.tau() < g_tau || (g_tau != g_tau && top.tau() < INFINITY))) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));
             }
             if (has_query) {

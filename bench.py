@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--kmeans-iters", type=int, default=8)
     ap.add_argument("--tc-candidates", type=int, default=0, choices=[0, 16, 32], help="k' of the tensor-core pre-selection (0 = library default)")
     ap.add_argument("--replicated-routing", action="store_true", help="multi-GPU IVF: every rank ranks the centroids for the whole batch (no probe exchange)")
+    ap.add_argument("--self-queries", action="store_true",
+                    help="flat: the batch is database rows [0, nq) themselves (one batch of generate_knn; BASELINE configs[4]: --n 2000000 --dim 50 --k 15 --metric euclidean)")
     ap.add_argument("--list-major", type=int, default=-1, choices=[-1, 0, 1], help="IVF scan: -1 auto, 0 query-major streaming kernel, 1 list-major")
     ap.add_argument("--no-cert-fallback", action="store_true", help="diagnostic: do not read back / act on the uncertified count")
     ap.add_argument("--cert-eps-log2", type=int, default=0, help="log2 of the certificate's error bound (0 = library default)")
@@ -120,19 +122,24 @@ def make_data(args):
     kind = "correlated"
     n = args.n
     data = datagen.make(kind, n, args.dim, seed=42)
-    queries = datagen.subsample_with_noise(data, args.nq, seed=42)
+    if args.self_queries:     # one batch of the all-vs-all kNN graph (exhaustive.rs:255-292): the rows themselves, self at rank 0
+        queries = np.ascontiguousarray(data[:args.nq])
+    else:
+        queries = datagen.subsample_with_noise(data, args.nq, seed=42)
     return data, queries, kind
 
 
 def metric_name(args):
     if args.workload == "flat":
-        return f"QPS flat {args.dtype} {args.metric} k={args.k}"
+        return f"QPS flat {args.dtype} {args.metric} k={args.k}" + (" self-query" if args.self_queries else "")
     return f"QPS ivf {args.dtype} {args.metric} nlist={args.nlist} nprobe={args.nprobe} k={args.k}"
 
 
 def workload_desc(args, kind, n_gpus):
     if args.workload == "flat":
         w = f"exhaustive flat {args.dtype} {args.metric}, {args.n}x{args.dim} {kind} synthetic, {args.nq}-query batch, k={args.k}"
+        if args.self_queries:
+            w += f" (self-query: the batch is rows [0, {args.nq}) of the database; the full kNN graph is {-(-args.n // args.nq)} such batches)"
     else:
         w = (f"IVF {args.dtype} {args.metric}, {args.n}x{args.dim} {kind} synthetic, nlist={args.nlist}, nprobe={args.nprobe}, "
              f"{args.nq}-query batch, k={args.k}")
@@ -485,6 +492,8 @@ def run_b200(args):
             "gpu_launches": int(launches), "roofline": roofline, "uncertified_queries_last_step": int(uncertified)}
     if algo_bytes_per_query is not None:
         line["config"]["algorithmic_bytes_per_query"] = algo_bytes_per_query
+    if args.self_queries:
+        line["full_knn_graph_seconds_extrapolated"] = n / qps
 
     # ---- parity spot check + recall on a query sample (outside the timed region) ----
     from oracle import oracle as o
