@@ -158,3 +158,28 @@ def test_host_entry_batches_large_query_sets(gpu):
     ref = o.ivf_search(ci, q, 10, nprobe=8)
     assert_exact(got[0], got[1], ref[0], ref[1], "ivf, 20000 queries")
     assert gi.get_stat("scanned_vectors") == int(ref[4].sum())
+
+
+def test_concurrent_searches_on_one_handle(gpu):
+    """`&self` queries are `Sync` in the reference (src/cpu/exhaustive.rs:142, src/gpu/exhaustive_gpu.rs:124): several host
+    threads may search one index at once.  The handle serialises them internally; every thread gets the oracle's answer."""
+    import threading
+    data = datagen.gaussian_noise(20000, 32, seed=17)
+    g, c = _pair(data, "f32", "l2", path=annb200.PATH_AUTO)
+    qs = [datagen.subsample_with_noise(data, 300 + 50 * t, seed=100 + t) for t in range(4)]
+    refs = [o.flat_search(c, q, 10) for q in qs]
+    out, errs = [None] * 4, []
+
+    def work(t):
+        try:
+            for _ in range(5):
+                out[t] = g.query_batch(qs[t], 10)
+        except Exception as e:   # surfaced below: an assertion inside a thread would be lost
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for t in range(4):
+        assert_exact(out[t][0], out[t][1], refs[t][0], refs[t][1], f"thread {t}")

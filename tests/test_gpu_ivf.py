@@ -337,3 +337,42 @@ def test_route_then_search_with_probes_equals_the_one_call_search(gpu, dtype):
     small = torch.empty((nq, 4), dtype=torch.int32, device="cuda")
     rc = lib.annb_ivf_route_dev(full.handle, dq.data_ptr(), nq, 32, k, nprobe, small.data_ptr(), npb.data_ptr(), 4, st)
     assert rc == -8
+
+
+@pytest.mark.parametrize("nq", [1, 3, 16, 40])
+def test_small_batches_both_scan_kernels(gpu, nq):
+    """Small batches: the query-major streaming kernel and the list-major kernels (forced through `ivf_list_major`) and the
+    library's own choice all return the oracle's answer (src/cpu/ivf.rs:337-390)."""
+    data = datagen.gaussian_noise(30000, 32, seed=23)
+    c = o.build_ivf(data, o.L2, nlist=64)
+    g = _gpu_from_oracle(c)
+    q = datagen.subsample_with_noise(data, nq, seed=29)
+    ref = o.ivf_search(c, q, 10, nprobe=6)
+    for mode in (0, 1, -1):
+        g.set_option("ivf_list_major", mode)
+        _check("f32", g.query_batch(q, 10, nprobe=6), ref, f"nq={nq} ivf_list_major={mode}")
+
+
+def test_concurrent_ivf_searches_on_one_handle(gpu):
+    """Several host threads searching one IVF index at once (`&self` queries, src/cpu/ivf.rs:337) all get the oracle's answer."""
+    import threading
+    data = datagen.gaussian_noise(30000, 32, seed=31)
+    c = o.build_ivf(data, o.L2, nlist=64)
+    g = _gpu_from_oracle(c)
+    qs = [datagen.subsample_with_noise(data, 200 + 64 * t, seed=200 + t) for t in range(4)]
+    refs = [o.ivf_search(c, q, 10, nprobe=5 + t) for t, q in enumerate(qs)]
+    out, errs = [None] * 4, []
+
+    def work(t):
+        try:
+            for _ in range(5):
+                out[t] = g.query_batch(qs[t], 10, nprobe=5 + t)
+        except Exception as e:
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    for t in range(4):
+        _check("f32", out[t], refs[t], f"thread {t}")

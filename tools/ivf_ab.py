@@ -1,5 +1,5 @@
-"""A/B of the tensor-core IVF scan's runtime switches (option ivf_tc_flags) on one index in one process.
-usage: python tools/ivf_ab.py [n] [nq] [nprobe] [dtypes: f32,bf16,sq8] [flags: 0,1,2,3]"""
+"""A/B of one integer index option (annb_index_set_option) on the 10M-row IVF bench workload, one index, one process.
+usage: python tools/ivf_ab.py [n] [nq] [nprobe] [dtypes: f32,bf16,sq8] [option name] [values: 0,1,...]"""
 import os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,7 +10,8 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 nq = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000
 nprobe = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 dts = sys.argv[4].split(",") if len(sys.argv) > 4 else ["f32"]
-flag_sets = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0, 1, 2, 3]
+opt = sys.argv[5] if len(sys.argv) > 5 else "ivf_list_major"
+flag_sets = [int(x) for x in sys.argv[6].split(",")] if len(sys.argv) > 6 else [0, 1]
 dim, nlist, k = 128, 4096, 10
 dev = torch.device("cuda:0")
 data = gs.correlated_gpu(n, dim, dev, seed=42)
@@ -25,7 +26,7 @@ for name in dts:
     ref = None
     for rep in range(2):
         for flags in flag_sets:
-            if flags: ix.set_option("ivf_tc_flags", flags)
+            ix.set_option(opt, flags)
             for _ in range(3):
                 annb200._check(lib.annb_ivf_search_dev(ix.handle, q.data_ptr(), nq, dim, k, nprobe, ids.data_ptr(), None, None, st))
             torch.cuda.synchronize()
@@ -42,7 +43,7 @@ for name in dts:
             same = True if ref is None else bool((ids == ref).all())
             if ref is None:
                 ref = ids.clone()
-            print(f"{name} flags {flags} rep {rep} step_ms {ms:.3f} scan_ms {kern:.3f} qps {nq / ms * 1e3:.0f} ids_equal {same}", flush=True)
+            print(f"{name} {opt} {flags} rep {rep} step_ms {ms:.3f} scan_ms {kern:.3f} qps {nq / ms * 1e3:.0f} ids_equal {same}", flush=True)
     ix.close()
     del parts
     torch.cuda.empty_cache()
