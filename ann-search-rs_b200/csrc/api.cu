@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "index.hpp"
@@ -840,6 +841,55 @@ int annb_flat_search_dev(const annb_index* index, const float* d_queries, uint64
     return ANNB_OK;
 }
 
+// out[list[i]] = src[i]
+static __global__ void scatter_u32_kernel(const uint32_t* __restrict__ list, uint32_t count, const uint32_t* __restrict__ src, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[list[i]] = src[i];
+}
+
+// The exact CUDA-core assignment kernel (direct_assign arithmetic, k_means_utils.rs:2119-2195) on rows [0, nr) of d_x.
+static int assign_simt(const float* d_x, uint32_t ld, uint64_t nr, const float* d_c, const float* d_aux, uint32_t nlist, uint32_t dim, bool cosine,
+                       uint32_t* d_a) {
+    TileParams p{};
+    p.rows = reinterpret_cast<const uint8_t*>(d_c); p.n_rows = nlist; p.row_bytes = ld * 4; p.row_aux = d_aux;
+    p.queries = reinterpret_cast<const uint8_t*>(d_x); p.q_bytes = ld * 4; p.nq = nr; p.dim = dim;
+    p.assign_out = d_a; p.assign_cosine = cosine;
+    const size_t smem = tile_kernel_smem(p.row_bytes, p.q_bytes, 0, false);
+    return launch_tile<0, QT_F32, MET_DOT, EPI_ARGMAX>(p, dim3(static_cast<uint32_t>(ceil_div<uint64_t>(nr, CTA_QUERIES)), 1), smem, 0);
+}
+
+// One chunk of rows: tensor-core pre-selection + exact scores + certificate (flat_tc.cu), the rows that fail it redone on
+// the exact kernel; without a tensor state (small tables, wide rows, ANNB200_ASSIGN_PATH=simt) the exact kernel alone.
+struct AssignScratch {
+    DevBuf uncert, fb_rows, fb_assign;
+    uint64_t redone = 0;
+    ~AssignScratch() { uncert.release(); fb_rows.release(); fb_assign.release(); }
+};
+static int assign_chunk(TcAssignState* tcs, AssignScratch& sc, const float* d_x, uint32_t ld, uint64_t nr, const float* d_c, const float* d_aux,
+                        uint32_t nlist, uint32_t dim, bool cosine, uint32_t* d_a) {
+    if (!tcs) return assign_simt(d_x, ld, nr, d_c, d_aux, nlist, dim, cosine, d_a);
+    ANNB_TRY(sc.uncert.ensure((nr + 1) * 4));
+    ANNB_TRY(tc_assign_run(tcs, d_x, ld, nr, d_c, ld, d_aux, cosine, d_a, sc.uncert.as<uint32_t>(), 0));
+    uint32_t n_unc = 0;
+    ANNB_CUDA_CHECK(cudaMemcpy(&n_unc, sc.uncert.p, 4, cudaMemcpyDeviceToHost));
+    if (n_unc == 0) return ANNB_OK;
+    sc.redone += n_unc;
+    const uint32_t* list = sc.uncert.as<uint32_t>() + 1;
+    ANNB_TRY(sc.fb_rows.ensure(static_cast<size_t>(n_unc) * ld * 4));
+    ANNB_TRY(sc.fb_assign.ensure(static_cast<size_t>(n_unc) * 4));
+    gather_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * (ld >> 2), 256), 256>>>(reinterpret_cast<const uint8_t*>(d_x), ld * 4, list, n_unc, sc.fb_rows.as<uint8_t>());
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    ANNB_TRY(assign_simt(sc.fb_rows.as<float>(), ld, n_unc, d_c, d_aux, nlist, dim, cosine, sc.fb_assign.as<uint32_t>()));
+    scatter_u32_kernel<<<ceil_div(n_unc, 256u), 256>>>(list, n_unc, sc.fb_assign.as<uint32_t>(), d_a);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    return ANNB_OK;
+}
+static bool assign_tensor_enabled() {
+    const char* e = std::getenv("ANNB200_ASSIGN_PATH");   // debugging / A-B switch: "simt" keeps the build-side assignment on the CUDA cores
+    return !(e && std::string(e) == "simt");
+}
+static thread_local uint64_t g_assign_redone = 0;   // rows of the last assign / Lloyd call that failed the certificate
+
 int annb_ivf_assign(const float* data, uint64_t n, uint32_t dim, const float* centroids, const float* centroid_norms,
                     uint32_t nlist, int metric, uint32_t* out_assign, int device) {
     if (metric == ANNB_MANHATTAN) return fail(ANNB_ERR_DISTANCE_NOT_SUPPORTED, "Manhattan distance is not supported");
@@ -862,20 +912,25 @@ int annb_ivf_assign(const float* data, uint64_t n, uint32_t dim, const float* ce
     }
     assign_aux_kernel<<<ceil_div(nlist, 128u), 128>>>(d_c, ld, dim, nlist, metric == ANNB_COSINE, d_cn, d_aux);
     ANNB_CUDA_CHECK(cudaGetLastError());
+    TcAssignState* tcs = nullptr;
+    struct FreeTc { TcAssignState*& p; ~FreeTc() { tc_assign_destroy(p); } } ftc{tcs};
+    if (assign_tensor_enabled() && n >= 4096) ANNB_TRY(tc_assign_create(&tcs, dim, nlist));
+    if (tcs) ANNB_TRY(tc_assign_set_centroids(tcs, d_c, ld, d_aux, metric == ANNB_COSINE, 0));
+    AssignScratch sc;
     for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
         const uint64_t nr = std::min<uint64_t>(chunk, n - r0);
         if (ld != dim) ANNB_CUDA_CHECK(cudaMemset(d_x, 0, nr * ld * 4ull));
         ANNB_CUDA_CHECK(cudaMemcpy2D(d_x, ld * 4ull, data + r0 * dim, dim * 4ull, dim * 4ull, nr, cudaMemcpyDefault));
-        TileParams p{};
-        p.rows = reinterpret_cast<const uint8_t*>(d_c); p.n_rows = nlist; p.row_bytes = ld * 4; p.row_aux = d_aux;
-        p.queries = reinterpret_cast<const uint8_t*>(d_x); p.q_bytes = ld * 4; p.nq = nr; p.dim = dim;
-        p.assign_out = d_a; p.assign_cosine = metric == ANNB_COSINE;
-        size_t smem = tile_kernel_smem(p.row_bytes, p.q_bytes, 0, false);
-        ANNB_TRY((launch_tile<0, QT_F32, MET_DOT, EPI_ARGMAX>(p, dim3(static_cast<uint32_t>(ceil_div<uint64_t>(nr, CTA_QUERIES)), 1), smem, 0)));
+        ANNB_TRY(assign_chunk(tcs, sc, d_x, ld, nr, d_c, d_aux, nlist, dim, metric == ANNB_COSINE, d_a));
         ANNB_CUDA_CHECK(cudaMemcpy(out_assign + r0, d_a, nr * 4ull, cudaMemcpyDefault));
     }
+    g_assign_redone = sc.redone;
     return ANNB_OK;
 }
+
+/* Diagnostic: rows of this thread's last annb_ivf_assign / annb_kmeans_lloyd call that failed the tensor path's certificate
+ * and were redone on the exact kernel (0 when the call ran on the exact kernel throughout). */
+uint64_t annb_assign_last_redone(void) { return g_assign_redone; }
 
 int annb_kmeans_lloyd(const float* data, uint64_t n, uint32_t dim, float* centroids, uint32_t nlist, int metric, uint32_t max_iters,
                       uint32_t* out_iters, int device) {
@@ -910,21 +965,21 @@ int annb_kmeans_lloyd(const float* data, uint64_t n, uint32_t dim, float* centro
     ANNB_CUDA_CHECK(cudaMemcpy2D(d_x, ld * 4ull, data, dim * 4ull, dim * 4ull, n, cudaMemcpyDefault));
     ANNB_CUDA_CHECK(cudaMemset(d_prev, 0xFF, n * 4ull));      // usize::MAX: every point counts as changed in the first iteration
     const uint64_t change_floor = std::max<uint64_t>(n / 10000, 1);
+    TcAssignState* tcs = nullptr;
+    struct FreeTc { TcAssignState*& p; ~FreeTc() { tc_assign_destroy(p); } } ftc{tcs};
+    if (assign_tensor_enabled() && n >= 4096) ANNB_TRY(tc_assign_create(&tcs, dim, nlist));
+    AssignScratch sc;
     uint32_t it = 0;
     for (; it < max_iters; it++) {
         // assignment: direct_assign arithmetic (k_means_utils.rs:2119-2195) on the current centroids
         if (metric == ANNB_COSINE) row_norms_f32_kernel<<<ceil_div(nlist, 128u), 128>>>(d_c, ld, dim, nlist, d_cn, 0);   // calculate_l2_norm
         assign_aux_kernel<<<ceil_div(nlist, 128u), 128>>>(d_c, ld, dim, nlist, metric == ANNB_COSINE, d_cn, d_aux);
         ANNB_CUDA_CHECK(cudaGetLastError());
+        if (tcs) ANNB_TRY(tc_assign_set_centroids(tcs, d_c, ld, d_aux, metric == ANNB_COSINE, 0));
         const uint64_t chunk = 1ull << 20;
         for (uint64_t r0 = 0; r0 < n; r0 += chunk) {
             const uint64_t nr = std::min<uint64_t>(chunk, n - r0);
-            TileParams p{};
-            p.rows = reinterpret_cast<const uint8_t*>(d_c); p.n_rows = nlist; p.row_bytes = ld * 4; p.row_aux = d_aux;
-            p.queries = reinterpret_cast<const uint8_t*>(d_x + r0 * ld); p.q_bytes = ld * 4; p.nq = nr; p.dim = dim;
-            p.assign_out = d_a + r0; p.assign_cosine = metric == ANNB_COSINE;
-            const size_t smem = tile_kernel_smem(p.row_bytes, p.q_bytes, 0, false);
-            ANNB_TRY((launch_tile<0, QT_F32, MET_DOT, EPI_ARGMAX>(p, dim3(static_cast<uint32_t>(ceil_div<uint64_t>(nr, CTA_QUERIES)), 1), smem, 0)));
+            ANNB_TRY(assign_chunk(tcs, sc, d_x + r0 * ld, ld, nr, d_c, d_aux, nlist, dim, metric == ANNB_COSINE, d_a + r0));
         }
         // convergence is tested before the update (k_means_utils.rs:1611-1624)
         ANNB_CUDA_CHECK(cudaMemset(d_changed, 0, 8));
@@ -939,6 +994,7 @@ int annb_kmeans_lloyd(const float* data, uint64_t n, uint32_t dim, float* centro
         ANNB_CUDA_CHECK(cudaGetLastError());
     }
     ANNB_CUDA_CHECK(cudaMemcpy2D(centroids, dim * 4ull, d_c, ld * 4ull, dim * 4ull, nlist, cudaMemcpyDefault));
+    g_assign_redone = sc.redone;
     if (out_iters) *out_iters = it;
     return ANNB_OK;
 }

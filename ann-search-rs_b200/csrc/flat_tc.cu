@@ -506,6 +506,86 @@ static __global__ void fill_aux_kernel(float* __restrict__ aux, uint64_t n, uint
     if (i < n_total) aux[i] = i < n ? value : INFINITY;
 }
 
+// ----------------------------------------------------------------------------------------------- build-side assignment
+// assign_all_parallel / direct_assign (src/utils/k_means_utils.rs:2119-2241): argmax_c of 2 x.c - |c|^2 (L2) or
+// x.c / |c| (cosine), lowest cell on ties.  The flat kernel's selection value IS the negated score (|c|^2 - 2 x.c, or
+// -x.c/|c|), so the centroid table is searched like a flat f32 index with k' = 16 and this kernel finishes the job: one
+// warp per data row recomputes the score of every retained cell at or below the final threshold in the reference's
+// arithmetic, takes the best, and certifies it -- every cell that was not retained has an approximate value >= the
+// threshold, so the winner is exact iff its negated score lies below the threshold by more than the error bound.
+// Rows that fail are listed for the exact CUDA-core kernel.
+struct AssignSelectParams {
+    const uint64_t* part_keys;   // [n][parts][kp]
+    uint32_t parts, kp;
+    const uint32_t* gtau;        // [n] final shared threshold (ordered image of the approximate value)
+    uint64_t n;
+    const float* rows;           // data rows [n][x_ld]
+    uint32_t x_ld;
+    const float* centroids;      // [nlist][c_ld]
+    uint32_t c_ld;
+    const float* aux;            // direct_assign constants: |c|^2 (L2) or 1/|c| (cosine, 0 for a zero centroid)
+    uint32_t dim;
+    int cosine;
+    float eps;
+    const uint32_t* cmax_sq_bits; // L2: bit pattern of max |c|^2
+    uint32_t* assign_out;        // [n]
+    uint32_t* uncert;            // [0] = count, [1..] = row numbers that could not be certified
+};
+
+__global__ void __launch_bounds__(256) assign_select_kernel(AssignSelectParams p) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t q = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= p.n) return;
+    const uint32_t thr = p.gtau[q];
+    const uint64_t* src = p.part_keys + q * (static_cast<uint64_t>(p.parts) * p.kp);
+    const uint32_t total = p.parts * p.kp;
+    const uint8_t* xrow = reinterpret_cast<const uint8_t*>(p.rows + q * p.x_ld);
+    float best_s = -INFINITY;
+    uint32_t best_c = IDX_INVALID;
+    for (uint32_t i = lane; i < total; i += 32) {
+        const uint64_t key = src[i];
+        if (key == KEY_SENTINEL || static_cast<uint32_t>(key >> 32) > thr) continue;
+        const uint32_t c = key_idx(key);
+        float dot[1];
+        accumulate_fp<4, 4, false, 1>(reinterpret_cast<const uint8_t*>(p.centroids + static_cast<uint64_t>(c) * p.c_ld), xrow, p.x_ld * 4, p.dim, dot);
+        const float a = p.aux[c];
+        const float score = p.cosine ? __fmul_rn(dot[0], a) : __fsub_rn(__fmul_rn(2.0f, dot[0]), a);
+        if (score > best_s || (score == best_s && c < best_c)) { best_s = score; best_c = c; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float os = __shfl_xor_sync(0xFFFFFFFFu, best_s, off);
+        const uint32_t oc = __shfl_xor_sync(0xFFFFFFFFu, best_c, off);
+        if (os > best_s || (os == best_s && oc < best_c)) { best_s = os; best_c = oc; }
+    }
+    float qn2 = 0.f;
+    for (uint32_t e = lane; e < p.dim; e += 32) {
+        const float x = reinterpret_cast<const float*>(xrow)[e];
+        qn2 = fmaf(x, x, qn2);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) qn2 += __shfl_xor_sync(0xFFFFFFFFu, qn2, off);
+    if (lane == 0) {
+        const float tv = ordered_to_f32(thr);   // NaN while no list was ever full: nothing is certified then
+        float margin;
+        if (p.cosine) {
+            margin = p.eps * sqrtf(qn2);                                        // value = -x.c/|c|
+        } else {
+            const float sn = sqrtf(qn2) + sqrtf(__uint_as_float(*p.cmax_sq_bits));   // value = |c|^2 - 2 x.c
+            margin = p.eps * sn * sn;
+        }
+        const bool ok = best_c != IDX_INVALID && (-best_s) < tv - margin;
+        p.assign_out[q] = best_c;
+        if (!ok) p.uncert[1 + atomicAdd(p.uncert, 1u)] = static_cast<uint32_t>(q);
+    }
+}
+
+// tensor-kernel row constants from the direct_assign constants: L2 |c|^2, cosine -1/|c|; +inf on pad rows
+static __global__ void assign_tc_aux_kernel(const float* __restrict__ assign_aux, uint32_t nlist, uint64_t total, int cosine, float* __restrict__ aux) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i < total) aux[i] = i < nlist ? (cosine ? -assign_aux[i] : assign_aux[i]) : INFINITY;
+}
+
 }  // namespace tc
 
 // =============================================================================================== host side
@@ -907,6 +987,104 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     else if (ix->dtype == ANNB_SQ8) ANNB_TRY(launch_coarse_select<MET_COS_PRENORM>(c, s));
     else ANNB_TRY(launch_coarse_select<MET_COS>(c, s));
     ix->stat_launches += 3;
+    return ANNB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- build-side assignment (host)
+struct TcAssignState {
+    uint32_t dim = 0, nlist = 0, kp = 0, nslab = 0, n_pad = 0;
+    void* d_x = nullptr;          // centroid table as stacked tf32 hi / lo operand
+    float* d_aux = nullptr;       // [n_pad + BN]
+    uint32_t* d_cmax = nullptr;   // bit pattern of max |c|^2
+    CUtensorMap tm_x;
+    DevBuf q_op, part, gtau;
+};
+
+// nullptr state (and ANNB_OK) when the shape is not covered: small tables are cheap on the CUDA cores anyway.
+int tc_assign_create(TcAssignState** out, uint32_t dim, uint32_t nlist) {
+    *out = nullptr;
+    const uint32_t kp = round_up(dim, tc::SLAB_BYTES / 4u);
+    if (nlist < 512 || kp * 4 > 512) return ANNB_OK;
+    TcAssignState* st = new TcAssignState();
+    st->dim = dim; st->nlist = nlist; st->kp = kp; st->nslab = kp / (tc::SLAB_BYTES / 4u);
+    st->n_pad = round_up<uint32_t>(nlist, tc::BN);
+    const uint64_t aux_rows = static_cast<uint64_t>(st->n_pad) + tc::BN;
+    cudaError_t e = cudaMalloc(&st->d_x, 2ull * st->n_pad * kp * 4);
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&st->d_aux), aux_rows * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&st->d_cmax), 4);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        set_last_error(std::string("cudaMalloc assignment operand: ") + cudaGetErrorString(e));
+        tc_assign_destroy(st);
+        return ANNB_ERR_OUT_OF_MEMORY;
+    }
+    int rc = tc_make_tmap(&st->tm_x, st->d_x, 2ull * st->n_pad, kp, 4);
+    if (rc != ANNB_OK) { tc_assign_destroy(st); return rc; }
+    *out = st;
+    return ANNB_OK;
+}
+
+void tc_assign_destroy(TcAssignState* st) {
+    if (!st) return;
+    cudaFree(st->d_x);
+    cudaFree(st->d_aux);
+    cudaFree(st->d_cmax);
+    st->q_op.release();
+    st->part.release();
+    st->gtau.release();
+    delete st;
+}
+
+// (Re)loads the centroid table: Lloyd iterations call this once per iteration.
+int tc_assign_set_centroids(TcAssignState* st, const float* d_c, uint32_t c_ld, const float* d_assign_aux, bool cosine, cudaStream_t s) {
+    const uint64_t aux_rows = static_cast<uint64_t>(st->n_pad) + tc::BN;
+    tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * st->kp), 256, 0, s>>>(d_c, c_ld, st->dim, st->nlist, st->n_pad, st->kp, static_cast<float*>(st->d_x));
+    tc::assign_tc_aux_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(d_assign_aux, st->nlist, aux_rows, cosine ? 1 : 0, st->d_aux);
+    ANNB_CUDA_CHECK(cudaMemsetAsync(st->d_cmax, 0, 4, s));
+    if (!cosine) tc::aux_max_kernel<<<32, 256, 0, s>>>(d_assign_aux, st->nlist, st->d_cmax);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    return ANNB_OK;
+}
+
+// Assigns rows [0, nr) of d_x; d_uncert[0] receives the number of rows that must be redone exactly, d_uncert[1..] their numbers.
+int tc_assign_run(TcAssignState* st, const float* d_x, uint32_t x_ld, uint64_t nr, const float* d_c, uint32_t c_ld, const float* d_assign_aux,
+                  bool cosine, uint32_t* d_assign, uint32_t* d_uncert, cudaStream_t s) {
+    constexpr uint32_t AKP = 16;
+    const uint32_t kp = st->kp;
+    const uint32_t nq_pad = static_cast<uint32_t>(round_up<uint64_t>(nr, tc::BM));
+    ANNB_TRY(st->q_op.ensure(2ull * nq_pad * kp * 4));
+    tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(nq_pad) * kp), 256, 0, s>>>(d_x, x_ld, st->dim, nr, nq_pad, kp, st->q_op.as<float>());
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    CUtensorMap tmq;
+    ANNB_TRY(tc_make_tmap(&tmq, st->q_op.p, 2ull * nq_pad, kp, 4));
+    const uint64_t q_tiles = nq_pad / tc::BM, db_tiles = st->n_pad / tc::BN;
+    const uint32_t splits_req = pick_splits(q_tiles, db_tiles, 0);
+    const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;
+    const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
+    const size_t fixed = 256 + 8 * 64 * 4, budget = 227 * 1024;
+    const uint32_t stages = static_cast<uint32_t>(std::min<size_t>(8, (budget - fixed) / (2 * tc::SLAB_TILE)));
+    const size_t smem = static_cast<size_t>(stages) * 2 * tc::SLAB_TILE + fixed;
+    ANNB_TRY(st->part.ensure(nr * 2ull * splits * AKP * 8));
+    ANNB_TRY(st->gtau.ensure(static_cast<uint64_t>(nq_pad) * 4));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(st->gtau.p, 0xFF, static_cast<uint64_t>(nq_pad) * 4, s));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(d_uncert, 0, 4, s));
+    tc::Params p{};
+    p.nq = nr; p.n_rows = st->nlist; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
+    p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = 2; p.aux = st->d_aux;
+    p.q_op = st->q_op.as<void>(); p.kp = kp; p.part_keys = st->part.as<uint64_t>(); p.gtau = st->gtau.as<uint32_t>();
+    dim3 grid(static_cast<uint32_t>(q_tiles), splits);
+    if (cosine) ANNB_TRY((launch_tc<tc::KIND_TF32X3, AKP, MET_COS, true>(tmq, st->tm_x, p, grid, smem, s)));
+    else ANNB_TRY((launch_tc<tc::KIND_TF32X3, AKP, MET_L2, true>(tmq, st->tm_x, p, grid, smem, s)));
+    tc::AssignSelectParams a{};
+    a.part_keys = st->part.as<uint64_t>(); a.parts = 2 * splits; a.kp = AKP; a.gtau = st->gtau.as<uint32_t>(); a.n = nr;
+    a.rows = d_x; a.x_ld = x_ld; a.centroids = d_c; a.c_ld = c_ld; a.aux = d_assign_aux; a.dim = st->dim; a.cosine = cosine ? 1 : 0;
+    // error budget of the selection value against the reference-order score: 3xTF32 products and the tensor core's
+    // accumulation (< 8.5 * 2^-20 |x||c|) plus the f32 rounding of the reference's own sequential sum
+    // (<= dim * 2^-24 |x||c| in the worst case); 2^-16 (|x| + |c|max)^2 >= 2^-14 |x||c| covers both up to dim 512
+    a.eps = 1.52587890625e-05f;
+    a.cmax_sq_bits = st->d_cmax; a.assign_out = d_assign; a.uncert = d_uncert;
+    tc::assign_select_kernel<<<static_cast<uint32_t>((nr + 7) / 8), 256, 0, s>>>(a);
+    ANNB_CUDA_CHECK(cudaGetLastError());
     return ANNB_OK;
 }
 

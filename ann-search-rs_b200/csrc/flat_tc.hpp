@@ -32,6 +32,15 @@ int tc_coarse_prepare(annb_index* ix);
 void tc_coarse_destroy(annb_index* ix);
 bool tc_coarse_supported(const annb_index* ix);
 int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint64_t nq, uint32_t pitch, uint64_t* d_ranked, cudaStream_t s);
+// Build-side assignment (assign_all_parallel) on the tensor path: the centroid table searched like a flat f32 index with
+// k' = 16, exact scores of the survivors in the reference's arithmetic, certificate; uncertified rows are listed for the
+// exact CUDA-core kernel.  tc_assign_create leaves *out == nullptr for shapes it does not cover.
+struct TcAssignState;
+int tc_assign_create(TcAssignState** out, uint32_t dim, uint32_t nlist);
+void tc_assign_destroy(TcAssignState* st);
+int tc_assign_set_centroids(TcAssignState* st, const float* d_c, uint32_t c_ld, const float* d_assign_aux, bool cosine, cudaStream_t s);
+int tc_assign_run(TcAssignState* st, const float* d_x, uint32_t x_ld, uint64_t nr, const float* d_c, uint32_t c_ld, const float* d_assign_aux,
+                  bool cosine, uint32_t* d_assign, uint32_t* d_uncert, cudaStream_t s);
 // Test hooks: CTA (0,0) of the tensor kernel dumps the 128 x 128 values of its first tile.
 int tc_debug_enable(annb_index* ix, bool on);
 int tc_debug_fetch(annb_index* ix, float* host_out);

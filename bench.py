@@ -40,7 +40,8 @@ def parse_args():
     ap.add_argument("--workload", default="flat", choices=["flat", "ivf"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "sq8"])
     ap.add_argument("--metric", default=None, choices=[None, "cosine", "euclidean"])
-    ap.add_argument("--n", type=int, default=None)
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=None,
+                    help="database rows (use --rows under torchrun: its own parser takes a bare --n for an abbreviation of --nnodes)")
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--nq", type=int, default=10_000)
     ap.add_argument("--k", type=int, default=10)

@@ -125,6 +125,13 @@ int annb_flat_search_dev(const annb_index* index, const float* d_queries, uint64
  * index (src/quantised/ivf_sq8.rs:214-215); NULL computes the former on the device. */
 int annb_ivf_assign(const float* data, uint64_t n, uint32_t dim, const float* centroids,
                     const float* centroid_norms, uint32_t nlist, int metric, uint32_t* out_assign, int device);
+/* Tables of >= 512 centroids with rows of <= 128 f32 elements (and n >= 4096) are assigned on the tensor cores: the centroid
+ * table is searched like a flat f32 index (3xTF32 values of |c|^2 - 2 x.c or -x.c/|c|, 16 cells kept per row), the kept
+ * cells' scores are recomputed in the direct_assign arithmetic, and a row whose winner cannot be certified against the
+ * pruning threshold is redone on the exact CUDA-core kernel -- the assignments are the same bits either way.
+ * annb_assign_last_redone: rows of this thread's last annb_ivf_assign / annb_kmeans_lloyd call that were redone
+ * (diagnostic).  The environment variable ANNB200_ASSIGN_PATH=simt keeps both calls on the exact kernel. */
+uint64_t annb_assign_last_redone(void);
 
 /* Lloyd iterations of train_centroids on the device (first step of section 8f: IVF build on the GPU).  Restates the
  * unbalanced `parallel_lloyd` loop (src/utils/k_means_utils.rs:1572-1700; GPU analogue src/gpu/k_means_gpu.rs:1813-2260):

@@ -140,6 +140,59 @@ def test_coarse_assignment_matches_direct_assign(gpu):
             assert np.array_equal(a.astype(np.int64), r), f"{metric} dim={dim}"
 
 
+def _assign_redone():
+    import ctypes as C
+    f = annb200.lib().annb_assign_last_redone
+    f.restype = C.c_uint64
+    return int(f())
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("dim", [32, 50, 128])
+def test_tensor_core_assignment_matches_direct_assign(gpu, metric, dim):
+    """Tables of >= 512 centroids: annb_ivf_assign pre-selects on the tensor cores, recomputes the kept cells' scores in the
+    direct_assign arithmetic (src/utils/k_means_utils.rs:2119-2195) and certifies the winner -- the assignments must be the
+    oracle's, bit for bit, including duplicate centroids (lowest cell wins the tie) and a zero centroid."""
+    data = datagen.gaussian_noise(20000, dim, seed=71)
+    rng = np.random.default_rng(7)
+    cent = data[rng.choice(20000, 1000, replace=False)].copy()
+    cent[500:520] = cent[100:120]          # exact duplicates: ties broken by the lower cell
+    cent[777] = 0.0                        # zero centroid: cosine score 0 (1/|c| := 0), L2 score -0
+    cn = np.array([o.seq_norm_f32(r) for r in cent], np.float32)
+    a = annb200.ivf_assign(data, cent, MET[metric][0], cn if metric == "cosine" else None)
+    redone = _assign_redone()
+    r = o.assign_all(data, cent, cn, MET[metric][1])
+    assert np.array_equal(a.astype(np.int64), r), f"{metric} dim={dim}: {(a.astype(np.int64) != r).sum()} rows differ"
+    assert redone < 200, redone            # the certificate passes for nearly every row
+    assert not np.isin(a, np.arange(500, 520)).any()
+
+
+def test_tensor_core_assignment_uncertifiable_rows_are_redone(gpu):
+    """Rows that coincide with many identical centroids cannot be separated from the pruning threshold: they are redone on
+    the exact kernel and still get the lowest cell."""
+    data = datagen.gaussian_noise(8000, 32, seed=73)
+    cent = np.concatenate([np.repeat(data[:1], 40, axis=0), data[100:700]]).astype(np.float32)   # cell 0..39 identical
+    pts = np.concatenate([np.repeat(data[:1], 300, axis=0), data[1000:8000]]).astype(np.float32)
+    cn = np.array([o.seq_norm_f32(r) for r in cent], np.float32)
+    a = annb200.ivf_assign(pts, cent, annb200.L2, None)
+    assert _assign_redone() >= 300
+    r = o.assign_all(pts, cent, cn, o.L2)
+    assert np.array_equal(a.astype(np.int64), r)
+    assert (a[:300] == 0).all()
+
+
+def test_device_lloyd_on_the_tensor_path(gpu):
+    """annb_kmeans_lloyd with a table large enough for the tensor-core assignment: same iterations and centroids as the
+    restated parallel_lloyd (src/utils/k_means_utils.rs:1572-1700)."""
+    data = datagen.gaussian_noise(12000, 32, seed=77)
+    rng = np.random.default_rng(9)
+    init = data[rng.choice(12000, 600, replace=False)].copy()
+    c, it = annb200.kmeans_lloyd(data, init, annb200.L2, max_iters=6)
+    r, rit = o.parallel_lloyd(data, init, o.L2, max_iters=6)
+    assert it == rit
+    np.testing.assert_allclose(c, r, rtol=1e-5, atol=1e-5)
+
+
 def test_mirror_build_and_query(gpu):
     data = datagen.gaussian_noise(4000, 32, seed=17)
     q = datagen.subsample_with_noise(data, 50, seed=17)
