@@ -748,7 +748,7 @@ bool tc_flat_supported(const annb_index* ix, int qt, uint32_t k_eff) {
 }
 
 // Database splits per query tile: fill whole waves of 148 CTAs.
-static uint32_t pick_splits(uint64_t q_tiles, uint64_t n_tiles_db, int requested) {
+static uint32_t pick_splits(uint64_t q_tiles, uint64_t n_tiles_db, int requested, uint32_t overhead_tiles = 8) {
     if (requested > 0) return static_cast<uint32_t>(std::min<uint64_t>(requested, n_tiles_db));
     const uint64_t sms = 148;
     uint32_t best = 1;
@@ -759,8 +759,11 @@ static uint32_t pick_splits(uint64_t q_tiles, uint64_t n_tiles_db, int requested
         const uint64_t splits = (n_tiles_db + tiles_per - 1) / tiles_per;
         const uint64_t ctas = q_tiles * splits;
         const uint64_t waves = (ctas + sms - 1) / sms;
-        // work per CTA shrinks with more splits; fixed per-CTA cost ~ 8 tiles' worth (query load, pipeline fill, warm-up of the k' list)
-        const double eff = (static_cast<double>(ctas) / static_cast<double>(waves * sms)) * (static_cast<double>(tiles_per) / static_cast<double>(tiles_per + 8));
+        // work per CTA shrinks with more splits; fixed per-CTA cost ~ 8 tiles' worth (query load, pipeline fill, warm-up of the
+        // k' list) for k' = 16.  k' = 32 lists warm up much more slowly and every extra split weakens the shared threshold:
+        // measured on a 250k x 50, k = 15 shard, 5 splits 2.74 ms, 9 splits 2.88 ms, 15 splits 3.50 ms -> ~40 tiles' worth.
+        const double eff = (static_cast<double>(ctas) / static_cast<double>(waves * sms)) *
+                           (static_cast<double>(tiles_per) / static_cast<double>(tiles_per + overhead_tiles));
         if (eff > best_eff + 1e-9) { best_eff = eff; best = static_cast<uint32_t>(splits); }
     }
     return best;
@@ -818,7 +821,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     // ---- geometry ----
     const uint64_t q_tiles = nq_pad / tc::BM;
     const uint64_t db_tiles = st->n_pad / tc::BN;
-    const uint32_t splits_req = pick_splits(q_tiles, db_tiles, ix->opt_db_splits);
+    const uint32_t splits_req = pick_splits(q_tiles, db_tiles, ix->opt_db_splits, kprime == 32 ? 40u : 8u);
     const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;
     const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
     const uint32_t nb = kind == tc::KIND_TF32X3 ? 2 : 1;
