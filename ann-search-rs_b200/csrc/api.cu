@@ -724,6 +724,78 @@ void annb_destroy(annb_index* ix) {
     delete ix;
 }
 
+// out[r][c] = src[r * rs + c * cs]: 32 x 32 tiles through shared memory, so a column-major source (rs == 1) is read and the
+// row-major result written with coalesced accesses.
+static __global__ void strided_to_rowmajor_kernel(const float* __restrict__ src, uint64_t nrows, uint32_t ncols, uint64_t rs, uint64_t cs,
+                                                  float* __restrict__ out) {
+    __shared__ float tile[32][33];
+    const uint64_t r0 = static_cast<uint64_t>(blockIdx.x) * 32;
+    const uint32_t c0 = blockIdx.y * 32;
+    for (uint32_t j = threadIdx.y; j < 32; j += blockDim.y) {
+        const uint64_t r = r0 + threadIdx.x;
+        const uint32_t c = c0 + j;
+        if (r < nrows && c < ncols) tile[j][threadIdx.x] = src[r * rs + c * cs];
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.y; j < 32; j += blockDim.y) {
+        const uint64_t r = r0 + j;
+        const uint32_t c = c0 + threadIdx.x;
+        if (r < nrows && c < ncols) out[r * ncols + c] = tile[threadIdx.x][j];
+    }
+}
+
+static bool is_device_pointer(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int annb_matrix_to_flat(const float* mat, uint64_t nrows, uint32_t ncols, int64_t row_stride, int64_t col_stride, float* out_rowmajor, int device) {
+    if (!mat || !out_rowmajor || nrows == 0 || ncols == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "empty matrix");
+    if (row_stride < 0 || col_stride < 0) return fail(ANNB_ERR_UNSUPPORTED, "negative strides (reversed views) are not supported");
+    if ((row_stride == 0 && nrows > 1) || (col_stride == 0 && ncols > 1)) return fail(ANNB_ERR_INVALID_ARGUMENT, "zero stride");
+    ANNB_DEVICE(device);
+    const uint64_t rs = static_cast<uint64_t>(row_stride), cs = static_cast<uint64_t>(col_stride);
+    const uint64_t total = nrows * ncols;
+    if (cs == 1 && rs == ncols) {   // already contiguous row-major
+        ANNB_CUDA_CHECK(cudaMemcpy(out_rowmajor, mat, total * 4, cudaMemcpyDefault));
+        return ANNB_OK;
+    }
+    if (cs == 1) {                  // row-major with padded rows
+        ANNB_CUDA_CHECK(cudaMemcpy2D(out_rowmajor, ncols * 4ull, mat, rs * 4, ncols * 4ull, nrows, cudaMemcpyDefault));
+        return ANNB_OK;
+    }
+    const bool src_dev = is_device_pointer(mat), out_dev = is_device_pointer(out_rowmajor);
+    DevBuf stage, result;
+    struct Rel { DevBuf& a; DevBuf& b; ~Rel() { a.release(); b.release(); } } rel{stage, result};
+    const float* d_src = mat;
+    uint64_t k_rs = rs, k_cs = cs;
+    if (!src_dev) {
+        if (rs == 1) {              // column-major (faer's default layout), columns possibly padded: pack the columns on the way up
+            ANNB_TRY(stage.ensure(total * 4));
+            ANNB_CUDA_CHECK(cudaMemcpy2D(stage.p, nrows * 4, mat, cs * 4, nrows * 4, ncols, cudaMemcpyDefault));
+            k_cs = nrows;
+        } else {                    // both strides non-trivial: upload the spanned region as it is
+            const uint64_t span = (nrows - 1) * rs + (ncols - 1) * cs + 1;
+            if (span > 8 * total + 1024) return fail(ANNB_ERR_UNSUPPORTED, "matrix view is too sparse in its buffer (span > 8x the elements): copy it first");
+            ANNB_TRY(stage.ensure(span * 4));
+            ANNB_CUDA_CHECK(cudaMemcpy(stage.p, mat, span * 4, cudaMemcpyDefault));
+        }
+        d_src = stage.as<float>();
+    }
+    float* d_out = out_rowmajor;
+    if (!out_dev) {
+        ANNB_TRY(result.ensure(total * 4));
+        d_out = result.as<float>();
+    }
+    if ((nrows + 31) / 32 > 0x7FFFFFFFull) return fail(ANNB_ERR_UNSUPPORTED, "too many rows");
+    strided_to_rowmajor_kernel<<<dim3(static_cast<uint32_t>((nrows + 31) / 32), (ncols + 31) / 32), dim3(32, 8)>>>(d_src, nrows, ncols, k_rs, k_cs, d_out);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    if (!out_dev) ANNB_CUDA_CHECK(cudaMemcpy(out_rowmajor, d_out, total * 4, cudaMemcpyDefault));
+    else ANNB_CUDA_CHECK(cudaDeviceSynchronize());
+    return ANNB_OK;
+}
+
 int annb_flat_create(annb_index** out, const float* data, uint64_t n, uint32_t dim, int dtype, int metric,
                      const float* sq8_scales, uint64_t id_base, int device) {
     if (!out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null out");

@@ -124,6 +124,21 @@ def _metric_or_default(dist_metric: str) -> int:
     return m
 
 
+def matrix_to_flat(mat, device: int = 0) -> np.ndarray:
+    """matrix_to_flat (src/utils/mod.rs:44-68) through annb_matrix_to_flat: any positively strided 2-D f32 view (e.g. a
+    column-major / Fortran-order matrix, as faer stores them) -> contiguous row-major copy, gathered on the device."""
+    a = np.asarray(mat)
+    if a.ndim != 2 or a.dtype != np.float32:
+        raise AnnSearchError(-4, "expected a 2-D float32 matrix (samples x features)")
+    rs, cs = (st // 4 for st in a.strides)
+    out = np.empty(a.shape, dtype=np.float32)
+    f = lib().annb_matrix_to_flat
+    f.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, C.c_int64, C.c_void_p, C.c_int32]
+    f.restype = C.c_int32
+    _check(f(C.c_void_p(a.ctypes.data), a.shape[0], a.shape[1], rs, cs, _ptr(out), device))
+    return out
+
+
 def _as_rowmajor_f32(mat) -> np.ndarray:
     """matrix_to_flat (src/utils/mod.rs:44-68): any-stride matrix -> contiguous row-major f32."""
     a = np.asarray(mat)

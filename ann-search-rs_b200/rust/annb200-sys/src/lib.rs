@@ -30,6 +30,9 @@ extern "C" {
                                  out_dist: *mut f32, out_counts: *mut u32) -> c_int;
     pub fn annb_ivf_assign(data: *const f32, n: u64, dim: u32, centroids: *const f32, centroid_norms: *const f32, nlist: u32,
                            metric: c_int, out_assign: *mut u32, device: c_int) -> c_int;
+    /// `matrix_to_flat` (src/utils/mod.rs:44-68) on the device; `mat` / `out_rowmajor` host or device memory, strides in elements.
+    pub fn annb_matrix_to_flat(mat: *const f32, nrows: u64, ncols: u32, row_stride: i64, col_stride: i64, out_rowmajor: *mut f32,
+                               device: c_int) -> c_int;
     /// Diagnostic: rows of this thread's last assign / Lloyd call that failed the tensor path's certificate and were redone exactly.
     pub fn annb_assign_last_redone() -> u64;
     pub fn annb_ivf_route_dev(index: *const annb_index, d_queries: *const f32, nq: u64, dim: u32, k: u32, nprobe: u32, d_probes: *mut u32,

@@ -83,6 +83,18 @@ int annb_device_count(int* out);
  * the caller's side). */
 int annb_parse_metric(const char* s);
 
+/* ---------------------------------------------------------------- ingest -- */
+
+/* matrix_to_flat (src/utils/mod.rs:44-68) on the device: a strided samples x features view (faer MatRef: element (r, c) at
+ * mat[r * row_stride + c * col_stride], strides in elements; faer's own matrices are column-major, row_stride = 1) ->
+ * contiguous row-major f32 [nrows * ncols].  `mat` and `out_rowmajor` may each be host or device memory; a device result
+ * can be handed straight to annb_flat_create / annb_ivf_assign / annb_kmeans_lloyd, which accept device pointers for
+ * their row-major inputs.  The reference does this with a single-threaded strided gather on the host; here a
+ * column-major host matrix is packed by a strided copy on the way up and transposed in 32 x 32 shared-memory tiles.
+ * Negative strides (reversed views) are not supported. */
+int annb_matrix_to_flat(const float* mat, uint64_t nrows, uint32_t ncols, int64_t row_stride, int64_t col_stride,
+                        float* out_rowmajor, int device);
+
 /* ------------------------------------------------------------------ flat -- */
 
 /* Replaces ExhaustiveIndexGpu::new (src/gpu/exhaustive_gpu.rs:72-110), and for dtype BF16 / SQ8

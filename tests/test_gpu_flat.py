@@ -183,3 +183,30 @@ def test_concurrent_searches_on_one_handle(gpu):
     assert not errs, errs
     for t in range(4):
         assert_exact(out[t][0], out[t][1], refs[t][0], refs[t][1], f"thread {t}")
+
+
+def test_matrix_to_flat_on_device(gpu):
+    """annb_matrix_to_flat == matrix_to_flat (src/utils/mod.rs:44-68): any positively strided view -> row-major copy."""
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((1237, 70)).astype(np.float32)
+    views = {
+        "row-major": base,
+        "column-major (faer default)": np.asfortranarray(base),
+        "column-major, padded columns": np.asfortranarray(rng.standard_normal((1300, 70)).astype(np.float32))[:1237, :],
+        "row-major, padded rows": base[:, :50],
+        "both strides non-trivial": base[::2, ::3],
+        "single column": np.asfortranarray(base)[:, :1],
+        "single row": base[:1, :],
+    }
+    for name, v in views.items():
+        got = annb200.matrix_to_flat(v)
+        assert got.flags["C_CONTIGUOUS"] and np.array_equal(got.view(np.uint32), np.ascontiguousarray(v).view(np.uint32)), name
+    with pytest.raises(annb200.AnnSearchError):
+        annb200.matrix_to_flat(base[::-1])
+    # the result feeds the index constructors: a column-major matrix and its row-major copy build the same index
+    data = datagen.gaussian_noise(3000, 24, seed=5)
+    q = datagen.subsample_with_noise(data, 40, seed=5)
+    g = annb200.ExhaustiveIndexB200.new(annb200.matrix_to_flat(np.asfortranarray(data)), annb200.L2, annb200.F32)
+    ids, d, _ = g.query_batch(q, 10)
+    rids, rd, _ = o.flat_search(o.build_flat(data, o.L2, o.F32), q, 10)
+    assert_exact(ids, d, rids, rd, "index built from a column-major matrix")
