@@ -501,6 +501,7 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         pp.group = use_tc ? 128u : static_cast<uint32_t>(CTA_QUERIES);
         pp.tasks = use_tc ? reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(w) + hdr + pairs_bytes) : nullptr;
         pp.offsets = ix->d_offsets; pp.shard_row0 = ix->shard_row0;
+        pp.order = (use_tc && ix->opt_ivf_task_order) ? ix->d_list_order : nullptr;
         const uint32_t g = static_cast<uint32_t>(ceil_div<uint64_t>(slots, 256));
         ivf_count_pairs_kernel<<<g, 256, 0, s>>>(pp);
         ivf_pair_offsets_kernel<<<1, 1024, 0, s>>>(pp);
@@ -714,7 +715,7 @@ void annb_destroy(annb_index* ix) {
     tc_ivf_destroy(ix);
     tc_coarse_destroy(ix);
     cudaFree(ix->d_rows); cudaFree(ix->d_norms); cudaFree(ix->d_norms_i); cudaFree(ix->d_scales);
-    cudaFree(ix->d_centroids); cudaFree(ix->d_centroid_norms); cudaFree(ix->d_offsets); cudaFree(ix->d_original_ids);
+    cudaFree(ix->d_centroids); cudaFree(ix->d_centroid_norms); cudaFree(ix->d_offsets); cudaFree(ix->d_original_ids); cudaFree(ix->d_list_order);
     for (DevBuf* b : {&ix->s_qpad, &ix->s_qcodes, &ix->s_route, &ix->s_cdist, &ix->s_probes, &ix->s_nprobes, &ix->s_keys, &ix->s_flags,
                       &ix->s_ids, &ix->s_dist, &ix->s_cnt, &ix->s_tmp, &ix->s_pairs, &ix->s_uncert, &ix->s_fbq, &ix->s_fbr, &ix->s_fbi, &ix->s_fbd, &ix->s_fbc})
         b->release();
@@ -1134,6 +1135,14 @@ int annb_ivf_create(annb_index** out, const void* vectors, const void* norms, co
     }
     ANNB_TRY(dmalloc(&ix->d_offsets, nlist + 1, ix));
     ANNB_CUDA_CHECK(cudaMemcpyAsync(ix->d_offsets, h_off.data(), (nlist + 1) * 8ull, cudaMemcpyHostToDevice, s));
+    {   // lists by descending length: the tensor-core scan hands out its (list x query group) tasks longest first, so the
+        // tail of the dynamic schedule is made of the shortest lists
+        std::vector<uint32_t> order(nlist);
+        for (uint32_t c = 0; c < nlist; c++) order[c] = c;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return h_off[a + 1] - h_off[a] > h_off[b + 1] - h_off[b]; });
+        ANNB_TRY(dmalloc(&ix->d_list_order, nlist, ix));
+        ANNB_CUDA_CHECK(cudaMemcpy(ix->d_list_order, order.data(), nlist * 4ull, cudaMemcpyHostToDevice));
+    }
     ANNB_TRY(dmalloc(&ix->d_original_ids, std::max<uint64_t>(n_local, 1), ix));
     if (n_local) ANNB_CUDA_CHECK(cudaMemcpyAsync(ix->d_original_ids, original_ids, n_local * 8ull, cudaMemcpyDefault, s));
     if (dtype == ANNB_SQ8) {
@@ -1265,6 +1274,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "tc_debug") { DeviceGuard g(ix->device); return ix->is_ivf ? tc_ivf_debug_enable(ix, value != 0) : tc_debug_enable(ix, value != 0); }
     else if (k == "db_splits") ix->opt_db_splits = static_cast<int>(value);
     else if (k == "scan_parts") ix->opt_scan_parts = static_cast<int>(value);
+    else if (k == "ivf_task_order") ix->opt_ivf_task_order = static_cast<int>(value);
     else if (k == "ivf_list_major") ix->opt_ivf_list_major = static_cast<int>(value);
     else if (k == "ivf_fast_probe") ix->opt_ivf_fast_probe = static_cast<int>(value);
     else if (k == "ivf_tc_coarse") ix->opt_ivf_tc_coarse = static_cast<int>(value);

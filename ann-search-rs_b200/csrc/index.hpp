@@ -67,6 +67,7 @@ struct annb_index {
     float* d_centroid_norms = nullptr;
     uint64_t* d_offsets = nullptr;       // [nlist+1] global
     uint64_t* d_original_ids = nullptr;  // [n]
+    uint32_t* d_list_order = nullptr;    // [nlist] lists by descending length (task order of the tensor-core scan)
     uint64_t shard_row0 = 0;
     std::vector<uint64_t> h_offsets;
 
@@ -77,6 +78,7 @@ struct annb_index {
     int opt_db_splits = 0;
     int opt_scan_parts = 0;
     int opt_ivf_fast_probe = 1;   // rank only nprobe + 64 centroids with the fused select (0: always dense matrix + full sort)
+    int opt_ivf_task_order = 1;   // tensor-core IVF scan: 1 = tasks handed out longest list first, 0 = in list order
     int opt_ivf_list_major = -1;  // -1 auto, 0 query-major scan, 1 list-major scan
     int opt_time_kernels = 0;  // record CUDA events around the dominant kernel of every search
 

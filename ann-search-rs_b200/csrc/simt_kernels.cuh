@@ -388,6 +388,7 @@ struct PairParams {
     uint4* tasks;              // optional [2 * n_tasks]: ready-made task records {list, pair0, pairs in group, 0} {row begin, row end (u64 each)}
     const uint64_t* offsets;   // global CSR offsets (task records)
     uint64_t shard_row0;
+    const uint32_t* order;     // optional [nlist]: the order in which lists receive their task slots (task records only)
 };
 
 __global__ void ivf_count_pairs_kernel(PairParams p) {
@@ -418,10 +419,11 @@ __global__ void __launch_bounds__(1024) ivf_pair_offsets_kernel(PairParams p) {
     __syncthreads();
     a = s_pairs[threadIdx.x];
     b = s_tasks[threadIdx.x];
+    const bool reorder = p.tasks != nullptr && p.order != nullptr;
     for (uint32_t c = lo; c < hi; c++) {
         p.pair_off[c] = a; p.cursor[c] = a; p.task_off[c] = b;
         const uint32_t nt = (p.cnt[c] + p.group - 1) / p.group;
-        if (p.tasks != nullptr) {   // one record per task, so the scan kernel fetches a task with a single round trip
+        if (p.tasks != nullptr && !reorder) {   // one record per task, so the scan kernel fetches a task with a single round trip
             const uint64_t rb = p.offsets[c] - p.shard_row0, re = p.offsets[c + 1] - p.shard_row0;
             for (uint32_t g = 0; g < nt; g++) {
                 p.tasks[2 * (b + g)] = make_uint4(c, a + g * p.group, min(p.group, p.cnt[c] - g * p.group), 0u);
@@ -429,6 +431,30 @@ __global__ void __launch_bounds__(1024) ivf_pair_offsets_kernel(PairParams p) {
             }
         }
         a += p.cnt[c]; b += nt;
+    }
+    if (!reorder) return;
+    // Task slots in the caller's list order (longest list first): a second scan of the task counts over the positions of
+    // `order`; the pair offsets written above stay in list order.
+    __syncthreads();   // pair_off[] of every list is visible
+    b = 0;
+    for (uint32_t i = lo; i < hi; i++) b += (p.cnt[p.order[i]] + p.group - 1) / p.group;
+    s_tasks[threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t rb = 0;
+        for (int i = 0; i < 1024; i++) { const uint32_t tb = s_tasks[i]; s_tasks[i] = rb; rb += tb; }
+    }
+    __syncthreads();
+    b = s_tasks[threadIdx.x];
+    for (uint32_t i = lo; i < hi; i++) {
+        const uint32_t c = p.order[i];
+        const uint32_t n_c = p.cnt[c], nt = (n_c + p.group - 1) / p.group, a0 = p.pair_off[c];
+        const uint64_t rb = p.offsets[c] - p.shard_row0, re = p.offsets[c + 1] - p.shard_row0;
+        for (uint32_t g = 0; g < nt; g++) {
+            p.tasks[2 * (b + g)] = make_uint4(c, a0 + g * p.group, min(p.group, n_c - g * p.group), 0u);
+            p.tasks[2 * (b + g) + 1] = make_uint4(static_cast<uint32_t>(rb), static_cast<uint32_t>(rb >> 32), static_cast<uint32_t>(re), static_cast<uint32_t>(re >> 32));
+        }
+        b += nt;
     }
 }
 __global__ void ivf_fill_pairs_kernel(PairParams p) {

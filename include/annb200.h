@@ -236,6 +236,7 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
  *               "db_splits" (flat: database splits per query tile, 0 = auto),
  *               "scan_parts" (IVF: partial scans per query, 0 = auto),
  *               "ivf_list_major" (IVF list scan: -1 auto, 0 query-major streaming kernel, 1 list-major batched kernel),
+ *               "ivf_task_order" (tensor-core IVF scan: 1 = (list x query group) tasks are handed out longest list first, 0 = in list order),
  *               "time_kernels" (1 = bracket the dominant kernel of every search with CUDA events on its stream),
  *               "tc_ts" (tensor paths: 1 = query operand resident in TMEM), "ivf_fast_probe" (0/1/2),
  *               "ivf_tc_coarse" (1 = rank the centroids on the tensor cores when nlist >= 512, 0 = CUDA-core ranking only),
