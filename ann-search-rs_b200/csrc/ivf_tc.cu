@@ -10,6 +10,8 @@
 //     rows of the last tile that belong to the next list are masked with a NaN row constant;
 //   * each (query, rank) keeps its own k' candidates; ivf rerank recomputes the merged survivors exactly in the reference's
 //     arithmetic and orders them by (distance, list position) like SortedBuffer (src/cpu/ivf.rs:367-381).
+// Tasks arrive longest list first (ivf_pair_offsets_kernel with the index's d_list_order), and an epilogue warp hands its
+// accumulator stage back as soon as the tile's values are in registers, before any select work.
 // Replaces compute_ivf_mega_* + radix_select_ivf_topk of the reference (src/gpu/dist_gpu.rs:922-1355, src/gpu/topk_gpu.rs:599-832).
 #include <cuda.h>
 

@@ -74,6 +74,12 @@ def test_no_cpu_fallback():
     with pytest.raises(annb200.AnnSearchError) as e:
         annb200.ivf_assign(np.zeros((4, 3), np.float32), np.zeros((2, 3), np.float32), annb200.L2)
     assert e.value.variant == "Cuda"
+    with pytest.raises(annb200.AnnSearchError) as e:          # even the ingest transpose is device work
+        annb200.matrix_to_flat(np.asfortranarray(np.zeros((4, 3), np.float32)))
+    assert e.value.variant == "Cuda"
+    with pytest.raises(annb200.AnnSearchError) as e:
+        annb200.kmeans_lloyd(np.zeros((8, 3), np.float32), np.zeros((2, 3), np.float32), annb200.L2)
+    assert e.value.variant == "Cuda"
 
 
 def test_product_never_imports_the_oracle():
