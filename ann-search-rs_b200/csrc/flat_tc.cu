@@ -54,8 +54,13 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     if ((smem_u32(smem) & 1023u) != 0) __trap();
 
-    uint8_t* s_q = smem;                                                         // [NA][nslab] slabs
-    uint8_t* s_x = TS ? smem : s_q + static_cast<size_t>(NA) * p.nslab * SLAB_TILE;  // [n_stages][NB] slabs
+    // Hybrid placement (bf16 index, f32 queries): terms q0, q1 live in TMEM, q2 stays in shared memory and is multiplied by an
+    // SS-mode MMA.  The A operand of a TS-mode MMA and the epilogue's tcgen05.ld share the TMEM read path: three TMEM terms
+    // read 96 KB per tile on top of the epilogue's 64 KB, which is what paces the bf16 kernel.
+    const bool hyb = TS && KIND == KIND_BF16 && p.hybrid != 0;
+    uint8_t* s_q = smem;                                                         // [NA][nslab] slabs (hybrid: [nslab], term q2)
+    uint8_t* s_x = TS ? (hyb ? smem + static_cast<size_t>(p.nslab) * SLAB_TILE : smem)
+                      : s_q + static_cast<size_t>(NA) * p.nslab * SLAB_TILE;     // [n_stages][NB] slabs
     uint8_t* s_tail = s_x + static_cast<size_t>(p.n_stages) * NB * SLAB_TILE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail);
     uint64_t* bar_full = bars;                         // [n_stages]
@@ -63,7 +68,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     uint64_t* bar_q = bars + 2 * p.n_stages;           // [1]
     uint64_t* bar_tfull = bar_q + 1;                   // [ACC_STAGES]
     uint64_t* bar_tempty = bar_tfull + ACC_STAGES;     // [ACC_STAGES]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + ACC_STAGES);
+    uint64_t* bar_q2 = bar_tempty + ACC_STAGES;        // [1] hybrid: term q2 has landed in shared memory
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_q2 + 1);
     float* s_aux_all = reinterpret_cast<float*>(s_tail + 256);   // [8 epilogue warps][64]: per-row constants of the warp's current half tile
 
     const uint32_t q0 = blockIdx.x * BM;
@@ -74,6 +80,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.n_stages; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
         mbar_init(bar_q, TS ? EPI_THREADS : 1);
+        mbar_init(bar_q2, 1);
         for (int a = 0; a < NACC; a++) { mbar_init(bar_tfull + a, 1); mbar_init(bar_tempty + a, EPI_THREADS); }
         fence_barrier_init();
         fence_proxy_async();
@@ -95,6 +102,11 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     for (uint32_t s = 0; s < p.nslab; s++)
                         tma_load_2d(smem_u32(s_q + (static_cast<size_t>(a) * p.nslab + s) * SLAB_TILE), &tm_q, bar_q, s * SLAB_ELEMS,
                                     a * p.nq_pad + q0);
+            }
+            if (hyb) {
+                mbar_expect_tx(bar_q2, p.nslab * SLAB_TILE);
+                for (uint32_t s = 0; s < p.nslab; s++)
+                    tma_load_2d(smem_u32(s_q + static_cast<size_t>(s) * SLAB_TILE), &tm_q, bar_q2, s * SLAB_ELEMS, 2 * p.nq_pad + q0);
             }
             uint32_t it = 0;
             long long w_prod = 0;
@@ -119,6 +131,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         constexpr uint32_t idesc = make_idesc(KIND);
         constexpr uint32_t SLAB_DESC = SLAB_TILE >> 4;    // descriptor start-address units (16 B) per slab
         mbar_wait(bar_q, 0);
+        if (hyb) mbar_wait(bar_q2, 0);
         tc_fence_after();
         const uint32_t q_desc0 = make_smem_desc(smem_u32(s_q));   // low descriptor words; the constant high word is added by umma()
         const uint32_t x_desc0 = make_smem_desc(smem_u32(s_x));
@@ -156,7 +169,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                             umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
                             if (p.a_pieces > 1) {
                                 umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
-                                umma_ts<KIND>(tmem_c, a0 + 2 * PIECE_COLS, xd + 2 * k, idesc, 1u);
+                                if (hyb) umma<KIND>(tmem_c, qd + 2 * k, xd + 2 * k, idesc, 1u);
+                                else umma_ts<KIND>(tmem_c, a0 + 2 * PIECE_COLS, xd + 2 * k, idesc, 1u);
                             }
                         } else if (KIND == KIND_TF32X3) {
                             // s = Qhi.Xhi + Qlo.Xhi + Qhi.Xlo   (the lo.lo term is below 2^-22 relative)
@@ -202,7 +216,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             // (even pieces to half 0, odd to half 1); thread = query row = TMEM lane, 32 columns (128 B of the row) per
             // tcgen05.st.  16-bit operands sit two per column, low half = even k, exactly as in memory.
             const uint32_t row_words = p.kp * ELEM / 4;
-            for (uint32_t pc = half; pc < p.a_pieces; pc += 2) {
+            const uint32_t tmem_pieces = hyb ? 2u : p.a_pieces;
+            for (uint32_t pc = half; pc < tmem_pieces; pc += 2) {
                 const uint32_t* src = reinterpret_cast<const uint32_t*>(p.q_op) + (static_cast<size_t>(pc) * p.nq_pad + q0 + row_in_tile) * row_words;
                 const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + pc * PIECE_COLS;
                 for (uint32_t c = 0; c < row_words; c += 32) {
@@ -827,7 +842,8 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     const uint32_t nb = kind == tc::KIND_TF32X3 ? 2 : 1;
     // query operand resident in TMEM (TS-mode MMA) when its pieces fit their column budget (bf16 terms: 64 columns each)
     const bool ts = kind == tc::KIND_I8 || (ix->opt_tc_ts != 0 && (kind != tc::KIND_BF16 || kp * elem <= 256));
-    const size_t q_smem = ts ? 0 : static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * st->nslab * tc::SLAB_TILE;
+    const bool hyb = ts && kind == tc::KIND_BF16 && na == 3 && ix->opt_tc_bf16_hybrid != 0;
+    const size_t q_smem = ts ? (hyb ? static_cast<size_t>(st->nslab) * tc::SLAB_TILE : 0) : static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * st->nslab * tc::SLAB_TILE;
     const size_t fixed = 256 /*barriers*/ + 8 * 64 * 4 /*per-warp row constants*/;
     const size_t budget = 227 * 1024;
     if (q_smem + fixed + nb * tc::SLAB_TILE > budget) { set_last_error("tensor path: query tile too large for shared memory"); return ANNB_ERR_UNSUPPORTED; }
@@ -840,7 +856,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     ANNB_CUDA_CHECK(cudaMemsetAsync(st->gtau.p, 0xFF, static_cast<uint64_t>(nq_pad) * 4, s));
     tc::Params p{};
     p.nq = nq; p.n_rows = ix->n; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
-    p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = na; p.aux = st->d_aux;
+    p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = na; p.aux = st->d_aux; p.hybrid = hyb ? 1u : 0u;
     p.part_keys = st->part.as<uint64_t>(); p.dbg = st->dbg.as<float>(); p.gtau = st->gtau.as<uint32_t>(); p.q_op = st->q_op.as<void>(); p.kp = kp; p.dbg_cycles = st->dbgc.as<unsigned long long>();
     {
         dim3 grid(static_cast<uint32_t>(q_tiles), splits);

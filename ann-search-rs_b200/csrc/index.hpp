@@ -74,6 +74,7 @@ struct annb_index {
     // options
     int opt_path = ANNB_PATH_AUTO;
     int opt_tc_candidates = 0;
+    int opt_tc_bf16_hybrid = 0; // flat tensor path, bf16 index + f32 queries: third query term in shared memory (SS-mode MMA) instead of TMEM
     int opt_tc_ts = 1;         // tensor path, f32: keep the query operand in TMEM (TS-mode MMA)
     int opt_db_splits = 0;
     int opt_scan_parts = 0;

@@ -33,6 +33,7 @@ struct Params {
     uint32_t n_splits;
     uint64_t rows_per_split;  // multiple of BN
     uint32_t a_pieces;        // query terms actually present (bf16 self query: 1)
+    uint32_t hybrid;          // bf16, queries in TMEM: the third query term stays in shared memory and is issued as an SS-mode MMA
     const float* aux;         // per database row: L2  v = aux - 2 s  (aux = |x|^2, pad rows +inf);
                               //                   cos v = s * aux    (aux = -1/|x|, pad rows +inf -> 0 * inf = NaN, never selected)
     uint64_t* part_keys;      // [nq][2 * n_splits][KPRIME] packed (approx value, row); one list per 64-column half

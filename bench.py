@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--kmeans-iters", type=int, default=8)
     ap.add_argument("--tc-candidates", type=int, default=0, choices=[0, 16, 32], help="k' of the tensor-core pre-selection (0 = library default)")
     ap.add_argument("--replicated-routing", action="store_true", help="multi-GPU IVF: every rank ranks the centroids for the whole batch (no probe exchange)")
+    ap.add_argument("--bf16-hybrid", type=int, default=-1, choices=[-1, 0, 1], help="flat bf16 tensor path: third query term in shared memory (-1 = library default)")
     ap.add_argument("--db-splits", type=int, default=0, help="flat tensor path: database splits per query tile (0 = library default)")
     ap.add_argument("--self-queries", action="store_true",
                     help="flat: the batch is database rows [0, nq) themselves (one batch of generate_knn; BASELINE configs[4]: --n 2000000 --dim 50 --k 15 --metric euclidean)")
@@ -288,6 +289,8 @@ def run_b200(args):
         index.set_option("cert_eps_log2", args.cert_eps_log2)
     if args.db_splits:
         index.set_option("db_splits", args.db_splits)
+    if args.bf16_hybrid >= 0:
+        index.set_option("tc_bf16_hybrid", args.bf16_hybrid)
     if args.no_cert_fallback:
         index.set_option("cert_fallback", 0)
     if args.workload == "ivf" and args.list_major >= 0:

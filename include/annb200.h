@@ -238,7 +238,8 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
  *               "ivf_list_major" (IVF list scan: -1 auto, 0 query-major streaming kernel, 1 list-major batched kernel),
  *               "ivf_task_order" (tensor-core IVF scan: 1 = (list x query group) tasks are handed out longest list first, 0 = in list order),
  *               "time_kernels" (1 = bracket the dominant kernel of every search with CUDA events on its stream),
- *               "tc_ts" (tensor paths: 1 = query operand resident in TMEM), "ivf_fast_probe" (0/1/2),
+ *               "tc_ts" (tensor paths: 1 = query operand resident in TMEM), "tc_bf16_hybrid" (flat BF16 index, f32 queries: 1 = third
+ *               query term multiplied from shared memory instead of TMEM; experiment, default 0), "ivf_fast_probe" (0/1/2),
  *               "ivf_tc_coarse" (1 = rank the centroids on the tensor cores when nlist >= 512, 0 = CUDA-core ranking only),
  *               "cert_eps_log2" (error bound assumed by the coverage certificate of the tensor paths, default -19; 0 = off),
  *               "cert_fallback" (1 = queries that fail the certificate are recomputed on the exact CUDA-core path)

@@ -156,3 +156,30 @@ def test_second_chance_certificate(gpu, dtype):
         ids, d, _ = g.query_batch(q, 10)
         assert g.get_stat("uncertified") <= 5, (e, g.get_stat("uncertified"))
         assert_exact(ids, d, ref[0], ref[1], f"second chance {dtype} eps=2^{e}")
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("dim", [128, 50])
+def test_bf16_hybrid_operand_placement(gpu, metric, dim):
+    """Option tc_bf16_hybrid: the third bf16 term of the f32 query is multiplied from shared memory (SS-mode MMA) instead of
+    TMEM.  Same selection values (tile (0,0) against a float64 product of the bf16-decoded rows) and the oracle's results."""
+    data = datagen.gaussian_noise(20000, dim, seed=23)
+    q = datagen.subsample_with_noise(data, 300, seed=23)
+    g, c = _pair(data, "bf16", metric)
+    g.set_option("tc_bf16_hybrid", 1)
+    g.set_option("tc_debug", 1)
+    g.set_option("db_splits", 1)
+    ids, d, cnt = g.query_batch(q, 10)
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    v = g.debug_fetch_tile().astype(np.float64)
+    x = o.decode_bf16(c.vectors[:128]).astype(np.float64)
+    s = q[:128].astype(np.float64) @ x.T
+    want = (x * x).sum(1)[None, :] - 2 * s if metric == "l2" else -s / c.norms[:128].astype(np.float64)[None, :]
+    err = np.abs(v - want).max() / np.abs(want).max()
+    assert err < 2e-6, f"tile error {err:.3e}"
+    rids, rd, rcnt = o.flat_search(c, q, 10)
+    assert_exact(ids, d, rids, rd, f"hybrid bf16 {metric} dim={dim}")
+    g.set_option("tc_debug", 0)
+    g.set_option("db_splits", 0)
+    ids, d, cnt = g.query_batch(q, 10)
+    assert_exact(ids, d, rids, rd, f"hybrid bf16 {metric} dim={dim}, auto splits")
