@@ -10,7 +10,7 @@ data = datagen.correlated(n, dim, seed=42)
 q = datagen.subsample_with_noise(data, nq, seed=42)
 lib = annb200.lib()
 lib.annb_debug_fetch_cycles.argtypes = [C.c_void_p, C.c_void_p]
-for name, dt in (("f32", annb200.F32), ("bf16", annb200.BF16)):
+for name, dt in (("f32", annb200.F32), ("bf16", annb200.BF16), ("sq8", annb200.SQ8)):
     g = annb200.ExhaustiveIndexB200.new(data, annb200.COSINE, dt)
     g.set_option("path", annb200.PATH_TENSOR)
     g.set_option("tc_debug", 1)
