@@ -400,25 +400,44 @@ __global__ void ivf_count_pairs_kernel(PairParams p) {
     const uint32_t c = p.probes[i];
     if (c >= p.list_begin && c < p.list_end) atomicAdd(p.cnt + c, 1u);
 }
+// Exclusive scan of one value per thread over a block of 1024 threads (warp shuffles + one shared row of warp totals);
+// *total receives the block sum.  Every thread of the block must call it.
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* s_warp /*[33]*/) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= static_cast<uint32_t>(off)) incl += t;
+    }
+    __syncthreads();                       // s_warp may still be read from a previous call
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t w = s_warp[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, off);
+            if (lane >= static_cast<uint32_t>(off)) wi += t;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) s_warp[32] = wi;
+    }
+    __syncthreads();
+    return incl - v + s_warp[warp];
+}
 // Single block: exclusive scans of the per-list pair counts and task counts (nlist <= 16384).
 __global__ void __launch_bounds__(1024) ivf_pair_offsets_kernel(PairParams p) {
-    __shared__ uint32_t s_pairs[1024], s_tasks[1024];
+    __shared__ uint32_t s_warp[33];
     const uint32_t per = (p.nlist + 1023) / 1024;
     const uint32_t lo = min(p.nlist, threadIdx.x * per), hi = min(p.nlist, lo + per);
     uint32_t a = 0, b = 0;
     for (uint32_t c = lo; c < hi; c++) { a += p.cnt[c]; b += (p.cnt[c] + p.group - 1) / p.group; }
-    s_pairs[threadIdx.x] = a;
-    s_tasks[threadIdx.x] = b;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t ra = 0, rb = 0;
-        for (int i = 0; i < 1024; i++) { uint32_t ta = s_pairs[i], tb = s_tasks[i]; s_pairs[i] = ra; s_tasks[i] = rb; ra += ta; rb += tb; }
-        p.pair_off[p.nlist] = ra;
-        p.task_off[p.nlist] = rb;
-    }
-    __syncthreads();
-    a = s_pairs[threadIdx.x];
-    b = s_tasks[threadIdx.x];
+    a = block_exclusive_scan_1024(a, s_warp);
+    if (threadIdx.x == 0) p.pair_off[p.nlist] = s_warp[32];
+    b = block_exclusive_scan_1024(b, s_warp);
+    if (threadIdx.x == 0) p.task_off[p.nlist] = s_warp[32];
     const bool reorder = p.tasks != nullptr && p.order != nullptr;
     for (uint32_t c = lo; c < hi; c++) {
         p.pair_off[c] = a; p.cursor[c] = a; p.task_off[c] = b;
@@ -435,17 +454,9 @@ __global__ void __launch_bounds__(1024) ivf_pair_offsets_kernel(PairParams p) {
     if (!reorder) return;
     // Task slots in the caller's list order (longest list first): a second scan of the task counts over the positions of
     // `order`; the pair offsets written above stay in list order.
-    __syncthreads();   // pair_off[] of every list is visible
     b = 0;
     for (uint32_t i = lo; i < hi; i++) b += (p.cnt[p.order[i]] + p.group - 1) / p.group;
-    s_tasks[threadIdx.x] = b;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t rb = 0;
-        for (int i = 0; i < 1024; i++) { const uint32_t tb = s_tasks[i]; s_tasks[i] = rb; rb += tb; }
-    }
-    __syncthreads();
-    b = s_tasks[threadIdx.x];
+    b = block_exclusive_scan_1024(b, s_warp);   // (its barriers also make pair_off[] of every list visible)
     for (uint32_t i = lo; i < hi; i++) {
         const uint32_t c = p.order[i];
         const uint32_t n_c = p.cnt[c], nt = (n_c + p.group - 1) / p.group, a0 = p.pair_off[c];
