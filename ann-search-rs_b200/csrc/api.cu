@@ -629,10 +629,8 @@ static int search_host(annb_index* ix, bool ivf, int mode, const float* queries,
         ANNB_TRY(ix->s_ids.ensure(nb * k * 8ull));
         ANNB_TRY(ix->s_dist.ensure(nb * k * 4ull));
         ANNB_TRY(ix->s_cnt.ensure(nb * 4ull));
-        const uint64_t* row_map = nullptr;
         if (ivf) {
             ANNB_TRY(ivf_core(ix, pq, nb, k, nprobe, nullptr, ix->s_ids.as<uint64_t>(), ix->s_dist.as<float>(), ix->s_cnt.as<uint32_t>(), s));
-            (void)row_map;
         } else {
             ANNB_TRY(flat_core(ix, pq, nb, k, ix->s_ids.as<uint64_t>(), ix->s_dist.as<float>(), ix->s_cnt.as<uint32_t>(), s));
         }
