@@ -795,6 +795,41 @@ int annb_matrix_to_flat(const float* mat, uint64_t nrows, uint32_t ncols, int64_
     return ANNB_OK;
 }
 
+// bincode 2 "standard" variable-length integers (the crate persists its Vec<usize> fields with them, src/serialise/mod.rs:51-64):
+// u < 251 one byte; then a marker byte 251 / 252 / 253 followed by the value as little-endian u16 / u32 / u64.  Host code only.
+int64_t annb_varint_encode_u64(const uint64_t* values, uint64_t count, uint8_t* out, uint64_t out_capacity) {
+    if ((!values && count) || (!out && out_capacity)) { fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer"); return -1; }
+    uint64_t w = 0;
+    for (uint64_t i = 0; i < count; i++) {
+        const uint64_t v = values[i];
+        const uint32_t nbytes = v < 251 ? 0u : (v <= 0xFFFFull ? 2u : (v <= 0xFFFFFFFFull ? 4u : 8u));
+        if (w + 1 + nbytes > out_capacity) { fail(ANNB_ERR_INVALID_ARGUMENT, "varint output buffer too small"); return -1; }
+        if (nbytes == 0) { out[w++] = static_cast<uint8_t>(v); continue; }
+        out[w++] = nbytes == 2 ? 251 : (nbytes == 4 ? 252 : 253);
+        for (uint32_t b = 0; b < nbytes; b++) out[w++] = static_cast<uint8_t>(v >> (8 * b));
+    }
+    return static_cast<int64_t>(w);
+}
+// Decodes `count` values; returns the number of bytes consumed, -1 if the buffer ends early or holds a marker this format
+// does not produce for 64-bit values (254 = u128, 255 = reserved).
+int64_t annb_varint_decode_u64(const uint8_t* buf, uint64_t len, uint64_t count, uint64_t* out) {
+    if ((!buf && len) || (!out && count)) { fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer"); return -1; }
+    uint64_t r = 0;
+    for (uint64_t i = 0; i < count; i++) {
+        if (r >= len) return -1;
+        const uint8_t m = buf[r++];
+        if (m < 251) { out[i] = m; continue; }
+        if (m > 253) return -1;
+        const uint32_t nbytes = m == 251 ? 2u : (m == 252 ? 4u : 8u);
+        if (r + nbytes > len) return -1;
+        uint64_t v = 0;
+        for (uint32_t b = 0; b < nbytes; b++) v |= static_cast<uint64_t>(buf[r + b]) << (8 * b);
+        r += nbytes;
+        out[i] = v;
+    }
+    return static_cast<int64_t>(r);
+}
+
 int annb_flat_create(annb_index** out, const float* data, uint64_t n, uint32_t dim, int dtype, int metric,
                      const float* sq8_scales, uint64_t id_base, int device) {
     if (!out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null out");

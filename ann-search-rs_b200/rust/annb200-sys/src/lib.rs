@@ -33,6 +33,9 @@ extern "C" {
     /// `matrix_to_flat` (src/utils/mod.rs:44-68) on the device; `mat` / `out_rowmajor` host or device memory, strides in elements.
     pub fn annb_matrix_to_flat(mat: *const f32, nrows: u64, ncols: u32, row_stride: i64, col_stride: i64, out_rowmajor: *mut f32,
                                device: c_int) -> c_int;
+    /// bincode "standard" varints of the crate's `Vec<usize>` fields (host only; the Rust side has bincode itself).
+    pub fn annb_varint_encode_u64(values: *const u64, count: u64, out: *mut u8, out_capacity: u64) -> i64;
+    pub fn annb_varint_decode_u64(buf: *const u8, len: u64, count: u64, out: *mut u64) -> i64;
     /// Diagnostic: rows of this thread's last assign / Lloyd call that failed the tensor path's certificate and were redone exactly.
     pub fn annb_assign_last_redone() -> u64;
     pub fn annb_ivf_route_dev(index: *const annb_index, d_queries: *const f32, nq: u64, dim: u32, k: u32, nprobe: u32, d_probes: *mut u32,

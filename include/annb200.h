@@ -95,6 +95,12 @@ int annb_parse_metric(const char* s);
 int annb_matrix_to_flat(const float* mat, uint64_t nrows, uint32_t ncols, int64_t row_stride, int64_t col_stride,
                         float* out_rowmajor, int device);
 
+/* Host-only helpers for the crate's on-disk format (src/serialise/mod.rs: bincode 2 "standard" configuration): the
+ * variable-length encoding of its Vec<usize> fields.  encode returns the bytes written, decode the bytes consumed for
+ * `count` values; -1 on a short buffer or a marker byte that 64-bit values never produce.  No device is touched. */
+int64_t annb_varint_encode_u64(const uint64_t* values, uint64_t count, uint8_t* out, uint64_t out_capacity);
+int64_t annb_varint_decode_u64(const uint8_t* buf, uint64_t len, uint64_t count, uint64_t* out);
+
 /* ------------------------------------------------------------------ flat -- */
 
 /* Replaces ExhaustiveIndexGpu::new (src/gpu/exhaustive_gpu.rs:72-110), and for dtype BF16 / SQ8

@@ -20,7 +20,7 @@ def _declared_symbols():
 
 def test_header_declares_the_expected_surface():
     syms = _declared_symbols()
-    for s in ["annb_flat_create", "annb_flat_search", "annb_flat_search_self", "annb_flat_search_dev", "annb_ivf_assign", "annb_assign_last_redone", "annb_matrix_to_flat", "annb_kmeans_lloyd",
+    for s in ["annb_flat_create", "annb_flat_search", "annb_flat_search_self", "annb_flat_search_dev", "annb_ivf_assign", "annb_assign_last_redone", "annb_matrix_to_flat", "annb_varint_encode_u64", "annb_varint_decode_u64", "annb_kmeans_lloyd",
               "annb_ivf_create", "annb_ivf_search", "annb_ivf_search_self", "annb_ivf_search_dev", "annb_ivf_route_dev", "annb_ivf_search_probes_dev", "annb_merge_topk_dev",
               "annb_destroy", "annb_last_error", "annb_index_get_info", "annb_index_set_option", "annb_index_get_stat"]:
         assert s in syms
