@@ -33,3 +33,24 @@ def test_defaults():
     assert annb200.default_nlist(10_000_000) == 3162     # src/cpu/ivf.rs:172
     assert annb200.default_nprobe(4096) == 64            # src/cpu/ivf.rs:345-347
     assert annb200.default_nprobe(1) == 1
+
+
+def test_bench_row_count_flag_survives_torchrun(monkeypatch):
+    """torch.distributed.run abbreviates its own options, so a bare `--n` after the script name is rejected as ambiguous
+    (--nnodes / --nproc-per-node / ...): multi-GPU launches pass `--rows`, which no launcher option starts with."""
+    import importlib.util
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "8", "--rows", "2000000", "--dim", "50", "--k", "15", "--self-queries"])
+    a = bench.parse_args()
+    assert a.n == 2_000_000 and a.gpus == 8 and a.self_queries and a.k == 15
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--n", "1234"])
+    assert bench.parse_args().n == 1234
+    from torch.distributed.run import get_args_parser
+    launcher = {s for act in get_args_parser()._actions for s in act.option_strings}
+    for flag in ("--rows", "--gpus", "--steps", "--warmup", "--workload", "--dtype", "--nprobe", "--self-queries", "--impl"):
+        assert not any(opt.startswith(flag) for opt in launcher), flag
