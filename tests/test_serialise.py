@@ -115,3 +115,47 @@ def test_rejects_files_that_are_not_indices_or_are_cut_short(tmp_path):
         S._header("a" * 256, 4)
     assert e.value.variant == "EncodeError"
     assert len(S._header("a" * 255, 4)) == 14 + 255
+
+
+def _build_cpp_tool():
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "ann-search-rs_b200")
+    os.makedirs(os.path.join(pkg, "build"), exist_ok=True)
+    exe = os.path.join(pkg, "build", "serialise_roundtrip")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-o", exe, os.path.join(pkg, "host", "tests", "serialise_roundtrip.cpp"),
+           "-L" + os.path.join(pkg, "lib"), "-lannb200", "-Wl,-rpath," + os.path.join(pkg, "lib"),
+           "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return exe
+
+
+def test_cpp_mirror_reads_and_rewrites_the_same_bytes(tmp_path):
+    """host/annb200_serialise.hpp and annb200/serialise.py agree byte for byte, and name the same error variants."""
+    import subprocess
+    exe = _build_cpp_tool()
+    a, b = tmp_path / "py", tmp_path / "cpp"
+    for d in (a / "ex", a / "ivf", b / "ex", b / "ivf"):
+        d.mkdir(parents=True)
+    data = datagen.gaussian_noise(500, 10, seed=3)
+    norms = np.array([o.l2_norm_f32(r) for r in data], np.float32)
+    S.save_exhaustive(str(a / "ex"), data, 1, norms)
+    ix = o.build_ivf(data, o.COSINE, nlist=300, kmeans_iters=2)          # 300 lists: offsets cross the one-byte varint range
+    S.save_ivf(str(a / "ivf"), ix.vectors, 1, ix.centroids, ix.offsets, ix.original_ids, norms=ix.norms, centroid_norms=ix.centroid_norms)
+    for kind, sub in (("exhaustive", "ex"), ("ivf", "ivf")):
+        r = subprocess.run([exe, kind, str(a / sub), str(b / sub)], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.strip() == "OK", r.stdout + r.stderr
+        assert open(a / sub / S.INDEX_FILE, "rb").read() == open(b / sub / S.INDEX_FILE, "rb").read(), kind
+    raw = open(a / "ex" / S.INDEX_FILE, "rb").read()
+    cases = {"NotAnIndexFile": b"definitely not an index", "TruncatedIndexFile": raw[:12], "DecodeError": raw[:len(raw) // 2],
+             "TrailingBytes": raw + bytes(28), "UnsupportedFormatVersion": raw[:8] + (3).to_bytes(4, "little") + raw[12:],
+             "FloatWidthMismatch": raw[:12] + bytes([8]) + raw[13:]}
+    for want, content in cases.items():
+        open(b / "ex" / S.INDEX_FILE, "wb").write(content)
+        r = subprocess.run([exe, "variant", "exhaustive", str(b / "ex")], capture_output=True, text=True)
+        assert r.stdout.strip() == want, (want, r.stdout)
+    r = subprocess.run([exe, "variant", "exhaustive", str(a / "ivf")], capture_output=True, text=True)
+    assert r.stdout.strip() == "IndexKindMismatch"
+    r = subprocess.run([exe, "variant", "ivf", str(tmp_path / "missing")], capture_output=True, text=True)
+    assert r.stdout.strip() == "IoError"
