@@ -251,7 +251,7 @@ static int read_ivf_stats(annb_index* ix, cudaStream_t s);
 // Number of queries of the tensor-path call just issued on `s` that failed the coverage certificate (synchronises s).
 static int read_uncertified(annb_index* ix, uint32_t* out, cudaStream_t s) {
     *out = 0;
-    if (!ix->opt_cert_fallback || ix->opt_cert_eps <= 0.f || !ix->s_uncert.p) return ANNB_OK;
+    if (!ix->opt_cert_fallback || ix->opt_cert_eps == 0.f || !ix->s_uncert.p) return ANNB_OK;
     ANNB_CUDA_CHECK(cudaMemcpyAsync(out, ix->s_uncert.p, 4, cudaMemcpyDeviceToHost, s));
     ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
     return ANNB_OK;
@@ -1304,7 +1304,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "tc_ts") ix->opt_tc_ts = static_cast<int>(value);
     else if (k == "tc_bf16_hybrid") ix->opt_tc_bf16_hybrid = static_cast<int>(value);
     else if (k == "cert_fallback") ix->opt_cert_fallback = static_cast<int>(value);
-    else if (k == "cert_eps_log2") ix->opt_cert_eps = value == 0 ? 0.f : std::ldexp(1.0f, static_cast<int>(value));   // e.g. -18; 0 switches the certificate off
+    else if (k == "cert_eps_log2") ix->opt_cert_eps = value == 0 ? 0.f : (value > 0 ? -1.0f : std::ldexp(1.0f, static_cast<int>(value)));   // e.g. -18; 0 switches the certificate off; 1 = derived bound (default)
     else if (k == "tc_debug") { DeviceGuard g(ix->device); return ix->is_ivf ? tc_ivf_debug_enable(ix, value != 0) : tc_debug_enable(ix, value != 0); }
     else if (k == "db_splits") ix->opt_db_splits = static_cast<int>(value);
     else if (k == "scan_parts") ix->opt_scan_parts = static_cast<int>(value);

@@ -121,7 +121,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                                     b * p.n_pad + row0);
                 }
             }
-            if (p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0) p.dbg_cycles[1] = w_prod;
+            if (TC_COUNTERS && p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0) p.dbg_cycles[1] = w_prod;
         }
         __syncwarp();
     } else if (warp == 1) {
@@ -137,7 +137,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const uint32_t x_desc0 = make_smem_desc(smem_u32(s_x));
         uint32_t it = 0;
         long long w_full = 0, w_tempty = 0;
-        const long long t_start = clock64();
+        const long long t_start = tc_clock();
         for (uint32_t t = 0; t < n_tiles; t++) {
             const uint32_t acc = t % NACC, aph = (t / NACC) & 1u;
             mbar_wait_timed(bar_tempty + acc, aph ^ 1u, w_tempty);
@@ -191,8 +191,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 __syncwarp();
             }
         }
-        if (p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
-            p.dbg_cycles[0] = clock64() - t_start;
+        if (TC_COUNTERS && p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+            p.dbg_cycles[0] = tc_clock() - t_start;
             p.dbg_cycles[2] = w_full;
             p.dbg_cycles[3] = w_tempty;
             p.dbg_cycles[6] = n_tiles;
@@ -298,14 +298,14 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     for (int j = 0; j < 64; j++) p.dbg[row_in_tile * BN + c * 64 + j] = v[j];
                 }
                 if (m < tau) {
-                    const long long ts0 = clock64();
+                    const long long ts0 = tc_clock();
                     select_from_tile<KP>(top, tau, v, gm, m, row0 + c * 64, scratch);
-                    w_slow += clock64() - ts0;
+                    w_slow += tc_clock() - ts0;
                 }
             }
             if (!DENSE && (top.tau() < g_tau || (g_tau != g_tau && top.tau() < INFINITY))) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));
         }
-        if (p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) { p.dbg_cycles[4] = w_tfull; p.dbg_cycles[5] = w_slow; }
+        if (TC_COUNTERS && p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) { p.dbg_cycles[4] = w_tfull; p.dbg_cycles[5] = w_slow; }
         const uint64_t q = static_cast<uint64_t>(q0) + row_in_tile;
         if (!DENSE && q < p.nq) {
             uint64_t* out = p.part_keys + (q * (2 * p.n_splits) + 2 * blockIdx.y + half) * KP;
@@ -492,23 +492,25 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(CoarseSelectParams p
     // 4. certified prefix
     float bound = INFINITY;
     if (partial) {
-        float qn2 = 0.f;
+        double qn2 = 0.0;   // f64: the value -> distance map must not add rounding of its own
         for (uint32_t e = lane; e < p.dim; e += 32) {
-            const float x = reinterpret_cast<const float*>(qrow)[e];
-            qn2 = fmaf(x, x, qn2);
+            const double x = reinterpret_cast<const float*>(qrow)[e];
+            qn2 += x * x;
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) qn2 += __shfl_xor_sync(0xFFFFFFFFu, qn2, off);
-        const float tv = ordered_to_f32(thr);   // every non-candidate's approximate value exceeds this
+        const double tv = ordered_to_f32(thr);   // every non-candidate's approximate value exceeds this
+        double b;
         if (MET == MET_L2) {
-            const float s = sqrtf(qn2) + p.cnorm_max;            // value = dist - |q|^2, error <= eps (|q| + |c|max)^2
-            bound = tv + qn2 - p.eps * s * s;
+            const double s = sqrt(qn2) + p.cnorm_max;            // value = dist - |q|^2, error <= eps (|q| + |c|max)^2
+            b = tv + qn2 - p.eps * s * s;
         } else if (MET == MET_COS) {
-            const float qq = sqrtf(qn2);                          // value = (dist - 1) |q|, error <= eps |q|
-            bound = qq > 0.f ? tv / qq + 1.0f - p.eps : -INFINITY;
+            const double qq = qn;                                 // value = (dist - 1) |q| with the reference's |q|, error <= eps
+            b = qq > 0.0 ? tv / qq + 1.0 - p.eps : -INFINITY;
         } else {
-            bound = tv + 1.0f - p.eps * fmaxf(1.0f, sqrtf(qn2) * p.cnorm_max);   // pre-normalised: value = dist - 1
+            b = tv + 1.0 - p.eps * fmax(1.0, sqrt(qn2) * p.cnorm_max);   // pre-normalised: value = dist - 1
         }
+        bound = __double2float_rd(b);
     }
     for (uint32_t j = lane; j < p.pitch; j += 32) {
         const uint64_t key = keys[j];
@@ -748,6 +750,42 @@ void tc_destroy(annb_index* ix) {
     ix->tc = nullptr;
 }
 
+// Error bound of the tensor-core pre-selection values, in the units the coverage certificates test:
+// |reference-order distance - distance implied by the selection value| <= eps * (|q| + |x|max)^2 (L2) or eps (cosine).
+//   E  = bound of |s - q.x| / (|q||x|) for the accumulated tensor-core dot s:
+//        operand representation (f32: dropped lo.lo term + residuals of the hi/lo splits; bf16 index: residual of the
+//        query's bf16 terms, the stored rows are exact) + TC_MMA_ULPS * 2^-23 per accumulating MMA instruction of a tile
+//        row (each tcgen05.mma K step adds its products to the f32 accumulator; modelled as at most TC_MMA_ULPS ulp of
+//        a partial sum bounded by |q||x| -- truncation or better; tests/test_gpu_tensor.py::test_adversarial_* measures it)
+//   +  the reference's own rounding: 8 lanes x dim/8 sequential adds + the reduce tree + finish (dist.rs:306-330)
+//   +  the epilogue's fma / multiply, the row constant (computed in f64, rounded once) and the value -> distance map.
+constexpr double TC_MMA_ULPS = 1.0;
+float tc_cert_eps(const annb_index* ix, int kind, uint32_t kp_elems, uint32_t terms, bool inkernel_split) {
+    if (ix->opt_cert_eps >= 0.f) return ix->opt_cert_eps;     // caller override ("cert_eps_log2"), 0 = certificate off
+    const bool l2 = ix->metric == ANNB_L2;
+    const double u23 = std::ldexp(1.0, -23), u24 = std::ldexp(1.0, -24);
+    double E;
+    if (kind == tc::KIND_I8) {
+        // exact integer dots.  L2 (dim <= 256: sums < 2^24 are exact in f32): only a tie between the k-th distance and the
+        // k'-th selection value has to be excluded (pruning is strict); cosine: a few roundings on an exact dot.
+        if (l2 && ix->dim <= 256) return 1e-30f;
+        if (!l2) return 4.7683716e-07f;   // 2^-21: the reference divides the exact integer dot by two square roots -- a handful of roundings on each side
+        E = 0.0;
+    } else if (kind == tc::KIND_TF32X3) {
+        const double n_mma = 3.0 * (kp_elems / 8);
+        // flat: q and x both split with cvt.rna (2^-22 residual each) + dropped lo.lo (2^-22); IVF in-kernel split: x hi
+        // truncated, lo rounded (2^-21 residual), dropped lo.lo <= 2^-21, query residual 2^-22
+        E = (inkernel_split ? 5.0 : 3.0) * std::ldexp(1.0, -22) + TC_MMA_ULPS * n_mma * u23;
+    } else {
+        const double n_mma = static_cast<double>(terms) * (kp_elems / 16);
+        const double repr = terms >= 3 ? std::ldexp(1.0, -27) : (terms == 2 ? std::ldexp(1.0, -18) : 0.0);   // residual of the query's bf16 terms (self queries: exact)
+        E = repr + TC_MMA_ULPS * n_mma * u23;
+    }
+    const double ref = (ix->dim / 8 + 8) * u24;
+    const double eps = l2 ? (E / 2 + ref) : (E * (1.0 + 1.0 / 128) + ref + 6 * u24);
+    return static_cast<float>(eps);
+}
+
 static uint32_t pick_kprime(const annb_index* ix, uint32_t k_eff) {
     if (ix->opt_tc_candidates == 16 || ix->opt_tc_candidates == 32) return std::max<uint32_t>(ix->opt_tc_candidates, k_eff <= 16 ? 16 : 32);
     return k_eff <= 10 ? 16 : 32;
@@ -884,11 +922,8 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     r.bf16_self = bf16_self; r.id_base = ix->id_base; r.out_ids = d_ids; r.out_dist = d_dist; r.out_counts = d_cnt;
     ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));
     ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
-    // SQ8 L2 (dim <= 256): the pre-selection values are exact integers, so the certificate only has to exclude a tie between
-    // the k-th exact distance and the k'-th pre-selected value (pruning is strict, a tied row of lower id could have been dropped)
-    r.cert_eps = (kind == tc::KIND_I8 && ix->metric != ANNB_COSINE && ix->dim <= 256) ? std::min(ix->opt_cert_eps, 1e-30f) : ix->opt_cert_eps;
-    // SQ8 cosine: the selection value is two float operations on an exact integer dot (a few ulp): 2^-21 bounds it
-    if (kind == tc::KIND_I8 && ix->metric == ANNB_COSINE) r.cert_eps = std::min(r.cert_eps, 4.7683716e-07f); r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
+    r.cert_eps = tc_cert_eps(ix, kind, kp, na, false);
+    r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
     const bool cos = ix->metric == ANNB_COSINE;
     int rc;
     if (ix->dtype == ANNB_SQ8) rc = cos ? launch_rerank<2, QT_I8, MET_COS>(r, s) : launch_rerank<2, QT_I8, MET_L2>(r, s);
@@ -1001,7 +1036,7 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     tc::CoarseSelectParams c{};
     c.dense = st->dense.as<float>(); c.dense_ld = st->n_pad; c.nq = nq; c.nlist = ix->nlist; c.pitch = pitch; c.cmax = next_pow2(pitch + 1);
     c.queries = d_route; c.q_ld = route_ld; c.centroids = ix->d_centroids; c.c_ld = ix->cent_ld; c.centroid_norms = ix->d_centroid_norms;
-    c.dim = ix->dim; c.eps = ix->opt_cert_eps; c.cnorm_max = ix->tc_cnorm_max; c.ranked = d_ranked;
+    c.dim = ix->dim; c.eps = tc_cert_eps(ix, tc::KIND_TF32X3, kp, 2, false); c.cnorm_max = ix->tc_cnorm_max; c.ranked = d_ranked;
     if (ix->metric == ANNB_L2) ANNB_TRY(launch_coarse_select<MET_L2>(c, s));
     else if (ix->dtype == ANNB_SQ8) ANNB_TRY(launch_coarse_select<MET_COS_PRENORM>(c, s));
     else ANNB_TRY(launch_coarse_select<MET_COS>(c, s));

@@ -100,7 +100,7 @@ struct annb_index {
     cudaStream_t stream = nullptr;
     annb::DevBuf s_qpad, s_qcodes, s_route, s_cdist, s_probes, s_nprobes, s_keys, s_flags, s_ids, s_dist, s_cnt, s_tmp, s_pairs;
     float tc_xnorm_max = 0.f;      // largest stored-row norm (coverage certificate of the tensor paths, L2)
-    float opt_cert_eps = 1.9073486e-06f;  // 2^-19: error bound of the pre-selection values (relative to (|q|+|x|max)^2 / |q|), see DESIGN.md section 3
+    float opt_cert_eps = -1.0f;    // < 0: derived per kernel from its MMA count (tc_cert_eps); >= 0: caller override, 0 = certificate off
     int opt_cert_fallback = 1;     // re-run uncertified queries on the exact CUDA-core path
     mutable int64_t stat_fallback_queries = 0;  // cumulative
     bool skip_next_ivf_stats = false;

@@ -114,12 +114,12 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     TopList<KP> top;
     float scratch[64];
 
-    const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0;
+    const bool dbg_on = TC_COUNTERS && p.dbg != nullptr && blockIdx.x == 0;
     long long c_sched = 0, c_gather = 0, c_tfull = 0, c_wq = 0, c_wdata = 0, c_wtempty = 0, c_tasks = 0, c_tiles = 0;
-    const long long c_start = clock64();
+    const long long c_start = tc_clock();
     for (;;) {
         __syncthreads();   // every role has finished the previous task (TMEM query region and s_task are reusable)
-        const long long c_t0 = clock64();
+        const long long c_t0 = tc_clock();
         if (threadIdx.x == 0) {
             const uint32_t task = atomicAdd(p.task_counter, 1u);
             if (task < total_tasks) {
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
         }
         __syncthreads();
         if (s_task[3] == 0) break;
-        const long long c_t1 = clock64();
+        const long long c_t1 = tc_clock();
         c_sched += c_t1 - c_t0;
         const uint32_t pair0 = s_task[1], n_in_group = s_task[2];
         const uint64_t r_begin = s_rows[0], r_end = s_rows[1];
@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(bar_q);
-                c_gather += clock64() - c_t1;
+                c_gather += tc_clock() - c_t1;
             }
             top.init();
             uint32_t* gtau_ptr = p.gtau + (has_query ? pr.x : 0);
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
         c_tiles += n_tiles;
     }
     if (dbg_on) {
-        if (threadIdx.x == 0) { p.dbg[0] = clock64() - c_start; p.dbg[1] = c_sched; p.dbg[7] = (static_cast<unsigned long long>(c_tasks) << 32) | static_cast<unsigned long long>(c_tiles); }
+        if (threadIdx.x == 0) { p.dbg[0] = tc_clock() - c_start; p.dbg[1] = c_sched; p.dbg[7] = (static_cast<unsigned long long>(c_tasks) << 32) | static_cast<unsigned long long>(c_tiles); }
         if (threadIdx.x == 32) { p.dbg[4] = c_wq; p.dbg[5] = c_wdata; p.dbg[6] = c_wtempty; }
         if (threadIdx.x == EPI_WARP0 * 32) { p.dbg[2] = c_gather; p.dbg[3] = c_tfull; }
     }
@@ -567,8 +567,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     r.out_ids = d_ids; r.out_dist = d_dist; r.out_counts = d_cnt;
     ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));
     ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
-    r.cert_eps = (st->kind == tc::KIND_I8 && l2 && ix->dim <= 256) ? std::min(ix->opt_cert_eps, 1e-30f) : ix->opt_cert_eps;   // exact integers: tie check only
-    if (st->kind == tc::KIND_I8 && !l2) r.cert_eps = std::min(r.cert_eps, 4.7683716e-07f);   // SQ8 cosine: a few ulp on an exact integer dot
+    r.cert_eps = tc_cert_eps(ix, st->kind, st->kp_elems, 3, st->kind == tc::KIND_TF32X3);
     r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
     int rc;
     if (ix->dtype == ANNB_SQ8) rc = l2 ? launch_ivf_rerank<2, MET_L2>(r, s) : launch_ivf_rerank<2, MET_COS>(r, s);

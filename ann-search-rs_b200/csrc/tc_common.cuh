@@ -75,10 +75,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000ll) __trap();
     }
 }
+// Role counters (tools/tc_cycles.py, tools/ivf_cycles.py) exist only in the -DANNB_TC_COUNTERS build
+// (lib/libannb200_counters.so): the production kernels carry no clock reads on their per-tile chains.
+#ifdef ANNB_TC_COUNTERS
+constexpr bool TC_COUNTERS = true;
+__device__ __forceinline__ long long tc_clock() { return clock64(); }
+#else
+constexpr bool TC_COUNTERS = false;
+__device__ __forceinline__ long long tc_clock() { return 0; }
+#endif
 __device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, long long& acc) {
-    const long long t0 = clock64();
+    const long long t0 = tc_clock();
     mbar_wait(bar, parity);
-    acc += clock64() - t0;
+    acc += tc_clock() - t0;
 }
 // One lane of a converged warp (elect.sync): lets the compiler keep the surrounding values in uniform registers.
 __device__ __forceinline__ bool elect_one() {
@@ -377,12 +386,12 @@ static __global__ void aux_kernel(const uint8_t* __restrict__ rows, uint32_t row
                 }
                 o = static_cast<float>(s);
             } else {
-                float s = 0.f;
+                double s = 0.0;   // f64, rounded once: the certificates budget 2^-24 |x|^2 for this constant
                 for (uint32_t e = 0; e < dim; e++) {
-                    const float x = rt == 1 ? bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(r)[e]) : reinterpret_cast<const float*>(r)[e];
-                    s = fmaf(x, x, s);
+                    const double x = rt == 1 ? bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(r)[e]) : reinterpret_cast<const float*>(r)[e];
+                    s += x * x;
                 }
-                o = s;
+                o = static_cast<float>(s);
             }
         }
     }
@@ -504,23 +513,30 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
             return make_key(finish_fp<MET>(raw[0], qn, xn), idx);
         }
     };
-    // coverage test: every row that was not re-ranked has an approximate value >= a_thr; is the k-th exact distance safely below?
+    // coverage test: every row that was not re-ranked has an approximate value >= a_thr; is the k-th exact distance safely
+    // below the distance that value stands for?  (one thread, f64: the map itself must not add rounding of its own)
     auto covered = [&](float a_thr, float dk) -> bool {
-        float qn2 = 0.f;
+        double qn2 = 0.0;
         for (uint32_t e = 0; e < p.dim; e++) {
-            float x;
-            if constexpr (QT == QT_I8) x = static_cast<float>(reinterpret_cast<const int8_t*>(qv)[e]);
-            else x = load1<(QT == QT_F32) ? 4 : 2>(qv, e);
-            qn2 = fmaf(x, x, qn2);
+            double x;
+            if constexpr (QT == QT_I8) x = static_cast<double>(reinterpret_cast<const int8_t*>(qv)[e]);
+            else x = static_cast<double>(load1<(QT == QT_F32) ? 4 : 2>(qv, e));
+            qn2 += x * x;
         }
         if (MET == MET_L2) {
             // approx value = |x|^2 - 2 q.x = dist - |q|^2 ; error <= eps * (|q| + |x|max)^2
-            const float s = sqrtf(qn2) + p.xnorm_max;
-            return (a_thr + qn2 - p.cert_eps * s * s) > dk;
+            const double s = sqrt(qn2) + static_cast<double>(p.xnorm_max);
+            return (static_cast<double>(a_thr) + qn2 - static_cast<double>(p.cert_eps) * s * s) > static_cast<double>(dk);
         }
-        // approx value = -q.x / |x| = (dist - 1) * |q| ; error <= eps * |q|
-        const float qn = sqrtf(qn2);
-        return qn > 0.f ? ((a_thr / qn + 1.0f - p.cert_eps) > dk) : true;
+        // approx value = -q.x / |x| = (dist - 1) * |q| with the reference's own |q| (sequential fold, bf16-rounded for
+        // bf16 self queries; sqrt of the integer norm for SQ8) ; error <= eps
+        double qn = sqrt(qn2);
+        if constexpr (QT != QT_I8) {
+            float qf = seq_norm<(QT == QT_F32) ? 4 : 2>(qv, p.dim);
+            if (p.bf16_self) qf = round_to_bf16(qf);
+            qn = static_cast<double>(qf);
+        }
+        return qn > 0.0 ? ((static_cast<double>(a_thr) / qn + 1.0 - static_cast<double>(p.cert_eps)) > static_cast<double>(dk)) : true;
     };
     __shared__ int s_extend;
     if (threadIdx.x < 64) exact[threadIdx.x] = (threadIdx.x < p.kp) ? exact_of(keys[threadIdx.x]) : KEY_SENTINEL;

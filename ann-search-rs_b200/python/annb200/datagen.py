@@ -1,6 +1,6 @@
 """Synthetic inputs: numpy restatement of examples/commons/mod.rs generators.
 
-TEST / BENCH INFRASTRUCTURE (inputs only).  Structure and constants follow
+Inputs only: used by bench.py, tools/ and tests/ (no search arithmetic lives here).  Structure and constants follow
 /root/reference/examples/commons/mod.rs; the random stream is numpy's PCG64
 because rand 0.9's StdRng (ChaCha12) stream cannot be reproduced without a Rust
 toolchain -- the *distribution* matches, individual samples do not.

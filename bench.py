@@ -121,7 +121,7 @@ def measured_peaks():
 
 
 def make_data(args):
-    from oracle import datagen
+    from annb200 import datagen
     kind = "correlated"
     n = args.n
     data = datagen.make(kind, n, args.dim, seed=42)

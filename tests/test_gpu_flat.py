@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 
 import annb200
-from oracle import datagen, oracle as o
+from annb200 import datagen
+from oracle import oracle as o
 from util import assert_exact, assert_tolerance
 
 pytestmark = pytest.mark.gpu

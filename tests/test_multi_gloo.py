@@ -11,7 +11,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from annb200 import distributed as D
-from oracle import datagen, oracle as o
+from annb200 import datagen
+from oracle import oracle as o
 
 
 def _free_port():

@@ -8,7 +8,8 @@ import pytest
 
 import annb200
 from annb200 import serialise as S
-from oracle import datagen, oracle as o
+from annb200 import datagen
+from oracle import oracle as o
 
 
 def _saved_exhaustive(tmp_path, metric=0):

@@ -21,7 +21,7 @@ for p in (ROOT, os.path.join(ROOT, "ann-search-rs_b200", "python")):
         sys.path.insert(0, p)
 
 import annb200  # noqa: E402
-from oracle import datagen  # noqa: E402
+from annb200 import datagen  # noqa: E402
 
 
 def correlated_gpu(n, dim, device, seed=42, n_clusters=datagen.DEFAULT_N_CLUSTERS, chunk=1 << 20):

@@ -4,7 +4,7 @@ import ctypes as C, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, ROOT + "/ann-search-rs_b200/python"]
 import numpy as np, annb200
-from oracle import datagen
+from annb200 import datagen
 redone = annb200.lib().annb_assign_last_redone
 redone.restype = C.c_uint64
 d = datagen.correlated(250_000, 128, seed=42)

@@ -5,7 +5,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "ann-search-rs_b200", "python")]
 import annb200
-from oracle import datagen, oracle as o
+from annb200 import datagen
+from oracle import oracle as o
 
 def same(a, b): return np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint32), b[1].view(np.uint32))
 

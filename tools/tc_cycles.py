@@ -4,7 +4,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "ann-search-rs_b200", "python")]
 import annb200
-from oracle import datagen
+from annb200 import datagen
 n, dim, nq = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000, 128, int(sys.argv[2]) if len(sys.argv) > 2 else 10_000
 data = datagen.correlated(n, dim, seed=42)
 q = datagen.subsample_with_noise(data, nq, seed=42)
