@@ -242,22 +242,56 @@ static int prepare_self(annb_index* ix, uint64_t pos_begin, uint64_t nq, bool ne
 }
 
 // ---------------------------------------------------------------------------
+// Status words.  A search batch is enqueued optimistically (tensor-core ranking / pre-selection); what may force a
+// second look -- a probe set that outgrew its ranked prefix, queries that failed the coverage certificate -- is written
+// by the kernels into two small device blocks and read back ONCE per batch into a pinned host block, together with the
+// batch's results when the caller wants them on the host (no extra synchronisation on that path).
+// ---------------------------------------------------------------------------
+struct CoreState {
+    bool tensor = false;    // the batch went through a tensor-path kernel with a coverage certificate
+    bool routed = false;    // centroid ranking ran in this call (probe statistics and the overflow flag are meaningful)
+    int stage = -1;         // IVF ranking stage used: 3 tensor cores, 2 fused CUDA-core select, 1 dense + ranked prefix, 0 dense + full sort
+    uint32_t pitch = 0;     // IVF: probe pitch of the lists in s_probes
+};
+struct HostStatus {          // layout of ix->h_status (pinned)
+    uint32_t overflow, export_overflow;
+    unsigned long long scanned, probed, local;
+    uint32_t n_unc, pad1;
+};
+
+static int enqueue_status_read(annb_index* ix, const CoreState& cs, cudaStream_t s) {
+    HostStatus* h = reinterpret_cast<HostStatus*>(ix->h_status);
+    std::memset(h, 0, sizeof(HostStatus));
+    if (cs.routed) ANNB_CUDA_CHECK(cudaMemcpyAsync(h, ix->s_flags.p, 32, cudaMemcpyDeviceToHost, s));
+    if (cs.tensor && ix->s_uncert.p) ANNB_CUDA_CHECK(cudaMemcpyAsync(&h->n_unc, ix->s_uncert.p, 4, cudaMemcpyDeviceToHost, s));
+    return ANNB_OK;
+}
+static bool wants_status(const annb_index* ix, const CoreState& cs) {
+    return cs.routed || (cs.tensor && ix->opt_cert_fallback && ix->opt_cert_eps != 0.f);
+}
+
+// Calls on one handle share its scratch buffers; the mutex orders the host side, this orders the device side when
+// consecutive calls use different streams.
+static int order_after_previous(annb_index* ix, cudaStream_t s) {
+    if (ix->last_event_valid && s != ix->last_stream) ANNB_CUDA_CHECK(cudaStreamWaitEvent(s, ix->last_event, 0));
+    return ANNB_OK;
+}
+static int mark_call_done(annb_index* ix, cudaStream_t s) {
+    if (!ix->last_event) ANNB_CUDA_CHECK(cudaEventCreateWithFlags(&ix->last_event, cudaEventDisableTiming));
+    ANNB_CUDA_CHECK(cudaEventRecord(ix->last_event, s));
+    ix->last_event_valid = true;
+    ix->last_stream = s;
+    return ANNB_OK;
+}
+
+// ---------------------------------------------------------------------------
 // flat search core (device pointers, asynchronous on s)
 // ---------------------------------------------------------------------------
 static int flat_simt(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint32_t kk, uint64_t* d_ids, float* d_dist,
                      uint32_t* d_cnt, cudaStream_t s, bool is_fallback = false);
-static int read_ivf_stats(annb_index* ix, cudaStream_t s);
 
-// Number of queries of the tensor-path call just issued on `s` that failed the coverage certificate (synchronises s).
-static int read_uncertified(annb_index* ix, uint32_t* out, cudaStream_t s) {
-    *out = 0;
-    if (!ix->opt_cert_fallback || ix->opt_cert_eps == 0.f || !ix->s_uncert.p) return ANNB_OK;
-    ANNB_CUDA_CHECK(cudaMemcpyAsync(out, ix->s_uncert.p, 4, cudaMemcpyDeviceToHost, s));
-    ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
-    return ANNB_OK;
-}
-static int flat_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint64_t* d_ids, float* d_dist,
-                     uint32_t* d_cnt, cudaStream_t s) {
+static int flat_enqueue(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint64_t* d_ids, float* d_dist,
+                        uint32_t* d_cnt, cudaStream_t s, CoreState* cs) {
     const uint32_t kk = static_cast<uint32_t>(std::min<uint64_t>(k, ix->n));
     if (kk == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "k must be >= 1");
     bool use_tc = false;
@@ -268,30 +302,33 @@ static int flat_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uin
     }
     if (use_tc) {
         ix->stat_last_path = ANNB_PATH_TENSOR;
-        ANNB_TRY(tc_flat_search(ix, pq.scan, pq.scan_bytes, pq.qt, pq.bf16_self, nq, kk, k, d_ids, d_dist, d_cnt, s));
-        // queries whose pre-selection could not be certified are recomputed on the exact path (rare)
-        uint32_t n_unc = 0;
-        ANNB_TRY(read_uncertified(ix, &n_unc, s));
-        if (n_unc == 0) return ANNB_OK;
-        const uint32_t* list = ix->s_uncert.as<uint32_t>() + 1;
-        PreparedQueries sub = pq;
-        ANNB_TRY(ix->s_fbq.ensure(static_cast<uint64_t>(n_unc) * pq.scan_bytes));
-        gather_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * (pq.scan_bytes >> 4), 256), 256, 0, s>>>(pq.scan, pq.scan_bytes, list, n_unc, ix->s_fbq.as<uint8_t>());
-        ANNB_CUDA_CHECK(cudaGetLastError());
-        sub.scan = ix->s_fbq.as<uint8_t>();
-        ANNB_TRY(ix->s_fbi.ensure(static_cast<uint64_t>(n_unc) * k * 8));
-        ANNB_TRY(ix->s_fbd.ensure(static_cast<uint64_t>(n_unc) * k * 4));
-        ANNB_TRY(ix->s_fbc.ensure(static_cast<uint64_t>(n_unc) * 4));
-        ANNB_TRY(flat_simt(ix, sub, n_unc, k, kk, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(), ix->s_fbc.as<uint32_t>(), s, true));
-        scatter_results_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * k, 256), 256, 0, s>>>(list, n_unc, k, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(),
-                                                                                             ix->s_fbc.as<uint32_t>(), d_ids, d_dist, d_cnt);
-        ANNB_CUDA_CHECK(cudaGetLastError());
-        ix->stat_launches += 2;
-        ix->stat_fallback_queries += n_unc;
-        return ANNB_OK;
+        cs->tensor = true;
+        return tc_flat_search(ix, pq.scan, pq.scan_bytes, pq.qt, pq.bf16_self, nq, kk, k, d_ids, d_dist, d_cnt, s);
     }
     ix->stat_last_path = ANNB_PATH_SIMT;
     return flat_simt(ix, pq, nq, k, kk, d_ids, d_dist, d_cnt, s);
+}
+
+// Queries whose pre-selection could not be certified are recomputed on the exact path (rare) and scattered over their rows.
+static int flat_fallback(annb_index* ix, const PreparedQueries& pq, uint32_t k, uint32_t n_unc, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt,
+                         cudaStream_t s) {
+    const uint32_t kk = static_cast<uint32_t>(std::min<uint64_t>(k, ix->n));
+    const uint32_t* list = ix->s_uncert.as<uint32_t>() + 1;
+    PreparedQueries sub = pq;
+    ANNB_TRY(ix->s_fbq.ensure(static_cast<uint64_t>(n_unc) * pq.scan_bytes));
+    gather_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * (pq.scan_bytes >> 4), 256), 256, 0, s>>>(pq.scan, pq.scan_bytes, list, n_unc, ix->s_fbq.as<uint8_t>());
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    sub.scan = ix->s_fbq.as<uint8_t>();
+    ANNB_TRY(ix->s_fbi.ensure(static_cast<uint64_t>(n_unc) * k * 8));
+    ANNB_TRY(ix->s_fbd.ensure(static_cast<uint64_t>(n_unc) * k * 4));
+    ANNB_TRY(ix->s_fbc.ensure(static_cast<uint64_t>(n_unc) * 4));
+    ANNB_TRY(flat_simt(ix, sub, n_unc, k, kk, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(), ix->s_fbc.as<uint32_t>(), s, true));
+    scatter_results_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * k, 256), 256, 0, s>>>(list, n_unc, k, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(),
+                                                                                         ix->s_fbc.as<uint32_t>(), d_ids, d_dist, d_cnt);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    ix->stat_launches += 2;
+    ix->stat_fallback_queries += n_unc;
+    return ANNB_OK;
 }
 
 // Exact CUDA-core flat search (tile_kernel + finalize).
@@ -325,66 +362,57 @@ static int flat_simt(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uin
 // IVF search core
 // ---------------------------------------------------------------------------
 struct RouteOut { uint32_t* probes; uint32_t* n_probes; uint32_t pitch; };
-static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint32_t nprobe, const uint64_t* row_map,
-                    uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s, bool force_simt = false,
-                    const uint32_t* preset_probes = nullptr, const uint32_t* preset_nprobes = nullptr, uint32_t preset_pitch = 0,
-                    const RouteOut* route_out = nullptr) {
-    // preset_*: probe lists already computed for these queries (the exact fallback of the tensor path re-uses the
-    // parent call's ranking instead of ranking the centroids again; sharded searches route a slice of the batch per rank).
-    // route_out: stop after the routing stage and export the probe lists.
-    const uint32_t kk = static_cast<uint32_t>(std::min<uint64_t>(k, ix->n_total));
-    if (kk == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "k must be >= 1");
-    if (kk > 1024) return fail(ANNB_ERR_UNSUPPORTED, "k > 1024 is not supported");
-    // nprobe default and clamp: src/cpu/ivf.rs:345-347
-    uint32_t np = nprobe ? nprobe : std::max<uint32_t>(1, static_cast<uint32_t>(std::sqrt(static_cast<double>(ix->nlist))));
-    np = std::min(np, ix->nlist);
-    const uint32_t nl2 = next_pow2(ix->nlist);
-    if (static_cast<size_t>(nl2) * 8 > 200 * 1024) return fail(ANNB_ERR_UNSUPPORTED, "nlist > 16384 is not supported yet");
 
-    // 1+2 (fast path). rank only the `pitch` nearest centroids: the tile kernel's fused select replaces the dense
-    //      [nq][nlist] matrix and the full per-query sort; a one-thread-per-query walk applies the probe-expansion rule.
+static void fill_probe_params(annb_index* ix, ProbeParams& pp, uint64_t nq, uint32_t np, uint32_t kk, uint32_t pitch) {
+    pp.nq = nq; pp.nlist = ix->nlist; pp.offsets = ix->d_offsets; pp.nprobe = np; pp.k = kk;
+    pp.probes = ix->s_probes.as<uint32_t>(); pp.probe_pitch = pitch; pp.n_probes = ix->s_nprobes.as<uint32_t>();
+    pp.overflow = ix->s_flags.as<uint32_t>();
+    pp.stat_scanned = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 8);
+    pp.stat_probed = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 16);
+    pp.list_begin = ix->list_begin; pp.list_end = ix->list_end;
+}
+
+// Centroid ranking + probe expansion (src/cpu/ivf.rs:349-365) into s_probes / s_nprobes.  Stages, most optimistic first:
+//   3  dense approximate values on the tensor cores, per query radix select of the nearest np + 32 cells, exact distances
+//      for those, certified (distance, cell) prefix, probe walk;
+//   2  exact fused select of a short ranked prefix on the CUDA cores (tile_kernel<EPI_SELECT>), probe walk;
+//   1  exact dense matrix (get_centroids_dist / _prenorm arithmetic) + full per-query sort, probes cut at the prefix pitch;
+//   0  the same with pitch = nlist (cannot overflow).
+// Stages 3..1 raise the overflow flag (s_flags[0]) when some query needs more cells than the stage can rank (or certify);
+// nothing is read back here -- the caller repeats the batch from the next stage if the flag turns out set.
+static int ivf_route(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t np, uint32_t kk, int stage_start, bool force_simt,
+                     CoreState* cs, cudaStream_t s) {
     ANNB_TRY(ix->s_flags.ensure(64));
     ANNB_TRY(ix->s_nprobes.ensure(nq * 4));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 64, s));
+    cs->routed = true;
     // ranked prefix length: room for probe expansion (>= nprobe + 16 cells) and pitch + 64 a power of two, so the fused
     // select's sort buffer is exactly full (smaller shared memory -> more resident CTAs)
-    uint32_t pitch = ix->nlist <= 1024 ? ix->nlist : std::min(ix->nlist, next_pow2(np + 16 + 64) - 64);
-    bool probes_ready = false;
-    if (preset_probes) { pitch = preset_pitch; probes_ready = true; }
-    ix->stat_coarse_path = 0;
-    // 1+2 (tensor path). dense approximate values on the tensor cores, then per query: radix select of the nearest
-    //      np + 32 cells, exact distances for those, certified (distance, cell) prefix -> the same probe walk.
-    if (!probes_ready && !force_simt && ix->opt_path != ANNB_PATH_SIMT && ix->opt_ivf_tc_coarse && tc_coarse_supported(ix)) {
+    const uint32_t pitch_short = ix->nlist <= 1024 ? ix->nlist : std::min(ix->nlist, next_pow2(np + 16 + 64) - 64);
+    if (stage_start >= 3 && !force_simt && ix->opt_path != ANNB_PATH_SIMT && ix->opt_ivf_tc_coarse && tc_coarse_supported(ix)) {
         const uint32_t p_tc = round_up(np + 32u, 32u);
         if (p_tc < ix->nlist && p_tc <= 480) {
             ANNB_TRY(ix->s_cdist.ensure(nq * static_cast<uint64_t>(p_tc) * 8));
             ANNB_TRY(ix->s_probes.ensure(nq * static_cast<uint64_t>(p_tc) * 4));
-            ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 64, s));
             ANNB_TRY(tc_coarse_rank(ix, pq.route, pq.route_ld, nq, p_tc, ix->s_cdist.as<uint64_t>(), s));
             ProbeParams pp{};
-            pp.nq = nq; pp.nlist = ix->nlist; pp.offsets = ix->d_offsets; pp.nprobe = np; pp.k = kk;
-            pp.probes = ix->s_probes.as<uint32_t>(); pp.probe_pitch = p_tc; pp.n_probes = ix->s_nprobes.as<uint32_t>();
-            pp.overflow = ix->s_flags.as<uint32_t>();
-            pp.stat_scanned = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 8);
-            pp.stat_probed = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 16);
-            pp.list_begin = ix->list_begin; pp.list_end = ix->list_end;
+            fill_probe_params(ix, pp, nq, np, kk, p_tc);
             probe_walk_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 128)), 128, 0, s>>>(ix->s_cdist.as<uint64_t>(), pp);
             ANNB_CUDA_CHECK(cudaGetLastError());
             ix->stat_launches++;
-            uint32_t h_flag[2];
-            ANNB_CUDA_CHECK(cudaMemcpyAsync(h_flag, ix->s_flags.p, sizeof(h_flag), cudaMemcpyDeviceToHost, s));
-            ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
-            if (!h_flag[0]) { probes_ready = true; pitch = p_tc; ix->stat_coarse_path = 2; }   // else: some rank was not certifiable -> exact ranking below
+            cs->stage = 3; cs->pitch = p_tc; ix->stat_coarse_path = 2;
+            return ANNB_OK;
         }
     }
     // (wide prefixes make the fused select's sort buffers large and its pass rate high: above 64 ranks the dense matrix + sort wins)
-    if (!probes_ready && pitch < ix->nlist && (ix->opt_ivf_fast_probe == 1 ? pitch <= 64 : ix->opt_ivf_fast_probe != 0)) {
+    if (stage_start >= 2 && pitch_short < ix->nlist && (ix->opt_ivf_fast_probe == 1 ? pitch_short <= 64 : ix->opt_ivf_fast_probe != 0)) {
+        const uint32_t pitch = pitch_short;
         const uint32_t nsort = WarpSelect::sort_size(pitch);
         const uint32_t cb = ix->cent_ld * 4, qb = pq.route_ld * 4;
         const size_t smem = tile_kernel_smem(cb, qb, nsort, true);
         if (smem <= 200 * 1024) {
             ANNB_TRY(ix->s_cdist.ensure(nq * static_cast<uint64_t>(pitch) * 8));
             ANNB_TRY(ix->s_probes.ensure(nq * static_cast<uint64_t>(pitch) * 4));
-            ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 64, s));
             TileParams p{};
             p.rows = reinterpret_cast<const uint8_t*>(ix->d_centroids); p.n_rows = ix->nlist; p.row_bytes = cb; p.row_norms = ix->d_centroid_norms;
             p.queries = reinterpret_cast<const uint8_t*>(pq.route); p.q_bytes = qb; p.nq = nq; p.dim = ix->dim;
@@ -394,25 +422,19 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
             else if (ix->dtype == ANNB_SQ8) ANNB_TRY((launch_tile<0, QT_F32, MET_COS_PRENORM, EPI_SELECT>(p, grid, smem, s)));
             else ANNB_TRY((launch_tile<0, QT_F32, MET_COS, EPI_SELECT>(p, grid, smem, s)));
             ProbeParams pp{};
-            pp.nq = nq; pp.nlist = ix->nlist; pp.offsets = ix->d_offsets; pp.nprobe = np; pp.k = kk;
-            pp.probes = ix->s_probes.as<uint32_t>(); pp.probe_pitch = pitch; pp.n_probes = ix->s_nprobes.as<uint32_t>();
-            pp.overflow = ix->s_flags.as<uint32_t>();
-            pp.stat_scanned = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 8);
-            pp.stat_probed = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 16);
-            pp.list_begin = ix->list_begin; pp.list_end = ix->list_end;
+            fill_probe_params(ix, pp, nq, np, kk, pitch);
             probe_walk_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 128)), 128, 0, s>>>(ix->s_cdist.as<uint64_t>(), pp);
             ANNB_CUDA_CHECK(cudaGetLastError());
             ix->stat_launches += 2;
-            uint32_t h_flag[2];
-            ANNB_CUDA_CHECK(cudaMemcpyAsync(h_flag, ix->s_flags.p, sizeof(h_flag), cudaMemcpyDeviceToHost, s));
-            ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
-            if (!h_flag[0]) { probes_ready = true; ix->stat_coarse_path = 1; }
-            else pitch = ix->nlist;      // rare: some query needs more than nprobe + 64 cells -> full ranking below
+            cs->stage = 2; cs->pitch = pitch; ix->stat_coarse_path = 1;
+            return ANNB_OK;
         }
     }
-    // 1. query -> all centroids (dense), reference arithmetic of get_centroids_dist / _prenorm
-    if (!probes_ready) ANNB_TRY(ix->s_cdist.ensure(nq * static_cast<uint64_t>(ix->nlist) * 4));
-    if (!probes_ready) {
+    // query -> all centroids (dense), reference arithmetic of get_centroids_dist / _prenorm; full per-query sort
+    const uint32_t nl2 = next_pow2(ix->nlist);
+    const uint32_t pitch = stage_start >= 1 ? pitch_short : ix->nlist;
+    ANNB_TRY(ix->s_cdist.ensure(nq * static_cast<uint64_t>(ix->nlist) * 4));
+    {
         TileParams p{};
         p.rows = reinterpret_cast<const uint8_t*>(ix->d_centroids); p.n_rows = ix->nlist; p.row_bytes = ix->cent_ld * 4;
         p.row_norms = ix->d_centroid_norms;
@@ -425,47 +447,52 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         else ANNB_TRY((launch_tile<0, QT_F32, MET_COS, EPI_DENSE>(p, grid, smem, s)));
         ix->stat_launches++;
     }
-    // 2. rank + probe expansion (full per-query sort)
-    for (int attempt = 0; attempt < 2 && !probes_ready; attempt++) {
-        ANNB_TRY(ix->s_probes.ensure(nq * static_cast<uint64_t>(pitch) * 4));
-        ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 64, s));
-        ProbeParams pp{};
-        pp.cdist = ix->s_cdist.as<float>(); pp.nq = nq; pp.nlist = ix->nlist; pp.nlist_pow2 = nl2; pp.offsets = ix->d_offsets;
-        pp.nprobe = np; pp.k = kk; pp.probes = ix->s_probes.as<uint32_t>(); pp.probe_pitch = pitch;
-        pp.n_probes = ix->s_nprobes.as<uint32_t>();
-        pp.overflow = ix->s_flags.as<uint32_t>();
-        pp.stat_scanned = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 8);
-        pp.stat_probed = reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 16);
-            pp.list_begin = ix->list_begin; pp.list_end = ix->list_end;
-        size_t smem = static_cast<size_t>(nl2) * 8;
-        ANNB_CUDA_CHECK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        probe_kernel<<<static_cast<uint32_t>(nq), 256, smem, s>>>(pp);
-        ANNB_CUDA_CHECK(cudaGetLastError());
-        ix->stat_launches++;
-        if (pitch == ix->nlist) break;
-        // rare: a query needed more than nprobe + 64 cells to reach k vectors -> redo with the full pitch
-        uint32_t h_flag[6];
-        ANNB_CUDA_CHECK(cudaMemcpyAsync(h_flag, ix->s_flags.p, sizeof(h_flag), cudaMemcpyDeviceToHost, s));
-        ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
-        if (!h_flag[0]) break;
-        pitch = ix->nlist;
+    ANNB_TRY(ix->s_probes.ensure(nq * static_cast<uint64_t>(pitch) * 4));
+    ProbeParams pp{};
+    fill_probe_params(ix, pp, nq, np, kk, pitch);
+    pp.cdist = ix->s_cdist.as<float>(); pp.nlist_pow2 = nl2;
+    const size_t smem = static_cast<size_t>(nl2) * 8;
+    ANNB_CUDA_CHECK(cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    probe_kernel<<<static_cast<uint32_t>(nq), 256, smem, s>>>(pp);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    ix->stat_launches++;
+    cs->stage = pitch == ix->nlist ? 0 : 1; cs->pitch = pitch; ix->stat_coarse_path = 0;
+    return ANNB_OK;
+}
+
+static int ivf_enqueue(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint32_t k, uint32_t nprobe, const uint64_t* row_map,
+                       uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s, CoreState* cs, int stage_start = 3, bool force_simt = false,
+                       const uint32_t* preset_probes = nullptr, const uint32_t* preset_nprobes = nullptr, uint32_t preset_pitch = 0,
+                       const RouteOut* route_out = nullptr) {
+    // preset_*: probe lists already computed for these queries (the exact fallback of the tensor path re-uses the
+    // parent call's ranking instead of ranking the centroids again; sharded searches route a slice of the batch per rank).
+    // route_out: stop after the routing stage and export the probe lists.
+    const uint32_t kk = static_cast<uint32_t>(std::min<uint64_t>(k, ix->n_total));
+    if (kk == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "k must be >= 1");
+    if (kk > 1024) return fail(ANNB_ERR_UNSUPPORTED, "k > 1024 is not supported");
+    // nprobe default and clamp: src/cpu/ivf.rs:345-347
+    uint32_t np = nprobe ? nprobe : std::max<uint32_t>(1, static_cast<uint32_t>(std::sqrt(static_cast<double>(ix->nlist))));
+    np = std::min(np, ix->nlist);
+    if (static_cast<size_t>(next_pow2(ix->nlist)) * 8 > 200 * 1024) return fail(ANNB_ERR_UNSUPPORTED, "nlist > 16384 is not supported yet");
+
+    uint32_t pitch = preset_pitch;
+    if (!preset_probes) {
+        ANNB_TRY(ivf_route(ix, pq, nq, np, kk, stage_start, force_simt, cs, s));
+        pitch = cs->pitch;
     }
     const uint32_t* d_probes = preset_probes ? preset_probes : ix->s_probes.as<uint32_t>();
     const uint32_t* d_nprobes = preset_probes ? preset_nprobes : ix->s_nprobes.as<uint32_t>();
     if (route_out != nullptr) {
-        ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 4, s));
+        // the export shares the overflow flag with the ranking: a probe set that does not fit the caller's pitch can only be
+        // reported, a ranking that ran out of prefix is repeated from the next stage (see ivf_finish_route)
         export_probes_kernel<<<grid_for(nq * route_out->pitch, 256, 1u << 30), 256, 0, s>>>(d_probes, pitch, d_nprobes, nq, route_out->probes, route_out->pitch,
-                                                                                      route_out->n_probes, ix->s_flags.as<uint32_t>());
+                                                                                      route_out->n_probes, ix->s_flags.as<uint32_t>() + 1);
         ANNB_CUDA_CHECK(cudaGetLastError());
         ix->stat_launches++;
-        uint32_t over = 0;
-        ANNB_CUDA_CHECK(cudaMemcpyAsync(&over, ix->s_flags.p, 4, cudaMemcpyDeviceToHost, s));
-        ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
-        if (over) return fail(ANNB_ERR_UNSUPPORTED, "a query needs more probed lists than the caller's probe pitch");
         return ANNB_OK;
     }
-    // 3. list scan.  A batch that probes every list many times goes list-major (one staged list tile serves up to 32
-    //    queries); small batches keep the query-major streaming kernel (one warp per query part).
+    // list scan.  A batch that probes every list many times goes list-major (one staged list tile serves many queries);
+    // small batches keep the query-major streaming kernel (one warp per query part).
     const uint64_t n_local_lists = std::max<uint32_t>(1, ix->list_end - ix->list_begin);
     // the merge kernels sort all per-(query, rank) lists of a query in shared memory: very wide probe sets go query-major
     // (both kernels sort a power-of-two padded array, so the guard is on the padded size)
@@ -509,40 +536,9 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         ANNB_CUDA_CHECK(cudaGetLastError());
         ix->stat_launches += 3;
         if (use_tc) {
-            ANNB_TRY(tc_ivf_scan(ix, pq.scan, pq.scan_bytes, nq, kk, k, pitch, pp.pair_off, pp.task_off, pp.pairs, pp.task_counter, max_tasks_tc,
-                                 d_nprobes, row_map, d_ids, d_dist, d_cnt, s, pp.tasks));
-            uint32_t n_unc = 0;
-            ANNB_TRY(read_uncertified(ix, &n_unc, s));
-            if (n_unc == 0 || row_map != nullptr) return ANNB_OK;
-            // exact fallback: the uncertified queries go through the CUDA-core pipeline again
-            ANNB_TRY(read_ivf_stats(ix, s));          // keep the whole batch's probe statistics
-            ix->skip_next_ivf_stats = true;
-            const uint32_t* list = ix->s_uncert.as<uint32_t>() + 1;
-            PreparedQueries sub = pq;
-            ANNB_TRY(ix->s_fbq.ensure(static_cast<uint64_t>(n_unc) * pq.scan_bytes));
-            gather_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * (pq.scan_bytes >> 4), 256), 256, 0, s>>>(pq.scan, pq.scan_bytes, list, n_unc, ix->s_fbq.as<uint8_t>());
-            sub.scan = ix->s_fbq.as<uint8_t>();
-            // their probe lists are re-used: [n_unc][pitch] cell ids followed by [n_unc] probe counts
-            ANNB_TRY(ix->s_fbr.ensure(static_cast<uint64_t>(n_unc) * (pitch + 1) * 4));
-            uint32_t* fb_probes = ix->s_fbr.as<uint32_t>();
-            uint32_t* fb_nprobes = fb_probes + static_cast<uint64_t>(n_unc) * pitch;
-            gather_u32_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * pitch, 256), 256, 0, s>>>(d_probes, pitch, list, n_unc, fb_probes);
-            gather_u32_rows_kernel<<<grid_for(n_unc, 256), 256, 0, s>>>(d_nprobes, 1, list, n_unc, fb_nprobes);
-            ANNB_CUDA_CHECK(cudaGetLastError());
-            sub.route = nullptr;
-            ANNB_TRY(ix->s_fbi.ensure(static_cast<uint64_t>(n_unc) * k * 8));
-            ANNB_TRY(ix->s_fbd.ensure(static_cast<uint64_t>(n_unc) * k * 4));
-            ANNB_TRY(ix->s_fbc.ensure(static_cast<uint64_t>(n_unc) * 4));
-            // the list of uncertified queries lives in s_uncert, which the nested call does not touch (it stays on the CUDA-core path)
-            ANNB_TRY(ivf_core(ix, sub, n_unc, k, nprobe, nullptr, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(), ix->s_fbc.as<uint32_t>(), s, true,
-                              fb_probes, fb_nprobes, pitch));
-            scatter_results_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * k, 256), 256, 0, s>>>(list, n_unc, k, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(),
-                                                                                                 ix->s_fbc.as<uint32_t>(), d_ids, d_dist, d_cnt);
-            ANNB_CUDA_CHECK(cudaGetLastError());
-            ix->stat_launches += 4;
-            ix->stat_fallback_queries += n_unc;
-            ix->stat_last_path = ANNB_PATH_TENSOR;
-            return ANNB_OK;
+            cs->tensor = true;
+            return tc_ivf_scan(ix, pq.scan, pq.scan_bytes, nq, kk, k, pitch, pp.pair_off, pp.task_off, pp.pairs, pp.task_counter, max_tasks_tc,
+                               d_nprobes, row_map, d_ids, d_dist, d_cnt, s, pp.tasks);
         }
         ListScanParams lp{};
         lp.rows = ix->d_rows; lp.row_bytes = ix->row_bytes; lp.row_norms = ix->d_norms; lp.row_norms_i = ix->d_norms_i;
@@ -561,6 +557,7 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         ix->stat_launches++;
         return run_finalize(ix, ix->s_keys.as<uint64_t>(), pitch, kk, k, nq, ix->d_original_ids, 0, row_map, d_ids, d_dist, d_cnt, s, d_nprobes);
     }
+    ix->stat_last_path = ANNB_PATH_SIMT;
     // warps wanted per query so that a small batch still fills the machine (148 SMs x 32 warps)
     const uint64_t want = std::max<uint64_t>(1, std::min<uint64_t>(256, ceil_div<uint64_t>(148ull * 32, std::max<uint64_t>(nq, 1))));
     uint32_t parts = ix->opt_scan_parts > 0 ? static_cast<uint32_t>(ix->opt_scan_parts) : static_cast<uint32_t>(std::min<uint64_t>(want, 32));
@@ -580,27 +577,103 @@ static int ivf_core(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uint
         size_t smem = scan_kernel_smem(ix->row_bytes, pq.scan_bytes, nsort);
         uint32_t grid = static_cast<uint32_t>(ceil_div<uint64_t>(nq * parts * subs, SCAN_WARPS));
         {
-            KernelTimer kt(ix, s, preset_probes == nullptr);   // (the exact fallback of a tensor-path call is not the dominant kernel)
+            KernelTimer kt(ix, s, !force_simt);   // (the exact fallback of a tensor-path call is not the dominant kernel)
             ANNB_TRY(launch_scan(ix->dtype, pq.qt, ix->metric, sp, grid, smem, s));
         }
         ix->stat_launches++;
     }
-    // 4. merge parts, map list-order positions to original ids (src/cpu/ivf.rs:383-389)
+    // merge parts, map list-order positions to original ids (src/cpu/ivf.rs:383-389)
     return run_finalize(ix, ix->s_keys.as<uint64_t>(), parts * subs, kk, k, nq, ix->d_original_ids, 0, row_map, d_ids, d_dist, d_cnt, s);
 }
 
-static int read_ivf_stats(annb_index* ix, cudaStream_t s) {
-    if (ix->skip_next_ivf_stats) { ix->skip_next_ivf_stats = false; return ANNB_OK; }
-    unsigned long long h[4] = {0, 0, 0, 0};
-    ANNB_CUDA_CHECK(cudaMemcpyAsync(h, ix->s_flags.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-    ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
-    ix->stat_scanned += static_cast<int64_t>(h[1]);
-    ix->stat_probed += static_cast<int64_t>(h[2]);
-    ix->stat_scanned_local += static_cast<int64_t>(h[3]);
+// Exact fallback of a tensor-path IVF batch: the uncertified queries go through the CUDA-core pipeline again, re-using
+// their probe lists ([n_unc][pitch] cell ids followed by [n_unc] probe counts).
+static int ivf_fallback(annb_index* ix, const PreparedQueries& pq, uint32_t k, uint32_t nprobe, uint32_t n_unc, const uint32_t* d_probes,
+                        const uint32_t* d_nprobes, uint32_t pitch, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s) {
+    const uint32_t* list = ix->s_uncert.as<uint32_t>() + 1;
+    PreparedQueries sub = pq;
+    ANNB_TRY(ix->s_fbq.ensure(static_cast<uint64_t>(n_unc) * pq.scan_bytes));
+    gather_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * (pq.scan_bytes >> 4), 256), 256, 0, s>>>(pq.scan, pq.scan_bytes, list, n_unc, ix->s_fbq.as<uint8_t>());
+    sub.scan = ix->s_fbq.as<uint8_t>();
+    ANNB_TRY(ix->s_fbr.ensure(static_cast<uint64_t>(n_unc) * (pitch + 1) * 4));
+    uint32_t* fb_probes = ix->s_fbr.as<uint32_t>();
+    uint32_t* fb_nprobes = fb_probes + static_cast<uint64_t>(n_unc) * pitch;
+    gather_u32_rows_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * pitch, 256), 256, 0, s>>>(d_probes, pitch, list, n_unc, fb_probes);
+    gather_u32_rows_kernel<<<grid_for(n_unc, 256), 256, 0, s>>>(d_nprobes, 1, list, n_unc, fb_nprobes);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    sub.route = nullptr;
+    ANNB_TRY(ix->s_fbi.ensure(static_cast<uint64_t>(n_unc) * k * 8));
+    ANNB_TRY(ix->s_fbd.ensure(static_cast<uint64_t>(n_unc) * k * 4));
+    ANNB_TRY(ix->s_fbc.ensure(static_cast<uint64_t>(n_unc) * 4));
+    // the list of uncertified queries lives in s_uncert, which the nested call does not touch (it stays on the CUDA-core path)
+    CoreState nested;
+    ANNB_TRY(ivf_enqueue(ix, sub, n_unc, k, nprobe, nullptr, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(), ix->s_fbc.as<uint32_t>(), s, &nested, 0, true,
+                         fb_probes, fb_nprobes, pitch));
+    scatter_results_kernel<<<grid_for(static_cast<uint64_t>(n_unc) * k, 256), 256, 0, s>>>(list, n_unc, k, ix->s_fbi.as<uint64_t>(), ix->s_fbd.as<float>(),
+                                                                                         ix->s_fbc.as<uint32_t>(), d_ids, d_dist, d_cnt);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    ix->stat_launches += 4;
+    ix->stat_fallback_queries += n_unc;
+    ix->stat_last_path = ANNB_PATH_TENSOR;
     return ANNB_OK;
 }
 
 constexpr uint64_t QUERY_BATCH = 16384;
+
+// One batch, from prepared queries to final results in the device buffers d_*: enqueue, read the status words back once
+// (together with whatever `copy_out` enqueues -- the host entry points copy the results in the same synchronisation), and
+// only if they say so repeat the ranking from the next stage / recompute the uncertified queries and copy again.
+// preset_*: probe lists supplied by the caller (sharded search after a probe exchange).
+template <typename CopyOut>
+static int run_batch(annb_index* ix, bool ivf, const PreparedQueries& pq, uint64_t nb, uint32_t k, uint32_t nprobe, uint64_t* d_ids, float* d_dist,
+                     uint32_t* d_cnt, cudaStream_t s, bool may_sync, CopyOut copy_out, const uint32_t* preset_probes = nullptr,
+                     const uint32_t* preset_nprobes = nullptr, uint32_t preset_pitch = 0) {
+    int stage = 3;
+    for (;;) {
+        CoreState cs;
+        if (ivf) ANNB_TRY(ivf_enqueue(ix, pq, nb, k, nprobe, nullptr, d_ids, d_dist, d_cnt, s, &cs, stage, false, preset_probes, preset_nprobes, preset_pitch));
+        else ANNB_TRY(flat_enqueue(ix, pq, nb, k, d_ids, d_dist, d_cnt, s, &cs));
+        ANNB_TRY(copy_out());
+        if (!may_sync || !wants_status(ix, cs)) {
+            if (may_sync) ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+            return ANNB_OK;
+        }
+        ANNB_TRY(enqueue_status_read(ix, cs, s));
+        ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+        const HostStatus h = *reinterpret_cast<const HostStatus*>(ix->h_status);
+        if (cs.routed && h.overflow && cs.stage > 0) { stage = cs.stage - 1; continue; }   // rare: some probe set outgrew the ranked / certified prefix
+        if (cs.routed) {
+            ix->stat_scanned += static_cast<int64_t>(h.scanned);
+            ix->stat_probed += static_cast<int64_t>(h.probed);
+            ix->stat_scanned_local += static_cast<int64_t>(h.local);
+        }
+        const uint32_t n_unc = (cs.tensor && ix->opt_cert_fallback && ix->opt_cert_eps != 0.f) ? h.n_unc : 0u;
+        ix->stat_uncertified = cs.tensor ? static_cast<int64_t>(h.n_unc) : 0;
+        if (n_unc == 0) return ANNB_OK;
+        if (ivf) ANNB_TRY(ivf_fallback(ix, pq, k, nprobe, n_unc, preset_probes ? preset_probes : ix->s_probes.as<uint32_t>(),
+                                       preset_probes ? preset_nprobes : ix->s_nprobes.as<uint32_t>(), preset_probes ? preset_pitch : cs.pitch, d_ids, d_dist, d_cnt, s));
+        else ANNB_TRY(flat_fallback(ix, pq, k, n_unc, d_ids, d_dist, d_cnt, s));
+        ANNB_TRY(copy_out());
+        ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+        return ANNB_OK;
+    }
+}
+
+// Routing only (sharded searches): probe lists of one batch exported at the caller's pitch; repeats from the next ranking
+// stage when the optimistic one ran out of (certified) prefix.
+static int route_batch(annb_index* ix, const PreparedQueries& pq, uint64_t nb, uint32_t k, uint32_t nprobe, const RouteOut& ro, cudaStream_t s) {
+    for (int stage = 3;;) {
+        CoreState cs;
+        ANNB_TRY(ivf_enqueue(ix, pq, nb, k, nprobe, nullptr, nullptr, nullptr, nullptr, s, &cs, stage, false, nullptr, nullptr, 0, &ro));
+        if (ix->opt_async_dev) return ANNB_OK;
+        ANNB_TRY(enqueue_status_read(ix, cs, s));
+        ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+        const HostStatus h = *reinterpret_cast<const HostStatus*>(ix->h_status);
+        if (h.overflow && cs.stage > 0) { stage = cs.stage - 1; continue; }
+        if (h.export_overflow) return fail(ANNB_ERR_UNSUPPORTED, "a query needs more probed lists than the caller's probe pitch");
+        return ANNB_OK;
+    }
+}
 
 // Host-buffer driver shared by the four host entry points.
 //   mode 0: external queries (host or device f32 [nq][dim]);  mode 1: self queries [pos_begin, pos_begin + nq)
@@ -613,6 +686,7 @@ static int search_host(annb_index* ix, bool ivf, int mode, const float* queries,
     ANNB_DEVICE(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
     cudaStream_t s = ix->stream;
+    ANNB_TRY(order_after_previous(ix, s));
     ix->stat_scanned = 0;
     ix->stat_probed = 0;
     ix->stat_scanned_local = 0;
@@ -629,45 +703,48 @@ static int search_host(annb_index* ix, bool ivf, int mode, const float* queries,
         ANNB_TRY(ix->s_ids.ensure(nb * k * 8ull));
         ANNB_TRY(ix->s_dist.ensure(nb * k * 4ull));
         ANNB_TRY(ix->s_cnt.ensure(nb * 4ull));
-        if (ivf) {
-            ANNB_TRY(ivf_core(ix, pq, nb, k, nprobe, nullptr, ix->s_ids.as<uint64_t>(), ix->s_dist.as<float>(), ix->s_cnt.as<uint32_t>(), s));
-        } else {
-            ANNB_TRY(flat_core(ix, pq, nb, k, ix->s_ids.as<uint64_t>(), ix->s_dist.as<float>(), ix->s_cnt.as<uint32_t>(), s));
-        }
         if (ivf && mode == 1 && scatter) {
             // generate_knn: row of internal position p belongs to original id original_ids[p] (ivf.rs:476-486)
             std::vector<uint64_t> oid(nb);
             std::vector<uint64_t> ids(nb * k);
             std::vector<float> dist(out_dist ? nb * k : 0);
             std::vector<uint32_t> cnt(out_counts ? nb : 0);
-            ANNB_CUDA_CHECK(cudaMemcpyAsync(oid.data(), ix->d_original_ids + pos_begin + b0, nb * 8, cudaMemcpyDeviceToHost, s));
-            ANNB_CUDA_CHECK(cudaMemcpyAsync(ids.data(), ix->s_ids.p, nb * k * 8ull, cudaMemcpyDeviceToHost, s));
-            if (out_dist) ANNB_CUDA_CHECK(cudaMemcpyAsync(dist.data(), ix->s_dist.p, nb * k * 4ull, cudaMemcpyDeviceToHost, s));
-            if (out_counts) ANNB_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), ix->s_cnt.p, nb * 4ull, cudaMemcpyDeviceToHost, s));
-            ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+            auto copy_out = [&]() -> int {
+                ANNB_CUDA_CHECK(cudaMemcpyAsync(oid.data(), ix->d_original_ids + pos_begin + b0, nb * 8, cudaMemcpyDeviceToHost, s));
+                ANNB_CUDA_CHECK(cudaMemcpyAsync(ids.data(), ix->s_ids.p, nb * k * 8ull, cudaMemcpyDeviceToHost, s));
+                if (out_dist) ANNB_CUDA_CHECK(cudaMemcpyAsync(dist.data(), ix->s_dist.p, nb * k * 4ull, cudaMemcpyDeviceToHost, s));
+                if (out_counts) ANNB_CUDA_CHECK(cudaMemcpyAsync(cnt.data(), ix->s_cnt.p, nb * 4ull, cudaMemcpyDeviceToHost, s));
+                return ANNB_OK;
+            };
+            ANNB_TRY(run_batch(ix, ivf, pq, nb, k, nprobe, ix->s_ids.as<uint64_t>(), ix->s_dist.as<float>(), ix->s_cnt.as<uint32_t>(), s, true, copy_out));
             for (uint64_t i = 0; i < nb; i++) {
                 std::memcpy(out_ids + oid[i] * k, ids.data() + i * k, k * 8ull);
                 if (out_dist) std::memcpy(out_dist + oid[i] * k, dist.data() + i * k, k * 4ull);
                 if (out_counts) out_counts[oid[i]] = cnt[i];
             }
         } else {
-            ANNB_CUDA_CHECK(cudaMemcpyAsync(out_ids + b0 * k, ix->s_ids.p, nb * k * 8ull, cudaMemcpyDefault, s));
-            if (out_dist) ANNB_CUDA_CHECK(cudaMemcpyAsync(out_dist + b0 * k, ix->s_dist.p, nb * k * 4ull, cudaMemcpyDefault, s));
-            if (out_counts) ANNB_CUDA_CHECK(cudaMemcpyAsync(out_counts + b0, ix->s_cnt.p, nb * 4ull, cudaMemcpyDefault, s));
-            ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+            auto copy_out = [&]() -> int {
+                ANNB_CUDA_CHECK(cudaMemcpyAsync(out_ids + b0 * k, ix->s_ids.p, nb * k * 8ull, cudaMemcpyDefault, s));
+                if (out_dist) ANNB_CUDA_CHECK(cudaMemcpyAsync(out_dist + b0 * k, ix->s_dist.p, nb * k * 4ull, cudaMemcpyDefault, s));
+                if (out_counts) ANNB_CUDA_CHECK(cudaMemcpyAsync(out_counts + b0, ix->s_cnt.p, nb * 4ull, cudaMemcpyDefault, s));
+                return ANNB_OK;
+            };
+            ANNB_TRY(run_batch(ix, ivf, pq, nb, k, nprobe, ix->s_ids.as<uint64_t>(), ix->s_dist.as<float>(), ix->s_cnt.as<uint32_t>(), s, true, copy_out));
         }
-        if (ivf) ANNB_TRY(read_ivf_stats(ix, s));
     }
-    return ANNB_OK;
+    return mark_call_done(ix, s);
 }
 
 static int common_create(annb_index* ix, int device) {
     ix->device = device;
     ANNB_CUDA_CHECK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    ANNB_CUDA_CHECK(cudaMallocHost(&ix->h_status, 64));
     return ANNB_OK;
 }
 
 }  // namespace annb
+
+#include "multi.cuh"
 
 using namespace annb;
 
@@ -704,6 +781,11 @@ int annb_parse_metric(const char* str) {
 
 void annb_destroy(annb_index* ix) {
     if (!ix) return;
+    if (ix->multi) {   // front of a multi-device index: the shards own everything
+        multi_destroy(ix->multi);
+        delete ix;
+        return;
+    }
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(ix->device);
@@ -718,6 +800,8 @@ void annb_destroy(annb_index* ix) {
                       &ix->s_ids, &ix->s_dist, &ix->s_cnt, &ix->s_tmp, &ix->s_pairs, &ix->s_uncert, &ix->s_fbq, &ix->s_fbr, &ix->s_fbi, &ix->s_fbd, &ix->s_fbc})
         b->release();
     if (ix->stream) cudaStreamDestroy(ix->stream);
+    if (ix->last_event) cudaEventDestroy(ix->last_event);
+    if (ix->h_status) cudaFreeHost(ix->h_status);
     (void)cudaGetLastError();
     if (prev >= 0) cudaSetDevice(prev);
     delete ix;
@@ -918,6 +1002,7 @@ int annb_flat_search(const annb_index* index, const float* queries, uint64_t nq,
                      uint64_t* out_ids, float* out_dist, uint32_t* out_counts) {
     if (index && dim != index->dim)
         return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(index->dim));
+    if (index && index->multi) return multi_search(const_cast<annb_index*>(index), false, 0, queries, 0, nq, k, 0, out_ids, out_dist, out_counts);
     return search_host(const_cast<annb_index*>(index), false, 0, queries, 0, nq, k, 0, 0, out_ids, out_dist, out_counts);
 }
 
@@ -925,6 +1010,7 @@ int annb_flat_search_self(const annb_index* index, uint64_t row_begin, uint64_t 
                           uint64_t* out_ids, float* out_dist, uint32_t* out_counts) {
     if (!index) return fail(ANNB_ERR_INVALID_ARGUMENT, "null index");
     if (row_begin > row_end || row_end > index->n) return fail(ANNB_ERR_INVALID_ARGUMENT, "row range outside the index");
+    if (index->multi) return multi_search(const_cast<annb_index*>(index), false, 1, nullptr, row_begin, row_end - row_begin, k, 0, out_ids, out_dist, out_counts);
     return search_host(const_cast<annb_index*>(index), false, 1, nullptr, row_begin, row_end - row_begin, k, 0, 0, out_ids, out_dist, out_counts);
 }
 
@@ -934,17 +1020,23 @@ int annb_flat_search_dev(const annb_index* index, const float* d_queries, uint64
     if (!ix || ix->is_ivf) return fail(ANNB_ERR_INVALID_ARGUMENT, "not a flat index");
     if (dim != ix->dim) return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(ix->dim));
     if (!d_queries || !d_out_ids || k == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / k == 0");
+    if (ix->multi) {   // buffers live on the first device; the call is synchronous (the shards run on their own streams)
+        ANNB_DEVICE(ix->device);
+        ANNB_CUDA_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+        return multi_search(ix, false, 0, d_queries, 0, nq, k, 0, d_out_ids, d_out_dist, d_out_counts);
+    }
     ANNB_DEVICE(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ANNB_TRY(order_after_previous(ix, s));
     for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
         const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
         PreparedQueries pq;
         ANNB_TRY(prepare_external(ix, d_queries + b0 * dim, nb, &pq, s));
-        ANNB_TRY(flat_core(ix, pq, nb, k, d_out_ids + b0 * k, d_out_dist ? d_out_dist + b0 * k : nullptr,
-                           d_out_counts ? d_out_counts + b0 : nullptr, s));
+        ANNB_TRY(run_batch(ix, false, pq, nb, k, 0, d_out_ids + b0 * k, d_out_dist ? d_out_dist + b0 * k : nullptr,
+                           d_out_counts ? d_out_counts + b0 : nullptr, s, ix->opt_async_dev == 0, []() -> int { return ANNB_OK; }));
     }
-    return ANNB_OK;
+    return mark_call_done(ix, s);
 }
 
 // out[list[i]] = src[i]
@@ -1195,13 +1287,14 @@ int annb_ivf_search(const annb_index* index, const float* queries, uint64_t nq, 
                     uint32_t nprobe, uint64_t* out_ids, float* out_dist, uint32_t* out_counts) {
     if (index && dim != index->dim)
         return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(index->dim));
+    if (index && index->multi) return multi_search(const_cast<annb_index*>(index), true, 0, queries, 0, nq, k, nprobe, out_ids, out_dist, out_counts);
     return search_host(const_cast<annb_index*>(index), true, 0, queries, 0, nq, k, nprobe, 0, out_ids, out_dist, out_counts);
 }
 
 int annb_ivf_search_self(const annb_index* index, uint64_t pos_begin, uint64_t pos_end, uint32_t k, uint32_t nprobe,
                          int scatter_to_original, uint64_t* out_ids, float* out_dist, uint32_t* out_counts) {
     if (!index) return fail(ANNB_ERR_INVALID_ARGUMENT, "null index");
-    if (index->list_begin != 0 || index->list_end != index->nlist) return fail(ANNB_ERR_UNSUPPORTED, "self search needs an unsharded IVF index");
+    if (index->multi || index->list_begin != 0 || index->list_end != index->nlist) return fail(ANNB_ERR_UNSUPPORTED, "self search needs an unsharded IVF index");
     if (pos_begin > pos_end || pos_end > index->n) return fail(ANNB_ERR_INVALID_ARGUMENT, "position range outside the index");
     return search_host(const_cast<annb_index*>(index), true, 1, nullptr, pos_begin, pos_end - pos_begin, k, nprobe, scatter_to_original,
                        out_ids, out_dist, out_counts);
@@ -1213,9 +1306,15 @@ int annb_ivf_search_dev(const annb_index* index, const float* d_queries, uint64_
     if (!ix || !ix->is_ivf) return fail(ANNB_ERR_INVALID_ARGUMENT, "not an IVF index");
     if (dim != ix->dim) return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(ix->dim));
     if (!d_queries || !d_out_ids || k == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / k == 0");
+    if (ix->multi) {
+        ANNB_DEVICE(ix->device);
+        ANNB_CUDA_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+        return multi_search(ix, true, 0, d_queries, 0, nq, k, nprobe, d_out_ids, d_out_dist, d_out_counts);
+    }
     ANNB_DEVICE(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ANNB_TRY(order_after_previous(ix, s));
     ix->stat_scanned = 0;
     ix->stat_probed = 0;
     ix->stat_scanned_local = 0;
@@ -1223,51 +1322,52 @@ int annb_ivf_search_dev(const annb_index* index, const float* d_queries, uint64_
         const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
         PreparedQueries pq;
         ANNB_TRY(prepare_external(ix, d_queries + b0 * dim, nb, &pq, s));
-        ANNB_TRY(ivf_core(ix, pq, nb, k, nprobe, nullptr, d_out_ids + b0 * k, d_out_dist ? d_out_dist + b0 * k : nullptr,
-                          d_out_counts ? d_out_counts + b0 : nullptr, s));
+        ANNB_TRY(run_batch(ix, true, pq, nb, k, nprobe, d_out_ids + b0 * k, d_out_dist ? d_out_dist + b0 * k : nullptr,
+                           d_out_counts ? d_out_counts + b0 : nullptr, s, ix->opt_async_dev == 0, []() -> int { return ANNB_OK; }));
     }
-    return ANNB_OK;
+    return mark_call_done(ix, s);
 }
 
 int annb_ivf_route_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,
                        uint32_t* d_probes, uint32_t* d_n_probes, uint32_t probe_pitch, void* stream) {
     annb_index* ix = const_cast<annb_index*>(index);
-    if (!ix || !ix->is_ivf) return fail(ANNB_ERR_INVALID_ARGUMENT, "not an IVF index");
+    if (!ix || !ix->is_ivf || ix->multi) return fail(ANNB_ERR_INVALID_ARGUMENT, "not a (single-device) IVF index");
     if (dim != ix->dim) return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(ix->dim));
     if (!d_queries || !d_probes || !d_n_probes || k == 0 || probe_pitch == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / k == 0 / zero pitch");
     ANNB_DEVICE(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ANNB_TRY(order_after_previous(ix, s));
     for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
         const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
         PreparedQueries pq;
         ANNB_TRY(prepare_external(ix, d_queries + b0 * dim, nb, &pq, s));
         RouteOut ro{d_probes + b0 * probe_pitch, d_n_probes + b0, probe_pitch};
-        ANNB_TRY(ivf_core(ix, pq, nb, k, nprobe, nullptr, nullptr, nullptr, nullptr, s, false, nullptr, nullptr, 0, &ro));
+        ANNB_TRY(route_batch(ix, pq, nb, k, nprobe, ro, s));
     }
-    return ANNB_OK;
+    return mark_call_done(ix, s);
 }
 
 int annb_ivf_search_probes_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,
                                const uint32_t* d_probes, const uint32_t* d_n_probes, uint32_t probe_pitch, uint64_t* d_out_ids, float* d_out_dist,
                                uint32_t* d_out_counts, void* stream) {
     annb_index* ix = const_cast<annb_index*>(index);
-    if (!ix || !ix->is_ivf) return fail(ANNB_ERR_INVALID_ARGUMENT, "not an IVF index");
+    if (!ix || !ix->is_ivf || ix->multi) return fail(ANNB_ERR_INVALID_ARGUMENT, "not a (single-device) IVF index");
     if (dim != ix->dim) return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(ix->dim));
     if (!d_queries || !d_probes || !d_n_probes || !d_out_ids || k == 0 || probe_pitch == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / k == 0 / zero pitch");
     ANNB_DEVICE(ix->device);
     std::lock_guard<std::mutex> lock(ix->mu);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ANNB_TRY(order_after_previous(ix, s));
     for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
         const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
         PreparedQueries pq;
         ANNB_TRY(prepare_external(ix, d_queries + b0 * dim, nb, &pq, s));
-        ix->skip_next_ivf_stats = true;   // no routing ran in this call
-        ANNB_TRY(ivf_core(ix, pq, nb, k, nprobe, nullptr, d_out_ids + b0 * k, d_out_dist ? d_out_dist + b0 * k : nullptr,
-                          d_out_counts ? d_out_counts + b0 : nullptr, s, false, d_probes + b0 * probe_pitch, d_n_probes + b0, probe_pitch));
+        ANNB_TRY(run_batch(ix, true, pq, nb, k, nprobe, d_out_ids + b0 * k, d_out_dist ? d_out_dist + b0 * k : nullptr,
+                           d_out_counts ? d_out_counts + b0 : nullptr, s, ix->opt_async_dev == 0, []() -> int { return ANNB_OK; },
+                           d_probes + b0 * probe_pitch, d_n_probes + b0, probe_pitch));
     }
-    ix->skip_next_ivf_stats = false;
-    return ANNB_OK;
+    return mark_call_done(ix, s);
 }
 
 int annb_merge_topk_dev(const uint64_t* d_part_ids, const float* d_part_dist, uint32_t parts, uint64_t nq, uint32_t k,
@@ -1286,6 +1386,40 @@ int annb_merge_topk_dev(const uint64_t* d_part_ids, const float* d_part_dist, ui
     return ANNB_OK;
 }
 
+int annb_merge_shards_dev(const void* d_parts, uint64_t part_stride_bytes, uint64_t dist_offset_bytes, uint32_t parts, uint64_t nq, uint32_t k,
+                          uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, void* stream) {
+    if (!d_parts || !d_out_ids || parts == 0 || k == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / empty shape");
+    if ((part_stride_bytes & 7) || (dist_offset_bytes & 3)) return fail(ANNB_ERR_INVALID_ARGUMENT, "misaligned shard layout");
+    if (nq == 0) return ANNB_OK;
+    MergeShardsParams m{};
+    m.base = static_cast<const uint8_t*>(d_parts); m.part_stride = part_stride_bytes; m.dist_offset = dist_offset_bytes;
+    m.parts = parts; m.k = k; m.nq = nq; m.out_ids = d_out_ids; m.out_dist = d_out_dist; m.out_counts = d_out_counts;
+    merge_shards_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 4)), 128, 0, static_cast<cudaStream_t>(stream)>>>(m);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    return ANNB_OK;
+}
+
+int annb_flat_create_multi(annb_index** out, const float* data, uint64_t n, uint32_t dim, int dtype, int metric, const int* devices, int n_devices) {
+    if (metric == ANNB_MANHATTAN) return fail(ANNB_ERR_DISTANCE_NOT_SUPPORTED, "Manhattan distance is not supported by the GPU / quantised indices");
+    if (metric != ANNB_L2 && metric != ANNB_COSINE) return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown metric");
+    if (dtype < ANNB_F32 || dtype > ANNB_SQ8) return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown dtype");
+    return multi_flat_create(out, data, n, dim, dtype, metric, devices, n_devices);
+}
+
+int annb_ivf_create_multi(annb_index** out, const void* vectors, const void* norms, const float* centroids, const float* centroid_norms,
+                          const uint64_t* offsets, const uint64_t* original_ids, uint64_t n, uint32_t dim, uint32_t nlist, int dtype, int metric,
+                          const float* sq8_scales, const int* devices, int n_devices) {
+    if (metric == ANNB_MANHATTAN) return fail(ANNB_ERR_DISTANCE_NOT_SUPPORTED, "Manhattan distance is not supported by the IVF indices");
+    if (metric != ANNB_L2 && metric != ANNB_COSINE) return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown metric");
+    return multi_ivf_create(out, vectors, norms, centroids, centroid_norms, offsets, original_ids, n, dim, nlist, dtype, metric, sq8_scales, devices, n_devices);
+}
+
+int annb_index_shard_count(const annb_index* ix, uint32_t* out) {
+    if (!ix || !out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
+    *out = ix->multi ? static_cast<uint32_t>(ix->multi->shards.size()) : 1u;
+    return ANNB_OK;
+}
+
 int annb_index_get_info(const annb_index* ix, annb_index_info* out) {
     if (!ix || !out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
     out->n = ix->n; out->n_total = ix->n_total; out->dim = ix->dim; out->nlist = ix->nlist;
@@ -1297,6 +1431,10 @@ int annb_index_get_info(const annb_index* ix, annb_index_info* out) {
 
 int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     if (!ix || !key) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
+    if (ix->multi) {   // options apply to every shard
+        for (annb_index* sh : ix->multi->shards) ANNB_TRY(annb_index_set_option(sh, key, value));
+        return ANNB_OK;
+    }
     std::lock_guard<std::mutex> lock(ix->mu);
     std::string k(key);
     if (k == "path") { if (value < 0 || value > 2) return fail(ANNB_ERR_INVALID_ARGUMENT, "path must be 0..2"); ix->opt_path = static_cast<int>(value); }
@@ -1312,6 +1450,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "ivf_list_major") ix->opt_ivf_list_major = static_cast<int>(value);
     else if (k == "ivf_fast_probe") ix->opt_ivf_fast_probe = static_cast<int>(value);
     else if (k == "ivf_tc_coarse") ix->opt_ivf_tc_coarse = static_cast<int>(value);
+    else if (k == "async_dev") ix->opt_async_dev = static_cast<int>(value);
     else if (k == "time_kernels") { ix->opt_time_kernels = static_cast<int>(value); ix->timed_ms_total = 0.0; ix->timed_launches = 0; }
     else return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown option " + k);
     return ANNB_OK;
@@ -1326,6 +1465,21 @@ int annb_debug_fetch_tile(annb_index* ix, float* host_out) {
     return rc;
 }
 
+int annb_debug_fetch_uncertified(annb_index* ix, uint32_t* host_out, uint32_t capacity, uint32_t* out_count) {
+    if (!ix || !out_count || (!host_out && capacity)) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
+    if (ix->multi) return fail(ANNB_ERR_UNSUPPORTED, "per-shard diagnostic");
+    *out_count = 0;
+    if (!ix->s_uncert.p) return ANNB_OK;
+    DeviceGuard g(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    uint32_t c = 0;
+    ANNB_CUDA_CHECK(cudaMemcpy(&c, ix->s_uncert.p, 4, cudaMemcpyDeviceToHost));
+    *out_count = c;
+    const uint32_t m = std::min(c, capacity);
+    if (m) ANNB_CUDA_CHECK(cudaMemcpy(host_out, ix->s_uncert.as<uint32_t>() + 1, m * 4ull, cudaMemcpyDeviceToHost));
+    return ANNB_OK;
+}
+
 int annb_debug_fetch_cycles(annb_index* ix, uint64_t* host_out8) {
     if (!ix || !host_out8) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
     DeviceGuard g(ix->device);
@@ -1337,6 +1491,18 @@ int annb_debug_fetch_cycles(annb_index* ix, uint64_t* host_out8) {
 
 int annb_index_get_stat(const annb_index* ix, const char* key, int64_t* out) {
     if (!ix || !key || !out) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument");
+    if (ix->multi) {   // counters add up over the shards; path-like values are the first shard's
+        const std::string kk(key);
+        const bool sum = kk != "last_path" && kk != "coarse_path";
+        int64_t acc = 0;
+        for (size_t i = 0; i < ix->multi->shards.size(); i++) {
+            int64_t v = 0;
+            ANNB_TRY(annb_index_get_stat(ix->multi->shards[i], key, &v));
+            if (sum) acc += v; else if (i == 0) acc = v;
+        }
+        *out = acc;
+        return ANNB_OK;
+    }
     std::string k(key);
     if (k == "kernel_launches") *out = ix->stat_launches;
     else if (k == "scanned_vectors") *out = ix->stat_scanned;
@@ -1345,6 +1511,7 @@ int annb_index_get_stat(const annb_index* ix, const char* key, int64_t* out) {
     else if (k == "last_path") *out = ix->stat_last_path;
     else if (k == "coarse_path") *out = ix->stat_coarse_path;
     else if (k == "fallback_queries") *out = ix->stat_fallback_queries;
+    else if (k == "cert_eps_bits") *out = ix->stat_cert_eps_bits;
     else if (k == "uncertified") {
         // queries of the last tensor-path call whose pre-selection margin could not be certified (see rerank_kernel)
         *out = 0;

@@ -9,6 +9,8 @@
 
 #include "common.cuh"
 
+struct annb_multi;
+
 namespace annb {
 
 // Grow-only device scratch buffer.
@@ -103,7 +105,13 @@ struct annb_index {
     float opt_cert_eps = -1.0f;    // < 0: derived per kernel from its MMA count (tc_cert_eps); >= 0: caller override, 0 = certificate off
     int opt_cert_fallback = 1;     // re-run uncertified queries on the exact CUDA-core path
     mutable int64_t stat_fallback_queries = 0;  // cumulative
-    bool skip_next_ivf_stats = false;
+    mutable int64_t stat_cert_eps_bits = 0;     // f32 bit pattern of the error bound the last tensor-path certificate used
+    void* h_status = nullptr;      // pinned host block the status words of a batch are read back into (api.cu HostStatus)
+    cudaEvent_t last_event = nullptr;   // end of the last call that used the scratch buffers, and the stream it ran on
+    bool last_event_valid = false;
+    cudaStream_t last_stream = nullptr;
+    int opt_async_dev = 0;         // 1: the _dev entry points never synchronise (no certificate fallback, no ranking retry; the caller polls the stats)
+    struct annb_multi* multi = nullptr;   // multi-device handle (multi.cu): this object is only the front of its per-device shards
     annb::DevBuf s_fbq, s_fbr, s_fbi, s_fbd, s_fbc;
     annb::DevBuf s_uncert;         // [1 + nq] uncertified-query counter + list of the last tensor-path call
     annb::TcState* tc = nullptr;

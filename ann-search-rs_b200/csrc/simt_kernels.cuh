@@ -845,4 +845,68 @@ __global__ void __launch_bounds__(128) merge_kernel(MergeParams p) {
     }
 }
 
+// Cross-shard merge of interleaved per-shard results (annb_merge_shards_dev): shard p's [nq][k] ids start at
+// base + p * part_stride, its [nq][k] distances dist_offset bytes further on -- one buffer per shard, so one all-gather
+// (or one peer copy per shard) moves ids and distances together.  Order: (distance, shard, position inside the shard's
+// own list).  Every shard's list is already in the index's own order -- (distance, row) for flat shards, (distance, list
+// position) for IVF shards -- and shards own ascending, disjoint row / list ranges, so with the shards passed in that
+// order this IS the order of the unsharded index (src/utils/heap_structs.rs:12-38, src/cpu/ivf.rs:367-381).
+struct MergeShardsParams {
+    const uint8_t* base;
+    uint64_t part_stride, dist_offset;
+    uint32_t parts, k;
+    uint64_t nq;
+    uint64_t* out_ids;
+    float* out_dist;
+    uint32_t* out_counts;
+};
+
+// One warp per query.  Each per-shard list is ascending, so an entry's final rank is its own slot plus, for every other
+// shard, the number of that shard's entries that precede it (<= for earlier shards, < for later ones): k * parts * parts
+// compares per query, no sort, no shared memory.
+__global__ void __launch_bounds__(128) merge_shards_kernel(MergeShardsParams p) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t q = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= p.nq) return;
+    const uint32_t total = p.parts * p.k;
+    uint32_t valid = 0;
+    for (uint32_t i = lane; i < total; i += 32) {
+        const uint32_t part = i / p.k, j = i - part * p.k;
+        const uint8_t* pb = p.base + static_cast<uint64_t>(part) * p.part_stride;
+        const uint64_t id = reinterpret_cast<const uint64_t*>(pb)[q * p.k + j];
+        if (id == 0xFFFFFFFFFFFFFFFFull) continue;
+        const float d = reinterpret_cast<const float*>(pb + p.dist_offset)[q * p.k + j];
+        const uint32_t od = f32_to_ordered(d);
+        uint32_t rank = j;
+        for (uint32_t o = 0; o < p.parts && rank < p.k; o++) {
+            if (o == part) continue;
+            const uint8_t* ob = p.base + static_cast<uint64_t>(o) * p.part_stride;
+            const uint64_t* oids = reinterpret_cast<const uint64_t*>(ob) + q * p.k;
+            const float* odist = reinterpret_cast<const float*>(ob + p.dist_offset) + q * p.k;
+            // number of entries of shard o that come before (d, part): binary search over its ascending list
+            uint32_t lo = 0, hi = p.k;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const bool before = oids[mid] != 0xFFFFFFFFFFFFFFFFull &&
+                                    (o < part ? f32_to_ordered(odist[mid]) <= od : f32_to_ordered(odist[mid]) < od);
+                if (before) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < p.k) {
+            p.out_ids[q * p.k + rank] = id;
+            if (p.out_dist) p.out_dist[q * p.k + rank] = d;
+            valid++;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) valid += __shfl_xor_sync(0xFFFFFFFFu, valid, off);
+    // fewer than k valid entries in total: pad the tail
+    for (uint32_t j = valid + lane; j < p.k; j += 32) {
+        p.out_ids[q * p.k + j] = 0xFFFFFFFFFFFFFFFFull;
+        if (p.out_dist) p.out_dist[q * p.k + j] = INFINITY;
+    }
+    if (p.out_counts && lane == 0) p.out_counts[q] = valid;
+}
+
 }  // namespace annb

@@ -84,6 +84,10 @@ def lib():
         _lib.annb_ivf_search_self.argtypes = [vp, u64, u64, u32, u32, i32, vp, vp, vp]
         _lib.annb_ivf_search_dev.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, vp, vp]
         _lib.annb_merge_topk_dev.argtypes = [vp, vp, u32, u64, u32, vp, vp, vp, vp]
+        _lib.annb_merge_shards_dev.argtypes = [vp, u64, u64, u32, u64, u32, vp, vp, vp, vp]
+        _lib.annb_flat_create_multi.argtypes = [C.POINTER(vp), vp, u64, u32, i32, i32, vp, i32]
+        _lib.annb_ivf_create_multi.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, vp, vp, i32]
+        _lib.annb_index_shard_count.argtypes = [vp, C.POINTER(u32)]
         _lib.annb_index_get_info.argtypes = [vp, C.POINTER(_Info)]
         _lib.annb_index_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
         _lib.annb_index_get_stat.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int64)]
@@ -171,6 +175,13 @@ class _IndexBase:
     def dim(self) -> int:
         return int(self.info().dim)
 
+    @property
+    def shard_count(self) -> int:
+        """Per-device shards behind the handle (1 unless it was built over a device list)."""
+        c = C.c_uint32(0)
+        _check(lib().annb_index_shard_count(self._h, C.byref(c)))
+        return int(c.value)
+
     def memory_usage_bytes(self) -> Tuple[int, int]:
         """(ram, vram) as IvfIndexGpu::memory_usage_bytes (src/gpu/ivf_gpu.rs:590-604)."""
         i = self.info()
@@ -189,6 +200,19 @@ class _IndexBase:
         _check(lib().annb_debug_fetch_tile(self._h, _ptr(out)))
         return out
 
+    def uncertified_queries(self) -> np.ndarray:
+        """Batch-relative numbers of the queries of the last tensor-path batch that failed the coverage certificate."""
+        f = lib().annb_debug_fetch_uncertified
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        cnt = C.c_uint32(0)
+        buf = np.zeros(1 << 16, dtype=np.uint32)
+        _check(f(self._h, _ptr(buf), buf.size, C.byref(cnt)))
+        return buf[:min(int(cnt.value), buf.size)].copy()
+
+    def cert_eps(self) -> float:
+        """Error bound the last tensor-path certificate assumed."""
+        return float(np.array([self.get_stat("cert_eps_bits")], dtype=np.uint32).view(np.float32)[0])
+
     def close(self):
         if self._h is not None:
             lib().annb_destroy(self._h)
@@ -205,9 +229,15 @@ class ExhaustiveIndexB200(_IndexBase):
     """Resident flat index: ExhaustiveIndexGpu (src/gpu/exhaustive_gpu.rs:17-33) and its BF16 / SQ8 twins."""
 
     @classmethod
-    def new(cls, data, metric: int, dtype: int = F32, device: int = 0, id_base: int = 0, sq8_scales=None):
+    def new(cls, data, metric: int, dtype: int = F32, device=0, id_base: int = 0, sq8_scales=None):
+        """`device`: one ordinal, or a list of ordinals -- the rows are then sharded over those GPUs behind one handle
+        (annb_flat_create_multi) and every query method below works unchanged."""
         x = _as_rowmajor_f32(data)
         h = C.c_void_p()
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(d) for d in device])
+            _check(lib().annb_flat_create_multi(C.byref(h), _ptr(x), x.shape[0], x.shape[1], dtype, metric, devs, len(device)))
+            return cls(h)
         sc = None if sq8_scales is None else np.ascontiguousarray(sq8_scales, dtype=np.float32)
         _check(lib().annb_flat_create(C.byref(h), _ptr(x), x.shape[0], x.shape[1], dtype, metric, _ptr(sc), id_base, device))
         return cls(h)
@@ -241,8 +271,9 @@ class IvfIndexB200(_IndexBase):
     @classmethod
     def from_parts(cls, vectors, centroids, offsets, original_ids, dtype: int, metric: int, norms=None,
                    centroid_norms=None, sq8_scales=None, list_begin: int = 0, list_end: Optional[int] = None,
-                   device: int = 0, n_total: Optional[int] = None):
-        """annb_ivf_create: the contents of the reference's IvfIndex struct, already in list order."""
+                   device=0, n_total: Optional[int] = None):
+        """annb_ivf_create: the contents of the reference's IvfIndex struct, already in list order.  `device` may be a
+        list of ordinals: the inverted lists are then sharded over those GPUs behind one handle (annb_ivf_create_multi)."""
         want = {F32: np.float32, BF16: np.uint16, SQ8: np.int8}[dtype]
         v = np.ascontiguousarray(vectors, dtype=want)
         cent = np.ascontiguousarray(centroids, dtype=np.float32)
@@ -257,6 +288,11 @@ class IvfIndexB200(_IndexBase):
         cn = None if centroid_norms is None else np.ascontiguousarray(centroid_norms, dtype=np.float32)
         sc = None if sq8_scales is None else np.ascontiguousarray(sq8_scales, dtype=np.float32)
         h = C.c_void_p()
+        if isinstance(device, (list, tuple)):
+            devs = (C.c_int * len(device))(*[int(d) for d in device])
+            _check(lib().annb_ivf_create_multi(C.byref(h), _ptr(v), _ptr(nr), _ptr(cent), _ptr(cn), _ptr(off), _ptr(oid), n,
+                                               cent.shape[1], nlist, dtype, metric, _ptr(sc), devs, len(device)))
+            return cls(h)
         _check(lib().annb_ivf_create(C.byref(h), _ptr(v), _ptr(nr), _ptr(cent), _ptr(cn), _ptr(off), _ptr(oid), n,
                                      cent.shape[1], nlist, dtype, metric, _ptr(sc), list_begin, list_end, device))
         return cls(h)
@@ -339,8 +375,9 @@ def _finish(res, return_dist):
     return ids, (dist if return_dist else None)
 
 
-def build_exhaustive_index_gpu(mat, dist_metric: str = "euclidean", device: int = 0) -> ExhaustiveIndexB200:
-    """src/lib.rs:2813-2840."""
+def build_exhaustive_index_gpu(mat, dist_metric: str = "euclidean", device=0) -> ExhaustiveIndexB200:
+    """src/lib.rs:2813-2840.  `device` (the reference's R::Device argument): a GPU ordinal, or a list of ordinals to
+    shard the rows over several GPUs of the box."""
     return ExhaustiveIndexB200.new(mat, _metric_or_default(dist_metric), F32, device)
 
 
@@ -463,6 +500,10 @@ def build_ivf_host_parts(mat, centroids, metric: int, dtype: int, train_rows=Non
                 norms=(norms[order] if norms is not None else norms_i), centroid_norms=cnorms, sq8_scales=scales)
 
 
+def _first_device(device) -> int:
+    return int(device[0]) if isinstance(device, (list, tuple)) else int(device)
+
+
 def _build_ivf(mat, nlist, centroids, dist_metric, dtype, seed, device, verbose, kmeans_iters=30) -> IvfIndexB200:
     metric = _metric_or_default(dist_metric)
     if metric == MANHATTAN:
@@ -481,8 +522,8 @@ def _build_ivf(mat, nlist, centroids, dist_metric, dtype, seed, device, verbose,
             xt = normalise_rows(xt)
         if verbose:
             print(f"  Generating IVF index with {nlist} Voronoi cells.")
-        centroids = train_centroids_lloyd(xt, nlist, metric, kmeans_iters, device)
-    parts = build_ivf_host_parts(x, centroids, metric, dtype, train_rows, device)
+        centroids = train_centroids_lloyd(xt, nlist, metric, kmeans_iters, _first_device(device))
+    parts = build_ivf_host_parts(x, centroids, metric, dtype, train_rows, _first_device(device))
     ix = IvfIndexB200.from_parts(device=device, **parts)
     ix.parts = parts
     return ix

@@ -65,39 +65,148 @@ def probe_pitch(nprobe: int) -> int:
     return ((max(1, nprobe) + 32 + 31) // 32) * 32
 
 
-def ivf_search_sharded(index, queries, k: int, nprobe: int, out_ids=None, out_dist=None, group=None, stream=None):
-    """One sharded IVF search step on CUDA tensors (one process per GPU, `index` = this rank's list range):
-      1. every rank ranks the centroids for ITS slice of the query batch (annb_ivf_route_dev),
-      2. the probe lists are all-gathered (4 * nq * pitch bytes),
-      3. every rank scans its own lists for the whole batch (annb_ivf_search_probes_dev),
-      4. the per-shard top-k are all-gathered and merged (annb_merge_topk_dev).
-    Raises AnnSearchError(Unsupported) when a probe set does not fit the pitch.
-    Returns (ids [nq, k] int64, dist [nq, k] float32) on the rank's device."""
+def shard_block_bytes(nq: int, k: int) -> int:
+    """Size of one shard's interleaved result block: [nq * k] int64 ids followed by [nq * k] float32 distances, padded to
+    256 bytes so every rank's slot of the gathered buffer stays aligned."""
+    return ((nq * k * 12 + 255) // 256) * 256
+
+
+def pack_block(ids, dist):
+    """One shard's interleaved result block (uint8 tensor of shard_block_bytes): ids [nq, k] int64, dist [nq, k] float32."""
+    import torch
+    nq, k = ids.shape
+    blk = torch.zeros((shard_block_bytes(nq, k),), dtype=torch.uint8, device=ids.device)
+    blk[:nq * k * 8].view(torch.int64).copy_(ids.contiguous().view(-1))
+    blk[nq * k * 8:nq * k * 12].view(torch.float32).copy_(dist.contiguous().view(-1))
+    return blk
+
+
+def unpack_blocks(gathered, world: int, nq: int, k: int):
+    """[world * block] uint8 -> (ids [world, nq, k] int64, dist [world, nq, k] float32) views-by-copy."""
+    import torch
+    b = shard_block_bytes(nq, k)
+    g = gathered.view(world, b)
+    ids = torch.stack([g[p, :nq * k * 8].view(torch.int64).view(nq, k) for p in range(world)])
+    dist = torch.stack([g[p, nq * k * 8:nq * k * 12].view(torch.float32).view(nq, k) for p in range(world)])
+    return ids, dist
+
+
+def allgather_blocks(block, group=None):
+    """ONE collective for ids and distances: all-gather of the ranks' interleaved blocks (any backend)."""
     import torch
     import torch.distributed as dist_
+    world = dist_.get_world_size(group)
+    out = torch.empty((world * block.numel(),), dtype=torch.uint8, device=block.device)
+    dist_.all_gather_into_tensor(out, block, group=group)
+    return out
 
-    from . import _check, lib
-    world, rank = dist_.get_world_size(group), dist_.get_rank(group)
+
+class ShardedSearch:
+    """One sharded search step per call, one process per GPU.  `index` is this rank's shard -- a row range
+    (flat, built with id_base = first row) or a list range (IVF) -- and ranks hold ascending ranges in rank order.
+
+        flat : search the shard for the whole batch -> ONE all-gather of the interleaved [ids | distances] blocks
+               (12 * nq * k bytes per rank) -> annb_merge_shards_dev.
+        IVF  : every rank ranks the centroids for ITS slice of the batch (annb_ivf_route_dev), ONE all-gather of the
+               slices' [probe lists | probe counts] blocks, every rank scans its own lists for the whole batch
+               (annb_ivf_search_probes_dev), then the same result exchange.
+
+    Everything is enqueued on `stream` (default: torch's current stream), collectives included.  A rank whose library
+    call fails still enters every collective of the step with an error mark in its block; all ranks raise together
+    afterwards instead of leaving the others blocked in NCCL."""
+
+    def __init__(self, index, nq: int, dim: int, k: int, nprobe: int = 0, group=None, device=None):
+        import torch
+        import torch.distributed as dist_
+        self.index, self.nq, self.dim, self.k, self.nprobe, self.group = index, nq, dim, k, nprobe, group
+        self.world, self.rank = dist_.get_world_size(group), dist_.get_rank(group)
+        dev = device or torch.device("cuda", torch.cuda.current_device())
+        self.dev = dev
+        self.block = shard_block_bytes(nq, k)
+        self.mine = torch.empty((self.block,), dtype=torch.uint8, device=dev)
+        self.gathered = torch.empty((self.world * self.block,), dtype=torch.uint8, device=dev)
+        self.ids = self.mine[:nq * k * 8].view(torch.int64).view(nq, k)
+        self.dist = self.mine[nq * k * 8:nq * k * 12].view(torch.float32).view(nq, k)
+        self.out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+        self.out_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        self.is_ivf = bool(index.info().is_ivf)
+        if self.is_ivf:
+            self.pitch = probe_pitch(nprobe or int(max(1, index.info().nlist ** 0.5)))
+            self.per = (nq + self.world - 1) // self.world
+            # one exchange block per rank: [per * pitch] probe cells, [per] probe counts, [1] status word
+            self.route_words = self.per * self.pitch + self.per + 1
+            self.my_route = torch.zeros((self.route_words,), dtype=torch.int32, device=dev)
+            self.all_route = torch.empty((self.world * self.route_words,), dtype=torch.int32, device=dev)
+            self.probes = torch.empty((self.world * self.per, self.pitch), dtype=torch.int32, device=dev)
+            self.nprobes = torch.empty((self.world * self.per,), dtype=torch.int32, device=dev)
+        self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
+
+    def _raise_together(self, err):
+        """All ranks learn whether any of them failed (one tiny all-reduce, only on the error path of the caller)."""
+        import torch
+        import torch.distributed as dist_
+        flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=self.dev)
+        dist_.all_reduce(flag, op=dist_.ReduceOp.MAX, group=self.group)
+        if int(flag.item()):
+            raise err if err is not None else RuntimeError("another rank failed in the sharded search step")
+
+    def __call__(self, queries, stream=None, check: bool = True):
+        """queries: [nq, dim] float32 CUDA tensor (the whole batch, on every rank).  Returns (ids, dist) on the device.
+        `check`: agree on success across ranks before returning (one 4-byte all-reduce)."""
+        import torch
+        import torch.distributed as dist_
+
+        from . import AnnSearchError, lib
+        L = lib()
+        st_obj = stream or torch.cuda.current_stream(self.dev)
+        st = st_obj.cuda_stream
+        nq, dim, k = self.nq, self.dim, self.k
+        err = None
+        with torch.cuda.stream(st_obj):
+            if self.is_ivf:
+                lo, hi = min(nq, self.rank * self.per), min(nq, (self.rank + 1) * self.per)
+                pw = self.per * self.pitch
+                self.my_route[pw + self.per:].zero_()
+                if hi > lo:
+                    rc = L.annb_ivf_route_dev(self.index.handle, queries[lo:hi].data_ptr(), hi - lo, dim, k, self.nprobe, self.my_route.data_ptr(),
+                                              self.my_route[pw:].data_ptr(), self.pitch, st)
+                    if rc != 0:   # e.g. Unsupported: a probe set did not fit the pitch -- mark the block, keep the collectives matched
+                        err = AnnSearchError(rc, L.annb_last_error().decode("utf-8", "replace"))
+                        self.my_route[pw + self.per:].fill_(1)
+                dist_.all_gather_into_tensor(self.all_route, self.my_route, group=self.group)
+                blocks = self.all_route.view(self.world, self.route_words)
+                self.probes.view(self.world, pw).copy_(blocks[:, :pw])
+                self.nprobes.view(self.world, self.per).copy_(blocks[:, pw:pw + self.per])
+                if err is None:
+                    rc = L.annb_ivf_search_probes_dev(self.index.handle, queries.data_ptr(), nq, dim, k, self.nprobe, self.probes.data_ptr(),
+                                                      self.nprobes.data_ptr(), self.pitch, self.ids.data_ptr(), self.dist.data_ptr(), None, st)
+                    if rc != 0:
+                        err = AnnSearchError(rc, L.annb_last_error().decode("utf-8", "replace"))
+            else:
+                rc = L.annb_flat_search_dev(self.index.handle, queries.data_ptr(), nq, dim, k, self.ids.data_ptr(), self.dist.data_ptr(), None, st)
+                if rc != 0:
+                    err = AnnSearchError(rc, L.annb_last_error().decode("utf-8", "replace"))
+            dist_.all_gather_into_tensor(self.gathered, self.mine, group=self.group)
+            if err is None:
+                rc = L.annb_merge_shards_dev(self.gathered.data_ptr(), self.block, nq * k * 8, self.world, nq, k, self.out_ids.data_ptr(),
+                                             self.out_dist.data_ptr(), None, st)
+                if rc != 0:
+                    err = AnnSearchError(rc, L.annb_last_error().decode("utf-8", "replace"))
+            if check or err is not None:
+                self._raise_together(err)
+        return self.out_ids, self.out_dist
+
+
+def ivf_search_sharded(index, queries, k: int, nprobe: int, out_ids=None, out_dist=None, group=None, stream=None):
+    """One sharded IVF search step (convenience wrapper over ShardedSearch; allocates its buffers per call).
+    Returns (ids [nq, k] int64, dist [nq, k] float32) on the rank's device; raises on ALL ranks if any rank failed."""
     nq, dim = queries.shape
-    dev = queries.device
-    st = (stream or torch.cuda.current_stream(dev)).cuda_stream
-    L = lib()
-    pitch = probe_pitch(nprobe)
-    per = (nq + world - 1) // world
-    lo, hi = min(nq, rank * per), min(nq, (rank + 1) * per)
-    ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
-    dst = torch.empty((nq, k), dtype=torch.float32, device=dev)
-    my_probes = torch.full((per, pitch), -1, dtype=torch.int32, device=dev)
-    my_n = torch.zeros((per,), dtype=torch.int32, device=dev)
-    if hi > lo:
-        # ANNB_ERR_UNSUPPORTED here means a probe set did not fit the pitch (tiny lists, huge k): the error is raised on this
-        # rank before any collective of the step, so the job fails loudly instead of hanging; use a larger pitch then
-        _check(L.annb_ivf_route_dev(index.handle, queries[lo:hi].data_ptr(), hi - lo, dim, k, nprobe, my_probes.data_ptr(), my_n.data_ptr(), pitch, st))
-    g_probes = torch.empty((world * per, pitch), dtype=torch.int32, device=dev)
-    g_n = torch.empty((world * per,), dtype=torch.int32, device=dev)
-    dist_.all_gather_into_tensor(g_probes.view(-1), my_probes.view(-1), group=group)
-    dist_.all_gather_into_tensor(g_n, my_n, group=group)
-    _check(L.annb_ivf_search_probes_dev(index.handle, queries.data_ptr(), nq, dim, k, nprobe, g_probes.data_ptr(), g_n.data_ptr(), pitch,
-                                        ids.data_ptr(), dst.data_ptr(), None, st))
-    g_ids, g_dist = allgather_topk(ids, dst, group)
-    return merge_topk_device(g_ids, g_dist, out_ids, out_dist, stream)
+    step = ShardedSearch(index, nq, dim, k, nprobe, group, queries.device)
+    ids, dst = step(queries, stream)
+    if out_ids is not None:
+        out_ids.copy_(ids)
+        ids = out_ids
+    if out_dist is not None:
+        out_dist.copy_(dst)
+        dst = out_dist
+    return ids, dst

@@ -17,8 +17,15 @@
  *     the last failure on the calling thread is available via annb_last_error();
  *   - host-buffer entry points (`annb_*_search`) accept pageable or pinned host
  *     memory, or device memory (resolved through UVA);
- *   - `_dev` entry points take device pointers and a cudaStream_t (as void*)
- *     and are asynchronous with respect to the host;
+ *   - `_dev` entry points take device pointers and a cudaStream_t (as void*): all work is enqueued on that stream and the
+ *     results are complete, in stream order, when the call returns.  The call itself may synchronise the stream once
+ *     per internal batch of 16384 queries: the tensor-core paths are optimistic, and a 40-byte status block (queries that
+ *     failed the coverage certificate, a probe set that outgrew its ranked prefix) is read back to decide whether the
+ *     exact kernels have to run for some queries.  Option "async_dev" = 1 drops that read-back: the call then never
+ *     blocks, nothing is recomputed, and the caller polls get_stat "uncertified" after its own synchronisation;
+ *   - calls on one handle may come from several threads and on different streams: a per-handle mutex orders the host
+ *     side, and a call whose stream differs from the previous call's first waits (on the device) for that call's end,
+ *     because the scratch buffers are shared;
  *   - the create / host-buffer entry points copy on a private non-blocking
  *     stream: device buffers passed to them must be complete (no kernel of
  *     the caller still writing them) when the call is made;
@@ -221,6 +228,38 @@ int annb_merge_topk_dev(const uint64_t* d_part_ids, const float* d_part_dist, ui
                         uint32_t k, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
                         void* stream);
 
+/* The same exchange with one buffer per shard: shard p's [nq * k] ids start at d_parts + p * part_stride_bytes, its
+ * [nq * k] distances dist_offset_bytes further on, so ONE all-gather (or one peer copy per shard) moves ids and distances
+ * together.  Ties on distance keep the shards' own order, lower shard first: every shard returns its rows in the index's
+ * own order -- (distance, row) flat, (distance, list position) IVF -- and shards own ascending disjoint row / list
+ * ranges, so with the shards passed in that order the merged rows are bit-identical to the unsharded index's
+ * (annb_merge_topk_dev orders ties by id instead, which differs from the reference for IVF lists). */
+int annb_merge_shards_dev(const void* d_parts, uint64_t part_stride_bytes, uint64_t dist_offset_bytes, uint32_t parts,
+                          uint64_t nq, uint32_t k, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
+                          void* stream);
+
+/* ------------------------------------------------------- several devices -- */
+
+/* One index over several GPUs of one box, driven from one process: the `device` argument of
+ * build_exhaustive_index_gpu / build_ivf_index_gpu (src/lib.rs:2813, 2913) becomes a device list.  Rows (flat) or
+ * inverted lists (IVF: contiguous list ranges balanced by vector count; centroid table and offsets replicated) are
+ * sharded over `devices`; the returned handle is accepted by annb_flat_search, annb_flat_search_self, annb_ivf_search,
+ * annb_flat_search_dev / annb_ivf_search_dev (buffers on devices[0]; these two then run synchronously),
+ * annb_index_get_info / set_option / get_stat (options go to every shard, counters add up) and annb_destroy.
+ * Per batch every device receives the queries straight from the caller's buffer, IVF devices rank the centroids for
+ * their slice of the batch and exchange the probe lists by peer copies, every device searches its shard and stores its
+ * per-shard top-k into its slot on devices[0] over NVLink, devices[0] merges (annb_merge_shards_dev's order: results are
+ * bit-identical to the single-device index) and the result leaves with one device -> host copy.  Arguments as for
+ * annb_flat_create / annb_ivf_create (SQ8 flat shards share one codebook trained on all rows). */
+int annb_flat_create_multi(annb_index** out, const float* data, uint64_t n, uint32_t dim, int dtype, int metric,
+                           const int* devices, int n_devices);
+int annb_ivf_create_multi(annb_index** out, const void* vectors, const void* norms, const float* centroids,
+                          const float* centroid_norms, const uint64_t* offsets, const uint64_t* original_ids,
+                          uint64_t n, uint32_t dim, uint32_t nlist, int dtype, int metric, const float* sq8_scales,
+                          const int* devices, int n_devices);
+/* Number of per-device shards behind a handle (1 for an ordinary handle). */
+int annb_index_shard_count(const annb_index* index, uint32_t* out);
+
 /* Index facts: ExhaustiveIndexGpu::memory_usage_bytes (src/gpu/exhaustive_gpu.rs:205-209),
  * IvfIndexGpu::memory_usage_bytes (src/gpu/ivf_gpu.rs:590-604). */
 typedef struct annb_index_info {
@@ -247,7 +286,8 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
  *               "tc_ts" (tensor paths: 1 = query operand resident in TMEM), "tc_bf16_hybrid" (flat BF16 index, f32 queries: 1 = third
  *               query term multiplied from shared memory instead of TMEM; experiment, default 0), "ivf_fast_probe" (0/1/2),
  *               "ivf_tc_coarse" (1 = rank the centroids on the tensor cores when nlist >= 512, 0 = CUDA-core ranking only),
- *               "cert_eps_log2" (error bound assumed by the coverage certificate of the tensor paths, default -19; 0 = off),
+ *               "cert_eps_log2" (error bound assumed by the coverage certificate of the tensor paths: negative = 2^value, 0 = certificate off,
+ *               1 = derived per kernel from its MMA count, the default -- DESIGN.md section 3), "async_dev" (see Conventions),
  *               "cert_fallback" (1 = queries that fail the certificate are recomputed on the exact CUDA-core path)
  *   get_stat  : "kernel_launches" (cumulative), "scanned_vectors" (IVF, last call: sum of probed
  *               list lengths), "scanned_vectors_local" (the part of it that lies in this handle's own lists),
@@ -255,6 +295,7 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
  *               "coarse_path" (IVF, last call: 0 exact dense centroid ranking, 1 fused CUDA-core select, 2 tensor cores),
  *               "uncertified" (tensor path, last call: queries that failed the coverage certificate),
  *               "fallback_queries" (cumulative: queries recomputed on the exact path),
+ *               "cert_eps_bits" (f32 bit pattern of the error bound the last tensor-path certificate assumed),
  *               "dominant_kernel_ns" / "dominant_kernel_launches" (with "time_kernels": summed device time and count
  *               of the dominant kernel -- flat distance+select kernel or IVF list-scan kernel -- since the option was set) */
 int annb_index_set_option(annb_index* index, const char* key, int64_t value);
@@ -269,6 +310,10 @@ int annb_debug_fetch_tile(annb_index* index, float* host_out);
  * IVF handle: {total, schedule, query gather, epilogue wait-tmem-full, mma wait-queries, mma wait-data,
  * mma wait-tmem-empty, tasks << 32 | tiles} of CTA 0 of the last tensor-core scan. */
 int annb_debug_fetch_cycles(annb_index* index, uint64_t* host_out8);
+/* The queries (batch-relative numbers) of the last tensor-path batch that failed the coverage certificate: *out_count
+ * receives their number, host_out the first min(count, capacity) of them.  With option "cert_fallback" = 0 these are the
+ * only rows of the result that may differ from the exact answer. */
+int annb_debug_fetch_uncertified(annb_index* index, uint32_t* host_out, uint32_t capacity, uint32_t* out_count);
 
 void annb_destroy(annb_index* index);
 

@@ -1,0 +1,114 @@
+"""Multi-device handles (annb_flat_create_multi / annb_ivf_create_multi): one index sharded over several
+GPUs behind ONE handle, driven from one process.  Results must be bit-identical to the single-device handle and to the CPU
+oracle -- including the order of equal distances, which the merge takes from the shard order.  On a one-GPU box the shards
+all live on device 0 (an ordinal may be listed more than once); with more GPUs visible the same tests spread over them."""
+import numpy as np
+import pytest
+
+import annb200
+from annb200 import datagen
+from oracle import oracle as o
+from util import assert_exact, assert_tie_classes
+
+pytestmark = pytest.mark.gpu
+
+DT = {"f32": (annb200.F32, o.F32), "bf16": (annb200.BF16, o.BF16), "sq8": (annb200.SQ8, o.SQ8)}
+MET = {"l2": (annb200.L2, o.L2), "cosine": (annb200.COSINE, o.COSINE)}
+
+
+def _devices(gpu, shards):
+    return [i % gpu for i in range(shards)]
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "sq8"])
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("shards", [1, 3, 8])
+def test_flat_multi_equals_single_and_oracle(gpu, dtype, metric, shards):
+    data = datagen.gaussian_noise(40_000, 64, seed=3)
+    q = datagen.subsample_with_noise(data, 500, seed=3)
+    m = annb200.ExhaustiveIndexB200.new(data, MET[metric][0], DT[dtype][0], device=_devices(gpu, shards))
+    assert m.shard_count == shards and m.n == 40_000
+    ids, d, cnt = m.query_batch(q, 10)
+    c = o.build_flat(data, MET[metric][1], DT[dtype][1])
+    ref = o.flat_search(c, q, 10)
+    assert_exact(ids, d, ref[0], ref[1], f"multi flat {dtype} {metric} x{shards}")
+    assert (cnt == 10).all()
+    s = annb200.ExhaustiveIndexB200.new(data, MET[metric][0], DT[dtype][0])
+    ids1, d1, _ = s.query_batch(q, 10)
+    assert_exact(ids, d, ids1, d1, "multi vs single handle")
+
+
+def test_flat_multi_ties_follow_the_unsharded_order(gpu):
+    """Coarse integer data: many equal distances across shard borders.  The merged order must be (distance, row)."""
+    rng = np.random.default_rng(5)
+    data = rng.integers(-2, 3, size=(20_000, 16)).astype(np.float32)
+    q = rng.integers(-2, 3, size=(200, 16)).astype(np.float32)
+    m = annb200.ExhaustiveIndexB200.new(data, annb200.L2, annb200.F32, device=_devices(gpu, 5))
+    ids, d, _ = m.query_batch(q, 25)
+    ref = o.flat_search(o.build_flat(data, o.L2), q, 25)
+    assert_exact(ids, d, ref[0], ref[1], "ties across shards")
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "sq8"])
+def test_flat_multi_self_knn(gpu, dtype):
+    """generate_knn over a multi-device handle: query rows come from the shards that own them (peer copies)."""
+    data = datagen.correlated(30_000, 50, seed=9)
+    m = annb200.ExhaustiveIndexB200.new(data, annb200.L2, DT[dtype][0], device=_devices(gpu, 4))
+    ids, d, _ = m.generate_knn(15, row_begin=7_000, row_end=9_000)       # straddles the border between shards 0 and 1
+    c = o.build_flat(data, o.L2, DT[dtype][1])
+    ref = o.flat_search(c, None, 15, self_rows=np.arange(7_000, 9_000), self_mode=True)
+    assert_exact(ids, d, ref[0], ref[1], f"multi self {dtype}")
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "sq8"])
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("shards", [2, 8])
+def test_ivf_multi_equals_oracle(gpu, dtype, metric, shards):
+    data = datagen.gaussian_noise(60_000, 64, seed=13)
+    q = datagen.subsample_with_noise(data, 700, seed=13)
+    ci = o.build_ivf(data, MET[metric][1], nlist=128, dtype=DT[dtype][1], kmeans_iters=4)
+    norms = ci.norms_i if ci.dtype == o.SQ8 else ci.norms
+    m = annb200.IvfIndexB200.from_parts(ci.vectors, ci.centroids, ci.offsets, ci.original_ids, ci.dtype, ci.metric, norms=norms,
+                                        centroid_norms=ci.centroid_norms, sq8_scales=ci.scales, device=_devices(gpu, shards))
+    assert m.shard_count == shards
+    for nprobe in (8, 0):
+        ids, d, cnt = m.query_batch(q, 10, nprobe=nprobe or None)
+        ref = o.ivf_search(ci, q, 10, nprobe=nprobe or None)
+        if dtype == "sq8":
+            assert_tie_classes(ids, d, ref[0], ref[1], f"multi ivf sq8 {metric} x{shards}")
+        else:
+            assert_exact(ids, d, ref[0], ref[1], f"multi ivf {dtype} {metric} x{shards} nprobe={nprobe}")
+
+
+def test_ivf_multi_ties_follow_list_position(gpu):
+    """Equal distances that straddle shards: the unsharded IVF order is (distance, list position), NOT (distance, id)."""
+    rng = np.random.default_rng(21)
+    base = rng.integers(-2, 3, size=(400, 8)).astype(np.float32)
+    data = np.repeat(base, 30, axis=0)                                  # 30 copies of every vector, original ids interleaved below
+    perm = rng.permutation(data.shape[0])
+    data = np.ascontiguousarray(data[perm])
+    q = base[:100] + 0.01
+    ci = o.build_ivf(data, o.L2, nlist=32, kmeans_iters=3)
+    m = annb200.IvfIndexB200.from_parts(ci.vectors, ci.centroids, ci.offsets, ci.original_ids, ci.dtype, ci.metric, device=_devices(gpu, 4))
+    ids, d, _ = m.query_batch(q, 20, nprobe=32)
+    ref = o.ivf_search(ci, q, 20, nprobe=32)
+    assert_exact(ids, d, ref[0], ref[1], "ivf ties across shards")
+
+
+def test_multi_handle_errors_and_info(gpu):
+    data = datagen.gaussian_noise(5_000, 32, seed=1)
+    with pytest.raises(annb200.AnnSearchError) as e:
+        annb200.ExhaustiveIndexB200.new(data, annb200.L2, annb200.F32, device=[0, 99])
+    assert e.value.variant == "InvalidArgument"
+    with pytest.raises(annb200.AnnSearchError) as e:
+        annb200.ExhaustiveIndexB200.new(data, annb200.MANHATTAN, annb200.F32, device=[0, 0])
+    assert e.value.variant == "DistanceNotSupported"
+    m = annb200.ExhaustiveIndexB200.new(data, annb200.L2, annb200.F32, device=[0, 0])
+    with pytest.raises(annb200.AnnSearchError) as e:
+        m.query_batch(np.zeros((3, 31), np.float32), 5)
+    assert e.value.variant == "DimensionMismatch"
+    info = m.info()
+    assert info.n == 5_000 and info.dim == 32 and info.device == 0 and info.device_bytes > 5_000 * 32 * 4
+    m.set_option("path", annb200.PATH_SIMT)
+    ids, d, _ = m.query_batch(data[:10], 3)
+    assert (ids[:, 0] == np.arange(10)).all() and m.get_stat("last_path") == annb200.PATH_SIMT

@@ -184,3 +184,66 @@ def test_bf16_hybrid_operand_placement(gpu, metric, dim):
     g.set_option("db_splits", 0)
     ids, d, cnt = g.query_batch(q, 10)
     assert_exact(ids, d, rids, rd, f"hybrid bf16 {metric} dim={dim}, auto splits")
+
+
+def _adversarial_data(rng, n, dim, nq):
+    """Worst case for the tensor core's accumulation and for the certificate: all-positive operands (every product and
+    every partial sum has the same sign, so truncation errors add up instead of cancelling), dim 128, row norms spread
+    over 10^3, and groups of near-duplicates whose mutual distances lie far BELOW the error bound (perturbation 1e-6) next
+    to groups that are well separated (perturbation 3e-2)."""
+    bases = rng.uniform(0.5, 1.0, size=(64, dim)).astype(np.float32)
+    which = rng.integers(0, 64, n)
+    scale = np.float32(10.0) ** rng.integers(0, 4, n).astype(np.float32)          # |x| in {1, 10, 100, 1000} x |base|
+    pert = np.where(which < 32, np.float32(1e-6), np.float32(3e-2))
+    rows = bases[which] * (1.0 + pert[:, None] * np.abs(rng.standard_normal((n, dim)))).astype(np.float32)
+    data = np.ascontiguousarray(rows * scale[:, None], dtype=np.float32)
+    pick = rng.choice(n, nq, replace=False)
+    q = np.ascontiguousarray(data[pick] * (1.0 + np.float32(1e-3) * np.abs(rng.standard_normal((nq, dim)))).astype(np.float32))
+    return data, q
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_adversarial_certificate_same_sign_operands(gpu, dtype, metric):
+    """(i) With the exact fallback on, results are the oracle's bits -- whatever the certificate decided.
+    (ii) With the fallback off, every query the certificate did NOT list must already be the oracle's bits:
+    certified => equal.  (iii) The measured error of the selection values stays inside the bound the certificate assumes
+    (at most one ulp of a |q||x|-sized partial sum per accumulating MMA)."""
+    rng = np.random.default_rng(77)
+    n, dim, nq, k = 16384, 128, 256, 10
+    data, q = _adversarial_data(rng, n, dim, nq)
+    g, c = _pair(data, dtype, metric)
+    ref = o.flat_search(c, q, k)
+    ids, d, _ = g.query_batch(q, k)
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    assert_exact(ids, d, ref[0], ref[1], f"adversarial {dtype} {metric}: with fallback")
+    n_unc = g.get_stat("uncertified")
+    g.set_option("cert_fallback", 0)
+    ids0, d0, _ = g.query_batch(q, k)
+    unc = set(g.uncertified_queries().tolist())
+    assert len(unc) == n_unc
+    differ = np.nonzero((ids0 != ref[0]).any(axis=1) | (bits(d0) != bits(ref[1])).any(axis=1))[0]
+    assert set(differ.tolist()) <= unc, f"{len(set(differ.tolist()) - unc)} queries were certified but differ from the oracle"
+    assert 0 < n_unc, "the near-duplicate groups must defeat the certificate (otherwise this test exercises nothing)"
+    # (iii) tile (0, 0): selection values against float64 on the very operands the index stores
+    g.set_option("cert_fallback", 1)
+    g.set_option("tc_debug", 1)
+    g.set_option("db_splits", 1)
+    g.query_batch(q, k)
+    v = g.debug_fetch_tile().astype(np.float64)
+    x = (o.decode_bf16(c.vectors[:128]) if dtype == "bf16" else data[:128]).astype(np.float64)
+    q64 = q[:128].astype(np.float64)
+    s = q64 @ x.T
+    qn, xn = np.sqrt((q64 * q64).sum(1)), np.sqrt((x * x).sum(1))
+    eps = g.cert_eps()
+    if metric == "l2":
+        err = np.abs(v - ((x * x).sum(1)[None, :] - 2 * s)) / (qn[:, None] + xn[None, :]) ** 2
+    else:
+        err = np.abs(v - (-s / c.norms[:128].astype(np.float64)[None, :])) / qn[:, None]
+    print(f"\n[adversarial {dtype} {metric}] max selection-value error {err.max():.3e} = {err.max() / eps:.3f} of the certificate bound {eps:.3e}; "
+          f"uncertified {n_unc}/{nq}")
+    assert err.max() <= eps, f"selection-value error {err.max():.3e} exceeds the bound {eps:.3e} the certificate assumes"
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)

@@ -36,6 +36,21 @@ def _merge_reference(g_ids, g_dist, k):
     return out_i, out_d
 
 
+def _merge_shards_reference(g_ids, g_dist, k):
+    """(distance, shard, position) merge -- numpy statement of annb_merge_shards_dev: a stable sort on distance alone of the
+    shards' lists concatenated in shard order."""
+    parts, nq, _ = g_ids.shape
+    out_i = np.full((nq, k), -1, np.int64)
+    out_d = np.full((nq, k), np.inf, np.float32)
+    for q in range(nq):
+        ids = g_ids[:, q, :].reshape(-1)
+        d = g_dist[:, q, :].reshape(-1)
+        keep = ids >= 0
+        order = np.argsort(d[keep], kind="stable")[:k]
+        out_i[q, :order.size], out_d[q, :order.size] = ids[keep][order], d[keep][order]
+    return out_i, out_d
+
+
 def _worker(rank, world, port, kind, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -68,8 +83,14 @@ def _worker(rank, world, port, kind, ret):
                     ids[qi, j], d[qi, j] = full.original_ids[v], dd
         g_ids, g_d = D.allgather_topk(torch.from_numpy(ids), torch.from_numpy(d))
         m_ids, m_d = _merge_reference(g_ids.numpy(), g_d.numpy(), k)
+        # the one-collective form used by ShardedSearch: interleaved [ids | distances] blocks, merged in shard order
+        gathered = D.allgather_blocks(D.pack_block(torch.from_numpy(ids), torch.from_numpy(d)))
+        b_ids, b_d = D.unpack_blocks(gathered, world, q.shape[0], k)
+        assert torch.equal(b_ids, g_ids) and torch.equal(b_d.view(torch.int32), g_d.view(torch.int32))
+        s_ids, s_d = _merge_shards_reference(b_ids.numpy(), b_d.numpy(), k)
         if rank == 0:
             ret["ids"], ret["dist"] = m_ids, m_d
+            ret["s_ids"], ret["s_dist"] = s_ids, s_d
     finally:
         dist.destroy_process_group()
 
@@ -88,6 +109,9 @@ def test_two_rank_sharded_search_equals_unsharded(kind):
         ref = o.ivf_search(o.build_ivf(data, o.L2, nlist=24, kmeans_iters=4), q, 7, nprobe=5)
     assert (np.asarray(ret["dist"]).view(np.uint32) == ref[1].view(np.uint32)).all()
     assert (np.sort(np.asarray(ret["ids"]), axis=1) == np.sort(ref[0], axis=1)).all()
+    # the shard-order merge reproduces the unsharded rows exactly, ids in the reference's own tie order included
+    assert (np.asarray(ret["s_dist"]).view(np.uint32) == ref[1].view(np.uint32)).all()
+    assert (np.asarray(ret["s_ids"]) == ref[0]).all()
 
 
 def test_partition_helpers():

@@ -129,25 +129,48 @@ def build_ivf_parts_gpu(data, nlist, dtype, device_index, seed=42, kmeans_iters=
     counts = torch.bincount(assign, minlength=nlist).cpu().numpy()
     offsets = np.zeros(nlist + 1, dtype=np.uint64)
     offsets[1:] = np.cumsum(counts)
-    scales = None
+    base = dict(vectors=data[order].contiguous(), centroids=cent, offsets=offsets, original_ids=order.contiguous(), scales=None,
+                train_absmax=train.abs().amax(dim=0))
+    return requantise_parts(base, dtype)
+
+
+def requantise_parts(base, dtype, chunk=1 << 20):
+    """The BF16 / SQ8 form of an f32 parts dict (same lists, same centroids): encode_bf16_quantisation (quantisers.rs:31-38)
+    or ScalarQuantiser with the codebook of the training sample (ivf_sq8.rs:211).  F32: the dict itself."""
     if dtype == annb200.F32:
-        vec = data[order].contiguous()
-    elif dtype == annb200.BF16:
-        vec = data[order].to(torch.bfloat16).contiguous()              # RNE, as half::bf16::from_f32
-    else:
-        mx = train.abs().amax(dim=0)                                    # codebook from the training sample (ivf_sq8.rs:211)
-        scales = torch.where(mx <= 0, torch.ones_like(mx), mx / 128.0)
-        scaled = data[order] / scales
+        return base
+    src = base["vectors"]
+    out = dict(base)
+    if dtype == annb200.BF16:
+        out["vectors"] = src.to(torch.bfloat16).contiguous()              # RNE, as half::bf16::from_f32
+        return out
+    mx = base["train_absmax"]
+    scales = torch.where(mx <= 0, torch.ones_like(mx), mx / 128.0)
+    vec = torch.empty(src.shape, dtype=torch.int8, device=src.device)
+    for s in range(0, src.shape[0], chunk):
+        scaled = src[s:s + chunk] / scales
         r = scaled + 0.5 * torch.where(torch.signbit(scaled), -torch.ones_like(scaled), torch.ones_like(scaled))
-        vec = torch.trunc(r.clamp(-128.0, 127.0)).to(torch.int8).contiguous()
-    return dict(vectors=vec, centroids=cent, offsets=offsets, original_ids=order.contiguous(), scales=scales)
+        vec[s:s + chunk] = torch.trunc(r.clamp(-128.0, 127.0)).to(torch.int8)
+    out["vectors"] = vec
+    out["scales"] = scales
+    return out
 
 
 def ivf_handle_from_parts(parts, n_total, dim, dtype, metric, device_index, list_begin=0, list_end=None):
+    """device_index: one ordinal (optionally with a list range = one shard), or a list of ordinals (annb_ivf_create_multi)."""
     lib = annb200.lib()
     nlist = parts["centroids"].shape[0]
-    list_end = nlist if list_end is None else list_end
     off = parts["offsets"]
+    if isinstance(device_index, (list, tuple)):
+        vec, oid, cent, sc = parts["vectors"], parts["original_ids"], parts["centroids"].contiguous(), parts["scales"]
+        torch.cuda.synchronize(vec.device)
+        devs = (C.c_int * len(device_index))(*[int(d) for d in device_index])
+        h = C.c_void_p()
+        annb200._check(lib.annb_ivf_create_multi(C.byref(h), C.c_void_p(vec.data_ptr()), None, C.c_void_p(cent.data_ptr()), None,
+                                                 C.c_void_p(off.ctypes.data), C.c_void_p(oid.data_ptr()), n_total, dim, nlist, dtype, metric,
+                                                 None if sc is None else C.c_void_p(sc.contiguous().data_ptr()), devs, len(device_index)))
+        return annb200.IvfIndexB200(h)
+    list_end = nlist if list_end is None else list_end
     r0, r1 = int(off[list_begin]), int(off[list_end])
     vec = parts["vectors"][r0:r1]
     oid = parts["original_ids"][r0:r1]
