@@ -563,7 +563,7 @@ static int ivf_enqueue(annb_index* ix, const PreparedQueries& pq, uint64_t nq, u
     uint32_t parts = ix->opt_scan_parts > 0 ? static_cast<uint32_t>(ix->opt_scan_parts) : static_cast<uint32_t>(std::min<uint64_t>(want, 32));
     parts = std::max(1u, std::min(parts, np));
     // very small batches (the tensor path's exact fallback): also cut every list into row segments
-    uint32_t subs = ix->opt_scan_parts > 0 ? 1u : static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(8, want / parts)));
+    uint32_t subs = ix->opt_scan_parts > 0 ? 1u : static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(16, want / parts)));
     while (subs > 1 && static_cast<uint64_t>(parts) * subs * kk * 8 > 128 * 1024) subs--;
     const uint32_t nsort = WarpSelect::sort_size(kk);
     ANNB_TRY(ix->s_keys.ensure(nq * parts * subs * static_cast<uint64_t>(kk) * 8));
@@ -578,7 +578,12 @@ static int ivf_enqueue(annb_index* ix, const PreparedQueries& pq, uint64_t nq, u
         uint32_t grid = static_cast<uint32_t>(ceil_div<uint64_t>(nq * parts * subs, SCAN_WARPS));
         {
             KernelTimer kt(ix, s, !force_simt);   // (the exact fallback of a tensor-path call is not the dominant kernel)
-            ANNB_TRY(launch_scan(ix->dtype, pq.qt, ix->metric, sp, grid, smem, s));
+            if (tc_stream_supported(ix)) {
+                StreamScanArgs a{pq.scan, pq.scan_bytes, nq, pq.qt, pq.bf16_self, d_probes, pitch, d_nprobes, parts, subs, kk, nsort, ix->s_keys.as<uint64_t>()};
+                ANNB_TRY(tc_stream_scan(ix, a, s));
+            } else {
+                ANNB_TRY(launch_scan(ix->dtype, pq.qt, ix->metric, sp, grid, smem, s));
+            }
         }
         ix->stat_launches++;
     }
@@ -793,6 +798,7 @@ void annb_destroy(annb_index* ix) {
     collect_timers(ix);
     tc_destroy(ix);
     tc_ivf_destroy(ix);
+    tc_stream_destroy(ix);
     tc_coarse_destroy(ix);
     cudaFree(ix->d_rows); cudaFree(ix->d_norms); cudaFree(ix->d_norms_i); cudaFree(ix->d_scales);
     cudaFree(ix->d_centroids); cudaFree(ix->d_centroid_norms); cudaFree(ix->d_offsets); cudaFree(ix->d_original_ids); cudaFree(ix->d_list_order);
@@ -1276,6 +1282,7 @@ int annb_ivf_create(annb_index** out, const void* vectors, const void* norms, co
     }
     ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
     ANNB_TRY(tc_ivf_prepare(ix));
+    ANNB_TRY(tc_stream_prepare(ix));
     ANNB_TRY(tc_coarse_prepare(ix));
     ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
     cleanup.armed = false;
@@ -1441,6 +1448,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "tc_candidates") ix->opt_tc_candidates = static_cast<int>(value);
     else if (k == "tc_ts") ix->opt_tc_ts = static_cast<int>(value);
     else if (k == "tc_bf16_hybrid") ix->opt_tc_bf16_hybrid = static_cast<int>(value);
+    else if (k == "tc_bf16_terms") ix->opt_tc_bf16_terms = static_cast<int>(value);
     else if (k == "cert_fallback") ix->opt_cert_fallback = static_cast<int>(value);
     else if (k == "cert_eps_log2") ix->opt_cert_eps = value == 0 ? 0.f : (value > 0 ? -1.0f : std::ldexp(1.0f, static_cast<int>(value)));   // e.g. -18; 0 switches the certificate off; 1 = derived bound (default)
     else if (k == "tc_debug") { DeviceGuard g(ix->device); return ix->is_ivf ? tc_ivf_debug_enable(ix, value != 0) : tc_debug_enable(ix, value != 0); }
@@ -1450,6 +1458,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "ivf_list_major") ix->opt_ivf_list_major = static_cast<int>(value);
     else if (k == "ivf_fast_probe") ix->opt_ivf_fast_probe = static_cast<int>(value);
     else if (k == "ivf_tc_coarse") ix->opt_ivf_tc_coarse = static_cast<int>(value);
+    else if (k == "ivf_stream") ix->opt_ivf_stream = static_cast<int>(value);
     else if (k == "async_dev") ix->opt_async_dev = static_cast<int>(value);
     else if (k == "time_kernels") { ix->opt_time_kernels = static_cast<int>(value); ix->timed_ms_total = 0.0; ix->timed_launches = 0; }
     else return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown option " + k);

@@ -36,6 +36,8 @@ namespace tc {
 // database slab from shared memory (half the operand bandwidth) and the whole 227 KB becomes database ring.
 // DENSE = write every selection value to p.dense instead of keeping a top-k' (the IVF centroid ranking consumes the full
 // [nq x nlist] matrix of approximate values; see coarse_select_kernel).
+__device__ __forceinline__ bool hyb_cfg(const Params& p) { return p.hybrid != 0; }
+
 template <int KIND, int KP, int MET, bool TS, bool DENSE = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const Params p) {
@@ -45,10 +47,13 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     static_assert(KIND != KIND_I8 || TS, "the int8 kernel keeps its queries in TMEM");
     constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;      // 32 tf32 / 64 bf16 per slab row
     constexpr int KSTEPS = 4;                          // 128 B / 32 B per UMMA K step (8 tf32 / 16 bf16)
-    // accumulator stages behind the TMEM-resident queries (TS): f32 / bf16 pieces take up to 256 columns, int8 codes 128
-    constexpr int NACC = TS ? (KIND == KIND_I8 ? 3 : 2) : ACC_STAGES;
-    constexpr uint32_t ACC_COL0 = TS ? (KIND == KIND_I8 ? 128u : 256u) : 0u;
-    constexpr uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : (KIND == KIND_I8 ? 32u : 64u);   // TMEM columns per query piece (32-bit words per row)
+    // TMEM columns per query piece (32-bit words per row): f32 128; bf16 terms 64 (rows of <= 128 elements) or 128; int8 codes 128
+    const uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : (KIND == KIND_I8 ? 128u : (p.kp > 128u ? 128u : 64u));
+    // accumulator stages behind the TMEM-resident queries (TS): three when the pieces take at most 128 columns (int8 codes, one
+    // or two bf16 terms of narrow rows), two when they take up to 256 (f32 hi / lo, three bf16 terms, two bf16 terms of wide rows)
+    const uint32_t q_cols = (KIND == KIND_I8) ? 128u : ((hyb_cfg(p) ? 2u : p.a_pieces) * PIECE_COLS);
+    const uint32_t NACC = TS ? (q_cols <= 128u ? 3u : 2u) : static_cast<uint32_t>(ACC_STAGES);
+    const uint32_t ACC_COL0 = TS ? (q_cols <= 128u ? 128u : 256u) : 0u;
 
     extern __shared__ __align__(1024) uint8_t smem[];  // SWIZZLE_128B tiles need 1024-byte aligned bases
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -81,7 +86,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         for (uint32_t s = 0; s < p.n_stages; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
         mbar_init(bar_q, TS ? EPI_THREADS : 1);
         mbar_init(bar_q2, 1);
-        for (int a = 0; a < NACC; a++) { mbar_init(bar_tfull + a, 1); mbar_init(bar_tempty + a, EPI_THREADS); }
+        for (uint32_t a = 0; a < NACC; a++) { mbar_init(bar_tfull + a, 1); mbar_init(bar_tempty + a, EPI_THREADS); }
         fence_barrier_init();
         fence_proxy_async();
         tma_prefetch_desc(&tm_q);
@@ -167,8 +172,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                             // bf16 query terms q0, q1, q2 in TMEM at columns [0,64), [64,128), [128,192); 8 columns (16 bf16) per K step
                             const uint32_t a0 = tmem_base + s * 32 + k * 8;
                             umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
-                            if (p.a_pieces > 1) {
-                                umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
+                            if (p.a_pieces > 1) umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
+                            if (p.a_pieces > 2) {
                                 if (hyb) umma<KIND>(tmem_c, qd + 2 * k, xd + 2 * k, idesc, 1u);
                                 else umma_ts<KIND>(tmem_c, a0 + 2 * PIECE_COLS, xd + 2 * k, idesc, 1u);
                             }
@@ -179,10 +184,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                             umma<KIND>(tmem_c, qd + 2 * k, xd + SLAB_DESC + 2 * k, idesc, 1u);
                         } else {
                             umma<KIND>(tmem_c, qd + 2 * k, xd + 2 * k, idesc, first);
-                            if (p.a_pieces > 1) {
-                                umma<KIND>(tmem_c, qd + q_piece + 2 * k, xd + 2 * k, idesc, 1u);
-                                umma<KIND>(tmem_c, qd + 2 * q_piece + 2 * k, xd + 2 * k, idesc, 1u);
-                            }
+                            if (p.a_pieces > 1) umma<KIND>(tmem_c, qd + q_piece + 2 * k, xd + 2 * k, idesc, 1u);
+                            if (p.a_pieces > 2) umma<KIND>(tmem_c, qd + 2 * q_piece + 2 * k, xd + 2 * k, idesc, 1u);
                         }
                     }
                     umma_commit(bar_empty + stage);                       // slab consumed once the MMAs above retire
@@ -336,6 +339,7 @@ struct CoarseSelectParams {
     uint32_t dense_ld;
     uint64_t nq;
     uint32_t nlist, pitch, cmax;   // cmax: candidate capacity, a power of two >= pitch
+    uint32_t staged_words;         // round_up(nlist, 4) when the row of values is kept in shared memory, 0 otherwise
     const float* queries;       // f32 routing queries [nq][q_ld]
     uint32_t q_ld;
     const float* centroids;     // [nlist][c_ld]
@@ -346,8 +350,8 @@ struct CoarseSelectParams {
     uint64_t* ranked;           // [nq][pitch]
 };
 
-__host__ __device__ inline size_t coarse_select_warp_bytes(uint32_t cmax) {
-    return static_cast<size_t>(cmax) * 8 + 256 * 4 + static_cast<size_t>(cmax) * 4;   // keys | histogram | candidate cells
+__host__ __device__ inline size_t coarse_select_warp_bytes(uint32_t cmax, uint32_t staged_words) {
+    return static_cast<size_t>(cmax) * 8 + 256 * 4 + static_cast<size_t>(cmax) * 4 + static_cast<size_t>(staged_words) * 4;   // keys | histogram | candidate cells | staged row
 }
 
 template <int MET>
@@ -356,26 +360,35 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(CoarseSelectParams p
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t q = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
     if (q >= p.nq) return;   // warps are independent: no block-wide barrier below
-    uint8_t* base = smem + warp * coarse_select_warp_bytes(p.cmax);
+    uint8_t* base = smem + warp * coarse_select_warp_bytes(p.cmax, p.staged_words);
     uint64_t* keys = reinterpret_cast<uint64_t*>(base);                  // [cmax]
     uint32_t* hist = reinterpret_cast<uint32_t*>(keys + p.cmax);         // [256]
     uint32_t* cand = hist + 256;                                          // [cmax]
-    // The row of values is not staged: the (few) passes re-read it with coalesced 128-bit loads -- it stays in L1 / L2,
-    // and the small shared-memory footprint keeps many warps resident to hide the latency.  dense_ld is a multiple of 128.
+    uint4* staged = reinterpret_cast<uint4*>(cand + p.cmax);              // [staged_words / 4] ordered images of the row (16-byte aligned: cmax is a multiple of 4)
+    // The row of values is read from global memory once (coalesced 128-bit loads) and kept in shared memory as ordered
+    // integer images; the select's passes then run at shared-memory speed.  Very long rows (staged_words == 0) are
+    // re-read from L2 by every pass instead.  dense_ld is a multiple of 128.
     const float4* src4 = reinterpret_cast<const float4*>(p.dense + q * p.dense_ld);
     const uint32_t n4 = (p.nlist + 3) >> 2;
+    const bool use_smem = p.staged_words != 0;
     auto ord = [&](float4 x, uint32_t i4, uint32_t u[4]) {   // ordered images; columns past nlist never qualify
         u[0] = f32_to_ordered(x.x); u[1] = f32_to_ordered(x.y); u[2] = f32_to_ordered(x.z); u[3] = f32_to_ordered(x.w);
 #pragma unroll
         for (int e = 0; e < 4; e++) if (4 * i4 + e >= p.nlist) u[e] = 0xFFFFFFFFu;
     };
+    auto fetch = [&](uint32_t i4, uint32_t u[4]) {
+        if (use_smem) { const uint4 w = staged[i4]; u[0] = w.x; u[1] = w.y; u[2] = w.z; u[3] = w.w; }
+        else ord(__ldg(src4 + i4), i4, u);
+    };
     uint32_t umin = 0xFFFFFFFFu, umax = 0u;
     for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
         uint32_t u[4];
         ord(__ldg(src4 + i4), i4, u);
+        if (use_smem) staged[i4] = make_uint4(u[0], u[1], u[2], u[3]);
 #pragma unroll
         for (int e = 0; e < 4; e++) if (4 * i4 + e < p.nlist) { umin = min(umin, u[e]); umax = max(umax, u[e]); }
     }
+    __syncwarp();
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         umin = min(umin, __shfl_xor_sync(0xFFFFFFFFu, umin, off));
@@ -400,7 +413,7 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(CoarseSelectParams p
             __syncwarp();
             for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
                 uint32_t u[4];
-                ord(__ldg(src4 + i4), i4, u);
+                fetch(i4, u);
 #pragma unroll
                 for (int e = 0; e < 4; e++)
                     if (4 * i4 + e < p.nlist && (u[e] & hmask) == prefix) atomicAdd(hist + ((u[e] >> sh) & dmask), 1u);
@@ -446,7 +459,7 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(CoarseSelectParams p
     for (uint32_t i0 = 0; i0 < n4; i0 += 32) {
         const uint32_t i4 = i0 + lane;
         uint32_t u[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
-        if (i4 < n4) ord(__ldg(src4 + i4), i4, u);
+        if (i4 < n4) fetch(i4, u);
         uint32_t mine = 0;
 #pragma unroll
         for (int e = 0; e < 4; e++) mine += (4 * i4 + e < p.nlist && u[e] <= thr) ? 1u : 0u;
@@ -635,12 +648,14 @@ static EncodeTiledFn encode_fn() {
 }
 
 // 2-D row-major [rows][kp] tensor, box = {128 bytes of K, 128 rows}, SWIZZLE_128B.
-int tc_make_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint32_t kp_elems, int elem_bytes) {
+int tc_make_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint32_t kp_elems, int elem_bytes, uint32_t box_rows);
+int tc_make_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint32_t kp_elems, int elem_bytes) { return tc_make_tmap(tm, base, rows, kp_elems, elem_bytes, tc::BM); }
+int tc_make_tmap(CUtensorMap* tm, void* base, uint64_t rows, uint32_t kp_elems, int elem_bytes, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_last_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return ANNB_ERR_CUDA; }
     cuuint64_t dims[2] = {kp_elems, rows};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(kp_elems) * elem_bytes};
-    cuuint32_t box[2] = {static_cast<cuuint32_t>(tc::SLAB_BYTES / elem_bytes), static_cast<cuuint32_t>(tc::BM)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(tc::SLAB_BYTES / elem_bytes), static_cast<cuuint32_t>(box_rows)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8), 2, base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -778,7 +793,9 @@ float tc_cert_eps(const annb_index* ix, int kind, uint32_t kp_elems, uint32_t te
         E = (inkernel_split ? 5.0 : 3.0) * std::ldexp(1.0, -22) + TC_MMA_ULPS * n_mma * u23;
     } else {
         const double n_mma = static_cast<double>(terms) * (kp_elems / 16);
-        const double repr = terms >= 3 ? std::ldexp(1.0, -27) : (terms == 2 ? std::ldexp(1.0, -18) : 0.0);   // residual of the query's bf16 terms (self queries: exact)
+        // residual of the f32 query after its bf16 terms (each term keeps 8 significant bits, round to nearest: 2^-8 of what
+        // it rounds): 2^-16 |q| after two terms, 2^-24 after three; bf16 self queries are exact
+        const double repr = terms >= 3 ? std::ldexp(1.0, -24) : (terms == 2 ? std::ldexp(1.0, -16) : 0.0);
         E = repr + TC_MMA_ULPS * n_mma * u23;
     }
     const double ref = (ix->dim / 8 + 8) * u24;
@@ -849,7 +866,9 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     const uint32_t kp = st->kp_elems;
     const uint32_t kprime = pick_kprime(ix, k_eff);
     const uint32_t nq_pad = static_cast<uint32_t>(round_up<uint64_t>(nq, tc::BM));
-    const uint32_t na = kind == tc::KIND_TF32X3 ? 2 : ((qt == QT_BF16 || kind == tc::KIND_I8) ? 1 : 3);
+    // f32 queries against a BF16 index go in as two (default) or three bf16 terms q0 + q1 [+ q2]: 16 instead of 24 MMAs per tile
+    const uint32_t bf16_terms = ix->opt_tc_bf16_terms == 3 ? 3u : 2u;
+    const uint32_t na = kind == tc::KIND_TF32X3 ? 2 : ((qt == QT_BF16 || kind == tc::KIND_I8) ? 1 : bf16_terms);
 
     // ---- query operand: stacked pieces, zero padded ----
     ANNB_TRY(st->q_op.ensure(static_cast<uint64_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * nq_pad * kp * elem));
@@ -879,7 +898,8 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
     const uint32_t nb = kind == tc::KIND_TF32X3 ? 2 : 1;
     // query operand resident in TMEM (TS-mode MMA) when its pieces fit their column budget (bf16 terms: 64 columns each)
-    const bool ts = kind == tc::KIND_I8 || (ix->opt_tc_ts != 0 && (kind != tc::KIND_BF16 || kp * elem <= 256));
+    const uint32_t bf16_piece_cols = kp > 128 ? 128u : 64u;
+    const bool ts = kind == tc::KIND_I8 || (ix->opt_tc_ts != 0 && (kind != tc::KIND_BF16 || na * bf16_piece_cols <= 256));
     const bool hyb = ts && kind == tc::KIND_BF16 && na == 3 && ix->opt_tc_bf16_hybrid != 0;
     const size_t q_smem = ts ? (hyb ? static_cast<size_t>(st->nslab) * tc::SLAB_TILE : 0) : static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * st->nslab * tc::SLAB_TILE;
     const size_t fixed = 256 /*barriers*/ + 8 * 64 * 4 /*per-warp row constants*/;
@@ -988,8 +1008,8 @@ bool tc_coarse_supported(const annb_index* ix) { return ix->tc_coarse != nullptr
 template <int MET>
 static int launch_coarse_select(const tc::CoarseSelectParams& c, cudaStream_t s) {
     auto kern = tc::coarse_select_kernel<MET>;
-    const size_t per_warp = tc::coarse_select_warp_bytes(c.cmax);
-    const uint32_t warps = 8;
+    const uint32_t warps = 4;
+    const size_t per_warp = tc::coarse_select_warp_bytes(c.cmax, c.staged_words);
     const size_t smem = per_warp * warps;
     ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<static_cast<uint32_t>((c.nq + warps - 1) / warps), warps * 32, smem, s>>>(c);
@@ -1036,6 +1056,8 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     }
     tc::CoarseSelectParams c{};
     c.dense = st->dense.as<float>(); c.dense_ld = st->n_pad; c.nq = nq; c.nlist = ix->nlist; c.pitch = pitch; c.cmax = next_pow2(pitch + 1);
+    // rows of up to 8192 cells are staged in shared memory (32 KB per warp, four warps per CTA)
+    c.staged_words = ix->nlist <= 8192 ? round_up(ix->nlist, 4u) : 0u;
     c.queries = d_route; c.q_ld = route_ld; c.centroids = ix->d_centroids; c.c_ld = ix->cent_ld; c.centroid_norms = ix->d_centroid_norms;
     c.dim = ix->dim; c.eps = tc_cert_eps(ix, tc::KIND_TF32X3, kp, 2, false); c.cnorm_max = ix->tc_cnorm_max; c.ranked = d_ranked;
     if (ix->metric == ANNB_L2) ANNB_TRY(launch_coarse_select<MET_L2>(c, s));

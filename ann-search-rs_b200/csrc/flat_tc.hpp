@@ -28,6 +28,18 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
                 const uint32_t* d_pair_off, const uint32_t* d_task_off, const void* d_pairs, uint32_t* d_task_counter, uint64_t max_tasks,
                 const uint32_t* d_n_probes, const uint64_t* row_map, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s,
                 const void* d_tasks);
+// HBM-streaming query-major list scan (ivf_stream.cu): per-warp rings of TMA tile loads over the index rows themselves.
+struct StreamState;
+struct StreamScanArgs {
+    const uint8_t* queries; uint32_t q_bytes; uint64_t nq; int qt; int bf16_self;
+    const uint32_t* probes; uint32_t probe_pitch; const uint32_t* n_probes;
+    uint32_t parts, subs, k, nsort;
+    uint64_t* part_keys;
+};
+int tc_stream_prepare(annb_index* ix);
+void tc_stream_destroy(annb_index* ix);
+bool tc_stream_supported(const annb_index* ix);
+int tc_stream_scan(annb_index* ix, const StreamScanArgs& a, cudaStream_t s);
 // Tensor-core centroid ranking of an IVF index: dense approximate values (DENSE mode of the flat kernel) + per-query
 // radix select, exact re-computation and certification of the `pitch` nearest cells.
 int tc_coarse_prepare(annb_index* ix);

@@ -42,6 +42,7 @@ struct DevBuf {
 };
 
 struct TcState;     // tensor-core operand copies + tensor maps (flat_tc.cu)
+struct StreamState; // tensor map of the streaming list scan (ivf_stream.cu)
 struct IvfTcState;  // same for the IVF list scan (ivf_tc.cu)
 
 }  // namespace annb
@@ -77,6 +78,7 @@ struct annb_index {
     int opt_path = ANNB_PATH_AUTO;
     int opt_tc_candidates = 0;
     int opt_tc_bf16_hybrid = 0; // flat tensor path, bf16 index + f32 queries: third query term in shared memory (SS-mode MMA) instead of TMEM
+    int opt_tc_bf16_terms = 2;  // tensor paths, bf16 index + f32 queries: bf16 terms the query is split into (2 or 3)
     int opt_tc_ts = 1;         // tensor path, f32: keep the query operand in TMEM (TS-mode MMA)
     int opt_db_splits = 0;
     int opt_scan_parts = 0;
@@ -116,6 +118,8 @@ struct annb_index {
     annb::DevBuf s_uncert;         // [1 + nq] uncertified-query counter + list of the last tensor-path call
     annb::TcState* tc = nullptr;
     annb::IvfTcState* tc_ivf = nullptr;
+    annb::StreamState* tc_stream = nullptr;
+    int opt_ivf_stream = 1;               // query-major list scan: 1 = TMA-ring streaming kernel (ivf_stream.cu), 0 = cp.async kernel
     annb::TcState* tc_coarse = nullptr;   // centroid table as a tensor-core operand (IVF centroid ranking)
     float tc_cnorm_max = 0.f;             // largest centroid norm
     int opt_ivf_tc_coarse = 1;            // rank the centroids on the tensor cores (0: CUDA-core ranking only)

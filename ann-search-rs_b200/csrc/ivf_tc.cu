@@ -44,6 +44,7 @@ struct IvfTcParams {
     const uint4* tasks;        // [2 * n_tasks] task records written by ivf_pair_offsets_kernel
     uint32_t* task_counter;
     uint32_t probe_pitch;
+    uint32_t bf16_terms;       // bf16 lists: bf16 terms of the f32 query (2 or 3)
     uint64_t* part_keys;       // [nq][probe_pitch][2][KP]
     uint32_t* gtau;            // [nq] shared pruning threshold
     unsigned long long* dbg;   // optional [8]: CTA 0 cycle counters {total, schedule, gather, epi wait-tfull, mma wait-queries, mma wait-data, mma wait-tempty, tasks << 32 | tiles}
@@ -63,10 +64,12 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     constexpr int ELEM = (KIND == KIND_TF32X3) ? 4 : (KIND == KIND_I8 ? 1 : 2);
     constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;
     constexpr int KSTEPS = 4;
-    // TMEM: query pieces at column 0 (f32 256 columns, bf16 192, int8 32), accumulator ring behind them
-    constexpr int NACC = (KIND == KIND_I8) ? 3 : 2;
-    constexpr uint32_t ACC_COL0 = (KIND == KIND_I8) ? 128u : 256u;
-    constexpr uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : (KIND == KIND_I8 ? 32u : 64u);
+    // TMEM: query pieces at column 0 (f32 hi / lo 2 x 128 columns, bf16 terms 64 or 128 each, int8 codes <= 128), accumulator
+    // ring behind them: three stages when the pieces fit 128 columns, two otherwise
+    const uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : (KIND == KIND_I8 ? 128u : (p.nslab > 2u ? 128u : 64u));
+    const uint32_t q_cols = (KIND == KIND_TF32X3) ? 256u : (KIND == KIND_I8 ? 128u : p.bf16_terms * PIECE_COLS);
+    const uint32_t NACC = q_cols <= 128u ? 3u : 2u;
+    const uint32_t ACC_COL0 = q_cols <= 128u ? 128u : 256u;
     constexpr uint32_t idesc = make_idesc(KIND);
     constexpr uint32_t SLAB_DESC = SLAB_TILE >> 4;
 
@@ -80,9 +83,9 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     uint64_t* bar_empty = bars + p.n_stages;       // [n_stages]
     uint64_t* bar_xf = bars + 2 * p.n_stages;      // [n_stages] slab split into hi / lo (f32 lists)
     uint64_t* bar_q = bars + 3 * p.n_stages;       // [1]  queries of the current task are in TMEM
-    uint64_t* bar_tfull = bar_q + 1;               // [NACC]
-    uint64_t* bar_tempty = bar_tfull + NACC;       // [NACC]
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + NACC);
+    uint64_t* bar_tfull = bar_q + 1;               // [3]
+    uint64_t* bar_tempty = bar_tfull + 3;          // [3]
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 3);
     uint32_t* s_task = s_tmem + 1;                 // [4]: list, pair0, n_in_group, valid flag
     uint64_t* s_rows = reinterpret_cast<uint64_t*>(s_tmem + 6);  // [2]: r_begin, r_end (8-byte aligned: bars + ... even count)
     float* s_aux_all = reinterpret_cast<float*>(s_tail + 512);   // [8 epilogue warps][64] row constants of the warp's current half tile
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.n_stages; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); mbar_init(bar_xf + s, XF_THREADS); }
         mbar_init(bar_q, EPI_THREADS);
-        for (int a = 0; a < NACC; a++) { mbar_init(bar_tfull + a, 1); mbar_init(bar_tempty + a, EPI_THREADS); }
+        for (uint32_t a = 0; a < NACC; a++) { mbar_init(bar_tfull + a, 1); mbar_init(bar_tempty + a, EPI_THREADS); }
         fence_barrier_init();
         fence_proxy_async();
         tma_prefetch_desc(&tm_x);
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                             } else {
                                 umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
                                 umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
-                                umma_ts<KIND>(tmem_c, a0 + 2 * PIECE_COLS, xd + 2 * k, idesc, 1u);
+                                if (p.bf16_terms > 2) umma_ts<KIND>(tmem_c, a0 + 2 * PIECE_COLS, xd + 2 * k, idesc, 1u);
                             }
                         }
                         umma_commit(bar_empty + stage);
@@ -294,7 +297,8 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                         tmem_st32(tmem_base + ((quarter * 32u) << 16) + pc * PIECE_COLS + c, w);
                     };
                     for (uint32_t c = 0; c < row_words; c += 32) copy_chunk(half, c);
-                    for (uint32_t c = half * 32; c < row_words; c += 64) copy_chunk(2, c);
+                    if (p.bf16_terms > 2)
+                        for (uint32_t c = half * 32; c < row_words; c += 64) copy_chunk(2, c);
                 }
                 tmem_st_wait();
                 tc_fence_before();
@@ -410,8 +414,8 @@ int tc_ivf_prepare(annb_index* ix) {
     const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : (kind == tc::KIND_BF16 ? 2 : 1);
     const uint32_t slab_elems = tc::SLAB_BYTES / elem;
     const uint32_t kp = round_up(ix->dim, slab_elems);
-    // the query pieces live in TMEM (128 columns per f32 / int8 piece, 64 per bf16 term); larger dims stay on the CUDA-core scan
-    if (kp * elem > (kind == tc::KIND_BF16 ? 256u : 512u)) return ANNB_OK;
+    // the query pieces live in TMEM (128 columns per f32 / int8 piece, 64 or 128 per bf16 term); larger dims stay on the CUDA-core scan
+    if (kp * elem > 512u) return ANNB_OK;
     IvfTcState* st = new IvfTcState();
     ix->tc_ivf = st;
     st->kind = kind;
@@ -529,19 +533,21 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     const bool l2 = ix->metric == ANNB_L2;
     // operand pieces of the batch's queries, split once (every query is gathered once per probed list)
     const uint32_t kp_q = st->kp_elems;
+    const uint32_t bf16_terms = (ix->opt_tc_bf16_terms == 3 && kp_q <= 128) ? 3u : 2u;
     if (st->kind == tc::KIND_TF32X3) {
         ANNB_TRY(st->q_op.ensure(2ull * nq * kp_q * 4));
         tc::split_tf32_kernel<<<tc_blocks_for(nq * kp_q), 256, 0, s>>>(reinterpret_cast<const float*>(d_q), q_bytes / 4, ix->dim, nq, nq, kp_q, st->q_op.as<float>());
         ANNB_CUDA_CHECK(cudaGetLastError());
         ix->stat_launches++;
     } else if (st->kind == tc::KIND_BF16) {
+        if (bf16_terms * (kp_q > 128 ? 128u : 64u) > 256u) { set_last_error("ivf tensor path: three bf16 query terms need rows of at most 128 elements"); return ANNB_ERR_UNSUPPORTED; }
         ANNB_TRY(st->q_op.ensure(3ull * nq * kp_q * 2));
         tc::split_bf16x3_kernel<<<tc_blocks_for(nq * kp_q), 256, 0, s>>>(reinterpret_cast<const float*>(d_q), q_bytes / 4, ix->dim, nq, nq, kp_q, st->q_op.as<__nv_bfloat16>());
         ANNB_CUDA_CHECK(cudaGetLastError());
         ix->stat_launches++;
     }
     tc::IvfTcParams p{};
-    p.q_op = st->q_op.p; p.nq = nq;
+    p.q_op = st->q_op.p; p.nq = nq; p.bf16_terms = bf16_terms;
     p.queries = d_q; p.q_bytes = q_bytes; p.dim = ix->dim; p.nslab = st->nslab; p.n_stages = stages; p.n_pad = st->n_pad; p.aux = st->d_aux;
     p.offsets = ix->d_offsets; p.shard_row0 = ix->shard_row0; p.nlist = ix->nlist; p.pair_off = d_pair_off; p.task_off = d_task_off;
     p.pairs = static_cast<const uint2*>(d_pairs); p.tasks = static_cast<const uint4*>(d_tasks); p.task_counter = d_task_counter; p.probe_pitch = probe_pitch;
@@ -568,7 +574,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     r.out_ids = d_ids; r.out_dist = d_dist; r.out_counts = d_cnt;
     ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));
     ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
-    r.cert_eps = tc_cert_eps(ix, st->kind, st->kp_elems, 3, st->kind == tc::KIND_TF32X3);
+    r.cert_eps = tc_cert_eps(ix, st->kind, st->kp_elems, bf16_terms, st->kind == tc::KIND_TF32X3);
     { uint32_t b; std::memcpy(&b, &r.cert_eps, 4); ix->stat_cert_eps_bits = b; }
     r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
     int rc;

@@ -487,30 +487,96 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     }
     const uint64_t orow = p.row_map ? p.row_map[q] : q;
     const uint8_t* qv = p.queries + q * p.q_bytes;
-    // exact distance of a candidate in the reference's arithmetic
-    auto exact_of = [&](uint64_t key) -> uint64_t {
-        const uint32_t idx = key_idx(key);
-        if (idx == IDX_INVALID) return KEY_SENTINEL;
-        const uint8_t* row = p.rows + static_cast<uint64_t>(idx) * p.row_bytes;
+    // Exact distances of candidates keys[0 .. count) in the reference's arithmetic, written to exact[0 .. 64) (sentinels
+    // beyond count).  Eight threads share one candidate: thread l of a group owns SIMD lane l of the reference's 8-lane
+    // accumulation (src/utils/dist.rs:306-330, 3615-3636) -- element 8c + l of every 8-element chunk, in chunk order, with
+    // the same rounding steps -- and the group folds its eight partial sums with the reference's own horizontal-add tree
+    // (shuffles), then thread 0 appends the scalar tail and finishes.  Same bits as one thread walking the row
+    // (refdist.cuh), an eighth of the dependent chain.  16 candidates per round of the 128 threads.
+    __shared__ float s_qn;
+    __shared__ int32_t s_qs;
+    if (threadIdx.x == 96) {   // query scalars, once per CTA (a sequential fold in the reference: one thread, off the other warps' path)
+        float qn = 1.0f;
+        int32_t qs = 0;
         if constexpr (RT == 2) {
-            // SQ8: exact code-space distance (src/utils/dist.rs:5015-5077)
-            int32_t dot[1], xx, qs = 0;
-            accumulate_i8<1>(row, qv, p.q_bytes, p.dim, dot, xx);
             for (uint32_t e = 0; e < p.dim; e++) {
                 const int32_t v = reinterpret_cast<const int8_t*>(qv)[e];
                 qs += v * v;
             }
-            return make_key(finish_i8<MET>(dot[0], xx, qs, (MET == MET_COS) ? p.row_norms_i[idx] : 0), idx);
-        } else {
-            float raw[1];
-            accumulate_fp<(RT == 0) ? 4 : 2, (QT == QT_F32) ? 4 : 2, MET == MET_L2, 1>(row, qv, p.q_bytes, p.dim, raw);
-            float qn = 1.0f, xn = 1.0f;
-            if (MET == MET_COS) {
-                qn = seq_norm<(QT == QT_F32) ? 4 : 2>(qv, p.dim);
-                if (p.bf16_self) qn = round_to_bf16(qn);
-                xn = p.row_norms[idx];
+        } else if (MET == MET_COS) {
+            qn = seq_norm<(QT == QT_F32) ? 4 : 2>(qv, p.dim);
+            if (p.bf16_self) qn = round_to_bf16(qn);
+        }
+        s_qn = qn;
+        s_qs = qs;
+    }
+    __syncthreads();
+    auto exact_range = [&](uint32_t count) {
+        const uint32_t l = threadIdx.x & 7u, grp = threadIdx.x >> 3;
+        for (uint32_t base = 0; base < 64; base += 16) {
+            const uint32_t j = base + grp;
+            if (base >= count) {                       // whole round beyond the candidates (uniform over the CTA)
+                if (l == 0) exact[j] = KEY_SENTINEL;
+                continue;
             }
-            return make_key(finish_fp<MET>(raw[0], qn, xn), idx);
+            const uint64_t key = j < count ? keys[j] : KEY_SENTINEL;
+            const uint32_t idx = key_idx(key);
+            const bool live = idx != IDX_INVALID;
+            const uint8_t* row = p.rows + static_cast<uint64_t>(live ? idx : 0u) * p.row_bytes;
+            uint64_t out = KEY_SENTINEL;
+            if constexpr (RT == 2) {
+                // SQ8: exact code-space integers (src/utils/dist.rs:5015-5077); any summation order gives the same value
+                int32_t dot = 0, xx = 0;
+                for (uint32_t c = l; c < (p.dim + 15u) / 16u; c += 8) {
+                    const int4 x = *reinterpret_cast<const int4*>(row + c * 16);
+                    const int4 y = *reinterpret_cast<const int4*>(qv + c * 16);
+                    xx = __dp4a(x.x, x.x, xx); xx = __dp4a(x.y, x.y, xx); xx = __dp4a(x.z, x.z, xx); xx = __dp4a(x.w, x.w, xx);
+                    dot = __dp4a(x.x, y.x, dot); dot = __dp4a(x.y, y.y, dot); dot = __dp4a(x.z, y.z, dot); dot = __dp4a(x.w, y.w, dot);
+                }
+#pragma unroll
+                for (int off = 4; off > 0; off >>= 1) {
+                    dot += __shfl_down_sync(0xFFFFFFFFu, dot, off, 8);
+                    xx += __shfl_down_sync(0xFFFFFFFFu, xx, off, 8);
+                }
+                if (live) out = make_key(finish_i8<MET>(dot, xx, s_qs, (MET == MET_COS) ? p.row_norms_i[idx] : 0), idx);
+            } else {
+                constexpr int RELEM = (RT == 0) ? 4 : 2, QELEM = (QT == QT_F32) ? 4 : 2;
+                constexpr bool FMA = (RELEM == 2);
+                const uint32_t chunks = p.dim >> 3;
+                float acc = 0.0f;
+                for (uint32_t c = 0; c < chunks; c++) {
+                    const float x = load1<RELEM>(row, c * 8 + l), y = load1<QELEM>(qv, c * 8 + l);
+                    if (MET == MET_L2) {
+                        const float d = __fsub_rn(x, y);
+                        acc = FMA ? __fmaf_rn(d, d, acc) : __fadd_rn(acc, __fmul_rn(d, d));
+                    } else {
+                        acc = FMA ? __fmaf_rn(x, y, acc) : __fadd_rn(acc, __fmul_rn(x, y));
+                    }
+                }
+                // s_l = a_l + a_(l+4);  wide: (s0 + s2) + (s1 + s3);  hsum_f32_avx2: (s0 + s1) + (s2 + s3)
+                const float s4 = __fadd_rn(acc, __shfl_down_sync(0xFFFFFFFFu, acc, 4, 8));
+                float sum;
+                if (FMA) {
+                    const float u = __fadd_rn(s4, __shfl_down_sync(0xFFFFFFFFu, s4, 1, 8));
+                    sum = __fadd_rn(u, __shfl_down_sync(0xFFFFFFFFu, u, 2, 8));
+                } else {
+                    const float t = __fadd_rn(s4, __shfl_down_sync(0xFFFFFFFFu, s4, 2, 8));
+                    sum = __fadd_rn(t, __shfl_down_sync(0xFFFFFFFFu, t, 1, 8));
+                }
+                if (l == 0 && live) {
+                    for (uint32_t e = chunks * 8; e < p.dim; e++) {   // scalar tail: `sum += d * d` (not fused)
+                        const float x = load1<RELEM>(row, e), y = load1<QELEM>(qv, e);
+                        if (MET == MET_L2) {
+                            const float d = __fsub_rn(x, y);
+                            sum = __fadd_rn(sum, __fmul_rn(d, d));
+                        } else {
+                            sum = __fadd_rn(sum, __fmul_rn(x, y));
+                        }
+                    }
+                    out = make_key(finish_fp<MET>(sum, s_qn, (MET == MET_COS) ? p.row_norms[idx] : 1.0f), idx);
+                }
+            }
+            if (l == 0) exact[j] = out;
         }
     };
     // coverage test: every row that was not re-ranked has an approximate value >= a_thr; is the k-th exact distance safely
@@ -531,15 +597,11 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         // approx value = -q.x / |x| = (dist - 1) * |q| with the reference's own |q| (sequential fold, bf16-rounded for
         // bf16 self queries; sqrt of the integer norm for SQ8) ; error <= eps
         double qn = sqrt(qn2);
-        if constexpr (QT != QT_I8) {
-            float qf = seq_norm<(QT == QT_F32) ? 4 : 2>(qv, p.dim);
-            if (p.bf16_self) qf = round_to_bf16(qf);
-            qn = static_cast<double>(qf);
-        }
+        if constexpr (QT != QT_I8) qn = static_cast<double>(s_qn);
         return qn > 0.0 ? ((static_cast<double>(a_thr) / qn + 1.0 - static_cast<double>(p.cert_eps)) > static_cast<double>(dk)) : true;
     };
     __shared__ int s_extend;
-    if (threadIdx.x < 64) exact[threadIdx.x] = (threadIdx.x < p.kp) ? exact_of(keys[threadIdx.x]) : KEY_SENTINEL;
+    exact_range(p.kp);
     if (threadIdx.x == 0) s_extend = 0;
     __syncthreads();
     if (threadIdx.x < 32) bitonic_sort_keys<false>(exact, 64, threadIdx.x, 32);
@@ -558,7 +620,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     }
     __syncthreads();
     if (s_extend) {
-        if (threadIdx.x < 64) exact[threadIdx.x] = (threadIdx.x < n_cand) ? exact_of(keys[threadIdx.x]) : KEY_SENTINEL;
+        exact_range(min(n_cand, 64u));
         __syncthreads();
         if (threadIdx.x < 32) bitonic_sort_keys<false>(exact, 64, threadIdx.x, 32);
         __syncthreads();

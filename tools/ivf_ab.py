@@ -22,6 +22,11 @@ for name in dts:
     dt = {"f32": annb200.F32, "bf16": annb200.BF16, "sq8": annb200.SQ8}[name]
     parts = gs.build_ivf_parts_gpu(data, nlist, dt, 0, seed=42, kmeans_iters=8)
     ix = gs.ivf_handle_from_parts(parts, n, dim, dt, annb200.L2, 0)
+    for kv in os.environ.get("ANNB_AB_FIXED", "").split(","):      # options held fixed during the A/B, e.g. ivf_list_major=0
+        if kv:
+            ix.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+    ix.query_batch(q.cpu().numpy(), k, nprobe=nprobe)              # host-buffer call: fills the probe statistics
+    scanned_bytes = ix.get_stat("scanned_vectors") * dim * {"f32": 4, "bf16": 2, "sq8": 1}[name]
     ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
     ref = None
     for rep in range(2):
@@ -43,7 +48,8 @@ for name in dts:
             same = True if ref is None else bool((ids == ref).all())
             if ref is None:
                 ref = ids.clone()
-            print(f"{name} {opt} {flags} rep {rep} step_ms {ms:.3f} scan_ms {kern:.3f} qps {nq / ms * 1e3:.0f} ids_equal {same}", flush=True)
+            print(f"{name} {opt} {flags} rep {rep} nq {nq} step_ms {ms:.3f} scan_ms {kern:.3f} qps {nq / ms * 1e3:.0f} ids_equal {same} "
+                  f"algorithmic_GBs {scanned_bytes / (kern * 1e-3) / 1e9:.0f} path {ix.get_stat('last_path')} fallback_total {ix.get_stat('fallback_queries')}", flush=True)
     ix.close()
     del parts
     torch.cuda.empty_cache()
