@@ -559,11 +559,11 @@ static int ivf_enqueue(annb_index* ix, const PreparedQueries& pq, uint64_t nq, u
     }
     ix->stat_last_path = ANNB_PATH_SIMT;
     // warps wanted per query so that a small batch still fills the machine (148 SMs x 32 warps)
-    const uint64_t want = std::max<uint64_t>(1, std::min<uint64_t>(256, ceil_div<uint64_t>(148ull * 32, std::max<uint64_t>(nq, 1))));
+    const uint64_t want = std::max<uint64_t>(1, std::min<uint64_t>(1024, ceil_div<uint64_t>(148ull * 32, std::max<uint64_t>(nq, 1))));
     uint32_t parts = ix->opt_scan_parts > 0 ? static_cast<uint32_t>(ix->opt_scan_parts) : static_cast<uint32_t>(std::min<uint64_t>(want, 32));
     parts = std::max(1u, std::min(parts, np));
     // very small batches (the tensor path's exact fallback): also cut every list into row segments
-    uint32_t subs = ix->opt_scan_parts > 0 ? 1u : static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(16, want / parts)));
+    uint32_t subs = ix->opt_scan_parts > 0 ? 1u : static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(32, want / parts)));
     while (subs > 1 && static_cast<uint64_t>(parts) * subs * kk * 8 > 128 * 1024) subs--;
     const uint32_t nsort = WarpSelect::sort_size(kk);
     ANNB_TRY(ix->s_keys.ensure(nq * parts * subs * static_cast<uint64_t>(kk) * 8));

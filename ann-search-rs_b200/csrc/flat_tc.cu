@@ -803,6 +803,16 @@ float tc_cert_eps(const annb_index* ix, int kind, uint32_t kp_elems, uint32_t te
     return static_cast<float>(eps);
 }
 
+// bf16 terms of an f32 query against a BF16 index.  Two terms leave a residual of 2^-16 |q|: the certificate then needs the
+// k-th neighbour to lie ~1e-5 (|q| + |x|max)^2 below the pruning threshold.  Cosine distances of a BF16 index are spread by
+// the index's own rounding (the reference divides by the norm of the UN-rounded row), two terms certify there; squared
+// distances of close neighbours are not (measured on the bench data, tools/gap_stats.py: a quarter of the queries would
+// go to the exact fallback), so L2 keeps three terms unless the caller insists.
+uint32_t tc_bf16_terms(const annb_index* ix) {
+    if (ix->opt_tc_bf16_terms == 2 || ix->opt_tc_bf16_terms == 3) return static_cast<uint32_t>(ix->opt_tc_bf16_terms);
+    return ix->metric == ANNB_COSINE ? 2u : 3u;
+}
+
 static uint32_t pick_kprime(const annb_index* ix, uint32_t k_eff) {
     if (ix->opt_tc_candidates == 16 || ix->opt_tc_candidates == 32) return std::max<uint32_t>(ix->opt_tc_candidates, k_eff <= 16 ? 16 : 32);
     return k_eff <= 10 ? 16 : 32;
@@ -866,8 +876,8 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     const uint32_t kp = st->kp_elems;
     const uint32_t kprime = pick_kprime(ix, k_eff);
     const uint32_t nq_pad = static_cast<uint32_t>(round_up<uint64_t>(nq, tc::BM));
-    // f32 queries against a BF16 index go in as two (default) or three bf16 terms q0 + q1 [+ q2]: 16 instead of 24 MMAs per tile
-    const uint32_t bf16_terms = ix->opt_tc_bf16_terms == 3 ? 3u : 2u;
+    // f32 queries against a BF16 index go in as two or three bf16 terms q0 + q1 [+ q2]: 16 or 24 MMAs per tile
+    const uint32_t bf16_terms = tc_bf16_terms(ix);
     const uint32_t na = kind == tc::KIND_TF32X3 ? 2 : ((qt == QT_BF16 || kind == tc::KIND_I8) ? 1 : bf16_terms);
 
     // ---- query operand: stacked pieces, zero padded ----

@@ -17,6 +17,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
                    uint32_t k_out, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s);
 void tc_destroy(annb_index* ix);
 // Error bound the coverage certificates assume for the pre-selection values of a (kind, padded K, query terms) kernel.
+uint32_t tc_bf16_terms(const annb_index* ix);
 float tc_cert_eps(const annb_index* ix, int kind, uint32_t kp_elems, uint32_t terms, bool inkernel_split);
 
 // Tensor-core IVF list scan (ivf_tc.cu): operand copies in list order, grouped (list x 128 queries) tasks, exact re-rank.

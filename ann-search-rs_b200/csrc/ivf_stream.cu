@@ -4,8 +4,9 @@
 //
 // One warp = one (query, part [, list segment]) and walks its probed lists in 32-row tiles.  The tiles do not go through
 // per-lane cp.async: lane 0 of every warp drives a private ring of TMA tile loads (cp.async.bulk.tensor.2d, one 128-byte
-// K slab x 32 rows per load, SWIZZLE_128B, completion on an mbarrier), 3 to 8 tiles deep, so every warp keeps 32-48 KB in
-// flight and the SM's four warps together cover the HBM latency without any occupancy games.  The 128-byte swizzle makes the
+// K slab x 32 rows per load, SWIZZLE_128B, completion on an mbarrier), three or four tiles deep: two tiles per warp are in
+// flight while one is scored, and the SM's resident warps (4 for f32 rows of 128, 8 for bf16, 12 for SQ8 -- the ring is the
+// only large shared-memory user) together keep well over the HBM latency-bandwidth product in flight.  The 128-byte swizzle makes the
 // lane-per-row reads conflict-free (lane r reads 16-byte chunk j of its row at position j ^ (r & 7) of the slab row), and
 // TMA zero-fills rows past the end of the index.  Rows of the box that belong to the next list are loaded and ignored.
 // Arithmetic: refdist.cuh's reference order (8 lane accumulators over consecutive chunks, the reference's reduce tree,
@@ -193,6 +194,7 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32) ivf_stream_kernel(const __g
             // SQ8: exact code-space integers (src/utils/dist.rs:5015-5077), whole 16-code chunks through dp4a
             int32_t dot = 0, xx = 0;
             const uint32_t chunks = (p.dim + 15u) >> 4;
+#pragma unroll 4
             for (uint32_t c = 0; c < chunks; c++) {
                 const int4 x = *reinterpret_cast<const int4*>(swz(tile, lane, c));
                 const int4 y = *reinterpret_cast<const int4*>(s_q + c * 16);
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(STREAM_WARPS * 32) ivf_stream_kernel(const __g
 #pragma unroll
             for (int j = 0; j < 8; j++) acc[j] = 0.0f;
             const uint32_t chunks = p.dim >> 3;
+#pragma unroll 4
             for (uint32_t c = 0; c < chunks; c++) {
                 float x[8], y[8];
                 load8_swz<RELEM>(tile, lane, c, x);
@@ -302,9 +305,11 @@ int tc_stream_scan(annb_index* ix, const StreamScanArgs& a, cudaStream_t s) {
     p.nslab = st->nslab;
     const size_t tile = static_cast<size_t>(st->nslab) * tc::STREAM_SLAB;
     const size_t per_warp_tail = 64 + a.q_bytes + static_cast<size_t>(a.nsort) * 8;
-    // ring depth: up to 48 KiB of tiles per warp (f32 d = 128: 3 tiles of 16 KiB; bf16: 6; SQ8: 8), at least 2
+    // ring depth: three tiles per warp (four for the 4 KiB tiles of narrow rows).  Bytes in flight come from the number of
+    // resident warps, not from deep rings: f32 d = 128 -> 48 KiB per warp, one CTA per SM (already HBM-bound); bf16 -> 24 KiB,
+    // two CTAs; SQ8 -> 16 KiB, three CTAs -- the narrower the rows, the more warps hide the per-tile latencies.
     const size_t budget = 220 * 1024;
-    size_t stages = std::min<size_t>(8, (48 * 1024) / tile);
+    size_t stages = tile <= 4096 ? 4 : 3;
     while (stages > 2 && tc::STREAM_WARPS * (stages * tile + per_warp_tail) > budget) stages--;
     if (stages < 2 || tc::STREAM_WARPS * (stages * tile + per_warp_tail) > budget) { set_last_error("streaming scan: rows too wide for the tile ring"); return ANNB_ERR_UNSUPPORTED; }
     p.n_stages = static_cast<uint32_t>(stages);

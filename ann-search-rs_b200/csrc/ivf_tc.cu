@@ -533,7 +533,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     const bool l2 = ix->metric == ANNB_L2;
     // operand pieces of the batch's queries, split once (every query is gathered once per probed list)
     const uint32_t kp_q = st->kp_elems;
-    const uint32_t bf16_terms = (ix->opt_tc_bf16_terms == 3 && kp_q <= 128) ? 3u : 2u;
+    const uint32_t bf16_terms = kp_q <= 128 ? tc_bf16_terms(ix) : 2u;   // three terms need rows of at most 128 elements (TMEM columns)
     if (st->kind == tc::KIND_TF32X3) {
         ANNB_TRY(st->q_op.ensure(2ull * nq * kp_q * 4));
         tc::split_tf32_kernel<<<tc_blocks_for(nq * kp_q), 256, 0, s>>>(reinterpret_cast<const float*>(d_q), q_bytes / 4, ix->dim, nq, nq, kp_q, st->q_op.as<float>());
