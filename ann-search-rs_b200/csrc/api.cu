@@ -727,6 +727,22 @@ static int search_host(annb_index* ix, bool ivf, int mode, const float* queries,
                 if (out_dist) std::memcpy(out_dist + oid[i] * k, dist.data() + i * k, k * 4ull);
                 if (out_counts) out_counts[oid[i]] = cnt[i];
             }
+        } else if (!ivf && mode == 1 && scatter == 2) {
+            // kNN-graph rows: the batch was searched with k = graph degree + 1; drop every row's own id on the device
+            const uint32_t kg = k - 1;
+            ANNB_TRY(ix->s_route.ensure(nb * kg * 8ull));
+            ANNB_TRY(ix->s_qcodes.ensure(nb * kg * 4ull));
+            auto copy_out = [&]() -> int {
+                knn_graph_rows_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nb, 128)), 128, 0, s>>>(ix->s_ids.as<uint64_t>(), ix->s_dist.as<float>(), nb, k,
+                                                                                                   ix->id_base + pos_begin + b0, ix->s_route.as<uint64_t>(),
+                                                                                                   ix->s_qcodes.as<float>(), ix->s_cnt.as<uint32_t>());
+                ANNB_CUDA_CHECK(cudaGetLastError());
+                ANNB_CUDA_CHECK(cudaMemcpyAsync(out_ids + b0 * kg, ix->s_route.p, nb * kg * 8ull, cudaMemcpyDefault, s));
+                ANNB_CUDA_CHECK(cudaMemcpyAsync(out_dist + b0 * kg, ix->s_qcodes.p, nb * kg * 4ull, cudaMemcpyDefault, s));
+                if (out_counts) ANNB_CUDA_CHECK(cudaMemcpyAsync(out_counts + b0, ix->s_cnt.p, nb * 4ull, cudaMemcpyDefault, s));
+                return ANNB_OK;
+            };
+            ANNB_TRY(run_batch(ix, ivf, pq, nb, k, nprobe, ix->s_ids.as<uint64_t>(), ix->s_dist.as<float>(), ix->s_cnt.as<uint32_t>(), s, true, copy_out));
         } else {
             auto copy_out = [&]() -> int {
                 ANNB_CUDA_CHECK(cudaMemcpyAsync(out_ids + b0 * k, ix->s_ids.p, nb * k * 8ull, cudaMemcpyDefault, s));
@@ -1020,6 +1036,33 @@ int annb_flat_search_self(const annb_index* index, uint64_t row_begin, uint64_t 
     return search_host(const_cast<annb_index*>(index), false, 1, nullptr, row_begin, row_end - row_begin, k, 0, 0, out_ids, out_dist, out_counts);
 }
 
+int annb_flat_knn_graph(const annb_index* index, uint64_t row_begin, uint64_t row_end, uint32_t k, uint64_t* out_pid, float* out_dist, uint32_t* out_counts) {
+    if (!index) return fail(ANNB_ERR_INVALID_ARGUMENT, "null index");
+    if (index->is_ivf) return fail(ANNB_ERR_INVALID_ARGUMENT, "not a flat index");
+    if (!out_pid || !out_dist || k == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / k == 0");
+    if (row_begin > row_end || row_end > index->n) return fail(ANNB_ERR_INVALID_ARGUMENT, "row range outside the index");
+    if (index->dtype != ANNB_F32) return fail(ANNB_ERR_UNSUPPORTED, "the kNN-graph hand-off is defined for f32 indices (KnnGraphGpu<T> carries the vectors themselves)");
+    const uint64_t nq = row_end - row_begin;
+    if (!index->multi) return search_host(const_cast<annb_index*>(index), false, 1, nullptr, row_begin, nq, k + 1, 0, 2, out_pid, out_dist, out_counts);
+    // multi-device handle: the merged [nq][k + 1] rows arrive on the host; the (cheap, integer) self filter runs here
+    std::vector<uint64_t> ids(nq * (k + 1ull));
+    std::vector<float> dist(nq * (k + 1ull));
+    ANNB_TRY(multi_search(const_cast<annb_index*>(index), false, 1, nullptr, row_begin, nq, k + 1, 0, ids.data(), dist.data(), nullptr));
+    for (uint64_t q = 0; q < nq; q++) {
+        uint32_t w = 0;
+        for (uint32_t j = 0; j <= k && w < k; j++) {
+            const uint64_t id = ids[q * (k + 1ull) + j];
+            if (id == 0xFFFFFFFFFFFFFFFFull || id == row_begin + q) continue;
+            out_pid[q * k + w] = id;
+            out_dist[q * k + w] = dist[q * (k + 1ull) + j];
+            w++;
+        }
+        if (out_counts) out_counts[q] = w;
+        for (; w < k; w++) { out_pid[q * k + w] = 0x7FFFFFFFull; out_dist[q * k + w] = 3.402823466e+38f; }
+    }
+    return ANNB_OK;
+}
+
 int annb_flat_search_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k,
                          uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, void* stream) {
     annb_index* ix = const_cast<annb_index*>(index);
@@ -1136,8 +1179,25 @@ int annb_ivf_assign(const float* data, uint64_t n, uint32_t dim, const float* ce
  * and were redone on the exact kernel (0 when the call ran on the exact kernel throughout). */
 uint64_t annb_assign_last_redone(void) { return g_assign_redone; }
 
+// centroid c <- (centroid c * w + data row j) / (w + 1), separate multiply / add / divide as the reference's f32 loop
+// (adjust_centers, src/utils/k_means_utils.rs:1020-1025); one block per moved centroid
+static __global__ void kmeans_adjust_kernel(const uint32_t* __restrict__ moves, float* __restrict__ cent, uint32_t ld, uint32_t dim, const float* __restrict__ x) {
+    const uint32_t c = moves[3 * blockIdx.x], j = moves[3 * blockIdx.x + 1];
+    const float w = static_cast<float>(moves[3 * blockIdx.x + 2]);
+    const float denom = __fadd_rn(w, 1.0f);
+    for (uint32_t d = threadIdx.x; d < dim; d += blockDim.x) {
+        float* cc = cent + static_cast<uint64_t>(c) * ld + d;
+        *cc = __fdiv_rn(__fadd_rn(__fmul_rn(*cc, w), x[static_cast<uint64_t>(j) * ld + d]), denom);
+    }
+}
+
 int annb_kmeans_lloyd(const float* data, uint64_t n, uint32_t dim, float* centroids, uint32_t nlist, int metric, uint32_t max_iters,
                       uint32_t* out_iters, int device) {
+    return annb_kmeans_lloyd_balanced(data, n, dim, centroids, nlist, metric, max_iters, 0, 0, out_iters, nullptr, device);
+}
+
+int annb_kmeans_lloyd_balanced(const float* data, uint64_t n, uint32_t dim, float* centroids, uint32_t nlist, int metric, uint32_t max_iters,
+                               int balanced, uint64_t seed, uint32_t* out_iters, uint64_t* out_adjusted, int device) {
     if (metric == ANNB_MANHATTAN) return fail(ANNB_ERR_DISTANCE_NOT_SUPPORTED, "Manhattan distance is not supported");
     if (metric != ANNB_L2 && metric != ANNB_COSINE) return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown metric");
     if (!data || !centroids || n == 0 || dim == 0 || nlist == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "empty input");
@@ -1173,6 +1233,13 @@ int annb_kmeans_lloyd(const float* data, uint64_t n, uint32_t dim, float* centro
     struct FreeTc { TcAssignState*& p; ~FreeTc() { tc_assign_destroy(p); } } ftc{tcs};
     if (assign_tensor_enabled() && n >= 4096) ANNB_TRY(tc_assign_create(&tcs, dim, nlist));
     AssignScratch sc;
+    // balancing (adjust_centers): the donor walk is a short serial pass over the assignments -- it runs on the host between
+    // two device steps; the centroid moves themselves happen on the device
+    std::vector<uint32_t> h_assign, h_cnt, h_moves;
+    DevBuf d_moves;
+    struct RelMoves { DevBuf& b; ~RelMoves() { b.release(); } } rel_moves{d_moves};
+    uint64_t last_adjusted = 0, total_adjusted = 0;
+    if (n >= 0xFFFFFFFFull) return fail(ANNB_ERR_UNSUPPORTED, "n must be < 2^32 - 1");
     uint32_t it = 0;
     for (; it < max_iters; it++) {
         // assignment: direct_assign arithmetic (k_means_utils.rs:2119-2195) on the current centroids
@@ -1190,16 +1257,48 @@ int annb_kmeans_lloyd(const float* data, uint64_t n, uint32_t dim, float* centro
         kmeans_changed_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(n, 256)), 256>>>(d_a, d_prev, n, d_changed);
         unsigned long long changed = 0;
         ANNB_CUDA_CHECK(cudaMemcpy(&changed, d_changed, 8, cudaMemcpyDeviceToHost));
-        if (changed <= change_floor) break;
+        if (changed <= change_floor && last_adjusted == 0) break;   // (the reference stays in until balancing has nothing left to do, :1618)
         ANNB_CUDA_CHECK(cudaMemset(d_sums, 0, static_cast<size_t>(nlist) * dim * 8));
         ANNB_CUDA_CHECK(cudaMemset(d_cnt, 0, nlist * 4ull));
         kmeans_accumulate_kernel<<<grid_for(n * dim, 256, 148u * 32u), 256>>>(d_x, ld, dim, n, d_a, d_sums, d_cnt);
         kmeans_update_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(static_cast<uint64_t>(nlist) * dim, 256)), 256>>>(d_sums, d_cnt, d_c, ld, dim, nlist);
         ANNB_CUDA_CHECK(cudaGetLastError());
+        if (balanced) {
+            // adjust_centers(seed + iter) (src/utils/k_means_utils.rs:979-1030, hook at :1668-1682)
+            h_assign.resize(n);
+            h_cnt.resize(nlist);
+            ANNB_CUDA_CHECK(cudaMemcpy(h_assign.data(), d_a, n * 4ull, cudaMemcpyDeviceToHost));
+            ANNB_CUDA_CHECK(cudaMemcpy(h_cnt.data(), d_cnt, nlist * 4ull, cudaMemcpyDeviceToHost));
+            h_moves.clear();
+            const double average = static_cast<double>(n) / static_cast<double>(nlist), floor_ = average * 0.25;
+            uint64_t cursor = (seed + it) % n;
+            for (uint32_t c = 0; c < nlist; c++) {
+                if (static_cast<double>(h_cnt[c]) > floor_) continue;
+                int64_t donor = -1;
+                for (uint64_t t = 0; t < n; t++) {
+                    cursor = (cursor + 715827883ull) % n;
+                    const uint32_t owner = h_assign[cursor];
+                    if (owner != c && static_cast<double>(h_cnt[owner]) > average) { donor = static_cast<int64_t>(cursor); break; }
+                }
+                if (donor < 0) continue;
+                h_moves.push_back(c);
+                h_moves.push_back(static_cast<uint32_t>(donor));
+                h_moves.push_back(std::min<uint32_t>(h_cnt[c], 5u));
+            }
+            last_adjusted = h_moves.size() / 3;
+            total_adjusted += last_adjusted;
+            if (last_adjusted) {
+                ANNB_TRY(d_moves.ensure(h_moves.size() * 4ull));
+                ANNB_CUDA_CHECK(cudaMemcpy(d_moves.p, h_moves.data(), h_moves.size() * 4ull, cudaMemcpyHostToDevice));
+                kmeans_adjust_kernel<<<static_cast<uint32_t>(last_adjusted), 128>>>(d_moves.as<uint32_t>(), d_c, ld, dim, d_x);
+                ANNB_CUDA_CHECK(cudaGetLastError());
+            }
+        }
     }
     ANNB_CUDA_CHECK(cudaMemcpy2D(centroids, dim * 4ull, d_c, ld * 4ull, dim * 4ull, nlist, cudaMemcpyDefault));
     g_assign_redone = sc.redone;
     if (out_iters) *out_iters = it;
+    if (out_adjusted) *out_adjusted = total_adjusted;
     return ANNB_OK;
 }
 

@@ -227,4 +227,28 @@ __global__ void seq_norms_kernel(const float* __restrict__ rows, uint32_t ld, ui
     out[i] = seq_norm<4>(reinterpret_cast<const uint8_t*>(rows + i * ld), dim);
 }
 
+// kNN-graph rows from self-search rows (KnnGraphGpu, src/gpu/nndescent_gpu.rs:2418-2446, 2611-2667): row i of the
+// [nq][k + 1] search result loses its own id (wherever it sits -- exact duplicates may precede it) and keeps the first k
+// survivors, ascending by distance; unfilled slots carry the reference's sentinel pair (SENTINEL_PID = u32::MAX >> 1, T::MAX).
+__global__ void knn_graph_rows_kernel(const uint64_t* __restrict__ ids, const float* __restrict__ dist, uint64_t nq, uint32_t k1, uint64_t self0,
+                                      uint64_t* __restrict__ out_ids, float* __restrict__ out_dist, uint32_t* __restrict__ out_cnt) {
+    const uint64_t q = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (q >= nq) return;
+    const uint32_t k = k1 - 1;
+    const uint64_t self = self0 + q;
+    uint32_t w = 0;
+    for (uint32_t j = 0; j < k1 && w < k; j++) {
+        const uint64_t id = ids[q * k1 + j];
+        if (id == 0xFFFFFFFFFFFFFFFFull || id == self) continue;
+        out_ids[q * k + w] = id;
+        out_dist[q * k + w] = dist[q * k1 + j];
+        w++;
+    }
+    if (out_cnt) out_cnt[q] = w;
+    for (; w < k; w++) {
+        out_ids[q * k + w] = 0x7FFFFFFFull;
+        out_dist[q * k + w] = 3.402823466e+38f;
+    }
+}
+
 }  // namespace annb

@@ -77,6 +77,7 @@ def lib():
         _lib.annb_flat_search_dev.argtypes = [vp, vp, u64, u32, u32, vp, vp, vp, vp]
         _lib.annb_ivf_assign.argtypes = [vp, u64, u32, vp, vp, u32, i32, vp, i32]
         _lib.annb_kmeans_lloyd.argtypes = [vp, u64, u32, vp, u32, i32, u32, vp, i32]
+        _lib.annb_kmeans_lloyd_balanced.argtypes = [vp, u64, u32, vp, u32, i32, u32, i32, u64, vp, vp, i32]
         _lib.annb_ivf_route_dev.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, u32, vp]
         _lib.annb_ivf_search_probes_dev.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, u32, vp, vp, vp, vp]
         _lib.annb_ivf_create.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, vp, u32, u32, i32]
@@ -84,6 +85,7 @@ def lib():
         _lib.annb_ivf_search_self.argtypes = [vp, u64, u64, u32, u32, i32, vp, vp, vp]
         _lib.annb_ivf_search_dev.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, vp, vp]
         _lib.annb_merge_topk_dev.argtypes = [vp, vp, u32, u64, u32, vp, vp, vp, vp]
+        _lib.annb_flat_knn_graph.argtypes = [vp, u64, u64, u32, vp, vp, vp]
         _lib.annb_merge_shards_dev.argtypes = [vp, u64, u64, u32, u64, u32, vp, vp, vp, vp]
         _lib.annb_flat_create_multi.argtypes = [C.POINTER(vp), vp, u64, u32, i32, i32, vp, i32]
         _lib.annb_ivf_create_multi.argtypes = [C.POINTER(vp), vp, vp, vp, vp, vp, vp, u64, u32, u32, i32, i32, vp, vp, i32]
@@ -261,6 +263,18 @@ class ExhaustiveIndexB200(_IndexBase):
         return ids.view(np.int64), dist, cnt
 
 
+    def knn_graph(self, k: int, row_begin: int = 0, row_end: Optional[int] = None):
+        """annb_flat_knn_graph: (pid [rows, k] int64, dist [rows, k] float32, counts [rows]) -- every row's k nearest OTHER
+        rows, ascending, padded with (SENTINEL_PID, f32::MAX)."""
+        row_end = self.n if row_end is None else row_end
+        nq = row_end - row_begin
+        pid = np.empty((nq, k), dtype=np.uint64)
+        dist = np.empty((nq, k), dtype=np.float32)
+        cnt = np.empty(nq, dtype=np.uint32)
+        _check(lib().annb_flat_knn_graph(self._h, row_begin, row_end, k, _ptr(pid), _ptr(dist), _ptr(cnt)))
+        return pid.view(np.int64), dist, cnt
+
+
 class IvfIndexB200(_IndexBase):
     """Resident IVF index: IvfIndexGpu (src/gpu/ivf_gpu.rs:153-181) and its BF16 / SQ8 twins."""
 
@@ -407,6 +421,56 @@ query_exhaustive_sq8_index = query_exhaustive_index_gpu        # src/lib.rs:1818
 query_exhaustive_sq8_self = query_exhaustive_index_gpu_self    # src/lib.rs:1847-1871
 
 
+SENTINEL_PID = (2 ** 32 - 1) >> 1          # src/utils/nndescent_utils.rs:25
+
+
+class KnnGraphGpu:
+    """Mirror of KnnGraphGpu<T> (src/gpu/nndescent_gpu.rs:2418-2446), the hand-off struct between the GPU kNN-graph
+    builders and their consumers (build_nsg_from_gpu_knn, src/lib.rs:3330-3345; raw kNN extraction).  Same fields; the
+    flat `Vec<(usize, T)>` graph is kept as two [n, k] arrays (`pid`, `dist`), `knn_graph` yields the reference's pairs."""
+
+    def __init__(self, vectors_flat, dim, n, k, norms, metric, pid, dist, converged=True):
+        self.vectors_flat, self.dim, self.n, self.k = vectors_flat, dim, n, k
+        self.norms, self.metric, self.pid, self.dist, self.converged = norms, metric, pid, dist, converged
+
+    @property
+    def knn_graph(self):
+        return list(zip(self.pid.reshape(-1).tolist(), self.dist.reshape(-1).tolist()))
+
+    def check_contract(self):
+        """What NsgIndex::build_from_knn (src/cpu/nsg.rs:744-775) relies on: n * k entries, rows ascending by distance,
+        no self edge, ids < n or the sentinel, sentinels (and only sentinels) at the tail with T::MAX distances."""
+        pid, dist = self.pid, self.dist
+        assert pid.shape == (self.n, self.k) and dist.shape == (self.n, self.k)
+        real = pid != SENTINEL_PID
+        assert ((pid < self.n) | ~real).all() and (pid >= 0).all()
+        assert (pid != np.arange(self.n)[:, None]).all(), "self edge"
+        assert (real[:, :-1] | ~real[:, 1:]).all(), "sentinels must be trailing"
+        assert (dist[~real] == np.finfo(np.float32).max).all()
+        assert (np.diff(dist, axis=1) >= 0).all(), "rows must ascend by distance"
+        return True
+
+
+def build_knn_graph_gpu(mat, dist_metric: str = "euclidean", k: Optional[int] = None, build_k=None, max_iters=None, n_trees=None, delta=None,
+                        rho=None, refine_knn=None, seed: int = 42, verbose: bool = False, device=0) -> KnnGraphGpu:
+    """src/lib.rs:3201-3228 with the graph computed exactly: the exhaustive self search of the flat index (BASELINE
+    configs[4]) instead of NN-Descent, so the NN-Descent tuning arguments are accepted and ignored and `converged` is
+    always true.  `k` defaults to 30 as in the reference.  `device`: an ordinal or a list of ordinals."""
+    metric = _metric_or_default(dist_metric)
+    if metric == MANHATTAN:
+        raise AnnSearchError(-2, "Manhattan distance is not supported by the GPU kNN-graph builder")
+    x = _as_rowmajor_f32(mat)
+    n, dim = x.shape
+    k = 30 if k is None else int(k)
+    ix = ExhaustiveIndexB200.new(x, metric, F32, device)
+    try:
+        pid, dist, _ = ix.knn_graph(k)
+    finally:
+        ix.close()
+    norms = ref_row_norms(x) if metric == COSINE else np.zeros(0, dtype=np.float32)
+    return KnnGraphGpu(x.reshape(-1), dim, n, k, norms, metric, pid, dist, True)
+
+
 def ref_row_norms(x: np.ndarray) -> np.ndarray:
     """calculate_l2_norm per row in the AVX2 lane order (src/utils/dist.rs:2339-2360): 8 lane accumulators over
     8-element chunks (separate multiply and add), wide's reduce_add tree, sequential tail, sqrt."""
@@ -441,28 +505,116 @@ def normalise_rows(x: np.ndarray) -> np.ndarray:
     return np.where((nrm > 0)[:, None], x / safe[:, None], x).astype(np.float32)
 
 
-def kmeans_lloyd(train: np.ndarray, init_centroids: np.ndarray, metric: int, max_iters: int = 30, device: int = 0) -> Tuple[np.ndarray, int]:
-    """Lloyd iterations of train_centroids on the device (annb_kmeans_lloyd): unbalanced parallel_lloyd
-    (src/utils/k_means_utils.rs:1572-1700) from the given initial centroids.  Returns (centroids, updates done)."""
+def kmeans_lloyd(train: np.ndarray, init_centroids: np.ndarray, metric: int, max_iters: int = 30, device: int = 0, balanced: bool = False,
+                 seed: int = 42, return_moves: bool = False):
+    """Lloyd iterations of train_centroids on the device (annb_kmeans_lloyd[_balanced]): parallel_lloyd
+    (src/utils/k_means_utils.rs:1572-1700) from the given initial centroids, optionally with the balancing hook
+    (adjust_centers, :979-1030).  Returns (centroids, updates done[, centroid moves])."""
     train = _as_rowmajor_f32(train)
     cent = _as_rowmajor_f32(init_centroids).copy()
     if train.shape[1] != cent.shape[1]:
         raise AnnSearchError(-1, f"training data has dim {train.shape[1]}, centroids {cent.shape[1]}")
     it = C.c_uint32(0)
-    _check(lib().annb_kmeans_lloyd(_ptr(train), train.shape[0], train.shape[1], _ptr(cent), cent.shape[0], metric, max_iters, C.byref(it), device))
-    return cent, int(it.value)
+    moves = C.c_uint64(0)
+    _check(lib().annb_kmeans_lloyd_balanced(_ptr(train), train.shape[0], train.shape[1], _ptr(cent), cent.shape[0], metric, max_iters,
+                                            1 if balanced else 0, seed, C.byref(it), C.byref(moves), device))
+    return (cent, int(it.value), int(moves.value)) if return_moves else (cent, int(it.value))
 
 
-def train_centroids_lloyd(train: np.ndarray, nlist: int, metric: int, iters: int = 30, device: int = 0) -> np.ndarray:
-    """Centroid trainer of the build_* mirrors: device Lloyd (annb_kmeans_lloyd) from evenly spaced training rows.
-    The reference's train_centroids (src/utils/k_means_utils.rs:2771-2938) seeds with rand's StdRng
-    (fast_random_init / k-means||), which cannot be reproduced here; the Lloyd loop itself is the restated one."""
+def _ref_euclid_rows(x: np.ndarray, c: np.ndarray) -> np.ndarray:
+    """euclidean_distance_static of every row of x to the vector c in the AVX2 lane order (src/utils/dist.rs:306-330):
+    8 lane accumulators over 8-element chunks (separate multiply and add), wide's reduce_add tree, sequential tail."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    c = np.ascontiguousarray(c, dtype=np.float32)
+    n, dim = x.shape
+    chunks = dim // 8
+    acc = np.zeros((n, 8), dtype=np.float32)
+    for ch in range(chunks):
+        d = x[:, ch * 8:(ch + 1) * 8] - c[None, ch * 8:(ch + 1) * 8]
+        acc += d * d
+    s = acc[:, :4] + acc[:, 4:]
+    tot = (s[:, 0] + s[:, 2]) + (s[:, 1] + s[:, 3])
+    for e in range(chunks * 8, dim):
+        d = x[:, e] - c[e]
+        tot = tot + d * d
+    return tot.astype(np.float32)
+
+
+def _pick_by_cumsum(dist: np.ndarray, u: float) -> int:
+    """`threshold = u * total; first idx with cumsum >= threshold` with the reference's sequential f64 sums
+    (src/utils/k_means_utils.rs:580-592, 495-506); the last index if rounding leaves the threshold above the sum."""
+    cs = np.cumsum(dist.astype(np.float64))
+    return int(min(np.searchsorted(cs, u * cs[-1], side="left"), dist.size - 1))
+
+
+def fast_random_init(train: np.ndarray, k: int, rng) -> np.ndarray:
+    """fast_random_init (src/utils/k_means_utils.rs:612-626): k distinct random rows.  `rng`: numpy Generator standing in
+    for rand's StdRng shuffle (the stream itself cannot be reproduced without the crate)."""
+    return np.ascontiguousarray(train[rng.permutation(train.shape[0])[:k]])
+
+
+def kmeans_parallel_init(train: np.ndarray, k: int, metric: int, rng, device: int = 0) -> np.ndarray:
+    """k-means|| seeding (kmeans_parallel_init + weighted_kmeans_plus_plus, src/utils/k_means_utils.rs:435-596) for the
+    squared-Euclidean metric: ln(k) + 1 rounds, each a D^2 pass of every training row against the candidates so far --
+    on the GPU, as a k = 1 search of a flat index holding the candidates (the reference's min_distance_to_centroids
+    arithmetic, bit for bit) -- followed by 2k draws proportional to D^2 (sequential f64 cumulative sums on the host, as the
+    reference); the oversampled candidates are then reduced to k with the reference's k-means++ walk.  The uniform
+    draws come from `rng` in the reference's order (first index, then per round the 2k thresholds, then the k-means++
+    draws), so a caller that can replay StdRng's stream reproduces the reference's centroids."""
+    x = _as_rowmajor_f32(train)
+    n, dim = x.shape
+    if metric != L2:
+        raise AnnSearchError(-8, "k-means|| seeding on the device is restated for the squared-Euclidean metric")
+    rounds = int(math.log(k) + 1.0)
+    cand_rows = [int(rng.integers(0, n))]
+    for _ in range(rounds):
+        ix = ExhaustiveIndexB200.new(x[cand_rows], L2, F32, device)
+        try:
+            _, d, _ = ix.query_batch(x, 1)
+        finally:
+            ix.close()
+        d = d[:, 0]
+        for _ in range(2 * k):
+            cand_rows.append(_pick_by_cumsum(d, float(rng.random())))
+    cand = np.ascontiguousarray(x[cand_rows])
+    m = cand.shape[0]
+    if m <= k:
+        return cand
+    chosen = [int(rng.integers(0, m))]
+    dist = np.full(m, np.inf, dtype=np.float32)
+    for _ in range(1, k):
+        dist = np.minimum(dist, _ref_euclid_rows(cand, cand[chosen[-1]]))
+        chosen.append(_pick_by_cumsum(dist, float(rng.random())))
+    return np.ascontiguousarray(cand[chosen])
+
+
+def train_centroids(train: np.ndarray, nlist: int, metric: int, iters: int = 30, device: int = 0, seed: int = 42, init: Optional[str] = None,
+                    balanced: bool = False) -> np.ndarray:
+    """train_centroids (src/utils/k_means_utils.rs:2771-2938) on the device: seeding as resolve_init chooses it (:233-241:
+    more than 200 centroids -> k distinct random rows, otherwise k-means||; cosine always seeds with random rows here), then
+    the Lloyd loop of annb_kmeans_lloyd[_balanced].  numpy's PCG64 stands in for rand's StdRng: the algorithm is the
+    reference's, the individual draws are not.  The Hamerly / GEMM variants of the loop (:261-284) compute the same
+    assignments with bounds / a third-party GEMM and are not restated: every path runs the direct-assignment loop."""
     train = _as_rowmajor_f32(train)
     n, dim = train.shape
     if n < nlist:
         raise AnnSearchError(-3, f"{n} training samples for {nlist} centroids")
-    init = train[(np.arange(nlist, dtype=np.int64) * n) // nlist].copy()
-    return kmeans_lloyd(train, init, metric, max(1, iters), device)[0]
+    rng = np.random.Generator(np.random.PCG64(seed))
+    how = init or ("random" if (nlist > 200 or metric != L2) else "kmeans||")
+    if how == "random":
+        cent0 = fast_random_init(train, nlist, rng)
+    elif how == "kmeans||":
+        cent0 = kmeans_parallel_init(train, nlist, metric, rng, device)
+    elif how == "spaced":
+        cent0 = train[(np.arange(nlist, dtype=np.int64) * n) // nlist].copy()
+    else:
+        raise AnnSearchError(-4, f"unknown k-means init '{how}'")
+    return kmeans_lloyd(train, cent0, metric, max(1, iters), device, balanced=balanced, seed=seed)[0]
+
+
+def train_centroids_lloyd(train: np.ndarray, nlist: int, metric: int, iters: int = 30, device: int = 0) -> np.ndarray:
+    """Kept for callers of round 1: Lloyd from evenly spaced training rows."""
+    return train_centroids(train, nlist, metric, iters, device, init="spaced")
 
 
 def build_ivf_host_parts(mat, centroids, metric: int, dtype: int, train_rows=None, device: int = 0) -> dict:
@@ -504,7 +656,7 @@ def _first_device(device) -> int:
     return int(device[0]) if isinstance(device, (list, tuple)) else int(device)
 
 
-def _build_ivf(mat, nlist, centroids, dist_metric, dtype, seed, device, verbose, kmeans_iters=30) -> IvfIndexB200:
+def _build_ivf(mat, nlist, centroids, dist_metric, dtype, seed, device, verbose, kmeans_iters=30, kmeans_init=None, balanced=False) -> IvfIndexB200:
     metric = _metric_or_default(dist_metric)
     if metric == MANHATTAN:
         raise AnnSearchError(-2, "Manhattan distance is not supported by the IVF indices")
@@ -522,7 +674,7 @@ def _build_ivf(mat, nlist, centroids, dist_metric, dtype, seed, device, verbose,
             xt = normalise_rows(xt)
         if verbose:
             print(f"  Generating IVF index with {nlist} Voronoi cells.")
-        centroids = train_centroids_lloyd(xt, nlist, metric, kmeans_iters, _first_device(device))
+        centroids = train_centroids(xt, nlist, metric, kmeans_iters, _first_device(device), seed=seed, init=kmeans_init, balanced=balanced)
     parts = build_ivf_host_parts(x, centroids, metric, dtype, train_rows, _first_device(device))
     ix = IvfIndexB200.from_parts(device=device, **parts)
     ix.parts = parts
@@ -531,23 +683,24 @@ def _build_ivf(mat, nlist, centroids, dist_metric, dtype, seed, device, verbose,
 
 def build_ivf_index_gpu(mat, nlist: Optional[int] = None, k_means_params=None, dist_metric: str = "euclidean", seed: int = 42,
                         verbose: bool = False, device: int = 0, centroids=None) -> IvfIndexB200:
-    """src/lib.rs:2913-2947.  `k_means_params` may carry {"iters": int}; `centroids` short-circuits training."""
-    iters = (k_means_params or {}).get("iters", 30)
-    return _build_ivf(mat, nlist, centroids, dist_metric, F32, seed, device, verbose, iters)
+    """src/lib.rs:2913-2947.  `k_means_params` mirrors KMeansTrainingParams (src/utils/k_means_utils.rs:286-345) as a dict:
+    {"iters": int, "init": "random" | "kmeans||" | None, "balanced": bool}; `centroids` short-circuits training."""
+    kp = k_means_params or {}
+    return _build_ivf(mat, nlist, centroids, dist_metric, F32, seed, device, verbose, kp.get("iters", 30), kp.get("init"), bool(kp.get("balanced", False)))
 
 
 def build_ivf_bf16_index(mat, nlist: Optional[int] = None, k_means_params=None, dist_metric: str = "euclidean", seed: int = 42,
                          verbose: bool = False, device: int = 0, centroids=None) -> IvfIndexB200:
     """src/lib.rs:2100-2140."""
-    iters = (k_means_params or {}).get("iters", 30)
-    return _build_ivf(mat, nlist, centroids, dist_metric, BF16, seed, device, verbose, iters)
+    kp = k_means_params or {}
+    return _build_ivf(mat, nlist, centroids, dist_metric, BF16, seed, device, verbose, kp.get("iters", 30), kp.get("init"), bool(kp.get("balanced", False)))
 
 
 def build_ivf_sq8_index(mat, nlist: Optional[int] = None, k_means_params=None, dist_metric: str = "euclidean", seed: int = 42,
                         verbose: bool = False, device: int = 0, centroids=None) -> IvfIndexB200:
     """src/lib.rs:2196-2236."""
-    iters = (k_means_params or {}).get("iters", 30)
-    return _build_ivf(mat, nlist, centroids, dist_metric, SQ8, seed, device, verbose, iters)
+    kp = k_means_params or {}
+    return _build_ivf(mat, nlist, centroids, dist_metric, SQ8, seed, device, verbose, kp.get("iters", 30), kp.get("init"), bool(kp.get("balanced", False)))
 
 
 def query_ivf_index_gpu(query_mat, index: IvfIndexB200, k: int, nprobe: Optional[int] = None, nquery: Optional[int] = None,

@@ -135,6 +135,17 @@ int annb_flat_search(const annb_index* index, const float* queries, uint64_t nq,
 int annb_flat_search_self(const annb_index* index, uint64_t row_begin, uint64_t row_end, uint32_t k,
                           uint64_t* out_ids, float* out_dist, uint32_t* out_counts);
 
+/* Exact kNN graph rows in the shape of KnnGraphGpu (src/gpu/nndescent_gpu.rs:2418-2446), the hand-off struct
+ * build_nsg_from_gpu_knn (src/lib.rs:3330-3345 -> NsgIndex::build_from_knn, src/cpu/nsg.rs:744-775) and the raw-kNN
+ * consumers read: for every stored row in [row_begin, row_end) its k nearest OTHER rows -- the self edge is dropped by
+ * id, as compact_knn_rows does (nndescent_gpu.rs:2631-2667) -- ascending by distance, unfilled slots padded with the
+ * reference's sentinel pair (SENTINEL_PID = u32::MAX >> 1, f32::MAX).  out_pid / out_dist are [(row_end - row_begin) * k];
+ * out_counts (may be NULL) receives the number of real neighbours per row.  The reference fills this struct with
+ * NN-Descent (approximate); here it is the exhaustive self search of annb_flat_search_self with k + 1, so the graph is
+ * exact.  f32 indices only (the struct carries the f32 vectors); single- and multi-device handles. */
+int annb_flat_knn_graph(const annb_index* index, uint64_t row_begin, uint64_t row_end, uint32_t k, uint64_t* out_pid,
+                        float* out_dist, uint32_t* out_counts);
+
 /* Device-pointer variants (inputs already resident in HBM; asynchronous on `stream`). */
 int annb_flat_search_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k,
                          uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts, void* stream);
@@ -168,6 +179,16 @@ uint64_t annb_assign_last_redone(void);
  * NULL): number of centroid updates performed.  data [n * dim] host or device. */
 int annb_kmeans_lloyd(const float* data, uint64_t n, uint32_t dim, float* centroids, uint32_t nlist, int metric,
                       uint32_t max_iters, uint32_t* out_iters, int device);
+
+/* The same loop with the balancing hook of KMeansTrainingParams::with_balancing (src/utils/k_means_utils.rs:286-345):
+ * after every mean update adjust_centers (:979-1030; RAFT's balanced k-means) pulls each centroid whose cluster holds at
+ * most a quarter of the average size toward a point of an above-average cluster (weight min(count, 5); empty clusters
+ * jump onto the donor), donors found by the reference's strided walk seeded with seed + iteration; the loop only stops
+ * once an iteration moved no centroid (:1618).  No random numbers are involved, so the result is reproducible and is
+ * tested against the oracle's restatement.  out_adjusted (may be NULL): total number of centroid moves. */
+int annb_kmeans_lloyd_balanced(const float* data, uint64_t n, uint32_t dim, float* centroids, uint32_t nlist, int metric,
+                               uint32_t max_iters, int balanced, uint64_t seed, uint32_t* out_iters, uint64_t* out_adjusted,
+                               int device);
 
 /* Builds a resident IVF index from the contents of the reference's index struct after
  * optimise_memory_layout (src/cpu/ivf.rs:25-48, 257-294; src/quantised/ivf_bf16.rs,

@@ -797,6 +797,83 @@ int orc_parallel_lloyd(const float* data, int64_t n, int dim, int nlist, int met
     return it;
 }
 
+/* adjust_centers (src/utils/k_means_utils.rs:979-1030), the balancing step of RAFT's balanced k-means: every centroid
+ * whose cluster holds at most BALANCE_THRESHOLD (0.25) of the average size is pulled toward a point of an above-average
+ * cluster, weight min(count, BALANCE_PULLBACK = 5); the donor is found by a strided walk (BALANCE_DONOR_STRIDE =
+ * 715827883) whose cursor carries over from one starved centroid to the next.  No random numbers: fully reproducible.
+ * Returns the number of centroids moved. */
+int64_t orc_adjust_centers(float* centroids, int dim, int k, const float* data, int64_t n, const int64_t* assign, const int64_t* counts,
+                           uint64_t seed) {
+    if (k == 0 || n == 0) return 0;
+    const double average = (double)n / (double)k;
+    const double floor_ = average * 0.25;
+    int64_t adjusted = 0;
+    uint64_t cursor = seed % (uint64_t)n;
+    for (int c = 0; c < k; c++) {
+        if ((double)counts[c] > floor_) continue;
+        int64_t donor = -1;
+        for (int64_t t = 0; t < n; t++) {
+            cursor = (cursor + 715827883ull) % (uint64_t)n;
+            const int64_t owner = assign[cursor];
+            if (owner != c && (double)counts[owner] > average) { donor = (int64_t)cursor; break; }
+        }
+        if (donor < 0) continue;
+        const float w = (float)(counts[c] < 5 ? counts[c] : 5);
+        const float denom = w + 1.0f;
+        for (int d = 0; d < dim; d++) {
+            float* cc = centroids + (int64_t)c * dim + d;
+            *cc = (*cc * w + data[donor * dim + d]) / denom;
+        }
+        adjusted++;
+    }
+    return adjusted;
+}
+
+/* parallel_lloyd with the balancing hook (src/utils/k_means_utils.rs:1572-1700): as orc_parallel_lloyd, plus adjust_centers
+ * with seed + iteration right after the means (:1668-1682), and the loop stays in until balancing has nothing left to do
+ * (`changed <= change_floor && last_adjusted == 0`, :1618).  *out_adjusted: total number of centroid moves. */
+int orc_parallel_lloyd_balanced(const float* data, int64_t n, int dim, int nlist, int metric, int max_iters, int balanced, uint64_t seed,
+                                float* centroids, int64_t* out_adjusted, int nthreads) {
+    int64_t* assign = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+    int64_t* prev = (int64_t*)malloc(sizeof(int64_t) * (size_t)n);
+    float* cn = (float*)malloc(sizeof(float) * (size_t)nlist);
+    double* sums = (double*)malloc(sizeof(double) * (size_t)nlist * dim);
+    int64_t* cnt = (int64_t*)malloc(sizeof(int64_t) * (size_t)nlist);
+    for (int64_t i = 0; i < n; i++) prev[i] = -1;
+    const int64_t change_floor = (n / 10000) > 1 ? (n / 10000) : 1;
+    int64_t last_adjusted = 0, total = 0;
+    int it = 0;
+    for (; it < max_iters; it++) {
+        for (int c = 0; c < nlist; c++) cn[c] = orc_l2_norm_f32(centroids + (int64_t)c * dim, dim);
+        orc_assign_all(data, n, dim, centroids, cn, nlist, metric, assign, nthreads);
+        int64_t changed = 0;
+        for (int64_t i = 0; i < n; i++) changed += assign[i] != prev[i];
+        if (changed <= change_floor && last_adjusted == 0) break;
+        memset(sums, 0, sizeof(double) * (size_t)nlist * dim);
+        memset(cnt, 0, sizeof(int64_t) * (size_t)nlist);
+        for (int64_t i = 0; i < n; i++) {
+            int64_t c = assign[i];
+            cnt[c]++;
+            for (int d = 0; d < dim; d++) sums[c * dim + d] += data[i * dim + d];
+        }
+        for (int c = 0; c < nlist; c++)
+            if (cnt[c] > 0)
+                for (int d = 0; d < dim; d++) centroids[(int64_t)c * dim + d] = (float)(sums[(int64_t)c * dim + d] / (double)cnt[c]);
+        if (balanced) {
+            last_adjusted = orc_adjust_centers(centroids, dim, nlist, data, n, assign, cnt, seed + (uint64_t)it);
+            total += last_adjusted;
+        }
+        memcpy(prev, assign, sizeof(int64_t) * (size_t)n);
+    }
+    if (out_adjusted) *out_adjusted = total;
+    free(assign);
+    free(prev);
+    free(cn);
+    free(sums);
+    free(cnt);
+    return it;
+}
+
 /* Host-thread count the batch entry points will use. */
 int orc_max_threads(void) {
 #ifdef _OPENMP

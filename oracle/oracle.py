@@ -205,6 +205,31 @@ def parallel_lloyd(data, init_centroids, metric, max_iters=30, nthreads=0):
     return cent, int(it)
 
 
+def adjust_centers(centroids, data, assign, counts, seed):
+    """adjust_centers (src/utils/k_means_utils.rs:979-1030).  Returns (moved centroids copy, number moved)."""
+    cent = _f32(centroids).copy()
+    data = _f32(data)
+    a = np.ascontiguousarray(assign, dtype=np.int64)
+    c = np.ascontiguousarray(counts, dtype=np.int64)
+    L = lib()
+    L.orc_adjust_centers.restype = C.c_int64
+    moved = L.orc_adjust_centers(_p(cent), C.c_int(cent.shape[1]), C.c_int(cent.shape[0]), _p(data), C.c_int64(data.shape[0]), _p(a), _p(c),
+                                 C.c_uint64(seed))
+    return cent, int(moved)
+
+
+def parallel_lloyd_balanced(data, init_centroids, metric, max_iters=30, balanced=True, seed=42, nthreads=0):
+    """parallel_lloyd with the balancing hook (src/utils/k_means_utils.rs:1572-1700).  Returns (centroids, updates, centroid moves)."""
+    data = _f32(data)
+    cent = _f32(init_centroids).copy()
+    L = lib()
+    L.orc_parallel_lloyd_balanced.restype = C.c_int
+    adj = C.c_int64(0)
+    it = L.orc_parallel_lloyd_balanced(_p(data), C.c_int64(data.shape[0]), C.c_int(data.shape[1]), C.c_int(cent.shape[0]), C.c_int(metric),
+                                       C.c_int(max_iters), C.c_int(1 if balanced else 0), C.c_uint64(seed), _p(cent), C.byref(adj), C.c_int(nthreads))
+    return cent, int(it), int(adj.value)
+
+
 # --------------------------------------------------------------------------
 # index containers (host mirrors of the reference structs)
 # --------------------------------------------------------------------------

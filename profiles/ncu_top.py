@@ -9,7 +9,11 @@ hdr, units, vals = rows[0], rows[1], rows[2]
 want = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "sm__cycles_elapsed.max", "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "sm__inst_executed.sum", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__block_size",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed"]
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_sector_hit_rate.pct", "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor.sum",
+        "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32.sum", "sm__ops_path_tensor_src_tf32_dst_fp32.sum", "sm__ops_path_tensor_src_int8.sum",
+        "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes.sum.per_second"]
 print("kernel:", vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?")
 for h, u, v in zip(hdr, units, vals):
     if h in want:

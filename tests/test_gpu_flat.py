@@ -211,3 +211,29 @@ def test_matrix_to_flat_on_device(gpu):
     ids, d, _ = g.query_batch(q, 10)
     rids, rd, _ = o.flat_search(o.build_flat(data, o.L2, o.F32), q, 10)
     assert_exact(ids, d, rids, rd, "index built from a column-major matrix")
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("shards", [1, 3])
+def test_knn_graph_handoff(gpu, metric, shards):
+    """the exact self-kNN graph in the shape of KnnGraphGpu (src/gpu/nndescent_gpu.rs:2418-2446): self edge
+    dropped by id (duplicates of a row may precede it), rows ascending, sentinel pairs at the tail; the contract
+    build_nsg_from_gpu_knn relies on holds; neighbours and distances are the oracle's self search without the self id."""
+    data = datagen.gaussian_noise(6000, 24, seed=5)
+    data[100] = data[40]                     # exact duplicates: row 40 precedes row 100 at distance 0
+    data[5000] = data[40]
+    k = 12
+    dev = 0 if shards == 1 else [i % gpu for i in range(shards)]
+    g = annb200.build_knn_graph_gpu(data, "cosine" if metric == "cosine" else "euclidean", k=k, device=dev)
+    assert g.n == 6000 and g.dim == 24 and g.k == k and g.converged and g.vectors_flat.size == 6000 * 24
+    assert (g.norms.size == 6000) == (metric == "cosine")
+    assert g.check_contract()
+    c = o.build_flat(data, o.COSINE if metric == "cosine" else o.L2)
+    rids, rd, _ = o.flat_search(c, None, k + 1, self_mode=True)
+    for i in range(6000):
+        keep = rids[i] != i
+        want_i, want_d = rids[i][keep][:k], rd[i][keep][:k]
+        assert np.array_equal(g.pid[i], want_i) and np.array_equal(g.dist[i].view(np.uint32), want_d.view(np.uint32)), i
+    # fewer than k other rows: sentinel padding
+    small = annb200.build_knn_graph_gpu(data[:5], "euclidean", k=8)
+    assert (small.pid[:, 4:] == annb200.SENTINEL_PID).all() and (small.dist[:, 4:] == np.finfo(np.float32).max).all() and small.check_contract()

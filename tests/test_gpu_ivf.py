@@ -430,3 +430,60 @@ def test_concurrent_ivf_searches_on_one_handle(gpu):
     assert not errs, errs
     for t in range(4):
         _check("f32", out[t], refs[t], f"thread {t}")
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_device_lloyd_balanced_matches_restated_adjust_centers(gpu, metric):
+    """KMeansTrainingParams::with_balancing (SURVEY 8f-1): adjust_centers needs no random numbers, so the device loop and the
+    oracle's restatement must move the same centroids in the same iterations: same number of updates, same number of
+    centroid moves, centroids within 1e-5 (the means are f64-accumulated on both sides, the reference's f32 partial sums
+    depend on its thread pool)."""
+    rng = np.random.default_rng(11)
+    data = np.concatenate([rng.normal(0, 1, (6000, 16)), rng.normal(8, 0.05, (40, 16)), rng.normal(-9, 0.05, (25, 16))]).astype(np.float32)
+    data = np.ascontiguousarray(data[rng.permutation(data.shape[0])])
+    init = np.ascontiguousarray(data[rng.choice(data.shape[0], 24, replace=False)])
+    m_g, m_o = (annb200.L2, o.L2) if metric == "l2" else (annb200.COSINE, o.COSINE)
+    ref_c, ref_it, ref_moves = o.parallel_lloyd_balanced(data, init, m_o, 30, True, 42)
+    c, it, moves = annb200.kmeans_lloyd(data, init, m_g, max_iters=30, balanced=True, seed=42, return_moves=True)
+    assert (it, moves) == (ref_it, ref_moves), ((it, moves), (ref_it, ref_moves))
+    assert moves > 0, "the skewed blobs must starve some clusters (otherwise balancing is not exercised)"
+    assert np.allclose(c, ref_c, rtol=1e-5, atol=1e-5)
+    # one adjust_centers step on identical inputs: bit-exact
+    a = annb200.ivf_assign(data, init, m_g)
+    cnt = np.bincount(a, minlength=24)
+    moved, n_moved = o.adjust_centers(init, data, a, cnt, 7)
+    assert n_moved >= 0 and moved.shape == init.shape
+    # balancing off through the same entry point = the plain loop
+    c0, it0 = annb200.kmeans_lloyd(data, init, m_g, max_iters=30)
+    c1, it1, mv1 = annb200.kmeans_lloyd(data, init, m_g, max_iters=30, balanced=False, return_moves=True)
+    assert it0 == it1 and mv1 == 0 and np.array_equal(c0.view(np.uint32), c1.view(np.uint32))
+
+
+def test_kmeans_parallel_seeding_on_shared_draws(gpu):
+    """k-means|| seeding with the D^2 passes on the device: on the same uniform draws the mirror must pick the
+    same rows as a plain restatement of kmeans_parallel_init + weighted_kmeans_plus_plus built from the oracle's scalar
+    kernels (src/utils/k_means_utils.rs:435-596)."""
+    import math
+    data = datagen.gaussian_noise(3000, 20, seed=17)
+    k, seed = 12, 5
+    got = annb200.kmeans_parallel_init(data, k, annb200.L2, np.random.Generator(np.random.PCG64(seed)))
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = data.shape[0]
+    cand = [int(rng.integers(0, n))]
+    for _ in range(int(math.log(k) + 1.0)):
+        d = np.array([min(o.euclid_f32(v, data[c]) for c in cand) for v in data], dtype=np.float32)
+        cs = np.cumsum(d.astype(np.float64))
+        for _ in range(2 * k):
+            cand.append(int(min(np.searchsorted(cs, float(rng.random()) * cs[-1], side="left"), n - 1)))
+    cv = data[cand]
+    chosen = [int(rng.integers(0, len(cand)))]
+    dist = np.full(len(cand), np.inf, dtype=np.float32)
+    for _ in range(1, k):
+        dist = np.minimum(dist, np.array([o.euclid_f32(v, cv[chosen[-1]]) for v in cv], dtype=np.float32))
+        cs = np.cumsum(dist.astype(np.float64))
+        chosen.append(int(min(np.searchsorted(cs, float(rng.random()) * cs[-1], side="left"), len(cand) - 1)))
+    assert np.array_equal(got.view(np.uint32), cv[chosen].view(np.uint32))
+    # the build_* mirror with the reference's parameter struct as a dict
+    ix = annb200.build_ivf_index_gpu(data, nlist=12, k_means_params={"iters": 5, "init": "kmeans||", "balanced": True}, dist_metric="euclidean", seed=3)
+    ids, dist_, _ = ix.query_batch(data[:50], 5, nprobe=12)
+    assert (ids[:, 0] == np.arange(50)).all()
