@@ -564,7 +564,7 @@ static int ivf_enqueue(annb_index* ix, const PreparedQueries& pq, uint64_t nq, u
     parts = std::max(1u, std::min(parts, np));
     // very small batches (the tensor path's exact fallback): also cut every list into row segments
     uint32_t subs = ix->opt_scan_parts > 0 ? 1u : static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(32, want / parts)));
-    while (subs > 1 && static_cast<uint64_t>(parts) * subs * kk * 8 > 128 * 1024) subs--;
+    while (subs > 1 && static_cast<uint64_t>(parts) * subs * kk * 8 > 32 * 1024) subs--;   // finalize sorts parts * subs * k keys per query: keep that a 4096-key sort
     const uint32_t nsort = WarpSelect::sort_size(kk);
     ANNB_TRY(ix->s_keys.ensure(nq * parts * subs * static_cast<uint64_t>(kk) * 8));
     {
@@ -1558,6 +1558,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "ivf_fast_probe") ix->opt_ivf_fast_probe = static_cast<int>(value);
     else if (k == "ivf_tc_coarse") ix->opt_ivf_tc_coarse = static_cast<int>(value);
     else if (k == "ivf_stream") ix->opt_ivf_stream = static_cast<int>(value);
+    else if (k == "ivf_coarse_stage") ix->opt_ivf_coarse_stage = static_cast<int>(value);
     else if (k == "async_dev") ix->opt_async_dev = static_cast<int>(value);
     else if (k == "time_kernels") { ix->opt_time_kernels = static_cast<int>(value); ix->timed_ms_total = 0.0; ix->timed_launches = 0; }
     else return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown option " + k);

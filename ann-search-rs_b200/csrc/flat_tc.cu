@@ -1018,7 +1018,7 @@ bool tc_coarse_supported(const annb_index* ix) { return ix->tc_coarse != nullptr
 template <int MET>
 static int launch_coarse_select(const tc::CoarseSelectParams& c, cudaStream_t s) {
     auto kern = tc::coarse_select_kernel<MET>;
-    const uint32_t warps = 4;
+    const uint32_t warps = c.staged_words ? 4 : 8;
     const size_t per_warp = tc::coarse_select_warp_bytes(c.cmax, c.staged_words);
     const size_t smem = per_warp * warps;
     ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -1066,8 +1066,10 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     }
     tc::CoarseSelectParams c{};
     c.dense = st->dense.as<float>(); c.dense_ld = st->n_pad; c.nq = nq; c.nlist = ix->nlist; c.pitch = pitch; c.cmax = next_pow2(pitch + 1);
-    // rows of up to 8192 cells are staged in shared memory (32 KB per warp, four warps per CTA)
-    c.staged_words = ix->nlist <= 8192 ? round_up(ix->nlist, 4u) : 0u;
+    // Staging the row of values in shared memory (one global pass instead of ~5 L2 passes) was measured SLOWER at nlist 4096,
+    // 10k queries: 0.41 ms against 0.27 ms per launch -- 16 KB per warp leaves 12 resident warps per SM where the L2 variant
+    // keeps 64, and the select is a chain of dependent passes that only occupancy hides.  Kept behind option ivf_coarse_stage.
+    c.staged_words = (ix->opt_ivf_coarse_stage && ix->nlist <= 8192) ? round_up(ix->nlist, 4u) : 0u;
     c.queries = d_route; c.q_ld = route_ld; c.centroids = ix->d_centroids; c.c_ld = ix->cent_ld; c.centroid_norms = ix->d_centroid_norms;
     c.dim = ix->dim; c.eps = tc_cert_eps(ix, tc::KIND_TF32X3, kp, 2, false); c.cnorm_max = ix->tc_cnorm_max; c.ranked = d_ranked;
     if (ix->metric == ANNB_L2) ANNB_TRY(launch_coarse_select<MET_L2>(c, s));

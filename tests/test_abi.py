@@ -118,3 +118,15 @@ def test_cpp_host_mirror_compiles_links_and_fails_loudly_without_gpu():
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("OK"), r.stdout
+
+
+def test_rust_ffi_declares_every_header_symbol():
+    """rust/annb200-sys cannot be compiled in this image (no cargo / rustc); at least its extern block must name every
+    entry point include/annb200.h declares, so the crate links against the library as it is."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "annb200.h")).read()
+    rs = open(os.path.join(root, "ann-search-rs_b200", "rust", "annb200-sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"\b(annb_[a-z0-9_]+)\s*\(", hdr)) - {"annb_status"}   # (a comment mentions the enum with a parenthesis)
+    in_rust = set(re.findall(r"pub fn (annb_[a-z0-9_]+)\s*\(", rs))
+    assert declared - in_rust == set(), f"missing in annb200-sys: {sorted(declared - in_rust)}"
