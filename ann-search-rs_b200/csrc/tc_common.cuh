@@ -510,85 +510,119 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         s_qn = qn;
         s_qs = qs;
     }
+    // |q|^2 in f64 for the certificate's value -> distance map (any summation order: the rounding is 2^-53-sized)
+    __shared__ double s_qn2w[4];
+    {
+        double part = 0.0;
+        for (uint32_t e = threadIdx.x; e < p.dim; e += blockDim.x) {
+            double x;
+            if constexpr (QT == QT_I8) x = static_cast<double>(reinterpret_cast<const int8_t*>(qv)[e]);
+            else x = static_cast<double>(load1<(QT == QT_F32) ? 4 : 2>(qv, e));
+            part += x * x;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, off);
+        if ((threadIdx.x & 31u) == 0) s_qn2w[threadIdx.x >> 5] = part;
+    }
     __syncthreads();
     auto exact_range = [&](uint32_t count) {
+        // up to four candidates per 8-thread group (j = grp, grp + 16, grp + 32, grp + 48) with independent accumulators: the row
+        // gathers of all of them are in flight together -- one DRAM round trip for a 64-candidate second chance instead of four
         const uint32_t l = threadIdx.x & 7u, grp = threadIdx.x >> 3;
-        for (uint32_t base = 0; base < 64; base += 16) {
-            const uint32_t j = base + grp;
-            if (base >= count) {                       // whole round beyond the candidates (uniform over the CTA)
-                if (l == 0) exact[j] = KEY_SENTINEL;
-                continue;
-            }
-            const uint64_t key = j < count ? keys[j] : KEY_SENTINEL;
-            const uint32_t idx = key_idx(key);
-            const bool live = idx != IDX_INVALID;
-            const uint8_t* row = p.rows + static_cast<uint64_t>(live ? idx : 0u) * p.row_bytes;
-            uint64_t out = KEY_SENTINEL;
-            if constexpr (RT == 2) {
-                // SQ8: exact code-space integers (src/utils/dist.rs:5015-5077); any summation order gives the same value
-                int32_t dot = 0, xx = 0;
-                for (uint32_t c = l; c < (p.dim + 15u) / 16u; c += 8) {
-                    const int4 x = *reinterpret_cast<const int4*>(row + c * 16);
-                    const int4 y = *reinterpret_cast<const int4*>(qv + c * 16);
-                    xx = __dp4a(x.x, x.x, xx); xx = __dp4a(x.y, x.y, xx); xx = __dp4a(x.z, x.z, xx); xx = __dp4a(x.w, x.w, xx);
-                    dot = __dp4a(x.x, y.x, dot); dot = __dp4a(x.y, y.y, dot); dot = __dp4a(x.z, y.z, dot); dot = __dp4a(x.w, y.w, dot);
-                }
+        const uint32_t rounds = min(4u, (count + 15u) >> 4);     // uniform over the CTA
+        uint32_t idx[4];
+        const uint8_t* row[4];
 #pragma unroll
-                for (int off = 4; off > 0; off >>= 1) {
-                    dot += __shfl_down_sync(0xFFFFFFFFu, dot, off, 8);
-                    xx += __shfl_down_sync(0xFFFFFFFFu, xx, off, 8);
-                }
-                if (live) out = make_key(finish_i8<MET>(dot, xx, s_qs, (MET == MET_COS) ? p.row_norms_i[idx] : 0), idx);
-            } else {
-                constexpr int RELEM = (RT == 0) ? 4 : 2, QELEM = (QT == QT_F32) ? 4 : 2;
-                constexpr bool FMA = (RELEM == 2);
-                const uint32_t chunks = p.dim >> 3;
-                float acc = 0.0f;
-                for (uint32_t c = 0; c < chunks; c++) {
-                    const float x = load1<RELEM>(row, c * 8 + l), y = load1<QELEM>(qv, c * 8 + l);
-                    if (MET == MET_L2) {
-                        const float d = __fsub_rn(x, y);
-                        acc = FMA ? __fmaf_rn(d, d, acc) : __fadd_rn(acc, __fmul_rn(d, d));
-                    } else {
-                        acc = FMA ? __fmaf_rn(x, y, acc) : __fadd_rn(acc, __fmul_rn(x, y));
+        for (int r = 0; r < 4; r++) {
+            const uint32_t j = r * 16 + grp;
+            const uint64_t key = (static_cast<uint32_t>(r) < rounds && j < count) ? keys[j] : KEY_SENTINEL;
+            idx[r] = key_idx(key);
+            row[r] = p.rows + static_cast<uint64_t>(idx[r] != IDX_INVALID ? idx[r] : 0u) * p.row_bytes;
+        }
+        uint64_t out[4] = {KEY_SENTINEL, KEY_SENTINEL, KEY_SENTINEL, KEY_SENTINEL};
+        if constexpr (RT == 2) {
+            // SQ8: exact code-space integers (src/utils/dist.rs:5015-5077); any summation order gives the same value
+            int32_t dot[4] = {0, 0, 0, 0}, xx[4] = {0, 0, 0, 0};
+            for (uint32_t c = l; c < (p.dim + 15u) / 16u; c += 8) {
+                const int4 y = *reinterpret_cast<const int4*>(qv + c * 16);
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    if (static_cast<uint32_t>(r) < rounds) {
+                        const int4 x = *reinterpret_cast<const int4*>(row[r] + c * 16);
+                        xx[r] = __dp4a(x.x, x.x, xx[r]); xx[r] = __dp4a(x.y, x.y, xx[r]); xx[r] = __dp4a(x.z, x.z, xx[r]); xx[r] = __dp4a(x.w, x.w, xx[r]);
+                        dot[r] = __dp4a(x.x, y.x, dot[r]); dot[r] = __dp4a(x.y, y.y, dot[r]); dot[r] = __dp4a(x.z, y.z, dot[r]); dot[r] = __dp4a(x.w, y.w, dot[r]);
                     }
                 }
-                // s_l = a_l + a_(l+4);  wide: (s0 + s2) + (s1 + s3);  hsum_f32_avx2: (s0 + s1) + (s2 + s3)
-                const float s4 = __fadd_rn(acc, __shfl_down_sync(0xFFFFFFFFu, acc, 4, 8));
-                float sum;
-                if (FMA) {
-                    const float u = __fadd_rn(s4, __shfl_down_sync(0xFFFFFFFFu, s4, 1, 8));
-                    sum = __fadd_rn(u, __shfl_down_sync(0xFFFFFFFFu, u, 2, 8));
-                } else {
-                    const float t = __fadd_rn(s4, __shfl_down_sync(0xFFFFFFFFu, s4, 2, 8));
-                    sum = __fadd_rn(t, __shfl_down_sync(0xFFFFFFFFu, t, 1, 8));
+            }
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                if (static_cast<uint32_t>(r) < rounds) {
+#pragma unroll
+                    for (int off = 4; off > 0; off >>= 1) {
+                        dot[r] += __shfl_down_sync(0xFFFFFFFFu, dot[r], off, 8);
+                        xx[r] += __shfl_down_sync(0xFFFFFFFFu, xx[r], off, 8);
+                    }
+                    if (idx[r] != IDX_INVALID) out[r] = make_key(finish_i8<MET>(dot[r], xx[r], s_qs, (MET == MET_COS) ? p.row_norms_i[idx[r]] : 0), idx[r]);
                 }
-                if (l == 0 && live) {
-                    for (uint32_t e = chunks * 8; e < p.dim; e++) {   // scalar tail: `sum += d * d` (not fused)
-                        const float x = load1<RELEM>(row, e), y = load1<QELEM>(qv, e);
+            }
+        } else {
+            constexpr int RELEM = (RT == 0) ? 4 : 2, QELEM = (QT == QT_F32) ? 4 : 2;
+            constexpr bool FMA = (RELEM == 2);
+            const uint32_t chunks = p.dim >> 3;
+            float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 2
+            for (uint32_t c = 0; c < chunks; c++) {
+                const float y = load1<QELEM>(qv, c * 8 + l);
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    if (static_cast<uint32_t>(r) < rounds) {
+                        const float x = load1<RELEM>(row[r], c * 8 + l);
                         if (MET == MET_L2) {
                             const float d = __fsub_rn(x, y);
-                            sum = __fadd_rn(sum, __fmul_rn(d, d));
+                            acc[r] = FMA ? __fmaf_rn(d, d, acc[r]) : __fadd_rn(acc[r], __fmul_rn(d, d));
                         } else {
-                            sum = __fadd_rn(sum, __fmul_rn(x, y));
+                            acc[r] = FMA ? __fmaf_rn(x, y, acc[r]) : __fadd_rn(acc[r], __fmul_rn(x, y));
                         }
                     }
-                    out = make_key(finish_fp<MET>(sum, s_qn, (MET == MET_COS) ? p.row_norms[idx] : 1.0f), idx);
                 }
             }
-            if (l == 0) exact[j] = out;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                if (static_cast<uint32_t>(r) < rounds) {
+                    // s_l = a_l + a_(l+4);  wide: (s0 + s2) + (s1 + s3);  hsum_f32_avx2: (s0 + s1) + (s2 + s3)
+                    const float s4 = __fadd_rn(acc[r], __shfl_down_sync(0xFFFFFFFFu, acc[r], 4, 8));
+                    float sum;
+                    if (FMA) {
+                        const float u = __fadd_rn(s4, __shfl_down_sync(0xFFFFFFFFu, s4, 1, 8));
+                        sum = __fadd_rn(u, __shfl_down_sync(0xFFFFFFFFu, u, 2, 8));
+                    } else {
+                        const float t = __fadd_rn(s4, __shfl_down_sync(0xFFFFFFFFu, s4, 2, 8));
+                        sum = __fadd_rn(t, __shfl_down_sync(0xFFFFFFFFu, t, 1, 8));
+                    }
+                    if (l == 0 && idx[r] != IDX_INVALID) {
+                        for (uint32_t e = chunks * 8; e < p.dim; e++) {   // scalar tail: `sum += d * d` (not fused)
+                            const float x = load1<RELEM>(row[r], e), y = load1<QELEM>(qv, e);
+                            if (MET == MET_L2) {
+                                const float d = __fsub_rn(x, y);
+                                sum = __fadd_rn(sum, __fmul_rn(d, d));
+                            } else {
+                                sum = __fadd_rn(sum, __fmul_rn(x, y));
+                            }
+                        }
+                        out[r] = make_key(finish_fp<MET>(sum, s_qn, (MET == MET_COS) ? p.row_norms[idx[r]] : 1.0f), idx[r]);
+                    }
+                }
+            }
+        }
+        if (l == 0) {
+#pragma unroll
+            for (int r = 0; r < 4; r++) exact[r * 16 + grp] = out[r];
         }
     };
     // coverage test: every row that was not re-ranked has an approximate value >= a_thr; is the k-th exact distance safely
     // below the distance that value stands for?  (one thread, f64: the map itself must not add rounding of its own)
     auto covered = [&](float a_thr, float dk) -> bool {
-        double qn2 = 0.0;
-        for (uint32_t e = 0; e < p.dim; e++) {
-            double x;
-            if constexpr (QT == QT_I8) x = static_cast<double>(reinterpret_cast<const int8_t*>(qv)[e]);
-            else x = static_cast<double>(load1<(QT == QT_F32) ? 4 : 2>(qv, e));
-            qn2 += x * x;
-        }
+        const double qn2 = (s_qn2w[0] + s_qn2w[1]) + (s_qn2w[2] + s_qn2w[3]);
         if (MET == MET_L2) {
             // approx value = |x|^2 - 2 q.x = dist - |q|^2 ; error <= eps * (|q| + |x|max)^2
             const double s = sqrt(qn2) + static_cast<double>(p.xnorm_max);
