@@ -1548,6 +1548,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "tc_ts") ix->opt_tc_ts = static_cast<int>(value);
     else if (k == "tc_bf16_hybrid") ix->opt_tc_bf16_hybrid = static_cast<int>(value);
     else if (k == "tc_bf16_terms") ix->opt_tc_bf16_terms = static_cast<int>(value);
+    else if (k == "tc_epi_warps") ix->opt_tc_epi_warps = static_cast<int>(value);
     else if (k == "cert_fallback") ix->opt_cert_fallback = static_cast<int>(value);
     else if (k == "cert_eps_log2") ix->opt_cert_eps = value == 0 ? 0.f : (value > 0 ? -1.0f : std::ldexp(1.0f, static_cast<int>(value)));   // e.g. -18; 0 switches the certificate off; 1 = derived bound (default)
     else if (k == "tc_debug") { DeviceGuard g(ix->device); return ix->is_ivf ? tc_ivf_debug_enable(ix, value != 0) : tc_debug_enable(ix, value != 0); }

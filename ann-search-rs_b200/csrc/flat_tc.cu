@@ -38,8 +38,11 @@ namespace tc {
 // [nq x nlist] matrix of approximate values; see coarse_select_kernel).
 __device__ __forceinline__ bool hyb_cfg(const Params& p) { return p.hybrid != 0; }
 
-template <int KIND, int KP, int MET, bool TS, bool DENSE = false>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// EW = epilogue warps per TMEM lane quarter (2 or 4): every warp owns 128 / EW columns of each tile.  The kernels whose
+// epilogue paces them (int8 codes, bf16 terms: few MMAs per tile) run four, so that four warps per scheduler interleave
+// their load -> transform -> select chains; the MMA-bound f32 kernels keep two (and their larger register budget).
+template <int KIND, int KP, int MET, bool TS, bool DENSE = false, int EW = 2>
+__global__ void __launch_bounds__(64 + EW * 128, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const Params p) {
     constexpr int NA = (KIND == KIND_TF32X3) ? 2 : (KIND == KIND_I8 ? 1 : 3);  // stacked query pieces
     constexpr int NB = (KIND == KIND_TF32X3) ? 2 : 1;  // stacked database pieces
@@ -47,6 +50,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     static_assert(KIND != KIND_I8 || TS, "the int8 kernel keeps its queries in TMEM");
     constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;      // 32 tf32 / 64 bf16 per slab row
     constexpr int KSTEPS = 4;                          // 128 B / 32 B per UMMA K step (8 tf32 / 16 bf16)
+    constexpr int NV = BN / EW;                        // columns per epilogue warp and tile
+    constexpr int NG = NV / 8;
+    constexpr uint32_t EPI_T = EW * 128;               // epilogue threads
     // TMEM columns per query piece (32-bit words per row): f32 128; bf16 terms 64 (rows of <= 128 elements) or 128; int8 codes 128
     const uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : (KIND == KIND_I8 ? 128u : (p.kp > 128u ? 128u : 64u));
     // accumulator stages behind the TMEM-resident queries (TS): three when the pieces take at most 128 columns (int8 codes, one
@@ -75,7 +81,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     uint64_t* bar_tempty = bar_tfull + ACC_STAGES;     // [ACC_STAGES]
     uint64_t* bar_q2 = bar_tempty + ACC_STAGES;        // [1] hybrid: term q2 has landed in shared memory
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_q2 + 1);
-    float* s_aux_all = reinterpret_cast<float*>(s_tail + 256);   // [8 epilogue warps][64]: per-row constants of the warp's current half tile
+    float* s_aux_all = reinterpret_cast<float*>(s_tail + 256);   // [4 * EW epilogue warps][NV]: per-row constants of the warp's current column group
 
     const uint32_t q0 = blockIdx.x * BM;
     const uint64_t r_begin = static_cast<uint64_t>(blockIdx.y) * p.rows_per_split;
@@ -84,9 +90,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.n_stages; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
-        mbar_init(bar_q, TS ? EPI_THREADS : 1);
+        mbar_init(bar_q, TS ? EPI_T : 1);
         mbar_init(bar_q2, 1);
-        for (uint32_t a = 0; a < NACC; a++) { mbar_init(bar_tfull + a, 1); mbar_init(bar_tempty + a, EPI_THREADS); }
+        for (uint32_t a = 0; a < NACC; a++) { mbar_init(bar_tfull + a, 1); mbar_init(bar_tempty + a, EPI_T); }
         fence_barrier_init();
         fence_proxy_async();
         tma_prefetch_desc(&tm_q);
@@ -205,11 +211,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         // ===================================================================== epilogue (4 warps, thread = query row)
         const uint32_t quarter = warp & 3u;                 // TMEM lane quarter this warp may access
         const uint32_t row_in_tile = quarter * 32 + lane;   // query row inside the tile
-        const uint32_t half = (warp - 2) >> 2;              // which 64-column half of every tile this warp scans
-        const uint32_t e = threadIdx.x - 64;                // 0..255; the first 128 stage aux
+        const uint32_t half = (warp - 2) >> 2;              // which NV-column group of every tile this warp scans (0 .. EW - 1)
         TopList<KP> top;
         top.init();
-        float scratch[64];
+        float scratch[NV];
         long long w_tfull = 0, w_slow = 0;
         // Shared threshold: the k'-th best value any CTA of this query has seen so far (monotone, atomicMin on the
         // order-preserving integer image).  A value that does not beat it cannot be in the merged top-k', whichever
@@ -220,18 +225,18 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             // tcgen05.st.  16-bit operands sit two per column, low half = even k, exactly as in memory.
             const uint32_t row_words = p.kp * ELEM / 4;
             const uint32_t tmem_pieces = hyb ? 2u : p.a_pieces;
-            for (uint32_t pc = half; pc < tmem_pieces; pc += 2) {
+            const uint32_t cpp = row_words / 32;                       // 32-column chunks per piece
+            for (uint32_t item = half; item < tmem_pieces * cpp; item += EW) {   // (piece, chunk) items dealt round-robin to the quarter's warps
+                const uint32_t pc = item / cpp, c = (item - pc * cpp) * 32;
                 const uint32_t* src = reinterpret_cast<const uint32_t*>(p.q_op) + (static_cast<size_t>(pc) * p.nq_pad + q0 + row_in_tile) * row_words;
                 const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + pc * PIECE_COLS;
-                for (uint32_t c = 0; c < row_words; c += 32) {
-                    uint32_t w[32];
+                uint32_t w[32];
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const uint4 x = __ldg(reinterpret_cast<const uint4*>(src + c) + j);
-                        w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
-                    }
-                    tmem_st32(tq + c, w);
+                for (int j = 0; j < 8; j++) {
+                    const uint4 x = __ldg(reinterpret_cast<const uint4*>(src + c) + j);
+                    w[4 * j] = x.x; w[4 * j + 1] = x.y; w[4 * j + 2] = x.z; w[4 * j + 3] = x.w;
                 }
+                tmem_st32(tq + c, w);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -242,10 +247,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         // Per-column constants of this warp's 64-column half: lane l fetches columns l and l + 32 (coalesced, one tile
         // ahead) and parks them in a warp-private shared-memory row; the value loop reads them back as 128-bit broadcast
         // loads (16 per tile instead of 64 shuffles).  No CTA-wide barrier: only __syncwarp.
-        float* s_aux = s_aux_all + (warp - 2) * 64;
-        const float* aux_half = p.aux + r_begin + half * 64 + lane;
+        float* s_aux = s_aux_all + (warp - 2) * NV;
+        const float* aux_half = p.aux + r_begin + half * NV + lane;
         float aux_lo_next = 0.f, aux_hi_next = 0.f;
-        if (n_tiles > 0) { aux_lo_next = __ldg(aux_half); aux_hi_next = __ldg(aux_half + 32); }
+        if (n_tiles > 0) { aux_lo_next = __ldg(aux_half); if (NV > 32) aux_hi_next = __ldg(aux_half + 32); }
         for (uint32_t t = 0; t < n_tiles; t++) {
             const uint32_t acc = t % NACC, aph = (t / NACC) & 1u;
             const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
@@ -253,12 +258,12 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             const float aux_lo = aux_lo_next, aux_hi = aux_hi_next;
             if (t + 1 < n_tiles) {   // prefetch for the next tile: latency hidden behind this tile's work
                 aux_lo_next = __ldg(aux_half + static_cast<size_t>(t + 1) * BN);
-                aux_hi_next = __ldg(aux_half + static_cast<size_t>(t + 1) * BN + 32);
+                if (NV > 32) aux_hi_next = __ldg(aux_half + static_cast<size_t>(t + 1) * BN + 32);
                 if (!DENSE) g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
             }
             __syncwarp();                      // every lane is done with the previous tile's constants
             s_aux[lane] = aux_lo;
-            s_aux[lane + 32] = aux_hi;
+            if (NV > 32) s_aux[lane + 32] = aux_hi;
             __syncwarp();
             mbar_wait_timed(bar_tfull + acc, aph, w_tfull);
             tc_fence_after();
@@ -267,16 +272,17 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + ACC_COL0 + acc * BN;
             {
                 const int c = static_cast<int>(half);
-                uint32_t r[64];
-                tmem_ld64_sync(taddr + c * 64, r);
+                uint32_t r[NV];
+                if constexpr (NV == 64) tmem_ld64_sync(taddr + c * NV, r);
+                else tmem_ld32_sync(taddr + c * NV, r);
                 // the tile's values are in registers: hand the accumulator stage back before the select work, so the
                 // issuer never waits on this warp's candidate inserts
                 tc_fence_before();
                 mbar_arrive(bar_tempty + acc);
-                float v[64];
-                float gm[8];  // minima of the 8 groups of 8 columns
+                float v[NV];
+                float gm[NG];  // minima of the groups of 8 columns
 #pragma unroll
-                for (int g = 0; g < 8; g++) {
+                for (int g = 0; g < NG; g++) {
                     float mg = INFINITY;
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
@@ -290,19 +296,23 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 }
                 if constexpr (DENSE) {
                     if (static_cast<uint64_t>(q0) + row_in_tile < p.nq) {
-                        float4* dst = reinterpret_cast<float4*>(p.dense + (static_cast<uint64_t>(q0) + row_in_tile) * p.dense_ld + row0 + c * 64);
+                        float4* dst = reinterpret_cast<float4*>(p.dense + (static_cast<uint64_t>(q0) + row_in_tile) * p.dense_ld + row0 + c * NV);
 #pragma unroll
-                        for (int j = 0; j < 16; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int j = 0; j < NV / 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
                 }
-                const float m = DENSE ? INFINITY : fminf(fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])), fminf(fminf(gm[4], gm[5]), fminf(gm[6], gm[7])));
+                float m = INFINITY;
+                if (!DENSE) {
+#pragma unroll
+                    for (int g = 0; g < NG; g++) m = fminf(m, gm[g]);
+                }
                 if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t == 0) {
 #pragma unroll
-                    for (int j = 0; j < 64; j++) p.dbg[row_in_tile * BN + c * 64 + j] = v[j];
+                    for (int j = 0; j < NV; j++) p.dbg[row_in_tile * BN + c * NV + j] = v[j];
                 }
                 if (m < tau) {
                     const long long ts0 = tc_clock();
-                    select_from_tile<KP>(top, tau, v, gm, m, row0 + c * 64, scratch);
+                    select_from_tile<KP, NV>(top, tau, v, gm, m, row0 + c * NV, scratch);
                     w_slow += tc_clock() - ts0;
                 }
             }
@@ -311,7 +321,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         if (TC_COUNTERS && p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) { p.dbg_cycles[4] = w_tfull; p.dbg_cycles[5] = w_slow; }
         const uint64_t q = static_cast<uint64_t>(q0) + row_in_tile;
         if (!DENSE && q < p.nq) {
-            uint64_t* out = p.part_keys + (q * (2 * p.n_splits) + 2 * blockIdx.y + half) * KP;
+            uint64_t* out = p.part_keys + (q * (EW * p.n_splits) + EW * blockIdx.y + half) * KP;
 #pragma unroll
             for (int j = 0; j < KP; j++) out[j] = (top.i[j] == IDX_INVALID) ? KEY_SENTINEL : make_key(top.v[j], top.i[j]);
         }
@@ -849,11 +859,11 @@ static uint32_t pick_splits(uint64_t q_tiles, uint64_t n_tiles_db, int requested
     return best;
 }
 
-template <int KIND, int KP, int MET, bool TS>
+template <int KIND, int KP, int MET, bool TS, int EW = 2>
 static int launch_tc(const CUtensorMap& tmq, const CUtensorMap& tmx, const tc::Params& p, dim3 grid, size_t smem, cudaStream_t s) {
-    auto kern = tc::flat_tc_kernel<KIND, KP, MET, TS>;
+    auto kern = tc::flat_tc_kernel<KIND, KP, MET, TS, false, EW>;
     ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    kern<<<grid, tc::NUM_THREADS, smem, s>>>(tmq, tmx, p);
+    kern<<<grid, 64 + EW * 128, smem, s>>>(tmq, tmx, p);
     ANNB_CUDA_CHECK(cudaGetLastError());
     return ANNB_OK;
 }
@@ -919,7 +929,10 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     stages = std::min<uint32_t>(stages, 8);
     const size_t smem = q_smem + static_cast<size_t>(stages) * nb * tc::SLAB_TILE + fixed;
 
-    ANNB_TRY(st->part.ensure(nq * 2 * splits * static_cast<uint64_t>(kprime) * 8));
+    // epilogue warps per TMEM lane quarter: the int8 and bf16 kernels (few MMAs per tile, epilogue-paced) run four, k' = 16 only
+    // (a k' = 32 list does not fit the 112-register budget of 18 warps); option tc_epi_warps = 2 forces the narrow layout
+    const uint32_t ew = (kind != tc::KIND_TF32X3 && ts && kprime == 16 && ix->opt_tc_epi_warps != 2) ? 4u : 2u;
+    ANNB_TRY(st->part.ensure(nq * ew * splits * static_cast<uint64_t>(kprime) * 8));
     ANNB_TRY(st->gtau.ensure(static_cast<uint64_t>(nq_pad) * 4));
     ANNB_CUDA_CHECK(cudaMemsetAsync(st->gtau.p, 0xFF, static_cast<uint64_t>(nq_pad) * 4, s));
     tc::Params p{};
@@ -934,20 +947,23 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
         int rc;
         const bool l2 = ix->metric == ANNB_L2;
 #define ANNB_TC_LAUNCH(KIND_, KP_, TS_) (l2 ? launch_tc<KIND_, KP_, MET_L2, TS_>(tmq, st->tm_x, p, grid, smem, s) : launch_tc<KIND_, KP_, MET_COS, TS_>(tmq, st->tm_x, p, grid, smem, s))
-        if (kind == tc::KIND_I8) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_I8, 16, true) : ANNB_TC_LAUNCH(tc::KIND_I8, 32, true);
+#define ANNB_TC_LAUNCH4(KIND_) (l2 ? launch_tc<KIND_, 16, MET_L2, true, 4>(tmq, st->tm_x, p, grid, smem, s) : launch_tc<KIND_, 16, MET_COS, true, 4>(tmq, st->tm_x, p, grid, smem, s))
+        if (ew == 4) rc = kind == tc::KIND_I8 ? ANNB_TC_LAUNCH4(tc::KIND_I8) : ANNB_TC_LAUNCH4(tc::KIND_BF16);
+        else if (kind == tc::KIND_I8) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_I8, 16, true) : ANNB_TC_LAUNCH(tc::KIND_I8, 32, true);
         else if (kind == tc::KIND_TF32X3 && ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, true) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, true);
         else if (kind == tc::KIND_TF32X3) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, false) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, false);
         else if (ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_BF16, 16, true) : ANNB_TC_LAUNCH(tc::KIND_BF16, 32, true);
         else rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_BF16, 16, false) : ANNB_TC_LAUNCH(tc::KIND_BF16, 32, false);
 #undef ANNB_TC_LAUNCH
+#undef ANNB_TC_LAUNCH4
         if (ea && eb) { cudaEventRecord(eb, s); ix->timed.emplace_back(ea, eb); }
         ANNB_TRY(rc);
         ix->stat_launches++;
     }
     // ---- exact re-rank + merge ----
     tc::RerankParams r{};
-    r.part_keys = st->part.as<uint64_t>(); r.parts = 2 * splits; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out; r.gtau = st->gtau.as<uint32_t>();
-    r.nsort = next_pow2(std::max(2 * splits * kprime, 64u));
+    r.part_keys = st->part.as<uint64_t>(); r.parts = ew * splits; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out; r.gtau = st->gtau.as<uint32_t>();
+    r.nsort = next_pow2(std::max(ew * splits * kprime, 64u));
     r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.row_norms_i = ix->d_norms_i; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
     r.bf16_self = bf16_self; r.id_base = ix->id_base; r.out_ids = d_ids; r.out_dist = d_dist; r.out_counts = d_cnt;
     ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));

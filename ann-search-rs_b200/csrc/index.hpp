@@ -79,6 +79,7 @@ struct annb_index {
     int opt_tc_candidates = 0;
     int opt_tc_bf16_hybrid = 0; // flat tensor path, bf16 index + f32 queries: third query term in shared memory (SS-mode MMA) instead of TMEM
     int opt_tc_bf16_terms = 0;  // tensor paths, bf16 index + f32 queries: bf16 terms the query is split into (2 or 3); 0 = by metric (cosine 2, L2 3)
+    int opt_tc_epi_warps = 0;   // flat tensor path, bf16 / int8 kernels: epilogue warps per TMEM lane quarter (0 = auto: four for k' = 16, 2 = two)
     int opt_tc_ts = 1;         // tensor path, f32: keep the query operand in TMEM (TS-mode MMA)
     int opt_db_splits = 0;
     int opt_scan_parts = 0;

@@ -148,6 +148,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t r[32]) {
         : "r"(taddr)
         : "memory");
 }
+// 32 columns, completed (load + wait in one statement, see tmem_ld64_sync)
+__device__ __forceinline__ void tmem_ld32_sync(uint32_t taddr, uint32_t r[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
 // 64 consecutive columns of this warp's 32 lanes, *completed*: both loads and the tcgen05.wait::ld sit in one asm statement,
 // so the compiler cannot move, copy or spill the destination registers while the asynchronous loads are still in flight
 // (with separate statements it may, under register pressure, and the late-arriving data then lands in re-used registers).
@@ -246,17 +259,18 @@ struct TopList {
 // the group minima, column via selects -- no dynamically indexed registers, no local memory) and insert it.  Only if a
 // second value of the tile also beats the (now tighter) threshold does the thread fall back to the bulk path: stash
 // the 64 values in local memory and walk the groups that hold candidates.
-template <int KP>
-__device__ __forceinline__ void select_from_tile(TopList<KP>& top, float& tau, const float (&v)[64], const float (&gm)[8], float m, uint32_t col0,
-                                                 float (&scratch)[64]) {
+template <int KP, int NV = 64>
+__device__ __forceinline__ void select_from_tile(TopList<KP>& top, float& tau, const float (&v)[NV], const float (&gm)[NV / 8], float m, uint32_t col0,
+                                                 float (&scratch)[NV]) {
+    constexpr int NG = NV / 8;
     uint32_t gs = 0;
 #pragma unroll
-    for (int g = 7; g >= 0; g--) gs = (gm[g] == m) ? static_cast<uint32_t>(g) : gs;   // lowest group holding the minimum
+    for (int g = NG - 1; g >= 0; g--) gs = (gm[g] == m) ? static_cast<uint32_t>(g) : gs;   // lowest group holding the minimum
     float s8[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) s8[j] = v[j];
 #pragma unroll
-    for (int g = 1; g < 8; g++) {
+    for (int g = 1; g < NG; g++) {
         const bool here = gs == static_cast<uint32_t>(g);
 #pragma unroll
         for (int j = 0; j < 8; j++) s8[j] = here ? v[g * 8 + j] : s8[j];
@@ -269,16 +283,16 @@ __device__ __forceinline__ void select_from_tile(TopList<KP>& top, float& tau, c
     // second-best value of the tile: other groups' minima, and the minimum's own group without it
     float m2 = INFINITY;
 #pragma unroll
-    for (int g = 0; g < 8; g++) m2 = fminf(m2, gs == static_cast<uint32_t>(g) ? INFINITY : gm[g]);
+    for (int g = 0; g < NG; g++) m2 = fminf(m2, gs == static_cast<uint32_t>(g) ? INFINITY : gm[g]);
 #pragma unroll
     for (int j = 0; j < 8; j++) m2 = fminf(m2, js == static_cast<uint32_t>(j) ? INFINITY : s8[j]);
     if (m2 < tau) {
         const uint32_t done = gs * 8 + js;
 #pragma unroll
-        for (int j = 0; j < 64; j++) scratch[j] = v[j];
+        for (int j = 0; j < NV; j++) scratch[j] = v[j];
         uint32_t gmask = 0;
 #pragma unroll
-        for (int g = 0; g < 8; g++) gmask |= (gm[g] < tau || gs == static_cast<uint32_t>(g)) ? (1u << g) : 0u;
+        for (int g = 0; g < NG; g++) gmask |= (gm[g] < tau || gs == static_cast<uint32_t>(g)) ? (1u << g) : 0u;
         while (gmask) {
             const int g = __ffs(gmask) - 1;
             gmask &= gmask - 1;
