@@ -47,7 +47,6 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     constexpr int NA = (KIND == KIND_TF32X3) ? 2 : (KIND == KIND_I8 ? 1 : 3);  // stacked query pieces
     constexpr int NB = (KIND == KIND_TF32X3) ? 2 : 1;  // stacked database pieces
     constexpr int ELEM = (KIND == KIND_TF32X3) ? 4 : (KIND == KIND_I8 ? 1 : 2);
-    static_assert(KIND != KIND_I8 || TS, "the int8 kernel keeps its queries in TMEM");
     constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;      // 32 tf32 / 64 bf16 per slab row
     constexpr int KSTEPS = 4;                          // 128 B / 32 B per UMMA K step (8 tf32 / 16 bf16)
     constexpr int NV = BN / EW;                        // columns per epilogue warp and tile
@@ -919,9 +918,9 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     const uint32_t nb = kind == tc::KIND_TF32X3 ? 2 : 1;
     // query operand resident in TMEM (TS-mode MMA) when its pieces fit their column budget (bf16 terms: 64 columns each)
     const uint32_t bf16_piece_cols = kp > 128 ? 128u : 64u;
-    const bool ts = kind == tc::KIND_I8 || (ix->opt_tc_ts != 0 && (kind != tc::KIND_BF16 || na * bf16_piece_cols <= 256));
+    const bool ts = ix->opt_tc_ts != 0 && (kind != tc::KIND_BF16 || na * bf16_piece_cols <= 256);
     const bool hyb = ts && kind == tc::KIND_BF16 && na == 3 && ix->opt_tc_bf16_hybrid != 0;
-    const size_t q_smem = ts ? (hyb ? static_cast<size_t>(st->nslab) * tc::SLAB_TILE : 0) : static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * st->nslab * tc::SLAB_TILE;
+    const size_t q_smem = ts ? (hyb ? static_cast<size_t>(st->nslab) * tc::SLAB_TILE : 0) : static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : (kind == tc::KIND_I8 ? 1 : 3)) * st->nslab * tc::SLAB_TILE;
     const size_t fixed = 256 /*barriers*/ + 8 * 64 * 4 /*per-warp row constants*/;
     const size_t budget = 227 * 1024;
     if (q_smem + fixed + nb * tc::SLAB_TILE > budget) { set_last_error("tensor path: query tile too large for shared memory"); return ANNB_ERR_UNSUPPORTED; }
@@ -931,7 +930,9 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
 
     // epilogue warps per TMEM lane quarter: the int8 and bf16 kernels (few MMAs per tile, epilogue-paced) run four, k' = 16 only
     // (a k' = 32 list does not fit the 112-register budget of 18 warps); option tc_epi_warps = 2 forces the narrow layout
-    const uint32_t ew = (kind != tc::KIND_TF32X3 && ts && kprime == 16 && ix->opt_tc_epi_warps != 2) ? 4u : 2u;
+    // (measured: four epilogue warps per quarter are SLOWER -- bf16 4.84 -> 5.29 ms, int8 3.15 -> 3.80 ms on 1M x 128: the epilogue
+    // is bound by the 64 B / cycle TMEM read path, not by latency; kept behind option tc_epi_warps = 4)
+    const uint32_t ew = (kind != tc::KIND_TF32X3 && ts && kprime == 16 && ix->opt_tc_epi_warps == 4) ? 4u : 2u;
     ANNB_TRY(st->part.ensure(nq * ew * splits * static_cast<uint64_t>(kprime) * 8));
     ANNB_TRY(st->gtau.ensure(static_cast<uint64_t>(nq_pad) * 4));
     ANNB_CUDA_CHECK(cudaMemsetAsync(st->gtau.p, 0xFF, static_cast<uint64_t>(nq_pad) * 4, s));
@@ -949,7 +950,8 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
 #define ANNB_TC_LAUNCH(KIND_, KP_, TS_) (l2 ? launch_tc<KIND_, KP_, MET_L2, TS_>(tmq, st->tm_x, p, grid, smem, s) : launch_tc<KIND_, KP_, MET_COS, TS_>(tmq, st->tm_x, p, grid, smem, s))
 #define ANNB_TC_LAUNCH4(KIND_) (l2 ? launch_tc<KIND_, 16, MET_L2, true, 4>(tmq, st->tm_x, p, grid, smem, s) : launch_tc<KIND_, 16, MET_COS, true, 4>(tmq, st->tm_x, p, grid, smem, s))
         if (ew == 4) rc = kind == tc::KIND_I8 ? ANNB_TC_LAUNCH4(tc::KIND_I8) : ANNB_TC_LAUNCH4(tc::KIND_BF16);
-        else if (kind == tc::KIND_I8) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_I8, 16, true) : ANNB_TC_LAUNCH(tc::KIND_I8, 32, true);
+        else if (kind == tc::KIND_I8 && ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_I8, 16, true) : ANNB_TC_LAUNCH(tc::KIND_I8, 32, true);
+        else if (kind == tc::KIND_I8) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_I8, 16, false) : ANNB_TC_LAUNCH(tc::KIND_I8, 32, false);
         else if (kind == tc::KIND_TF32X3 && ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, true) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, true);
         else if (kind == tc::KIND_TF32X3) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, false) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, false);
         else if (ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_BF16, 16, true) : ANNB_TC_LAUNCH(tc::KIND_BF16, 32, true);
