@@ -267,7 +267,7 @@ static int enqueue_status_read(annb_index* ix, const CoreState& cs, cudaStream_t
     return ANNB_OK;
 }
 static bool wants_status(const annb_index* ix, const CoreState& cs) {
-    return cs.routed || (cs.tensor && ix->opt_cert_fallback && ix->opt_cert_eps != 0.f);
+    return cs.routed || (cs.tensor && ix->opt_cert_fallback && ix->opt_cert_eps != 0.f && ix->shard_bound == nullptr);
 }
 
 // Calls on one handle share its scratch buffers; the mutex orders the host side, this orders the device side when
@@ -652,7 +652,7 @@ static int run_batch(annb_index* ix, bool ivf, const PreparedQueries& pq, uint64
             ix->stat_probed += static_cast<int64_t>(h.probed);
             ix->stat_scanned_local += static_cast<int64_t>(h.local);
         }
-        const uint32_t n_unc = (cs.tensor && ix->opt_cert_fallback && ix->opt_cert_eps != 0.f) ? h.n_unc : 0u;
+        const uint32_t n_unc = (cs.tensor && ix->opt_cert_fallback && ix->opt_cert_eps != 0.f && ix->shard_bound == nullptr) ? h.n_unc : 0u;
         ix->stat_uncertified = cs.tensor ? static_cast<int64_t>(h.n_unc) : 0;
         if (n_unc == 0) return ANNB_OK;
         if (ivf) ANNB_TRY(ivf_fallback(ix, pq, k, nprobe, n_unc, preset_probes ? preset_probes : ix->s_probes.as<uint32_t>(),
@@ -1473,6 +1473,100 @@ int annb_ivf_search_probes_dev(const annb_index* index, const float* d_queries, 
                            d_out_counts ? d_out_counts + b0 : nullptr, s, ix->opt_async_dev == 0, []() -> int { return ANNB_OK; },
                            d_probes + b0 * probe_pitch, d_n_probes + b0, probe_pitch));
     }
+    return mark_call_done(ix, s);
+}
+
+// Shard-mode searches (see include/annb200.h): as the _dev searches, but the coverage certificate is left to the caller, who
+// knows the merged result: d_out_bound[q] = the distance below which no row of this shard that was NOT re-ranked can lie
+// (+inf where every candidate was re-ranked, or the shard ran on the exact kernels).  Nothing is recomputed locally, and
+// with preset probes nothing is read back: the call is asynchronous.
+static __global__ void fill_f32_kernel(float* __restrict__ p, uint64_t n, float v) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+static int shard_search(annb_index* ix, bool ivf, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe, const uint32_t* d_probes,
+                        const uint32_t* d_n_probes, uint32_t probe_pitch, uint64_t* d_out_ids, float* d_out_dist, float* d_out_bound, void* stream) {
+    if (!ix || ix->is_ivf != ivf || ix->multi) return fail(ANNB_ERR_INVALID_ARGUMENT, ivf ? "not a (single-device) IVF index" : "not a (single-device) flat index");
+    if (dim != ix->dim) return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(ix->dim));
+    if (!d_queries || !d_out_ids || !d_out_bound || k == 0 || (ivf && (!d_probes || !d_n_probes || probe_pitch == 0))) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / k == 0 / zero pitch");
+    ANNB_DEVICE(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ANNB_TRY(order_after_previous(ix, s));
+    fill_f32_kernel<<<grid_for(nq, 256, 1u << 30), 256, 0, s>>>(d_out_bound, nq, INFINITY);   // exact kernels re-rank nothing: their rows are complete
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    struct Reset { annb_index* ix; ~Reset() { ix->shard_bound = nullptr; } } reset{ix};
+    for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
+        const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
+        PreparedQueries pq;
+        ANNB_TRY(prepare_external(ix, d_queries + b0 * dim, nb, &pq, s));
+        ix->shard_bound = d_out_bound + b0;
+        ANNB_TRY(run_batch(ix, ivf, pq, nb, k, nprobe, d_out_ids + b0 * k, d_out_dist ? d_out_dist + b0 * k : nullptr, nullptr, s, false,
+                           []() -> int { return ANNB_OK; }, ivf ? d_probes + b0 * probe_pitch : nullptr, ivf ? d_n_probes + b0 : nullptr, probe_pitch));
+    }
+    return mark_call_done(ix, s);
+}
+
+int annb_flat_search_shard_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint64_t* d_out_ids,
+                               float* d_out_dist, float* d_out_bound, void* stream) {
+    return shard_search(const_cast<annb_index*>(index), false, d_queries, nq, dim, k, 0, nullptr, nullptr, 0, d_out_ids, d_out_dist, d_out_bound, stream);
+}
+
+int annb_ivf_search_probes_shard_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,
+                                     const uint32_t* d_probes, const uint32_t* d_n_probes, uint32_t probe_pitch, uint64_t* d_out_ids, float* d_out_dist,
+                                     float* d_out_bound, void* stream) {
+    return shard_search(const_cast<annb_index*>(index), true, d_queries, nq, dim, k, nprobe, d_probes, d_n_probes, probe_pitch, d_out_ids, d_out_dist,
+                        d_out_bound, stream);
+}
+
+// queries whose merged k-th distance does not lie strictly below this shard's bound
+static __global__ void shard_check_kernel(const float* __restrict__ bound, const float* __restrict__ merged_dist, uint64_t nq, uint32_t k,
+                                          uint32_t* __restrict__ uncert) {
+    const uint64_t q = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (q >= nq) return;
+    const float dk = merged_dist[q * k + (k - 1)];      // +inf where fewer than k rows were found at all
+    if (!(bound[q] > dk) && bound[q] != INFINITY) uncert[1 + atomicAdd(uncert, 1u)] = static_cast<uint32_t>(q);
+}
+
+int annb_shard_check_dev(annb_index* ix, const float* d_bound, const float* d_merged_dist, uint64_t nq, uint32_t k, uint32_t* out_count, void* stream) {
+    if (!ix || !d_bound || !d_merged_dist || !out_count || k == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument / k == 0");
+    if (nq > QUERY_BATCH) return fail(ANNB_ERR_UNSUPPORTED, "shard check: at most 16384 queries per call");
+    *out_count = 0;
+    ANNB_DEVICE(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ANNB_TRY(order_after_previous(ix, s));
+    ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
+    shard_check_kernel<<<grid_for(nq, 256, 1u << 30), 256, 0, s>>>(d_bound, d_merged_dist, nq, k, ix->s_uncert.as<uint32_t>());
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    HostStatus* h = reinterpret_cast<HostStatus*>(ix->h_status);
+    ANNB_CUDA_CHECK(cudaMemcpyAsync(&h->n_unc, ix->s_uncert.p, 4, cudaMemcpyDeviceToHost, s));
+    ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+    *out_count = h->n_unc;
+    ix->stat_uncertified = h->n_unc;
+    return mark_call_done(ix, s);
+}
+
+int annb_shard_refine_dev(annb_index* ix, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe, const uint32_t* d_probes,
+                          const uint32_t* d_n_probes, uint32_t probe_pitch, uint64_t* d_ids, float* d_dist, void* stream) {
+    if (!ix || ix->multi || !d_queries || !d_ids || k == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument / k == 0");
+    if (dim != ix->dim) return fail(ANNB_ERR_DIMENSION_MISMATCH, "query dim " + std::to_string(dim) + " != index dim " + std::to_string(ix->dim));
+    if (ix->is_ivf && (!d_probes || !d_n_probes || probe_pitch == 0)) return fail(ANNB_ERR_INVALID_ARGUMENT, "IVF shard: probe lists required");
+    if (nq > QUERY_BATCH) return fail(ANNB_ERR_UNSUPPORTED, "shard refine: at most 16384 queries per call");
+    ANNB_DEVICE(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ANNB_TRY(order_after_previous(ix, s));
+    HostStatus* h = reinterpret_cast<HostStatus*>(ix->h_status);
+    ANNB_CUDA_CHECK(cudaMemcpyAsync(&h->n_unc, ix->s_uncert.p, 4, cudaMemcpyDeviceToHost, s));
+    ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+    const uint32_t n_unc = h->n_unc;
+    if (n_unc == 0) return ANNB_OK;
+    PreparedQueries pq;
+    ANNB_TRY(prepare_external(ix, d_queries, nq, &pq, s));
+    if (ix->is_ivf) ANNB_TRY(ivf_fallback(ix, pq, k, nprobe, n_unc, d_probes, d_n_probes, probe_pitch, d_ids, d_dist, nullptr, s));
+    else ANNB_TRY(flat_fallback(ix, pq, k, n_unc, d_ids, d_dist, nullptr, s));
     return mark_call_done(ix, s);
 }
 

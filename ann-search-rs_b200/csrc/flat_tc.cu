@@ -972,7 +972,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
     r.cert_eps = tc_cert_eps(ix, kind, kp, na, false);
     { uint32_t b; std::memcpy(&b, &r.cert_eps, 4); ix->stat_cert_eps_bits = b; }
-    r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
+    r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1; r.out_bound = ix->shard_bound;
     const bool cos = ix->metric == ANNB_COSINE;
     int rc;
     if (ix->dtype == ANNB_SQ8) rc = cos ? launch_rerank<2, QT_I8, MET_COS>(r, s) : launch_rerank<2, QT_I8, MET_L2>(r, s);

@@ -109,6 +109,7 @@ struct annb_index {
     int opt_cert_fallback = 1;     // re-run uncertified queries on the exact CUDA-core path
     mutable int64_t stat_fallback_queries = 0;  // cumulative
     mutable int64_t stat_cert_eps_bits = 0;     // f32 bit pattern of the error bound the last tensor-path certificate used
+    float* shard_bound = nullptr;  // set (under mu) for the duration of a shard-mode search: the re-rank kernel reports per-query bounds there
     void* h_status = nullptr;      // pinned host block the status words of a batch are read back into (api.cu HostStatus)
     cudaEvent_t last_event = nullptr;   // end of the last call that used the scratch buffers, and the stream it ran on
     bool last_event_valid = false;

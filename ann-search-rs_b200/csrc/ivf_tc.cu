@@ -576,7 +576,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
     r.cert_eps = tc_cert_eps(ix, st->kind, st->kp_elems, bf16_terms, st->kind == tc::KIND_TF32X3);
     { uint32_t b; std::memcpy(&b, &r.cert_eps, 4); ix->stat_cert_eps_bits = b; }
-    r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1;
+    r.xnorm_max = ix->tc_xnorm_max; r.uncert_count = ix->s_uncert.as<uint32_t>(); r.uncert_list = ix->s_uncert.as<uint32_t>() + 1; r.out_bound = ix->shard_bound;
     int rc;
     if (ix->dtype == ANNB_SQ8) rc = l2 ? launch_ivf_rerank<2, MET_L2>(r, s) : launch_ivf_rerank<2, MET_COS>(r, s);
     else if (ix->dtype == ANNB_F32) rc = l2 ? launch_ivf_rerank<0, MET_L2>(r, s) : launch_ivf_rerank<0, MET_COS>(r, s);

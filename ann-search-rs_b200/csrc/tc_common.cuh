@@ -457,6 +457,7 @@ struct RerankParams {
     uint32_t* uncert_count;      // number of queries that could not be certified
     uint32_t* uncert_list;       // their indices (capacity nq)
     const uint32_t* gtau;        // optional [nq]: final shared pruning threshold of the scan (ordered image); bounds the k'-th merged value
+    float* out_bound;            // optional [nq] (shard mode): distance bound of the rows that were not re-ranked, instead of a local verdict
     uint64_t* out_ids;
     float* out_dist;
     uint32_t* out_counts;
@@ -635,35 +636,43 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     };
     // coverage test: every row that was not re-ranked has an approximate value >= a_thr; is the k-th exact distance safely
     // below the distance that value stands for?  (one thread, f64: the map itself must not add rounding of its own)
-    auto covered = [&](float a_thr, float dk) -> bool {
+    // bound_of(a): every row whose approximate value is >= a has a reference-order distance ABOVE this bound
+    auto bound_of = [&](float a_thr) -> double {
         const double qn2 = (s_qn2w[0] + s_qn2w[1]) + (s_qn2w[2] + s_qn2w[3]);
         if (MET == MET_L2) {
             // approx value = |x|^2 - 2 q.x = dist - |q|^2 ; error <= eps * (|q| + |x|max)^2
             const double s = sqrt(qn2) + static_cast<double>(p.xnorm_max);
-            return (static_cast<double>(a_thr) + qn2 - static_cast<double>(p.cert_eps) * s * s) > static_cast<double>(dk);
+            return static_cast<double>(a_thr) + qn2 - static_cast<double>(p.cert_eps) * s * s;
         }
         // approx value = -q.x / |x| = (dist - 1) * |q| with the reference's own |q| (sequential fold, bf16-rounded for
         // bf16 self queries; sqrt of the integer norm for SQ8) ; error <= eps
         double qn = sqrt(qn2);
         if constexpr (QT != QT_I8) qn = static_cast<double>(s_qn);
-        return qn > 0.0 ? ((static_cast<double>(a_thr) / qn + 1.0 - static_cast<double>(p.cert_eps)) > static_cast<double>(dk)) : true;
+        return qn > 0.0 ? (static_cast<double>(a_thr) / qn + 1.0 - static_cast<double>(p.cert_eps)) : static_cast<double>(INFINITY);
     };
+    auto covered = [&](float a_thr, float dk) -> bool { return bound_of(a_thr) > static_cast<double>(dk); };
     __shared__ int s_extend;
     exact_range(p.kp);
     if (threadIdx.x == 0) s_extend = 0;
     __syncthreads();
     if (threadIdx.x < 32) bitonic_sort_keys<false>(exact, 64, threadIdx.x, 32);
     __syncthreads();
-    const bool certify = p.uncert_count != nullptr && p.cert_eps > 0.f;
+    // Shard mode (out_bound != nullptr): the certificate is not decided here.  The kernel reports the bound below which
+    // this shard's un-re-ranked rows cannot lie; the caller tests it against the k-th distance of the MERGED result
+    // (annb_shard_check_dev) -- a shard holding only far lists of a query need not be exact about candidates that cannot
+    // reach the global top-k.
+    const bool certify = (p.uncert_count != nullptr || p.out_bound != nullptr) && p.cert_eps > 0.f;
+    if (threadIdx.x == 0 && p.out_bound != nullptr) p.out_bound[q] = INFINITY;
     if (threadIdx.x == 0 && certify) {
         const uint64_t a_key = keys[p.kp - 1];                       // k'-th merged approximate key (sentinel: every row was re-ranked)
         const uint64_t d_key = exact[p.k_eff - 1];                   // k-th exact key (sentinel: fewer than k rows exist)
+        if (key_idx(a_key) != IDX_INVALID && p.out_bound != nullptr) p.out_bound[q] = __double2float_rd(bound_of(key_dist(a_key)));
         if (key_idx(a_key) != IDX_INVALID && key_idx(d_key) != IDX_INVALID && !covered(key_dist(a_key), key_dist(d_key))) {
             // Second chance before the exact fallback: the compacted candidate set holds every scanned row whose value is
             // at or below the query's final pruning threshold G (every rejected row is >= G, which is usually well above
             // the k'-th merged value).  Re-rank up to 64 of them and test against G (or the 65th value).
             if (p.gtau != nullptr && n_cand > p.kp) s_extend = 1;
-            else p.uncert_list[atomicAdd(p.uncert_count, 1u)] = static_cast<uint32_t>(q);
+            else if (p.out_bound == nullptr) p.uncert_list[atomicAdd(p.uncert_count, 1u)] = static_cast<uint32_t>(q);
         }
     }
     __syncthreads();
@@ -674,10 +683,11 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         __syncthreads();
         if (threadIdx.x == 0) {
             const uint64_t d_key = exact[p.k_eff - 1];
-            bool ok = true;
-            if (n_cand > 64) ok = covered(key_dist(keys[64]), key_dist(d_key));
-            else if (p.gtau[q] != 0xFFFFFFFFu) ok = covered(ordered_to_f32(p.gtau[q]), key_dist(d_key));   // 0xFFFFFFFF: nothing was ever pruned
-            if (!ok) p.uncert_list[atomicAdd(p.uncert_count, 1u)] = static_cast<uint32_t>(q);
+            double b = static_cast<double>(INFINITY);
+            if (n_cand > 64) b = bound_of(key_dist(keys[64]));
+            else if (p.gtau[q] != 0xFFFFFFFFu) b = bound_of(ordered_to_f32(p.gtau[q]));   // 0xFFFFFFFF: nothing was ever pruned
+            if (p.out_bound != nullptr) p.out_bound[q] = __double2float_rd(b);
+            else if (!(b > static_cast<double>(key_dist(d_key)))) p.uncert_list[atomicAdd(p.uncert_count, 1u)] = static_cast<uint32_t>(q);
         }
     }
     uint32_t valid = 0;

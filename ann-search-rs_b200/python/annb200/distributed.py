@@ -105,15 +105,19 @@ class ShardedSearch:
     """One sharded search step per call, one process per GPU.  `index` is this rank's shard -- a row range
     (flat, built with id_base = first row) or a list range (IVF) -- and ranks hold ascending ranges in rank order.
 
-        flat : search the shard for the whole batch -> ONE all-gather of the interleaved [ids | distances] blocks
-               (12 * nq * k bytes per rank) -> annb_merge_shards_dev.
+        flat : shard-mode search of the whole batch (annb_flat_search_shard_dev) -> ONE all-gather of the interleaved
+               [ids | distances] blocks (12 * nq * k bytes per rank) -> annb_merge_shards_dev.
         IVF  : every rank ranks the centroids for ITS slice of the batch (annb_ivf_route_dev), ONE all-gather of the
-               slices' [probe lists | probe counts] blocks, every rank scans its own lists for the whole batch
-               (annb_ivf_search_probes_dev), then the same result exchange.
+               slices' [probe lists | probe counts | status] blocks, every rank scans its own lists for the whole batch
+               (annb_ivf_search_probes_shard_dev), then the same result exchange.
+        certificate : shards do not certify their own k-th neighbour -- it is usually irrelevant to the merged top-k --
+               but report a bound; after the merge every rank tests its bound against the merged k-th distances
+               (annb_shard_check_dev), one 4-byte all-reduce tells all ranks whether anybody has to refine
+               (annb_shard_refine_dev: exact kernels for the listed queries), and only then the exchange is repeated.
 
     Everything is enqueued on `stream` (default: torch's current stream), collectives included.  A rank whose library
-    call fails still enters every collective of the step with an error mark in its block; all ranks raise together
-    afterwards instead of leaving the others blocked in NCCL."""
+    call fails still enters every collective of the step; the verdict all-reduce carries the error, and all ranks raise
+    together instead of leaving the others blocked in NCCL."""
 
     def __init__(self, index, nq: int, dim: int, k: int, nprobe: int = 0, group=None, device=None):
         import torch
@@ -129,6 +133,9 @@ class ShardedSearch:
         self.dist = self.mine[nq * k * 8:nq * k * 12].view(torch.float32).view(nq, k)
         self.out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
         self.out_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        self.bound = torch.empty((nq,), dtype=torch.float32, device=dev)
+        self.verdict = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.refined_queries = 0          # cumulative: queries this rank recomputed exactly after the merged check
         self.is_ivf = bool(index.info().is_ivf)
         if self.is_ivf:
             self.pitch = probe_pitch(nprobe or int(max(1, index.info().nlist ** 0.5)))
@@ -139,20 +146,17 @@ class ShardedSearch:
             self.all_route = torch.empty((self.world * self.route_words,), dtype=torch.int32, device=dev)
             self.probes = torch.empty((self.world * self.per, self.pitch), dtype=torch.int32, device=dev)
             self.nprobes = torch.empty((self.world * self.per,), dtype=torch.int32, device=dev)
-        self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
 
-    def _raise_together(self, err):
-        """All ranks learn whether any of them failed (one tiny all-reduce, only on the error path of the caller)."""
-        import torch
+    def _exchange_and_merge(self, L, st):
         import torch.distributed as dist_
-        flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=self.dev)
-        dist_.all_reduce(flag, op=dist_.ReduceOp.MAX, group=self.group)
-        if int(flag.item()):
-            raise err if err is not None else RuntimeError("another rank failed in the sharded search step")
+        dist_.all_gather_into_tensor(self.gathered, self.mine, group=self.group)
+        return L.annb_merge_shards_dev(self.gathered.data_ptr(), self.block, self.nq * self.k * 8, self.world, self.nq, self.k, self.out_ids.data_ptr(),
+                                       self.out_dist.data_ptr(), None, st)
 
-    def __call__(self, queries, stream=None, check: bool = True):
-        """queries: [nq, dim] float32 CUDA tensor (the whole batch, on every rank).  Returns (ids, dist) on the device.
-        `check`: agree on success across ranks before returning (one 4-byte all-reduce)."""
+    def __call__(self, queries, stream=None):
+        """queries: [nq, dim] float32 CUDA tensor (the whole batch, on every rank).  Returns (ids, dist) on the device."""
+        import ctypes as C
+
         import torch
         import torch.distributed as dist_
 
@@ -162,38 +166,61 @@ class ShardedSearch:
         st = st_obj.cuda_stream
         nq, dim, k = self.nq, self.dim, self.k
         err = None
+
+        def failed(rc):
+            return AnnSearchError(rc, L.annb_last_error().decode("utf-8", "replace"))
+
         with torch.cuda.stream(st_obj):
             if self.is_ivf:
                 lo, hi = min(nq, self.rank * self.per), min(nq, (self.rank + 1) * self.per)
                 pw = self.per * self.pitch
-                self.my_route[pw + self.per:].zero_()
                 if hi > lo:
                     rc = L.annb_ivf_route_dev(self.index.handle, queries[lo:hi].data_ptr(), hi - lo, dim, k, self.nprobe, self.my_route.data_ptr(),
                                               self.my_route[pw:].data_ptr(), self.pitch, st)
-                    if rc != 0:   # e.g. Unsupported: a probe set did not fit the pitch -- mark the block, keep the collectives matched
-                        err = AnnSearchError(rc, L.annb_last_error().decode("utf-8", "replace"))
-                        self.my_route[pw + self.per:].fill_(1)
+                    if rc != 0:   # e.g. Unsupported: a probe set did not fit the pitch -- keep the collectives matched, raise at the verdict
+                        err = failed(rc)
                 dist_.all_gather_into_tensor(self.all_route, self.my_route, group=self.group)
                 blocks = self.all_route.view(self.world, self.route_words)
                 self.probes.view(self.world, pw).copy_(blocks[:, :pw])
                 self.nprobes.view(self.world, self.per).copy_(blocks[:, pw:pw + self.per])
                 if err is None:
-                    rc = L.annb_ivf_search_probes_dev(self.index.handle, queries.data_ptr(), nq, dim, k, self.nprobe, self.probes.data_ptr(),
-                                                      self.nprobes.data_ptr(), self.pitch, self.ids.data_ptr(), self.dist.data_ptr(), None, st)
-                    if rc != 0:
-                        err = AnnSearchError(rc, L.annb_last_error().decode("utf-8", "replace"))
+                    rc = L.annb_ivf_search_probes_shard_dev(self.index.handle, queries.data_ptr(), nq, dim, k, self.nprobe, self.probes.data_ptr(),
+                                                            self.nprobes.data_ptr(), self.pitch, self.ids.data_ptr(), self.dist.data_ptr(),
+                                                            self.bound.data_ptr(), st)
+                    err = failed(rc) if rc != 0 else None
             else:
-                rc = L.annb_flat_search_dev(self.index.handle, queries.data_ptr(), nq, dim, k, self.ids.data_ptr(), self.dist.data_ptr(), None, st)
-                if rc != 0:
-                    err = AnnSearchError(rc, L.annb_last_error().decode("utf-8", "replace"))
-            dist_.all_gather_into_tensor(self.gathered, self.mine, group=self.group)
+                rc = L.annb_flat_search_shard_dev(self.index.handle, queries.data_ptr(), nq, dim, k, self.ids.data_ptr(), self.dist.data_ptr(),
+                                                  self.bound.data_ptr(), st)
+                err = failed(rc) if rc != 0 else None
+            rc = self._exchange_and_merge(L, st)
+            if rc != 0 and err is None:
+                err = failed(rc)
+            # verdict: 0 = every shard's bound clears the merged k-th distances, 1 = somebody refines, 2 = somebody failed
+            count = C.c_uint32(0)
             if err is None:
-                rc = L.annb_merge_shards_dev(self.gathered.data_ptr(), self.block, nq * k * 8, self.world, nq, k, self.out_ids.data_ptr(),
-                                             self.out_dist.data_ptr(), None, st)
+                rc = L.annb_shard_check_dev(self.index.handle, self.bound.data_ptr(), self.out_dist.data_ptr(), nq, k, C.byref(count), st)
                 if rc != 0:
-                    err = AnnSearchError(rc, L.annb_last_error().decode("utf-8", "replace"))
-            if check or err is not None:
-                self._raise_together(err)
+                    err = failed(rc)
+            self.verdict.fill_(2 if err is not None else (1 if count.value else 0))
+            dist_.all_reduce(self.verdict, op=dist_.ReduceOp.MAX, group=self.group)
+            verdict = int(self.verdict.item())
+            if verdict == 2:
+                raise err if err is not None else RuntimeError("another rank failed in the sharded search step")
+            if verdict == 1:
+                if count.value:
+                    rc = L.annb_shard_refine_dev(self.index.handle, queries.data_ptr(), nq, dim, k, self.nprobe,
+                                                 self.probes.data_ptr() if self.is_ivf else None, self.nprobes.data_ptr() if self.is_ivf else None,
+                                                 self.pitch if self.is_ivf else 0, self.ids.data_ptr(), self.dist.data_ptr(), st)
+                    if rc != 0:
+                        err = failed(rc)
+                    self.refined_queries += int(count.value)
+                rc = self._exchange_and_merge(L, st)
+                if rc != 0 and err is None:
+                    err = failed(rc)
+                self.verdict.fill_(2 if err is not None else 0)
+                dist_.all_reduce(self.verdict, op=dist_.ReduceOp.MAX, group=self.group)
+                if int(self.verdict.item()) == 2:
+                    raise err if err is not None else RuntimeError("another rank failed in the sharded search step")
         return self.out_ids, self.out_dist
 
 

@@ -347,7 +347,7 @@ class Searcher:
         c, lib, annb200 = self.c, self.c.lib, self.c.annb
         sp = c.torch.cuda.current_stream().cuda_stream
         if self.sharded is not None:
-            self.sharded(self.dq, check=False)
+            self.sharded(self.dq)
             self.extra_launches += 1                   # the merge kernel
             return
         if self.ivf:
@@ -362,7 +362,7 @@ class Searcher:
         if self.sharded is not None:
             # one process per GPU: pinned host queries -> device, sharded step, merged result -> pinned host (no bounce through the host in between)
             self.dq.copy_(self.hq, non_blocking=True)
-            ids, dst = self.sharded(self.dq, check=False)
+            ids, dst = self.sharded(self.dq)
             self.h_ids.copy_(ids, non_blocking=True)
             self.h_dist.copy_(dst, non_blocking=True)
             c.torch.cuda.synchronize()

@@ -259,6 +259,31 @@ int annb_merge_shards_dev(const void* d_parts, uint64_t part_stride_bytes, uint6
                           uint64_t nq, uint32_t k, uint64_t* d_out_ids, float* d_out_dist, uint32_t* d_out_counts,
                           void* stream);
 
+/* Shard-mode searches: what a sharded deployment calls instead of annb_flat_search_dev / annb_ivf_search_probes_dev.  A
+ * shard cannot know the k-th distance of the merged result, and being exact about its own k-th neighbour is wasted work
+ * when that neighbour is far from the global top-k (a shard that holds only distant lists of a query sees densely
+ * packed, uncertifiable candidates).  So these calls never recompute anything locally: next to the shard's k rows they
+ * report d_out_bound[q], the distance below which no row of the shard that was NOT re-ranked exactly can lie (+inf where
+ * every candidate was re-ranked).  After the exchange and the merge,
+ *   annb_shard_check_dev  lists (inside the handle) the queries whose merged k-th distance is not strictly below this
+ *                         shard's bound -- only those could be missing a row of this shard -- and returns their number
+ *                         (one 4-byte read-back); and, if any shard reported any,
+ *   annb_shard_refine_dev recomputes exactly those queries on the exact kernels and overwrites their rows in the
+ *                         shard's result block, after which the exchange and the merge are repeated.
+ * With every bound above the merged k-th distance the result is provably the unsharded one.  At most 16384 queries per
+ * call for check / refine. */
+int annb_flat_search_shard_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k,
+                               uint64_t* d_out_ids, float* d_out_dist, float* d_out_bound, void* stream);
+int annb_ivf_search_probes_shard_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k,
+                                     uint32_t nprobe, const uint32_t* d_probes, const uint32_t* d_n_probes,
+                                     uint32_t probe_pitch, uint64_t* d_out_ids, float* d_out_dist, float* d_out_bound,
+                                     void* stream);
+int annb_shard_check_dev(annb_index* index, const float* d_bound, const float* d_merged_dist, uint64_t nq, uint32_t k,
+                         uint32_t* out_count, void* stream);
+int annb_shard_refine_dev(annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,
+                          const uint32_t* d_probes, const uint32_t* d_n_probes, uint32_t probe_pitch, uint64_t* d_ids,
+                          float* d_dist, void* stream);
+
 /* ------------------------------------------------------- several devices -- */
 
 /* One index over several GPUs of one box, driven from one process: the `device` argument of

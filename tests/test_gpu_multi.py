@@ -112,3 +112,88 @@ def test_multi_handle_errors_and_info(gpu):
     m.set_option("path", annb200.PATH_SIMT)
     ids, d, _ = m.query_batch(data[:10], 3)
     assert (ids[:, 0] == np.arange(10)).all() and m.get_stat("last_path") == annb200.PATH_SIMT
+
+
+@pytest.mark.parametrize("kind", ["flat", "ivf"])
+def test_shard_mode_certificate_against_the_merged_result(gpu, kind):
+    """The call sequence of a sharded deployment on ONE device (shards searched one after the other, which is what each
+    rank does concurrently): shard-mode searches report a bound instead of certifying locally, the bound is tested against
+    the MERGED k-th distances (annb_shard_check_dev), listed queries are recomputed exactly (annb_shard_refine_dev) and
+    merged again.  Result: the oracle's rows, and far fewer exact recomputations than local certification would need."""
+    import ctypes as C
+    import torch
+    lib = annb200.lib()
+    dev = torch.device("cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    data = datagen.correlated(120_000, 64, seed=31)
+    q = datagen.subsample_with_noise(data, 2000, seed=31)
+    nq, dim, k, shards = q.shape[0], 64, 10, 4
+    dq = torch.from_numpy(q).to(dev)
+    if kind == "flat":
+        ref = o.flat_search(o.build_flat(data, o.L2), q, k)
+        handles = []
+        for s in range(shards):
+            lo, hi = (s * data.shape[0]) // shards, ((s + 1) * data.shape[0]) // shards
+            handles.append(annb200.ExhaustiveIndexB200.new(data[lo:hi], annb200.L2, annb200.F32, id_base=lo))
+        probes = nprobes = None
+        pitch, nprobe = 0, 0
+    else:
+        nprobe = 16
+        ci = o.build_ivf(data, o.L2, nlist=256, kmeans_iters=4)
+        ref = o.ivf_search(ci, q, k, nprobe=nprobe)
+        from annb200 import distributed as D
+        handles = []
+        for (lb, le) in D.list_ranges(ci.offsets, shards):
+            r0, r1 = int(ci.offsets[lb]), int(ci.offsets[le])
+            handles.append(annb200.IvfIndexB200.from_parts(ci.vectors[r0:r1], ci.centroids, ci.offsets, ci.original_ids[r0:r1], ci.dtype, ci.metric,
+                                                           list_begin=lb, list_end=le, n_total=ci.n))
+        pitch = D.probe_pitch(nprobe)
+        probes = torch.empty((nq, pitch), dtype=torch.int32, device=dev)
+        nprobes = torch.empty((nq,), dtype=torch.int32, device=dev)
+        annb200._check(lib.annb_ivf_route_dev(handles[0].handle, dq.data_ptr(), nq, dim, k, nprobe, probes.data_ptr(), nprobes.data_ptr(), pitch, st))
+    block = ((nq * k * 12 + 255) // 256) * 256
+    gathered = torch.empty((shards * block,), dtype=torch.uint8, device=dev)
+    bounds = [torch.empty((nq,), dtype=torch.float32, device=dev) for _ in range(shards)]
+    m_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    m_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+
+    def slot(s):
+        b = gathered[s * block:(s + 1) * block]
+        return b.data_ptr(), b[nq * k * 8:].data_ptr()
+
+    for s, h in enumerate(handles):
+        h.set_option("path", annb200.PATH_TENSOR if kind == "flat" else annb200.PATH_AUTO)
+        ids_p, d_p = slot(s)
+        if kind == "flat":
+            annb200._check(lib.annb_flat_search_shard_dev(h.handle, dq.data_ptr(), nq, dim, k, ids_p, d_p, bounds[s].data_ptr(), st))
+        else:
+            annb200._check(lib.annb_ivf_search_probes_shard_dev(h.handle, dq.data_ptr(), nq, dim, k, nprobe, probes.data_ptr(), nprobes.data_ptr(), pitch,
+                                                                ids_p, d_p, bounds[s].data_ptr(), st))
+    annb200._check(lib.annb_merge_shards_dev(gathered.data_ptr(), block, nq * k * 8, shards, nq, k, m_ids.data_ptr(), m_d.data_ptr(), None, st))
+    refined = 0
+    for s, h in enumerate(handles):
+        cnt = C.c_uint32(0)
+        annb200._check(lib.annb_shard_check_dev(h.handle, bounds[s].data_ptr(), m_d.data_ptr(), nq, k, C.byref(cnt), st))
+        refined += cnt.value
+        if cnt.value:
+            ids_p, d_p = slot(s)
+            annb200._check(lib.annb_shard_refine_dev(h.handle, dq.data_ptr(), nq, dim, k, nprobe, None if probes is None else probes.data_ptr(),
+                                                     None if nprobes is None else nprobes.data_ptr(), pitch, ids_p, d_p, st))
+    if refined:
+        annb200._check(lib.annb_merge_shards_dev(gathered.data_ptr(), block, nq * k * 8, shards, nq, k, m_ids.data_ptr(), m_d.data_ptr(), None, st))
+    torch.cuda.synchronize()
+    assert_exact(m_ids.cpu().numpy(), m_d.cpu().numpy(), ref[0], ref[1], f"shard mode {kind}")
+    # local certification on the same shards, for comparison: how many queries each shard would have recomputed on its own
+    local = 0
+    out_i = torch.empty((nq, k), dtype=torch.int64, device=dev)
+    for s, h in enumerate(handles):
+        f0 = h.get_stat("fallback_queries")
+        if kind == "flat":
+            annb200._check(lib.annb_flat_search_dev(h.handle, dq.data_ptr(), nq, dim, k, out_i.data_ptr(), None, None, st))
+        else:
+            annb200._check(lib.annb_ivf_search_probes_dev(h.handle, dq.data_ptr(), nq, dim, k, nprobe, probes.data_ptr(), nprobes.data_ptr(), pitch,
+                                                          out_i.data_ptr(), None, None, st))
+        torch.cuda.synchronize()
+        local += h.get_stat("fallback_queries") - f0
+    print(f"\\n[shard mode {kind}] queries refined after the merged check: {refined}; recomputed under local certification: {local}")
+    assert refined <= local
