@@ -1548,6 +1548,58 @@ int annb_shard_check_dev(annb_index* ix, const float* d_bound, const float* d_me
     return mark_call_done(ix, s);
 }
 
+// The same test when every shard's bounds travelled with its result block (one process per GPU: the all-gather already
+// brought them): each rank evaluates ALL shards' bounds against the merged rows, so every rank derives the same
+// "somebody refines" verdict without another collective, and lists its own queries for annb_shard_refine_dev.
+static __global__ void shard_check_gathered_kernel(const uint8_t* __restrict__ parts_base, uint64_t stride, uint64_t bound_off, uint32_t parts,
+                                                   uint32_t my_part, const float* __restrict__ merged_dist, uint64_t nq, uint32_t k,
+                                                   uint32_t* __restrict__ uncert, uint32_t* __restrict__ any) {
+    const uint64_t q = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (q >= nq) return;
+    if (q == 0) {   // the int32 behind every shard's bounds is its status word: a failed shard poisons the step on every rank alike
+        for (uint32_t s = 0; s < parts; s++)
+            if (*reinterpret_cast<const int32_t*>(parts_base + s * stride + bound_off + nq * 4) != 0) atomicOr(any, 2u);
+    }
+    const float dk = merged_dist[q * k + (k - 1)];
+    bool some = false;
+    for (uint32_t s = 0; s < parts; s++) {
+        const float b = reinterpret_cast<const float*>(parts_base + s * stride + bound_off)[q];
+        const bool need = !(b > dk) && b != INFINITY;
+        some = some || need;
+        if (need && s == my_part) uncert[1 + atomicAdd(uncert, 1u)] = static_cast<uint32_t>(q);
+    }
+    if (some) atomicOr(any, 1u);
+}
+
+int annb_shard_check_gathered_dev(annb_index* ix, const void* d_parts, uint64_t part_stride_bytes, uint64_t bound_offset_bytes, uint32_t parts,
+                                  uint32_t my_part, const float* d_merged_dist, uint64_t nq, uint32_t k, uint32_t* out_mine, uint32_t* out_any,
+                                  void* stream) {
+    if (!ix || !d_parts || !d_merged_dist || !out_mine || !out_any || k == 0 || parts == 0 || my_part >= parts) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument / bad shape");
+    if ((part_stride_bytes & 3) || (bound_offset_bytes & 3)) return fail(ANNB_ERR_INVALID_ARGUMENT, "misaligned shard layout");
+    if (nq > QUERY_BATCH) return fail(ANNB_ERR_UNSUPPORTED, "shard check: at most 16384 queries per call");
+    *out_mine = 0;
+    *out_any = 0;
+    ANNB_DEVICE(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ANNB_TRY(order_after_previous(ix, s));
+    ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));
+    ANNB_TRY(ix->s_flags.ensure(64));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 4, s));
+    shard_check_gathered_kernel<<<grid_for(nq, 256, 1u << 30), 256, 0, s>>>(static_cast<const uint8_t*>(d_parts), part_stride_bytes, bound_offset_bytes, parts,
+                                                                          my_part, d_merged_dist, nq, k, ix->s_uncert.as<uint32_t>(), ix->s_flags.as<uint32_t>());
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    HostStatus* h = reinterpret_cast<HostStatus*>(ix->h_status);
+    ANNB_CUDA_CHECK(cudaMemcpyAsync(&h->n_unc, ix->s_uncert.p, 4, cudaMemcpyDeviceToHost, s));
+    ANNB_CUDA_CHECK(cudaMemcpyAsync(&h->overflow, ix->s_flags.p, 4, cudaMemcpyDeviceToHost, s));
+    ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+    *out_mine = h->n_unc;
+    *out_any = h->overflow;
+    ix->stat_uncertified = h->n_unc;
+    return mark_call_done(ix, s);
+}
+
 int annb_shard_refine_dev(annb_index* ix, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe, const uint32_t* d_probes,
                           const uint32_t* d_n_probes, uint32_t probe_pitch, uint64_t* d_ids, float* d_dist, void* stream) {
     if (!ix || ix->multi || !d_queries || !d_ids || k == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument / k == 0");

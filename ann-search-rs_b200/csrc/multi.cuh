@@ -85,7 +85,7 @@ struct annb_multi {
     std::vector<uint64_t> row0;                    // flat: first row of every shard (+ n at the end)
     std::vector<std::unique_ptr<annb::ShardWorker>> workers;
     // per-shard device buffers (grow-only; touched by the shard's worker only)
-    std::vector<annb::DevBuf> d_q, d_res, d_probes, d_nprobes;
+    std::vector<annb::DevBuf> d_q, d_res, d_probes, d_nprobes, d_bound, d_mdist;
     // first device: gather slots, merged result
     annb::DevBuf g_parts, g_ids, g_dist, g_cnt;
     cudaStream_t root_stream = nullptr;
@@ -148,7 +148,7 @@ static annb_index* multi_front(annb_multi* m, bool ivf) {
 
 static void multi_start_workers(annb_multi* m) {
     const size_t nd = m->devices.size();
-    m->d_q.resize(nd); m->d_res.resize(nd); m->d_probes.resize(nd); m->d_nprobes.resize(nd);
+    m->d_q.resize(nd); m->d_res.resize(nd); m->d_probes.resize(nd); m->d_nprobes.resize(nd); m->d_bound.resize(nd); m->d_mdist.resize(nd);
     for (size_t i = 0; i < nd; i++) {
         m->workers.emplace_back(new ShardWorker());
         m->workers.back()->device = m->devices[i];
@@ -160,7 +160,7 @@ static void multi_destroy(annb_multi* m) {
     if (!m) return;
     if (!m->workers.empty()) {
         multi_run_all(m, [m](size_t i) {
-            m->d_q[i].release(); m->d_res[i].release(); m->d_probes[i].release(); m->d_nprobes[i].release();
+            m->d_q[i].release(); m->d_res[i].release(); m->d_probes[i].release(); m->d_nprobes[i].release(); m->d_bound[i].release(); m->d_mdist[i].release();
             return ANNB_OK;
         });
     }
@@ -380,36 +380,70 @@ static int multi_search(annb_index* front, bool ivf, int mode, const float* quer
             }));
         }
         // ---- every device searches its shard for the whole batch; its result block lands in its gather slot ----
+        // External queries run in shard mode: no shard certifies its own k-th neighbour, every shard reports a bound that is
+        // tested against the merged result below.  Self queries (index dtype) keep the local certificate.
+        const bool shard_mode = mode == 0;
+        cudaStream_t rs = m->root_stream;
+        auto copy_block = [&](size_t i, cudaStream_t s) -> int {
+            ANNB_CUDA_CHECK(cudaMemcpyPeerAsync(gather + i * stride, root, m->d_res[i].p, m->devices[i], nb * k * 12ull, s));
+            return ANNB_OK;
+        };
         ANNB_TRY(multi_run_all(m, [&](size_t i) -> int {
             annb_index* ix = m->shards[i];
-            std::lock_guard<std::mutex> sl(ix->mu);
             cudaStream_t s = ix->stream;
             ANNB_TRY(m->d_res[i].ensure(stride));
             uint64_t* r_ids = m->d_res[i].as<uint64_t>();
             float* r_dist = reinterpret_cast<float*>(m->d_res[i].as<uint8_t>() + nb * k * 8ull);
-            auto copy_out = [&]() -> int {
-                ANNB_CUDA_CHECK(cudaMemcpyPeerAsync(gather + i * stride, root, m->d_res[i].p, m->devices[i], nb * k * 12ull, s));
-                return ANNB_OK;
-            };
             if (ix->n == 0) {   // a shard without vectors (more devices than lists): an all-sentinel block
                 ANNB_CUDA_CHECK(cudaMemsetAsync(m->d_res[i].p, 0xFF, nb * k * 8ull, s));
-                ANNB_TRY(copy_out());
+                ANNB_TRY(copy_block(i, s));
                 ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
                 return ANNB_OK;
             }
-            if (ivf) {
-                ix->stat_scanned = 0; ix->stat_probed = 0; ix->stat_scanned_local = 0;
-                ANNB_TRY(run_batch(ix, true, pqs[i], nb, k, nprobe, r_ids, r_dist, nullptr, s, true, copy_out, m->d_probes[i].as<uint32_t>(),
-                                   m->d_nprobes[i].as<uint32_t>(), pitch));
-            } else {
-                ANNB_TRY(run_batch(ix, false, pqs[i], nb, k, 0, r_ids, r_dist, nullptr, s, true, copy_out));
+            if (shard_mode) {
+                ANNB_TRY(m->d_bound[i].ensure(nb * 4ull));
+                ANNB_TRY(m->d_mdist[i].ensure(nb * k * 4ull));
+                if (ivf) ANNB_TRY(annb_ivf_search_probes_shard_dev(ix, m->d_q[i].as<float>(), nb, dim, k, nprobe, m->d_probes[i].as<uint32_t>(),
+                                                                   m->d_nprobes[i].as<uint32_t>(), pitch, r_ids, r_dist, m->d_bound[i].as<float>(), s));
+                else ANNB_TRY(annb_flat_search_shard_dev(ix, m->d_q[i].as<float>(), nb, dim, k, r_ids, r_dist, m->d_bound[i].as<float>(), s));
+                ANNB_TRY(copy_block(i, s));
+                ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+                return ANNB_OK;
             }
+            std::lock_guard<std::mutex> sl(ix->mu);
+            auto copy_out = [&]() -> int { return copy_block(i, s); };
+            ANNB_TRY(run_batch(ix, false, pqs[i], nb, k, 0, r_ids, r_dist, nullptr, s, true, copy_out));
             return mark_call_done(ix, s);
         }));
-        // ---- merge on the first device, one copy out ----
-        cudaStream_t rs = m->root_stream;
         ANNB_TRY(annb_merge_shards_dev(gather, stride, nb * k * 8ull, static_cast<uint32_t>(nd), nb, k, m->g_ids.as<uint64_t>(), m->g_dist.as<float>(),
                                        m->g_cnt.as<uint32_t>(), rs));
+        if (shard_mode) {
+            // the merged k-th distances go back to every device; a shard whose bound does not clear them recomputes those queries
+            // exactly and re-sends its block, and the merge is repeated (rare)
+            ANNB_CUDA_CHECK(cudaStreamSynchronize(rs));
+            std::vector<uint32_t> counts(nd, 0);
+            ANNB_TRY(multi_run_all(m, [&](size_t i) -> int {
+                annb_index* ix = m->shards[i];
+                if (ix->n == 0) return ANNB_OK;
+                cudaStream_t s = ix->stream;
+                ANNB_CUDA_CHECK(cudaMemcpyPeerAsync(m->d_mdist[i].p, m->devices[i], m->g_dist.p, root, nb * k * 4ull, s));
+                ANNB_TRY(annb_shard_check_dev(ix, m->d_bound[i].as<float>(), m->d_mdist[i].as<float>(), nb, k, &counts[i], s));
+                if (counts[i] == 0) return ANNB_OK;
+                uint64_t* r_ids = m->d_res[i].as<uint64_t>();
+                float* r_dist = reinterpret_cast<float*>(m->d_res[i].as<uint8_t>() + nb * k * 8ull);
+                ANNB_TRY(annb_shard_refine_dev(ix, m->d_q[i].as<float>(), nb, dim, k, nprobe, ivf ? m->d_probes[i].as<uint32_t>() : nullptr,
+                                               ivf ? m->d_nprobes[i].as<uint32_t>() : nullptr, pitch, r_ids, r_dist, s));
+                ANNB_TRY(copy_block(i, s));
+                ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+                return ANNB_OK;
+            }));
+            bool any = false;
+            for (uint32_t c : counts) any = any || c != 0;
+            if (any)
+                ANNB_TRY(annb_merge_shards_dev(gather, stride, nb * k * 8ull, static_cast<uint32_t>(nd), nb, k, m->g_ids.as<uint64_t>(),
+                                               m->g_dist.as<float>(), m->g_cnt.as<uint32_t>(), rs));
+        }
+        // ---- one copy out of the merged rows ----
         ANNB_CUDA_CHECK(cudaMemcpyAsync(out_ids + b0 * k, m->g_ids.p, nb * k * 8ull, cudaMemcpyDefault, rs));
         if (out_dist) ANNB_CUDA_CHECK(cudaMemcpyAsync(out_dist + b0 * k, m->g_dist.p, nb * k * 4ull, cudaMemcpyDefault, rs));
         if (out_counts) ANNB_CUDA_CHECK(cudaMemcpyAsync(out_counts + b0, m->g_cnt.p, nb * 4ull, cudaMemcpyDefault, rs));

@@ -66,9 +66,10 @@ def probe_pitch(nprobe: int) -> int:
 
 
 def shard_block_bytes(nq: int, k: int) -> int:
-    """Size of one shard's interleaved result block: [nq * k] int64 ids followed by [nq * k] float32 distances, padded to
-    256 bytes so every rank's slot of the gathered buffer stays aligned."""
-    return ((nq * k * 12 + 255) // 256) * 256
+    """Size of one shard's interleaved result block: [nq * k] int64 ids, [nq * k] float32 distances, [nq] float32 bounds of
+    the shard-mode certificate and one int32 status word, padded to 256 bytes so every rank's slot of the gathered buffer
+    stays aligned."""
+    return ((nq * k * 12 + nq * 4 + 4 + 255) // 256) * 256
 
 
 def pack_block(ids, dist):
@@ -133,8 +134,9 @@ class ShardedSearch:
         self.dist = self.mine[nq * k * 8:nq * k * 12].view(torch.float32).view(nq, k)
         self.out_ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
         self.out_dist = torch.empty((nq, k), dtype=torch.float32, device=dev)
-        self.bound = torch.empty((nq,), dtype=torch.float32, device=dev)
-        self.verdict = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.bound = self.mine[nq * k * 12:nq * k * 12 + nq * 4].view(torch.float32)          # travels with the block
+        self.status = self.mine[nq * k * 12 + nq * 4:nq * k * 12 + nq * 4 + 4].view(torch.int32)   # 1 = this rank's library call failed
+        self.status.zero_()
         self.refined_queries = 0          # cumulative: queries this rank recomputed exactly after the merged check
         self.is_ivf = bool(index.info().is_ivf)
         if self.is_ivf:
@@ -192,35 +194,33 @@ class ShardedSearch:
                 rc = L.annb_flat_search_shard_dev(self.index.handle, queries.data_ptr(), nq, dim, k, self.ids.data_ptr(), self.dist.data_ptr(),
                                                   self.bound.data_ptr(), st)
                 err = failed(rc) if rc != 0 else None
+            self.status.fill_(1 if err is not None else 0)
             rc = self._exchange_and_merge(L, st)
             if rc != 0 and err is None:
                 err = failed(rc)
-            # verdict: 0 = every shard's bound clears the merged k-th distances, 1 = somebody refines, 2 = somebody failed
-            count = C.c_uint32(0)
-            if err is None:
-                rc = L.annb_shard_check_dev(self.index.handle, self.bound.data_ptr(), self.out_dist.data_ptr(), nq, k, C.byref(count), st)
-                if rc != 0:
-                    err = failed(rc)
-            self.verdict.fill_(2 if err is not None else (1 if count.value else 0))
-            dist_.all_reduce(self.verdict, op=dist_.ReduceOp.MAX, group=self.group)
-            verdict = int(self.verdict.item())
-            if verdict == 2:
+            # Every rank holds every shard's bounds and status now: the verdict needs no further collective.
+            mine, any_ = C.c_uint32(0), C.c_uint32(0)
+            rc = L.annb_shard_check_gathered_dev(self.index.handle, self.gathered.data_ptr(), self.block, nq * k * 12, self.world, self.rank,
+                                                 self.out_dist.data_ptr(), nq, k, C.byref(mine), C.byref(any_), st)      # (one read-back: synchronises)
+            if rc != 0 and err is None:
+                err = failed(rc)
+            if err is not None or (any_.value & 2):
                 raise err if err is not None else RuntimeError("another rank failed in the sharded search step")
-            if verdict == 1:
-                if count.value:
+            if any_.value & 1:
+                if mine.value:
                     rc = L.annb_shard_refine_dev(self.index.handle, queries.data_ptr(), nq, dim, k, self.nprobe,
                                                  self.probes.data_ptr() if self.is_ivf else None, self.nprobes.data_ptr() if self.is_ivf else None,
                                                  self.pitch if self.is_ivf else 0, self.ids.data_ptr(), self.dist.data_ptr(), st)
                     if rc != 0:
                         err = failed(rc)
-                    self.refined_queries += int(count.value)
+                    self.refined_queries += int(mine.value)
+                self.status.fill_(1 if err is not None else 0)
                 rc = self._exchange_and_merge(L, st)
-                if rc != 0 and err is None:
-                    err = failed(rc)
-                self.verdict.fill_(2 if err is not None else 0)
-                dist_.all_reduce(self.verdict, op=dist_.ReduceOp.MAX, group=self.group)
-                if int(self.verdict.item()) == 2:
-                    raise err if err is not None else RuntimeError("another rank failed in the sharded search step")
+                if rc == 0:     # (status words only: the refined rows are exact)
+                    rc = L.annb_shard_check_gathered_dev(self.index.handle, self.gathered.data_ptr(), self.block, nq * k * 12, self.world, self.rank,
+                                                         self.out_dist.data_ptr(), nq, k, C.byref(mine), C.byref(any_), st)
+                if err is not None or rc != 0 or (any_.value & 2):
+                    raise err if err is not None else RuntimeError("a rank failed while refining the sharded search step")
         return self.out_ids, self.out_dist
 
 

@@ -77,6 +77,19 @@ extern "C" {
     pub fn annb_ivf_create_multi(out: *mut *mut annb_index, vectors: *const c_void, norms: *const c_void, centroids: *const f32,
                                  centroid_norms: *const f32, offsets: *const u64, original_ids: *const u64, n: u64, dim: u32, nlist: u32,
                                  dtype: c_int, metric: c_int, sq8_scales: *const f32, devices: *const c_int, n_devices: c_int) -> c_int;
+    /// Shard-mode searches: a bound instead of a local certificate; tested against the merged rows afterwards.
+    pub fn annb_flat_search_shard_dev(index: *const annb_index, d_queries: *const f32, nq: u64, dim: u32, k: u32, d_out_ids: *mut u64,
+                                      d_out_dist: *mut f32, d_out_bound: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn annb_ivf_search_probes_shard_dev(index: *const annb_index, d_queries: *const f32, nq: u64, dim: u32, k: u32, nprobe: u32,
+                                            d_probes: *const u32, d_n_probes: *const u32, probe_pitch: u32, d_out_ids: *mut u64,
+                                            d_out_dist: *mut f32, d_out_bound: *mut f32, stream: *mut c_void) -> c_int;
+    pub fn annb_shard_check_dev(index: *mut annb_index, d_bound: *const f32, d_merged_dist: *const f32, nq: u64, k: u32, out_count: *mut u32,
+                                stream: *mut c_void) -> c_int;
+    pub fn annb_shard_check_gathered_dev(index: *mut annb_index, d_parts: *const c_void, part_stride_bytes: u64, bound_offset_bytes: u64, parts: u32,
+                                         my_part: u32, d_merged_dist: *const f32, nq: u64, k: u32, out_mine: *mut u32, out_any: *mut u32,
+                                         stream: *mut c_void) -> c_int;
+    pub fn annb_shard_refine_dev(index: *mut annb_index, d_queries: *const f32, nq: u64, dim: u32, k: u32, nprobe: u32, d_probes: *const u32,
+                                 d_n_probes: *const u32, probe_pitch: u32, d_ids: *mut u64, d_dist: *mut f32, stream: *mut c_void) -> c_int;
     pub fn annb_index_shard_count(index: *const annb_index, out: *mut u32) -> c_int;
     pub fn annb_index_get_info(index: *const annb_index, out: *mut annb_index_info) -> c_int;
     pub fn annb_index_set_option(index: *mut annb_index, key: *const c_char, value: i64) -> c_int;

@@ -280,6 +280,15 @@ int annb_ivf_search_probes_shard_dev(const annb_index* index, const float* d_que
                                      void* stream);
 int annb_shard_check_dev(annb_index* index, const float* d_bound, const float* d_merged_dist, uint64_t nq, uint32_t k,
                          uint32_t* out_count, void* stream);
+/* annb_shard_check_dev for deployments whose exchange already carries the bounds: every shard appends its [nq] bounds to
+ * its result block (bound_offset_bytes into the block), and after the all-gather each rank tests ALL shards' bounds against
+ * the merged rows -- *out_any (some shard has to refine) is then the same on every rank without another collective;
+ * *out_mine is the number of queries listed for this shard (my_part).  The int32 that follows a shard's bounds in its block
+ * is the shard's status word: bit 1 of *out_any reports that some shard wrote a non-zero status (its search failed), so all
+ * ranks can give up on the step together. */
+int annb_shard_check_gathered_dev(annb_index* index, const void* d_parts, uint64_t part_stride_bytes, uint64_t bound_offset_bytes,
+                                  uint32_t parts, uint32_t my_part, const float* d_merged_dist, uint64_t nq, uint32_t k,
+                                  uint32_t* out_mine, uint32_t* out_any, void* stream);
 int annb_shard_refine_dev(annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,
                           const uint32_t* d_probes, const uint32_t* d_n_probes, uint32_t probe_pitch, uint64_t* d_ids,
                           float* d_dist, void* stream);
