@@ -654,6 +654,7 @@ static int run_batch(annb_index* ix, bool ivf, const PreparedQueries& pq, uint64
         }
         const uint32_t n_unc = (cs.tensor && ix->opt_cert_fallback && ix->opt_cert_eps != 0.f && ix->shard_bound == nullptr) ? h.n_unc : 0u;
         ix->stat_uncertified = cs.tensor ? static_cast<int64_t>(h.n_unc) : 0;
+        if (!ivf && cs.tensor && n_unc >= 8 && static_cast<uint64_t>(n_unc) * 50 > nb) ix->tc_escalate = 1;   // see tc_flat_search: wide-k mode from the next batch on
         if (n_unc == 0) return ANNB_OK;
         if (ivf) ANNB_TRY(ivf_fallback(ix, pq, k, nprobe, n_unc, preset_probes ? preset_probes : ix->s_probes.as<uint32_t>(),
                                        preset_probes ? preset_nprobes : ix->s_nprobes.as<uint32_t>(), preset_probes ? preset_pitch : cs.pitch, d_ids, d_dist, d_cnt, s));
@@ -1692,6 +1693,9 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     if (k == "path") { if (value < 0 || value > 2) return fail(ANNB_ERR_INVALID_ARGUMENT, "path must be 0..2"); ix->opt_path = static_cast<int>(value); }
     else if (k == "tc_candidates") ix->opt_tc_candidates = static_cast<int>(value);
     else if (k == "tc_ts") ix->opt_tc_ts = static_cast<int>(value);
+    else if (k == "tc_wide_k") ix->opt_tc_wide_k = static_cast<int>(value);
+    else if (k == "tc_strided") ix->opt_tc_strided = static_cast<int>(value);
+    else if (k == "tc_f32_lo_smem") ix->opt_tc_f32_lo_smem = static_cast<int>(value);
     else if (k == "tc_bf16_hybrid") ix->opt_tc_bf16_hybrid = static_cast<int>(value);
     else if (k == "tc_bf16_terms") ix->opt_tc_bf16_terms = static_cast<int>(value);
     else if (k == "tc_epi_warps") ix->opt_tc_epi_warps = static_cast<int>(value);
@@ -1768,6 +1772,7 @@ int annb_index_get_stat(const annb_index* ix, const char* key, int64_t* out) {
     else if (k == "coarse_path") *out = ix->stat_coarse_path;
     else if (k == "fallback_queries") *out = ix->stat_fallback_queries;
     else if (k == "cert_eps_bits") *out = ix->stat_cert_eps_bits;
+    else if (k == "tc_escalated") *out = ix->tc_escalate;
     else if (k == "uncertified") {
         // queries of the last tensor-path call whose pre-selection margin could not be certified (see rerank_kernel)
         *out = 0;

@@ -53,10 +53,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     constexpr int NG = NV / 8;
     constexpr uint32_t EPI_T = EW * 128;               // epilogue threads
     // TMEM columns per query piece (32-bit words per row): f32 128; bf16 terms 64 (rows of <= 128 elements) or 128; int8 codes 128
-    const uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : (KIND == KIND_I8 ? 128u : (p.kp > 128u ? 128u : 64u));
+    const uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? (p.lo_smem ? p.kp : 128u) : (KIND == KIND_I8 ? 128u : (p.kp > 128u ? 128u : 64u));
     // accumulator stages behind the TMEM-resident queries (TS): three when the pieces take at most 128 columns (int8 codes, one
     // or two bf16 terms of narrow rows), two when they take up to 256 (f32 hi / lo, three bf16 terms, two bf16 terms of wide rows)
-    const uint32_t q_cols = (KIND == KIND_I8) ? 128u : ((hyb_cfg(p) ? 2u : p.a_pieces) * PIECE_COLS);
+    const uint32_t q_cols = (KIND == KIND_I8) ? 128u : ((KIND == KIND_TF32X3 && p.lo_smem) ? PIECE_COLS : (hyb_cfg(p) ? 2u : p.a_pieces) * PIECE_COLS);
     const uint32_t NACC = TS ? (q_cols <= 128u ? 3u : 2u) : static_cast<uint32_t>(ACC_STAGES);
     const uint32_t ACC_COL0 = TS ? (q_cols <= 128u ? 128u : 256u) : 0u;
 
@@ -68,10 +68,20 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     // SS-mode MMA.  The A operand of a TS-mode MMA and the epilogue's tcgen05.ld share the TMEM read path: three TMEM terms
     // read 96 KB per tile on top of the epilogue's 64 KB, which is what paces the bf16 kernel.
     const bool hyb = TS && KIND == KIND_BF16 && p.hybrid != 0;
-    uint8_t* s_q = smem;                                                         // [NA][nslab] slabs (hybrid: [nslab], term q2)
-    uint8_t* s_x = TS ? (hyb ? smem + static_cast<size_t>(p.nslab) * SLAB_TILE : smem)
+    // f32 rows of more than 128 elements (option: of any width): only the hi piece fits TMEM beside two accumulator stages; the lo
+    // piece stays in shared memory and its term Qlo.Xhi is issued as an SS-mode MMA.
+    const bool lo_s = TS && KIND == KIND_TF32X3 && p.lo_smem != 0;
+    uint8_t* s_q = smem;                                                         // [NA][nslab] slabs (hybrid: [nslab], term q2; f32 lo_smem: [nslab], piece lo)
+    uint8_t* s_x = TS ? ((hyb || lo_s) ? smem + static_cast<size_t>(p.nslab) * SLAB_TILE : smem)
                       : s_q + static_cast<size_t>(NA) * p.nslab * SLAB_TILE;     // [n_stages][NB] slabs
-    uint8_t* s_tail = s_x + static_cast<size_t>(p.n_stages) * NB * SLAB_TILE;
+    // stream_q (SS mode only, rows too wide for a resident query tile): the query slabs travel through the ring with the database
+    // slabs -- one stage = [a_pieces query slabs | NB database slabs] of the same K slab; the tile's queries are re-read from L2
+    // for every database tile.
+    const bool stream_q = !TS && p.stream_q != 0;
+    const uint32_t q_slabs = stream_q ? p.a_pieces : 0u;          // query slabs per ring stage
+    const uint32_t stage_slabs = q_slabs + NB;
+    if (stream_q) s_x = smem;
+    uint8_t* s_tail = s_x + static_cast<size_t>(p.n_stages) * stage_slabs * SLAB_TILE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail);
     uint64_t* bar_full = bars;                         // [n_stages]
     uint64_t* bar_empty = bars + p.n_stages;           // [n_stages]
@@ -83,9 +93,11 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     float* s_aux_all = reinterpret_cast<float*>(s_tail + 256);   // [4 * EW epilogue warps][NV]: per-row constants of the warp's current column group
 
     const uint32_t q0 = blockIdx.x * BM;
-    const uint64_t r_begin = static_cast<uint64_t>(blockIdx.y) * p.rows_per_split;
-    const uint64_t r_end = min(static_cast<uint64_t>(p.n_pad), r_begin + p.rows_per_split);
-    const uint32_t n_tiles = (r_begin < r_end) ? static_cast<uint32_t>((r_end - r_begin + BN - 1) / BN) : 0;
+    // contiguous: split y owns rows [y * rows_per_split, ...); strided: tiles y, y + n_splits, y + 2 n_splits, ... of the database
+    const uint32_t tile_step = p.strided ? p.n_splits : 1u;
+    const uint64_t r_begin = p.strided ? static_cast<uint64_t>(blockIdx.y) * BN : static_cast<uint64_t>(blockIdx.y) * p.rows_per_split;
+    const uint64_t r_end = p.strided ? static_cast<uint64_t>(p.n_pad) : min(static_cast<uint64_t>(p.n_pad), r_begin + p.rows_per_split);
+    const uint32_t n_tiles = (r_begin < r_end) ? static_cast<uint32_t>((r_end - r_begin + static_cast<uint64_t>(BN) * tile_step - 1) / (static_cast<uint64_t>(BN) * tile_step)) : 0;
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.n_stages; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
@@ -106,28 +118,32 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
-            if (!TS) {
+            if (!TS && !stream_q) {
                 mbar_expect_tx(bar_q, p.a_pieces * p.nslab * SLAB_TILE);
                 for (uint32_t a = 0; a < p.a_pieces; a++)
                     for (uint32_t s = 0; s < p.nslab; s++)
                         tma_load_2d(smem_u32(s_q + (static_cast<size_t>(a) * p.nslab + s) * SLAB_TILE), &tm_q, bar_q, s * SLAB_ELEMS,
                                     a * p.nq_pad + q0);
             }
-            if (hyb) {
+            if (hyb || lo_s) {
+                const uint32_t piece = hyb ? 2u : 1u;
                 mbar_expect_tx(bar_q2, p.nslab * SLAB_TILE);
                 for (uint32_t s = 0; s < p.nslab; s++)
-                    tma_load_2d(smem_u32(s_q + static_cast<size_t>(s) * SLAB_TILE), &tm_q, bar_q2, s * SLAB_ELEMS, 2 * p.nq_pad + q0);
+                    tma_load_2d(smem_u32(s_q + static_cast<size_t>(s) * SLAB_TILE), &tm_q, bar_q2, s * SLAB_ELEMS, piece * p.nq_pad + q0);
             }
             uint32_t it = 0;
             long long w_prod = 0;
             for (uint32_t t = 0; t < n_tiles; t++) {
-                const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
+                const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * tile_step * BN;
                 for (uint32_t s = 0; s < p.nslab; s++, it++) {
                     const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
                     mbar_wait_timed(bar_empty + stage, ph ^ 1u, w_prod);
-                    mbar_expect_tx(bar_full + stage, NB * SLAB_TILE);
+                    mbar_expect_tx(bar_full + stage, stage_slabs * SLAB_TILE);
+                    for (uint32_t a = 0; a < q_slabs; a++)
+                        tma_load_2d(smem_u32(s_x + (static_cast<size_t>(stage) * stage_slabs + a) * SLAB_TILE), &tm_q, bar_full + stage, s * SLAB_ELEMS,
+                                    a * p.nq_pad + q0);
                     for (int b = 0; b < NB; b++)
-                        tma_load_2d(smem_u32(s_x + (static_cast<size_t>(stage) * NB + b) * SLAB_TILE), &tm_x, bar_full + stage, s * SLAB_ELEMS,
+                        tma_load_2d(smem_u32(s_x + (static_cast<size_t>(stage) * stage_slabs + q_slabs + b) * SLAB_TILE), &tm_x, bar_full + stage, s * SLAB_ELEMS,
                                     b * p.n_pad + row0);
                 }
             }
@@ -140,8 +156,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         // uniform registers); only the tcgen05 instructions themselves are issued by one elected lane.
         constexpr uint32_t idesc = make_idesc(KIND);
         constexpr uint32_t SLAB_DESC = SLAB_TILE >> 4;    // descriptor start-address units (16 B) per slab
-        mbar_wait(bar_q, 0);
-        if (hyb) mbar_wait(bar_q2, 0);
+        if (!stream_q) mbar_wait(bar_q, 0);
+        if (hyb || lo_s) mbar_wait(bar_q2, 0);
         tc_fence_after();
         const uint32_t q_desc0 = make_smem_desc(smem_u32(s_q));   // low descriptor words; the constant high word is added by umma()
         const uint32_t x_desc0 = make_smem_desc(smem_u32(s_x));
@@ -157,9 +173,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
                 mbar_wait_timed(bar_full + stage, ph, w_full);
                 tc_fence_after();
-                const uint32_t xd = x_desc0 + stage * NB * SLAB_DESC;
-                const uint32_t qd = q_desc0 + s * SLAB_DESC;
-                const uint32_t q_piece = p.nslab * SLAB_DESC;
+                const uint32_t xd = x_desc0 + (stage * stage_slabs + q_slabs) * SLAB_DESC;
+                const uint32_t qd = stream_q ? x_desc0 + stage * stage_slabs * SLAB_DESC : q_desc0 + s * SLAB_DESC;
+                const uint32_t q_piece = stream_q ? SLAB_DESC : p.nslab * SLAB_DESC;
                 if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < KSTEPS; k++) {
@@ -168,7 +184,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                             // queries in TMEM: hi at columns [0, 128), lo at [128, 256); 8 columns (8 tf32) per K step
                             const uint32_t a_hi = tmem_base + s * 32 + k * 8, a_lo = a_hi + PIECE_COLS;
                             umma_ts<KIND>(tmem_c, a_hi, xd + 2 * k, idesc, first);
-                            umma_ts<KIND>(tmem_c, a_lo, xd + 2 * k, idesc, 1u);
+                            if (lo_s) umma<KIND>(tmem_c, qd + 2 * k, xd + 2 * k, idesc, 1u);     // Qlo from shared memory
+                            else umma_ts<KIND>(tmem_c, a_lo, xd + 2 * k, idesc, 1u);
                             umma_ts<KIND>(tmem_c, a_hi, xd + SLAB_DESC + 2 * k, idesc, 1u);
                         } else if (TS && KIND == KIND_I8) {
                             // int8 codes, four per column: 8 columns (32 codes) per K step; one exact s32 term
@@ -223,7 +240,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             // (even pieces to half 0, odd to half 1); thread = query row = TMEM lane, 32 columns (128 B of the row) per
             // tcgen05.st.  16-bit operands sit two per column, low half = even k, exactly as in memory.
             const uint32_t row_words = p.kp * ELEM / 4;
-            const uint32_t tmem_pieces = hyb ? 2u : p.a_pieces;
+            const uint32_t tmem_pieces = hyb ? 2u : (lo_s ? 1u : p.a_pieces);
             const uint32_t cpp = row_words / 32;                       // 32-column chunks per piece
             for (uint32_t item = half; item < tmem_pieces * cpp; item += EW) {   // (piece, chunk) items dealt round-robin to the quarter's warps
                 const uint32_t pc = item / cpp, c = (item - pc * cpp) * 32;
@@ -242,23 +259,25 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             mbar_arrive(bar_q);
         }
         uint32_t* gtau_ptr = p.gtau + q0 + row_in_tile;
-        uint32_t g_next = DENSE ? 0xFFFFFFFFu : *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
+        const bool share_tau = !DENSE && p.wide_k == 0;     // wide-k lists prune with their own thresholds only (see Params::wide_k)
+        uint32_t g_next = share_tau ? *reinterpret_cast<volatile uint32_t*>(gtau_ptr) : 0xFFFFFFFFu;
         // Per-column constants of this warp's 64-column half: lane l fetches columns l and l + 32 (coalesced, one tile
         // ahead) and parks them in a warp-private shared-memory row; the value loop reads them back as 128-bit broadcast
         // loads (16 per tile instead of 64 shuffles).  No CTA-wide barrier: only __syncwarp.
         float* s_aux = s_aux_all + (warp - 2) * NV;
         const float* aux_half = p.aux + r_begin + half * NV + lane;
+        const size_t aux_step = static_cast<size_t>(tile_step) * BN;
         float aux_lo_next = 0.f, aux_hi_next = 0.f;
         if (n_tiles > 0) { aux_lo_next = __ldg(aux_half); if (NV > 32) aux_hi_next = __ldg(aux_half + 32); }
         for (uint32_t t = 0; t < n_tiles; t++) {
             const uint32_t acc = t % NACC, aph = (t / NACC) & 1u;
-            const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
+            const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * tile_step * BN;
             const uint32_t g_bits = g_next;
             const float aux_lo = aux_lo_next, aux_hi = aux_hi_next;
             if (t + 1 < n_tiles) {   // prefetch for the next tile: latency hidden behind this tile's work
-                aux_lo_next = __ldg(aux_half + static_cast<size_t>(t + 1) * BN);
-                if (NV > 32) aux_hi_next = __ldg(aux_half + static_cast<size_t>(t + 1) * BN + 32);
-                if (!DENSE) g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
+                aux_lo_next = __ldg(aux_half + static_cast<size_t>(t + 1) * aux_step);
+                if (NV > 32) aux_hi_next = __ldg(aux_half + static_cast<size_t>(t + 1) * aux_step + 32);
+                if (share_tau) g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
             }
             __syncwarp();                      // every lane is done with the previous tile's constants
             s_aux[lane] = aux_lo;
@@ -315,8 +334,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     w_slow += tc_clock() - ts0;
                 }
             }
-            if (!DENSE && (top.tau() < g_tau || (g_tau != g_tau && top.tau() < INFINITY))) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));
+            if (share_tau && (top.tau() < g_tau || (g_tau != g_tau && top.tau() < INFINITY))) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));
         }
+        if (!DENSE && !share_tau && top.tau() < INFINITY) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));   // wide-k: this list's final threshold
         if (TC_COUNTERS && p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) { p.dbg_cycles[4] = w_tfull; p.dbg_cycles[5] = w_slow; }
         const uint64_t q = static_cast<uint64_t>(q0) + row_in_tile;
         if (!DENSE && q < p.nq) {
@@ -704,7 +724,10 @@ int tc_flat_prepare(annb_index* ix) {
     const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : (kind == tc::KIND_BF16 ? 2 : 1);
     const uint32_t slab_elems = tc::SLAB_BYTES / elem;
     const uint32_t kp = round_up(ix->dim, slab_elems);
-    if (kp * elem > 512) return ANNB_OK;  // query tile would not fit in shared memory: the exact CUDA-core path serves this index
+    // the query tile lives in TMEM: 512 B of a row per piece (f32 dim <= 128, bf16 <= 256, int8 <= 512); f32 rows of up to 1024 B
+    // keep only their hi piece there and the lo piece in shared memory (Params::lo_smem).  Wider rows: the exact CUDA-core path.
+    // Rows of up to 2048 B (f32 dim <= 512) stream their query slabs through the ring with the database (Params::stream_q).
+    if (kp * elem > 2048u) return ANNB_OK;
     if (ix->n < 4096) return ANNB_OK;     // tiny indices stay on the exact CUDA-core path
     TcState* st = new TcState();
     ix->tc = st;
@@ -827,9 +850,19 @@ static uint32_t pick_kprime(const annb_index* ix, uint32_t k_eff) {
     return k_eff <= 10 ? 16 : 32;
 }
 
+// k above TC_K_LIST (one k' = 32 list per thread covers it) and up to TC_K_WIDE: "wide-k" mode.  Every (split, half tile) list
+// keeps its own 32 best and prunes with its own threshold only; the lists interleave over the database (strided tiles), so the
+// true top-k of a query spread over all of them and the union of >= max(8, k / 8) lists holds it with room to spare.  Whether
+// it did is not assumed but checked: the re-rank recomputes every candidate at or below G = the smallest final list threshold
+// and certifies the query iff its k-th exact distance lies below the bound of G (rerank_kernel, wide branch); a database whose
+// order defeats the interleaving (a query's neighbours all in one 64-row half tile stride) sends those queries to the exact path.
+constexpr uint32_t TC_K_LIST = 24, TC_K_WIDE = 256;
+static uint32_t wide_k_lists(uint32_t k_eff) { return std::max<uint32_t>(8u, (k_eff + 7u) / 8u); }
+
 bool tc_flat_supported(const annb_index* ix, int qt, uint32_t k_eff) {
     if (!ix->tc) return false;
-    if (k_eff > 24) return false;
+    if (k_eff > TC_K_WIDE) return false;
+    if (k_eff > TC_K_LIST && (ix->opt_tc_wide_k == 0 || static_cast<uint64_t>(ix->tc->n_pad / tc::BN) * 2 < wide_k_lists(k_eff))) return false;
     if (ix->dtype == ANNB_F32) return qt == QT_F32;
     if (ix->dtype == ANNB_BF16) return qt == QT_F32 || qt == QT_BF16;
     if (ix->dtype == ANNB_SQ8) return qt == QT_I8;
@@ -870,7 +903,7 @@ static int launch_tc(const CUtensorMap& tmq, const CUtensorMap& tmx, const tc::P
 template <int RT, int QT, int MET>
 static int launch_rerank(const tc::RerankParams& r, cudaStream_t s) {
     auto kern = tc::rerank_kernel<RT, QT, MET>;
-    const size_t smem = static_cast<size_t>(r.nsort) * 8;
+    const size_t smem = (static_cast<size_t>(r.nsort) + (r.n_exact > 64u ? r.n_exact : 0u)) * 8;
     ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<static_cast<uint32_t>(r.nq), 128, smem, s>>>(r);
     ANNB_CUDA_CHECK(cudaGetLastError());
@@ -883,7 +916,11 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     const int kind = st->kind;
     const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : (kind == tc::KIND_BF16 ? 2 : 1);
     const uint32_t kp = st->kp_elems;
-    const uint32_t kprime = pick_kprime(ix, k_eff);
+    uint32_t kprime = pick_kprime(ix, k_eff);
+    // f32 rows of more than 128 elements: the accumulation error of the tensor core grows with the MMAs per tile row (tc_cert_eps),
+    // and a k' = 16 list's threshold then sits inside the certificate's margin of the k-th distance on data with ~1e-6 neighbour
+    // gaps (measured, 1M x 256 Correlated cosine k = 10: 7.5 % of the queries uncertified with k' = 16)
+    if (kind == tc::KIND_TF32X3 && kp > 128 && ix->opt_tc_candidates == 0) kprime = 32;
     const uint32_t nq_pad = static_cast<uint32_t>(round_up<uint64_t>(nq, tc::BM));
     // f32 queries against a BF16 index go in as two or three bf16 terms q0 + q1 [+ q2]: 16 or 24 MMAs per tile
     const uint32_t bf16_terms = tc_bf16_terms(ix);
@@ -912,21 +949,32 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     // ---- geometry ----
     const uint64_t q_tiles = nq_pad / tc::BM;
     const uint64_t db_tiles = st->n_pad / tc::BN;
-    const uint32_t splits_req = pick_splits(q_tiles, db_tiles, ix->opt_db_splits, kprime == 32 ? 40u : 8u);
+    // A handle whose batches keep failing the certificate (more than 2 % of a batch went to the exact fallback: run_batch sets
+    // tc_escalate) switches to the wide-k machinery whatever k is: the union of >= 8 unshared k' = 32 lists reaches far beyond
+    // the k-th neighbour, which a wide certificate margin needs (1M x 256 Correlated cosine, k = 10: 748 uncertified queries per
+    // 10 000 with a shared threshold and the 64-candidate second chance -- 65 ms per batch; 0 in wide mode -- 27 ms).
+    const bool wide_k = k_eff > TC_K_LIST || (ix->tc_escalate != 0 && ix->opt_tc_wide_k != 0);
+    uint32_t splits_req = pick_splits(q_tiles, db_tiles, ix->opt_db_splits, kprime == 32 ? 40u : 8u);
+    if (wide_k) splits_req = static_cast<uint32_t>(std::min<uint64_t>(db_tiles, std::max<uint32_t>(splits_req, (wide_k_lists(k_eff) + 1) / 2)));
     const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;
-    const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
+    const uint32_t splits = wide_k ? splits_req : static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
     const uint32_t nb = kind == tc::KIND_TF32X3 ? 2 : 1;
     // query operand resident in TMEM (TS-mode MMA) when its pieces fit their column budget (bf16 terms: 64 columns each)
     const uint32_t bf16_piece_cols = kp > 128 ? 128u : 64u;
-    const bool ts = ix->opt_tc_ts != 0 && (kind != tc::KIND_BF16 || na * bf16_piece_cols <= 256);
+    const bool ts = ix->opt_tc_ts != 0 && (kind != tc::KIND_BF16 || na * bf16_piece_cols <= 256) && kp * elem <= (kind == tc::KIND_TF32X3 ? 1024u : 512u);
     const bool hyb = ts && kind == tc::KIND_BF16 && na == 3 && ix->opt_tc_bf16_hybrid != 0;
-    const size_t q_smem = ts ? (hyb ? static_cast<size_t>(st->nslab) * tc::SLAB_TILE : 0) : static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : (kind == tc::KIND_I8 ? 1 : 3)) * st->nslab * tc::SLAB_TILE;
+    // f32 rows of 129 .. 256 elements: hi piece in TMEM, lo piece in shared memory (option tc_f32_lo_smem = 1 forces it for narrow rows too)
+    const bool lo_s = ts && kind == tc::KIND_TF32X3 && (kp > 128 || ix->opt_tc_f32_lo_smem != 0);
     const size_t fixed = 256 /*barriers*/ + 8 * 64 * 4 /*per-warp row constants*/;
     const size_t budget = 227 * 1024;
-    if (q_smem + fixed + nb * tc::SLAB_TILE > budget) { set_last_error("tensor path: query tile too large for shared memory"); return ANNB_ERR_UNSUPPORTED; }
-    uint32_t stages = static_cast<uint32_t>((budget - q_smem - fixed) / (nb * tc::SLAB_TILE));
+    size_t q_smem = ts ? ((hyb || lo_s) ? static_cast<size_t>(st->nslab) * tc::SLAB_TILE : 0) : static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : (kind == tc::KIND_I8 ? 1 : 3)) * st->nslab * tc::SLAB_TILE;
+    // SS mode with a query tile that leaves fewer than two ring stages: stream the query slabs with the database slabs instead
+    const bool stream_q = !ts && q_smem + fixed + 2 * nb * tc::SLAB_TILE > budget;
+    if (stream_q) q_smem = 0;
+    const uint32_t stage_slabs = nb + (stream_q ? na : 0u);
+    uint32_t stages = static_cast<uint32_t>((budget - q_smem - fixed) / (stage_slabs * tc::SLAB_TILE));
     stages = std::min<uint32_t>(stages, 8);
-    const size_t smem = q_smem + static_cast<size_t>(stages) * nb * tc::SLAB_TILE + fixed;
+    const size_t smem = q_smem + static_cast<size_t>(stages) * stage_slabs * tc::SLAB_TILE + fixed;
 
     // epilogue warps per TMEM lane quarter: the int8 and bf16 kernels (few MMAs per tile, epilogue-paced) run four, k' = 16 only
     // (a k' = 32 list does not fit the 112-register budget of 18 warps); option tc_epi_warps = 2 forces the narrow layout
@@ -939,6 +987,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     tc::Params p{};
     p.nq = nq; p.n_rows = ix->n; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
     p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = na; p.aux = st->d_aux; p.hybrid = hyb ? 1u : 0u;
+    p.lo_smem = lo_s ? 1u : 0u; p.stream_q = stream_q ? 1u : 0u; p.wide_k = wide_k ? 1u : 0u; p.strided = (wide_k || ix->opt_tc_strided != 0) ? 1u : 0u;
     p.part_keys = st->part.as<uint64_t>(); p.dbg = st->dbg.as<float>(); p.gtau = st->gtau.as<uint32_t>(); p.q_op = st->q_op.as<void>(); p.kp = kp; p.dbg_cycles = st->dbgc.as<unsigned long long>();
     {
         dim3 grid(static_cast<uint32_t>(q_tiles), splits);
@@ -966,6 +1015,8 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     tc::RerankParams r{};
     r.part_keys = st->part.as<uint64_t>(); r.parts = ew * splits; r.kp = kprime; r.k_eff = k_eff; r.k_out = k_out; r.gtau = st->gtau.as<uint32_t>();
     r.nsort = next_pow2(std::max(ew * splits * kprime, 64u));
+    r.n_exact = wide_k ? std::min<uint32_t>(r.nsort, 2048u) : 0u;     // every candidate below the certificate's threshold, up to 2048 per query
+    if (wide_k) r.n_exact = std::max<uint32_t>(r.n_exact, 128u);
     r.nq = nq; r.rows = ix->d_rows; r.row_bytes = ix->row_bytes; r.row_norms = ix->d_norms; r.row_norms_i = ix->d_norms_i; r.queries = d_q; r.q_bytes = q_bytes; r.dim = ix->dim;
     r.bf16_self = bf16_self; r.id_base = ix->id_base; r.out_ids = d_ids; r.out_dist = d_dist; r.out_counts = d_cnt;
     ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));

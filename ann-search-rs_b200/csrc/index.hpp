@@ -80,6 +80,10 @@ struct annb_index {
     int opt_tc_bf16_hybrid = 0; // flat tensor path, bf16 index + f32 queries: third query term in shared memory (SS-mode MMA) instead of TMEM
     int opt_tc_bf16_terms = 0;  // tensor paths, bf16 index + f32 queries: bf16 terms the query is split into (2 or 3); 0 = by metric (cosine 2, L2 3)
     int opt_tc_epi_warps = 0;   // flat tensor path, bf16 / int8 kernels: epilogue warps per TMEM lane quarter (0 = auto: four for k' = 16, 2 = two)
+    int tc_escalate = 0;        // sticky: a batch of this flat handle left more than 2 % of its queries uncertified -> later batches run in wide-k mode
+    int opt_tc_wide_k = 1;      // flat tensor path: serve 24 < k <= 128 from the union of interleaved k' = 32 lists (0: such k go to the CUDA-core path)
+    int opt_tc_strided = 0;     // flat tensor path: interleave the splits' tiles over the database also for k <= 24
+    int opt_tc_f32_lo_smem = 0; // flat tensor path, f32 rows of <= 128 elements: lo query piece in shared memory (frees TMEM for a third accumulator stage)
     int opt_tc_ts = 1;         // tensor path, f32: keep the query operand in TMEM (TS-mode MMA)
     int opt_db_splits = 0;
     int opt_scan_parts = 0;

@@ -34,6 +34,11 @@ struct Params {
     uint64_t rows_per_split;  // multiple of BN
     uint32_t a_pieces;        // query terms actually present (bf16 self query: 1)
     uint32_t hybrid;          // bf16, queries in TMEM: the third query term stays in shared memory and is issued as an SS-mode MMA
+    uint32_t lo_smem;         // f32, queries in TMEM: only the hi piece; the lo piece stays in shared memory (SS-mode MMA) -- rows of up to 256 elements
+    uint32_t stream_q;        // SS mode: query slabs are streamed through the ring with the database slabs (rows too wide for a resident query tile)
+    uint32_t wide_k;          // k > k': every list prunes with its OWN threshold only (a value above another list's k'-th may still be in the top-k);
+                              // gtau receives the minimum of the lists' final thresholds (the certificate's bound), once per list
+    uint32_t strided;         // split y owns the tiles y, y + n_splits, ... (lists interleave over the database) instead of a contiguous range
     const float* aux;         // per database row: L2  v = aux - 2 s  (aux = |x|^2, pad rows +inf);
                               //                   cos v = s * aux    (aux = -1/|x|, pad rows +inf -> 0 * inf = NaN, never selected)
     uint64_t* part_keys;      // [nq][2 * n_splits][KPRIME] packed (approx value, row); one list per 64-column half
@@ -435,6 +440,7 @@ static __global__ void pad_i8_kernel(const int8_t* __restrict__ src, uint32_t ld
 struct RerankParams {
     const uint64_t* part_keys;  // [nq][parts][kp] approximate keys
     uint32_t parts, kp, k_eff, k_out, nsort;
+    uint32_t n_exact;           // wide-k mode (k > k'): candidates recomputed exactly per query (power of two > 64, exact keys behind keys[nsort]); 0 otherwise
     uint64_t nq;
     const uint8_t* rows;  // index rows in the index dtype
     uint32_t row_bytes;
@@ -469,7 +475,9 @@ template <int RT, int QT, int MET>
 __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t* keys = reinterpret_cast<uint64_t*>(smem);
-    __shared__ uint64_t exact[64];
+    __shared__ uint64_t exact64[64];
+    const bool wide = p.n_exact > 64u;
+    uint64_t* exact = wide ? keys + p.nsort : exact64;
     const uint64_t q = blockIdx.x;
     const uint32_t parts_q = p.parts_used ? min(p.parts, p.parts_used[q] * p.part_mult) : p.parts;
     const uint32_t total = parts_q * p.kp;
@@ -540,7 +548,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         if ((threadIdx.x & 31u) == 0) s_qn2w[threadIdx.x >> 5] = part;
     }
     __syncthreads();
-    auto exact_range = [&](uint32_t count) {
+    auto exact_range = [&](uint32_t count, uint32_t base = 0u) {   // candidates keys[base .. base + count), count <= 64 -> exact[base .. base + 64)
         // up to four candidates per 8-thread group (j = grp, grp + 16, grp + 32, grp + 48) with independent accumulators: the row
         // gathers of all of them are in flight together -- one DRAM round trip for a 64-candidate second chance instead of four
         const uint32_t l = threadIdx.x & 7u, grp = threadIdx.x >> 3;
@@ -550,7 +558,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
 #pragma unroll
         for (int r = 0; r < 4; r++) {
             const uint32_t j = r * 16 + grp;
-            const uint64_t key = (static_cast<uint32_t>(r) < rounds && j < count) ? keys[j] : KEY_SENTINEL;
+            const uint64_t key = (static_cast<uint32_t>(r) < rounds && j < count) ? keys[base + j] : KEY_SENTINEL;
             idx[r] = key_idx(key);
             row[r] = p.rows + static_cast<uint64_t>(idx[r] != IDX_INVALID ? idx[r] : 0u) * p.row_bytes;
         }
@@ -631,7 +639,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         }
         if (l == 0) {
 #pragma unroll
-            for (int r = 0; r < 4; r++) exact[r * 16 + grp] = out[r];
+            for (int r = 0; r < 4; r++) exact[base + r * 16 + grp] = out[r];
         }
     };
     // coverage test: every row that was not re-ranked has an approximate value >= a_thr; is the k-th exact distance safely
@@ -652,6 +660,30 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     };
     auto covered = [&](float a_thr, float dk) -> bool { return bound_of(a_thr) > static_cast<double>(dk); };
     __shared__ int s_extend;
+    if (wide) {
+        // k > k' (wide-k mode, gtau path only).  No list shared its threshold, so G = gtau[q] is the minimum of the lists' final
+        // thresholds: a row that is in no list has a value >= G, and every scanned row with a value below G sits in the compacted
+        // set.  All of them (up to n_exact, in approximate order) are recomputed exactly; the query is certified iff its k-th exact
+        // distance lies below the distance bound of G (or of the first candidate that was not recomputed).
+        const uint32_t ne = min(n_cand, p.n_exact);
+        for (uint32_t base = 0; base < p.n_exact; base += 64) {
+            if (base < ne) exact_range(min(64u, ne - base), base);
+            else if (threadIdx.x < 64) exact[base + threadIdx.x] = KEY_SENTINEL;
+        }
+        __syncthreads();
+        bitonic_sort_keys<true>(exact, p.n_exact, threadIdx.x, blockDim.x);
+        if (threadIdx.x == 0) {
+            const uint32_t g = p.gtau[q];
+            double b = static_cast<double>(INFINITY);                       // nothing was ever pruned: every row is a candidate
+            if (n_cand > ne) b = bound_of(key_dist(keys[ne]));
+            else if (g != 0xFFFFFFFFu) b = bound_of(ordered_to_f32(g));
+            const uint64_t d_key = exact[p.k_eff - 1];
+            const bool ok = key_idx(d_key) != IDX_INVALID ? (b > static_cast<double>(key_dist(d_key))) : (g == 0xFFFFFFFFu && n_cand <= ne);
+            if (p.out_bound != nullptr) p.out_bound[q] = (p.cert_eps > 0.f) ? __double2float_rd(b) : INFINITY;
+            else if (!ok && p.uncert_count != nullptr && p.cert_eps > 0.f) p.uncert_list[atomicAdd(p.uncert_count, 1u)] = static_cast<uint32_t>(q);
+        }
+        __syncthreads();
+    } else {
     exact_range(p.kp);
     if (threadIdx.x == 0) s_extend = 0;
     __syncthreads();
@@ -690,9 +722,11 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
             else if (!(b > static_cast<double>(key_dist(d_key)))) p.uncert_list[atomicAdd(p.uncert_count, 1u)] = static_cast<uint32_t>(q);
         }
     }
+    }   // !wide
+    const uint32_t exact_cap = wide ? p.n_exact : 64u;
     uint32_t valid = 0;
     for (uint32_t j = threadIdx.x; j < p.k_out; j += blockDim.x) {
-        uint64_t key = (j < p.k_eff && j < 64) ? exact[j] : KEY_SENTINEL;
+        uint64_t key = (j < p.k_eff && j < exact_cap) ? exact[j] : KEY_SENTINEL;
         uint64_t id = 0xFFFFFFFFFFFFFFFFull;
         float d = INFINITY;
         if (key_idx(key) != IDX_INVALID) {

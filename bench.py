@@ -407,6 +407,30 @@ def tensor_roofline(c, dtype, flops, dom_s, kernel, tf32_peak):
             "executed": {"mma_terms_per_element": terms, "tflops": achieved * terms, "pipe_peak": pipe_peak, "frac_of_pipe_peak": achieved * terms / pipe_peak}}
 
 
+def tie_classes_equal(ids, dist, ref_ids, ref_dist):
+    """Same rule as tests/util.py::assert_tie_classes: distance bits equal, and inside every run of equal distances that ends
+    before the last valid slot the id SETS agree (the reference's IVF-SQ8 heap, src/quantised/ivf_sq8.rs:329-352, keeps an
+    implementation-defined subset of the last tie class; integer distances tie often)."""
+    if not np.array_equal(np.asarray(dist).view(np.uint32), np.asarray(ref_dist).view(np.uint32)):
+        return False
+    for r in range(ids.shape[0]):
+        valid = int((ids[r] >= 0).sum())
+        if valid != int((ref_ids[r] >= 0).sum()):
+            return False
+        j = 0
+        while j < valid:
+            e = j
+            while e + 1 < valid and dist[r, e + 1] == dist[r, j]:
+                e += 1
+            if e < valid - 1:
+                if set(ids[r, j:e + 1].tolist()) != set(ref_ids[r, j:e + 1].tolist()):
+                    return False
+            elif len(set(ids[r, j:e + 1].tolist())) != e + 1 - j:
+                return False
+            j = e + 1
+    return True
+
+
 def cpu_baseline_flat(oix, queries, k, n, dim, nq, self_mode=False):
     from oracle import oracle as o
     cores = os.cpu_count() or 1
@@ -617,6 +641,8 @@ def bench_ivf_set(c, n, dim, nq, k, nlist, entries, tf32_peak):
             entry["parity_sample"] = {"queries": ns, "ids_equal": bool(np.array_equal(got_ids[:ns], ref[0])),
                                       "dist_bits_equal": bool(np.array_equal(got_d[:ns].view(np.uint32), ref[1].view(np.uint32))),
                                       "against": "CPU oracle (oracle/oracle.c) on the same index contents" + (f", merged over {c.shards} shards" if c.shards > 1 else "")}
+            if dtype == "sq8":   # integer distances tie: ids are compared per tie class (see tie_classes_equal)
+                entry["parity_sample"]["tie_classes_equal"] = bool(tie_classes_equal(np.asarray(got_ids[:ns]).astype(np.int64), got_d[:ns], np.asarray(ref[0]).astype(np.int64), ref[1]))
             entry["recall_at_k_vs_exact_f32"] = {"value": o.recall_at_k(truth_ids, got_ids[:truth_ids.shape[0]], k), "queries": int(truth_ids.shape[0])}
             if not args.no_cpu_baseline:
                 per_query_s = (nprobe * n / nlist + nlist) * dim / 3.0e9

@@ -247,3 +247,109 @@ def test_adversarial_certificate_same_sign_operands(gpu, dtype, metric):
 
 def bits(a):
     return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+# ---- wide k (24 < k <= 128) and wide f32 rows (128 < dim <= 256) on the tensor path -------------------------------------
+@pytest.mark.parametrize("dtype,metric,n,dim,nq,k", [
+    ("f32", "l2", 40000, 64, 200, 32), ("f32", "cosine", 40000, 128, 150, 100), ("f32", "l2", 20000, 32, 130, 128),
+    ("bf16", "l2", 30000, 96, 100, 64), ("sq8", "cosine", 30000, 64, 100, 50), ("f32", "l2", 5000, 50, 40, 25),
+    ("f32", "cosine", 60000, 64, 100, 200), ("f32", "l2", 60000, 32, 70, 256)])
+def test_wide_k_matches_oracle(gpu, dtype, metric, n, dim, nq, k):
+    """k above one k' = 32 list: the union of the interleaved lists + the certificate against the smallest list threshold
+    (reference spec of large k: src/gpu/topk_gpu.rs:992-1237, tested there at k = 250 / 1024; order (distance, index))."""
+    data = datagen.gaussian_noise(n, dim, seed=31)
+    q = datagen.subsample_with_noise(data, nq, seed=31)
+    g, c = _pair(data, dtype, metric)
+    ids, d, cnt = g.query_batch(q, k)
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    rids, rd, _ = o.flat_search(c, q, k)
+    assert_exact(ids, d, rids, rd, f"wide-k tensor flat {dtype} {metric} n={n} dim={dim} k={k}")
+    # randomly ordered rows spread a query's neighbours over all lists: (nearly) nothing may need the exact fallback
+    assert g.get_stat("fallback_queries") <= nq // 20, g.get_stat("fallback_queries")
+
+
+def test_wide_k_clustered_row_order_is_still_exact(gpu):
+    """Rows sorted by cluster, clusters smaller than one list stride: a query's neighbours crowd into few lists, those lists'
+    thresholds fall below the k-th distance, and the certificate must send such queries to the exact path instead of
+    returning a wrong set."""
+    rng = np.random.default_rng(5)
+    centres = rng.normal(size=(400, 48)).astype(np.float32) * 6
+    data = (np.repeat(centres, 40, axis=0) + rng.normal(size=(16000, 48)).astype(np.float32) * 0.05).astype(np.float32)   # 40 contiguous rows per cluster
+    q = datagen.subsample_with_noise(data, 128, seed=5)
+    g, c = _pair(data, "f32", "l2")
+    ids, d, _ = g.query_batch(q, 60)
+    rids, rd, _ = o.flat_search(c, q, 60)
+    assert_exact(ids, d, rids, rd, "wide-k, clustered row order")
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("dim,k", [(160, 10), (256, 15), (200, 40), (132, 1)])
+def test_wide_f32_rows_on_the_tensor_path(gpu, metric, dim, k):
+    """f32 rows of more than 128 elements: hi query piece in TMEM, lo piece in shared memory (SS-mode MMA for Qlo.Xhi).
+    The reference accepts any dim (src/gpu/exhaustive_gpu.rs:116-117)."""
+    data = datagen.gaussian_noise(12000, dim, seed=37)
+    q = datagen.subsample_with_noise(data, 140, seed=37)
+    g, c = _pair(data, "f32", metric)
+    ids, d, _ = g.query_batch(q, k)
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    rids, rd, _ = o.flat_search(c, q, k)
+    assert_exact(ids, d, rids, rd, f"wide f32 rows dim={dim} {metric} k={k}")
+
+
+def test_wide_f32_rows_first_tile_values(gpu):
+    data = datagen.gaussian_noise(8192, 256, seed=3)
+    q = datagen.subsample_with_noise(data, 128, seed=3)
+    g, c = _pair(data, "f32", "l2")
+    g.set_option("tc_debug", 1)
+    g.set_option("db_splits", 1)
+    g.query_batch(q, 10)
+    v = g.debug_fetch_tile().astype(np.float64)
+    x = data[:128].astype(np.float64)
+    want = (x * x).sum(1)[None, :] - 2 * (q.astype(np.float64) @ x.T)
+    err = np.abs(v - want).max() / np.abs(want).max()
+    # the tensor core's f32 accumulation truncates: the error grows with the MMAs per tile row (96 here: 3.7e-6 measured,
+    # 1.6e-6 at dim 128, 1.0e-6 at dim 64 -- tools/tile_err.py; exact 3xTF32 arithmetic would give 3e-8); tc_cert_eps budgets it
+    assert err < 6e-6, f"tile error {err:.3e}"
+
+
+@pytest.mark.parametrize("opt", ["tc_f32_lo_smem", "tc_strided"])
+def test_layout_options_do_not_change_results(gpu, opt):
+    data = datagen.correlated(30000, 128, seed=41)
+    q = datagen.subsample_with_noise(data, 300, seed=41)
+    g, c = _pair(data, "f32", "cosine")
+    ref = o.flat_search(c, q, 10)
+    g.set_option(opt, 1)
+    ids, d, _ = g.query_batch(q, 10)
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    assert_exact(ids, d, ref[0], ref[1], opt)
+
+
+@pytest.mark.parametrize("dtype,metric,dim,k", [("f32", "l2", 320, 10), ("f32", "cosine", 512, 15), ("f32", "l2", 388, 50),
+                                                ("bf16", "cosine", 384, 10), ("bf16", "l2", 1000, 10), ("sq8", "l2", 640, 10), ("sq8", "cosine", 2048, 12)])
+def test_streamed_query_slabs_for_very_wide_rows(gpu, dtype, metric, dim, k):
+    """Rows too wide for a resident query tile (f32 dim > 256, bf16 > 256, int8 > 512; up to 2048 B per row): the query slabs
+    stream through the ring with the database slabs (SS-mode MMAs)."""
+    data = datagen.gaussian_noise(9000, dim, seed=43)
+    q = datagen.subsample_with_noise(data, 130, seed=43)
+    g, c = _pair(data, dtype, metric)
+    ids, d, _ = g.query_batch(q, k)
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    rids, rd, _ = o.flat_search(c, q, k)
+    assert_exact(ids, d, rids, rd, f"streamed query slabs {dtype} dim={dim} {metric} k={k}")
+
+
+def test_escalation_to_wide_mode_after_an_uncertified_batch(gpu):
+    """A handle whose batch left > 2 % of the queries uncertified runs its later batches in wide-k mode (stat tc_escalated);
+    forced here with a pessimistic error bound.  Results stay the oracle's in both modes."""
+    data = datagen.gaussian_noise(20000, 96, seed=47)
+    q = datagen.subsample_with_noise(data, 400, seed=47)
+    g, c = _pair(data, "f32", "l2")
+    ref = o.flat_search(c, q, 10)
+    g.set_option("cert_eps_log2", -6)
+    ids, d, _ = g.query_batch(q, 10)
+    assert g.get_stat("tc_escalated") == 1 and g.get_stat("fallback_queries") > 8
+    assert_exact(ids, d, ref[0], ref[1], "before escalation")
+    g.set_option("cert_eps_log2", 1)
+    ids, d, _ = g.query_batch(q, 10)
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    assert_exact(ids, d, ref[0], ref[1], "wide mode at k = 10")
