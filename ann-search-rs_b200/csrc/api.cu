@@ -257,12 +257,14 @@ struct HostStatus {          // layout of ix->h_status (pinned)
     uint32_t overflow, export_overflow;
     unsigned long long scanned, probed, local;
     uint32_t n_unc, pad1;
+    unsigned long long tiles;      // tensor-core IVF scan: 128-row tiles executed by the batch's tasks
 };
 
 static int enqueue_status_read(annb_index* ix, const CoreState& cs, cudaStream_t s) {
     HostStatus* h = reinterpret_cast<HostStatus*>(ix->h_status);
     std::memset(h, 0, sizeof(HostStatus));
     if (cs.routed) ANNB_CUDA_CHECK(cudaMemcpyAsync(h, ix->s_flags.p, 32, cudaMemcpyDeviceToHost, s));
+    if (cs.routed && cs.tensor) ANNB_CUDA_CHECK(cudaMemcpyAsync(&h->tiles, ix->s_flags.as<uint8_t>() + 32, 8, cudaMemcpyDeviceToHost, s));
     if (cs.tensor && ix->s_uncert.p) ANNB_CUDA_CHECK(cudaMemcpyAsync(&h->n_unc, ix->s_uncert.p, 4, cudaMemcpyDeviceToHost, s));
     return ANNB_OK;
 }
@@ -529,6 +531,7 @@ static int ivf_enqueue(annb_index* ix, const PreparedQueries& pq, uint64_t nq, u
         pp.tasks = use_tc ? reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(w) + hdr + pairs_bytes) : nullptr;
         pp.offsets = ix->d_offsets; pp.shard_row0 = ix->shard_row0;
         pp.order = (use_tc && ix->opt_ivf_task_order) ? ix->d_list_order : nullptr;
+        pp.stat_tiles = (use_tc && !preset_probes && ix->s_flags.p) ? reinterpret_cast<unsigned long long*>(ix->s_flags.as<uint8_t>() + 32) : nullptr;
         const uint32_t g = static_cast<uint32_t>(ceil_div<uint64_t>(slots, 256));
         ivf_count_pairs_kernel<<<g, 256, 0, s>>>(pp);
         ivf_pair_offsets_kernel<<<1, 1024, 0, s>>>(pp);
@@ -651,10 +654,11 @@ static int run_batch(annb_index* ix, bool ivf, const PreparedQueries& pq, uint64
             ix->stat_scanned += static_cast<int64_t>(h.scanned);
             ix->stat_probed += static_cast<int64_t>(h.probed);
             ix->stat_scanned_local += static_cast<int64_t>(h.local);
+            ix->stat_tc_tiles += static_cast<int64_t>(h.tiles);
         }
         const uint32_t n_unc = (cs.tensor && ix->opt_cert_fallback && ix->opt_cert_eps != 0.f && ix->shard_bound == nullptr) ? h.n_unc : 0u;
         ix->stat_uncertified = cs.tensor ? static_cast<int64_t>(h.n_unc) : 0;
-        if (!ivf && cs.tensor && n_unc >= 8 && static_cast<uint64_t>(n_unc) * 50 > nb) ix->tc_escalate = 1;   // see tc_flat_search: wide-k mode from the next batch on
+        if (!ivf && cs.tensor && n_unc >= 8 && static_cast<uint64_t>(n_unc) * 50 > nb) ix->tc_escalate = std::min(ix->tc_escalate + 1, 2);   // see tc_flat_search: k' = 32, then wide-k mode, from the next batch on
         if (n_unc == 0) return ANNB_OK;
         if (ivf) ANNB_TRY(ivf_fallback(ix, pq, k, nprobe, n_unc, preset_probes ? preset_probes : ix->s_probes.as<uint32_t>(),
                                        preset_probes ? preset_nprobes : ix->s_nprobes.as<uint32_t>(), preset_probes ? preset_pitch : cs.pitch, d_ids, d_dist, d_cnt, s));
@@ -696,6 +700,7 @@ static int search_host(annb_index* ix, bool ivf, int mode, const float* queries,
     ix->stat_scanned = 0;
     ix->stat_probed = 0;
     ix->stat_scanned_local = 0;
+    ix->stat_tc_tiles = 0;
     for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
         const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
         PreparedQueries pq;
@@ -1425,6 +1430,7 @@ int annb_ivf_search_dev(const annb_index* index, const float* d_queries, uint64_
     ix->stat_scanned = 0;
     ix->stat_probed = 0;
     ix->stat_scanned_local = 0;
+    ix->stat_tc_tiles = 0;
     for (uint64_t b0 = 0; b0 < nq; b0 += QUERY_BATCH) {
         const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, nq - b0);
         PreparedQueries pq;
@@ -1601,6 +1607,33 @@ int annb_shard_check_gathered_dev(annb_index* ix, const void* d_parts, uint64_t 
     return mark_call_done(ix, s);
 }
 
+// The same check without the read-back: the two verdict words are copied into the caller's (pinned) host buffer on `stream` and
+// the call returns at once -- the caller records an event behind it and reads h_verdict[0] (this shard's queries to refine) and
+// h_verdict[1] (bit 0: some shard has to refine, bit 1: some shard's call failed) once that event has completed.  Lets a
+// serving loop enqueue the next batch before the previous verdict is known (annb200.distributed.ShardedSearch, defer = True).
+// The list of queries to refine stays in the handle's scratch only until the handle's next search: a deferred refine repeats
+// the (synchronous) check first.
+int annb_shard_check_gathered_async_dev(annb_index* ix, const void* d_parts, uint64_t part_stride_bytes, uint64_t bound_offset_bytes, uint32_t parts,
+                                        uint32_t my_part, const float* d_merged_dist, uint64_t nq, uint32_t k, uint32_t* h_verdict, void* stream) {
+    if (!ix || !d_parts || !d_merged_dist || !h_verdict || k == 0 || parts == 0 || my_part >= parts) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument / bad shape");
+    if ((part_stride_bytes & 3) || (bound_offset_bytes & 3)) return fail(ANNB_ERR_INVALID_ARGUMENT, "misaligned shard layout");
+    if (nq > QUERY_BATCH) return fail(ANNB_ERR_UNSUPPORTED, "shard check: at most 16384 queries per call");
+    ANNB_DEVICE(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ANNB_TRY(order_after_previous(ix, s));
+    ANNB_TRY(ix->s_uncert.ensure((nq + 1) * 4));
+    ANNB_TRY(ix->s_flags.ensure(64));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_uncert.p, 0, 4, s));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 4, s));
+    shard_check_gathered_kernel<<<grid_for(nq, 256, 1u << 30), 256, 0, s>>>(static_cast<const uint8_t*>(d_parts), part_stride_bytes, bound_offset_bytes, parts,
+                                                                          my_part, d_merged_dist, nq, k, ix->s_uncert.as<uint32_t>(), ix->s_flags.as<uint32_t>());
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    ANNB_CUDA_CHECK(cudaMemcpyAsync(h_verdict, ix->s_uncert.p, 4, cudaMemcpyDeviceToHost, s));
+    ANNB_CUDA_CHECK(cudaMemcpyAsync(h_verdict + 1, ix->s_flags.p, 4, cudaMemcpyDeviceToHost, s));
+    return mark_call_done(ix, s);
+}
+
 int annb_shard_refine_dev(annb_index* ix, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe, const uint32_t* d_probes,
                           const uint32_t* d_n_probes, uint32_t probe_pitch, uint64_t* d_ids, float* d_dist, void* stream) {
     if (!ix || ix->multi || !d_queries || !d_ids || k == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument / k == 0");
@@ -1768,6 +1801,7 @@ int annb_index_get_stat(const annb_index* ix, const char* key, int64_t* out) {
     else if (k == "scanned_vectors") *out = ix->stat_scanned;
     else if (k == "probed_lists") *out = ix->stat_probed;
     else if (k == "scanned_vectors_local") *out = ix->stat_scanned_local;
+    else if (k == "tc_scan_tiles") *out = ix->stat_tc_tiles;
     else if (k == "last_path") *out = ix->stat_last_path;
     else if (k == "coarse_path") *out = ix->stat_coarse_path;
     else if (k == "fallback_queries") *out = ix->stat_fallback_queries;

@@ -845,9 +845,13 @@ uint32_t tc_bf16_terms(const annb_index* ix) {
     return ix->metric == ANNB_COSINE ? 2u : 3u;
 }
 
+// k' = 16 serves k <= 16: a query whose 16th merged value is too close to its k-th distance takes the re-rank's second chance
+// (up to 64 candidates below the scan's final threshold), and a handle whose batches still fail (tc_escalate, see run_batch)
+// moves to k' = 32 and then to wide-k mode.  Measured, self-kNN 2M x 50 k = 15: 12.1 ms (k' = 16) against 12.7 ms (k' = 32) per
+// 10 000 rows on one GPU, 1.94 against 2.62 ms on a 250k-row shard; no uncertified query either way.
 static uint32_t pick_kprime(const annb_index* ix, uint32_t k_eff) {
     if (ix->opt_tc_candidates == 16 || ix->opt_tc_candidates == 32) return std::max<uint32_t>(ix->opt_tc_candidates, k_eff <= 16 ? 16 : 32);
-    return k_eff <= 10 ? 16 : 32;
+    return (k_eff <= 16 && ix->tc_escalate == 0) ? 16 : 32;
 }
 
 // k above TC_K_LIST (one k' = 32 list per thread covers it) and up to TC_K_WIDE: "wide-k" mode.  Every (split, half tile) list
@@ -921,6 +925,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     // and a k' = 16 list's threshold then sits inside the certificate's margin of the k-th distance on data with ~1e-6 neighbour
     // gaps (measured, 1M x 256 Correlated cosine k = 10: 7.5 % of the queries uncertified with k' = 16)
     if (kind == tc::KIND_TF32X3 && kp > 128 && ix->opt_tc_candidates == 0) kprime = 32;
+    if (k_eff > TC_K_LIST) kprime = 32;
     const uint32_t nq_pad = static_cast<uint32_t>(round_up<uint64_t>(nq, tc::BM));
     // f32 queries against a BF16 index go in as two or three bf16 terms q0 + q1 [+ q2]: 16 or 24 MMAs per tile
     const uint32_t bf16_terms = tc_bf16_terms(ix);
@@ -949,11 +954,11 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     // ---- geometry ----
     const uint64_t q_tiles = nq_pad / tc::BM;
     const uint64_t db_tiles = st->n_pad / tc::BN;
-    // A handle whose batches keep failing the certificate (more than 2 % of a batch went to the exact fallback: run_batch sets
-    // tc_escalate) switches to the wide-k machinery whatever k is: the union of >= 8 unshared k' = 32 lists reaches far beyond
+    // A handle whose batches keep failing the certificate (more than 2 % of a batch went to the exact fallback: run_batch raises
+    // tc_escalate -- first to k' = 32, then to this) switches to the wide-k machinery whatever k is: the union of >= 8 unshared k' = 32 lists reaches far beyond
     // the k-th neighbour, which a wide certificate margin needs (1M x 256 Correlated cosine, k = 10: 748 uncertified queries per
     // 10 000 with a shared threshold and the 64-candidate second chance -- 65 ms per batch; 0 in wide mode -- 27 ms).
-    const bool wide_k = k_eff > TC_K_LIST || (ix->tc_escalate != 0 && ix->opt_tc_wide_k != 0);
+    const bool wide_k = k_eff > TC_K_LIST || (ix->tc_escalate >= 2 && ix->opt_tc_wide_k != 0);
     uint32_t splits_req = pick_splits(q_tiles, db_tiles, ix->opt_db_splits, kprime == 32 ? 40u : 8u);
     if (wide_k) splits_req = static_cast<uint32_t>(std::min<uint64_t>(db_tiles, std::max<uint32_t>(splits_req, (wide_k_lists(k_eff) + 1) / 2)));
     const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;

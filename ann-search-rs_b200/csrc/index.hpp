@@ -80,7 +80,7 @@ struct annb_index {
     int opt_tc_bf16_hybrid = 0; // flat tensor path, bf16 index + f32 queries: third query term in shared memory (SS-mode MMA) instead of TMEM
     int opt_tc_bf16_terms = 0;  // tensor paths, bf16 index + f32 queries: bf16 terms the query is split into (2 or 3); 0 = by metric (cosine 2, L2 3)
     int opt_tc_epi_warps = 0;   // flat tensor path, bf16 / int8 kernels: epilogue warps per TMEM lane quarter (0 = auto: four for k' = 16, 2 = two)
-    int tc_escalate = 0;        // sticky: a batch of this flat handle left more than 2 % of its queries uncertified -> later batches run in wide-k mode
+    int tc_escalate = 0;        // sticky level: a batch of this flat handle left more than 2 % of its queries uncertified -> 1: k' = 32, 2: wide-k mode
     int opt_tc_wide_k = 1;      // flat tensor path: serve 24 < k <= 128 from the union of interleaved k' = 32 lists (0: such k go to the CUDA-core path)
     int opt_tc_strided = 0;     // flat tensor path: interleave the splits' tiles over the database also for k <= 24
     int opt_tc_f32_lo_smem = 0; // flat tensor path, f32 rows of <= 128 elements: lo query piece in shared memory (frees TMEM for a third accumulator stage)
@@ -96,6 +96,7 @@ struct annb_index {
     mutable int64_t stat_launches = 0;
     mutable int64_t stat_scanned = 0, stat_probed = 0, stat_last_path = 0, stat_uncertified = 0;
     mutable int64_t stat_scanned_local = 0;   // vectors of this shard's own lists among stat_scanned
+    mutable int64_t stat_tc_tiles = 0;      // last host-buffer call: 128-row tiles executed by the tensor-core IVF scan (padded MMA work = tiles * 128 * 128 * kp)
 
     uint64_t device_bytes = 0;
 

@@ -389,6 +389,7 @@ struct PairParams {
     const uint64_t* offsets;   // global CSR offsets (task records)
     uint64_t shard_row0;
     const uint32_t* order;     // optional [nlist]: the order in which lists receive their task slots (task records only)
+    unsigned long long* stat_tiles;  // optional: receives the number of 128-row tiles the tasks will execute (sum over tasks of ceil(list rows / 128))
 };
 
 __global__ void ivf_count_pairs_kernel(PairParams p) {
@@ -438,6 +439,11 @@ __global__ void __launch_bounds__(1024) ivf_pair_offsets_kernel(PairParams p) {
     if (threadIdx.x == 0) p.pair_off[p.nlist] = s_warp[32];
     b = block_exclusive_scan_1024(b, s_warp);
     if (threadIdx.x == 0) p.task_off[p.nlist] = s_warp[32];
+    if (p.stat_tiles != nullptr) {
+        unsigned long long t = 0;
+        for (uint32_t c = lo; c < hi; c++) t += static_cast<unsigned long long>((p.cnt[c] + p.group - 1) / p.group) * ((p.offsets[c + 1] - p.offsets[c] + 127) / 128);
+        if (t) atomicAdd(p.stat_tiles, t);
+    }
     const bool reorder = p.tasks != nullptr && p.order != nullptr;
     for (uint32_t c = lo; c < hi; c++) {
         p.pair_off[c] = a; p.cursor[c] = a; p.task_off[c] = b;

@@ -90,6 +90,7 @@ def lib():
         _lib.annb_ivf_search_probes_shard_dev.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, u32, vp, vp, vp, vp]
         _lib.annb_shard_check_dev.argtypes = [vp, vp, vp, u64, u32, C.POINTER(u32), vp]
         _lib.annb_shard_check_gathered_dev.argtypes = [vp, vp, u64, u64, u32, u32, vp, u64, u32, C.POINTER(u32), C.POINTER(u32), vp]
+        _lib.annb_shard_check_gathered_async_dev.argtypes = [vp, vp, u64, u64, u32, u32, vp, u64, u32, vp, vp]
         _lib.annb_shard_refine_dev.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, u32, vp, vp, vp]
         _lib.annb_merge_shards_dev.argtypes = [vp, u64, u64, u32, u64, u32, vp, vp, vp, vp]
         _lib.annb_flat_create_multi.argtypes = [C.POINTER(vp), vp, u64, u32, i32, i32, vp, i32]

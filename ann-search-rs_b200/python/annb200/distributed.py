@@ -117,8 +117,14 @@ class ShardedSearch:
                (annb_shard_refine_dev: exact kernels for the listed queries), and only then the exchange is repeated.
 
     Everything is enqueued on `stream` (default: torch's current stream), collectives included.  A rank whose library
-    call fails still enters every collective of the step; the verdict all-reduce carries the error, and all ranks raise
-    together instead of leaving the others blocked in NCCL."""
+    call fails still enters every collective of the step; the gathered status words carry the error, and all ranks raise
+    together instead of leaving the others blocked in NCCL.
+
+    defer=True (a serving loop): the call returns as soon as the step is enqueued -- the verdict words travel to pinned host
+    memory behind it -- and `resolve()` finishes the step later: it waits for the verdict and, if some shard has to refine,
+    runs the refine + second exchange (a collective path: every rank reaches the same verdict from the gathered bounds, so all
+    ranks take it together).  The returned tensors are final only after resolve(); an object holds one pending step, so a
+    loop that wants the host one step ahead of the devices alternates two objects (bench.py does)."""
 
     def __init__(self, index, nq: int, dim: int, k: int, nprobe: int = 0, group=None, device=None):
         import torch
@@ -138,6 +144,9 @@ class ShardedSearch:
         self.status = self.mine[nq * k * 12 + nq * 4:nq * k * 12 + nq * 4 + 4].view(torch.int32)   # 1 = this rank's library call failed
         self.status.zero_()
         self.refined_queries = 0          # cumulative: queries this rank recomputed exactly after the merged check
+        self.h_verdict = torch.zeros((2,), dtype=torch.int32).pin_memory()   # deferred steps: {mine, any} land here
+        self.ev = torch.cuda.Event()
+        self._pending = None              # (queries, stream object, error) of a deferred step awaiting resolve()
         self.is_ivf = bool(index.info().is_ivf)
         if self.is_ivf:
             self.pitch = probe_pitch(nprobe or int(max(1, index.info().nlist ** 0.5)))
@@ -155,8 +164,9 @@ class ShardedSearch:
         return L.annb_merge_shards_dev(self.gathered.data_ptr(), self.block, self.nq * self.k * 8, self.world, self.nq, self.k, self.out_ids.data_ptr(),
                                        self.out_dist.data_ptr(), None, st)
 
-    def __call__(self, queries, stream=None):
-        """queries: [nq, dim] float32 CUDA tensor (the whole batch, on every rank).  Returns (ids, dist) on the device."""
+    def __call__(self, queries, stream=None, defer=False):
+        """queries: [nq, dim] float32 CUDA tensor (the whole batch, on every rank).  Returns (ids, dist) on the device
+        (defer=True: final only after resolve(); `queries` must stay untouched until then)."""
         import ctypes as C
 
         import torch
@@ -164,6 +174,7 @@ class ShardedSearch:
 
         from . import AnnSearchError, lib
         L = lib()
+        self.resolve()
         st_obj = stream or torch.cuda.current_stream(self.dev)
         st = st_obj.cuda_stream
         nq, dim, k = self.nq, self.dim, self.k
@@ -199,29 +210,67 @@ class ShardedSearch:
             if rc != 0 and err is None:
                 err = failed(rc)
             # Every rank holds every shard's bounds and status now: the verdict needs no further collective.
-            mine, any_ = C.c_uint32(0), C.c_uint32(0)
-            rc = L.annb_shard_check_gathered_dev(self.index.handle, self.gathered.data_ptr(), self.block, nq * k * 12, self.world, self.rank,
-                                                 self.out_dist.data_ptr(), nq, k, C.byref(mine), C.byref(any_), st)      # (one read-back: synchronises)
-            if rc != 0 and err is None:
-                err = failed(rc)
-            if err is not None or (any_.value & 2):
-                raise err if err is not None else RuntimeError("another rank failed in the sharded search step")
-            if any_.value & 1:
-                if mine.value:
-                    rc = L.annb_shard_refine_dev(self.index.handle, queries.data_ptr(), nq, dim, k, self.nprobe,
-                                                 self.probes.data_ptr() if self.is_ivf else None, self.nprobes.data_ptr() if self.is_ivf else None,
-                                                 self.pitch if self.is_ivf else 0, self.ids.data_ptr(), self.dist.data_ptr(), st)
-                    if rc != 0:
-                        err = failed(rc)
-                    self.refined_queries += int(mine.value)
-                self.status.fill_(1 if err is not None else 0)
-                rc = self._exchange_and_merge(L, st)
-                if rc == 0:     # (status words only: the refined rows are exact)
-                    rc = L.annb_shard_check_gathered_dev(self.index.handle, self.gathered.data_ptr(), self.block, nq * k * 12, self.world, self.rank,
-                                                         self.out_dist.data_ptr(), nq, k, C.byref(mine), C.byref(any_), st)
-                if err is not None or rc != 0 or (any_.value & 2):
-                    raise err if err is not None else RuntimeError("a rank failed while refining the sharded search step")
+            if defer:
+                rc = L.annb_shard_check_gathered_async_dev(self.index.handle, self.gathered.data_ptr(), self.block, nq * k * 12, self.world, self.rank,
+                                                           self.out_dist.data_ptr(), nq, k, self.h_verdict.data_ptr(), st)
+                if rc != 0 and err is None:
+                    err = failed(rc)
+                self.ev.record(st_obj)
+                self._pending = (queries, st_obj, err)
+                return self.out_ids, self.out_dist
+            self._finish(queries, st_obj, err)
         return self.out_ids, self.out_dist
+
+    def resolve(self):
+        """Finish a deferred step (no-op when none is pending).  Collective when a refine is needed: call it on all ranks."""
+        if self._pending is None:
+            return
+        import torch
+        queries, st_obj, err = self._pending
+        self._pending = None
+        self.ev.synchronize()
+        mine, any_ = int(self.h_verdict[0]), int(self.h_verdict[1])
+        if err is not None or (any_ & 2):
+            raise err if err is not None else RuntimeError("another rank failed in the sharded search step")
+        if any_ & 1:
+            # the handle may have searched since: the synchronous check rebuilds the list of queries to refine, then the usual path
+            with torch.cuda.stream(st_obj):
+                self._finish(queries, st_obj, None)
+
+    def _finish(self, queries, st_obj, err):
+        """Synchronous verdict of the step whose blocks are in self.gathered / self.out_dist, refine + second exchange if needed."""
+        import ctypes as C
+
+        from . import AnnSearchError, lib
+        L = lib()
+        st = st_obj.cuda_stream
+        nq, dim, k = self.nq, self.dim, self.k
+
+        def failed(rc):
+            return AnnSearchError(rc, L.annb_last_error().decode("utf-8", "replace"))
+
+        mine, any_ = C.c_uint32(0), C.c_uint32(0)
+        rc = L.annb_shard_check_gathered_dev(self.index.handle, self.gathered.data_ptr(), self.block, nq * k * 12, self.world, self.rank,
+                                             self.out_dist.data_ptr(), nq, k, C.byref(mine), C.byref(any_), st)      # (one read-back: synchronises)
+        if rc != 0 and err is None:
+            err = failed(rc)
+        if err is not None or (any_.value & 2):
+            raise err if err is not None else RuntimeError("another rank failed in the sharded search step")
+        if any_.value & 1:
+            if mine.value:
+                rc = L.annb_shard_refine_dev(self.index.handle, queries.data_ptr(), nq, dim, k, self.nprobe,
+                                             self.probes.data_ptr() if self.is_ivf else None, self.nprobes.data_ptr() if self.is_ivf else None,
+                                             self.pitch if self.is_ivf else 0, self.ids.data_ptr(), self.dist.data_ptr(), st)
+                if rc != 0:
+                    err = failed(rc)
+                self.refined_queries += int(mine.value)
+            self.status.fill_(1 if err is not None else 0)
+            rc = self._exchange_and_merge(L, st)
+            if rc == 0:     # (status words only: the refined rows are exact)
+                rc = L.annb_shard_check_gathered_dev(self.index.handle, self.gathered.data_ptr(), self.block, nq * k * 12, self.world, self.rank,
+                                                     self.out_dist.data_ptr(), nq, k, C.byref(mine), C.byref(any_), st)
+            if err is not None or rc != 0 or (any_.value & 2):
+                raise err if err is not None else RuntimeError("a rank failed while refining the sharded search step")
 
 
 def ivf_search_sharded(index, queries, k: int, nprobe: int, out_ids=None, out_dist=None, group=None, stream=None):

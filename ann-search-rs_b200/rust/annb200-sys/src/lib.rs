@@ -88,6 +88,8 @@ extern "C" {
     pub fn annb_shard_check_gathered_dev(index: *mut annb_index, d_parts: *const c_void, part_stride_bytes: u64, bound_offset_bytes: u64, parts: u32,
                                          my_part: u32, d_merged_dist: *const f32, nq: u64, k: u32, out_mine: *mut u32, out_any: *mut u32,
                                          stream: *mut c_void) -> c_int;
+    pub fn annb_shard_check_gathered_async_dev(index: *mut annb_index, d_parts: *const c_void, part_stride_bytes: u64, bound_offset_bytes: u64, parts: u32,
+                                               my_part: u32, d_merged_dist: *const f32, nq: u64, k: u32, h_verdict: *mut u32, stream: *mut c_void) -> c_int;
     pub fn annb_shard_refine_dev(index: *mut annb_index, d_queries: *const f32, nq: u64, dim: u32, k: u32, nprobe: u32, d_probes: *const u32,
                                  d_n_probes: *const u32, probe_pitch: u32, d_ids: *mut u64, d_dist: *mut f32, stream: *mut c_void) -> c_int;
     pub fn annb_index_shard_count(index: *const annb_index, out: *mut u32) -> c_int;

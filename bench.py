@@ -265,10 +265,13 @@ def apply_options(args, index):
         index.set_option(key, int(val))
 
 
-def timed_run(c, index, step_device, step_host, nq, steps, warmup):
+def timed_run(c, index, step_device, step_host, nq, steps, warmup, flush=None):
     """W untimed warm-up steps, then exactly `steps` steps bracketed by barrier + synchronize on both sides, CUDA events on
-    the launching stream, max over ranks; then the same for the host-buffer (end-to-end) step, wall clock."""
+    the launching stream, max over ranks; then the same for the host-buffer (end-to-end) step, wall clock.
+    flush: finishes steps the device loop left pending (sharded runs defer every step's verdict by one step); it runs INSIDE
+    the timed region, so a refine any verdict asks for is paid for there."""
     torch, dist = c.torch, c.dist
+    flush = flush or (lambda: None)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -282,6 +285,7 @@ def timed_run(c, index, step_device, step_host, nq, steps, warmup):
     stream = torch.cuda.current_stream()
     for _ in range(warmup):
         step_device()
+    flush()
     sync_all()
     index.set_option("time_kernels", 1)          # resets the dominant-kernel accumulator after warm-up
     launches0 = index.get_stat("kernel_launches")
@@ -292,6 +296,7 @@ def timed_run(c, index, step_device, step_host, nq, steps, warmup):
     e0.record(stream)
     for _ in range(steps):
         step_device()
+    flush()
     e1.record(stream)
     sync_all()
     torch.cuda.profiler.stop()
@@ -339,16 +344,29 @@ class Searcher:
         self.self_rows = self_rows                     # (begin, end): the batch is these resident rows (1 GPU / single process)
         self.extra_launches = 0
         self.sharded = None
+        self.pair = None
+        self.turn = 0
         if c.world > 1:
             from annb200 import distributed as D
-            self.sharded = D.ShardedSearch(index, nq, dim, k, nprobe if ivf else 0, None, c.dev)
+            # two step objects (each with its own exchange buffers) take turns in the device loop: step i + 1 is enqueued before
+            # the verdict of step i is read, so the host runs one step ahead of the devices (ShardedSearch, defer=True)
+            self.pair = [D.ShardedSearch(index, nq, dim, k, nprobe if ivf else 0, None, c.dev) for _ in range(2)]
+            self.sharded = self.pair[0]
+
+    def flush(self):
+        if self.pair is not None:
+            for s in self.pair:
+                s.resolve()
 
     def step_device(self):
         c, lib, annb200 = self.c, self.c.lib, self.c.annb
         sp = c.torch.cuda.current_stream().cuda_stream
-        if self.sharded is not None:
-            self.sharded(self.dq)
-            self.extra_launches += 1                   # the merge kernel
+        if self.pair is not None:
+            s = self.pair[self.turn & 1]
+            self.turn += 1
+            s(self.dq, defer=True)                     # (resolves its own previous step first)
+            self.sharded = s                           # device_result() reads the last step's object
+            self.extra_launches += 2                   # the merge and check kernels
             return
         if self.ivf:
             annb200._check(lib.annb_ivf_search_dev(self.index.handle, self.dq.data_ptr(), self.nq, self.dim, self.k, self.nprobe, self.out_ids.data_ptr(),
@@ -361,6 +379,7 @@ class Searcher:
         c, lib, annb200 = self.c, self.c.lib, self.c.annb
         if self.sharded is not None:
             # one process per GPU: pinned host queries -> device, sharded step, merged result -> pinned host (no bounce through the host in between)
+            self.flush()
             self.dq.copy_(self.hq, non_blocking=True)
             ids, dst = self.sharded(self.dq)
             self.h_ids.copy_(ids, non_blocking=True)
@@ -378,13 +397,15 @@ class Searcher:
                                                 self.h_dist.data_ptr(), self.h_cnt.data_ptr()))
 
     def device_result(self):
+        self.flush()
         if self.sharded is not None:
             return self.sharded.out_ids.cpu().numpy(), self.sharded.out_dist.cpu().numpy()
         return self.out_ids.cpu().numpy(), self.out_dist.cpu().numpy()
 
 
-def tensor_roofline(c, dtype, flops, dom_s, kernel, tf32_peak):
-    """Roofline row of a tensor-core kernel: achieved = algorithmic flops / kernel time."""
+def tensor_roofline(c, dtype, flops, dom_s, kernel, tf32_peak, bf16_terms=2):
+    """Roofline row of a tensor-core kernel: achieved = algorithmic flops / kernel time.
+    bf16_terms: bf16 terms the f32 query is fed as (library default: 2 for cosine, 3 for squared Euclidean)."""
     peaks = c.peaks
     if dtype == "f32":
         pipe_alt = peaks["bf16_tflops"] / 2.0
@@ -395,8 +416,8 @@ def tensor_roofline(c, dtype, flops, dom_s, kernel, tf32_peak):
                 f"{c.peak_src} bf16 burst peak / 2 (TF32 pipe) / 3 (3xTF32 terms)")
     elif dtype == "bf16":
         pipe_peak = pipe_alt = peaks["bf16_tflops"]
-        peak, terms = pipe_peak, 2
-        note = f"{c.peak_src} bf16 burst peak (the f32 query is fed as bf16 terms, see 'executed')"
+        peak, terms = pipe_peak, bf16_terms
+        note = f"{c.peak_src} bf16 burst peak (the f32 query is fed as {bf16_terms} bf16 terms, see 'executed')"
     else:
         pipe_peak = pipe_alt = peaks["bf16_tflops"] * 2.0
         peak, terms = pipe_peak, 1
@@ -475,7 +496,7 @@ def bench_flat(c, n, dim, nq, k, metric, dtype, self_queries, tf32_peak, on_gpu_
         index = annb200.ExhaustiveIndexB200.new(data[lo:hi], met, dt, device=c.local_rank, id_base=lo, sq8_scales=sq8_scales)
     apply_options(args, index)
     se = Searcher(c, index, False, nq, dim, k, 0, queries, self_rows=(0, nq) if (self_queries and c.world == 1) else None)
-    r = timed_run(c, index, se.step_device, se.step_host, nq, args.steps, args.warmup)
+    r = timed_run(c, index, se.step_device, se.step_host, nq, args.steps, args.warmup, se.flush)
     last_path = index.get_stat("last_path")
     uncertified = index.get_stat("uncertified")
     fallback_q = index.get_stat("fallback_queries")
@@ -485,7 +506,8 @@ def bench_flat(c, n, dim, nq, k, metric, dtype, self_queries, tf32_peak, on_gpu_
         return None
     rows_local = (n + c.shards - 1) // c.shards
     flops = 2.0 * nq * rows_local * dim                          # algorithmic flops per launch: 2 * nq * n_local * d
-    roofline = tensor_roofline(c, dtype, flops, r["dom_s"], "flat distance + top-k select (flat_tc_kernel)", tf32_peak)
+    roofline = tensor_roofline(c, dtype, flops, r["dom_s"], "flat distance + top-k select (flat_tc_kernel)", tf32_peak,
+                               bf16_terms=(1 if self_queries else (2 if metric == "cosine" else 3)))
     roofline["path"] = {0: "auto", 1: "simt (CUDA cores)", 2: "tensor (tcgen05)"}.get(last_path, str(last_path))
     if last_path != 2:
         roofline["executed"]["mma_terms_per_element"] = 0
@@ -503,7 +525,7 @@ def bench_flat(c, n, dim, nq, k, metric, dtype, self_queries, tf32_peak, on_gpu_
                       "sq8": "int8 (i32 accumulate)"}[dtype],
             "data": "synthetic",
             "config": {"workload": w, "n": n, "dim": dim, "nq": nq, "k": k,
-                       "sharding": (f"database rows over {c.shards} GPUs, " + ("one process, peer copies" if c.single else "one process per GPU, one NCCL all-gather"))
+                       "sharding": (f"database rows over {c.shards} GPUs, " + ("one process, peer copies" if c.single else "one process per GPU, one NCCL all-gather; device loop: verdict of step i read after step i+1 is enqueued"))
                        if c.shards > 1 else "none",
                        "l2_policy": "inputs larger than L2 (database streamed every step)"},
             "clocks": r["clocks"],
@@ -511,6 +533,8 @@ def bench_flat(c, n, dim, nq, k, metric, dtype, self_queries, tf32_peak, on_gpu_
                     "d2h_bytes_per_step": int(nq * k * 12 + (nq * 4 if c.world == 1 else 0)), "ms_per_step": r["e2e_s"] * 1e3},
             "gpu_launches": r["launches"] + se.extra_launches, "roofline": roofline, "uncertified_queries_last_step": int(uncertified),
             "fallback_queries_total": int(fallback_q)}
+    if se.pair is not None:
+        line["shard_refined_queries_total"] = int(sum(s.refined_queries for s in se.pair))
     if self_queries:
         line["full_knn_graph_seconds_extrapolated"] = n / r["qps"]
     # parity sample against the CPU oracle, recall for the quantised indices, CPU baseline
@@ -582,7 +606,7 @@ def bench_ivf_set(c, n, dim, nq, k, nlist, entries, tf32_peak):
             torch.cuda.empty_cache()
         for (_, nprobe) in [e for e in entries if e[0] == dtype]:
             se = Searcher(c, index, True, nq, dim, k, nprobe, queries)
-            r = timed_run(c, index, se.step_device, se.step_host, nq, args.steps, args.warmup)
+            r = timed_run(c, index, se.step_device, se.step_host, nq, args.steps, args.warmup, se.flush)
             last_path = index.get_stat("last_path")
             fallback_q = index.get_stat("fallback_queries")
             dev_ids, dev_dist = se.device_result()
@@ -604,9 +628,22 @@ def bench_ivf_set(c, n, dim, nq, k, nlist, entries, tf32_peak):
                    "note": "a list tile loaded once serves up to 128 queries of the batch, so the per-query (algorithmic) byte rate exceeds the HBM peak by design; "
                            "dram_gbs_from_traffic is what the kernel really moved (ncu), when a capture of this workload is committed"}
             if last_path == 2:
-                roofline = tensor_roofline(c, dtype, 2.0 * scanned_local * dim, r["dom_s"], "ivf grouped list scan + top-k' select (ivf_tc_kernel)", tf32_peak)
+                roofline = tensor_roofline(c, dtype, 2.0 * scanned_local * dim, r["dom_s"], "ivf grouped list scan + top-k' select (ivf_tc_kernel)", tf32_peak,
+                                           bf16_terms=3)
                 roofline["algorithmic_flops_per_launch"] = 2.0 * scanned_local * dim
                 roofline["executed"]["note"] = "padded (list x 128-query group) tiles execute more MMA work than the algorithmic count"
+                tiles = index.get_stat("tc_scan_tiles") if (c.world == 1 and not c.single) else 0
+                if tiles and r["dom_s"]:
+                    # what the tensor pipe really executed: every task multiplies whole 128-row tiles of its list by a 128-row query group
+                    # (groups hold fewer than 128 queries at this batch size), K padded to the 128-byte slab, all MMA terms
+                    kp = -(-dim // {"f32": 32, "bf16": 64, "sq8": 128}[dtype]) * {"f32": 32, "bf16": 64, "sq8": 128}[dtype]
+                    ex = roofline["executed"]
+                    padded = tiles * 128.0 * 128.0 * kp * 2.0 * ex["mma_terms_per_element"]
+                    ex["padded"] = {"tiles_per_launch": int(tiles), "tflops": padded / r["dom_s"] / 1e12,
+                                    "frac_of_pipe_peak": padded / r["dom_s"] / 1e12 / ex["pipe_peak"],
+                                    "query_group_fill": (2.0 * scanned_local * dim * ex["mma_terms_per_element"]) / padded,
+                                    "note": "tiles counted by the library (stat tc_scan_tiles) for the same batch; the padded figure is the tensor-pipe utilisation, "
+                                            "the algorithmic one (frac) is what the metric pays for"}
                 roofline["hbm_view"] = hbm
                 roofline["path"] = "tensor (tcgen05)"
             else:
@@ -626,13 +663,15 @@ def bench_ivf_set(c, n, dim, nq, k, nlist, entries, tf32_peak):
                      "dtype": {"f32": "f32 (3xTF32 select + f32 exact re-rank)", "bf16": "bf16 (f32 accumulate)", "sq8": "int8 (i32 accumulate)"}[dtype],
                      "config": {"workload": f"IVF {dtype} euclidean, {n}x{dim} {kind} synthetic, nlist={nlist}, nprobe={nprobe}, {nq}-query batch, k={k}",
                                 "sharding": (f"inverted lists over {c.shards} GPUs, " +
-                                             ("one process, peer copies" if c.single else "one process per GPU, probe exchange + one NCCL all-gather"))
+                                             ("one process, peer copies" if c.single else "one process per GPU, probe exchange + one NCCL all-gather; device loop: verdict of step i read after step i+1 is enqueued"))
                                 if c.shards > 1 else "none",
                                 "algorithmic_bytes_per_query": scanned * per_vec / nq, "l2_policy": "inputs larger than L2"},
                      "clocks": r["clocks"],
                      "e2e": {"value": r["e2e_qps"], "unit": "queries/s", "h2d_bytes_per_step": int(nq * dim * 4),
                              "d2h_bytes_per_step": int(nq * k * 12 + (nq * 4 if c.world == 1 else 0)), "ms_per_step": r["e2e_s"] * 1e3},
                      "gpu_launches": r["launches"] + se.extra_launches, "roofline": roofline, "fallback_queries_total": int(fallback_q)}
+            if se.pair is not None:
+                entry["shard_refined_queries_total"] = int(sum(s.refined_queries for s in se.pair))
             if c.shards > 1:
                 entry["device_vs_e2e"] = {"ids_equal": bool(np.array_equal(dev_ids, got_ids)),
                                           "dist_bits_equal": bool(np.array_equal(dev_dist.view(np.uint32), got_d.view(np.uint32)))}

@@ -289,6 +289,16 @@ int annb_shard_check_dev(annb_index* index, const float* d_bound, const float* d
 int annb_shard_check_gathered_dev(annb_index* index, const void* d_parts, uint64_t part_stride_bytes, uint64_t bound_offset_bytes,
                                   uint32_t parts, uint32_t my_part, const float* d_merged_dist, uint64_t nq, uint32_t k,
                                   uint32_t* out_mine, uint32_t* out_any, void* stream);
+
+/* annb_shard_check_gathered_dev without the read-back: the verdict words are copied into the caller's pinned host buffer
+ * h_verdict[2] on `stream` and the call returns at once; h_verdict[0] = this shard's queries to refine, h_verdict[1] = bit 0:
+ * some shard has to refine, bit 1: some shard's call failed -- valid once an event recorded behind the call has completed.  A
+ * serving loop can enqueue the next batch before the previous verdict is known; the list of queries to refine lives in the handle
+ * only until its next search, so a deferred refine repeats the synchronous check first. */
+int annb_shard_check_gathered_async_dev(annb_index* index, const void* d_parts, uint64_t part_stride_bytes, uint64_t bound_offset_bytes,
+                                        uint32_t parts, uint32_t my_part, const float* d_merged_dist, uint64_t nq, uint32_t k,
+                                        uint32_t* h_verdict, void* stream);
+
 int annb_shard_refine_dev(annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,
                           const uint32_t* d_probes, const uint32_t* d_n_probes, uint32_t probe_pitch, uint64_t* d_ids,
                           float* d_dist, void* stream);
@@ -343,7 +353,11 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
  *               "ivf_tc_coarse" (1 = rank the centroids on the tensor cores when nlist >= 512, 0 = CUDA-core ranking only),
  *               "cert_eps_log2" (error bound assumed by the coverage certificate of the tensor paths: negative = 2^value, 0 = certificate off,
  *               1 = derived per kernel from its MMA count, the default -- DESIGN.md section 3), "async_dev" (see Conventions),
- *               "cert_fallback" (1 = queries that fail the certificate are recomputed on the exact CUDA-core path)
+ *               "cert_fallback" (1 = queries that fail the certificate are recomputed on the exact CUDA-core path),
+ *               "tc_wide_k" (flat tensor path: 1 = serve 24 < k <= 256 -- the reference's radix-select range, src/gpu/topk_gpu.rs:95 --
+ *               from the union of interleaved k' = 32 lists, and let a handle whose batches fail the certificate switch to that mode;
+ *               0 = such k go to the CUDA-core path), "tc_strided" (1 = interleave the splits' tiles over the database also for k <= 24),
+ *               "tc_f32_lo_smem" (f32 rows of <= 128 elements: 1 = lo query piece in shared memory, a third accumulator stage in TMEM)
  *   get_stat  : "kernel_launches" (cumulative), "scanned_vectors" (IVF, last call: sum of probed
  *               list lengths), "scanned_vectors_local" (the part of it that lies in this handle's own lists),
  *               "probed_lists" (last call), "last_path" (annb_path actually used),
@@ -351,6 +365,7 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
  *               "uncertified" (tensor path, last call: queries that failed the coverage certificate),
  *               "fallback_queries" (cumulative: queries recomputed on the exact path),
  *               "cert_eps_bits" (f32 bit pattern of the error bound the last tensor-path certificate assumed),
+ *               "tc_escalated" (flat: 1 once a batch left more than 2 % of its queries uncertified -- later batches run in wide-k mode),
  *               "dominant_kernel_ns" / "dominant_kernel_launches" (with "time_kernels": summed device time and count
  *               of the dominant kernel -- flat distance+select kernel or IVF list-scan kernel -- since the option was set) */
 int annb_index_set_option(annb_index* index, const char* key, int64_t value);

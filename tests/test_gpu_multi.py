@@ -197,3 +197,55 @@ def test_shard_mode_certificate_against_the_merged_result(gpu, kind):
         local += h.get_stat("fallback_queries") - f0
     print(f"\\n[shard mode {kind}] queries refined after the merged check: {refined}; recomputed under local certification: {local}")
     assert refined <= local
+
+
+@pytest.mark.parametrize("kind", ["flat", "ivf"])
+def test_sharded_search_deferred_verdict(gpu, kind):
+    """ShardedSearch on a one-rank NCCL group: a deferred step (verdict read later, resolve()) gives the rows of the immediate
+    step and of the oracle, also when the verdict asks for a refine (forced with a pessimistic certificate bound), and two
+    objects can take turns on one handle (the serving loop of bench.py)."""
+    import socket
+    import torch
+    import torch.distributed as dist
+    from annb200 import distributed as D
+    own_group = not dist.is_initialized()
+    if own_group:
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=0, world_size=1)
+    try:
+        dev = torch.device("cuda:0")
+        torch.cuda.set_device(dev)
+        data = datagen.correlated(60_000, 64, seed=33)
+        q = datagen.subsample_with_noise(data, 1500, seed=33)
+        nq, dim, k = q.shape[0], 64, 10
+        dq = torch.from_numpy(q).to(dev)
+        if kind == "flat":
+            ref = o.flat_search(o.build_flat(data, o.L2), q, k)
+            h = annb200.ExhaustiveIndexB200.new(data, annb200.L2, annb200.F32)
+            nprobe = 0
+        else:
+            nprobe = 12
+            ci = o.build_ivf(data, o.L2, nlist=128, kmeans_iters=4)
+            ref = o.ivf_search(ci, q, k, nprobe=nprobe)
+            h = annb200.IvfIndexB200.from_parts(ci.vectors, ci.centroids, ci.offsets, ci.original_ids, ci.dtype, ci.metric)
+        a, b = D.ShardedSearch(h, nq, dim, k, nprobe, None, dev), D.ShardedSearch(h, nq, dim, k, nprobe, None, dev)
+        ids, dd = a(dq)
+        torch.cuda.synchronize()
+        assert_exact(ids.cpu().numpy(), dd.cpu().numpy(), ref[0], ref[1], f"immediate {kind}")
+        for eps in (1, -3):                       # derived bound; absurd bound: (nearly) every query is refined after the merged check
+            h.set_option("cert_eps_log2", eps)
+            r0 = a.refined_queries + b.refined_queries
+            a(dq, defer=True)
+            b(dq, defer=True)                     # enqueued before a's verdict is read
+            a.resolve()
+            b.resolve()
+            torch.cuda.synchronize()
+            for s in (a, b):
+                assert_exact(s.out_ids.cpu().numpy(), s.out_dist.cpu().numpy(), ref[0], ref[1], f"deferred {kind} eps {eps}")
+            if eps == -3:
+                assert a.refined_queries + b.refined_queries - r0 > nq, "the pessimistic bound should have forced refines on both steps"
+    finally:
+        if own_group:
+            dist.destroy_process_group()

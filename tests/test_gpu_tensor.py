@@ -346,9 +346,10 @@ def test_escalation_to_wide_mode_after_an_uncertified_batch(gpu):
     g, c = _pair(data, "f32", "l2")
     ref = o.flat_search(c, q, 10)
     g.set_option("cert_eps_log2", -6)
-    ids, d, _ = g.query_batch(q, 10)
-    assert g.get_stat("tc_escalated") == 1 and g.get_stat("fallback_queries") > 8
-    assert_exact(ids, d, ref[0], ref[1], "before escalation")
+    for level in (1, 2):     # k' = 32, then wide-k mode
+        ids, d, _ = g.query_batch(q, 10)
+        assert g.get_stat("tc_escalated") == level and g.get_stat("fallback_queries") > 8
+        assert_exact(ids, d, ref[0], ref[1], f"escalation level {level}")
     g.set_option("cert_eps_log2", 1)
     ids, d, _ = g.query_batch(q, 10)
     assert g.get_stat("last_path") == annb200.PATH_TENSOR
