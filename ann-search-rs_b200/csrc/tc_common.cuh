@@ -684,8 +684,25 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         }
         __syncthreads();
     } else {
+    const bool certify = (p.uncert_count != nullptr || p.out_bound != nullptr) && p.cert_eps > 0.f;
+    // Outcome of the first test, predicted from the approximate values alone (no memory traffic): the k'-th merged value must
+    // clear the k-th candidate's value by the certificate's margin.  A query predicted to fail (on squared distances most do:
+    // |x|^2 dwarfs the neighbour gaps) skips the k'-candidate pass and goes straight to the 64-candidate one, whose certificate
+    // is the stronger of the two anyway -- one row-gather round trip and one sort per query instead of two.  A wrong prediction
+    // costs time only: both passes certify on their own terms.
+    bool direct = false;
+    if (certify && p.gtau != nullptr && n_cand > p.kp && p.k_eff <= p.kp) {
+        const float a_kp = key_dist(keys[p.kp - 1]), a_k = key_dist(keys[p.k_eff - 1]);
+        const double qn2 = (s_qn2w[0] + s_qn2w[1]) + (s_qn2w[2] + s_qn2w[3]);
+        double d_pred;       // distance the k-th candidate's approximate value stands for
+        if (MET == MET_L2) d_pred = static_cast<double>(a_k) + qn2;
+        else { double qn = sqrt(qn2); if constexpr (QT != QT_I8) qn = static_cast<double>(s_qn); d_pred = qn > 0.0 ? static_cast<double>(a_k) / qn + 1.0 : 0.0; }
+        direct = !(bound_of(a_kp) > d_pred);
+    }
+    if (threadIdx.x == 0) s_extend = direct ? 1 : 0;
+    if (threadIdx.x == 0 && p.out_bound != nullptr) p.out_bound[q] = INFINITY;
+    if (!direct) {
     exact_range(p.kp);
-    if (threadIdx.x == 0) s_extend = 0;
     __syncthreads();
     if (threadIdx.x < 32) bitonic_sort_keys<false>(exact, 64, threadIdx.x, 32);
     __syncthreads();
@@ -693,8 +710,6 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     // this shard's un-re-ranked rows cannot lie; the caller tests it against the k-th distance of the MERGED result
     // (annb_shard_check_dev) -- a shard holding only far lists of a query need not be exact about candidates that cannot
     // reach the global top-k.
-    const bool certify = (p.uncert_count != nullptr || p.out_bound != nullptr) && p.cert_eps > 0.f;
-    if (threadIdx.x == 0 && p.out_bound != nullptr) p.out_bound[q] = INFINITY;
     if (threadIdx.x == 0 && certify) {
         const uint64_t a_key = keys[p.kp - 1];                       // k'-th merged approximate key (sentinel: every row was re-ranked)
         const uint64_t d_key = exact[p.k_eff - 1];                   // k-th exact key (sentinel: fewer than k rows exist)
@@ -707,6 +722,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
             else if (p.out_bound == nullptr) p.uncert_list[atomicAdd(p.uncert_count, 1u)] = static_cast<uint32_t>(q);
         }
     }
+    }   // !direct
     __syncthreads();
     if (s_extend) {
         exact_range(min(n_cand, 64u));

@@ -1,5 +1,5 @@
 """Prints the role wait-cycle counters of CTA 0 of the IVF tensor-core scan kernel (debug instrumentation).
-usage: python tools/ivf_cycles.py [n] [nq] [nprobe] [dtype: f32|bf16|sq8]"""
+usage: python tools/ivf_cycles.py [n] [nq] [nprobe] [dtype: f32|bf16|sq8] [world: the handle holds the first of `world` list shards]"""
 import ctypes as C, os, sys
 import numpy as np
 import torch
@@ -11,6 +11,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 nq = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000
 nprobe = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 dts = sys.argv[4].split(",") if len(sys.argv) > 4 else ["f32"]
+world = int(sys.argv[5]) if len(sys.argv) > 5 else 1
 dim, nlist, k = 128, 4096, 10
 dev = torch.device("cuda:0")
 data = gs.correlated_gpu(n, dim, dev, seed=42)
@@ -20,7 +21,12 @@ lib.annb_debug_fetch_cycles.argtypes = [C.c_void_p, C.c_void_p]
 for name in dts:
     dt = {"f32": annb200.F32, "bf16": annb200.BF16, "sq8": annb200.SQ8}[name]
     parts = gs.build_ivf_parts_gpu(data, nlist, dt, 0, seed=42, kmeans_iters=8)
-    ix = gs.ivf_handle_from_parts(parts, n, dim, dt, annb200.L2, 0)
+    if world > 1:
+        from annb200 import distributed as D
+        lb, le = D.list_ranges(parts["offsets"], world)[0]
+        ix = gs.ivf_handle_from_parts(parts, n, dim, dt, annb200.L2, 0, lb, le)
+    else:
+        ix = gs.ivf_handle_from_parts(parts, n, dim, dt, annb200.L2, 0)
     ix.set_option("tc_debug", 1)
     ids = torch.empty((nq, k), dtype=torch.int64, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream
