@@ -626,6 +626,12 @@ static int ivf_fallback(annb_index* ix, const PreparedQueries& pq, uint32_t k, u
     return ANNB_OK;
 }
 
+// ids[i] = map[ids[i]] (positions -> original ids); out-of-range entries (padding) are left alone
+static __global__ void map_ids_kernel(uint64_t* __restrict__ ids, uint64_t count, const uint64_t* __restrict__ map, uint64_t n) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i < count && ids[i] < n) ids[i] = map[ids[i]];
+}
+
 constexpr uint64_t QUERY_BATCH = 16384;
 
 // One batch, from prepared queries to final results in the device buffers d_*: enqueue, read the status words back once
@@ -1410,6 +1416,74 @@ int annb_ivf_search_self(const annb_index* index, uint64_t pos_begin, uint64_t p
     if (pos_begin > pos_end || pos_end > index->n) return fail(ANNB_ERR_INVALID_ARGUMENT, "position range outside the index");
     return search_host(const_cast<annb_index*>(index), true, 1, nullptr, pos_begin, pos_end - pos_begin, k, nprobe, scatter_to_original,
                        out_ids, out_dist, out_counts);
+}
+
+// KnnValidation::validate_index (src/utils/mod.rs:210-242, implemented for the CPU IvfIndex in src/cpu/ivf.rs:496-523): the
+// stored vectors at `positions` (internal list-order positions, drawn by the caller -- the reference draws them with its
+// StdRng) are searched through the index itself (default nprobe when 0) and exhaustively over the same rows
+// (exhaustive_query, :133-196: ties by internal position, results mapped through original_ids); returns the mean of
+// |approx ∩ true| / k.  f32 unsharded single-device IVF handles only, like the reference's impl.
+int annb_ivf_validate(const annb_index* index, const uint64_t* positions, uint64_t n_samples, uint32_t k, uint32_t nprobe, double* out_recall) {
+    annb_index* ix = const_cast<annb_index*>(index);
+    if (!ix || !ix->is_ivf) return fail(ANNB_ERR_INVALID_ARGUMENT, "not an IVF index");
+    if (!positions || !out_recall || k == 0 || n_samples == 0) return fail(ANNB_ERR_INVALID_ARGUMENT, "null buffer / k == 0 / no samples");
+    if (ix->multi || ix->list_begin != 0 || ix->list_end != ix->nlist || ix->dtype != ANNB_F32)
+        return fail(ANNB_ERR_UNSUPPORTED, "validate_index needs an unsharded single-device f32 IVF index (the reference implements it for IvfIndex<T> only)");
+    for (uint64_t i = 0; i < n_samples; i++)
+        if (positions[i] >= ix->n) return fail(ANNB_ERR_INVALID_ARGUMENT, "sample position outside the index");
+    ANNB_DEVICE(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t s = ix->stream;
+    ANNB_TRY(order_after_previous(ix, s));
+    const uint32_t kk = static_cast<uint32_t>(std::min<uint64_t>(k, ix->n));
+    double matches = 0.0;
+    DevBuf d_pos, d_q, d_ia, d_it, d_da, d_dt;
+    struct Free { DevBuf* b[6]; ~Free() { for (DevBuf* x : b) x->release(); } } guard{{&d_pos, &d_q, &d_ia, &d_it, &d_da, &d_dt}};
+    std::vector<uint32_t> pos32;
+    std::vector<uint64_t> ia, it;
+    for (uint64_t b0 = 0; b0 < n_samples; b0 += QUERY_BATCH) {
+        const uint64_t nb = std::min<uint64_t>(QUERY_BATCH, n_samples - b0);
+        pos32.resize(nb);
+        for (uint64_t i = 0; i < nb; i++) pos32[i] = static_cast<uint32_t>(positions[b0 + i]);
+        ANNB_TRY(d_pos.ensure(nb * 4));
+        ANNB_TRY(d_q.ensure(nb * ix->row_bytes));
+        ANNB_TRY(d_ia.ensure(nb * k * 8ull)); ANNB_TRY(d_it.ensure(nb * k * 8ull));
+        ANNB_TRY(d_da.ensure(nb * k * 4ull)); ANNB_TRY(d_dt.ensure(nb * k * 4ull));
+        ANNB_CUDA_CHECK(cudaMemcpyAsync(d_pos.p, pos32.data(), nb * 4, cudaMemcpyHostToDevice, s));
+        gather_rows_kernel<<<grid_for(nb * (ix->row_bytes >> 4), 256), 256, 0, s>>>(ix->d_rows, ix->row_bytes, d_pos.as<uint32_t>(), static_cast<uint32_t>(nb), d_q.as<uint8_t>());
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        PreparedQueries pq;                       // f32 rows at the index's own pitch serve as routing and scan queries
+        pq.route = d_q.as<float>(); pq.route_ld = ix->row_bytes / 4; pq.scan = d_q.as<uint8_t>(); pq.scan_bytes = ix->row_bytes; pq.qt = QT_F32; pq.bf16_self = 0;
+        ANNB_TRY(run_batch(ix, true, pq, nb, k, nprobe, d_ia.as<uint64_t>(), d_da.as<float>(), nullptr, s, true, []() -> int { return ANNB_OK; }));
+        ANNB_TRY(flat_simt(ix, pq, nb, k, kk, d_it.as<uint64_t>(), d_dt.as<float>(), nullptr, s, true));   // ids = internal positions
+        ia.resize(nb * k); it.resize(nb * k);
+        ANNB_CUDA_CHECK(cudaMemcpyAsync(ia.data(), d_ia.p, nb * k * 8ull, cudaMemcpyDeviceToHost, s));
+        ANNB_CUDA_CHECK(cudaMemcpyAsync(it.data(), d_it.p, nb * k * 8ull, cudaMemcpyDeviceToHost, s));
+        ANNB_CUDA_CHECK(cudaStreamSynchronize(s));
+        std::vector<uint64_t> oid(nb * static_cast<uint64_t>(kk));
+        {   // original ids of the exhaustive rows (positions -> ids), fetched row by row would be slow: one gather on the device
+            DevBuf d_o;
+            ANNB_TRY(d_o.ensure(nb * static_cast<uint64_t>(kk) * 8));
+            std::vector<uint64_t> flat(nb * static_cast<uint64_t>(kk));
+            for (uint64_t q = 0; q < nb; q++) for (uint32_t j = 0; j < kk; j++) flat[q * kk + j] = it[q * k + j];
+            cudaError_t e = cudaMemcpyAsync(d_o.p, flat.data(), flat.size() * 8, cudaMemcpyHostToDevice, s);
+            if (e == cudaSuccess) { map_ids_kernel<<<grid_for(flat.size(), 256), 256, 0, s>>>(d_o.as<uint64_t>(), flat.size(), ix->d_original_ids, ix->n); e = cudaGetLastError(); }
+            if (e == cudaSuccess) e = cudaMemcpyAsync(oid.data(), d_o.p, flat.size() * 8, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+            d_o.release();
+            ANNB_CUDA_CHECK(e);
+        }
+        for (uint64_t q = 0; q < nb; q++) {
+            uint32_t m = 0;
+            for (uint32_t j = 0; j < kk; j++) {
+                const uint64_t t = oid[q * kk + j];
+                for (uint32_t a = 0; a < k; a++) if (ia[q * k + a] == t) { m++; break; }
+            }
+            matches += static_cast<double>(m) / static_cast<double>(k);
+        }
+    }
+    *out_recall = matches / static_cast<double>(n_samples);
+    return mark_call_done(ix, s);
 }
 
 int annb_ivf_search_dev(const annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,

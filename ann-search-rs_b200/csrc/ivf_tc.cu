@@ -47,6 +47,8 @@ struct IvfTcParams {
     uint32_t bf16_terms;       // bf16 lists: bf16 terms of the f32 query (2 or 3)
     uint64_t* part_keys;       // [nq][probe_pitch][2][KP]
     uint32_t* gtau;            // [nq] shared pruning threshold
+    uint32_t lo_smem;          // f32 lists with rows of 129 .. 256 elements: only the hi query piece fits TMEM beside two accumulator stages;
+                               // the lo piece is gathered into shared memory (swizzled K slabs) and its term is an SS-mode MMA
     unsigned long long* dbg;   // optional [8]: CTA 0 cycle counters {total, schedule, gather, epi wait-tfull, mma wait-queries, mma wait-data, mma wait-tempty, tasks << 32 | tiles}
 };
 
@@ -66,8 +68,9 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     constexpr int KSTEPS = 4;
     // TMEM: query pieces at column 0 (f32 hi / lo 2 x 128 columns, bf16 terms 64 or 128 each, int8 codes <= 128), accumulator
     // ring behind them: three stages when the pieces fit 128 columns, two otherwise
-    const uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? 128u : (KIND == KIND_I8 ? 128u : (p.nslab > 2u ? 128u : 64u));
-    const uint32_t q_cols = (KIND == KIND_TF32X3) ? 256u : (KIND == KIND_I8 ? 128u : p.bf16_terms * PIECE_COLS);
+    const bool lo_s = KIND == KIND_TF32X3 && p.lo_smem != 0;
+    const uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? (lo_s ? p.nslab * 32u : 128u) : (KIND == KIND_I8 ? 128u : (p.nslab > 2u ? 128u : 64u));
+    const uint32_t q_cols = (KIND == KIND_TF32X3) ? (lo_s ? PIECE_COLS : 256u) : (KIND == KIND_I8 ? 128u : p.bf16_terms * PIECE_COLS);
     const uint32_t NACC = q_cols <= 128u ? 3u : 2u;
     const uint32_t ACC_COL0 = q_cols <= 128u ? 128u : 256u;
     constexpr uint32_t idesc = make_idesc(KIND);
@@ -76,7 +79,8 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     if ((smem_u32(smem) & 1023u) != 0) __trap();
-    uint8_t* s_x = smem;                                                    // [n_stages][NB] slabs
+    uint8_t* s_qlo = smem;                                                  // lo_smem: [nslab] slabs holding the task's lo query piece
+    uint8_t* s_x = lo_s ? smem + static_cast<size_t>(p.nslab) * SLAB_TILE : smem;   // [n_stages][NB] slabs
     uint8_t* s_tail = s_x + static_cast<size_t>(p.n_stages) * NB * SLAB_TILE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_tail);
     uint64_t* bar_full = bars;                     // [n_stages]
@@ -174,6 +178,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
             mbar_wait_timed(bar_q, task_no & 1u, c_wq);
             tc_fence_after();
             const uint32_t x_desc0 = make_smem_desc(smem_u32(s_x));   // low descriptor word
+            const uint32_t qlo_desc0 = make_smem_desc(smem_u32(s_qlo));
             for (uint32_t t = 0; t < n_tiles; t++, tg++) {
                 const uint32_t acc = tg % NACC, aph = (tg / NACC) & 1u;
                 mbar_wait_timed(bar_tempty + acc, aph ^ 1u, c_wtempty);
@@ -191,7 +196,8 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                             const uint32_t a0 = tmem_base + s * 32 + k * 8;
                             if (KIND == KIND_TF32X3) {
                                 umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
-                                umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
+                                if (lo_s) umma<KIND>(tmem_c, qlo_desc0 + s * SLAB_DESC + 2 * k, xd + 2 * k, idesc, 1u);   // Qlo from shared memory
+                                else umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
                                 umma_ts<KIND>(tmem_c, a0, xd + SLAB_DESC + 2 * k, idesc, 1u);
                             } else if (KIND == KIND_I8) {
                                 umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
@@ -255,8 +261,22 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                             tmem_st32(tq + c, w);
                         }
                     }
+                } else if (KIND == KIND_TF32X3 && lo_s && half == 1) {
+                    // wide rows: half 1 writes the lo piece into the shared-memory K slabs in the layout the MMA descriptor reads
+                    // (SWIZZLE_128B: row r of a slab at r * 128 B, its 16-byte chunk c at position c ^ (r & 7))
+                    const uint4* src = reinterpret_cast<const uint4*>(static_cast<const float*>(p.q_op) + (static_cast<uint64_t>(p.nq) + (has_query ? pr.x : 0)) * kp);
+                    for (uint32_t sl = 0; sl < p.nslab; sl++) {
+                        uint4 x[8];
+#pragma unroll
+                        for (int c = 0; c < 8; c++) x[c] = has_query ? __ldg(src + sl * 8 + c) : make_uint4(0u, 0u, 0u, 0u);
+                        uint8_t* dst = s_qlo + static_cast<size_t>(sl) * SLAB_TILE + row_in_tile * 128u;
+#pragma unroll
+                        for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(c) ^ (row_in_tile & 7u)) << 4)) = x[c];
+                    }
+                    fence_proxy_async();           // generic-proxy writes -> visible to the tensor core's async-proxy reads
                 } else if (KIND == KIND_TF32X3) {
                     // pieces were split once per batch (split_tf32_kernel): half 0 copies hi to columns [0,128), half 1 lo to [128,256)
+                    // (wide rows: half 0 copies the whole hi piece, the lo piece goes to shared memory above)
                     const uint4* src = reinterpret_cast<const uint4*>(static_cast<const float*>(p.q_op) + (static_cast<uint64_t>(half) * p.nq + (has_query ? pr.x : 0)) * kp);
                     const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + half * PIECE_COLS;
                     uint32_t c = 0;
@@ -415,7 +435,8 @@ int tc_ivf_prepare(annb_index* ix) {
     const uint32_t slab_elems = tc::SLAB_BYTES / elem;
     const uint32_t kp = round_up(ix->dim, slab_elems);
     // the query pieces live in TMEM (128 columns per f32 / int8 piece, 64 or 128 per bf16 term); larger dims stay on the CUDA-core scan
-    if (kp * elem > 512u) return ANNB_OK;
+    // (f32 rows of up to 1024 B keep their lo piece in shared memory, IvfTcParams::lo_smem)
+    if (kp * elem > (kind == tc::KIND_TF32X3 ? 1024u : 512u)) return ANNB_OK;
     IvfTcState* st = new IvfTcState();
     ix->tc_ivf = st;
     st->kind = kind;
@@ -490,6 +511,7 @@ bool tc_ivf_supported(const annb_index* ix, int qt, uint32_t k_eff) {
 
 uint32_t tc_ivf_kprime(const annb_index* ix, uint32_t k_eff) {
     if (ix->opt_tc_candidates == 32) return 32;
+    if (ix->tc_ivf && ix->tc_ivf->kind == tc::KIND_TF32X3 && ix->tc_ivf->kp_elems > 128) return 32;   // wide rows: wider certificate margin (tc_cert_eps)
     return k_eff <= 10 ? 16 : 32;
 }
 
@@ -523,8 +545,10 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     const uint32_t nb = st->kind == tc::KIND_TF32X3 ? 2 : 1;
     const size_t fixed = 512 /*barriers, task slots (<= 296 B)*/ + 8 * 64 * 4 /*per-warp row constants*/;
     const size_t budget = 227 * 1024;
-    uint32_t stages = static_cast<uint32_t>(std::min<size_t>(8, (budget - fixed) / (nb * tc::SLAB_TILE)));
-    const size_t smem = static_cast<size_t>(stages) * nb * tc::SLAB_TILE + fixed;
+    const bool lo_s = st->kind == tc::KIND_TF32X3 && st->kp_elems > 128;
+    const size_t q_smem = lo_s ? static_cast<size_t>(st->nslab) * tc::SLAB_TILE : 0;
+    uint32_t stages = static_cast<uint32_t>(std::min<size_t>(8, (budget - fixed - q_smem) / (nb * tc::SLAB_TILE)));
+    const size_t smem = q_smem + static_cast<size_t>(stages) * nb * tc::SLAB_TILE + fixed;
     const uint64_t slots = nq * static_cast<uint64_t>(probe_pitch) * 2;
     ANNB_TRY(st->part.ensure(slots * kprime * 8));
     ANNB_CUDA_CHECK(cudaMemsetAsync(st->part.p, 0xFF, slots * kprime * 8, s));
@@ -547,7 +571,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
         ix->stat_launches++;
     }
     tc::IvfTcParams p{};
-    p.q_op = st->q_op.p; p.nq = nq; p.bf16_terms = bf16_terms;
+    p.q_op = st->q_op.p; p.nq = nq; p.bf16_terms = bf16_terms; p.lo_smem = lo_s ? 1u : 0u;
     p.queries = d_q; p.q_bytes = q_bytes; p.dim = ix->dim; p.nslab = st->nslab; p.n_stages = stages; p.n_pad = st->n_pad; p.aux = st->d_aux;
     p.offsets = ix->d_offsets; p.shard_row0 = ix->shard_row0; p.nlist = ix->nlist; p.pair_off = d_pair_off; p.task_off = d_task_off;
     p.pairs = static_cast<const uint2*>(d_pairs); p.tasks = static_cast<const uint4*>(d_tasks); p.task_counter = d_task_counter; p.probe_pitch = probe_pitch;

@@ -177,6 +177,13 @@ class IvfIndexB200 : public IndexHandle {
                                    return_dist ? dist.data() : nullptr, cnt.data()));
         return detail::unpack(ids, dist, cnt, n, k, return_dist);
     }
+    // KnnValidation::validate_index (src/utils/mod.rs:210-242): recall@k against an exhaustive search over the index's own vectors
+    // on the stored vectors at `positions` (drawn by the caller, as the reference draws them with its StdRng).
+    double validate_index(size_t k, const std::vector<uint64_t>& positions) const {
+        double recall = 0.0;
+        check(annb_ivf_validate(get(), positions.data(), positions.size(), static_cast<uint32_t>(k), 0, &recall));
+        return recall;
+    }
 };
 
 // ---- free functions, src/lib.rs ---------------------------------------------------------------------------------------

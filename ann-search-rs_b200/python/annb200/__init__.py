@@ -91,6 +91,7 @@ def lib():
         _lib.annb_shard_check_dev.argtypes = [vp, vp, vp, u64, u32, C.POINTER(u32), vp]
         _lib.annb_shard_check_gathered_dev.argtypes = [vp, vp, u64, u64, u32, u32, vp, u64, u32, C.POINTER(u32), C.POINTER(u32), vp]
         _lib.annb_shard_check_gathered_async_dev.argtypes = [vp, vp, u64, u64, u32, u32, vp, u64, u32, vp, vp]
+        _lib.annb_ivf_validate.argtypes = [vp, vp, u64, u32, u32, C.POINTER(C.c_double)]
         _lib.annb_shard_refine_dev.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, u32, vp, vp, vp]
         _lib.annb_merge_shards_dev.argtypes = [vp, u64, u64, u32, u64, u32, vp, vp, vp, vp]
         _lib.annb_flat_create_multi.argtypes = [C.POINTER(vp), vp, u64, u32, i32, i32, vp, i32]
@@ -339,6 +340,20 @@ class IvfIndexB200(_IndexBase):
         _check(lib().annb_ivf_search_self(self._h, pos_begin, pos_end, k, nprobe or 0, 1 if scatter else 0, _ptr(ids), _ptr(dist),
                                           _ptr(cnt)))
         return ids.view(np.int64), dist, cnt
+
+
+    def validate_index(self, k: int, seed: int = 42, no_samples: Optional[int] = None, positions=None) -> float:
+        """KnnValidation::validate_index (src/utils/mod.rs:210-242, src/cpu/ivf.rs:496-523): recall@k of the index against an
+        exhaustive search over its own vectors on `no_samples` (default min(1000, n)) stored vectors drawn with replacement.
+        numpy's PCG64 stands in for StdRng (or pass the internal positions yourself); unsharded f32 indices only."""
+        n = self.n
+        ns = min(1000 if no_samples is None else no_samples, n)
+        if positions is None:
+            positions = np.random.Generator(np.random.PCG64(seed)).integers(0, n, size=ns, dtype=np.uint64)
+        pos = np.ascontiguousarray(positions, dtype=np.uint64)
+        out = C.c_double(0.0)
+        _check(lib().annb_ivf_validate(self._h, _ptr(pos), pos.size, k, 0, C.byref(out)))
+        return float(out.value)
 
 
 # --------------------------------------------------------------------------

@@ -88,6 +88,7 @@ extern "C" {
     pub fn annb_shard_check_gathered_dev(index: *mut annb_index, d_parts: *const c_void, part_stride_bytes: u64, bound_offset_bytes: u64, parts: u32,
                                          my_part: u32, d_merged_dist: *const f32, nq: u64, k: u32, out_mine: *mut u32, out_any: *mut u32,
                                          stream: *mut c_void) -> c_int;
+    pub fn annb_ivf_validate(index: *const annb_index, positions: *const u64, n_samples: u64, k: u32, nprobe: u32, out_recall: *mut f64) -> c_int;
     pub fn annb_shard_check_gathered_async_dev(index: *mut annb_index, d_parts: *const c_void, part_stride_bytes: u64, bound_offset_bytes: u64, parts: u32,
                                                my_part: u32, d_merged_dist: *const f32, nq: u64, k: u32, h_verdict: *mut u32, stream: *mut c_void) -> c_int;
     pub fn annb_shard_refine_dev(index: *mut annb_index, d_queries: *const f32, nq: u64, dim: u32, k: u32, nprobe: u32, d_probes: *const u32,
@@ -261,6 +262,15 @@ impl IvfIndexB200 {
                                        ids.as_ptr(), n as u64, dim as u32, nlist as u32, ANNB_F32, metric, std::ptr::null(), 0,
                                        nlist as u32, device) })?;
         Ok(Self { handle, n, dim, nlist })
+    }
+
+    /// `KnnValidation::validate_index` (src/utils/mod.rs:210-242): recall@k against an exhaustive search over the index's own
+    /// vectors.  The caller draws the sample positions (`rng.random_range(0..n)` with the crate's StdRng, as the reference does).
+    pub fn validate_index(&self, k: usize, positions: &[usize]) -> Result<f64, AnnSearchErrors> {
+        let pos: Vec<u64> = positions.iter().map(|&v| v as u64).collect();
+        let mut recall = 0f64;
+        check(unsafe { annb_ivf_validate(self.handle, pos.as_ptr(), pos.len() as u64, k as u32, 0, &mut recall) })?;
+        Ok(recall)
     }
 }
 

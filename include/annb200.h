@@ -325,6 +325,14 @@ int annb_ivf_create_multi(annb_index** out, const void* vectors, const void* nor
 /* Number of per-device shards behind a handle (1 for an ordinary handle). */
 int annb_index_shard_count(const annb_index* index, uint32_t* out);
 
+/* KnnValidation::validate_index (src/utils/mod.rs:210-242; implemented for the CPU IvfIndex only, src/cpu/ivf.rs:496-523):
+ * recall@k of the index against an exhaustive search over its own vectors, on the stored vectors at `positions` (internal
+ * list-order positions in [0, n), drawn by the caller -- the reference draws them with rand's StdRng, which stays on the Rust
+ * side).  nprobe = 0: the index default, as validate_index queries with None.  *out_recall = mean |approx ∩ true| / k.
+ * Unsharded single-device f32 IVF handles only (ANNB_ERR_UNSUPPORTED otherwise). */
+int annb_ivf_validate(const annb_index* index, const uint64_t* positions, uint64_t n_samples, uint32_t k, uint32_t nprobe,
+                      double* out_recall);
+
 /* Index facts: ExhaustiveIndexGpu::memory_usage_bytes (src/gpu/exhaustive_gpu.rs:205-209),
  * IvfIndexGpu::memory_usage_bytes (src/gpu/ivf_gpu.rs:590-604). */
 typedef struct annb_index_info {

@@ -500,3 +500,41 @@ def test_kmeans_parallel_seeding_on_shared_draws(gpu):
     ix = annb200.build_ivf_index_gpu(data, nlist=12, k_means_params={"iters": 5, "init": "kmeans||", "balanced": True}, dist_metric="euclidean", seed=3)
     ids, dist_, _ = ix.query_batch(data[:50], 5, nprobe=12)
     assert (ids[:, 0] == np.arange(50)).all()
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_validate_index_matches_the_restated_trait(gpu, metric):
+    """KnnValidation::validate_index (src/utils/mod.rs:210-242, src/cpu/ivf.rs:496-523) on shared sample positions: index
+    query with the default nprobe against exhaustive_query over the stored (list-order) vectors, ids through original_ids."""
+    data = datagen.gaussian_noise(30_000, 48, seed=51)
+    c = o.build_ivf(data, MET[metric][1], nlist=200, kmeans_iters=4)
+    g = _gpu_from_oracle(c)
+    rng = np.random.default_rng(9)
+    pos = rng.integers(0, c.n, size=300)
+    k = 10
+    got = g.validate_index(k, positions=pos)
+    q = np.ascontiguousarray(c.vectors[pos])                     # stored rows, list order
+    approx = o.ivf_search(c, q, k)[0]                             # default nprobe = sqrt(nlist)
+    flat = o.build_flat(np.ascontiguousarray(c.vectors), MET[metric][1])
+    true_pos = o.flat_search(flat, q, k)[0]
+    true_ids = np.asarray(c.original_ids)[true_pos]
+    want = np.mean([len(set(approx[i].tolist()) & set(true_ids[i].tolist())) / k for i in range(pos.size)])
+    assert abs(got - want) < 1e-12, (got, want)
+    assert 0.3 < got <= 1.0
+    assert abs(g.validate_index(k, seed=3, no_samples=50) - g.validate_index(k, seed=3, no_samples=50)) == 0.0
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+@pytest.mark.parametrize("dim,k", [(160, 10), (256, 10), (200, 20)])
+def test_wide_f32_rows_on_the_tensor_scan(gpu, metric, dim, k):
+    """f32 lists with rows of 129 .. 256 elements on the tensor-core scan: hi query piece in TMEM, lo piece gathered into
+    swizzled shared-memory slabs (SS-mode MMA for Qlo.Xhi)."""
+    data = datagen.gaussian_noise(40_000, dim, seed=53)
+    c = o.build_ivf(data, MET[metric][1], nlist=64, kmeans_iters=3)
+    g = _gpu_from_oracle(c)
+    g.set_option("path", annb200.PATH_TENSOR)
+    q = datagen.subsample_with_noise(data, 500, seed=53)
+    got = g.query_batch(q, k, nprobe=8)
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    ref = o.ivf_search(c, q, k, nprobe=8)
+    _check("f32", got, ref[:3], f"ivf wide rows dim={dim} {metric}")
