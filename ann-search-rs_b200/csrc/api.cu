@@ -1754,7 +1754,8 @@ int annb_merge_shards_dev(const void* d_parts, uint64_t part_stride_bytes, uint6
     MergeShardsParams m{};
     m.base = static_cast<const uint8_t*>(d_parts); m.part_stride = part_stride_bytes; m.dist_offset = dist_offset_bytes;
     m.parts = parts; m.k = k; m.nq = nq; m.out_ids = d_out_ids; m.out_dist = d_out_dist; m.out_counts = d_out_counts;
-    merge_shards_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 4)), 128, 0, static_cast<cudaStream_t>(stream)>>>(m);
+    if (m.parts * m.k <= 128u) merge_shards_sort_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 4)), 128, 0, static_cast<cudaStream_t>(stream)>>>(m);
+    else merge_shards_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 4)), 128, 0, static_cast<cudaStream_t>(stream)>>>(m);
     ANNB_CUDA_CHECK(cudaGetLastError());
     return ANNB_OK;
 }

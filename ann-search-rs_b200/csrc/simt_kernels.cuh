@@ -867,6 +867,81 @@ struct MergeShardsParams {
     uint32_t* out_counts;
 };
 
+// Ascending bitonic sort of 32 * NPL keys held NPL per lane (element i = lane + 32 * j lives in key[j] of `lane`): strides below
+// 32 exchange by shuffle, larger strides inside the lane.
+template <int NPL>
+__device__ __forceinline__ void warp_bitonic_sort_regs(uint64_t (&key)[NPL], uint32_t lane) {
+#pragma unroll
+    for (int size = 2; size <= 32 * NPL; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int js = stride >> 5;
+#pragma unroll
+                for (int j = 0; j < NPL; j++) {
+                    if ((j & js) == 0) {
+                        const bool up = ((static_cast<int>(lane) + 32 * j) & size) == 0;
+                        const uint64_t a = key[j], b = key[j | js];
+                        if ((a > b) == up) { key[j] = b; key[j | js] = a; }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < NPL; j++) {
+                    const bool up = ((static_cast<int>(lane) + 32 * j) & size) == 0;
+                    const uint64_t other = __shfl_xor_sync(0xFFFFFFFFu, key[j], stride);
+                    const bool lower = (lane & static_cast<uint32_t>(stride)) == 0;
+                    key[j] = (lower == up) ? (key[j] < other ? key[j] : other) : (key[j] < other ? other : key[j]);
+                }
+            }
+        }
+    }
+}
+
+// Small merges (parts * k <= 128, e.g. 8 shards x k = 10 or 15): one warp per query sorts the (distance, slot) keys of all shards
+// in registers -- slot = shard * k + position, so the key order IS (distance, shard, position) -- and emits the first k.  The
+// binary-search variant below walks ~50 dependent loads per entry; this one is one load round trip and ~500 register ops.
+__global__ void __launch_bounds__(128) merge_shards_sort_kernel(MergeShardsParams p) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t q = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (q >= p.nq) return;
+    const uint32_t total = p.parts * p.k;
+    uint64_t key[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t i = lane + 32u * j;
+        key[j] = KEY_SENTINEL;
+        if (i < total) {
+            const uint32_t part = i / p.k, pos = i - part * p.k;
+            const uint8_t* pb = p.base + static_cast<uint64_t>(part) * p.part_stride;
+            if (reinterpret_cast<const uint64_t*>(pb)[q * p.k + pos] != 0xFFFFFFFFFFFFFFFFull)
+                key[j] = make_key(reinterpret_cast<const float*>(pb + p.dist_offset)[q * p.k + pos], i);
+        }
+    }
+    warp_bitonic_sort_regs<4>(key, lane);
+    uint32_t valid = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t r = lane + 32u * j;            // rank of key[j]
+        if (r < p.k) {
+            uint64_t id = 0xFFFFFFFFFFFFFFFFull;
+            float d = INFINITY;
+            if (key[j] != KEY_SENTINEL) {
+                const uint32_t i = key_idx(key[j]), part = i / p.k, pos = i - part * p.k;
+                const uint8_t* pb = p.base + static_cast<uint64_t>(part) * p.part_stride;
+                id = reinterpret_cast<const uint64_t*>(pb)[q * p.k + pos];
+                d = reinterpret_cast<const float*>(pb + p.dist_offset)[q * p.k + pos];
+                valid++;
+            }
+            p.out_ids[q * p.k + r] = id;
+            if (p.out_dist) p.out_dist[q * p.k + r] = d;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) valid += __shfl_xor_sync(0xFFFFFFFFu, valid, off);
+    if (p.out_counts && lane == 0) p.out_counts[q] = valid;
+}
+
 // One warp per query.  Each per-shard list is ascending, so an entry's final rank is its own slot plus, for every other
 // shard, the number of that shard's entries that precede it (<= for earlier shards, < for later ones): k * parts * parts
 // compares per query, no sort, no shared memory.
