@@ -434,6 +434,10 @@ static int ivf_route(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uin
     }
     // query -> all centroids (dense), reference arithmetic of get_centroids_dist / _prenorm; full per-query sort
     const uint32_t nl2 = next_pow2(ix->nlist);
+    // (the full sort of a centroid row lives in shared memory: tables of more than 16 384 cells are served by the ranked-prefix
+    // stages above only -- a batch that needs more cells than the prefix holds, e.g. many tiny lists, is refused here)
+    if (static_cast<size_t>(nl2) * 8 > 200 * 1024)
+        return fail(ANNB_ERR_UNSUPPORTED, "nlist > 16384: this batch needs the full centroid ranking (a probe set outgrew the ranked prefix), which is not supported for tables this large");
     const uint32_t pitch = stage_start >= 1 ? pitch_short : ix->nlist;
     ANNB_TRY(ix->s_cdist.ensure(nq * static_cast<uint64_t>(ix->nlist) * 4));
     {
@@ -475,7 +479,6 @@ static int ivf_enqueue(annb_index* ix, const PreparedQueries& pq, uint64_t nq, u
     // nprobe default and clamp: src/cpu/ivf.rs:345-347
     uint32_t np = nprobe ? nprobe : std::max<uint32_t>(1, static_cast<uint32_t>(std::sqrt(static_cast<double>(ix->nlist))));
     np = std::min(np, ix->nlist);
-    if (static_cast<size_t>(next_pow2(ix->nlist)) * 8 > 200 * 1024) return fail(ANNB_ERR_UNSUPPORTED, "nlist > 16384 is not supported yet");
 
     uint32_t pitch = preset_pitch;
     if (!preset_probes) {

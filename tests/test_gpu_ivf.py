@@ -538,3 +538,19 @@ def test_wide_f32_rows_on_the_tensor_scan(gpu, metric, dim, k):
     assert g.get_stat("last_path") == annb200.PATH_TENSOR
     ref = o.ivf_search(c, q, k, nprobe=8)
     _check("f32", got, ref[:3], f"ivf wide rows dim={dim} {metric}")
+
+
+def test_centroid_tables_above_16384_cells(gpu):
+    """nlist > 16 384: served by the ranked-prefix stages (tensor-core ranking + certified prefix, fused CUDA-core select); only a
+    batch that needs the full per-row sort (a probe set outgrowing the prefix) is refused.  Centroids are supplied (random rows)."""
+    rng = np.random.default_rng(61)
+    data = datagen.gaussian_noise(120_000, 16, seed=61)
+    nlist = 17_000
+    cent = np.ascontiguousarray(data[rng.choice(data.shape[0], nlist, replace=False)])
+    c = o.build_ivf(data, o.L2, nlist=nlist, centroids=cent)
+    g = _gpu_from_oracle(c)
+    q = datagen.subsample_with_noise(data, 300, seed=61)
+    for nprobe in (24, 100):
+        got = g.query_batch(q, 10, nprobe=nprobe)
+        ref = o.ivf_search(c, q, 10, nprobe=nprobe)
+        _check("f32", got, ref[:3], f"nlist {nlist} nprobe {nprobe}")
