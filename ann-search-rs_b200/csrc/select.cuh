@@ -19,7 +19,8 @@ __device__ __forceinline__ void bitonic_sort_keys(uint64_t* buf, uint32_t n, uin
     for (uint32_t size = 2; size <= n; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
             for (uint32_t t = tid; t < (n >> 1); t += nthreads) {
-                uint32_t i = ((t / stride) * (stride << 1)) + (t % stride);
+                const uint32_t lowmask = stride - 1u;                          // stride is a power of two: no division
+                uint32_t i = ((t & ~lowmask) << 1) | (t & lowmask);
                 uint32_t j = i + stride;
                 bool up = ((i & size) == 0);
                 uint64_t a = buf[i], b = buf[j];
