@@ -1805,6 +1805,20 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "tc_candidates") ix->opt_tc_candidates = static_cast<int>(value);
     else if (k == "tc_ts") ix->opt_tc_ts = static_cast<int>(value);
     else if (k == "tc_wide_k") ix->opt_tc_wide_k = static_cast<int>(value);
+    else if (k == "tc_f32_fp16") {
+        // the operand form is chosen when the tensor state is built: rebuild it for a flat f32 index whose setting changes
+        const int v = value != 0 ? 1 : 0;
+        if (v != ix->opt_tc_f32_fp16) {
+            ix->opt_tc_f32_fp16 = v;
+            if (!ix->is_ivf && ix->dtype == ANNB_F32 && ix->tc != nullptr) {
+                DeviceGuard g(ix->device);
+                ANNB_CUDA_CHECK(cudaStreamSynchronize(ix->stream));
+                tc_destroy(ix);
+                ANNB_TRY(tc_flat_prepare(ix));
+                ANNB_CUDA_CHECK(cudaStreamSynchronize(ix->stream));
+            }
+        }
+    }
     else if (k == "tc_strided") ix->opt_tc_strided = static_cast<int>(value);
     else if (k == "tc_f32_lo_smem") ix->opt_tc_f32_lo_smem = static_cast<int>(value);
     else if (k == "tc_bf16_hybrid") ix->opt_tc_bf16_hybrid = static_cast<int>(value);
@@ -1885,6 +1899,7 @@ int annb_index_get_stat(const annb_index* ix, const char* key, int64_t* out) {
     else if (k == "fallback_queries") *out = ix->stat_fallback_queries;
     else if (k == "cert_eps_bits") *out = ix->stat_cert_eps_bits;
     else if (k == "tc_escalated") *out = ix->tc_escalate;
+    else if (k == "tc_kind") *out = tc_flat_kind(ix);
     else if (k == "uncertified") {
         // queries of the last tensor-path call whose pre-selection margin could not be certified (see rerank_kernel)
         *out = 0;

@@ -44,8 +44,9 @@ __device__ __forceinline__ bool hyb_cfg(const Params& p) { return p.hybrid != 0;
 template <int KIND, int KP, int MET, bool TS, bool DENSE = false, int EW = 2>
 __global__ void __launch_bounds__(64 + EW * 128, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_x, const Params p) {
-    constexpr int NA = (KIND == KIND_TF32X3) ? 2 : (KIND == KIND_I8 ? 1 : 3);  // stacked query pieces
-    constexpr int NB = (KIND == KIND_TF32X3) ? 2 : 1;  // stacked database pieces
+    constexpr bool SPLIT3 = (KIND == KIND_TF32X3 || KIND == KIND_F16X3);   // hi / lo pieces on both sides, three product terms
+    constexpr int NA = SPLIT3 ? 2 : (KIND == KIND_I8 ? 1 : 3);  // stacked query pieces
+    constexpr int NB = SPLIT3 ? 2 : 1;  // stacked database pieces
     constexpr int ELEM = (KIND == KIND_TF32X3) ? 4 : (KIND == KIND_I8 ? 1 : 2);
     constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;      // 32 tf32 / 64 bf16 per slab row
     constexpr int KSTEPS = 4;                          // 128 B / 32 B per UMMA K step (8 tf32 / 16 bf16)
@@ -53,10 +54,11 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     constexpr int NG = NV / 8;
     constexpr uint32_t EPI_T = EW * 128;               // epilogue threads
     // TMEM columns per query piece (32-bit words per row): f32 128; bf16 terms 64 (rows of <= 128 elements) or 128; int8 codes 128
-    const uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? (p.lo_smem ? p.kp : 128u) : (KIND == KIND_I8 ? 128u : (p.kp > 128u ? 128u : 64u));
+    const uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? (p.lo_smem ? p.kp : 128u)
+                                : (KIND == KIND_F16X3 ? p.kp / 2u : (KIND == KIND_I8 ? 128u : (p.kp > 128u ? 128u : 64u)));
     // accumulator stages behind the TMEM-resident queries (TS): three when the pieces take at most 128 columns (int8 codes, one
     // or two bf16 terms of narrow rows), two when they take up to 256 (f32 hi / lo, three bf16 terms, two bf16 terms of wide rows)
-    const uint32_t q_cols = (KIND == KIND_I8) ? 128u : ((KIND == KIND_TF32X3 && p.lo_smem) ? PIECE_COLS : (hyb_cfg(p) ? 2u : p.a_pieces) * PIECE_COLS);
+    const uint32_t q_cols = (KIND == KIND_I8) ? 128u : ((SPLIT3 && p.lo_smem) ? PIECE_COLS : (KIND == KIND_F16X3 ? 2u * PIECE_COLS : (hyb_cfg(p) ? 2u : p.a_pieces) * PIECE_COLS));
     const uint32_t NACC = TS ? (q_cols <= 128u ? 3u : 2u) : static_cast<uint32_t>(ACC_STAGES);
     const uint32_t ACC_COL0 = TS ? (q_cols <= 128u ? 128u : 256u) : 0u;
 
@@ -70,7 +72,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     const bool hyb = TS && KIND == KIND_BF16 && p.hybrid != 0;
     // f32 rows of more than 128 elements (option: of any width): only the hi piece fits TMEM beside two accumulator stages; the lo
     // piece stays in shared memory and its term Qlo.Xhi is issued as an SS-mode MMA.
-    const bool lo_s = TS && KIND == KIND_TF32X3 && p.lo_smem != 0;
+    const bool lo_s = TS && SPLIT3 && p.lo_smem != 0;
     uint8_t* s_q = smem;                                                         // [NA][nslab] slabs (hybrid: [nslab], term q2; f32 lo_smem: [nslab], piece lo)
     uint8_t* s_x = TS ? ((hyb || lo_s) ? smem + static_cast<size_t>(p.nslab) * SLAB_TILE : smem)
                       : s_q + static_cast<size_t>(NA) * p.nslab * SLAB_TILE;     // [n_stages][NB] slabs
@@ -180,8 +182,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 #pragma unroll
                     for (int k = 0; k < KSTEPS; k++) {
                         const uint32_t first = (s | static_cast<uint32_t>(k)) != 0 ? 1u : 0u;   // 0 only for the tile's first MMA
-                        if (TS && KIND == KIND_TF32X3) {
-                            // queries in TMEM: hi at columns [0, 128), lo at [128, 256); 8 columns (8 tf32) per K step
+                        if (TS && SPLIT3) {
+                            // queries in TMEM: hi at columns [0, PIECE_COLS), lo behind it; 8 columns (8 tf32 / 16 fp16) per K step
                             const uint32_t a_hi = tmem_base + s * 32 + k * 8, a_lo = a_hi + PIECE_COLS;
                             umma_ts<KIND>(tmem_c, a_hi, xd + 2 * k, idesc, first);
                             if (lo_s) umma<KIND>(tmem_c, qd + 2 * k, xd + 2 * k, idesc, 1u);     // Qlo from shared memory
@@ -199,7 +201,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                                 if (hyb) umma<KIND>(tmem_c, qd + 2 * k, xd + 2 * k, idesc, 1u);
                                 else umma_ts<KIND>(tmem_c, a0 + 2 * PIECE_COLS, xd + 2 * k, idesc, 1u);
                             }
-                        } else if (KIND == KIND_TF32X3) {
+                        } else if (SPLIT3) {
                             // s = Qhi.Xhi + Qlo.Xhi + Qhi.Xlo   (the lo.lo term is below 2^-22 relative)
                             umma<KIND>(tmem_c, qd + 2 * k, xd + 2 * k, idesc, first);
                             umma<KIND>(tmem_c, qd + q_piece + 2 * k, xd + 2 * k, idesc, 1u);
@@ -269,19 +271,34 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const size_t aux_step = static_cast<size_t>(tile_step) * BN;
         float aux_lo_next = 0.f, aux_hi_next = 0.f;
         if (n_tiles > 0) { aux_lo_next = __ldg(aux_half); if (NV > 32) aux_hi_next = __ldg(aux_half + 32); }
+        // 3xFP16: operands were scaled per row by powers of two.  L2 needs the row's inverse scale as a second per-column constant
+        // (v = |x|^2 - 2 s / (sq sx)); cosine folds it into its only one (v = s * (-1 / (|x| sx)) / sq).  cq: the query's share.
+        constexpr bool RX = (KIND == KIND_F16X3) && (MET == MET_L2);
+        float* s_rx = s_aux_all + (4 * EW + (warp - 2)) * NV;           // second bank of warp-private rows
+        const float* rx_half = RX ? p.aux2 + r_begin + half * NV + lane : nullptr;
+        float rx_lo_next = 1.f, rx_hi_next = 1.f;
+        if (RX && n_tiles > 0) { rx_lo_next = __ldg(rx_half); if (NV > 32) rx_hi_next = __ldg(rx_half + 32); }
+        float cq = 1.0f;
+        if (KIND == KIND_F16X3) cq = __ldg(p.q_inv_scale + q0 + row_in_tile) * ((MET == MET_L2) ? -2.0f : 1.0f);
         for (uint32_t t = 0; t < n_tiles; t++) {
             const uint32_t acc = t % NACC, aph = (t / NACC) & 1u;
             const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * tile_step * BN;
             const uint32_t g_bits = g_next;
             const float aux_lo = aux_lo_next, aux_hi = aux_hi_next;
+            const float rx_lo = rx_lo_next, rx_hi = rx_hi_next;
             if (t + 1 < n_tiles) {   // prefetch for the next tile: latency hidden behind this tile's work
                 aux_lo_next = __ldg(aux_half + static_cast<size_t>(t + 1) * aux_step);
                 if (NV > 32) aux_hi_next = __ldg(aux_half + static_cast<size_t>(t + 1) * aux_step + 32);
+                if (RX) {
+                    rx_lo_next = __ldg(rx_half + static_cast<size_t>(t + 1) * aux_step);
+                    if (NV > 32) rx_hi_next = __ldg(rx_half + static_cast<size_t>(t + 1) * aux_step + 32);
+                }
                 if (share_tau) g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
             }
             __syncwarp();                      // every lane is done with the previous tile's constants
             s_aux[lane] = aux_lo;
             if (NV > 32) s_aux[lane + 32] = aux_hi;
+            if (RX) { s_rx[lane] = rx_lo; if (NV > 32) s_rx[lane + 32] = rx_hi; }
             __syncwarp();
             mbar_wait_timed(bar_tfull + acc, aph, w_tfull);
             tc_fence_after();
@@ -307,7 +324,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                         const int col = g * 8 + j;   // compile-time after unrolling
                         const float cst = s_aux[col];
                         const float sdot = (KIND == KIND_I8) ? __int2float_rn(static_cast<int32_t>(r[col])) : __uint_as_float(r[col]);   // s32 dots are exact in f32 (< 2^24)
-                        v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
+                        if (KIND == KIND_F16X3) v[col] = (MET == MET_L2) ? fmaf(sdot * s_rx[col], cq, cst) : (sdot * cst) * cq;
+                        else v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
                         mg = fminf(mg, v[g * 8 + j]);
                     }
                     gm[g] = mg;
@@ -655,8 +673,9 @@ struct TcState {
     uint32_t n_pad = 0;
     void* d_x = nullptr;      // stacked database operand (nullptr: the index rows themselves are used)
     float* d_aux = nullptr;   // [n_pad + BN]
+    float* d_aux2 = nullptr;  // KIND_F16X3: [n_pad + BN] inverse operand scale of every row
     CUtensorMap tm_x;
-    DevBuf q_op, part, dbg, gtau, dbgc, dense;
+    DevBuf q_op, part, dbg, gtau, dbgc, dense, q_scale;
     uint64_t bytes = 0;
 };
 
@@ -720,8 +739,11 @@ static int tc_aux_norm_max(annb_index* ix, const float* d_aux, uint64_t n, float
 
 int tc_flat_prepare(annb_index* ix) {
     if (ix->is_ivf) return ANNB_OK;
-    const int kind = ix->dtype == ANNB_F32 ? tc::KIND_TF32X3 : (ix->dtype == ANNB_BF16 ? tc::KIND_BF16 : tc::KIND_I8);
-    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : (kind == tc::KIND_BF16 ? 2 : 1);
+    int kind = ix->dtype == ANNB_F32 ? tc::KIND_TF32X3 : (ix->dtype == ANNB_BF16 ? tc::KIND_BF16 : tc::KIND_I8);
+    // f32 rows of up to 256 elements: 3xFP16 (rows scaled by powers of two, split_f16_kernel) -- the three-term product of 3xTF32
+    // at 16 instead of 8 elements per MMA K step.  Option tc_f32_fp16 = 0 keeps 3xTF32; wider rows keep it as well.
+    if (kind == tc::KIND_TF32X3 && ix->opt_tc_f32_fp16 != 0 && round_up(ix->dim, 64u) <= 256u) kind = tc::KIND_F16X3;
+    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : (kind == tc::KIND_I8 ? 1 : 2);
     const uint32_t slab_elems = tc::SLAB_BYTES / elem;
     const uint32_t kp = round_up(ix->dim, slab_elems);
     // the query tile lives in TMEM: 512 B of a row per piece (f32 dim <= 128, bf16 <= 256, int8 <= 512); f32 rows of up to 1024 B
@@ -747,7 +769,21 @@ int tc_flat_prepare(annb_index* ix) {
     ANNB_CUDA_CHECK(cudaGetLastError());
     void* xbase = nullptr;
     uint64_t xrows = 0;
-    if (kind == tc::KIND_TF32X3) {
+    if (kind == tc::KIND_F16X3) {
+        const uint64_t bytes = 2ull * st->n_pad * kp * 2;
+        cudaError_t e = cudaMalloc(&st->d_x, bytes);
+        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&st->d_aux2), aux_rows * sizeof(float));
+        if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
+        st->bytes += bytes + aux_rows * sizeof(float);
+        tc::fill_aux_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(st->d_aux2, aux_rows, aux_rows, 1.0f);
+        tc::split_f16_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * 32), 256, 0, s>>>(reinterpret_cast<const float*>(ix->d_rows), ix->row_bytes / 4, ix->dim, ix->n,
+                                                                                            st->n_pad, kp, static_cast<__half*>(st->d_x), st->d_aux2);
+        if (ix->metric == ANNB_COSINE)     // cosine: one constant per row, -1 / (|x| * scale); L2 keeps |x|^2 and reads the inverse scale separately
+            tc::mul_rows_kernel<<<static_cast<uint32_t>((static_cast<uint64_t>(st->n_pad) + 127) / 128), 128, 0, s>>>(st->d_aux, st->d_aux2, st->n_pad);
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        xbase = st->d_x;
+        xrows = 2ull * st->n_pad;
+    } else if (kind == tc::KIND_TF32X3) {
         const uint64_t bytes = 2ull * st->n_pad * kp * 4;
         cudaError_t e = cudaMalloc(&st->d_x, bytes);
         if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
@@ -788,6 +824,8 @@ void tc_destroy(annb_index* ix) {
     if (!ix->tc) return;
     cudaFree(ix->tc->d_x);
     cudaFree(ix->tc->d_aux);
+    cudaFree(ix->tc->d_aux2);
+    ix->tc->q_scale.release();
     ix->tc->q_op.release();
     ix->tc->part.release();
     ix->tc->dbg.release();
@@ -818,6 +856,11 @@ float tc_cert_eps(const annb_index* ix, int kind, uint32_t kp_elems, uint32_t te
         if (l2 && ix->dim <= 256) return 1e-30f;
         if (!l2) return 4.7683716e-07f;   // 2^-21: the reference divides the exact integer dot by two square roots -- a handful of roundings on each side
         E = 0.0;
+    } else if (kind == tc::KIND_F16X3) {
+        // same split as 3xTF32 (11 significant bits per piece, round to nearest both times; the power-of-two row scales are exact),
+        // half the accumulating MMAs per row (16 elements per K step)
+        const double n_mma = 3.0 * (kp_elems / 16);
+        E = 3.0 * std::ldexp(1.0, -22) + TC_MMA_ULPS * n_mma * u23;
     } else if (kind == tc::KIND_TF32X3) {
         const double n_mma = 3.0 * (kp_elems / 8);
         // flat: q and x both split with cvt.rna (2^-22 residual each) + dropped lo.lo (2^-22); IVF in-kernel split: x hi
@@ -862,6 +905,9 @@ static uint32_t pick_kprime(const annb_index* ix, uint32_t k_eff) {
 // order defeats the interleaving (a query's neighbours all in one 64-row half tile stride) sends those queries to the exact path.
 constexpr uint32_t TC_K_LIST = 24, TC_K_WIDE = 256;
 static uint32_t wide_k_lists(uint32_t k_eff) { return std::max<uint32_t>(8u, (k_eff + 7u) / 8u); }
+
+// operand form of the flat tensor path: -1 none, 0 3xTF32, 1 bf16 terms, 2 int8, 3 3xFP16
+int tc_flat_kind(const annb_index* ix) { return ix->tc ? ix->tc->kind : -1; }
 
 bool tc_flat_supported(const annb_index* ix, int qt, uint32_t k_eff) {
     if (!ix->tc) return false;
@@ -918,8 +964,9 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
                    uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s) {
     TcState* st = ix->tc;
     const int kind = st->kind;
-    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : (kind == tc::KIND_BF16 ? 2 : 1);
+    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : (kind == tc::KIND_I8 ? 1 : 2);
     const uint32_t kp = st->kp_elems;
+    const bool split3 = kind == tc::KIND_TF32X3 || kind == tc::KIND_F16X3;
     uint32_t kprime = pick_kprime(ix, k_eff);
     // f32 rows of more than 128 elements: the accumulation error of the tensor core grows with the MMAs per tile row (tc_cert_eps),
     // and a k' = 16 list's threshold then sits inside the certificate's margin of the k-th distance on data with ~1e-6 neighbour
@@ -929,11 +976,15 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     const uint32_t nq_pad = static_cast<uint32_t>(round_up<uint64_t>(nq, tc::BM));
     // f32 queries against a BF16 index go in as two or three bf16 terms q0 + q1 [+ q2]: 16 or 24 MMAs per tile
     const uint32_t bf16_terms = tc_bf16_terms(ix);
-    const uint32_t na = kind == tc::KIND_TF32X3 ? 2 : ((qt == QT_BF16 || kind == tc::KIND_I8) ? 1 : bf16_terms);
+    const uint32_t na = split3 ? 2 : ((qt == QT_BF16 || kind == tc::KIND_I8) ? 1 : bf16_terms);
 
     // ---- query operand: stacked pieces, zero padded ----
-    ANNB_TRY(st->q_op.ensure(static_cast<uint64_t>(kind == tc::KIND_TF32X3 ? 2 : 3) * nq_pad * kp * elem));
-    if (kind == tc::KIND_I8) {
+    ANNB_TRY(st->q_op.ensure(static_cast<uint64_t>(split3 ? 2 : 3) * nq_pad * kp * elem));
+    if (kind == tc::KIND_F16X3) {
+        ANNB_TRY(st->q_scale.ensure(static_cast<uint64_t>(nq_pad) * 4));
+        tc::split_f16_kernel<<<tc_blocks_for(static_cast<uint64_t>(nq_pad) * 32), 256, 0, s>>>(reinterpret_cast<const float*>(d_q), q_bytes / 4, ix->dim, nq, nq_pad, kp,
+                                                                                            st->q_op.as<__half>(), st->q_scale.as<float>());
+    } else if (kind == tc::KIND_I8) {
         tc::pad_i8_kernel<<<tc_blocks_for(static_cast<uint64_t>(nq_pad) * kp), 256, 0, s>>>(reinterpret_cast<const int8_t*>(d_q), q_bytes, ix->dim, nq, nq_pad, kp,
                                                                                          st->q_op.as<int8_t>());
     } else if (kind == tc::KIND_TF32X3) {
@@ -963,16 +1014,16 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     if (wide_k) splits_req = static_cast<uint32_t>(std::min<uint64_t>(db_tiles, std::max<uint32_t>(splits_req, (wide_k_lists(k_eff) + 1) / 2)));
     const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;
     const uint32_t splits = wide_k ? splits_req : static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
-    const uint32_t nb = kind == tc::KIND_TF32X3 ? 2 : 1;
+    const uint32_t nb = split3 ? 2 : 1;
     // query operand resident in TMEM (TS-mode MMA) when its pieces fit their column budget (bf16 terms: 64 columns each)
     const uint32_t bf16_piece_cols = kp > 128 ? 128u : 64u;
     const bool ts = ix->opt_tc_ts != 0 && (kind != tc::KIND_BF16 || na * bf16_piece_cols <= 256) && kp * elem <= (kind == tc::KIND_TF32X3 ? 1024u : 512u);
     const bool hyb = ts && kind == tc::KIND_BF16 && na == 3 && ix->opt_tc_bf16_hybrid != 0;
     // f32 rows of 129 .. 256 elements: hi piece in TMEM, lo piece in shared memory (option tc_f32_lo_smem = 1 forces it for narrow rows too)
-    const bool lo_s = ts && kind == tc::KIND_TF32X3 && (kp > 128 || ix->opt_tc_f32_lo_smem != 0);
-    const size_t fixed = 256 /*barriers*/ + 8 * 64 * 4 /*per-warp row constants*/;
+    const bool lo_s = ts && split3 && ((kind == tc::KIND_TF32X3 && kp > 128) || ix->opt_tc_f32_lo_smem != 0);
+    const size_t fixed = 256 /*barriers*/ + 2 * 8 * 64 * 4 /*per-warp row constants, two banks*/;
     const size_t budget = 227 * 1024;
-    size_t q_smem = ts ? ((hyb || lo_s) ? static_cast<size_t>(st->nslab) * tc::SLAB_TILE : 0) : static_cast<size_t>(kind == tc::KIND_TF32X3 ? 2 : (kind == tc::KIND_I8 ? 1 : 3)) * st->nslab * tc::SLAB_TILE;
+    size_t q_smem = ts ? ((hyb || lo_s) ? static_cast<size_t>(st->nslab) * tc::SLAB_TILE : 0) : static_cast<size_t>(split3 ? 2 : (kind == tc::KIND_I8 ? 1 : 3)) * st->nslab * tc::SLAB_TILE;
     // SS mode with a query tile that leaves fewer than two ring stages: stream the query slabs with the database slabs instead
     const bool stream_q = !ts && q_smem + fixed + 2 * nb * tc::SLAB_TILE > budget;
     if (stream_q) q_smem = 0;
@@ -985,13 +1036,14 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     // (a k' = 32 list does not fit the 112-register budget of 18 warps); option tc_epi_warps = 2 forces the narrow layout
     // (measured: four epilogue warps per quarter are SLOWER -- bf16 4.84 -> 5.29 ms, int8 3.15 -> 3.80 ms on 1M x 128: the epilogue
     // is bound by the 64 B / cycle TMEM read path, not by latency; kept behind option tc_epi_warps = 4)
-    const uint32_t ew = (kind != tc::KIND_TF32X3 && ts && kprime == 16 && ix->opt_tc_epi_warps == 4) ? 4u : 2u;
+    const uint32_t ew = (!split3 && ts && kprime == 16 && ix->opt_tc_epi_warps == 4) ? 4u : 2u;
     ANNB_TRY(st->part.ensure(nq * ew * splits * static_cast<uint64_t>(kprime) * 8));
     ANNB_TRY(st->gtau.ensure(static_cast<uint64_t>(nq_pad) * 4));
     ANNB_CUDA_CHECK(cudaMemsetAsync(st->gtau.p, 0xFF, static_cast<uint64_t>(nq_pad) * 4, s));
     tc::Params p{};
     p.nq = nq; p.n_rows = ix->n; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
     p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = na; p.aux = st->d_aux; p.hybrid = hyb ? 1u : 0u;
+    p.aux2 = st->d_aux2; p.q_inv_scale = st->q_scale.as<float>();
     p.lo_smem = lo_s ? 1u : 0u; p.stream_q = stream_q ? 1u : 0u; p.wide_k = wide_k ? 1u : 0u; p.strided = (wide_k || ix->opt_tc_strided != 0) ? 1u : 0u;
     p.part_keys = st->part.as<uint64_t>(); p.dbg = st->dbg.as<float>(); p.gtau = st->gtau.as<uint32_t>(); p.q_op = st->q_op.as<void>(); p.kp = kp; p.dbg_cycles = st->dbgc.as<unsigned long long>();
     {
@@ -1006,6 +1058,8 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
         if (ew == 4) rc = kind == tc::KIND_I8 ? ANNB_TC_LAUNCH4(tc::KIND_I8) : ANNB_TC_LAUNCH4(tc::KIND_BF16);
         else if (kind == tc::KIND_I8 && ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_I8, 16, true) : ANNB_TC_LAUNCH(tc::KIND_I8, 32, true);
         else if (kind == tc::KIND_I8) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_I8, 16, false) : ANNB_TC_LAUNCH(tc::KIND_I8, 32, false);
+        else if (kind == tc::KIND_F16X3 && ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_F16X3, 16, true) : ANNB_TC_LAUNCH(tc::KIND_F16X3, 32, true);
+        else if (kind == tc::KIND_F16X3) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_F16X3, 16, false) : ANNB_TC_LAUNCH(tc::KIND_F16X3, 32, false);
         else if (kind == tc::KIND_TF32X3 && ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, true) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, true);
         else if (kind == tc::KIND_TF32X3) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_TF32X3, 16, false) : ANNB_TC_LAUNCH(tc::KIND_TF32X3, 32, false);
         else if (ts) rc = kprime == 16 ? ANNB_TC_LAUNCH(tc::KIND_BF16, 16, true) : ANNB_TC_LAUNCH(tc::KIND_BF16, 32, true);

@@ -16,6 +16,7 @@ bool tc_flat_supported(const annb_index* ix, int qt, uint32_t k_eff);
 int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt, int bf16_self, uint64_t nq, uint32_t k_eff,
                    uint32_t k_out, uint64_t* d_ids, float* d_dist, uint32_t* d_cnt, cudaStream_t s);
 void tc_destroy(annb_index* ix);
+int tc_flat_kind(const annb_index* ix);   // operand form: -1 none, 0 3xTF32, 1 bf16 terms, 2 int8, 3 3xFP16
 // Error bound the coverage certificates assume for the pre-selection values of a (kind, padded K, query terms) kernel.
 uint32_t tc_bf16_terms(const annb_index* ix);
 float tc_cert_eps(const annb_index* ix, int kind, uint32_t kp_elems, uint32_t terms, bool inkernel_split);

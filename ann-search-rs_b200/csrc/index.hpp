@@ -84,6 +84,7 @@ struct annb_index {
     int opt_tc_wide_k = 1;      // flat tensor path: serve 24 < k <= 128 from the union of interleaved k' = 32 lists (0: such k go to the CUDA-core path)
     int opt_tc_strided = 0;     // flat tensor path: interleave the splits' tiles over the database also for k <= 24
     int opt_tc_f32_lo_smem = 0; // flat tensor path, f32 rows of <= 128 elements: lo query piece in shared memory (frees TMEM for a third accumulator stage)
+    int opt_tc_f32_fp16 = 1;    // flat tensor path, f32 index, rows <= 256 elements: 3xFP16 (rows scaled by powers of two) instead of 3xTF32
     int opt_tc_ts = 1;         // tensor path, f32: keep the query operand in TMEM (TS-mode MMA)
     int opt_db_splits = 0;
     int opt_scan_parts = 0;

@@ -2,6 +2,7 @@
 // the per-thread k' list, operand-preparation kernels and the exact re-rank kernel.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "refdist.cuh"
@@ -21,7 +22,8 @@ constexpr int ACC_STAGES = 4;          // accumulator ring in TMEM (4 x 128 colu
 constexpr int AUX_STAGES = 2;
 constexpr uint32_t TMEM_COLS = ACC_STAGES * BN;  // 512
 
-enum { KIND_TF32X3 = 0, KIND_BF16 = 1, KIND_I8 = 2 };   // 3xTF32 (f32 index), bf16 x3 query terms (BF16 index), int8 x int8 -> s32 (SQ8 index)
+// 3xTF32 (f32 index), bf16 query terms (BF16 index), int8 x int8 -> s32 (SQ8 index), 3xFP16 (f32 index, rows scaled by powers of two)
+enum { KIND_TF32X3 = 0, KIND_BF16 = 1, KIND_I8 = 2, KIND_F16X3 = 3 };
 
 struct Params {
     uint64_t nq;
@@ -41,6 +43,8 @@ struct Params {
     uint32_t strided;         // split y owns the tiles y, y + n_splits, ... (lists interleave over the database) instead of a contiguous range
     const float* aux;         // per database row: L2  v = aux - 2 s  (aux = |x|^2, pad rows +inf);
                               //                   cos v = s * aux    (aux = -1/|x|, pad rows +inf -> 0 * inf = NaN, never selected)
+    const float* aux2;        // KIND_F16X3, L2: per database row 1 / (its power-of-two operand scale); cosine folds it into aux
+    const float* q_inv_scale; // KIND_F16X3: per query 1 / (its power-of-two operand scale), [nq_pad]
     uint64_t* part_keys;      // [nq][2 * n_splits][KPRIME] packed (approx value, row); one list per 64-column half
     const void* q_op;         // stacked query operand [a_pieces][nq_pad][kp] (TS mode loads it into TMEM)
     uint32_t kp;              // padded K in elements
@@ -229,7 +233,7 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ uint32_t make_smem_desc(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 // UMMA instruction descriptor (cute/arch/mma_sm100_desc.hpp InstrDescriptor): f32 accumulate, K-major A and B.
 __host__ __device__ constexpr uint32_t make_idesc(int kind) {
-    const uint32_t fmt = (kind == KIND_TF32X3) ? 2u : 1u;  // TF32 = 2, BF16 = 1, signed INT8 = 1 (S8Format)
+    const uint32_t fmt = (kind == KIND_TF32X3) ? 2u : (kind == KIND_F16X3 ? 0u : 1u);  // TF32 = 2, F16 = 0, BF16 = 1, signed INT8 = 1 (S8Format)
     const uint32_t cfmt = (kind == KIND_I8) ? 2u : 1u;     // accumulator: F32 = 1, S32 = 2
     return (cfmt << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(BM >> 4) << 24);
 }
@@ -338,6 +342,49 @@ static __global__ void split_tf32_kernel(const float* __restrict__ src, uint32_t
         dst[i] = hi;
         dst[total + i] = lo;
     }
+}
+// f32 rows -> stacked [2][rows_pad][kp] fp16 hi / lo of the row scaled by a power of two, zero padded; inv_scale[row] = 1 / scale.
+// fp16 carries the 11 significant bits of tf32, so hi + lo holds x to 2^-22 |x| exactly like the tf32 split -- but a kind::f16 MMA
+// multiplies 16 elements per K step where kind::tf32 multiplies 8: the same three-term product at half the tensor-pipe time.
+// What fp16 lacks is exponent range (5 bits); every row is therefore scaled so that its largest element lands in [2^13, 2^14):
+// hi never overflows, lo (<= 2^-11 of hi) stays normal for every element within 2^-14 of the row maximum, and smaller elements
+// are off by at most 2^-25 against a row maximum of 2^13 -- far below the 2^-22 the split promises relative to the row NORM,
+// which is all the certificate's error model uses.  Scales are powers of two: applying and undoing them is exact.
+// One warp per row.
+static __global__ void split_f16_kernel(const float* __restrict__ src, uint32_t ld_src, uint32_t dim, uint64_t rows, uint64_t rows_pad, uint32_t kp,
+                                        __half* __restrict__ dst, float* __restrict__ inv_scale) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t total = rows_pad * kp;
+    for (uint64_t r = blockIdx.x * static_cast<uint64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows_pad; r += static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5)) {
+        float m = 0.f;
+        if (r < rows)
+            for (uint32_t c = lane; c < dim; c += 32) m = fmaxf(m, fabsf(src[r * ld_src + c]));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+        int e = 0;
+        if (m > 0.f && m < INFINITY) {
+            int ex;
+            (void)frexpf(m, &ex);                 // m = f * 2^ex, f in [0.5, 1)
+            e = min(max(14 - ex, -100), 100);     // m * 2^e in [2^13, 2^14)
+        }
+        const float scale = ldexpf(1.0f, e);
+        for (uint32_t c = lane; c < kp; c += 32) {
+            __half h = __float2half_rn(0.f), l = h;
+            if (r < rows && c < dim) {
+                const float xs = __fmul_rn(src[r * ld_src + c], scale);
+                h = __float2half_rn(xs);
+                l = __float2half_rn(__fsub_rn(xs, __half2float(h)));
+            }
+            dst[r * kp + c] = h;
+            dst[total + r * kp + c] = l;
+        }
+        if (lane == 0) inv_scale[r] = ldexpf(1.0f, -e);
+    }
+}
+// aux[i] *= s[i] (cosine row constants of the 3xFP16 kernel carry the row's inverse operand scale)
+static __global__ void mul_rows_kernel(float* __restrict__ aux, const float* __restrict__ s, uint64_t n) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) aux[i] *= s[i];
 }
 // f32 queries -> stacked [3][rows_pad][kp] bf16 terms q0 + q1 + q2 (each RNE), zero padded.
 static __global__ void split_bf16x3_kernel(const float* __restrict__ src, uint32_t ld_src, uint32_t dim, uint64_t rows, uint64_t rows_pad, uint32_t kp,

@@ -403,11 +403,18 @@ class Searcher:
         return self.out_ids.cpu().numpy(), self.out_dist.cpu().numpy()
 
 
-def tensor_roofline(c, dtype, flops, dom_s, kernel, tf32_peak, bf16_terms=2):
+def tensor_roofline(c, dtype, flops, dom_s, kernel, tf32_peak, bf16_terms=2, f32_kind=0):
     """Roofline row of a tensor-core kernel: achieved = algorithmic flops / kernel time.
-    bf16_terms: bf16 terms the f32 query is fed as (library default: 2 for cosine, 3 for squared Euclidean)."""
+    bf16_terms: bf16 terms the f32 query is fed as (library default: 2 for cosine, 3 for squared Euclidean).
+    f32_kind: operand form of the f32 kernel (stat tc_kind): 0 = 3xTF32 (kind::tf32 pipe), 3 = 3xFP16 (kind::f16 pipe: the same three
+    product terms at 16 elements per MMA K step, so its peak is the 16-bit pipe's, not the TF32 pipe's)."""
     peaks = c.peaks
-    if dtype == "f32":
+    if dtype == "f32" and f32_kind == 3:
+        pipe_peak = pipe_alt = peaks["bf16_tflops"]
+        peak, terms = pipe_peak / 3.0, 3
+        note = (f"{c.peak_src} 16-bit tensor burst peak ({pipe_peak:.1f} TFLOP/s, cuBLAS bf16) / 3 (3xFP16 terms); "
+                f"sustained figure of the same file: {peaks.get('bf16_tflops_sustained', 0):.1f}")
+    elif dtype == "f32":
         pipe_alt = peaks["bf16_tflops"] / 2.0
         pipe_peak = tf32_peak if tf32_peak else pipe_alt
         peak = pipe_peak / 3.0
@@ -423,9 +430,13 @@ def tensor_roofline(c, dtype, flops, dom_s, kernel, tf32_peak, bf16_terms=2):
         peak, terms = pipe_peak, 1
         note = f"2 x {c.peak_src} bf16 burst peak (nominal int8:bf16 ratio; the int8 pipe is not measured separately)"
     achieved = flops / dom_s / 1e12 if dom_s > 0 else 0.0
-    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "kernel": kernel,
-            "kernel_ms": dom_s * 1e3, "peak_source": note, "pipe_peak_from_bf16": pipe_alt,
-            "executed": {"mma_terms_per_element": terms, "tflops": achieved * terms, "pipe_peak": pipe_peak, "frac_of_pipe_peak": achieved * terms / pipe_peak}}
+    out = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "kernel": kernel,
+           "kernel_ms": dom_s * 1e3, "peak_source": note, "pipe_peak_from_bf16": pipe_alt,
+           "executed": {"mma_terms_per_element": terms, "tflops": achieved * terms, "pipe_peak": pipe_peak, "frac_of_pipe_peak": achieved * terms / pipe_peak}}
+    if dtype == "f32" and f32_kind == 3 and peaks.get("bf16_tflops_sustained"):
+        out["executed"]["frac_of_sustained_pipe_peak"] = achieved * terms / peaks["bf16_tflops_sustained"]
+        out["executed"]["operand_form"] = "3xFP16: rows scaled by powers of two, fp16 hi + lo pieces, f32 accumulate"
+    return out
 
 
 def tie_classes_equal(ids, dist, ref_ids, ref_dist):
@@ -506,8 +517,12 @@ def bench_flat(c, n, dim, nq, k, metric, dtype, self_queries, tf32_peak, on_gpu_
         return None
     rows_local = (n + c.shards - 1) // c.shards
     flops = 2.0 * nq * rows_local * dim                          # algorithmic flops per launch: 2 * nq * n_local * d
+    try:
+        f32_kind = index.get_stat("tc_kind")
+    except Exception:
+        f32_kind = 0
     roofline = tensor_roofline(c, dtype, flops, r["dom_s"], "flat distance + top-k select (flat_tc_kernel)", tf32_peak,
-                               bf16_terms=(1 if self_queries else (2 if metric == "cosine" else 3)))
+                               bf16_terms=(1 if self_queries else (2 if metric == "cosine" else 3)), f32_kind=f32_kind)
     roofline["path"] = {0: "auto", 1: "simt (CUDA cores)", 2: "tensor (tcgen05)"}.get(last_path, str(last_path))
     if last_path != 2:
         roofline["executed"]["mma_terms_per_element"] = 0
@@ -521,7 +536,7 @@ def bench_flat(c, n, dim, nq, k, metric, dtype, self_queries, tf32_peak, on_gpu_
     line = {"metric": f"QPS flat {dtype} {metric} k={k}" + (" self-query" if self_queries else ""), "value": r["qps"], "unit": "queries/s",
             "n_gpus": c.shards, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None,
-            "dtype": {"f32": "f32 (3xTF32 select + f32 exact re-rank)" if last_path == 2 else "f32", "bf16": "bf16 (f32 accumulate)",
+            "dtype": {"f32": ("f32 (3xFP16 split-precision select + f32 exact re-rank)" if f32_kind == 3 else "f32 (3xTF32 select + f32 exact re-rank)") if last_path == 2 else "f32", "bf16": "bf16 (f32 accumulate)",
                       "sq8": "int8 (i32 accumulate)"}[dtype],
             "data": "synthetic",
             "config": {"workload": w, "n": n, "dim": dim, "nq": nq, "k": k,

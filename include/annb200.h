@@ -365,7 +365,10 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
  *               "tc_wide_k" (flat tensor path: 1 = serve 24 < k <= 256 -- the reference's radix-select range, src/gpu/topk_gpu.rs:95 --
  *               from the union of interleaved k' = 32 lists, and let a handle whose batches fail the certificate switch to that mode;
  *               0 = such k go to the CUDA-core path), "tc_strided" (1 = interleave the splits' tiles over the database also for k <= 24),
- *               "tc_f32_lo_smem" (f32 rows of <= 128 elements: 1 = lo query piece in shared memory, a third accumulator stage in TMEM)
+ *               "tc_f32_lo_smem" (f32 rows of <= 128 elements: 1 = lo query piece in shared memory, a third accumulator stage in TMEM),
+ *               "tc_f32_fp16" (flat f32 index, rows of <= 256 elements: 1 (default) = 3xFP16 pre-selection -- rows scaled by powers of two,
+ *               fp16 hi + lo pieces, the three product terms of 3xTF32 at twice the elements per MMA; 0 = 3xTF32.  Changing it rebuilds
+ *               the handle's tensor-core operand copy)
  *   get_stat  : "kernel_launches" (cumulative), "scanned_vectors" (IVF, last call: sum of probed
  *               list lengths), "scanned_vectors_local" (the part of it that lies in this handle's own lists),
  *               "probed_lists" (last call), "last_path" (annb_path actually used),
@@ -373,6 +376,7 @@ int annb_index_get_info(const annb_index* index, annb_index_info* out);
  *               "uncertified" (tensor path, last call: queries that failed the coverage certificate),
  *               "fallback_queries" (cumulative: queries recomputed on the exact path),
  *               "cert_eps_bits" (f32 bit pattern of the error bound the last tensor-path certificate assumed),
+ *               "tc_kind" (flat: operand form of the tensor path: -1 none, 0 3xTF32, 1 bf16 terms, 2 int8, 3 3xFP16),
  *               "tc_escalated" (flat: 1 once a batch left more than 2 % of its queries uncertified -- later batches run in wide-k mode),
  *               "dominant_kernel_ns" / "dominant_kernel_launches" (with "time_kernels": summed device time and count
  *               of the dominant kernel -- flat distance+select kernel or IVF list-scan kernel -- since the option was set) */

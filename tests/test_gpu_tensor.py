@@ -354,3 +354,39 @@ def test_escalation_to_wide_mode_after_an_uncertified_batch(gpu):
     ids, d, _ = g.query_batch(q, 10)
     assert g.get_stat("last_path") == annb200.PATH_TENSOR
     assert_exact(ids, d, ref[0], ref[1], "wide mode at k = 10")
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_f32_operand_forms_agree(gpu, metric):
+    """3xFP16 (default: rows scaled by powers of two, fp16 hi + lo) and 3xTF32 pre-selection give the oracle's rows; data with a
+    wide dynamic range inside rows and across rows (the scaling must keep small rows and small elements accurate)."""
+    rng = np.random.default_rng(71)
+    base = datagen.correlated(30_000, 96, seed=71)
+    row_scale = np.float32(10.0) ** rng.integers(-6, 7, base.shape[0]).astype(np.float32)            # |x| over 12 decades
+    col_scale = np.float32(2.0) ** rng.integers(-10, 11, base.shape[1]).astype(np.float32)           # elements over 6 decades inside a row
+    data = np.ascontiguousarray(base * row_scale[:, None] * col_scale[None, :], dtype=np.float32)
+    q = datagen.subsample_with_noise(data, 300, seed=71)
+    g, c = _pair(data, "f32", metric)
+    ref = o.flat_search(c, q, 10)
+    assert g.get_stat("tc_kind") == 3
+    ids, d, _ = g.query_batch(q, 10)
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    assert_exact(ids, d, ref[0], ref[1], f"3xFP16 {metric}")
+    g.set_option("tc_f32_fp16", 0)
+    assert g.get_stat("tc_kind") == 0
+    ids, d, _ = g.query_batch(q, 10)
+    assert_exact(ids, d, ref[0], ref[1], f"3xTF32 {metric}")
+    g.set_option("tc_f32_fp16", 1)
+    g.set_option("tc_debug", 1)
+    g.set_option("db_splits", 1)
+    g.query_batch(q, 10)
+    v = g.debug_fetch_tile().astype(np.float64)
+    x = data[:128].astype(np.float64)
+    s = q[:128].astype(np.float64) @ x.T
+    qn, xn = np.sqrt((q[:128].astype(np.float64) ** 2).sum(1)), np.sqrt((x * x).sum(1))
+    if metric == "l2":
+        err = np.abs(v - ((x * x).sum(1)[None, :] - 2 * s)) / (qn[:, None] + xn[None, :]) ** 2
+    else:
+        err = np.abs(v - (-s / c.norms[:128].astype(np.float64)[None, :])) / qn[:, None]
+    eps = g.cert_eps()
+    assert err.max() <= eps, f"selection-value error {err.max():.3e} exceeds the certificate bound {eps:.3e}"
