@@ -1816,6 +1816,12 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
                 tc_destroy(ix);
                 ANNB_TRY(tc_flat_prepare(ix));
                 ANNB_CUDA_CHECK(cudaStreamSynchronize(ix->stream));
+            } else if (ix->is_ivf && ix->dtype == ANNB_F32 && ix->tc_ivf != nullptr) {
+                DeviceGuard g(ix->device);
+                ANNB_CUDA_CHECK(cudaStreamSynchronize(ix->stream));
+                tc_ivf_destroy(ix);
+                ANNB_TRY(tc_ivf_prepare(ix));
+                ANNB_CUDA_CHECK(cudaStreamSynchronize(ix->stream));
             }
         }
     }

@@ -47,6 +47,8 @@ struct IvfTcParams {
     uint32_t bf16_terms;       // bf16 lists: bf16 terms of the f32 query (2 or 3)
     uint64_t* part_keys;       // [nq][probe_pitch][2][KP]
     uint32_t* gtau;            // [nq] shared pruning threshold
+    const float* aux2;         // KIND_F16X3: per stored row 1 / (its power-of-two operand scale)
+    const float* q_inv_scale;  // KIND_F16X3: per query 1 / (its power-of-two operand scale), [nq]
     uint32_t lo_smem;          // f32 lists with rows of 129 .. 256 elements: only the hi query piece fits TMEM beside two accumulator stages;
                                // the lo piece is gathered into shared memory (swizzled K slabs) and its term is an SS-mode MMA
     unsigned long long* dbg;   // optional [8]: CTA 0 cycle counters {total, schedule, gather, epi wait-tfull, mma wait-queries, mma wait-data, mma wait-tempty, tasks << 32 | tiles}
@@ -61,16 +63,22 @@ template <int KIND> constexpr int ivf_tc_threads() { return KIND == KIND_TF32X3 
 
 template <int KIND, int KP, int MET>
 __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const IvfTcParams p) {
+    // KIND_F16X3 (f32 lists, 3xFP16): the operand is a pre-split copy of the lists, stacked fp16 hi / lo pieces of the rows scaled by
+    // their powers of two (split_f16_kernel; 4 B per element like the f32 rows themselves) -- a ring stage is one hi and one lo K slab
+    // (64 elements of K), no transform warps.  (Converting the raw f32 slabs inside the kernel was tried first: two transform warps
+    // need ~2 000 cycles per tile for it and paced the kernel at 3.2 ms where 3xTF32 takes 2.1.)
     constexpr bool XFORM = (KIND == KIND_TF32X3);
-    constexpr int NB = (KIND == KIND_TF32X3) ? 2 : 1;
-    constexpr int ELEM = (KIND == KIND_TF32X3) ? 4 : (KIND == KIND_I8 ? 1 : 2);
+    constexpr bool F16 = (KIND == KIND_F16X3);
+    constexpr int NB = (XFORM || F16) ? 2 : 1;
+    constexpr int ELEM = XFORM ? 4 : (KIND == KIND_I8 ? 1 : 2);      // element size of what TMA loads
     constexpr int SLAB_ELEMS = SLAB_BYTES / ELEM;
     constexpr int KSTEPS = 4;
     // TMEM: query pieces at column 0 (f32 hi / lo 2 x 128 columns, bf16 terms 64 or 128 each, int8 codes <= 128), accumulator
     // ring behind them: three stages when the pieces fit 128 columns, two otherwise
     const bool lo_s = KIND == KIND_TF32X3 && p.lo_smem != 0;
-    const uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? (lo_s ? p.nslab * 32u : 128u) : (KIND == KIND_I8 ? 128u : (p.nslab > 2u ? 128u : 64u));
-    const uint32_t q_cols = (KIND == KIND_TF32X3) ? (lo_s ? PIECE_COLS : 256u) : (KIND == KIND_I8 ? 128u : p.bf16_terms * PIECE_COLS);
+    const uint32_t PIECE_COLS = (KIND == KIND_TF32X3) ? (lo_s ? p.nslab * 32u : 128u)
+                                : (F16 ? p.nslab * 32u : (KIND == KIND_I8 ? 128u : (p.nslab > 2u ? 128u : 64u)));
+    const uint32_t q_cols = (KIND == KIND_TF32X3) ? (lo_s ? PIECE_COLS : 256u) : (F16 ? 2u * PIECE_COLS : (KIND == KIND_I8 ? 128u : p.bf16_terms * PIECE_COLS));
     const uint32_t NACC = q_cols <= 128u ? 3u : 2u;
     const uint32_t ACC_COL0 = q_cols <= 128u ? 128u : 256u;
     constexpr uint32_t idesc = make_idesc(KIND);
@@ -92,7 +100,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_tempty + 3);
     uint32_t* s_task = s_tmem + 1;                 // [4]: list, pair0, n_in_group, valid flag
     uint64_t* s_rows = reinterpret_cast<uint64_t*>(s_tmem + 6);  // [2]: r_begin, r_end (8-byte aligned: bars + ... even count)
-    float* s_aux_all = reinterpret_cast<float*>(s_tail + 512);   // [8 epilogue warps][64] row constants of the warp's current half tile
+    float* s_aux_all = reinterpret_cast<float*>(s_tail + 512);   // [2 banks][8 epilogue warps][64] row constants of the warp's current half tile
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < p.n_stages; s++) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); mbar_init(bar_xf + s, XF_THREADS); }
@@ -194,7 +202,11 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                         for (int k = 0; k < KSTEPS; k++) {
                             const uint32_t first = (s | static_cast<uint32_t>(k)) != 0 ? 1u : 0u;
                             const uint32_t a0 = tmem_base + s * 32 + k * 8;
-                            if (KIND == KIND_TF32X3) {
+                            if (F16) {
+                                umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
+                                umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
+                                umma_ts<KIND>(tmem_c, a0, xd + SLAB_DESC + 2 * k, idesc, 1u);
+                            } else if (KIND == KIND_TF32X3) {
                                 umma_ts<KIND>(tmem_c, a0, xd + 2 * k, idesc, first);
                                 if (lo_s) umma<KIND>(tmem_c, qlo_desc0 + s * SLAB_DESC + 2 * k, xd + 2 * k, idesc, 1u);   // Qlo from shared memory
                                 else umma_ts<KIND>(tmem_c, a0 + PIECE_COLS, xd + 2 * k, idesc, 1u);
@@ -274,9 +286,10 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                         for (int c = 0; c < 8; c++) *reinterpret_cast<uint4*>(dst + ((static_cast<uint32_t>(c) ^ (row_in_tile & 7u)) << 4)) = x[c];
                     }
                     fence_proxy_async();           // generic-proxy writes -> visible to the tensor core's async-proxy reads
-                } else if (KIND == KIND_TF32X3) {
-                    // pieces were split once per batch (split_tf32_kernel): half 0 copies hi to columns [0,128), half 1 lo to [128,256)
-                    // (wide rows: half 0 copies the whole hi piece, the lo piece goes to shared memory above)
+                } else if (XFORM || F16) {
+                    // pieces were split once per batch (split_tf32_kernel / split_f16_kernel): half 0 copies hi to columns [0, PIECE_COLS), half 1 lo behind it
+                    // (wide tf32 rows: half 0 copies the whole hi piece, the lo piece goes to shared memory above)
+                    const uint32_t kp = F16 ? p.nslab * 32u : p.nslab * SLAB_ELEMS;    // 32-bit words of a piece row (3xFP16: two elements per word)
                     const uint4* src = reinterpret_cast<const uint4*>(static_cast<const float*>(p.q_op) + (static_cast<uint64_t>(half) * p.nq + (has_query ? pr.x : 0)) * kp);
                     const uint32_t tq = tmem_base + ((quarter * 32u) << 16) + half * PIECE_COLS;
                     uint32_t c = 0;
@@ -326,6 +339,11 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                 c_gather += tc_clock() - c_t1;
             }
             top.init();
+            // 3xFP16: undo the operands' power-of-two scales -- per stored row (L2: second per-column constant; cosine: folded into aux)
+            // and per query (cq)
+            constexpr bool RX = F16 && (MET == MET_L2);
+            float cq = 1.0f;
+            if (F16) cq = (has_query ? __ldg(p.q_inv_scale + pr.x) : 1.0f) * ((MET == MET_L2) ? -2.0f : 1.0f);
             uint32_t* gtau_ptr = p.gtau + (has_query ? pr.x : 0);
             uint32_t g_next = has_query ? *reinterpret_cast<volatile uint32_t*>(gtau_ptr) : 0u;   // 0 = ordered(-NaN): prunes everything
             const float* aux_half = p.aux + r_begin + half * 64 + lane;
@@ -335,21 +353,27 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                 hi_v = (c0 + 32 < r_end) ? __ldg(aux_half + static_cast<size_t>(t) * BN + 32) : __int_as_float(0x7FC00000);
             };
             float* s_aux = s_aux_all + (warp - EPI_WARP0) * 64;   // warp-private: read back as broadcast loads by the value loop
-            float aux_lo_next = 0.f, aux_hi_next = 0.f;
+            float* s_rx = s_aux_all + (8 + (warp - EPI_WARP0)) * 64;
+            const float* rx_half = RX ? p.aux2 + r_begin + half * 64 + lane : nullptr;
+            float aux_lo_next = 0.f, aux_hi_next = 0.f, rx_lo_next = 1.f, rx_hi_next = 1.f;
             if (n_tiles > 0) load_aux(0, aux_lo_next, aux_hi_next);
+            if (RX && n_tiles > 0) { rx_lo_next = __ldg(rx_half); rx_hi_next = __ldg(rx_half + 32); }
             for (uint32_t t = 0; t < n_tiles; t++, tg++) {
                 const uint32_t acc = tg % NACC, aph = (tg / NACC) & 1u;
                 const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
                 const uint32_t g_bits = g_next;
                 const float aux_lo = aux_lo_next, aux_hi = aux_hi_next;
+                const float rx_lo = rx_lo_next, rx_hi = rx_hi_next;
                 if (t + 1 < n_tiles) {
                     load_aux(t + 1, aux_lo_next, aux_hi_next);
+                    if (RX) { rx_lo_next = __ldg(rx_half + static_cast<size_t>(t + 1) * BN); rx_hi_next = __ldg(rx_half + static_cast<size_t>(t + 1) * BN + 32); }
                     if (has_query) g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
                 }
                 if (warp_has_query) {
                     __syncwarp();                  // every lane is done with the previous tile's constants
                     s_aux[lane] = aux_lo;
                     s_aux[lane + 32] = aux_hi;
+                    if (RX) { s_rx[lane] = rx_lo; s_rx[lane + 32] = rx_hi; }
                     __syncwarp();
                 }
                 mbar_wait_timed(bar_tfull + acc, aph, c_tfull);
@@ -373,7 +397,8 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                             const int col = g * 8 + j;
                             const float cst = s_aux[col];
                             const float sdot = (KIND == KIND_I8) ? __int2float_rn(static_cast<int32_t>(r[col])) : __uint_as_float(r[col]);
-                            v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
+                            if (F16) v[col] = (MET == MET_L2) ? fmaf(sdot * s_rx[col], cq, cst) : (sdot * cst) * cq;
+                            else v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
                             mg = fminf(mg, v[col]);
                         }
                         gm[g] = mg;
@@ -423,16 +448,19 @@ struct IvfTcState {
     uint32_t kp_elems = 0, nslab = 0, n_pad = 0;
     void* d_x = nullptr;
     float* d_aux = nullptr;
+    float* d_aux2 = nullptr;   // KIND_F16X3: inverse power-of-two operand scale of every stored row
     CUtensorMap tm_x;
-    DevBuf part, gtau, dbgc, q_op;
+    DevBuf part, gtau, dbgc, q_op, q_scale;
     uint64_t bytes = 0;
 };
 
 int tc_ivf_prepare(annb_index* ix) {
     if (!ix->is_ivf || ix->n == 0) return ANNB_OK;
-    const int kind = ix->dtype == ANNB_F32 ? tc::KIND_TF32X3 : (ix->dtype == ANNB_BF16 ? tc::KIND_BF16 : tc::KIND_I8);
-    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : (kind == tc::KIND_BF16 ? 2 : 1);
-    const uint32_t slab_elems = tc::SLAB_BYTES / elem;
+    int kind = ix->dtype == ANNB_F32 ? tc::KIND_TF32X3 : (ix->dtype == ANNB_BF16 ? tc::KIND_BF16 : tc::KIND_I8);
+    // f32 lists with rows of up to 256 elements: 3xFP16 (see split_f16_kernel; the kernel converts the raw f32 slabs in place)
+    if (kind == tc::KIND_TF32X3 && ix->opt_tc_f32_fp16 != 0 && round_up(ix->dim, 64u) <= 256u) kind = tc::KIND_F16X3;
+    const uint32_t elem = kind == tc::KIND_TF32X3 ? 4 : (kind == tc::KIND_I8 ? 1 : 2);   // element size of the operand TMA loads
+    const uint32_t slab_elems = tc::SLAB_BYTES / elem;                                  // K elements per ring stage
     const uint32_t kp = round_up(ix->dim, slab_elems);
     // the query pieces live in TMEM (128 columns per f32 / int8 piece, 64 or 128 per bf16 term); larger dims stay on the CUDA-core scan
     // (f32 rows of up to 1024 B keep their lo piece in shared memory, IvfTcParams::lo_smem)
@@ -450,14 +478,30 @@ int tc_ivf_prepare(annb_index* ix) {
         if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc aux: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
         st->bytes += aux_rows * sizeof(float);
     }
-    tc::aux_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(ix->d_rows, ix->row_bytes, kind, ix->dim, ix->d_norms, ix->d_norms_i,
+    tc::aux_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(ix->d_rows, ix->row_bytes, kind == tc::KIND_F16X3 ? 0 : kind, ix->dim, ix->d_norms, ix->d_norms_i,
                                                                                 ix->metric == ANNB_COSINE, ix->n, aux_rows, st->d_aux);
     ANNB_CUDA_CHECK(cudaGetLastError());
+    if (kind == tc::KIND_F16X3) {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&st->d_aux2), aux_rows * sizeof(float));
+        if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc row scales: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
+        st->bytes += aux_rows * sizeof(float);
+        tc::fill_f32_value_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(st->d_aux2, aux_rows, 1.0f);
+        const uint64_t xbytes = 2ull * st->n_pad * kp * 2;
+        e = cudaMalloc(&st->d_x, xbytes);
+        if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
+        st->bytes += xbytes;
+        tc::split_f16_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * 32), 256, 0, s>>>(reinterpret_cast<const float*>(ix->d_rows), ix->row_bytes / 4, ix->dim, ix->n, st->n_pad, kp,
+                                                                                            static_cast<__half*>(st->d_x), st->d_aux2);
+        if (ix->metric == ANNB_COSINE) tc::mul_rows_kernel<<<static_cast<uint32_t>((ix->n + 127) / 128), 128, 0, s>>>(st->d_aux, st->d_aux2, ix->n);
+        ANNB_CUDA_CHECK(cudaGetLastError());
+    }
     // Database operand: the index's own rows whenever their pitch is a whole number of 128-byte K slabs (dim % 32 == 0 for
     // f32, % 64 for bf16, % 128 for SQ8) -- TMA zero-fills the rows past the end; otherwise a zero-padded copy.  f32 rows
     // are split into tf32 hi / lo inside the kernel.
     void* xbase = ix->d_rows;
-    if (ix->row_bytes != kp * elem) {
+    if (kind == tc::KIND_F16X3) {
+        xbase = st->d_x;
+    } else if (ix->row_bytes != kp * elem) {
         const uint64_t bytes = static_cast<uint64_t>(ix->n) * kp * elem;
         cudaError_t e = cudaMalloc(&st->d_x, bytes);
         if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
@@ -466,7 +510,7 @@ int tc_ivf_prepare(annb_index* ix) {
         ANNB_CUDA_CHECK(cudaGetLastError());
         xbase = st->d_x;
     }
-    ANNB_TRY(tc_make_tmap(&st->tm_x, xbase, ix->n, kp, elem));
+    ANNB_TRY(tc_make_tmap(&st->tm_x, xbase, kind == tc::KIND_F16X3 ? 2ull * st->n_pad : ix->n, kp, elem));
     ANNB_TRY(tc_compute_xnorm_max(ix, st->d_aux, ix->n));
     ix->device_bytes += st->bytes;
     return ANNB_OK;
@@ -476,6 +520,8 @@ void tc_ivf_destroy(annb_index* ix) {
     if (!ix->tc_ivf) return;
     cudaFree(ix->tc_ivf->d_x);
     cudaFree(ix->tc_ivf->d_aux);
+    cudaFree(ix->tc_ivf->d_aux2);
+    ix->tc_ivf->q_scale.release();
     ix->tc_ivf->part.release();
     ix->tc_ivf->gtau.release();
     ix->tc_ivf->dbgc.release();
@@ -542,8 +588,8 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
                 const void* d_tasks) {
     IvfTcState* st = ix->tc_ivf;
     const uint32_t kprime = tc_ivf_kprime(ix, k_eff);
-    const uint32_t nb = st->kind == tc::KIND_TF32X3 ? 2 : 1;
-    const size_t fixed = 512 /*barriers, task slots (<= 296 B)*/ + 8 * 64 * 4 /*per-warp row constants*/;
+    const uint32_t nb = (st->kind == tc::KIND_TF32X3 || st->kind == tc::KIND_F16X3) ? 2 : 1;
+    const size_t fixed = 512 /*barriers, task slots (<= 296 B)*/ + 2 * 8 * 64 * 4 /*per-warp row constants, two banks*/;
     const size_t budget = 227 * 1024;
     const bool lo_s = st->kind == tc::KIND_TF32X3 && st->kp_elems > 128;
     const size_t q_smem = lo_s ? static_cast<size_t>(st->nslab) * tc::SLAB_TILE : 0;
@@ -558,7 +604,13 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     // operand pieces of the batch's queries, split once (every query is gathered once per probed list)
     const uint32_t kp_q = st->kp_elems;
     const uint32_t bf16_terms = kp_q <= 128 ? tc_bf16_terms(ix) : 2u;   // three terms need rows of at most 128 elements (TMEM columns)
-    if (st->kind == tc::KIND_TF32X3) {
+    if (st->kind == tc::KIND_F16X3) {
+        ANNB_TRY(st->q_op.ensure(2ull * nq * kp_q * 2));
+        ANNB_TRY(st->q_scale.ensure(nq * 4 + 16));
+        tc::split_f16_kernel<<<tc_blocks_for(nq * 32), 256, 0, s>>>(reinterpret_cast<const float*>(d_q), q_bytes / 4, ix->dim, nq, nq, kp_q, st->q_op.as<__half>(), st->q_scale.as<float>());
+        ANNB_CUDA_CHECK(cudaGetLastError());
+        ix->stat_launches++;
+    } else if (st->kind == tc::KIND_TF32X3) {
         ANNB_TRY(st->q_op.ensure(2ull * nq * kp_q * 4));
         tc::split_tf32_kernel<<<tc_blocks_for(nq * kp_q), 256, 0, s>>>(reinterpret_cast<const float*>(d_q), q_bytes / 4, ix->dim, nq, nq, kp_q, st->q_op.as<float>());
         ANNB_CUDA_CHECK(cudaGetLastError());
@@ -571,7 +623,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
         ix->stat_launches++;
     }
     tc::IvfTcParams p{};
-    p.q_op = st->q_op.p; p.nq = nq; p.bf16_terms = bf16_terms; p.lo_smem = lo_s ? 1u : 0u;
+    p.q_op = st->q_op.p; p.nq = nq; p.bf16_terms = bf16_terms; p.lo_smem = lo_s ? 1u : 0u; p.aux2 = st->d_aux2; p.q_inv_scale = st->q_scale.as<float>();
     p.queries = d_q; p.q_bytes = q_bytes; p.dim = ix->dim; p.nslab = st->nslab; p.n_stages = stages; p.n_pad = st->n_pad; p.aux = st->d_aux;
     p.offsets = ix->d_offsets; p.shard_row0 = ix->shard_row0; p.nlist = ix->nlist; p.pair_off = d_pair_off; p.task_off = d_task_off;
     p.pairs = static_cast<const uint2*>(d_pairs); p.tasks = static_cast<const uint4*>(d_tasks); p.task_counter = d_task_counter; p.probe_pitch = probe_pitch;
@@ -583,6 +635,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
         int rc;
 #define ANNB_IVF_TC(KIND_, KP_) (l2 ? launch_ivf_tc<KIND_, KP_, MET_L2>(st->tm_x, p, grid, smem, s) : launch_ivf_tc<KIND_, KP_, MET_COS>(st->tm_x, p, grid, smem, s))
         if (st->kind == tc::KIND_I8) rc = kprime == 16 ? ANNB_IVF_TC(tc::KIND_I8, 16) : ANNB_IVF_TC(tc::KIND_I8, 32);
+        else if (st->kind == tc::KIND_F16X3) rc = kprime == 16 ? ANNB_IVF_TC(tc::KIND_F16X3, 16) : ANNB_IVF_TC(tc::KIND_F16X3, 32);
         else if (st->kind == tc::KIND_TF32X3) rc = kprime == 16 ? ANNB_IVF_TC(tc::KIND_TF32X3, 16) : ANNB_IVF_TC(tc::KIND_TF32X3, 32);
         else rc = kprime == 16 ? ANNB_IVF_TC(tc::KIND_BF16, 16) : ANNB_IVF_TC(tc::KIND_BF16, 32);
 #undef ANNB_IVF_TC

@@ -381,6 +381,29 @@ static __global__ void split_f16_kernel(const float* __restrict__ src, uint32_t 
         if (lane == 0) inv_scale[r] = ldexpf(1.0f, -e);
     }
 }
+// inv_scale[r] = 1 / (power-of-two scale that brings the largest element of row r into [2^13, 2^14)) -- the scale split_f16_kernel
+// would choose; the IVF scan converts its f32 slabs inside the kernel and only needs the scales.  One warp per row.
+static __global__ void row_inv_scale_kernel(const float* __restrict__ src, uint32_t ld_src, uint32_t dim, uint64_t rows, uint64_t rows_pad, float* __restrict__ inv_scale) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint64_t r = blockIdx.x * static_cast<uint64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows_pad; r += static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5)) {
+        float m = 0.f;
+        if (r < rows)
+            for (uint32_t c = lane; c < dim; c += 32) m = fmaxf(m, fabsf(src[r * ld_src + c]));
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+        int e = 0;
+        if (m > 0.f && m < INFINITY) {
+            int ex;
+            (void)frexpf(m, &ex);
+            e = min(max(14 - ex, -100), 100);
+        }
+        if (lane == 0) inv_scale[r] = ldexpf(1.0f, -e);
+    }
+}
+static __global__ void fill_f32_value_kernel(float* __restrict__ p, uint64_t n, float v) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i < n) p[i] = v;
+}
 // aux[i] *= s[i] (cosine row constants of the 3xFP16 kernel carry the row's inverse operand scale)
 static __global__ void mul_rows_kernel(float* __restrict__ aux, const float* __restrict__ s, uint64_t n) {
     const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
