@@ -1905,7 +1905,7 @@ int annb_index_get_stat(const annb_index* ix, const char* key, int64_t* out) {
     else if (k == "fallback_queries") *out = ix->stat_fallback_queries;
     else if (k == "cert_eps_bits") *out = ix->stat_cert_eps_bits;
     else if (k == "tc_escalated") *out = ix->tc_escalate;
-    else if (k == "tc_kind") *out = tc_flat_kind(ix);
+    else if (k == "tc_kind") *out = ix->is_ivf ? tc_ivf_kind(ix) : tc_flat_kind(ix);
     else if (k == "uncertified") {
         // queries of the last tensor-path call whose pre-selection margin could not be certified (see rerank_kernel)
         *out = 0;

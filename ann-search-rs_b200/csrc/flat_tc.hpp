@@ -25,6 +25,7 @@ float tc_cert_eps(const annb_index* ix, int kind, uint32_t kp_elems, uint32_t te
 int tc_ivf_prepare(annb_index* ix);
 void tc_ivf_destroy(annb_index* ix);
 bool tc_ivf_supported(const annb_index* ix, int qt, uint32_t k_eff);
+int tc_ivf_kind(const annb_index* ix);    // operand form of the tensor scan: -1 none, 0 3xTF32, 1 bf16 terms, 2 int8, 3 3xFP16
 uint32_t tc_ivf_kprime(const annb_index* ix, uint32_t k_eff);   // candidates kept per (query, rank, half tile)
 int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t nq, uint32_t k_eff, uint32_t k_out, uint32_t probe_pitch,
                 const uint32_t* d_pair_off, const uint32_t* d_task_off, const void* d_pairs, uint32_t* d_task_counter, uint64_t max_tasks,

@@ -550,6 +550,8 @@ int tc_ivf_debug_fetch(annb_index* ix, float* host_out) {
     return ANNB_OK;
 }
 
+int tc_ivf_kind(const annb_index* ix) { return ix->tc_ivf ? ix->tc_ivf->kind : -1; }
+
 bool tc_ivf_supported(const annb_index* ix, int qt, uint32_t k_eff) {
     if (ix->tc_ivf == nullptr || k_eff > 24) return false;
     return ix->dtype == ANNB_SQ8 ? qt == QT_I8 : qt == QT_F32;

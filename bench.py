@@ -643,15 +643,20 @@ def bench_ivf_set(c, n, dim, nq, k, nlist, entries, tf32_peak):
                    "note": "a list tile loaded once serves up to 128 queries of the batch, so the per-query (algorithmic) byte rate exceeds the HBM peak by design; "
                            "dram_gbs_from_traffic is what the kernel really moved (ncu), when a capture of this workload is committed"}
             if last_path == 2:
+                try:
+                    ivf_kind = index.get_stat("tc_kind")
+                except Exception:
+                    ivf_kind = 0
                 roofline = tensor_roofline(c, dtype, 2.0 * scanned_local * dim, r["dom_s"], "ivf grouped list scan + top-k' select (ivf_tc_kernel)", tf32_peak,
-                                           bf16_terms=3)
+                                           bf16_terms=3, f32_kind=ivf_kind)
                 roofline["algorithmic_flops_per_launch"] = 2.0 * scanned_local * dim
                 roofline["executed"]["note"] = "padded (list x 128-query group) tiles execute more MMA work than the algorithmic count"
                 tiles = index.get_stat("tc_scan_tiles") if (c.world == 1 and not c.single) else 0
                 if tiles and r["dom_s"]:
                     # what the tensor pipe really executed: every task multiplies whole 128-row tiles of its list by a 128-row query group
                     # (groups hold fewer than 128 queries at this batch size), K padded to the 128-byte slab, all MMA terms
-                    kp = -(-dim // {"f32": 32, "bf16": 64, "sq8": 128}[dtype]) * {"f32": 32, "bf16": 64, "sq8": 128}[dtype]
+                    slab = {"f32": 64 if ivf_kind == 3 else 32, "bf16": 64, "sq8": 128}[dtype]
+                    kp = -(-dim // slab) * slab
                     ex = roofline["executed"]
                     padded = tiles * 128.0 * 128.0 * kp * 2.0 * ex["mma_terms_per_element"]
                     ex["padded"] = {"tiles_per_launch": int(tiles), "tflops": padded / r["dom_s"] / 1e12,
@@ -675,7 +680,7 @@ def bench_ivf_set(c, n, dim, nq, k, nlist, entries, tf32_peak):
                     roofline["hbm_view"]["frac_of_hbm_peak"] = c.traffic[key]["dram_bytes"] / r["dom_s"] / 1e9 / c.peaks["hbm_gbs"]
             entry = {"metric": f"QPS ivf {dtype} euclidean nlist={nlist} nprobe={nprobe} k={k}", "value": r["qps"], "unit": "queries/s", "n_gpus": c.shards,
                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
-                     "dtype": {"f32": "f32 (3xTF32 select + f32 exact re-rank)", "bf16": "bf16 (f32 accumulate)", "sq8": "int8 (i32 accumulate)"}[dtype],
+                     "dtype": {"f32": "f32 (3xFP16 / 3xTF32 split-precision select + f32 exact re-rank)", "bf16": "bf16 (f32 accumulate)", "sq8": "int8 (i32 accumulate)"}[dtype],
                      "config": {"workload": f"IVF {dtype} euclidean, {n}x{dim} {kind} synthetic, nlist={nlist}, nprobe={nprobe}, {nq}-query batch, k={k}",
                                 "sharding": (f"inverted lists over {c.shards} GPUs, " +
                                              ("one process, peer copies" if c.single else "one process per GPU, probe exchange + one NCCL all-gather; device loop: verdict of step i read after step i+1 is enqueued"))
