@@ -867,37 +867,6 @@ struct MergeShardsParams {
     uint32_t* out_counts;
 };
 
-// Ascending bitonic sort of 32 * NPL keys held NPL per lane (element i = lane + 32 * j lives in key[j] of `lane`): strides below
-// 32 exchange by shuffle, larger strides inside the lane.
-template <int NPL>
-__device__ __forceinline__ void warp_bitonic_sort_regs(uint64_t (&key)[NPL], uint32_t lane) {
-#pragma unroll
-    for (int size = 2; size <= 32 * NPL; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride >= 32) {
-                const int js = stride >> 5;
-#pragma unroll
-                for (int j = 0; j < NPL; j++) {
-                    if ((j & js) == 0) {
-                        const bool up = ((static_cast<int>(lane) + 32 * j) & size) == 0;
-                        const uint64_t a = key[j], b = key[j | js];
-                        if ((a > b) == up) { key[j] = b; key[j | js] = a; }
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < NPL; j++) {
-                    const bool up = ((static_cast<int>(lane) + 32 * j) & size) == 0;
-                    const uint64_t other = __shfl_xor_sync(0xFFFFFFFFu, key[j], stride);
-                    const bool lower = (lane & static_cast<uint32_t>(stride)) == 0;
-                    key[j] = (lower == up) ? (key[j] < other ? key[j] : other) : (key[j] < other ? other : key[j]);
-                }
-            }
-        }
-    }
-}
-
 // Small merges (parts * k <= 128, e.g. 8 shards x k = 10 or 15): one warp per query sorts the (distance, slot) keys of all shards
 // in registers -- slot = shard * k + position, so the key order IS (distance, shard, position) -- and emits the first k.  The
 // binary-search variant below walks ~50 dependent loads per entry; this one is one load round trip and ~500 register ops.

@@ -570,9 +570,22 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         const uint32_t n = s_n;
         n_cand = n;
         const uint32_t nsort2 = min(nsort, next_pow2(max(n, 64u)));
+        if (nsort2 <= 128u) {
+            // the usual case (a few dozen candidates): one warp sorts them in registers -- no block barrier per bitonic stage
+            if (threadIdx.x < 32) {
+                uint64_t kreg[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) { const uint32_t i = threadIdx.x + 32u * j; kreg[j] = i < n ? keys[i] : KEY_SENTINEL; }
+                warp_bitonic_sort_regs<4>(kreg, threadIdx.x);
+#pragma unroll
+                for (int j = 0; j < 4; j++) { const uint32_t i = threadIdx.x + 32u * j; if (i < nsort2) keys[i] = kreg[j]; }
+            }
+            __syncthreads();
+        } else {
         for (uint32_t i = n + threadIdx.x; i < nsort2; i += blockDim.x) keys[i] = KEY_SENTINEL;
         __syncthreads();
         bitonic_sort_keys<true>(keys, nsort2, threadIdx.x, blockDim.x);
+        }
     } else {
         for (uint32_t i = threadIdx.x; i < nsort; i += blockDim.x) keys[i] = (i < total) ? src[i] : KEY_SENTINEL;
         __syncthreads();
@@ -774,7 +787,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     if (!direct) {
     exact_range(p.kp);
     __syncthreads();
-    if (threadIdx.x < 32) bitonic_sort_keys<false>(exact, 64, threadIdx.x, 32);
+    if (threadIdx.x < 32) { uint64_t er[2] = {exact[threadIdx.x], exact[threadIdx.x + 32]}; warp_bitonic_sort_regs<2>(er, threadIdx.x); exact[threadIdx.x] = er[0]; exact[threadIdx.x + 32] = er[1]; }
     __syncthreads();
     // Shard mode (out_bound != nullptr): the certificate is not decided here.  The kernel reports the bound below which
     // this shard's un-re-ranked rows cannot lie; the caller tests it against the k-th distance of the MERGED result
@@ -797,7 +810,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
     if (s_extend) {
         exact_range(min(n_cand, 64u));
         __syncthreads();
-        if (threadIdx.x < 32) bitonic_sort_keys<false>(exact, 64, threadIdx.x, 32);
+        if (threadIdx.x < 32) { uint64_t er[2] = {exact[threadIdx.x], exact[threadIdx.x + 32]}; warp_bitonic_sort_regs<2>(er, threadIdx.x); exact[threadIdx.x] = er[0]; exact[threadIdx.x + 32] = er[1]; }
         __syncthreads();
         if (threadIdx.x == 0) {
             const uint64_t d_key = exact[p.k_eff - 1];
