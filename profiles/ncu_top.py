@@ -13,7 +13,7 @@ want = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active_realtime.avg.pc
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_subpipe_imma_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_tensor.sum",
         "sm__ops_path_tensor_op_utchmma_src_tf32_dst_fp32.sum", "sm__ops_path_tensor_src_tf32_dst_fp32.sum", "sm__ops_path_tensor_src_int8.sum",
-        "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes.sum.per_second"]
+        "sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32.sum", "sm__ops_path_tensor_src_fp16_dst_fp32.sum", "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes.sum.per_second"]
 print("kernel:", vals[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?")
 for h, u, v in zip(hdr, units, vals):
     if h in want:
