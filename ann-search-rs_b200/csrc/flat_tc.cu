@@ -822,6 +822,7 @@ int tc_flat_prepare(annb_index* ix) {
 
 void tc_destroy(annb_index* ix) {
     if (!ix->tc) return;
+    ix->device_bytes -= std::min<uint64_t>(ix->device_bytes, ix->tc->bytes);
     cudaFree(ix->tc->d_x);
     cudaFree(ix->tc->d_aux);
     cudaFree(ix->tc->d_aux2);

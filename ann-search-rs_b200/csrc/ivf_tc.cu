@@ -518,6 +518,7 @@ int tc_ivf_prepare(annb_index* ix) {
 
 void tc_ivf_destroy(annb_index* ix) {
     if (!ix->tc_ivf) return;
+    ix->device_bytes -= std::min<uint64_t>(ix->device_bytes, ix->tc_ivf->bytes);
     cudaFree(ix->tc_ivf->d_x);
     cudaFree(ix->tc_ivf->d_aux);
     cudaFree(ix->tc_ivf->d_aux2);

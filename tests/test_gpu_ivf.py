@@ -554,3 +554,25 @@ def test_centroid_tables_above_16384_cells(gpu):
         got = g.query_batch(q, 10, nprobe=nprobe)
         ref = o.ivf_search(c, q, 10, nprobe=nprobe)
         _check("f32", got, ref[:3], f"nlist {nlist} nprobe {nprobe}")
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_ivf_f32_operand_forms_agree(gpu, metric):
+    """The f32 tensor scan with 3xFP16 (default: pre-split fp16 hi / lo copy of the lists, rows scaled by powers of two) and with
+    3xTF32 (in-kernel split of the raw rows) returns the oracle's rows; rows spanning many decades of norm."""
+    rng = np.random.default_rng(73)
+    base = datagen.correlated(40_000, 64, seed=73)
+    data = np.ascontiguousarray(base * (np.float32(10.0) ** rng.integers(-4, 5, base.shape[0]).astype(np.float32))[:, None], dtype=np.float32)
+    c = o.build_ivf(data, MET[metric][1], nlist=64, kmeans_iters=3)
+    g = _gpu_from_oracle(c)
+    g.set_option("path", annb200.PATH_TENSOR)
+    q = datagen.subsample_with_noise(data, 600, seed=73)
+    ref = o.ivf_search(c, q, 10, nprobe=8)
+    assert g.get_stat("tc_kind") == 3
+    bytes_fp16 = g.info().device_bytes
+    _check("f32", g.query_batch(q, 10, nprobe=8), ref[:3], f"ivf 3xFP16 {metric}")
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
+    g.set_option("tc_f32_fp16", 0)
+    assert g.get_stat("tc_kind") == 0 and g.info().device_bytes < bytes_fp16      # the fp16 copy of the lists is gone
+    _check("f32", g.query_batch(q, 10, nprobe=8), ref[:3], f"ivf 3xTF32 {metric}")
+    assert g.get_stat("last_path") == annb200.PATH_TENSOR
