@@ -571,7 +571,9 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         n_cand = n;
         const uint32_t nsort2 = min(nsort, next_pow2(max(n, 64u)));
         if (nsort2 <= 128u) {
-            // the usual case (a few dozen candidates): one warp sorts them in registers -- no block barrier per bitonic stage
+            // a few dozen candidates (IVF): one warp sorts them in registers -- no block barrier per bitonic stage.  (Flat searches
+            // leave ~200 keys below the smallest list threshold; a single warp sorting 256 keys in registers was measured slower than
+            // the block-wide sort: 0.201 against 0.186 ms per 10k queries.)
             if (threadIdx.x < 32) {
                 uint64_t kreg[4];
 #pragma unroll
