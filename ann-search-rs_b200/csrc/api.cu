@@ -1841,6 +1841,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "ivf_tc_coarse") ix->opt_ivf_tc_coarse = static_cast<int>(value);
     else if (k == "ivf_stream") ix->opt_ivf_stream = static_cast<int>(value);
     else if (k == "ivf_coarse_stage") ix->opt_ivf_coarse_stage = static_cast<int>(value);
+    else if (k == "ivf_coarse_gm") ix->opt_ivf_coarse_gm = static_cast<int>(value);
     else if (k == "async_dev") ix->opt_async_dev = static_cast<int>(value);
     else if (k == "time_kernels") { ix->opt_time_kernels = static_cast<int>(value); ix->timed_ms_total = 0.0; ix->timed_launches = 0; }
     else return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown option " + k);

@@ -335,6 +335,11 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                         float4* dst = reinterpret_cast<float4*>(p.dense + (static_cast<uint64_t>(q0) + row_in_tile) * p.dense_ld + row0 + c * NV);
 #pragma unroll
                         for (int j = 0; j < NV / 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        if (p.dense_gm != nullptr) {   // group minima (pad columns are +inf / NaN and never lower a minimum)
+                            float4* gdst = reinterpret_cast<float4*>(p.dense_gm + (static_cast<uint64_t>(q0) + row_in_tile) * (p.dense_ld >> 3) + ((row0 + c * NV) >> 3));
+#pragma unroll
+                            for (int j = 0; j < NG / 4; j++) gdst[j] = make_float4(gm[4 * j], gm[4 * j + 1], gm[4 * j + 2], gm[4 * j + 3]);
+                        }
                     }
                 }
                 float m = INFINITY;
@@ -384,6 +389,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 struct CoarseSelectParams {
     const float* dense;         // [nq][dense_ld] approximate selection values
     uint32_t dense_ld;
+    const float* gmin;          // coarse_select_gm_kernel: [nq][dense_ld / 8] minima of the aligned groups of 8 values
+    uint32_t glimit;            // ... its radix select stops once at most this many groups lie at or below the threshold
     uint64_t nq;
     uint32_t nlist, pitch, cmax;   // cmax: candidate capacity, a power of two >= pitch
     uint32_t staged_words;         // round_up(nlist, 4) when the row of values is kept in shared memory, 0 otherwise
@@ -400,24 +407,85 @@ struct CoarseSelectParams {
 __host__ __device__ inline size_t coarse_select_warp_bytes(uint32_t cmax, uint32_t staged_words) {
     return static_cast<size_t>(cmax) * 8 + 256 * 4 + static_cast<size_t>(cmax) * 4 + static_cast<size_t>(staged_words) * 4;   // keys | histogram | candidate cells | staged row
 }
+// coarse_select_gm_kernel: keys | candidate cells | area shared by (histogram + group minima) and (8 staged centroid rows + query row).
+// Staged rows sit 8 (mod 32) words apart: the 8-byte reads of a half warp (4 rows x 4 lanes) fall into distinct banks.
+__host__ __device__ inline uint32_t coarse_stage_row_words(uint32_t c_ld) { return ((c_ld + 31u) & ~31u) + 8u; }
+__host__ __device__ inline size_t coarse_stage_bytes(uint32_t c_ld, uint32_t dim) { return 8ull * coarse_stage_row_words(c_ld) * 4 + ((dim * 4ull + 15) & ~15ull); }
+__host__ __device__ inline size_t coarse_gm_warp_bytes(uint32_t cmax, uint32_t ngrp, uint32_t c_ld, uint32_t dim) {
+    const size_t sel = 256 * 4 + static_cast<size_t>(ngrp) * 4, dist = coarse_stage_bytes(c_ld, dim);
+    return static_cast<size_t>(cmax) * 12 + ((sel > dist ? sel : dist) + 15) / 16 * 16;
+}
 
-template <int MET>
-__global__ void __launch_bounds__(256) coarse_select_kernel(CoarseSelectParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint64_t q = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
-    if (q >= p.nq) return;   // warps are independent: no block-wide barrier below
-    uint8_t* base = smem + warp * coarse_select_warp_bytes(p.cmax, p.staged_words);
-    uint64_t* keys = reinterpret_cast<uint64_t*>(base);                  // [cmax]
-    uint32_t* hist = reinterpret_cast<uint32_t*>(keys + p.cmax);         // [256]
-    uint32_t* cand = hist + 256;                                          // [cmax]
-    uint4* staged = reinterpret_cast<uint4*>(cand + p.cmax);              // [staged_words / 4] ordered images of the row (16-byte aligned: cmax is a multiple of 4)
-    // The row of values is read from global memory once (coalesced 128-bit loads) and kept in shared memory as ordered
-    // integer images; the select's passes then run at shared-memory speed.  Very long rows (staged_words == 0) are
-    // re-read from L2 by every pass instead.  dense_ld is a multiple of 128.
+// Radix select over order-preserving integer images, one warp: a threshold thr such that the valid values at or below it
+// number at least `need` and -- as soon as a digit boundary allows -- at most `limit`.  Most significant digit first, starting
+// at the first bit in which the values differ (the common high bits -- sign, exponent -- would put every value into one
+// histogram bin); it stops as soon as the values at or below the chosen bin fit `limit` (the bin's upper edge is the
+// threshold) or no bits are left (ties: the count may then exceed `limit`, the caller checks).
+// fetch(i4, u): images 4 i4 .. 4 i4 + 3; values at positions >= nvalid are ignored.
+template <class Fetch>
+__device__ __forceinline__ uint32_t coarse_radix_threshold(Fetch fetch, uint32_t n4, uint32_t nvalid, uint32_t need, uint32_t limit, uint32_t umin,
+                                                           uint32_t umax, uint32_t* hist, uint32_t lane) {
+    uint32_t rem = 32u - __clz(umin ^ umax);          // unresolved low bits (0: all values equal)
+    uint32_t prefix = rem >= 32u ? 0u : (umin >> rem) << rem;
+    uint32_t below = 0;
+    uint32_t thr = prefix;                             // rem == 0
+    while (rem > 0) {
+        const uint32_t w = min(8u, rem), sh = rem - w, dmask = (1u << w) - 1u;
+        const uint32_t hmask = rem >= 32u ? 0u : ~0u << rem;
+        for (uint32_t b = lane; b < 256; b += 32) hist[b] = 0;
+        __syncwarp();
+        for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
+            uint32_t u[4];
+            fetch(i4, u);
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                if (4 * i4 + e < nvalid && (u[e] & hmask) == prefix) atomicAdd(hist + ((u[e] >> sh) & dmask), 1u);
+        }
+        __syncwarp();
+        uint32_t h[8], local = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { h[j] = hist[8 * lane + j]; local += h[j]; }
+        uint32_t incl = local;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (lane >= static_cast<uint32_t>(off)) incl += t;
+        }
+        const uint32_t excl = incl - local;
+        const bool mine = excl < need && need <= incl;
+        const int owner = __ffs(__ballot_sync(0xFFFFFFFFu, mine)) - 1;
+        uint32_t bin = 0, before = 0, upto = 0;
+        if (mine) {
+            uint32_t c = excl;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (need > c && need <= c + h[j]) { bin = 8 * lane + j; before = c; upto = c + h[j]; }
+                c += h[j];
+            }
+        }
+        bin = __shfl_sync(0xFFFFFFFFu, bin, owner);
+        before = __shfl_sync(0xFFFFFFFFu, before, owner);
+        upto = __shfl_sync(0xFFFFFFFFu, upto, owner);
+        __syncwarp();
+        if (below + upto <= limit || sh == 0) {      // few enough values at or below this bin (or nothing left to refine)
+            thr = prefix | (bin << sh) | ((sh ? (1u << sh) : 1u) - 1u);
+            break;
+        }
+        below += before;
+        need -= before;
+        prefix |= bin << sh;
+        rem = sh;
+    }
+    return thr;
+}
+
+// Threshold and candidates from the full row of values (read from L2 by every pass): every cell whose value is <= thr.
+// Returns the candidate count (cells beyond cmax are counted, not stored).
+__device__ __forceinline__ uint32_t coarse_candidates_full_row(const CoarseSelectParams& p, uint64_t q, uint32_t* hist, uint32_t* cand, uint4* staged,
+                                                               uint32_t lane, uint32_t& thr) {
     const float4* src4 = reinterpret_cast<const float4*>(p.dense + q * p.dense_ld);
     const uint32_t n4 = (p.nlist + 3) >> 2;
-    const bool use_smem = p.staged_words != 0;
+    const bool use_smem = staged != nullptr;
     auto ord = [&](float4 x, uint32_t i4, uint32_t u[4]) {   // ordered images; columns past nlist never qualify
         u[0] = f32_to_ordered(x.x); u[1] = f32_to_ordered(x.y); u[2] = f32_to_ordered(x.z); u[3] = f32_to_ordered(x.w);
 #pragma unroll
@@ -427,81 +495,31 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(CoarseSelectParams p
         if (use_smem) { const uint4 w = staged[i4]; u[0] = w.x; u[1] = w.y; u[2] = w.z; u[3] = w.w; }
         else ord(__ldg(src4 + i4), i4, u);
     };
-    uint32_t umin = 0xFFFFFFFFu, umax = 0u;
-    for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
-        uint32_t u[4];
-        ord(__ldg(src4 + i4), i4, u);
-        if (use_smem) staged[i4] = make_uint4(u[0], u[1], u[2], u[3]);
+    thr = 0xFFFFFFFFu;
+    if (p.pitch < p.nlist) {
+        uint32_t umin = 0xFFFFFFFFu, umax = 0u;
+        for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
+            uint32_t u[4];
+            ord(__ldg(src4 + i4), i4, u);
+            if (use_smem) staged[i4] = make_uint4(u[0], u[1], u[2], u[3]);
 #pragma unroll
-        for (int e = 0; e < 4; e++) if (4 * i4 + e < p.nlist) { umin = min(umin, u[e]); umax = max(umax, u[e]); }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        umin = min(umin, __shfl_xor_sync(0xFFFFFFFFu, umin, off));
-        umax = max(umax, __shfl_xor_sync(0xFFFFFFFFu, umax, off));
-    }
-
-    // 1. threshold: radix select, most significant digit first, starting at the first bit in which the row's values
-    //    differ (the common high bits -- sign, exponent -- would put every value into one histogram bin).  It stops as
-    //    soon as the cells at or below the chosen bin number between pitch and cmax: all of them become candidates and
-    //    the bin's upper edge is the threshold.
-    uint32_t thr = 0xFFFFFFFFu;
-    const bool partial = p.pitch < p.nlist;
-    if (partial) {
-        uint32_t rem = 32u - __clz(umin ^ umax);          // unresolved low bits (0: all values equal)
-        uint32_t prefix = rem >= 32u ? 0u : (umin >> rem) << rem;
-        uint32_t need = p.pitch, below = 0;
-        thr = prefix;                                      // rem == 0
-        while (rem > 0) {
-            const uint32_t w = min(8u, rem), sh = rem - w, dmask = (1u << w) - 1u;
-            const uint32_t hmask = rem >= 32u ? 0u : ~0u << rem;
-            for (uint32_t b = lane; b < 256; b += 32) hist[b] = 0;
-            __syncwarp();
-            for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
-                uint32_t u[4];
-                fetch(i4, u);
-#pragma unroll
-                for (int e = 0; e < 4; e++)
-                    if (4 * i4 + e < p.nlist && (u[e] & hmask) == prefix) atomicAdd(hist + ((u[e] >> sh) & dmask), 1u);
-            }
-            __syncwarp();
-            uint32_t h[8], local = 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) { h[j] = hist[8 * lane + j]; local += h[j]; }
-            uint32_t incl = local;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-                if (lane >= static_cast<uint32_t>(off)) incl += t;
-            }
-            const uint32_t excl = incl - local;
-            const bool mine = excl < need && need <= incl;
-            const int owner = __ffs(__ballot_sync(0xFFFFFFFFu, mine)) - 1;
-            uint32_t bin = 0, before = 0, upto = 0;
-            if (mine) {
-                uint32_t c = excl;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    if (need > c && need <= c + h[j]) { bin = 8 * lane + j; before = c; upto = c + h[j]; }
-                    c += h[j];
-                }
-            }
-            bin = __shfl_sync(0xFFFFFFFFu, bin, owner);
-            before = __shfl_sync(0xFFFFFFFFu, before, owner);
-            upto = __shfl_sync(0xFFFFFFFFu, upto, owner);
-            __syncwarp();
-            if (below + upto <= p.cmax || sh == 0) {      // few enough cells at or below this bin (or nothing left to refine)
-                thr = prefix | (bin << sh) | ((sh ? (1u << sh) : 1u) - 1u);
-                break;
-            }
-            below += before;
-            need -= before;
-            prefix |= bin << sh;
-            rem = sh;
+            for (int e = 0; e < 4; e++) if (4 * i4 + e < p.nlist) { umin = min(umin, u[e]); umax = max(umax, u[e]); }
         }
+        __syncwarp();
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            umin = min(umin, __shfl_xor_sync(0xFFFFFFFFu, umin, off));
+            umax = max(umax, __shfl_xor_sync(0xFFFFFFFFu, umax, off));
+        }
+        thr = coarse_radix_threshold(fetch, n4, p.nlist, p.pitch, p.cmax, umin, umax, hist, lane);
+    } else if (use_smem) {
+        for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
+            uint32_t u[4];
+            ord(__ldg(src4 + i4), i4, u);
+            staged[i4] = make_uint4(u[0], u[1], u[2], u[3]);
+        }
+        __syncwarp();
     }
-    // 2. candidates: every cell with value <= thr
     uint32_t count = 0;
     for (uint32_t i0 = 0; i0 < n4; i0 += 32) {
         const uint32_t i4 = i0 + lane;
@@ -510,8 +528,7 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(CoarseSelectParams p
         uint32_t mine = 0;
 #pragma unroll
         for (int e = 0; e < 4; e++) mine += (4 * i4 + e < p.nlist && u[e] <= thr) ? 1u : 0u;
-        // exclusive prefix of the per-lane hit counts
-        uint32_t incl = mine;
+        uint32_t incl = mine;   // inclusive prefix of the per-lane hit counts
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
@@ -524,24 +541,95 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(CoarseSelectParams p
         count += __shfl_sync(0xFFFFFFFFu, incl, 31);
     }
     __syncwarp();
+    return count;
+}
+
+// Steps 3 and 4 of the centroid select: exact distances of the candidates (reference arithmetic), (distance, cell) order,
+// certified prefix.  thr: every cell that is NOT a candidate has an approximate value above it.
+// stage != nullptr: a warp-private shared-memory area of coarse_stage_bytes(): the candidates' centroid rows are brought in eight
+// at a time with coalesced 16-byte cp.async copies (all of a batch's loads in flight together), and four lanes share one
+// candidate: lane t of a group owns SIMD lanes 2t and 2t + 1 of the reference's 8-lane accumulation (src/utils/dist.rs:306-330,
+// 587-609), walks the chunks in order with the same rounding steps, and the group folds with the reference's horizontal-add
+// tree by shuffles -- the bits of one thread walking the row (refdist.cuh), a ninth of the dependent L2 round trips.
+template <int MET>
+__device__ __forceinline__ void coarse_emit_ranked(const CoarseSelectParams& p, uint64_t q, uint32_t thr, uint32_t count, uint64_t* keys,
+                                                   const uint32_t* cand, uint32_t lane, uint8_t* stage = nullptr) {
     uint64_t* out = p.ranked + q * p.pitch;
     if (count > p.cmax) {   // a huge tie class: leave the query to the exact ranking
         for (uint32_t j = lane; j < p.pitch; j += 32) out[j] = KEY_SENTINEL;
         return;
     }
-    // 3. exact distances of the candidates, reference arithmetic
     const uint8_t* qrow = reinterpret_cast<const uint8_t*>(p.queries + q * p.q_ld);
+    if (stage != nullptr) {
+        const uint32_t rs = coarse_stage_row_words(p.c_ld) * 4;
+        float* qbuf = reinterpret_cast<float*>(stage + 8 * rs);
+        __syncwarp();                                     // the selection is done with this area (histogram, group minima)
+        for (uint32_t e = lane; e < p.dim; e += 32) qbuf[e] = reinterpret_cast<const float*>(qrow)[e];
+        __syncwarp();
+        qrow = reinterpret_cast<const uint8_t*>(qbuf);
+    }
     float qn = 1.0f;
     if (MET == MET_COS) {
         if (lane == 0) qn = seq_norm<4>(qrow, p.dim);
         qn = __shfl_sync(0xFFFFFFFFu, qn, 0);
     }
+    if (stage != nullptr) {
+        const uint32_t rs = coarse_stage_row_words(p.c_ld) * 4, row_bytes = p.c_ld * 4;
+        const uint32_t t = lane & 3u, r = lane >> 2;
+        const uint32_t chunks = p.dim >> 3;
+        for (uint32_t base = 0; base < count; base += 8) {
+            const uint32_t nb = min(8u, count - base);
+            for (uint32_t i = 0; i < nb; i++) {
+                const uint8_t* src = reinterpret_cast<const uint8_t*>(p.centroids + static_cast<uint64_t>(cand[base + i]) * p.c_ld);
+                for (uint32_t b = lane * 16; b < row_bytes; b += 512) cp_async16(stage + i * rs + b, src + b);
+            }
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncwarp();
+            const float* x = reinterpret_cast<const float*>(stage + r * rs);
+            const float* y = reinterpret_cast<const float*>(qrow);
+            float a0 = 0.0f, a1 = 0.0f;
+            if (r < nb) {
+#pragma unroll 4
+                for (uint32_t c = 0; c < chunks; c++) {
+                    const float2 xv = *reinterpret_cast<const float2*>(x + 8 * c + 2 * t), yv = *reinterpret_cast<const float2*>(y + 8 * c + 2 * t);
+                    if (MET == MET_L2) {
+                        const float d0 = __fsub_rn(xv.x, yv.x), d1 = __fsub_rn(xv.y, yv.y);
+                        a0 = __fadd_rn(a0, __fmul_rn(d0, d0));
+                        a1 = __fadd_rn(a1, __fmul_rn(d1, d1));
+                    } else {
+                        a0 = __fadd_rn(a0, __fmul_rn(xv.x, yv.x));
+                        a1 = __fadd_rn(a1, __fmul_rn(xv.y, yv.y));
+                    }
+                }
+            }
+            // wide::f32x8::reduce_add: s_j = a_j + a_(j+4); (s0 + s2) + (s1 + s3)
+            const float s0 = __fadd_rn(a0, __shfl_down_sync(0xFFFFFFFFu, a0, 2, 4)), s1 = __fadd_rn(a1, __shfl_down_sync(0xFFFFFFFFu, a1, 2, 4));   // lane 0: s0, s1; lane 1: s2, s3
+            const float u0 = __fadd_rn(s0, __shfl_down_sync(0xFFFFFFFFu, s0, 1, 4)), u1 = __fadd_rn(s1, __shfl_down_sync(0xFFFFFFFFu, s1, 1, 4));
+            if (t == 0 && r < nb) {
+                float sum = __fadd_rn(u0, u1);
+                for (uint32_t e = chunks * 8; e < p.dim; e++) {   // scalar tail: `sum += d * d` (not fused)
+                    if (MET == MET_L2) {
+                        const float d = __fsub_rn(x[e], y[e]);
+                        sum = __fadd_rn(sum, __fmul_rn(d, d));
+                    } else {
+                        sum = __fadd_rn(sum, __fmul_rn(x[e], y[e]));
+                    }
+                }
+                const uint32_t c = cand[base + r];
+                const float cn = (MET == MET_COS) ? p.centroid_norms[c] : 1.0f;
+                keys[base + r] = make_key(finish_fp<MET>(sum, qn, cn), c);
+            }
+            __syncwarp();                                 // the rows are consumed before the next batch lands on them
+        }
+        for (uint32_t j = count + lane; j < p.cmax; j += 32) keys[j] = KEY_SENTINEL;
+    } else
     for (uint32_t j = lane; j < p.cmax; j += 32) {
         uint64_t key = KEY_SENTINEL;
         if (j < count) {
             const uint32_t c = cand[j];
             float raw[1];
-            accumulate_fp<4, 4, MET == MET_L2, 1>(reinterpret_cast<const uint8_t*>(p.centroids + static_cast<uint64_t>(c) * p.c_ld), qrow, p.q_ld * 4, p.dim, raw);
+            accumulate_fp<4, 4, MET == MET_L2, 1, true>(reinterpret_cast<const uint8_t*>(p.centroids + static_cast<uint64_t>(c) * p.c_ld), qrow, p.q_ld * 4, p.dim, raw);
             const float cn = (MET == MET_COS) ? p.centroid_norms[c] : 1.0f;
             key = make_key(finish_fp<MET>(raw[0], qn, cn), c);
         }
@@ -549,9 +637,8 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(CoarseSelectParams p
     }
     __syncwarp();
     bitonic_sort_keys<false>(keys, p.cmax, lane, 32);
-    // 4. certified prefix
     float bound = INFINITY;
-    if (partial) {
+    if (p.pitch < p.nlist) {
         double qn2 = 0.0;   // f64: the value -> distance map must not add rounding of its own
         for (uint32_t e = lane; e < p.dim; e += 32) {
             const double x = reinterpret_cast<const float*>(qrow)[e];
@@ -576,6 +663,109 @@ __global__ void __launch_bounds__(256) coarse_select_kernel(CoarseSelectParams p
         const uint64_t key = keys[j];
         out[j] = (key_idx(key) != IDX_INVALID && key_dist(key) < bound) ? key : KEY_SENTINEL;
     }
+}
+
+template <int MET>
+__global__ void __launch_bounds__(256) coarse_select_kernel(CoarseSelectParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t q = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    if (q >= p.nq) return;   // warps are independent: no block-wide barrier below
+    uint8_t* base = smem + warp * coarse_select_warp_bytes(p.cmax, p.staged_words);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(base);                  // [cmax]
+    uint32_t* hist = reinterpret_cast<uint32_t*>(keys + p.cmax);         // [256]
+    uint32_t* cand = hist + 256;                                          // [cmax]
+    uint4* staged = reinterpret_cast<uint4*>(cand + p.cmax);              // [staged_words / 4] ordered images of the row (16-byte aligned: cmax is a multiple of 4)
+    // The row of values is either kept in shared memory as ordered integer images (one global pass, coalesced 128-bit loads) or
+    // re-read from L2 by every pass (staged_words == 0, the default: occupancy hides the dependent passes better than the
+    // staging saves).  dense_ld is a multiple of 128.
+    uint32_t thr;
+    const uint32_t count = coarse_candidates_full_row(p, q, hist, cand, p.staged_words ? staged : nullptr, lane, thr);
+    coarse_emit_ranked<MET>(p, q, thr, count, keys, cand, lane);
+}
+
+// The same select from the GROUP MINIMA the dense kernel's epilogue leaves behind (the minimum of every aligned group of 8
+// cells, [nq][dense_ld / 8]): the pitch-th smallest group minimum T bounds the pitch-th smallest value from above (pitch
+// distinct groups each hold a value <= T), and every cell with a value <= T lies in a group whose minimum is <= T.  So the
+// radix select runs over nlist / 8 minima kept in shared memory, and only the selected groups' 8 values each are read from the
+// dense matrix -- ~3 KB per query instead of ~5 passes over its 16 KB row at nlist 4096.  The candidate set is again "every
+// cell with a value <= thr", so the certificate of coarse_emit_ranked is unchanged.  A query whose selected groups hold more
+// than cmax cells at or below thr (cell ids that cluster in space) takes the full-row select instead.
+template <int MET>
+__global__ void __launch_bounds__(256) coarse_select_gm_kernel(CoarseSelectParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint64_t q = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + warp;
+    if (q >= p.nq) return;
+    uint8_t* base = smem + warp * coarse_gm_warp_bytes(p.cmax, p.dense_ld >> 3, p.c_ld, p.dim);
+    uint64_t* keys = reinterpret_cast<uint64_t*>(base);                  // [cmax]; first the selected group ids (uint32 view)
+    uint32_t* cand = reinterpret_cast<uint32_t*>(keys + p.cmax);         // [cmax]
+    uint32_t* hist = cand + p.cmax;                                       // [256]   (this area is reused for the staged centroid rows)
+    uint4* gst4 = reinterpret_cast<uint4*>(hist + 256);                   // [ngrp / 4] ordered images of the group minima
+    const uint32_t* gst = reinterpret_cast<const uint32_t*>(gst4);
+    uint32_t* glist = reinterpret_cast<uint32_t*>(keys);
+    const uint32_t ngrp = p.dense_ld >> 3, ngv = (p.nlist + 7) >> 3, n4 = (ngv + 3) >> 2;   // ngrp is a multiple of 16
+    const float4* g4 = reinterpret_cast<const float4*>(p.gmin + q * ngrp);
+    uint32_t umin = 0xFFFFFFFFu, umax = 0u;
+    for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
+        const float4 x = __ldg(g4 + i4);
+        uint32_t u[4] = {f32_to_ordered(x.x), f32_to_ordered(x.y), f32_to_ordered(x.z), f32_to_ordered(x.w)};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (4 * i4 + e < ngv) { umin = min(umin, u[e]); umax = max(umax, u[e]); }
+            else u[e] = 0xFFFFFFFFu;
+        }
+        gst4[i4] = make_uint4(u[0], u[1], u[2], u[3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        umin = min(umin, __shfl_xor_sync(0xFFFFFFFFu, umin, off));
+        umax = max(umax, __shfl_xor_sync(0xFFFFFFFFu, umax, off));
+    }
+    auto fetch = [&](uint32_t i4, uint32_t u[4]) { const uint4 w = gst4[i4]; u[0] = w.x; u[1] = w.y; u[2] = w.z; u[3] = w.w; };
+    uint32_t thr = coarse_radix_threshold(fetch, n4, ngv, p.pitch, p.glimit, umin, umax, hist, lane);
+    // selected groups, compacted (any order: the candidates are sorted by (distance, cell) later)
+    uint32_t n_sel = 0;
+    for (uint32_t i0 = 0; i0 < ngv; i0 += 32) {
+        const uint32_t g = i0 + lane;
+        const bool sel = g < ngv && gst[g] <= thr;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, sel);
+        const uint32_t pos = n_sel + __popc(m & ((1u << lane) - 1u));
+        if (sel && pos < 2 * p.cmax) glist[pos] = g;     // the keys area holds 2 cmax words
+        n_sel += __popc(m);
+    }
+    __syncwarp();
+    uint32_t count = n_sel <= 2 * p.cmax ? 0u : p.cmax + 1u;
+    if (count == 0) {
+        const float* row = p.dense + q * p.dense_ld;
+        for (uint32_t j0 = 0; j0 < n_sel; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            uint32_t mine = 0, hits = 0, g = 0;
+            if (j < n_sel) {
+                g = glist[j];
+                const float4 a = __ldg(reinterpret_cast<const float4*>(row + 8 * g)), b = __ldg(reinterpret_cast<const float4*>(row + 8 * g) + 1);
+                const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int e = 0; e < 8; e++)
+                    if (8 * g + e < p.nlist && f32_to_ordered(v[e]) <= thr) { hits |= 1u << e; mine++; }
+            }
+            uint32_t incl = mine;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                if (lane >= static_cast<uint32_t>(off)) incl += t;
+            }
+            uint32_t pos = count + incl - mine;
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+                if (hits & (1u << e)) { if (pos < p.cmax) cand[pos] = 8 * g + e; pos++; }
+            count += __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        __syncwarp();
+    }
+    if (count > p.cmax) count = coarse_candidates_full_row(p, q, hist, cand, nullptr, lane, thr);
+    coarse_emit_ranked<MET>(p, q, thr, count, keys, cand, lane, reinterpret_cast<uint8_t*>(hist));
 }
 
 static __global__ void fill_aux_kernel(float* __restrict__ aux, uint64_t n, uint64_t n_total, float value) {
@@ -675,7 +865,7 @@ struct TcState {
     float* d_aux = nullptr;   // [n_pad + BN]
     float* d_aux2 = nullptr;  // KIND_F16X3: [n_pad + BN] inverse operand scale of every row
     CUtensorMap tm_x;
-    DevBuf q_op, part, dbg, gtau, dbgc, dense, q_scale;
+    DevBuf q_op, part, dbg, gtau, dbgc, dense, dense_gm, q_scale;
     uint64_t bytes = 0;
 };
 
@@ -1138,6 +1328,7 @@ void tc_coarse_destroy(annb_index* ix) {
     cudaFree(ix->tc_coarse->d_aux);
     ix->tc_coarse->q_op.release();
     ix->tc_coarse->dense.release();
+    ix->tc_coarse->dense_gm.release();
     delete ix->tc_coarse;
     ix->tc_coarse = nullptr;
 }
@@ -1146,9 +1337,9 @@ bool tc_coarse_supported(const annb_index* ix) { return ix->tc_coarse != nullptr
 
 template <int MET>
 static int launch_coarse_select(const tc::CoarseSelectParams& c, cudaStream_t s) {
-    auto kern = tc::coarse_select_kernel<MET>;
-    const uint32_t warps = c.staged_words ? 4 : 8;
-    const size_t per_warp = tc::coarse_select_warp_bytes(c.cmax, c.staged_words);
+    auto kern = c.gmin ? tc::coarse_select_gm_kernel<MET> : tc::coarse_select_kernel<MET>;
+    const uint32_t warps = (c.staged_words && !c.gmin) ? 4 : 8;
+    const size_t per_warp = c.gmin ? tc::coarse_gm_warp_bytes(c.cmax, c.dense_ld >> 3, c.c_ld, c.dim) : tc::coarse_select_warp_bytes(c.cmax, c.staged_words);
     const size_t smem = per_warp * warps;
     ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<static_cast<uint32_t>((c.nq + warps - 1) / warps), warps * 32, smem, s>>>(c);
@@ -1180,6 +1371,21 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     p.nq = nq; p.n_rows = ix->nlist; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
     p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = 2; p.aux = st->d_aux;
     p.q_op = st->q_op.as<void>(); p.kp = kp; p.dense = st->dense.as<float>(); p.dense_ld = st->n_pad;
+    // Select from group minima (coarse_select_gm_kernel) when the selected groups are expected to hold well under cmax cells at
+    // or below the threshold: G groups carry about G (1 + 7 G / nlist) of them.
+    const uint32_t cmax = next_pow2(pitch + 1);
+    uint32_t glimit = 0;
+    if (ix->opt_ivf_coarse_gm && pitch < ix->nlist && st->n_pad / 8 <= 2048) {
+        auto expect = [&](uint32_t g) { return g * (1.0 + 7.0 * g / ix->nlist); };
+        if (expect(pitch) * 1.15 <= cmax) {
+            glimit = pitch;
+            while (glimit + 1 <= cmax && expect(glimit + 1) <= 0.9 * cmax) glimit++;
+        }
+    }
+    if (glimit) {
+        ANNB_TRY(st->dense_gm.ensure(nq * static_cast<uint64_t>(st->n_pad / 8) * 4));
+        p.dense_gm = st->dense_gm.as<float>();
+    }
     {
         dim3 grid(static_cast<uint32_t>(q_tiles), splits);
         if (ix->metric == ANNB_L2) {
@@ -1194,11 +1400,12 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
         ANNB_CUDA_CHECK(cudaGetLastError());
     }
     tc::CoarseSelectParams c{};
-    c.dense = st->dense.as<float>(); c.dense_ld = st->n_pad; c.nq = nq; c.nlist = ix->nlist; c.pitch = pitch; c.cmax = next_pow2(pitch + 1);
+    c.dense = st->dense.as<float>(); c.dense_ld = st->n_pad; c.nq = nq; c.nlist = ix->nlist; c.pitch = pitch; c.cmax = cmax;
     // Staging the row of values in shared memory (one global pass instead of ~5 L2 passes) was measured SLOWER at nlist 4096,
     // 10k queries: 0.41 ms against 0.27 ms per launch -- 16 KB per warp leaves 12 resident warps per SM where the L2 variant
     // keeps 64, and the select is a chain of dependent passes that only occupancy hides.  Kept behind option ivf_coarse_stage.
     c.staged_words = (ix->opt_ivf_coarse_stage && ix->nlist <= 8192) ? round_up(ix->nlist, 4u) : 0u;
+    if (glimit) { c.gmin = st->dense_gm.as<float>(); c.glimit = glimit; c.staged_words = st->n_pad / 8; }
     c.queries = d_route; c.q_ld = route_ld; c.centroids = ix->d_centroids; c.c_ld = ix->cent_ld; c.centroid_norms = ix->d_centroid_norms;
     c.dim = ix->dim; c.eps = tc_cert_eps(ix, tc::KIND_TF32X3, kp, 2, false); c.cnorm_max = ix->tc_cnorm_max; c.ranked = d_ranked;
     if (ix->metric == ANNB_L2) ANNB_TRY(launch_coarse_select<MET_L2>(c, s));

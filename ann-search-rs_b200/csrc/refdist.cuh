@@ -59,7 +59,9 @@ __device__ __forceinline__ float hsum_bf16path(const float a[8]) {
 // stored row against NQ queries held in shared memory.
 //   RELEM : bytes per row element (4 f32, 2 bf16);  QELEM : bytes per query element.
 //   FMA   : bf16 kernels of the reference use _mm256_fmadd_ps, f32 kernels do not.
-template <int RELEM, int QELEM, bool L2, int NQ>
+//   DEEP  : four chunks per loop trip with their row loads issued first, so that a latency-bound caller (one lane walking a row that sits in L2) keeps
+//           eight 128-bit row loads in flight instead of the compiler's two; the order of the arithmetic is unchanged.
+template <int RELEM, int QELEM, bool L2, int NQ, bool DEEP = false>
 __device__ __forceinline__ void accumulate_fp(const uint8_t* __restrict__ row, const uint8_t* __restrict__ q,
                                               uint32_t q_stride, int dim, float out[NQ]) {
     constexpr bool FMA = (RELEM == 2);
@@ -69,9 +71,7 @@ __device__ __forceinline__ void accumulate_fp(const uint8_t* __restrict__ row, c
 #pragma unroll
         for (int j = 0; j < 8; j++) acc[i][j] = 0.0f;
     const int chunks = dim >> 3;
-    for (int c = 0; c < chunks; c++) {
-        float x[8];
-        load8<RELEM>(row + c * 8 * RELEM, x);
+    auto chunk_x = [&](int c, const float x[8]) {
 #pragma unroll
         for (int i = 0; i < NQ; i++) {
             float y[8];
@@ -86,6 +86,25 @@ __device__ __forceinline__ void accumulate_fp(const uint8_t* __restrict__ row, c
                 }
             }
         }
+    };
+    auto chunk = [&](int c) {
+        float x[8];
+        load8<RELEM>(row + c * 8 * RELEM, x);
+        chunk_x(c, x);
+    };
+    if constexpr (DEEP) {
+        int c = 0;
+        for (; c + 4 <= chunks; c += 4) {
+            float x[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; u++) load8<RELEM>(row + (c + u) * 8 * RELEM, x[u]);   // the four chunks' row loads go out together ...
+            asm volatile("" ::: "memory");                                              // ... (compiler barrier: they are not sunk into the arithmetic)
+#pragma unroll
+            for (int u = 0; u < 4; u++) chunk_x(c + u, x[u]);
+        }
+        for (; c < chunks; c++) chunk(c);
+    } else {
+        for (int c = 0; c < chunks; c++) chunk(c);
     }
 #pragma unroll
     for (int i = 0; i < NQ; i++) {

@@ -51,6 +51,7 @@ struct Params {
     uint32_t* gtau;           // [nq_pad] shared pruning threshold per query (order-preserving image, atomicMin)
     float* dense;             // DENSE mode: the selection values themselves, [nq][dense_ld] (IVF centroid ranking)
     uint32_t dense_ld;
+    float* dense_gm;          // DENSE mode, optional: minima of every aligned group of 8 values, [nq][dense_ld / 8] (coarse_select_gm_kernel)
     float* dbg;               // optional: CTA (0,0) dumps v of its first tile [BM][BN]
     unsigned long long* dbg_cycles;  // optional: CTA (0,0) wait-cycle counters {total, prod_empty, mma_full, mma_tempty, epi_tfull, epi_slow}
 };

@@ -433,6 +433,35 @@ def test_concurrent_ivf_searches_on_one_handle(gpu):
 
 
 @pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_centroid_select_from_group_minima(gpu, metric):
+    """The tensor-core centroid ranking selects from the minima of aligned groups of 8 cells (coarse_select_gm_kernel) and falls
+    back to the full row of values when the selected groups hold more candidates than its buffer.  Two centroid tables, same
+    data: cell ids in random order (the group path serves every query) and cell ids that follow a curve through space (a
+    query's nearest cells are consecutive ids, every selected group is full of candidates, the full-row select takes over).
+    Both must give the exact ranking's probe sets (src/cpu/ivf.rs:349-365), and the old full-row kernel (option
+    `ivf_coarse_gm` = 0) the same again."""
+    rng = np.random.default_rng(77)
+    nlist, dim = 2048, 16
+    t = np.linspace(0.0, 40.0, nlist, dtype=np.float64)
+    curve = np.stack([np.cos(t * (1 + 0.1 * j)) * (1 + 0.05 * j) + 0.02 * t * (j % 3) for j in range(dim)], axis=1) + 3.0
+    cent_curve = (curve + 1e-3 * rng.standard_normal((nlist, dim))).astype(np.float32)
+    data = (cent_curve[rng.integers(0, nlist, 20000)] + 0.05 * rng.standard_normal((20000, dim))).astype(np.float32)
+    q = (cent_curve[rng.integers(0, nlist, 300)] + 0.05 * rng.standard_normal((300, dim))).astype(np.float32)
+    m_o = MET[metric][1]
+    for name, cent in (("curve order", cent_curve), ("random order", np.ascontiguousarray(cent_curve[rng.permutation(nlist)]))):
+        c = o.build_ivf(data, m_o, nlist=nlist, centroids=cent)
+        g = _gpu_from_oracle(c)
+        for k, nprobe in ((10, 8), (10, 32)):
+            ref = o.ivf_search(c, q, k, nprobe=nprobe)
+            for gm in (1, 0):
+                g.set_option("ivf_coarse_gm", gm)
+                got = g.query_batch(q, k, nprobe=nprobe)
+                assert g.get_stat("coarse_path") == 2, (name, nprobe, gm)
+                _check("f32", got, ref, f"{name} {metric} nprobe={nprobe} gm={gm}")
+                assert g.get_stat("probed_lists") == int(ref[3].sum())
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
 def test_device_lloyd_balanced_matches_restated_adjust_centers(gpu, metric):
     """KMeansTrainingParams::with_balancing (SURVEY 8f-1): adjust_centers needs no random numbers, so from identical inputs
     the device loop and the oracle's restatement must move the same centroids: one balanced iteration is compared closely
