@@ -1842,6 +1842,20 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "ivf_stream") ix->opt_ivf_stream = static_cast<int>(value);
     else if (k == "ivf_coarse_stage") ix->opt_ivf_coarse_stage = static_cast<int>(value);
     else if (k == "ivf_coarse_gm") ix->opt_ivf_coarse_gm = static_cast<int>(value);
+    else if (k == "ivf_coarse_fp16") {
+        // operand form of the tensor-core centroid ranking (1: 3xFP16, 0: 3xTF32), fixed when its state is built: rebuild on change
+        const int v = value != 0 ? 1 : 0;
+        if (v != ix->opt_ivf_coarse_fp16) {
+            ix->opt_ivf_coarse_fp16 = v;
+            if (ix->is_ivf && ix->tc_coarse != nullptr) {
+                DeviceGuard g(ix->device);
+                ANNB_CUDA_CHECK(cudaStreamSynchronize(ix->stream));
+                tc_coarse_destroy(ix);
+                ANNB_TRY(tc_coarse_prepare(ix));
+                ANNB_CUDA_CHECK(cudaStreamSynchronize(ix->stream));
+            }
+        }
+    }
     else if (k == "async_dev") ix->opt_async_dev = static_cast<int>(value);
     else if (k == "time_kernels") { ix->opt_time_kernels = static_cast<int>(value); ix->timed_ms_total = 0.0; ix->timed_launches = 0; }
     else return fail(ANNB_ERR_INVALID_ARGUMENT, "unknown option " + k);

@@ -636,7 +636,17 @@ __device__ __forceinline__ void coarse_emit_ranked(const CoarseSelectParams& p, 
         keys[j] = key;
     }
     __syncwarp();
-    bitonic_sort_keys<false>(keys, p.cmax, lane, 32);
+    if (p.cmax == 128u) {          // the usual capacity (prefixes of up to 127 ranks): sort in registers, shuffles instead of shared-memory passes
+        uint64_t kr[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) kr[j] = keys[lane + 32 * j];
+        warp_bitonic_sort_regs<4>(kr, lane);
+#pragma unroll
+        for (int j = 0; j < 4; j++) keys[lane + 32 * j] = kr[j];
+        __syncwarp();
+    } else {
+        bitonic_sort_keys<false>(keys, p.cmax, lane, 32);
+    }
     float bound = INFINITY;
     if (p.pitch < p.nlist) {
         double qn2 = 0.0;   // f64: the value -> distance map must not add rounding of its own
@@ -1289,12 +1299,16 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
 // The centroid table as a tensor-core operand (3xTF32, like a flat f32 index); see coarse_select_kernel.
 int tc_coarse_prepare(annb_index* ix) {
     if (!ix->is_ivf || ix->nlist < 512) return ANNB_OK;      // small tables: the exact CUDA-core ranking is already cheap
-    const uint32_t slab_elems = tc::SLAB_BYTES / 4;
+    // 3xFP16 (rows scaled by powers of two, 16 elements per MMA K step) like the flat f32 index; option ivf_coarse_fp16 = 0
+    // rebuilds this state as 3xTF32
+    const bool f16 = ix->opt_ivf_coarse_fp16 != 0;
+    const uint32_t elem = f16 ? 2u : 4u;
+    const uint32_t slab_elems = tc::SLAB_BYTES / elem;
     const uint32_t kp = round_up(ix->dim, slab_elems);
-    if (kp * 4 > 512) return ANNB_OK;
+    if (round_up(ix->dim, 32u) * 4 > 512) return ANNB_OK;
     TcState* st = new TcState();
     ix->tc_coarse = st;
-    st->kind = tc::KIND_TF32X3;
+    st->kind = f16 ? tc::KIND_F16X3 : tc::KIND_TF32X3;
     st->kp_elems = kp;
     st->nslab = kp / slab_elems;
     st->n_pad = round_up<uint32_t>(ix->nlist, tc::BN);
@@ -1311,21 +1325,34 @@ int tc_coarse_prepare(annb_index* ix) {
         else tc::aux_kernel<<<ag, 128, 0, s>>>(crow, ix->cent_ld * 4, 0, ix->dim, ix->d_centroid_norms, nullptr, 1, ix->nlist, aux_rows, st->d_aux);
         ANNB_CUDA_CHECK(cudaGetLastError());
     }
-    const uint64_t bytes = 2ull * st->n_pad * kp * 4;
+    const uint64_t bytes = 2ull * st->n_pad * kp * elem;
     ANNB_CUDA_CHECK(cudaMalloc(&st->d_x, bytes));
-    tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * kp), 256, 0, s>>>(ix->d_centroids, ix->cent_ld, ix->dim, ix->nlist, st->n_pad, kp,
-                                                                                            static_cast<float*>(st->d_x));
-    ANNB_CUDA_CHECK(cudaGetLastError());
-    ANNB_TRY(tc_make_tmap(&st->tm_x, st->d_x, 2ull * st->n_pad, kp, 4));
     st->bytes = bytes + aux_rows * sizeof(float);
+    if (f16) {
+        ANNB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&st->d_aux2), aux_rows * sizeof(float)));
+        st->bytes += aux_rows * sizeof(float);
+        tc::fill_aux_kernel<<<ag, 128, 0, s>>>(st->d_aux2, aux_rows, aux_rows, 1.0f);
+        tc::split_f16_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * 32), 256, 0, s>>>(ix->d_centroids, ix->cent_ld, ix->dim, ix->nlist, st->n_pad, kp,
+                                                                                            static_cast<__half*>(st->d_x), st->d_aux2);
+        if (ix->metric == ANNB_COSINE)     // cosine: one constant per cell, -1 / (|c| * scale); L2 keeps |c|^2 and reads the inverse scale separately
+            tc::mul_rows_kernel<<<static_cast<uint32_t>((static_cast<uint64_t>(st->n_pad) + 127) / 128), 128, 0, s>>>(st->d_aux, st->d_aux2, st->n_pad);
+    } else {
+        tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * kp), 256, 0, s>>>(ix->d_centroids, ix->cent_ld, ix->dim, ix->nlist, st->n_pad, kp,
+                                                                                                static_cast<float*>(st->d_x));
+    }
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    ANNB_TRY(tc_make_tmap(&st->tm_x, st->d_x, 2ull * st->n_pad, kp, elem));
     ix->device_bytes += st->bytes;
     return ANNB_OK;
 }
 
 void tc_coarse_destroy(annb_index* ix) {
     if (!ix->tc_coarse) return;
+    ix->device_bytes -= std::min<uint64_t>(ix->device_bytes, ix->tc_coarse->bytes);
     cudaFree(ix->tc_coarse->d_x);
     cudaFree(ix->tc_coarse->d_aux);
+    cudaFree(ix->tc_coarse->d_aux2);
+    ix->tc_coarse->q_scale.release();
     ix->tc_coarse->q_op.release();
     ix->tc_coarse->dense.release();
     ix->tc_coarse->dense_gm.release();
@@ -1353,17 +1380,25 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     TcState* st = ix->tc_coarse;
     const uint32_t kp = st->kp_elems;
     const uint32_t nq_pad = static_cast<uint32_t>(round_up<uint64_t>(nq, tc::BM));
-    ANNB_TRY(st->q_op.ensure(2ull * nq_pad * kp * 4));
-    tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(nq_pad) * kp), 256, 0, s>>>(d_route, route_ld, ix->dim, nq, nq_pad, kp, st->q_op.as<float>());
+    const bool f16 = st->kind == tc::KIND_F16X3;
+    const uint32_t elem = f16 ? 2u : 4u;
+    ANNB_TRY(st->q_op.ensure(2ull * nq_pad * kp * elem));
+    if (f16) {
+        ANNB_TRY(st->q_scale.ensure(static_cast<uint64_t>(nq_pad) * 4));
+        tc::split_f16_kernel<<<tc_blocks_for(static_cast<uint64_t>(nq_pad) * 32), 256, 0, s>>>(d_route, route_ld, ix->dim, nq, nq_pad, kp, st->q_op.as<__half>(),
+                                                                                            st->q_scale.as<float>());
+    } else {
+        tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(nq_pad) * kp), 256, 0, s>>>(d_route, route_ld, ix->dim, nq, nq_pad, kp, st->q_op.as<float>());
+    }
     ANNB_CUDA_CHECK(cudaGetLastError());
     CUtensorMap tmq;
-    ANNB_TRY(tc_make_tmap(&tmq, st->q_op.p, 2ull * nq_pad, kp, 4));
+    ANNB_TRY(tc_make_tmap(&tmq, st->q_op.p, 2ull * nq_pad, kp, elem));
     const uint64_t q_tiles = nq_pad / tc::BM, db_tiles = st->n_pad / tc::BN;
     // about two waves of CTAs: the whole matrix is a few tens of microseconds of tensor work
     const uint32_t splits_req = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(db_tiles, (2 * 148 + q_tiles - 1) / q_tiles)));
     const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;
     const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
-    const size_t fixed = 256 + 8 * 64 * 4, budget = 227 * 1024;
+    const size_t fixed = 256 + 2 * 8 * 64 * 4, budget = 227 * 1024;
     const uint32_t stages = static_cast<uint32_t>(std::min<size_t>(8, (budget - fixed) / (2 * tc::SLAB_TILE)));
     const size_t smem = static_cast<size_t>(stages) * 2 * tc::SLAB_TILE + fixed;
     ANNB_TRY(st->dense.ensure(nq * static_cast<uint64_t>(st->n_pad) * 4));
@@ -1371,6 +1406,7 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     p.nq = nq; p.n_rows = ix->nlist; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
     p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = 2; p.aux = st->d_aux;
     p.q_op = st->q_op.as<void>(); p.kp = kp; p.dense = st->dense.as<float>(); p.dense_ld = st->n_pad;
+    p.aux2 = st->d_aux2; p.q_inv_scale = st->q_scale.as<float>();
     // Select from group minima (coarse_select_gm_kernel) when the selected groups are expected to hold well under cmax cells at
     // or below the threshold: G groups carry about G (1 + 7 G / nlist) of them.
     const uint32_t cmax = next_pow2(pitch + 1);
@@ -1388,7 +1424,15 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     }
     {
         dim3 grid(static_cast<uint32_t>(q_tiles), splits);
-        if (ix->metric == ANNB_L2) {
+        if (f16 && ix->metric == ANNB_L2) {
+            auto kern = tc::flat_tc_kernel<tc::KIND_F16X3, 16, MET_L2, true, true>;
+            ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kern<<<grid, tc::NUM_THREADS, smem, s>>>(tmq, st->tm_x, p);
+        } else if (f16) {
+            auto kern = tc::flat_tc_kernel<tc::KIND_F16X3, 16, MET_COS, true, true>;
+            ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            kern<<<grid, tc::NUM_THREADS, smem, s>>>(tmq, st->tm_x, p);
+        } else if (ix->metric == ANNB_L2) {
             auto kern = tc::flat_tc_kernel<tc::KIND_TF32X3, 16, MET_L2, true, true>;
             ANNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             kern<<<grid, tc::NUM_THREADS, smem, s>>>(tmq, st->tm_x, p);
@@ -1407,7 +1451,7 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     c.staged_words = (ix->opt_ivf_coarse_stage && ix->nlist <= 8192) ? round_up(ix->nlist, 4u) : 0u;
     if (glimit) { c.gmin = st->dense_gm.as<float>(); c.glimit = glimit; c.staged_words = st->n_pad / 8; }
     c.queries = d_route; c.q_ld = route_ld; c.centroids = ix->d_centroids; c.c_ld = ix->cent_ld; c.centroid_norms = ix->d_centroid_norms;
-    c.dim = ix->dim; c.eps = tc_cert_eps(ix, tc::KIND_TF32X3, kp, 2, false); c.cnorm_max = ix->tc_cnorm_max; c.ranked = d_ranked;
+    c.dim = ix->dim; c.eps = tc_cert_eps(ix, st->kind, kp, 2, false); c.cnorm_max = ix->tc_cnorm_max; c.ranked = d_ranked;
     if (ix->metric == ANNB_L2) ANNB_TRY(launch_coarse_select<MET_L2>(c, s));
     else if (ix->dtype == ANNB_SQ8) ANNB_TRY(launch_coarse_select<MET_COS_PRENORM>(c, s));
     else ANNB_TRY(launch_coarse_select<MET_COS>(c, s));
@@ -1486,7 +1530,7 @@ int tc_assign_run(TcAssignState* st, const float* d_x, uint32_t x_ld, uint64_t n
     const uint32_t splits_req = pick_splits(q_tiles, db_tiles, 0);
     const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;
     const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
-    const size_t fixed = 256 + 8 * 64 * 4, budget = 227 * 1024;
+    const size_t fixed = 256 + 2 * 8 * 64 * 4, budget = 227 * 1024;
     const uint32_t stages = static_cast<uint32_t>(std::min<size_t>(8, (budget - fixed) / (2 * tc::SLAB_TILE)));
     const size_t smem = static_cast<size_t>(stages) * 2 * tc::SLAB_TILE + fixed;
     ANNB_TRY(st->part.ensure(nr * 2ull * splits * AKP * 8));
