@@ -1757,10 +1757,39 @@ int annb_merge_shards_dev(const void* d_parts, uint64_t part_stride_bytes, uint6
     MergeShardsParams m{};
     m.base = static_cast<const uint8_t*>(d_parts); m.part_stride = part_stride_bytes; m.dist_offset = dist_offset_bytes;
     m.parts = parts; m.k = k; m.nq = nq; m.out_ids = d_out_ids; m.out_dist = d_out_dist; m.out_counts = d_out_counts;
-    if (m.parts * m.k <= 128u) merge_shards_sort_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 4)), 128, 0, static_cast<cudaStream_t>(stream)>>>(m);
+    if (m.parts * m.k <= 128u) merge_shards_sort_kernel<false><<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 4)), 128, 0, static_cast<cudaStream_t>(stream)>>>(m);
     else merge_shards_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 4)), 128, 0, static_cast<cudaStream_t>(stream)>>>(m);
     ANNB_CUDA_CHECK(cudaGetLastError());
     return ANNB_OK;
+}
+
+// annb_merge_shards_dev + annb_shard_check_gathered_async_dev in one pass (one kernel, one 8-byte memset, one 8-byte copy to the
+// caller's pinned verdict words) for the serving loop's deferred verdict.  The list of this shard's queries to refine is NOT left in
+// the handle: a verdict that asks for a refine is followed by the synchronous annb_shard_check_gathered_dev, which builds it.
+int annb_merge_check_shards_async_dev(annb_index* ix, const void* d_parts, uint64_t part_stride_bytes, uint64_t dist_offset_bytes, uint64_t bound_offset_bytes,
+                                      uint32_t parts, uint32_t my_part, uint64_t nq, uint32_t k, uint64_t* d_out_ids, float* d_out_dist, uint32_t* h_verdict,
+                                      void* stream) {
+    if (!ix || !d_parts || !d_out_ids || !d_out_dist || !h_verdict || parts == 0 || k == 0 || my_part >= parts) return fail(ANNB_ERR_INVALID_ARGUMENT, "null argument / bad shape");
+    if ((part_stride_bytes & 7) || (dist_offset_bytes & 3) || (bound_offset_bytes & 3)) return fail(ANNB_ERR_INVALID_ARGUMENT, "misaligned shard layout");
+    if (nq > QUERY_BATCH) return fail(ANNB_ERR_UNSUPPORTED, "shard check: at most 16384 queries per call");
+    if (parts * k > 128u || nq == 0) {      // large merges: the two separate passes
+        ANNB_TRY(annb_merge_shards_dev(d_parts, part_stride_bytes, dist_offset_bytes, parts, nq, k, d_out_ids, d_out_dist, nullptr, stream));
+        return annb_shard_check_gathered_async_dev(ix, d_parts, part_stride_bytes, bound_offset_bytes, parts, my_part, d_out_dist, nq, k, h_verdict, stream);
+    }
+    ANNB_DEVICE(ix->device);
+    std::lock_guard<std::mutex> lock(ix->mu);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    ANNB_TRY(order_after_previous(ix, s));
+    ANNB_TRY(ix->s_flags.ensure(64));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(ix->s_flags.p, 0, 8, s));
+    MergeShardsParams m{};
+    m.base = static_cast<const uint8_t*>(d_parts); m.part_stride = part_stride_bytes; m.dist_offset = dist_offset_bytes;
+    m.parts = parts; m.k = k; m.nq = nq; m.out_ids = d_out_ids; m.out_dist = d_out_dist; m.out_counts = nullptr;
+    m.bound_offset = bound_offset_bytes; m.my_part = my_part; m.verdict = ix->s_flags.as<uint32_t>();
+    merge_shards_sort_kernel<true><<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 4)), 128, 0, s>>>(m);
+    ANNB_CUDA_CHECK(cudaGetLastError());
+    ANNB_CUDA_CHECK(cudaMemcpyAsync(h_verdict, ix->s_flags.p, 8, cudaMemcpyDeviceToHost, s));
+    return mark_call_done(ix, s);
 }
 
 int annb_flat_create_multi(annb_index** out, const float* data, uint64_t n, uint32_t dim, int dtype, int metric, const int* devices, int n_devices) {

@@ -1394,8 +1394,9 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     CUtensorMap tmq;
     ANNB_TRY(tc_make_tmap(&tmq, st->q_op.p, 2ull * nq_pad, kp, elem));
     const uint64_t q_tiles = nq_pad / tc::BM, db_tiles = st->n_pad / tc::BN;
-    // about two waves of CTAs: the whole matrix is a few tens of microseconds of tensor work
-    const uint32_t splits_req = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(db_tiles, (2 * 148 + q_tiles - 1) / q_tiles)));
+    // One CTA per SM: whole waves of CTAs against the per-CTA fixed cost (about two tiles' worth of query staging and pipeline fill)
+    // -- 79 query tiles: 5 splits = 2.7 waves of 7 tiles instead of 4 splits = 2.1 waves (three in practice) of 8
+    const uint32_t splits_req = pick_splits(q_tiles, db_tiles, 0, 2);
     const uint64_t tiles_per = (db_tiles + splits_req - 1) / splits_req;
     const uint32_t splits = static_cast<uint32_t>((db_tiles + tiles_per - 1) / tiles_per);
     const size_t fixed = 256 + 2 * 8 * 64 * 4, budget = 227 * 1024;

@@ -865,11 +865,20 @@ struct MergeShardsParams {
     uint64_t* out_ids;
     float* out_dist;
     uint32_t* out_counts;
+    // fused shard check (merge_shards_sort_kernel<true>): every shard's bounds [nq] sit bound_offset bytes into its block, its int32
+    // status word behind them; verdict[0] counts my_part's queries to refine, verdict[1]: bit 0 some shard has to refine, bit 1 some
+    // shard's call failed
+    uint64_t bound_offset;
+    uint32_t my_part;
+    uint32_t* verdict;
 };
 
 // Small merges (parts * k <= 128, e.g. 8 shards x k = 10 or 15): one warp per query sorts the (distance, slot) keys of all shards
 // in registers -- slot = shard * k + position, so the key order IS (distance, shard, position) -- and emits the first k.  The
 // binary-search variant below walks ~50 dependent loads per entry; this one is one load round trip and ~500 register ops.
+// CHECK: the merged verdict of annb_shard_check_gathered_dev in the same pass -- the k-th merged key is in a register, every
+// shard's bound for the query is one more load: no second kernel over the merged rows.
+template <bool CHECK>
 __global__ void __launch_bounds__(128) merge_shards_sort_kernel(MergeShardsParams p) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t q = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -909,6 +918,29 @@ __global__ void __launch_bounds__(128) merge_shards_sort_kernel(MergeShardsParam
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) valid += __shfl_xor_sync(0xFFFFFFFFu, valid, off);
     if (p.out_counts && lane == 0) p.out_counts[q] = valid;
+    if constexpr (CHECK) {
+        // k-th merged distance (+inf where fewer than k rows were found at all): rank k - 1 lives in key[(k - 1) / 32] of lane (k - 1) % 32
+        const uint32_t kr = p.k - 1;
+        uint64_t kk = KEY_SENTINEL;
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (static_cast<uint32_t>(j) == (kr >> 5)) kk = key[j];
+        kk = __shfl_sync(0xFFFFFFFFu, kk, kr & 31u);
+        const float dk = kk != KEY_SENTINEL ? key_dist(kk) : INFINITY;
+        uint32_t flags = 0, mine = 0;
+        for (uint32_t s = lane; s < p.parts; s += 32) {
+            const uint8_t* bb = p.base + static_cast<uint64_t>(s) * p.part_stride + p.bound_offset;
+            const float b = reinterpret_cast<const float*>(bb)[q];
+            const bool need = !(b > dk) && b != INFINITY;
+            if (need) { flags |= 1u; if (s == p.my_part) mine = 1; }
+            if (q == 0 && *reinterpret_cast<const int32_t*>(bb + p.nq * 4) != 0) flags |= 2u;   // a failed shard poisons the step on every rank alike
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { flags |= __shfl_xor_sync(0xFFFFFFFFu, flags, off); mine |= __shfl_xor_sync(0xFFFFFFFFu, mine, off); }
+        if (lane == 0) {
+            if (mine) atomicAdd(p.verdict, 1u);
+            if (flags) atomicOr(p.verdict + 1, flags);
+        }
+    }
 }
 
 // One warp per query.  Each per-shard list is ascending, so an entry's final rank is its own slot plus, for every other

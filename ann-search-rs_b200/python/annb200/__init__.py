@@ -91,6 +91,7 @@ def lib():
         _lib.annb_shard_check_dev.argtypes = [vp, vp, vp, u64, u32, C.POINTER(u32), vp]
         _lib.annb_shard_check_gathered_dev.argtypes = [vp, vp, u64, u64, u32, u32, vp, u64, u32, C.POINTER(u32), C.POINTER(u32), vp]
         _lib.annb_shard_check_gathered_async_dev.argtypes = [vp, vp, u64, u64, u32, u32, vp, u64, u32, vp, vp]
+        _lib.annb_merge_check_shards_async_dev.argtypes = [vp, vp, u64, u64, u64, u32, u32, u64, u32, vp, vp, vp, vp]
         _lib.annb_ivf_validate.argtypes = [vp, vp, u64, u32, u32, C.POINTER(C.c_double)]
         _lib.annb_shard_refine_dev.argtypes = [vp, vp, u64, u32, u32, u32, vp, vp, u32, vp, vp, vp]
         _lib.annb_merge_shards_dev.argtypes = [vp, u64, u64, u32, u64, u32, vp, vp, vp, vp]

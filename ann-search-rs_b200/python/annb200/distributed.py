@@ -206,18 +206,19 @@ class ShardedSearch:
                                                   self.bound.data_ptr(), st)
                 err = failed(rc) if rc != 0 else None
             self.status.fill_(1 if err is not None else 0)
-            rc = self._exchange_and_merge(L, st)
-            if rc != 0 and err is None:
-                err = failed(rc)
-            # Every rank holds every shard's bounds and status now: the verdict needs no further collective.
-            if defer:
-                rc = L.annb_shard_check_gathered_async_dev(self.index.handle, self.gathered.data_ptr(), self.block, nq * k * 12, self.world, self.rank,
-                                                           self.out_dist.data_ptr(), nq, k, self.h_verdict.data_ptr(), st)
+            # Every rank holds every shard's bounds and status after the exchange: the verdict needs no further collective.
+            if defer:      # merge and verdict in one pass over the gathered blocks, verdict words on their way to pinned memory
+                dist_.all_gather_into_tensor(self.gathered, self.mine, group=self.group)
+                rc = L.annb_merge_check_shards_async_dev(self.index.handle, self.gathered.data_ptr(), self.block, nq * k * 8, nq * k * 12, self.world,
+                                                         self.rank, nq, k, self.out_ids.data_ptr(), self.out_dist.data_ptr(), self.h_verdict.data_ptr(), st)
                 if rc != 0 and err is None:
                     err = failed(rc)
                 self.ev.record(st_obj)
                 self._pending = (queries, st_obj, err)
                 return self.out_ids, self.out_dist
+            rc = self._exchange_and_merge(L, st)
+            if rc != 0 and err is None:
+                err = failed(rc)
             self._finish(queries, st_obj, err)
         return self.out_ids, self.out_dist
 

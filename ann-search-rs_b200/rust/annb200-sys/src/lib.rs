@@ -91,6 +91,9 @@ extern "C" {
     pub fn annb_ivf_validate(index: *const annb_index, positions: *const u64, n_samples: u64, k: u32, nprobe: u32, out_recall: *mut f64) -> c_int;
     pub fn annb_shard_check_gathered_async_dev(index: *mut annb_index, d_parts: *const c_void, part_stride_bytes: u64, bound_offset_bytes: u64, parts: u32,
                                                my_part: u32, d_merged_dist: *const f32, nq: u64, k: u32, h_verdict: *mut u32, stream: *mut c_void) -> c_int;
+    pub fn annb_merge_check_shards_async_dev(index: *mut annb_index, d_parts: *const c_void, part_stride_bytes: u64, dist_offset_bytes: u64,
+                                             bound_offset_bytes: u64, parts: u32, my_part: u32, nq: u64, k: u32, d_out_ids: *mut u64,
+                                             d_out_dist: *mut f32, h_verdict: *mut u32, stream: *mut c_void) -> c_int;
     pub fn annb_shard_refine_dev(index: *mut annb_index, d_queries: *const f32, nq: u64, dim: u32, k: u32, nprobe: u32, d_probes: *const u32,
                                  d_n_probes: *const u32, probe_pitch: u32, d_ids: *mut u64, d_dist: *mut f32, stream: *mut c_void) -> c_int;
     pub fn annb_index_shard_count(index: *const annb_index, out: *mut u32) -> c_int;

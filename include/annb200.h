@@ -299,6 +299,14 @@ int annb_shard_check_gathered_async_dev(annb_index* index, const void* d_parts, 
                                         uint32_t parts, uint32_t my_part, const float* d_merged_dist, uint64_t nq, uint32_t k,
                                         uint32_t* h_verdict, void* stream);
 
+/* annb_merge_shards_dev and annb_shard_check_gathered_async_dev in ONE pass over the gathered blocks (the deferred step of a serving
+ * loop: one kernel, one 8-byte copy to h_verdict[2]); same merged rows, same verdict words.  The handle keeps no list of queries to
+ * refine from this call: a verdict that asks for a refine is followed by the synchronous annb_shard_check_gathered_dev.  Replaces the
+ * merge + host-side bookkeeping that follows the per-shard queries of src/lib.rs:2842, 2949 in a sharded deployment. */
+int annb_merge_check_shards_async_dev(annb_index* index, const void* d_parts, uint64_t part_stride_bytes, uint64_t dist_offset_bytes,
+                                      uint64_t bound_offset_bytes, uint32_t parts, uint32_t my_part, uint64_t nq, uint32_t k,
+                                      uint64_t* d_out_ids, float* d_out_dist, uint32_t* h_verdict, void* stream);
+
 int annb_shard_refine_dev(annb_index* index, const float* d_queries, uint64_t nq, uint32_t dim, uint32_t k, uint32_t nprobe,
                           const uint32_t* d_probes, const uint32_t* d_n_probes, uint32_t probe_pitch, uint64_t* d_ids,
                           float* d_dist, void* stream);

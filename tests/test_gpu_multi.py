@@ -199,6 +199,56 @@ def test_shard_mode_certificate_against_the_merged_result(gpu, kind):
     assert refined <= local
 
 
+@pytest.mark.parametrize("parts,k", [(1, 10), (3, 10), (8, 15), (8, 16), (12, 10), (9, 15)])
+def test_fused_merge_and_check_equals_the_two_passes(gpu, parts, k):
+    """annb_merge_check_shards_async_dev = annb_merge_shards_dev + annb_shard_check_gathered_async_dev on the same gathered blocks:
+    same merged rows (ties across shards, short lists, empty shards) and the same verdict words (bounds that fail, infinite
+    bounds, a shard whose status word is set).  parts * k <= 128 takes the fused kernel, larger merges the two passes inside."""
+    import torch
+    lib = annb200.lib()
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(parts * 100 + k)
+    nq = 777
+    data = datagen.gaussian_noise(5000, 16, seed=3)
+    h = annb200.ExhaustiveIndexB200.new(data, annb200.L2, annb200.F32)      # any handle: the call only uses its scratch and ordering
+    block = ((nq * k * 12 + nq * 4 + 4 + 255) // 256) * 256
+    host = np.zeros((parts, block), np.uint8)
+    for s_ in range(parts):
+        d = np.sort(rng.integers(0, 40, (nq, k)).astype(np.float32) * 0.5, axis=1)      # coarse values: many ties across shards
+        ids = (rng.integers(0, 1 << 40, (nq, k), dtype=np.int64)).astype(np.uint64)
+        valid = rng.integers(0, k + 1, nq) if s_ % 3 == 1 else np.full(nq, k)          # some shards hold short (or empty) lists
+        for q_ in np.nonzero(valid < k)[0]:
+            ids[q_, valid[q_]:] = np.uint64(0xFFFFFFFFFFFFFFFF)
+            d[q_, valid[q_]:] = np.inf
+        bound = rng.choice(np.array([np.inf, 1.0, 5.0, 12.0, 30.0], np.float32), nq)
+        host[s_, :nq * k * 8] = ids.view(np.uint8).reshape(-1)
+        host[s_, nq * k * 8:nq * k * 12] = d.view(np.uint8).reshape(-1)
+        host[s_, nq * k * 12:nq * k * 12 + nq * 4] = bound.view(np.uint8)
+    for status_part in (None, parts - 1):
+        if status_part is not None:
+            host[status_part, nq * k * 12 + nq * 4:nq * k * 12 + nq * 4 + 4] = np.array([1], np.int32).view(np.uint8)
+        gathered = torch.from_numpy(host.reshape(-1)).to(dev)
+        for my in sorted({0, parts - 1}):
+            a_ids = torch.empty((nq, k), dtype=torch.int64, device=dev); a_d = torch.empty((nq, k), dtype=torch.float32, device=dev)
+            b_ids = torch.empty_like(a_ids); b_d = torch.empty_like(a_d)
+            va = torch.zeros((2,), dtype=torch.int32).pin_memory(); vb = torch.zeros((2,), dtype=torch.int32).pin_memory()
+            annb200._check(lib.annb_merge_shards_dev(gathered.data_ptr(), block, nq * k * 8, parts, nq, k, a_ids.data_ptr(), a_d.data_ptr(), None, st))
+            annb200._check(lib.annb_shard_check_gathered_async_dev(h.handle, gathered.data_ptr(), block, nq * k * 12, parts, my, a_d.data_ptr(), nq, k,
+                                                                   va.data_ptr(), st))
+            annb200._check(lib.annb_merge_check_shards_async_dev(h.handle, gathered.data_ptr(), block, nq * k * 8, nq * k * 12, parts, my, nq, k,
+                                                                 b_ids.data_ptr(), b_d.data_ptr(), vb.data_ptr(), st))
+            torch.cuda.synchronize()
+            assert torch.equal(a_ids, b_ids) and torch.equal(a_d.view(torch.int32), b_d.view(torch.int32)), (parts, k, my)
+            assert va.tolist() == vb.tolist(), (parts, k, my, va.tolist(), vb.tolist())
+            assert (vb[1].item() & 2) == (0 if status_part is None else 2)
+            # the verdict against a plain numpy statement
+            dk = a_d.cpu().numpy()[:, k - 1]
+            bounds = np.stack([host[s_, nq * k * 12:nq * k * 12 + nq * 4].view(np.float32) for s_ in range(parts)])
+            need = ~(bounds > dk[None, :]) & np.isfinite(bounds)
+            assert vb[0].item() == int(need[my].sum()) and (vb[1].item() & 1) == int(need.any())
+
+
 @pytest.mark.parametrize("kind", ["flat", "ivf"])
 def test_sharded_search_deferred_verdict(gpu, kind):
     """ShardedSearch on a one-rank NCCL group: a deferred step (verdict read later, resolve()) gives the rows of the immediate

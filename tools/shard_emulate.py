@@ -127,7 +127,8 @@ def main():
                   f"balanced {total / 148:.0f} us, makespan {max(heap):.0f} us; lists {le - lb}, rows per list min/median/max "
                   f"{rows[lb:le].min()}/{int(np.median(rows[lb:le]))}/{rows[lb:le].max()}, pairs per list median/max {int(np.median(cnt[lb:le]))}/{cnt[lb:le].max()}")
     names = ["route(slice)", "scan(shard)", "merge", "check"]
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 2)] for _ in range(args.steps)]
+    h_verdict = torch.zeros((2,), dtype=torch.int32).pin_memory()
     tmp_p = torch.zeros((per * pitch,), dtype=torch.int32, device=dev)
     tmp_n = torch.zeros((per,), dtype=torch.int32, device=dev)
     mine_c, any_c = C.c_uint32(0), C.c_uint32(0)
@@ -155,6 +156,10 @@ def main():
                                                        C.byref(mine_c), C.byref(any_c), st))
         e[4].record()
         refine = mine_c.value
+        # the deferred step of the serving loop does both in one pass (no read-back)
+        annb200._check(L.annb_merge_check_shards_async_dev(index.handle, gathered.data_ptr(), block, nq * k * 8, nq * k * 12, W, R, nq, k, out_ids.data_ptr(),
+                                                           out_dist.data_ptr(), h_verdict.data_ptr(), st))
+        e[5].record()
     torch.cuda.synchronize()
     tot = 0.0
     for j, nm in enumerate(names):
@@ -162,6 +167,8 @@ def main():
         tot += ms
         print(f"{nm:14s} {ms:8.3f} ms")
     print(f"{'sum':14s} {tot:8.3f} ms   (world {W}, rank {R}; to-refine of this rank after the merged check: {refine})")
+    fused = float(np.median([ev[i][4].elapsed_time(ev[i][5]) for i in range(args.steps)]))
+    print(f"{'merge+check':14s} {fused:8.3f} ms   fused pass of the deferred step (annb_merge_check_shards_async_dev), instead of the two lines above")
     print(f"exchange payloads: probes {4 * (per * pitch + per + 1) * W / 1e6:.2f} MB gathered, results {block * W / 1e6:.2f} MB gathered")
     for key in ("last_path", "launches", "fallback_queries", "uncertified"):
         try:
