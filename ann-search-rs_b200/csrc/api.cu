@@ -1871,6 +1871,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "ivf_stream") ix->opt_ivf_stream = static_cast<int>(value);
     else if (k == "ivf_coarse_stage") ix->opt_ivf_coarse_stage = static_cast<int>(value);
     else if (k == "ivf_coarse_gm") ix->opt_ivf_coarse_gm = static_cast<int>(value);
+    else if (k == "ivf_coarse_blocked") ix->opt_ivf_coarse_blocked = static_cast<int>(value);
     else if (k == "ivf_coarse_fp16") {
         // operand form of the tensor-core centroid ranking (1: 3xFP16, 0: 3xTF32), fixed when its state is built: rebuild on change
         const int v = value != 0 ? 1 : 0;

@@ -332,9 +332,15 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 }
                 if constexpr (DENSE) {
                     if (static_cast<uint64_t>(q0) + row_in_tile < p.nq) {
-                        float4* dst = reinterpret_cast<float4*>(p.dense + (static_cast<uint64_t>(q0) + row_in_tile) * p.dense_ld + row0 + c * NV);
+                        if (p.dense_blocked) {
+                            float4* dst = reinterpret_cast<float4*>(p.dense) + dense_piece_index(static_cast<uint64_t>(q0) + row_in_tile, (row0 + c * NV) >> 2, p.dense_ld >> 7);
 #pragma unroll
-                        for (int j = 0; j < NV / 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                            for (int j = 0; j < NV / 4; j++) dst[j * 128] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        } else {
+                            float4* dst = reinterpret_cast<float4*>(p.dense + (static_cast<uint64_t>(q0) + row_in_tile) * p.dense_ld + row0 + c * NV);
+#pragma unroll
+                            for (int j = 0; j < NV / 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        }
                         if (p.dense_gm != nullptr) {   // group minima (pad columns are +inf / NaN and never lower a minimum)
                             float4* gdst = reinterpret_cast<float4*>(p.dense_gm + (static_cast<uint64_t>(q0) + row_in_tile) * (p.dense_ld >> 3) + ((row0 + c * NV) >> 3));
 #pragma unroll
@@ -389,6 +395,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 struct CoarseSelectParams {
     const float* dense;         // [nq][dense_ld] approximate selection values
     uint32_t dense_ld;
+    uint32_t blocked;           // dense is stored in the blocked layout of dense_piece_index()
     const float* gmin;          // coarse_select_gm_kernel: [nq][dense_ld / 8] minima of the aligned groups of 8 values
     uint32_t glimit;            // ... its radix select stops once at most this many groups lie at or below the threshold
     uint64_t nq;
@@ -484,6 +491,9 @@ __device__ __forceinline__ uint32_t coarse_radix_threshold(Fetch fetch, uint32_t
 __device__ __forceinline__ uint32_t coarse_candidates_full_row(const CoarseSelectParams& p, uint64_t q, uint32_t* hist, uint32_t* cand, uint4* staged,
                                                                uint32_t lane, uint32_t& thr) {
     const float4* src4 = reinterpret_cast<const float4*>(p.dense + q * p.dense_ld);
+    const float4* blk4 = reinterpret_cast<const float4*>(p.dense);
+    const uint32_t col_tiles = p.dense_ld >> 7;
+    auto piece = [&](uint32_t i4) { return p.blocked ? __ldg(blk4 + dense_piece_index(q, i4, col_tiles)) : __ldg(src4 + i4); };
     const uint32_t n4 = (p.nlist + 3) >> 2;
     const bool use_smem = staged != nullptr;
     auto ord = [&](float4 x, uint32_t i4, uint32_t u[4]) {   // ordered images; columns past nlist never qualify
@@ -493,14 +503,14 @@ __device__ __forceinline__ uint32_t coarse_candidates_full_row(const CoarseSelec
     };
     auto fetch = [&](uint32_t i4, uint32_t u[4]) {
         if (use_smem) { const uint4 w = staged[i4]; u[0] = w.x; u[1] = w.y; u[2] = w.z; u[3] = w.w; }
-        else ord(__ldg(src4 + i4), i4, u);
+        else ord(piece(i4), i4, u);
     };
     thr = 0xFFFFFFFFu;
     if (p.pitch < p.nlist) {
         uint32_t umin = 0xFFFFFFFFu, umax = 0u;
         for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
             uint32_t u[4];
-            ord(__ldg(src4 + i4), i4, u);
+            ord(piece(i4), i4, u);
             if (use_smem) staged[i4] = make_uint4(u[0], u[1], u[2], u[3]);
 #pragma unroll
             for (int e = 0; e < 4; e++) if (4 * i4 + e < p.nlist) { umin = min(umin, u[e]); umax = max(umax, u[e]); }
@@ -515,7 +525,7 @@ __device__ __forceinline__ uint32_t coarse_candidates_full_row(const CoarseSelec
     } else if (use_smem) {
         for (uint32_t i4 = lane; i4 < n4; i4 += 32) {
             uint32_t u[4];
-            ord(__ldg(src4 + i4), i4, u);
+            ord(piece(i4), i4, u);
             staged[i4] = make_uint4(u[0], u[1], u[2], u[3]);
         }
         __syncwarp();
@@ -754,7 +764,13 @@ __global__ void __launch_bounds__(256) coarse_select_gm_kernel(CoarseSelectParam
             uint32_t mine = 0, hits = 0, g = 0;
             if (j < n_sel) {
                 g = glist[j];
-                const float4 a = __ldg(reinterpret_cast<const float4*>(row + 8 * g)), b = __ldg(reinterpret_cast<const float4*>(row + 8 * g) + 1);
+                float4 a, b;
+                if (p.blocked) {
+                    const float4* pa = reinterpret_cast<const float4*>(p.dense) + dense_piece_index(q, 2 * g, p.dense_ld >> 7);
+                    a = __ldg(pa); b = __ldg(pa + 128);      // pieces 2g and 2g + 1 of one column tile sit 128 float4 apart
+                } else {
+                    a = __ldg(reinterpret_cast<const float4*>(row + 8 * g)); b = __ldg(reinterpret_cast<const float4*>(row + 8 * g) + 1);
+                }
                 const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
                 for (int e = 0; e < 8; e++)
@@ -1422,6 +1438,10 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     if (glimit) {
         ANNB_TRY(st->dense_gm.ensure(nq * static_cast<uint64_t>(st->n_pad / 8) * 4));
         p.dense_gm = st->dense_gm.as<float>();
+        // the select then reads single pieces: store the matrix in the blocked layout whose epilogue stores coalesce (whole query tiles)
+        ANNB_TRY(st->dense.ensure(static_cast<uint64_t>(nq_pad) * st->n_pad * 4));
+        p.dense = st->dense.as<float>();
+        p.dense_blocked = ix->opt_ivf_coarse_blocked ? 1u : 0u;
     }
     {
         dim3 grid(static_cast<uint32_t>(q_tiles), splits);
@@ -1450,7 +1470,7 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     // 10k queries: 0.41 ms against 0.27 ms per launch -- 16 KB per warp leaves 12 resident warps per SM where the L2 variant
     // keeps 64, and the select is a chain of dependent passes that only occupancy hides.  Kept behind option ivf_coarse_stage.
     c.staged_words = (ix->opt_ivf_coarse_stage && ix->nlist <= 8192) ? round_up(ix->nlist, 4u) : 0u;
-    if (glimit) { c.gmin = st->dense_gm.as<float>(); c.glimit = glimit; c.staged_words = st->n_pad / 8; }
+    if (glimit) { c.gmin = st->dense_gm.as<float>(); c.glimit = glimit; c.staged_words = st->n_pad / 8; c.blocked = p.dense_blocked; }
     c.queries = d_route; c.q_ld = route_ld; c.centroids = ix->d_centroids; c.c_ld = ix->cent_ld; c.centroid_norms = ix->d_centroid_norms;
     c.dim = ix->dim; c.eps = tc_cert_eps(ix, st->kind, kp, 2, false); c.cnorm_max = ix->tc_cnorm_max; c.ranked = d_ranked;
     if (ix->metric == ANNB_L2) ANNB_TRY(launch_coarse_select<MET_L2>(c, s));

@@ -52,9 +52,17 @@ struct Params {
     float* dense;             // DENSE mode: the selection values themselves, [nq][dense_ld] (IVF centroid ranking)
     uint32_t dense_ld;
     float* dense_gm;          // DENSE mode, optional: minima of every aligned group of 8 values, [nq][dense_ld / 8] (coarse_select_gm_kernel)
+    uint32_t dense_blocked;   // DENSE mode: 1 = the matrix is stored in the blocked layout of dense_piece_index() (coalesced epilogue stores)
     float* dbg;               // optional: CTA (0,0) dumps v of its first tile [BM][BN]
     unsigned long long* dbg_cycles;  // optional: CTA (0,0) wait-cycle counters {total, prod_empty, mma_full, mma_tempty, epi_tfull, epi_slow}
 };
+
+// Blocked layout of the DENSE matrix, in float4 pieces (4 consecutive columns of one query row): [query tile of 128][column tile
+// of 128][piece 0 .. 31][row in tile 0 .. 127].  An epilogue warp's store instruction (32 rows x one piece) is then 512 contiguous
+// bytes instead of 32 half-used sectors 4 * dense_ld bytes apart; readers fetch single pieces (the group-minima select reads two per group).
+__host__ __device__ __forceinline__ uint64_t dense_piece_index(uint64_t q, uint32_t i4, uint32_t col_tiles) {
+    return (((q >> 7) * col_tiles + (i4 >> 5)) * 32 + (i4 & 31u)) * 128 + (q & 127u);
+}
 
 // ----------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
