@@ -396,12 +396,17 @@ static int ivf_route(annb_index* ix, const PreparedQueries& pq, uint64_t nq, uin
         if (p_tc < ix->nlist && p_tc <= 480) {
             ANNB_TRY(ix->s_cdist.ensure(nq * static_cast<uint64_t>(p_tc) * 8));
             ANNB_TRY(ix->s_probes.ensure(nq * static_cast<uint64_t>(p_tc) * 4));
-            ANNB_TRY(tc_coarse_rank(ix, pq.route, pq.route_ld, nq, p_tc, ix->s_cdist.as<uint64_t>(), s));
             ProbeParams pp{};
             fill_probe_params(ix, pp, nq, np, kk, p_tc);
-            probe_walk_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 128)), 128, 0, s>>>(ix->s_cdist.as<uint64_t>(), pp);
-            ANNB_CUDA_CHECK(cudaGetLastError());
-            ix->stat_launches++;
+            if (ix->opt_ivf_coarse_walk) {      // the select's warp applies the probe-expansion rule to its own certified prefix
+                CoarseWalk w{pp.offsets, pp.nprobe, pp.k, pp.probes, pp.n_probes, pp.overflow, pp.stat_scanned, pp.stat_probed, pp.list_begin, pp.list_end};
+                ANNB_TRY(tc_coarse_rank(ix, pq.route, pq.route_ld, nq, p_tc, ix->s_cdist.as<uint64_t>(), s, &w));
+            } else {
+                ANNB_TRY(tc_coarse_rank(ix, pq.route, pq.route_ld, nq, p_tc, ix->s_cdist.as<uint64_t>(), s));
+                probe_walk_kernel<<<static_cast<uint32_t>(ceil_div<uint64_t>(nq, 128)), 128, 0, s>>>(ix->s_cdist.as<uint64_t>(), pp);
+                ANNB_CUDA_CHECK(cudaGetLastError());
+                ix->stat_launches++;
+            }
             cs->stage = 3; cs->pitch = p_tc; ix->stat_coarse_path = 2;
             return ANNB_OK;
         }
@@ -1871,6 +1876,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "ivf_stream") ix->opt_ivf_stream = static_cast<int>(value);
     else if (k == "ivf_coarse_stage") ix->opt_ivf_coarse_stage = static_cast<int>(value);
     else if (k == "ivf_coarse_gm") ix->opt_ivf_coarse_gm = static_cast<int>(value);
+    else if (k == "ivf_coarse_walk") ix->opt_ivf_coarse_walk = static_cast<int>(value);
     else if (k == "ivf_coarse_blocked") ix->opt_ivf_coarse_blocked = static_cast<int>(value);
     else if (k == "ivf_coarse_fp16") {
         // operand form of the tensor-core centroid ranking (1: 3xFP16, 0: 3xTF32), fixed when its state is built: rebuild on change

@@ -409,6 +409,8 @@ struct CoarseSelectParams {
     uint32_t dim;
     float eps, cnorm_max;
     uint64_t* ranked;           // [nq][pitch]
+    uint32_t do_walk;           // 1: apply the probe-expansion rule to the certified prefix here and write the probe lists instead of `ranked`
+    CoarseWalk walk;
 };
 
 __host__ __device__ inline size_t coarse_select_warp_bytes(uint32_t cmax, uint32_t staged_words) {
@@ -566,6 +568,10 @@ __device__ __forceinline__ void coarse_emit_ranked(const CoarseSelectParams& p, 
                                                    const uint32_t* cand, uint32_t lane, uint8_t* stage = nullptr) {
     uint64_t* out = p.ranked + q * p.pitch;
     if (count > p.cmax) {   // a huge tie class: leave the query to the exact ranking
+        if (p.do_walk) {
+            if (lane == 0) { atomicExch(p.walk.overflow, 1u); p.walk.n_probes[q] = 0; }
+            return;
+        }
         for (uint32_t j = lane; j < p.pitch; j += 32) out[j] = KEY_SENTINEL;
         return;
     }
@@ -679,9 +685,55 @@ __device__ __forceinline__ void coarse_emit_ranked(const CoarseSelectParams& p, 
         }
         bound = __double2float_rd(b);
     }
-    for (uint32_t j = lane; j < p.pitch; j += 32) {
-        const uint64_t key = keys[j];
-        out[j] = (key_idx(key) != IDX_INVALID && key_dist(key) < bound) ? key : KEY_SENTINEL;
+    if (!p.do_walk) {
+        for (uint32_t j = lane; j < p.pitch; j += 32) {
+            const uint64_t key = keys[j];
+            out[j] = (key_idx(key) != IDX_INVALID && key_dist(key) < bound) ? key : KEY_SENTINEL;
+        }
+        return;
+    }
+    // Probe expansion on the certified prefix, 32 ranks per step: cells are taken in rank order until nprobe are chosen AND at least
+    // k vectors are reachable (empty cells count toward nprobe only); an uncertified rank ends the prefix (probe_walk_kernel's rule).
+    uint32_t chosen = 0;
+    unsigned long long reach = 0, local = 0;
+    bool done = false;
+    for (uint32_t base = 0; base < p.pitch; base += 32) {
+        const uint32_t i = base + lane;
+        uint32_t c = IDX_INVALID;
+        if (i < p.pitch) {
+            const uint64_t key = keys[i];
+            if (key_idx(key) != IDX_INVALID && key_dist(key) < bound) c = key_idx(key);
+        }
+        const uint32_t inv = __ballot_sync(0xFFFFFFFFu, c == IDX_INVALID);
+        const uint32_t nvalid = inv ? static_cast<uint32_t>(__ffs(inv) - 1) : 32u;
+        unsigned long long sz = 0, lsz = 0;
+        if (lane < nvalid) {
+            sz = p.walk.offsets[c + 1] - p.walk.offsets[c];
+            if (c >= p.walk.list_begin && c < p.walk.list_end) lsz = sz;
+        }
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long a = __shfl_up_sync(0xFFFFFFFFu, sz, off), b = __shfl_up_sync(0xFFFFFFFFu, lsz, off);
+            if (lane >= static_cast<uint32_t>(off)) { sz += a; lsz += b; }
+        }
+        const bool cond = lane < nvalid && chosen + lane + 1 >= p.walk.nprobe && reach + sz >= p.walk.k;
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, cond);
+        const uint32_t take = m ? static_cast<uint32_t>(__ffs(m)) : nvalid;
+        if (lane < take) p.walk.probes[q * p.pitch + i] = c;
+        if (take > 0) {
+            reach += __shfl_sync(0xFFFFFFFFu, sz, take - 1);
+            local += __shfl_sync(0xFFFFFFFFu, lsz, take - 1);
+        }
+        chosen += take;
+        if (m) { done = true; break; }
+        if (nvalid < 32) break;
+    }
+    if (lane == 0) {
+        if (!done && chosen < p.nlist) atomicExch(p.walk.overflow, 1u);
+        p.walk.n_probes[q] = chosen;
+        atomicAdd(p.walk.stat_scanned, reach);
+        atomicAdd(p.walk.stat_probed, static_cast<unsigned long long>(chosen));
+        atomicAdd(p.walk.stat_probed + 1, local);
     }
 }
 
@@ -1392,7 +1444,7 @@ static int launch_coarse_select(const tc::CoarseSelectParams& c, cudaStream_t s)
 
 // Ranked prefix of the centroid table for every query: d_ranked[nq][pitch] ascending (distance, cell) keys, sentinels
 // where a rank could not be certified.
-int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint64_t nq, uint32_t pitch, uint64_t* d_ranked, cudaStream_t s) {
+int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint64_t nq, uint32_t pitch, uint64_t* d_ranked, cudaStream_t s, const CoarseWalk* walk) {
     TcState* st = ix->tc_coarse;
     const uint32_t kp = st->kp_elems;
     const uint32_t nq_pad = static_cast<uint32_t>(round_up<uint64_t>(nq, tc::BM));
@@ -1473,6 +1525,7 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     if (glimit) { c.gmin = st->dense_gm.as<float>(); c.glimit = glimit; c.staged_words = st->n_pad / 8; c.blocked = p.dense_blocked; }
     c.queries = d_route; c.q_ld = route_ld; c.centroids = ix->d_centroids; c.c_ld = ix->cent_ld; c.centroid_norms = ix->d_centroid_norms;
     c.dim = ix->dim; c.eps = tc_cert_eps(ix, st->kind, kp, 2, false); c.cnorm_max = ix->tc_cnorm_max; c.ranked = d_ranked;
+    if (walk != nullptr) { c.do_walk = 1; c.walk = *walk; }
     if (ix->metric == ANNB_L2) ANNB_TRY(launch_coarse_select<MET_L2>(c, s));
     else if (ix->dtype == ANNB_SQ8) ANNB_TRY(launch_coarse_select<MET_COS_PRENORM>(c, s));
     else ANNB_TRY(launch_coarse_select<MET_COS>(c, s));

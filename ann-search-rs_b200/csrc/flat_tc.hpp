@@ -48,7 +48,21 @@ int tc_stream_scan(annb_index* ix, const StreamScanArgs& a, cudaStream_t s);
 int tc_coarse_prepare(annb_index* ix);
 void tc_coarse_destroy(annb_index* ix);
 bool tc_coarse_supported(const annb_index* ix);
-int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint64_t nq, uint32_t pitch, uint64_t* d_ranked, cudaStream_t s);
+// Probe expansion fused into the select (select_probed_clusters, src/utils/k_means_utils.rs:3007-3029; the rule of probe_walk_kernel):
+// with `walk` the select's warp walks its own certified prefix and writes the probe list -- d_ranked is then not written at all.
+struct CoarseWalk {
+    const uint64_t* offsets;           // [nlist + 1] global list offsets
+    uint32_t nprobe;
+    uint64_t k;
+    uint32_t* probes;                  // [nq][pitch]
+    uint32_t* n_probes;                // [nq]
+    uint32_t* overflow;                // set to 1 when a query's prefix ends before the rule is satisfied
+    unsigned long long* stat_scanned;  // sum over queries of reachable vectors
+    unsigned long long* stat_probed;   // [0] probed cells, [1] reachable vectors of this shard's lists
+    uint32_t list_begin, list_end;
+};
+int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint64_t nq, uint32_t pitch, uint64_t* d_ranked, cudaStream_t s,
+                   const CoarseWalk* walk = nullptr);
 // Build-side assignment (assign_all_parallel) on the tensor path: the centroid table searched like a flat f32 index with
 // k' = 16, exact scores of the survivors in the reference's arithmetic, certificate; uncertified rows are listed for the
 // exact CUDA-core kernel.  tc_assign_create leaves *out == nullptr for shapes it does not cover.

@@ -129,6 +129,7 @@ struct annb_index {
     annb::StreamState* tc_stream = nullptr;
     int opt_ivf_coarse_stage = 0;         // tensor-core centroid ranking: stage each query's value row in shared memory (measured slower, off)
     int opt_ivf_coarse_gm = 1;            // tensor-core centroid ranking: select from the dense kernel's group minima (coarse_select_gm_kernel)
+    int opt_ivf_coarse_walk = 1;          // tensor-core centroid ranking: probe expansion inside the select kernel (0: separate probe_walk_kernel)
     int opt_ivf_coarse_blocked = 1;       // ... with the dense matrix in the blocked layout (coalesced epilogue stores); 0: row-major
     int opt_ivf_coarse_fp16 = 1;          // tensor-core centroid ranking: 3xFP16 operands (0: 3xTF32); read once, when the index is created
     int opt_ivf_stream = 1;               // query-major list scan: 1 = TMA-ring streaming kernel (ivf_stream.cu), 0 = cp.async kernel
