@@ -1876,6 +1876,7 @@ int annb_index_set_option(annb_index* ix, const char* key, int64_t value) {
     else if (k == "ivf_stream") ix->opt_ivf_stream = static_cast<int>(value);
     else if (k == "ivf_coarse_stage") ix->opt_ivf_coarse_stage = static_cast<int>(value);
     else if (k == "ivf_coarse_gm") ix->opt_ivf_coarse_gm = static_cast<int>(value);
+    else if (k == "ivf_task_prefetch") ix->opt_ivf_task_prefetch = static_cast<int>(value);
     else if (k == "ivf_coarse_walk") ix->opt_ivf_coarse_walk = static_cast<int>(value);
     else if (k == "ivf_coarse_blocked") ix->opt_ivf_coarse_blocked = static_cast<int>(value);
     else if (k == "ivf_coarse_fp16") {

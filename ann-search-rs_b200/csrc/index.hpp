@@ -128,6 +128,7 @@ struct annb_index {
     annb::IvfTcState* tc_ivf = nullptr;
     annb::StreamState* tc_stream = nullptr;
     int opt_ivf_coarse_stage = 0;         // tensor-core centroid ranking: stage each query's value row in shared memory (measured slower, off)
+    int opt_ivf_task_prefetch = 1;        // IVF tensor scan: next task claimed / fetched by the producer lane a few tiles before the current one ends
     int opt_ivf_coarse_gm = 1;            // tensor-core centroid ranking: select from the dense kernel's group minima (coarse_select_gm_kernel)
     int opt_ivf_coarse_walk = 1;          // tensor-core centroid ranking: probe expansion inside the select kernel (0: separate probe_walk_kernel)
     int opt_ivf_coarse_blocked = 1;       // ... with the dense matrix in the blocked layout (coalesced epilogue stores); 0: row-major

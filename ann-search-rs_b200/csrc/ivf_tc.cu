@@ -43,6 +43,7 @@ struct IvfTcParams {
     const uint2* pairs;        // (query, rank) grouped by list
     const uint4* tasks;        // [2 * n_tasks] task records written by ivf_pair_offsets_kernel
     uint32_t* task_counter;
+    uint32_t prefetch_task;    // 1: the producer lane claims / fetches the next task during the last tiles of the current one
     uint32_t probe_pitch;
     uint32_t bf16_terms;       // bf16 lists: bf16 terms of the f32 query (2 or 3)
     uint64_t* part_keys;       // [nq][probe_pitch][2][KP]
@@ -133,13 +134,25 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     const bool dbg_on = TC_COUNTERS && p.dbg != nullptr && blockIdx.x == 0;
     long long c_sched = 0, c_gather = 0, c_tfull = 0, c_wq = 0, c_wdata = 0, c_wtempty = 0, c_tasks = 0, c_tiles = 0;
     const long long c_start = tc_clock();
+    // Thread 0 (the TMA producer's issuing lane) claims and fetches the NEXT task while it streams the last tiles of the current one:
+    // the claim (an atomic on the shared counter) a few tiles before the end, the record two tiles before the end -- under the scan's
+    // own memory traffic each of the two dependent round trips takes microseconds, which used to sit between two CTA barriers with
+    // every role idle (19 % of the kernel).  Claiming a handful of tiles early, not a whole task early, keeps the tail of the dynamic
+    // schedule as short as before.
+    // The record travels by cp.async into a spare shared-memory slot: no registers are held for it across the task.
+    uint32_t nx_task = 0, nx_state = 0;            // 0: nothing in flight, 1: next task claimed, 2: ... and its record requested
+    uint4* s_next = reinterpret_cast<uint4*>(s_tail + 448);   // [2]
     for (;;) {
         __syncthreads();   // every role has finished the previous task (TMEM query region and s_task are reusable)
         const long long c_t0 = tc_clock();
         if (threadIdx.x == 0) {
-            const uint32_t task = atomicAdd(p.task_counter, 1u);
+            if (nx_state == 0) nx_task = atomicAdd(p.task_counter, 1u);
+            const uint32_t task = nx_task;
             if (task < total_tasks) {
-                const uint4 a = __ldg(p.tasks + 2 * static_cast<size_t>(task)), b = __ldg(p.tasks + 2 * static_cast<size_t>(task) + 1);
+                uint4 a, b;
+                if (nx_state == 2) { cp_async_wait<0>(); a = s_next[0]; b = s_next[1]; }
+                else { a = __ldg(p.tasks + 2 * static_cast<size_t>(task)); b = __ldg(p.tasks + 2 * static_cast<size_t>(task) + 1); }
+                nx_state = 0;
                 s_task[0] = a.x;
                 s_task[1] = a.y;
                 s_task[2] = a.z;
@@ -161,7 +174,17 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
         if (warp == 0) {
             // ================================================================= TMA producer
             if (lane == 0) {
+                const uint32_t claim_at = (p.prefetch_task && n_tiles > 6) ? n_tiles - 6 : 0u, fetch_at = n_tiles > 2 ? n_tiles - 2 : n_tiles - 1;
                 for (uint32_t t = 0; t < n_tiles; t++) {
+                    if (p.prefetch_task) {
+                        if (t == claim_at) { nx_task = atomicAdd(p.task_counter, 1u); nx_state = 1; }
+                        if (t == fetch_at && nx_state == 1 && nx_task < total_tasks) {
+                            cp_async16(s_next, p.tasks + 2 * static_cast<size_t>(nx_task));
+                            cp_async16(s_next + 1, p.tasks + 2 * static_cast<size_t>(nx_task) + 1);
+                            cp_async_commit();
+                            nx_state = 2;
+                        }
+                    }
                     const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
                     for (uint32_t s = 0; s < p.nslab; s++, it++) {
                         const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
@@ -629,7 +652,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
     p.q_op = st->q_op.p; p.nq = nq; p.bf16_terms = bf16_terms; p.lo_smem = lo_s ? 1u : 0u; p.aux2 = st->d_aux2; p.q_inv_scale = st->q_scale.as<float>();
     p.queries = d_q; p.q_bytes = q_bytes; p.dim = ix->dim; p.nslab = st->nslab; p.n_stages = stages; p.n_pad = st->n_pad; p.aux = st->d_aux;
     p.offsets = ix->d_offsets; p.shard_row0 = ix->shard_row0; p.nlist = ix->nlist; p.pair_off = d_pair_off; p.task_off = d_task_off;
-    p.pairs = static_cast<const uint2*>(d_pairs); p.tasks = static_cast<const uint4*>(d_tasks); p.task_counter = d_task_counter; p.probe_pitch = probe_pitch;
+    p.pairs = static_cast<const uint2*>(d_pairs); p.tasks = static_cast<const uint4*>(d_tasks); p.task_counter = d_task_counter; p.probe_pitch = probe_pitch; p.prefetch_task = ix->opt_ivf_task_prefetch ? 1u : 0u;
     p.part_keys = st->part.as<uint64_t>(); p.gtau = st->gtau.as<uint32_t>(); p.dbg = st->dbgc.as<unsigned long long>();
     const uint32_t grid = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(max_tasks, 1), 148));
     {
