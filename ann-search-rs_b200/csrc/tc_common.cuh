@@ -571,9 +571,13 @@ __global__ void __launch_bounds__(128) rerank_kernel(RerankParams p) {
         const uint32_t thr = p.gtau[q];
         if (threadIdx.x == 0) s_n = 0;
         __syncthreads();
-        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) {
-            const uint64_t key = src[i];
-            if (key != KEY_SENTINEL && static_cast<uint32_t>(key >> 32) <= thr) keys[atomicAdd(&s_n, 1u)] = key;
+        for (uint32_t i0 = threadIdx.x; i0 < total; i0 += 4 * blockDim.x) {   // four loads in flight per thread: one round trip per 512 slots
+            uint64_t kk[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) { const uint32_t i = i0 + j * blockDim.x; kk[j] = i < total ? __ldg(src + i) : KEY_SENTINEL; }
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (kk[j] != KEY_SENTINEL && static_cast<uint32_t>(kk[j] >> 32) <= thr) keys[atomicAdd(&s_n, 1u)] = kk[j];
         }
         __syncthreads();
         const uint32_t n = s_n;
