@@ -4,7 +4,8 @@
 //
 // Replaces, for the flat f32 / bf16 / SQ8 indices, the reference's distance-matrix kernels + separate top-k pass
 // (src/gpu/dist_gpu.rs:79-488 euclidean/cosine_tiled{,_reg}; :553-613 extract_topk; src/gpu/topk_gpu.rs:992-1237), and with
-// DENSE + coarse_select_kernel the centroid ranking of the IVF query (src/cpu/ivf.rs:349-365).
+// DENSE + coarse_select_gm_kernel / coarse_select_kernel the centroid ranking and probe expansion of the IVF query
+// (src/cpu/ivf.rs:349-365, src/utils/k_means_utils.rs:3007-3029).
 //
 // Kernel shape (one CTA = 128 queries x one database split, 320 threads, 1 CTA / SM):
 //   warp 0      TMA producer: a ring of database K-slabs (128 rows x 128 B, SWIZZLE_128B)
@@ -13,7 +14,7 @@
 //               mode), then per tile tcgen05.ld 64 columns, v = fma(s, -2, |x|^2) or s * (-1/|x|) with the row constants
 //               from a warp-private shared-memory row, min-tree + threshold test; a value that beats the threshold is
 //               inserted into a register-resident sorted k' list (select_from_tile)
-//   f32 index : 3xTF32 split precision  s = Qhi.Xhi + Qlo.Xhi + Qhi.Xlo   (kind::tf32, hi/lo rounded with cvt.rna)
+//   f32 index : 3xFP16 (rows scaled by powers of two, kind::f16) or 3xTF32 split precision  s = Qhi.Xhi + Qlo.Xhi + Qhi.Xlo   (hi/lo rounded to nearest)
 //   bf16 index: f32 queries split into three bf16 terms, s = (q0 + q1 + q2).X  (kind::f16), X = the stored bf16 rows
 //   SQ8 index : int8 codes x int8 codes, s32 accumulators (kind::i8): exact integer dots, three accumulator stages
 #include <cuda.h>
@@ -35,7 +36,7 @@ namespace tc {
 // TS = the query operand lives in TMEM (columns [0, 256): hi then lo) instead of shared memory: the MMAs read only the
 // database slab from shared memory (half the operand bandwidth) and the whole 227 KB becomes database ring.
 // DENSE = write every selection value to p.dense instead of keeping a top-k' (the IVF centroid ranking consumes the full
-// [nq x nlist] matrix of approximate values; see coarse_select_kernel).
+// [nq x nlist] matrix of approximate values and, optionally, the minima of its aligned groups of 8; see coarse_select_gm_kernel).
 __device__ __forceinline__ bool hyb_cfg(const Params& p) { return p.hybrid != 0; }
 
 // EW = epilogue warps per TMEM lane quarter (2 or 4): every warp owns 128 / EW columns of each tile.  The kernels whose
