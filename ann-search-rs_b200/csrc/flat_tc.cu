@@ -281,6 +281,11 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         if (RX && n_tiles > 0) { rx_lo_next = __ldg(rx_half); if (NV > 32) rx_hi_next = __ldg(rx_half + 32); }
         float cq = 1.0f;
         if (KIND == KIND_F16X3) cq = __ldg(p.q_inv_scale + q0 + row_in_tile) * ((MET == MET_L2) ? -2.0f : 1.0f);
+        // 3xFP16 cosine: cq is a positive power of two, so w = v / cq orders exactly like v and converts back without rounding.  The
+        // candidate list and the threshold test run on w = s * aux -- one multiply per value instead of two on the per-tile chain --
+        // and values cross into the common domain (shared threshold, emitted keys) through exact multiplications by cq / its inverse.
+        constexpr bool WDOM = (KIND == KIND_F16X3) && (MET != MET_L2) && !DENSE;
+        const float inv_cq = WDOM ? 1.0f / cq : 1.0f;
         for (uint32_t t = 0; t < n_tiles; t++) {
             const uint32_t acc = t % NACC, aph = (t / NACC) & 1u;
             const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * tile_step * BN;
@@ -303,7 +308,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             __syncwarp();
             mbar_wait_timed(bar_tfull + acc, aph, w_tfull);
             tc_fence_after();
-            const float g_tau = ordered_to_f32(g_bits);       // NaN (all-ones init) is ignored by fminf
+            const float g_tau = WDOM ? ordered_to_f32(g_bits) * inv_cq : ordered_to_f32(g_bits);       // NaN (all-ones init) is ignored by fminf
             float tau = fminf(top.tau(), g_tau);
             const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + ACC_COL0 + acc * BN;
             {
@@ -325,7 +330,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                         const int col = g * 8 + j;   // compile-time after unrolling
                         const float cst = s_aux[col];
                         const float sdot = (KIND == KIND_I8) ? __int2float_rn(static_cast<int32_t>(r[col])) : __uint_as_float(r[col]);   // s32 dots are exact in f32 (< 2^24)
-                        if (KIND == KIND_F16X3) v[col] = (MET == MET_L2) ? fmaf(sdot * s_rx[col], cq, cst) : (sdot * cst) * cq;
+                        if (KIND == KIND_F16X3) v[col] = (MET == MET_L2) ? fmaf(sdot * s_rx[col], cq, cst) : (WDOM ? sdot * cst : (sdot * cst) * cq);
                         else v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
                         mg = fminf(mg, v[g * 8 + j]);
                     }
@@ -356,7 +361,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 }
                 if (p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && t == 0) {
 #pragma unroll
-                    for (int j = 0; j < NV; j++) p.dbg[row_in_tile * BN + c * NV + j] = v[j];
+                    for (int j = 0; j < NV; j++) p.dbg[row_in_tile * BN + c * NV + j] = WDOM ? v[j] * cq : v[j];
                 }
                 if (m < tau) {
                     const long long ts0 = tc_clock();
@@ -364,15 +369,15 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                     w_slow += tc_clock() - ts0;
                 }
             }
-            if (share_tau && (top.tau() < g_tau || (g_tau != g_tau && top.tau() < INFINITY))) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));
+            if (share_tau && (top.tau() < g_tau || (g_tau != g_tau && top.tau() < INFINITY))) atomicMin(gtau_ptr, f32_to_ordered(WDOM ? top.tau() * cq : top.tau()));
         }
-        if (!DENSE && !share_tau && top.tau() < INFINITY) atomicMin(gtau_ptr, f32_to_ordered(top.tau()));   // wide-k: this list's final threshold
+        if (!DENSE && !share_tau && top.tau() < INFINITY) atomicMin(gtau_ptr, f32_to_ordered(WDOM ? top.tau() * cq : top.tau()));   // wide-k: this list's final threshold
         if (TC_COUNTERS && p.dbg_cycles && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 64) { p.dbg_cycles[4] = w_tfull; p.dbg_cycles[5] = w_slow; }
         const uint64_t q = static_cast<uint64_t>(q0) + row_in_tile;
         if (!DENSE && q < p.nq) {
             uint64_t* out = p.part_keys + (q * (EW * p.n_splits) + EW * blockIdx.y + half) * KP;
 #pragma unroll
-            for (int j = 0; j < KP; j++) out[j] = (top.i[j] == IDX_INVALID) ? KEY_SENTINEL : make_key(top.v[j], top.i[j]);
+            for (int j = 0; j < KP; j++) out[j] = (top.i[j] == IDX_INVALID) ? KEY_SENTINEL : make_key(WDOM ? top.v[j] * cq : top.v[j], top.i[j]);
         }
     }
     tc_fence_before();
