@@ -267,11 +267,16 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         // Per-column constants of this warp's 64-column half: lane l fetches columns l and l + 32 (coalesced, one tile
         // ahead) and parks them in a warp-private shared-memory row; the value loop reads them back as 128-bit broadcast
         // loads (16 per tile instead of 64 shuffles).  No CTA-wide barrier: only __syncwarp.
+        // UNIT (flat f32 index, cosine, 3xFP16): the database operand holds the rows divided by their index norm (uniform scale 2^13;
+        // pad rows and zero-norm rows carry a NaN, which min / compare ignore exactly as the NaN row constant used to) and the query
+        // operand is negated, so the accumulator IS the selection value up to the query's power-of-two scale: no per-column constant,
+        // no multiply, no staging of constants on the per-tile chain.
+        constexpr bool UNIT = (KIND == KIND_F16X3) && (MET != MET_L2) && !DENSE;
         float* s_aux = s_aux_all + (warp - 2) * NV;
         const float* aux_half = p.aux + r_begin + half * NV + lane;
         const size_t aux_step = static_cast<size_t>(tile_step) * BN;
         float aux_lo_next = 0.f, aux_hi_next = 0.f;
-        if (n_tiles > 0) { aux_lo_next = __ldg(aux_half); if (NV > 32) aux_hi_next = __ldg(aux_half + 32); }
+        if (!UNIT && n_tiles > 0) { aux_lo_next = __ldg(aux_half); if (NV > 32) aux_hi_next = __ldg(aux_half + 32); }
         // 3xFP16: operands were scaled per row by powers of two.  L2 needs the row's inverse scale as a second per-column constant
         // (v = |x|^2 - 2 s / (sq sx)); cosine folds it into its only one (v = s * (-1 / (|x| sx)) / sq).  cq: the query's share.
         constexpr bool RX = (KIND == KIND_F16X3) && (MET == MET_L2);
@@ -280,7 +285,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         float rx_lo_next = 1.f, rx_hi_next = 1.f;
         if (RX && n_tiles > 0) { rx_lo_next = __ldg(rx_half); if (NV > 32) rx_hi_next = __ldg(rx_half + 32); }
         float cq = 1.0f;
-        if (KIND == KIND_F16X3) cq = __ldg(p.q_inv_scale + q0 + row_in_tile) * ((MET == MET_L2) ? -2.0f : 1.0f);
+        if (KIND == KIND_F16X3) cq = __ldg(p.q_inv_scale + q0 + row_in_tile) * ((MET == MET_L2) ? -2.0f : (UNIT ? 1.0f / 8192.0f : 1.0f));
         // 3xFP16 cosine: cq is a positive power of two, so w = v / cq orders exactly like v and converts back without rounding.  The
         // candidate list and the threshold test run on w = s * aux -- one multiply per value instead of two on the per-tile chain --
         // and values cross into the common domain (shared threshold, emitted keys) through exact multiplications by cq / its inverse.
@@ -293,19 +298,23 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             const float aux_lo = aux_lo_next, aux_hi = aux_hi_next;
             const float rx_lo = rx_lo_next, rx_hi = rx_hi_next;
             if (t + 1 < n_tiles) {   // prefetch for the next tile: latency hidden behind this tile's work
-                aux_lo_next = __ldg(aux_half + static_cast<size_t>(t + 1) * aux_step);
-                if (NV > 32) aux_hi_next = __ldg(aux_half + static_cast<size_t>(t + 1) * aux_step + 32);
+                if (!UNIT) {
+                    aux_lo_next = __ldg(aux_half + static_cast<size_t>(t + 1) * aux_step);
+                    if (NV > 32) aux_hi_next = __ldg(aux_half + static_cast<size_t>(t + 1) * aux_step + 32);
+                }
                 if (RX) {
                     rx_lo_next = __ldg(rx_half + static_cast<size_t>(t + 1) * aux_step);
                     if (NV > 32) rx_hi_next = __ldg(rx_half + static_cast<size_t>(t + 1) * aux_step + 32);
                 }
                 if (share_tau) g_next = *reinterpret_cast<volatile uint32_t*>(gtau_ptr);
             }
-            __syncwarp();                      // every lane is done with the previous tile's constants
-            s_aux[lane] = aux_lo;
-            if (NV > 32) s_aux[lane + 32] = aux_hi;
-            if (RX) { s_rx[lane] = rx_lo; if (NV > 32) s_rx[lane + 32] = rx_hi; }
-            __syncwarp();
+            if (!UNIT) {
+                __syncwarp();                      // every lane is done with the previous tile's constants
+                s_aux[lane] = aux_lo;
+                if (NV > 32) s_aux[lane + 32] = aux_hi;
+                if (RX) { s_rx[lane] = rx_lo; if (NV > 32) s_rx[lane + 32] = rx_hi; }
+                __syncwarp();
+            }
             mbar_wait_timed(bar_tfull + acc, aph, w_tfull);
             tc_fence_after();
             const float g_tau = WDOM ? ordered_to_f32(g_bits) * inv_cq : ordered_to_f32(g_bits);       // NaN (all-ones init) is ignored by fminf
@@ -328,9 +337,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const int col = g * 8 + j;   // compile-time after unrolling
-                        const float cst = s_aux[col];
+                        const float cst = UNIT ? 0.0f : s_aux[col];
                         const float sdot = (KIND == KIND_I8) ? __int2float_rn(static_cast<int32_t>(r[col])) : __uint_as_float(r[col]);   // s32 dots are exact in f32 (< 2^24)
-                        if (KIND == KIND_F16X3) v[col] = (MET == MET_L2) ? fmaf(sdot * s_rx[col], cq, cst) : (WDOM ? sdot * cst : (sdot * cst) * cq);
+                        if (UNIT) v[col] = sdot;
+                        else if (KIND == KIND_F16X3) v[col] = (MET == MET_L2) ? fmaf(sdot * s_rx[col], cq, cst) : (WDOM ? sdot * cst : (sdot * cst) * cq);
                         else v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
                         mg = fminf(mg, v[g * 8 + j]);
                     }
@@ -1050,10 +1060,12 @@ int tc_flat_prepare(annb_index* ix) {
         if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
         st->bytes += bytes + aux_rows * sizeof(float);
         tc::fill_aux_kernel<<<static_cast<uint32_t>((aux_rows + 127) / 128), 128, 0, s>>>(st->d_aux2, aux_rows, aux_rows, 1.0f);
-        tc::split_f16_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * 32), 256, 0, s>>>(reinterpret_cast<const float*>(ix->d_rows), ix->row_bytes / 4, ix->dim, ix->n,
-                                                                                            st->n_pad, kp, static_cast<__half*>(st->d_x), st->d_aux2);
-        if (ix->metric == ANNB_COSINE)     // cosine: one constant per row, -1 / (|x| * scale); L2 keeps |x|^2 and reads the inverse scale separately
-            tc::mul_rows_kernel<<<static_cast<uint32_t>((static_cast<uint64_t>(st->n_pad) + 127) / 128), 128, 0, s>>>(st->d_aux, st->d_aux2, st->n_pad);
+        if (ix->metric == ANNB_COSINE)     // cosine: unit rows at a uniform scale, no per-row constant at all (flat_tc_kernel, UNIT; the aux arrays stay unused)
+            tc::split_f16_unit_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * 32), 256, 0, s>>>(reinterpret_cast<const float*>(ix->d_rows), ix->row_bytes / 4, ix->dim,
+                                                                                                     ix->n, st->n_pad, kp, ix->d_norms, static_cast<__half*>(st->d_x));
+        else                               // L2 keeps |x|^2 and reads the row's inverse power-of-two scale as a second constant
+            tc::split_f16_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * 32), 256, 0, s>>>(reinterpret_cast<const float*>(ix->d_rows), ix->row_bytes / 4, ix->dim, ix->n,
+                                                                                                st->n_pad, kp, static_cast<__half*>(st->d_x), st->d_aux2);
         ANNB_CUDA_CHECK(cudaGetLastError());
         xbase = st->d_x;
         xrows = 2ull * st->n_pad;
@@ -1136,6 +1148,7 @@ float tc_cert_eps(const annb_index* ix, int kind, uint32_t kp_elems, uint32_t te
         // half the accumulating MMAs per row (16 elements per K step)
         const double n_mma = 3.0 * (kp_elems / 16);
         E = 3.0 * std::ldexp(1.0, -22) + TC_MMA_ULPS * n_mma * u23;
+        if (!l2 && !ix->is_ivf) E += 2.0 * u24;     // flat cosine operand: rows divided by their norm in f32 (split_f16_unit_kernel)
     } else if (kind == tc::KIND_TF32X3) {
         const double n_mma = 3.0 * (kp_elems / 8);
         // flat: q and x both split with cvt.rna (2^-22 residual each) + dropped lo.lo (2^-22); IVF in-kernel split: x hi
@@ -1258,7 +1271,8 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     if (kind == tc::KIND_F16X3) {
         ANNB_TRY(st->q_scale.ensure(static_cast<uint64_t>(nq_pad) * 4));
         tc::split_f16_kernel<<<tc_blocks_for(static_cast<uint64_t>(nq_pad) * 32), 256, 0, s>>>(reinterpret_cast<const float*>(d_q), q_bytes / 4, ix->dim, nq, nq_pad, kp,
-                                                                                            st->q_op.as<__half>(), st->q_scale.as<float>());
+                                                                                            st->q_op.as<__half>(), st->q_scale.as<float>(),
+                                                                                            ix->metric == ANNB_COSINE ? -1.0f : 1.0f);   // cosine (UNIT): the accumulator is -q.x/|x| itself
     } else if (kind == tc::KIND_I8) {
         tc::pad_i8_kernel<<<tc_blocks_for(static_cast<uint64_t>(nq_pad) * kp), 256, 0, s>>>(reinterpret_cast<const int8_t*>(d_q), q_bytes, ix->dim, nq, nq_pad, kp,
                                                                                          st->q_op.as<int8_t>());

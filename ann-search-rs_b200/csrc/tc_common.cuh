@@ -361,7 +361,7 @@ static __global__ void split_tf32_kernel(const float* __restrict__ src, uint32_t
 // which is all the certificate's error model uses.  Scales are powers of two: applying and undoing them is exact.
 // One warp per row.
 static __global__ void split_f16_kernel(const float* __restrict__ src, uint32_t ld_src, uint32_t dim, uint64_t rows, uint64_t rows_pad, uint32_t kp,
-                                        __half* __restrict__ dst, float* __restrict__ inv_scale) {
+                                        __half* __restrict__ dst, float* __restrict__ inv_scale, float sign = 1.0f) {   // sign = -1: the negated rows (exact)
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t total = rows_pad * kp;
     for (uint64_t r = blockIdx.x * static_cast<uint64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows_pad; r += static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5)) {
@@ -380,7 +380,7 @@ static __global__ void split_f16_kernel(const float* __restrict__ src, uint32_t 
         for (uint32_t c = lane; c < kp; c += 32) {
             __half h = __float2half_rn(0.f), l = h;
             if (r < rows && c < dim) {
-                const float xs = __fmul_rn(src[r * ld_src + c], scale);
+                const float xs = __fmul_rn(src[r * ld_src + c], scale * sign);
                 h = __float2half_rn(xs);
                 l = __float2half_rn(__fsub_rn(xs, __half2float(h)));
             }
@@ -388,6 +388,32 @@ static __global__ void split_f16_kernel(const float* __restrict__ src, uint32_t 
             dst[total + r * kp + c] = l;
         }
         if (lane == 0) inv_scale[r] = ldexpf(1.0f, -e);
+    }
+}
+// Database operand of the flat f32 cosine kernel (flat_tc_kernel, UNIT): every row divided by its index norm (one f32 division per
+// element: 2^-24 relative, budgeted in tc_cert_eps), times the uniform scale 2^13, as stacked fp16 hi / lo pieces.  Unit rows have
+// their largest element in [2^13 / sqrt(dim), 2^13]: hi never overflows and the pieces hold the row to far better than 2^-22 of
+// its norm, as the per-row scales of split_f16_kernel do for un-normalised rows.  Rows past `rows` (tile padding) and rows whose
+// norm is zero or not finite carry a NaN in the first element of the hi piece: their whole accumulator column is NaN, which the
+// epilogue's min tree and threshold test ignore -- the role of the NaN row constant in the other operand forms.  One warp per row.
+static __global__ void split_f16_unit_kernel(const float* __restrict__ src, uint32_t ld_src, uint32_t dim, uint64_t rows, uint64_t rows_pad, uint32_t kp,
+                                             const float* __restrict__ norms, __half* __restrict__ dst) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t total = rows_pad * kp;
+    for (uint64_t r = blockIdx.x * static_cast<uint64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows_pad; r += static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5)) {
+        const float nrm = r < rows ? norms[r] : 0.f;
+        const bool ok = nrm > 0.f && nrm < INFINITY;
+        for (uint32_t c = lane; c < kp; c += 32) {
+            __half h = __float2half_rn(0.f), l = h;
+            if (ok && c < dim) {
+                const float xs = __fmul_rn(__fdiv_rn(src[r * ld_src + c], nrm), 8192.0f);
+                h = __float2half_rn(xs);
+                l = __float2half_rn(__fsub_rn(xs, __half2float(h)));
+            }
+            if (!ok && c == 0) h = __ushort_as_half(static_cast<unsigned short>(0x7E00));   // quiet NaN
+            dst[r * kp + c] = h;
+            dst[total + r * kp + c] = l;
+        }
     }
 }
 // inv_scale[r] = 1 / (power-of-two scale that brings the largest element of row r into [2^13, 2^14)) -- the scale split_f16_kernel
