@@ -279,13 +279,13 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         if (!UNIT && n_tiles > 0) { aux_lo_next = __ldg(aux_half); if (NV > 32) aux_hi_next = __ldg(aux_half + 32); }
         // 3xFP16: operands were scaled per row by powers of two.  L2 needs the row's inverse scale as a second per-column constant
         // (v = |x|^2 - 2 s / (sq sx)); cosine folds it into its only one (v = s * (-1 / (|x| sx)) / sq).  cq: the query's share.
-        constexpr bool RX = (KIND == KIND_F16X3) && (MET == MET_L2);
+        constexpr bool RX = false;      // (L2 operands carry one uniform scale since the closing rework: nothing per column to undo)
         float* s_rx = s_aux_all + (4 * EW + (warp - 2)) * NV;           // second bank of warp-private rows
         const float* rx_half = RX ? p.aux2 + r_begin + half * NV + lane : nullptr;
         float rx_lo_next = 1.f, rx_hi_next = 1.f;
         if (RX && n_tiles > 0) { rx_lo_next = __ldg(rx_half); if (NV > 32) rx_hi_next = __ldg(rx_half + 32); }
         float cq = 1.0f;
-        if (KIND == KIND_F16X3) cq = __ldg(p.q_inv_scale + q0 + row_in_tile) * ((MET == MET_L2) ? -2.0f : (UNIT ? 1.0f / 8192.0f : 1.0f));
+        if (KIND == KIND_F16X3) cq = __ldg(p.q_inv_scale + q0 + row_in_tile) * ((MET == MET_L2) ? -2.0f * p.db_inv_scale : (UNIT ? 1.0f / 8192.0f : 1.0f));
         // 3xFP16 cosine: cq is a positive power of two, so w = v / cq orders exactly like v and converts back without rounding.  The
         // candidate list and the threshold test run on w = s * aux -- one multiply per value instead of two on the per-tile chain --
         // and values cross into the common domain (shared threshold, emitted keys) through exact multiplications by cq / its inverse.
@@ -340,7 +340,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                         const float cst = UNIT ? 0.0f : s_aux[col];
                         const float sdot = (KIND == KIND_I8) ? __int2float_rn(static_cast<int32_t>(r[col])) : __uint_as_float(r[col]);   // s32 dots are exact in f32 (< 2^24)
                         if (UNIT) v[col] = sdot;
-                        else if (KIND == KIND_F16X3) v[col] = (MET == MET_L2) ? fmaf(sdot * s_rx[col], cq, cst) : (WDOM ? sdot * cst : (sdot * cst) * cq);
+                        else if (KIND == KIND_F16X3) v[col] = (MET == MET_L2) ? fmaf(sdot, cq, cst) : (WDOM ? sdot * cst : (sdot * cst) * cq);
                         else v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
                         mg = fminf(mg, v[g * 8 + j]);
                     }
@@ -960,6 +960,7 @@ struct TcState {
     float* d_aux2 = nullptr;  // KIND_F16X3: [n_pad + BN] inverse operand scale of every row
     CUtensorMap tm_x;
     DevBuf q_op, part, dbg, gtau, dbgc, dense, dense_gm, q_scale;
+    float db_inv_scale = 1.0f;   // KIND_F16X3, L2: 1 / (uniform operand scale)
     uint64_t bytes = 0;
 };
 
@@ -1021,6 +1022,24 @@ static int tc_aux_norm_max(annb_index* ix, const float* d_aux, uint64_t n, float
     return ANNB_OK;
 }
 
+int tc_uniform_f16_scale(annb_index* ix, const float* d_values, uint64_t count, float* out_scale) {
+    uint32_t* d_bits = nullptr;
+    ANNB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&d_bits), 4));
+    ANNB_CUDA_CHECK(cudaMemsetAsync(d_bits, 0, 4, ix->stream));
+    tc::absmax_kernel<<<148 * 8, 256, 0, ix->stream>>>(d_values, count, d_bits);
+    uint32_t bits = 0;
+    cudaError_t e = cudaMemcpyAsync(&bits, d_bits, 4, cudaMemcpyDeviceToHost, ix->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+    cudaFree(d_bits);
+    ANNB_CUDA_CHECK(e);
+    float m;
+    std::memcpy(&m, &bits, 4);
+    int ex = 0, sh = 0;
+    if (m > 0.f) { (void)std::frexp(m, &ex); sh = std::min(std::max(14 - ex, -100), 100); }   // m = f 2^ex, f in [0.5, 1): m 2^sh in [2^13, 2^14)
+    *out_scale = std::ldexp(1.0f, sh);
+    return ANNB_OK;
+}
+
 int tc_flat_prepare(annb_index* ix) {
     if (ix->is_ivf) return ANNB_OK;
     int kind = ix->dtype == ANNB_F32 ? tc::KIND_TF32X3 : (ix->dtype == ANNB_BF16 ? tc::KIND_BF16 : tc::KIND_I8);
@@ -1063,9 +1082,13 @@ int tc_flat_prepare(annb_index* ix) {
         if (ix->metric == ANNB_COSINE)     // cosine: unit rows at a uniform scale, no per-row constant at all (flat_tc_kernel, UNIT; the aux arrays stay unused)
             tc::split_f16_unit_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * 32), 256, 0, s>>>(reinterpret_cast<const float*>(ix->d_rows), ix->row_bytes / 4, ix->dim,
                                                                                                      ix->n, st->n_pad, kp, ix->d_norms, static_cast<__half*>(st->d_x));
-        else                               // L2 keeps |x|^2 and reads the row's inverse power-of-two scale as a second constant
+        else {                             // L2 keeps |x|^2 as its per-row constant; one uniform scale for the whole operand
+            float sc = 1.0f;
+            ANNB_TRY(tc_uniform_f16_scale(ix, reinterpret_cast<const float*>(ix->d_rows), ix->n * static_cast<uint64_t>(ix->row_bytes / 4), &sc));
+            st->db_inv_scale = 1.0f / sc;
             tc::split_f16_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * 32), 256, 0, s>>>(reinterpret_cast<const float*>(ix->d_rows), ix->row_bytes / 4, ix->dim, ix->n,
-                                                                                                st->n_pad, kp, static_cast<__half*>(st->d_x), st->d_aux2);
+                                                                                                st->n_pad, kp, static_cast<__half*>(st->d_x), nullptr, 1.0f, sc);
+        }
         ANNB_CUDA_CHECK(cudaGetLastError());
         xbase = st->d_x;
         xrows = 2ull * st->n_pad;
@@ -1332,7 +1355,7 @@ int tc_flat_search(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, int qt,
     tc::Params p{};
     p.nq = nq; p.n_rows = ix->n; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
     p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = na; p.aux = st->d_aux; p.hybrid = hyb ? 1u : 0u;
-    p.aux2 = st->d_aux2; p.q_inv_scale = st->q_scale.as<float>();
+    p.aux2 = st->d_aux2; p.q_inv_scale = st->q_scale.as<float>(); p.db_inv_scale = st->db_inv_scale;
     p.lo_smem = lo_s ? 1u : 0u; p.stream_q = stream_q ? 1u : 0u; p.wide_k = wide_k ? 1u : 0u; p.strided = (wide_k || ix->opt_tc_strided != 0) ? 1u : 0u;
     p.part_keys = st->part.as<uint64_t>(); p.dbg = st->dbg.as<float>(); p.gtau = st->gtau.as<uint32_t>(); p.q_op = st->q_op.as<void>(); p.kp = kp; p.dbg_cycles = st->dbgc.as<unsigned long long>();
     {
@@ -1420,9 +1443,14 @@ int tc_coarse_prepare(annb_index* ix) {
         ANNB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&st->d_aux2), aux_rows * sizeof(float)));
         st->bytes += aux_rows * sizeof(float);
         tc::fill_aux_kernel<<<ag, 128, 0, s>>>(st->d_aux2, aux_rows, aux_rows, 1.0f);
+        float sc = 0.0f;                   // L2: one uniform scale for the table (0 = per-row scales, cosine)
+        if (ix->metric != ANNB_COSINE) {
+            ANNB_TRY(tc_uniform_f16_scale(ix, ix->d_centroids, static_cast<uint64_t>(ix->nlist) * ix->cent_ld, &sc));
+            st->db_inv_scale = 1.0f / sc;
+        }
         tc::split_f16_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * 32), 256, 0, s>>>(ix->d_centroids, ix->cent_ld, ix->dim, ix->nlist, st->n_pad, kp,
-                                                                                            static_cast<__half*>(st->d_x), st->d_aux2);
-        if (ix->metric == ANNB_COSINE)     // cosine: one constant per cell, -1 / (|c| * scale); L2 keeps |c|^2 and reads the inverse scale separately
+                                                                                            static_cast<__half*>(st->d_x), st->d_aux2, 1.0f, sc);
+        if (ix->metric == ANNB_COSINE)     // cosine: one constant per cell, -1 / (|c| * scale); L2 keeps |c|^2 beside the uniform scale
             tc::mul_rows_kernel<<<static_cast<uint32_t>((static_cast<uint64_t>(st->n_pad) + 127) / 128), 128, 0, s>>>(st->d_aux, st->d_aux2, st->n_pad);
     } else {
         tc::split_tf32_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * kp), 256, 0, s>>>(ix->d_centroids, ix->cent_ld, ix->dim, ix->nlist, st->n_pad, kp,
@@ -1495,7 +1523,7 @@ int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint
     p.nq = nq; p.n_rows = ix->nlist; p.nq_pad = nq_pad; p.n_pad = st->n_pad; p.nslab = st->nslab; p.n_stages = stages;
     p.n_splits = splits; p.rows_per_split = tiles_per * tc::BN; p.a_pieces = 2; p.aux = st->d_aux;
     p.q_op = st->q_op.as<void>(); p.kp = kp; p.dense = st->dense.as<float>(); p.dense_ld = st->n_pad;
-    p.aux2 = st->d_aux2; p.q_inv_scale = st->q_scale.as<float>();
+    p.aux2 = st->d_aux2; p.q_inv_scale = st->q_scale.as<float>(); p.db_inv_scale = st->db_inv_scale;
     // Select from group minima (coarse_select_gm_kernel) when the selected groups are expected to hold well under cmax cells at
     // or below the threshold: G groups carry about G (1 + 7 G / nlist) of them.
     const uint32_t cmax = next_pow2(pitch + 1);

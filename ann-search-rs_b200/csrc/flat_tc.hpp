@@ -61,6 +61,8 @@ struct CoarseWalk {
     unsigned long long* stat_probed;   // [0] probed cells, [1] reachable vectors of this shard's lists
     uint32_t list_begin, list_end;
 };
+// Uniform power-of-two scale of a 3xFP16 L2 database operand: the largest finite |element| of the `count` floats lands in [2^13, 2^14).
+int tc_uniform_f16_scale(annb_index* ix, const float* d_values, uint64_t count, float* out_scale);
 int tc_coarse_rank(annb_index* ix, const float* d_route, uint32_t route_ld, uint64_t nq, uint32_t pitch, uint64_t* d_ranked, cudaStream_t s,
                    const CoarseWalk* walk = nullptr);
 // Build-side assignment (assign_all_parallel) on the tensor path: the centroid table searched like a flat f32 index with

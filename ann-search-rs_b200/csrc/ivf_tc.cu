@@ -50,6 +50,7 @@ struct IvfTcParams {
     uint32_t* gtau;            // [nq] shared pruning threshold
     const float* aux2;         // KIND_F16X3: per stored row 1 / (its power-of-two operand scale)
     const float* q_inv_scale;  // KIND_F16X3: per query 1 / (its power-of-two operand scale), [nq]
+    float db_inv_scale;        // KIND_F16X3, L2: 1 / (the list operand's uniform power-of-two scale)
     uint32_t lo_smem;          // f32 lists with rows of 129 .. 256 elements: only the hi query piece fits TMEM beside two accumulator stages;
                                // the lo piece is gathered into shared memory (swizzled K slabs) and its term is an SS-mode MMA
     unsigned long long* dbg;   // optional [8]: CTA 0 cycle counters {total, schedule, gather, epi wait-tfull, mma wait-queries, mma wait-data, mma wait-tempty, tasks << 32 | tiles}
@@ -364,9 +365,9 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
             top.init();
             // 3xFP16: undo the operands' power-of-two scales -- per stored row (L2: second per-column constant; cosine: folded into aux)
             // and per query (cq)
-            constexpr bool RX = F16 && (MET == MET_L2);
+            constexpr bool RX = false;     // (L2 list operands carry one uniform scale: nothing per column to undo)
             float cq = 1.0f;
-            if (F16) cq = (has_query ? __ldg(p.q_inv_scale + pr.x) : 1.0f) * ((MET == MET_L2) ? -2.0f : 1.0f);
+            if (F16) cq = (has_query ? __ldg(p.q_inv_scale + pr.x) : 1.0f) * ((MET == MET_L2) ? -2.0f * p.db_inv_scale : 1.0f);
             uint32_t* gtau_ptr = p.gtau + (has_query ? pr.x : 0);
             uint32_t g_next = has_query ? *reinterpret_cast<volatile uint32_t*>(gtau_ptr) : 0u;   // 0 = ordered(-NaN): prunes everything
             const float* aux_half = p.aux + r_begin + half * 64 + lane;
@@ -420,7 +421,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                             const int col = g * 8 + j;
                             const float cst = s_aux[col];
                             const float sdot = (KIND == KIND_I8) ? __int2float_rn(static_cast<int32_t>(r[col])) : __uint_as_float(r[col]);
-                            if (F16) v[col] = (MET == MET_L2) ? fmaf(sdot * s_rx[col], cq, cst) : (sdot * cst) * cq;
+                            if (F16) v[col] = (MET == MET_L2) ? fmaf(sdot, cq, cst) : (sdot * cst) * cq;
                             else v[col] = (MET == MET_L2) ? fmaf(sdot, -2.0f, cst) : sdot * cst;
                             mg = fminf(mg, v[col]);
                         }
@@ -472,6 +473,7 @@ struct IvfTcState {
     void* d_x = nullptr;
     float* d_aux = nullptr;
     float* d_aux2 = nullptr;   // KIND_F16X3: inverse power-of-two operand scale of every stored row
+    float db_inv_scale = 1.0f; // KIND_F16X3, L2: 1 / (uniform operand scale)
     CUtensorMap tm_x;
     DevBuf part, gtau, dbgc, q_op, q_scale;
     uint64_t bytes = 0;
@@ -513,8 +515,13 @@ int tc_ivf_prepare(annb_index* ix) {
         e = cudaMalloc(&st->d_x, xbytes);
         if (e != cudaSuccess) { (void)cudaGetLastError(); set_last_error(std::string("cudaMalloc ivf tc operand: ") + cudaGetErrorString(e)); return ANNB_ERR_OUT_OF_MEMORY; }
         st->bytes += xbytes;
+        float sc = 0.0f;                   // L2: one uniform scale for the lists (0 = per-row scales, cosine)
+        if (ix->metric != ANNB_COSINE) {
+            ANNB_TRY(tc_uniform_f16_scale(ix, reinterpret_cast<const float*>(ix->d_rows), ix->n * static_cast<uint64_t>(ix->row_bytes / 4), &sc));
+            st->db_inv_scale = 1.0f / sc;
+        }
         tc::split_f16_kernel<<<tc_blocks_for(static_cast<uint64_t>(st->n_pad) * 32), 256, 0, s>>>(reinterpret_cast<const float*>(ix->d_rows), ix->row_bytes / 4, ix->dim, ix->n, st->n_pad, kp,
-                                                                                            static_cast<__half*>(st->d_x), st->d_aux2);
+                                                                                            static_cast<__half*>(st->d_x), st->d_aux2, 1.0f, sc);
         if (ix->metric == ANNB_COSINE) tc::mul_rows_kernel<<<static_cast<uint32_t>((ix->n + 127) / 128), 128, 0, s>>>(st->d_aux, st->d_aux2, ix->n);
         ANNB_CUDA_CHECK(cudaGetLastError());
     }
@@ -649,7 +656,7 @@ int tc_ivf_scan(annb_index* ix, const uint8_t* d_q, uint32_t q_bytes, uint64_t n
         ix->stat_launches++;
     }
     tc::IvfTcParams p{};
-    p.q_op = st->q_op.p; p.nq = nq; p.bf16_terms = bf16_terms; p.lo_smem = lo_s ? 1u : 0u; p.aux2 = st->d_aux2; p.q_inv_scale = st->q_scale.as<float>();
+    p.q_op = st->q_op.p; p.nq = nq; p.bf16_terms = bf16_terms; p.lo_smem = lo_s ? 1u : 0u; p.aux2 = st->d_aux2; p.q_inv_scale = st->q_scale.as<float>(); p.db_inv_scale = st->db_inv_scale;
     p.queries = d_q; p.q_bytes = q_bytes; p.dim = ix->dim; p.nslab = st->nslab; p.n_stages = stages; p.n_pad = st->n_pad; p.aux = st->d_aux;
     p.offsets = ix->d_offsets; p.shard_row0 = ix->shard_row0; p.nlist = ix->nlist; p.pair_off = d_pair_off; p.task_off = d_task_off;
     p.pairs = static_cast<const uint2*>(d_pairs); p.tasks = static_cast<const uint4*>(d_tasks); p.task_counter = d_task_counter; p.probe_pitch = probe_pitch; p.prefetch_task = ix->opt_ivf_task_prefetch ? 1u : 0u;

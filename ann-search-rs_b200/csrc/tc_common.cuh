@@ -43,7 +43,8 @@ struct Params {
     uint32_t strided;         // split y owns the tiles y, y + n_splits, ... (lists interleave over the database) instead of a contiguous range
     const float* aux;         // per database row: L2  v = aux - 2 s  (aux = |x|^2, pad rows +inf);
                               //                   cos v = s * aux    (aux = -1/|x|, pad rows +inf -> 0 * inf = NaN, never selected)
-    const float* aux2;        // KIND_F16X3, L2: per database row 1 / (its power-of-two operand scale); cosine folds it into aux
+    const float* aux2;        // (KIND_F16X3 operands with per-row scales, cosine: folded into aux; unused by the kernels)
+    float db_inv_scale;       // KIND_F16X3, L2: 1 / (the database operand's uniform power-of-two scale)
     const float* q_inv_scale; // KIND_F16X3: per query 1 / (its power-of-two operand scale), [nq_pad]
     uint64_t* part_keys;      // [nq][2 * n_splits][KPRIME] packed (approx value, row); one list per 64-column half
     const void* q_op;         // stacked query operand [a_pieces][nq_pad][kp] (TS mode loads it into TMEM)
@@ -360,8 +361,11 @@ static __global__ void split_tf32_kernel(const float* __restrict__ src, uint32_t
 // are off by at most 2^-25 against a row maximum of 2^13 -- far below the 2^-22 the split promises relative to the row NORM,
 // which is all the certificate's error model uses.  Scales are powers of two: applying and undoing them is exact.
 // One warp per row.
+// fixed_scale > 0: every row uses this power of two instead of its own (L2 database operands: the certificate's error model is
+// relative to the LARGEST row norm anyway, and a uniform scale leaves the epilogue without a per-column scale to undo; elements
+// far below the largest one go subnormal -- an absolute error of 2^-25 / scale, i.e. below 2^-38 of the largest element).
 static __global__ void split_f16_kernel(const float* __restrict__ src, uint32_t ld_src, uint32_t dim, uint64_t rows, uint64_t rows_pad, uint32_t kp,
-                                        __half* __restrict__ dst, float* __restrict__ inv_scale, float sign = 1.0f) {   // sign = -1: the negated rows (exact)
+                                        __half* __restrict__ dst, float* __restrict__ inv_scale, float sign = 1.0f, float fixed_scale = 0.0f) {   // sign = -1: the negated rows (exact)
     const uint32_t lane = threadIdx.x & 31u;
     const uint64_t total = rows_pad * kp;
     for (uint64_t r = blockIdx.x * static_cast<uint64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); r < rows_pad; r += static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5)) {
@@ -376,7 +380,7 @@ static __global__ void split_f16_kernel(const float* __restrict__ src, uint32_t 
             (void)frexpf(m, &ex);                 // m = f * 2^ex, f in [0.5, 1)
             e = min(max(14 - ex, -100), 100);     // m * 2^e in [2^13, 2^14)
         }
-        const float scale = ldexpf(1.0f, e);
+        const float scale = fixed_scale > 0.0f ? fixed_scale : ldexpf(1.0f, e);
         for (uint32_t c = lane; c < kp; c += 32) {
             __half h = __float2half_rn(0.f), l = h;
             if (r < rows && c < dim) {
@@ -387,8 +391,17 @@ static __global__ void split_f16_kernel(const float* __restrict__ src, uint32_t 
             dst[r * kp + c] = h;
             dst[total + r * kp + c] = l;
         }
-        if (lane == 0) inv_scale[r] = ldexpf(1.0f, -e);
+        if (lane == 0 && inv_scale != nullptr) inv_scale[r] = fixed_scale > 0.0f ? 1.0f / fixed_scale : ldexpf(1.0f, -e);
     }
+}
+// largest finite |value| of an f32 array (bit pattern; non-negative floats order like their bits)
+static __global__ void absmax_kernel(const float* __restrict__ p, uint64_t n, uint32_t* __restrict__ out_bits) {
+    uint32_t m = 0;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const float v = fabsf(p[i]);
+        if (v < INFINITY) m = max(m, __float_as_uint(v));
+    }
+    atomicMax(out_bits, m);
 }
 // Database operand of the flat f32 cosine kernel (flat_tc_kernel, UNIT): every row divided by its index norm (one f32 division per
 // element: 2^-24 relative, budgeted in tc_cert_eps), times the uniform scale 2^13, as stacked fp16 hi / lo pieces.  Unit rows have

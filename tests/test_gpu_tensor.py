@@ -237,7 +237,10 @@ def test_adversarial_certificate_same_sign_operands(gpu, dtype, metric):
     qn, xn = np.sqrt((q64 * q64).sum(1)), np.sqrt((x * x).sum(1))
     eps = g.cert_eps()
     if metric == "l2":
-        err = np.abs(v - ((x * x).sum(1)[None, :] - 2 * s)) / (qn[:, None] + xn[None, :]) ** 2
+        # f32 lists / rows go in as 3xFP16 pieces at ONE power-of-two scale for the whole index: their error is relative to the
+        # largest row norm, the quantity the L2 bound eps * (|q| + |x|max)^2 is stated in; bf16 rows are stored exactly
+        xs = np.full(128, np.sqrt((data.astype(np.float64) ** 2).sum(1)).max()) if dtype == "f32" else xn
+        err = np.abs(v - ((x * x).sum(1)[None, :] - 2 * s)) / (qn[:, None] + xs[None, :]) ** 2
     else:
         err = np.abs(v - (-s / c.norms[:128].astype(np.float64)[None, :])) / qn[:, None]
     print(f"\n[adversarial {dtype} {metric}] max selection-value error {err.max():.3e} = {err.max() / eps:.3f} of the certificate bound {eps:.3e}; "
@@ -358,8 +361,11 @@ def test_escalation_to_wide_mode_after_an_uncertified_batch(gpu):
 
 @pytest.mark.parametrize("metric", ["l2", "cosine"])
 def test_f32_operand_forms_agree(gpu, metric):
-    """3xFP16 (default: rows scaled by powers of two, fp16 hi + lo) and 3xTF32 pre-selection give the oracle's rows; data with a
-    wide dynamic range inside rows and across rows (the scaling must keep small rows and small elements accurate)."""
+    """3xFP16 (default: fp16 hi + lo of operands scaled by powers of two) and 3xTF32 pre-selection give the oracle's rows; data
+    with a wide dynamic range inside rows and across rows.  The selection values must stay inside the certificate's error model:
+    cosine operands are scaled row by row (unit rows), so their error is relative to |q| alone; L2 database operands carry ONE scale
+    for the whole index, so their error is relative to (|q| + |x|max)^2 with the LARGEST row norm -- the quantity the L2 bound is
+    stated in -- and rows far below it are exact only through the re-rank / fallback, which assert_exact checks."""
     rng = np.random.default_rng(71)
     base = datagen.correlated(30_000, 96, seed=71)
     row_scale = np.float32(10.0) ** rng.integers(-6, 7, base.shape[0]).astype(np.float32)            # |x| over 12 decades
@@ -385,7 +391,8 @@ def test_f32_operand_forms_agree(gpu, metric):
     s = q[:128].astype(np.float64) @ x.T
     qn, xn = np.sqrt((q[:128].astype(np.float64) ** 2).sum(1)), np.sqrt((x * x).sum(1))
     if metric == "l2":
-        err = np.abs(v - ((x * x).sum(1)[None, :] - 2 * s)) / (qn[:, None] + xn[None, :]) ** 2
+        xn_max = np.sqrt((data.astype(np.float64) ** 2).sum(1)).max()
+        err = np.abs(v - ((x * x).sum(1)[None, :] - 2 * s)) / (qn[:, None] + xn_max) ** 2
     else:
         err = np.abs(v - (-s / c.norms[:128].astype(np.float64)[None, :])) / qn[:, None]
     eps = g.cert_eps()
