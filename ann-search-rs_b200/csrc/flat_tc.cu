@@ -277,8 +277,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const size_t aux_step = static_cast<size_t>(tile_step) * BN;
         float aux_lo_next = 0.f, aux_hi_next = 0.f;
         if (!UNIT && n_tiles > 0) { aux_lo_next = __ldg(aux_half); if (NV > 32) aux_hi_next = __ldg(aux_half + 32); }
-        // 3xFP16: operands were scaled per row by powers of two.  L2 needs the row's inverse scale as a second per-column constant
-        // (v = |x|^2 - 2 s / (sq sx)); cosine folds it into its only one (v = s * (-1 / (|x| sx)) / sq).  cq: the query's share.
+        // 3xFP16: operands were scaled by powers of two -- queries per row (cq undoes it), the database per index for L2
+        // (v = |x|^2 - 2 s / (sq S): folded into cq as well) and per row for the cosine forms that keep a row constant
+        // (the DENSE centroid values: v = s * (-1 / (|c| sc)) / sq); the flat cosine operand needs nothing (UNIT, above).
         constexpr bool RX = false;      // (L2 operands carry one uniform scale since the closing rework: nothing per column to undo)
         float* s_rx = s_aux_all + (4 * EW + (warp - 2)) * NV;           // second bank of warp-private rows
         const float* rx_half = RX ? p.aux2 + r_begin + half * NV + lane : nullptr;

@@ -363,8 +363,8 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                 c_gather += tc_clock() - c_t1;
             }
             top.init();
-            // 3xFP16: undo the operands' power-of-two scales -- per stored row (L2: second per-column constant; cosine: folded into aux)
-            // and per query (cq)
+            // 3xFP16: undo the operands' power-of-two scales -- one per index for L2 lists and one per query, both in cq; cosine lists
+            // keep per-row scales folded into aux
             constexpr bool RX = false;     // (L2 list operands carry one uniform scale: nothing per column to undo)
             float cq = 1.0f;
             if (F16) cq = (has_query ? __ldg(p.q_inv_scale + pr.x) : 1.0f) * ((MET == MET_L2) ? -2.0f * p.db_inv_scale : 1.0f);
