@@ -134,12 +134,11 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
                 for (uint32_t s = 0; s < p.nslab; s++)
                     tma_load_2d(smem_u32(s_q + static_cast<size_t>(s) * SLAB_TILE), &tm_q, bar_q2, s * SLAB_ELEMS, piece * p.nq_pad + q0);
             }
-            uint32_t it = 0;
+            uint32_t stage = 0, ph = 0;          // ring position and its phase bit, advanced incrementally (no division per slab)
             long long w_prod = 0;
             for (uint32_t t = 0; t < n_tiles; t++) {
                 const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * tile_step * BN;
-                for (uint32_t s = 0; s < p.nslab; s++, it++) {
-                    const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
+                for (uint32_t s = 0; s < p.nslab; s++, ph ^= (++stage == p.n_stages) ? 1u : 0u, stage = (stage == p.n_stages) ? 0u : stage) {
                     mbar_wait_timed(bar_empty + stage, ph ^ 1u, w_prod);
                     mbar_expect_tx(bar_full + stage, stage_slabs * SLAB_TILE);
                     for (uint32_t a = 0; a < q_slabs; a++)
@@ -164,16 +163,14 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         tc_fence_after();
         const uint32_t q_desc0 = make_smem_desc(smem_u32(s_q));   // low descriptor words; the constant high word is added by umma()
         const uint32_t x_desc0 = make_smem_desc(smem_u32(s_x));
-        uint32_t it = 0;
+        uint32_t stage = 0, ph = 0, acc = 0, aph = 0;   // ring / accumulator positions and phase bits, advanced incrementally
         long long w_full = 0, w_tempty = 0;
         const long long t_start = tc_clock();
-        for (uint32_t t = 0; t < n_tiles; t++) {
-            const uint32_t acc = t % NACC, aph = (t / NACC) & 1u;
+        for (uint32_t t = 0; t < n_tiles; t++, aph ^= (++acc == NACC) ? 1u : 0u, acc = (acc == NACC) ? 0u : acc) {
             mbar_wait_timed(bar_tempty + acc, aph ^ 1u, w_tempty);
             tc_fence_after();
             const uint32_t tmem_c = tmem_base + ACC_COL0 + acc * BN;
-            for (uint32_t s = 0; s < p.nslab; s++, it++) {
-                const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
+            for (uint32_t s = 0; s < p.nslab; s++, ph ^= (++stage == p.n_stages) ? 1u : 0u, stage = (stage == p.n_stages) ? 0u : stage) {
                 mbar_wait_timed(bar_full + stage, ph, w_full);
                 tc_fence_after();
                 const uint32_t xd = x_desc0 + (stage * stage_slabs + q_slabs) * SLAB_DESC;
@@ -292,8 +289,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         // and values cross into the common domain (shared threshold, emitted keys) through exact multiplications by cq / its inverse.
         constexpr bool WDOM = (KIND == KIND_F16X3) && (MET != MET_L2) && !DENSE;
         const float inv_cq = WDOM ? 1.0f / cq : 1.0f;
-        for (uint32_t t = 0; t < n_tiles; t++) {
-            const uint32_t acc = t % NACC, aph = (t / NACC) & 1u;
+        uint32_t acc = 0, aph = 0;               // accumulator stage and its phase bit, advanced incrementally (no division per tile)
+        for (uint32_t t = 0; t < n_tiles; t++, aph ^= (++acc == NACC) ? 1u : 0u, acc = (acc == NACC) ? 0u : acc) {
             const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * tile_step * BN;
             const uint32_t g_bits = g_next;
             const float aux_lo = aux_lo_next, aux_hi = aux_hi_next;

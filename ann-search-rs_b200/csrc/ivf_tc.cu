@@ -120,8 +120,11 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
     const uint32_t total_tasks = p.task_off[p.nlist];
 
     // role-local running counters: the smem ring and the accumulator ring keep rolling across tasks
-    uint32_t it = 0;        // K-slab counter (producer and MMA issuer advance it identically)
-    uint32_t tg = 0;        // tile counter (MMA issuer and epilogue advance it identically)
+    // ring position / accumulator stage and their phase bits: every role advances its own copies identically, slab by slab and tile
+    // by tile (incrementally: no division on the per-slab / per-tile chains)
+    uint32_t r_stage = 0, r_ph = 0, r_acc = 0, r_aph = 0;
+    auto next_slab = [&]() { if (++r_stage == p.n_stages) { r_stage = 0; r_ph ^= 1u; } };
+    auto next_tile = [&]() { if (++r_acc == NACC) { r_acc = 0; r_aph ^= 1u; } };
     uint32_t task_no = 0;   // tasks done by this CTA (parity of bar_q)
 
     // epilogue-only state
@@ -187,8 +190,8 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                         }
                     }
                     const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
-                    for (uint32_t s = 0; s < p.nslab; s++, it++) {
-                        const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
+                    for (uint32_t s = 0; s < p.nslab; s++, next_slab()) {
+                        const uint32_t stage = r_stage, ph = r_ph;
                         mbar_wait(bar_empty + stage, ph ^ 1u);
                         if (XFORM) {   // raw f32 slab; rows past the shard's end are zero filled by TMA
                             mbar_expect_tx(bar_full + stage, SLAB_TILE);
@@ -201,9 +204,7 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
                         }
                     }
                 }
-            } else {
-                it += n_tiles * p.nslab;   // keep the other lanes' copy consistent (only lane 0's is used)
-            }
+            }                              // (the other lanes of the producer warp never use their ring position)
             __syncwarp();
         } else if (warp == 1) {
             // ================================================================= MMA issuer (converged warp, elected issue)
@@ -211,13 +212,13 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
             tc_fence_after();
             const uint32_t x_desc0 = make_smem_desc(smem_u32(s_x));   // low descriptor word
             const uint32_t qlo_desc0 = make_smem_desc(smem_u32(s_qlo));
-            for (uint32_t t = 0; t < n_tiles; t++, tg++) {
-                const uint32_t acc = tg % NACC, aph = (tg / NACC) & 1u;
+            for (uint32_t t = 0; t < n_tiles; t++, next_tile()) {
+                const uint32_t acc = r_acc, aph = r_aph;
                 mbar_wait_timed(bar_tempty + acc, aph ^ 1u, c_wtempty);
                 tc_fence_after();
                 const uint32_t tmem_c = tmem_base + ACC_COL0 + acc * BN;
-                for (uint32_t s = 0; s < p.nslab; s++, it++) {
-                    const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
+                for (uint32_t s = 0; s < p.nslab; s++, next_slab()) {
+                    const uint32_t stage = r_stage, ph = r_ph;
                     mbar_wait_timed((XFORM ? bar_xf : bar_full) + stage, ph, c_wdata);
                     tc_fence_after();
                     const uint32_t xd = x_desc0 + stage * NB * SLAB_DESC;
@@ -253,8 +254,8 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
             // ================================================================= transform (2 warps): slab -> tf32 lo tile (hi = the raw slab)
             const uint32_t xt = threadIdx.x - 2 * 32;
             for (uint32_t t = 0; t < n_tiles; t++) {
-                for (uint32_t s = 0; s < p.nslab; s++, it++) {
-                    const uint32_t stage = it % p.n_stages, ph = (it / p.n_stages) & 1u;
+                for (uint32_t s = 0; s < p.nslab; s++, next_slab()) {
+                    const uint32_t stage = r_stage, ph = r_ph;
                     mbar_wait(bar_full + stage, ph);
                     uint8_t* raw = s_x + static_cast<size_t>(stage) * NB * SLAB_TILE;
                     // elementwise, so the slab's swizzled layout carries over: thread i owns 16-byte chunks i, i + 64, ...
@@ -382,8 +383,8 @@ __global__ void __launch_bounds__(ivf_tc_threads<KIND>(), 1) ivf_tc_kernel(const
             float aux_lo_next = 0.f, aux_hi_next = 0.f, rx_lo_next = 1.f, rx_hi_next = 1.f;
             if (n_tiles > 0) load_aux(0, aux_lo_next, aux_hi_next);
             if (RX && n_tiles > 0) { rx_lo_next = __ldg(rx_half); rx_hi_next = __ldg(rx_half + 32); }
-            for (uint32_t t = 0; t < n_tiles; t++, tg++) {
-                const uint32_t acc = tg % NACC, aph = (tg / NACC) & 1u;
+            for (uint32_t t = 0; t < n_tiles; t++, next_tile()) {
+                const uint32_t acc = r_acc, aph = r_aph;
                 const uint32_t row0 = static_cast<uint32_t>(r_begin) + t * BN;
                 const uint32_t g_bits = g_next;
                 const float aux_lo = aux_lo_next, aux_hi = aux_hi_next;
